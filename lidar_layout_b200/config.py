@@ -1,0 +1,160 @@
+"""Configuration for the B200 LiDM sampling path.
+
+Parsed from the reference's own YAML format (`target:` + `params:`), e.g.
+`models/lidm/kitti/uncond/config.yaml` (reference), so the drop-in is constructed from the same
+file a reference user already has (SURVEY.md section 8(b) "Construction").
+"""
+from __future__ import annotations
+
+import dataclasses
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+
+@dataclass
+class UNetConfig:
+    """Mirror of UNetModel.__init__ arguments (reference lidm/modules/diffusion/openaimodel.py:445-470)."""
+    image_size: Tuple[int, int] = (16, 128)
+    in_channels: int = 8
+    out_channels: int = 8
+    model_channels: int = 256
+    attention_resolutions: Tuple[int, ...] = (4, 2, 1)
+    num_res_blocks: int = 2
+    channel_mult: Tuple[int, ...] = (1, 2, 4)
+    num_head_channels: int = 32
+    num_heads: int = -1
+    lib_name: str = "lidm"
+    use_spatial_transformer: bool = False
+    context_dim: Optional[int] = None
+    use_scale_shift_norm: bool = False
+    resblock_updown: bool = False
+    conv_resample: bool = True
+    dropout: float = 0.0
+
+    @property
+    def time_embed_dim(self) -> int:
+        return self.model_channels * 4
+
+
+@dataclass
+class AEConfig:
+    """Mirror of VQModelInterface/Decoder arguments (reference lidm/models/ae/autoencoder.py:15-68,
+    lidm/modules/diffusion/model_lidm.py:315-383)."""
+    embed_dim: int = 8
+    n_embed: int = 16384
+    use_mask: bool = False
+    z_channels: int = 8
+    in_channels: int = 1
+    out_ch: int = 1
+    ch: int = 64
+    ch_mult: Tuple[int, ...] = (1, 2, 2, 4)
+    strides: Tuple[Tuple[int, int], ...] = ((1, 2), (2, 2), (2, 2))
+    num_res_blocks: int = 2
+    attn_levels: Tuple[int, ...] = ()
+    lib_name: str = "lidm"
+
+
+@dataclass
+class DatasetConfig:
+    """`data.params.dataset` block (what range2pcd / range2xyz are called with, scripts/sample.py:29-35)."""
+    size: Tuple[int, int] = (64, 1024)
+    fov: Tuple[float, float] = (3.0, -25.0)
+    depth_range: Tuple[float, float] = (1.0, 56.0)
+    depth_scale: float = 5.84
+    log_scale: bool = True
+
+
+@dataclass
+class LidmConfig:
+    timesteps: int = 1000
+    linear_start: float = 0.0015
+    linear_end: float = 0.0195
+    beta_schedule: str = "linear"
+    channels: int = 8
+    image_size: Tuple[int, int] = (16, 128)
+    scale_factor: float = 1.0
+    parameterization: str = "eps"
+    conditioning_key: Optional[str] = None
+    unet: UNetConfig = field(default_factory=UNetConfig)
+    ae: AEConfig = field(default_factory=AEConfig)
+    dataset: DatasetConfig = field(default_factory=DatasetConfig)
+
+    @property
+    def latent_shape(self) -> Tuple[int, int, int]:
+        return (self.channels, self.image_size[0], self.image_size[1])
+
+
+def _tup(x):
+    if isinstance(x, (list, tuple)):
+        return tuple(_tup(v) for v in x)
+    return x
+
+
+def _pick(cls, params: dict):
+    names = {f.name for f in dataclasses.fields(cls)}
+    return {k: _tup(v) for k, v in params.items() if k in names}
+
+
+def from_reference_dict(cfg: dict) -> LidmConfig:
+    """Build a LidmConfig from a parsed reference YAML (dict with `model:` and optional `data:`)."""
+    model = cfg["model"]
+    target = model.get("target", "")
+    if not target.endswith("LatentDiffusion"):
+        raise ValueError(f"unsupported model target {target!r}: only LatentDiffusion is on the B200 path")
+    p = model["params"]
+    unet_p = p["unet_config"]["params"]
+    if not p["unet_config"]["target"].endswith("openaimodel.UNetModel"):
+        raise ValueError("unsupported unet target " + p["unet_config"]["target"])
+    unet = UNetConfig(**_pick(UNetConfig, unet_p))
+    fs = p["first_stage_config"]
+    if not fs["target"].endswith("VQModelInterface"):
+        raise ValueError("unsupported first stage target " + fs["target"])
+    fsp = fs["params"]
+    ae_kw = _pick(AEConfig, fsp)
+    ae_kw.update(_pick(AEConfig, fsp["ddconfig"]))
+    ae = AEConfig(**ae_kw)
+    cond = p.get("cond_stage_config", "__is_unconditional__")
+    conditioning_key = p.get("conditioning_key", None)
+    if cond == "__is_unconditional__":
+        conditioning_key = None
+    elif conditioning_key is None:
+        conditioning_key = "concat" if p.get("concat_mode", True) else "crossattn"
+    kw = dict(
+        timesteps=p.get("timesteps", 1000),
+        linear_start=p.get("linear_start", 1e-4),
+        linear_end=p.get("linear_end", 2e-2),
+        beta_schedule=p.get("beta_schedule", "linear"),
+        channels=p.get("channels", 3),
+        image_size=_tup(p.get("image_size", (256, 256))),
+        scale_factor=p.get("scale_factor", 1.0),
+        parameterization=p.get("parameterization", "eps"),
+        conditioning_key=conditioning_key,
+        unet=unet, ae=ae,
+    )
+    ds = DatasetConfig()
+    try:
+        ds = DatasetConfig(**_pick(DatasetConfig, cfg["data"]["params"]["dataset"]))
+    except (KeyError, TypeError):
+        pass
+    return LidmConfig(dataset=ds, **kw)
+
+
+def from_yaml(path: str) -> LidmConfig:
+    import yaml
+    with open(path) as f:
+        return from_reference_dict(yaml.safe_load(f))
+
+
+def kitti_uncond() -> LidmConfig:
+    """The released unconditional KITTI-360 LiDM config (reference models/lidm/kitti/uncond/config.yaml)."""
+    return LidmConfig()
+
+
+def tiny(image_size=(8, 64), model_channels=64, channel_mult=(1, 2), n_embed=512) -> LidmConfig:
+    """A small same-topology config for fast tests (same op types, fewer channels/levels)."""
+    unet = UNetConfig(image_size=image_size, model_channels=model_channels, channel_mult=channel_mult,
+                      attention_resolutions=(2, 1), num_res_blocks=1, num_head_channels=32)
+    ae = AEConfig(n_embed=n_embed, ch=64, ch_mult=(1, 2, 2), strides=((1, 2), (2, 2)), num_res_blocks=1)
+    H, W = image_size
+    return LidmConfig(timesteps=1000, image_size=image_size, unet=unet, ae=ae,
+                      dataset=DatasetConfig(size=(H * 2, W * 4)))

@@ -1,0 +1,233 @@
+"""State-dict key/shape specification of the reference LiDM and a seeded synthetic state-dict.
+
+Checkpoints are not available offline, so tests/bench use random-init weights.  The reference's own
+random init is degenerate for parity testing (34 zero-init tensors make
+eps == 0, the U(+-1/16384) codebook makes the quantised decode insensitive to z), therefore this
+module generates a *platform-independent* (numpy PCG64) state-dict in the reference's own key scheme
+in which every tensor is non-degenerate.  `oracle/make_golden.py` loads it with
+`load_state_dict(strict=True)` into the real reference modules, which pins names and shapes.
+
+Key scheme (reference): `model.diffusion_model.*` (lidm/models/diffusion/ddpm.py:91, 2306-2311),
+`first_stage_model.{decoder,quantize.embedding,post_quant_conv}.*` (lidm/models/ae/autoencoder.py:42-50).
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, Tuple
+
+import numpy as np
+
+from .config import AEConfig, LidmConfig, UNetConfig
+
+UNET_PREFIX = "model.diffusion_model."
+AE_PREFIX = "first_stage_model."
+
+
+def _conv(spec, name, cout, cin, kh, kw, zero_init=False):
+    spec[name + ".weight"] = ((cout, cin, kh, kw), "conv_zero" if zero_init else "conv")
+    spec[name + ".bias"] = ((cout,), "bias")
+
+
+def _conv1d(spec, name, cout, cin, zero_init=False):
+    spec[name + ".weight"] = ((cout, cin, 1), "conv_zero" if zero_init else "conv")
+    spec[name + ".bias"] = ((cout,), "bias")
+
+
+def _linear(spec, name, cout, cin):
+    spec[name + ".weight"] = ((cout, cin), "conv")
+    spec[name + ".bias"] = ((cout,), "bias")
+
+
+def _norm(spec, name, c):
+    spec[name + ".weight"] = ((c,), "gamma")
+    spec[name + ".bias"] = ((c,), "beta")
+
+
+def unet_blocks(cfg: UNetConfig):
+    """Walk the U-Net topology exactly like UNetModel.__init__ (reference openaimodel.py:509-687).
+
+    Returns (input_blocks, middle, output_blocks, final_ch) where every block is a list of layer tuples:
+      ("conv", cin, cout)              3x3 circular conv (input_blocks.0)
+      ("res", cin, cout)               ResBlock
+      ("attn", ch, heads)              AttentionBlock
+      ("down", ch)                     Downsample (conv 3x3 stride 2)
+      ("up", ch)                       Upsample (nearest x2 + conv 3x3)
+    """
+    if cfg.use_spatial_transformer or cfg.use_scale_shift_norm or cfg.resblock_updown:
+        raise NotImplementedError("only the unconditional AttentionBlock U-Net is on the B200 path (round 1)")
+    mc = cfg.model_channels
+    inputs = [[("conv", cfg.in_channels, mc)]]
+    chans = [mc]
+    ch, ds = mc, 1
+    for level, mult in enumerate(cfg.channel_mult):
+        for _ in range(cfg.num_res_blocks):
+            layers = [("res", ch, mult * mc)]
+            ch = mult * mc
+            if ds in cfg.attention_resolutions:
+                layers.append(("attn", ch, ch // cfg.num_head_channels))
+            inputs.append(layers)
+            chans.append(ch)
+        if level != len(cfg.channel_mult) - 1:
+            inputs.append([("down", ch)])
+            chans.append(ch)
+            ds *= 2
+    middle = [("res", ch, ch), ("attn", ch, ch // cfg.num_head_channels), ("res", ch, ch)]
+    outputs = []
+    for level, mult in list(enumerate(cfg.channel_mult))[::-1]:
+        for i in range(cfg.num_res_blocks + 1):
+            ich = chans.pop()
+            layers = [("res", ch + ich, mc * mult)]
+            ch = mc * mult
+            if ds in cfg.attention_resolutions:
+                layers.append(("attn", ch, ch // cfg.num_head_channels))
+            if level and i == cfg.num_res_blocks:
+                layers.append(("up", ch))
+                ds //= 2
+            outputs.append(layers)
+    return inputs, middle, outputs, ch
+
+
+def _block_spec(spec, prefix, layers, ted):
+    for j, layer in enumerate(layers):
+        p = f"{prefix}.{j}"
+        kind = layer[0]
+        if kind == "conv":
+            _conv(spec, p, layer[2], layer[1], 3, 3)
+        elif kind == "res":
+            _, cin, cout = layer
+            _norm(spec, p + ".in_layers.0", cin)
+            _conv(spec, p + ".in_layers.2", cout, cin, 3, 3)
+            _linear(spec, p + ".emb_layers.1", cout, ted)
+            _norm(spec, p + ".out_layers.0", cout)
+            _conv(spec, p + ".out_layers.3", cout, cout, 3, 3, zero_init=True)
+            if cin != cout:
+                _conv(spec, p + ".skip_connection", cout, cin, 1, 1)
+        elif kind == "attn":
+            ch = layer[1]
+            _norm(spec, p + ".norm", ch)
+            _conv1d(spec, p + ".qkv", 3 * ch, ch)
+            _conv1d(spec, p + ".proj_out", ch, ch, zero_init=True)
+        elif kind == "down":
+            _conv(spec, p + ".op", layer[1], layer[1], 3, 3)
+        elif kind == "up":
+            _conv(spec, p + ".conv", layer[1], layer[1], 3, 3)
+        else:  # pragma: no cover
+            raise ValueError(kind)
+
+
+def unet_param_spec(cfg: UNetConfig, prefix: str = UNET_PREFIX) -> "OrderedDict[str, Tuple[tuple, str]]":
+    spec: OrderedDict = OrderedDict()
+    mc, ted = cfg.model_channels, cfg.time_embed_dim
+    _linear(spec, prefix + "time_embed.0", ted, mc)
+    _linear(spec, prefix + "time_embed.2", ted, ted)
+    inputs, middle, outputs, ch = unet_blocks(cfg)
+    for i, layers in enumerate(inputs):
+        _block_spec(spec, f"{prefix}input_blocks.{i}", layers, ted)
+    _block_spec(spec, f"{prefix}middle_block", middle, ted)
+    for i, layers in enumerate(outputs):
+        _block_spec(spec, f"{prefix}output_blocks.{i}", layers, ted)
+    _norm(spec, prefix + "out.0", ch)
+    _conv(spec, prefix + "out.2", cfg.out_channels, mc, 3, 3, zero_init=True)
+    return spec
+
+
+def decoder_levels(cfg: AEConfig):
+    """Decoder topology (reference model_lidm.py:315-383): list over i_level (reversed order of execution)
+    of dicts {blocks:[(cin,cout)], kernel:(kh,kw), stride:None|(sh,sw)}; plus block_in at the lowest res."""
+    stride2kernel = {(2, 2): (3, 3), (1, 2): (1, 4)}
+    nres = len(cfg.ch_mult)
+    block_in = cfg.ch * cfg.ch_mult[nres - 1]
+    top = block_in
+    levels = {}
+    for i_level in reversed(range(nres)):
+        stride = tuple(cfg.strides[i_level - 1]) if i_level > 0 else None
+        kernel = stride2kernel[stride] if stride is not None else (1, 4)
+        block_out = cfg.ch * cfg.ch_mult[i_level]
+        blocks = []
+        for _ in range(cfg.num_res_blocks + 1):
+            blocks.append((block_in, block_out))
+            block_in = block_out
+        levels[i_level] = dict(blocks=blocks, kernel=kernel, stride=stride, ch=block_in)
+    return top, levels, block_in
+
+
+def _resnet_spec(spec, p, cin, cout, k):
+    _norm(spec, p + ".norm1", cin)
+    _conv(spec, p + ".conv1", cout, cin, k[0], k[1])
+    _norm(spec, p + ".norm2", cout)
+    _conv(spec, p + ".conv2", cout, cout, k[0], k[1])
+    if cin != cout:
+        _conv(spec, p + ".nin_shortcut", cout, cin, 1, 1)
+
+
+UPSAMPLE_STRIDE2KERNEL = {(1, 2): (1, 5), (1, 4): (1, 7), (2, 1): (5, 1), (2, 2): (3, 3)}
+
+
+def ae_param_spec(cfg: AEConfig, prefix: str = AE_PREFIX) -> "OrderedDict[str, Tuple[tuple, str]]":
+    """Decode-side tensors of VQModelInterface (encoder tensors are not on the path)."""
+    if cfg.attn_levels:
+        raise NotImplementedError("decoder level attention is not used by the named configs")
+    spec: OrderedDict = OrderedDict()
+    spec[prefix + "quantize.embedding.weight"] = ((cfg.n_embed, cfg.embed_dim), "codebook")
+    _conv(spec, prefix + "post_quant_conv", cfg.z_channels, cfg.embed_dim, 1, 1)
+    d = prefix + "decoder."
+    top, levels, last = decoder_levels(cfg)
+    _conv(spec, d + "conv_in", top, cfg.z_channels, 3, 3)
+    _resnet_spec(spec, d + "mid.block_1", top, top, (3, 3))
+    _norm(spec, d + "mid.attn_1.norm", top)
+    for n in ("q", "k", "v", "proj_out"):
+        _conv(spec, d + f"mid.attn_1.{n}", top, top, 1, 1)
+    _resnet_spec(spec, d + "mid.block_2", top, top, (3, 3))
+    for i_level in reversed(range(len(cfg.ch_mult))):
+        lv = levels[i_level]
+        for i_block, (cin, cout) in enumerate(lv["blocks"]):
+            _resnet_spec(spec, d + f"up.{i_level}.block.{i_block}", cin, cout, lv["kernel"])
+        if lv["stride"] is not None:
+            k = UPSAMPLE_STRIDE2KERNEL[lv["stride"]]
+            _conv(spec, d + f"up.{i_level}.upsample.conv", lv["ch"], lv["ch"], k[0], k[1])
+    _norm(spec, d + "norm_out", last)
+    _conv(spec, d + "conv_out", cfg.out_ch, last, 1, 4)
+    return spec
+
+
+def param_spec(cfg: LidmConfig):
+    spec = unet_param_spec(cfg.unet)
+    spec.update(ae_param_spec(cfg.ae))
+    return spec
+
+
+def random_state_dict(cfg: LidmConfig, seed: int = 0, zero_init_scale: float = 1.0,
+                      codebook_std: float = 1.0, as_torch: bool = True) -> Dict[str, "np.ndarray"]:
+    """Seeded, platform-independent synthetic weights in the reference key scheme.
+
+    conv/linear: U(-b, b), b = 1/sqrt(fan_in)   (PyTorch default init distribution)
+    conv_zero  : same distribution x zero_init_scale (the reference zero-inits these; see module docstring)
+    bias       : U(-0.05, 0.05)
+    gamma/beta : 1 + 0.1 N(0,1) / 0.1 N(0,1)
+    codebook   : N(0, codebook_std^2)  (latent scale)
+    """
+    rng = np.random.Generator(np.random.PCG64(seed))
+    out = OrderedDict()
+    for name, (shape, kind) in param_spec(cfg).items():
+        n = int(np.prod(shape))
+        if kind in ("conv", "conv_zero"):
+            fan_in = int(np.prod(shape[1:]))
+            b = 1.0 / np.sqrt(fan_in)
+            a = (rng.random(n, dtype=np.float32) * 2.0 - 1.0) * np.float32(b)
+            if kind == "conv_zero":
+                a = a * np.float32(zero_init_scale)
+        elif kind == "bias":
+            a = (rng.random(n, dtype=np.float32) * 2.0 - 1.0) * np.float32(0.05)
+        elif kind == "gamma":
+            a = 1.0 + 0.1 * rng.standard_normal(n, dtype=np.float32)
+        elif kind == "beta":
+            a = 0.1 * rng.standard_normal(n, dtype=np.float32)
+        elif kind == "codebook":
+            a = np.float32(codebook_std) * rng.standard_normal(n, dtype=np.float32)
+        else:  # pragma: no cover
+            raise ValueError(kind)
+        out[name] = np.ascontiguousarray(a.astype(np.float32).reshape(shape))
+    if as_torch:
+        import torch
+        return OrderedDict((k, torch.from_numpy(v)) for k, v in out.items())
+    return out

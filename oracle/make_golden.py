@@ -1,0 +1,201 @@
+"""Generate tests/golden/*.npz by executing the UNMODIFIED reference modules (this container only).
+
+    python -m oracle.make_golden            # writes tests/golden/{kitti_uncond,tiny}.npz
+
+The synthetic state-dict (lidar_layout_b200.weights.random_state_dict, numpy PCG64 => platform
+independent) is loaded with strict key/shape checking into the reference's LatentDiffusion built from
+the reference's own YAML; inputs come from the same PCG64 family; outputs are what the reference
+computes on CPU in fp32.  The fixtures are small (latents, one decoded image, schedule tables).
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from lidar_layout_b200 import config as cfgmod            # noqa: E402
+from lidar_layout_b200.weights import param_spec, random_state_dict  # noqa: E402
+from oracle import ref_shim                               # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+WEIGHT_SEED = 0
+INPUT_SEED = 1000
+
+
+def inputs_for(cfg, B, n_noise, seed=INPUT_SEED):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    C, H, W = cfg.latent_shape
+    x_T = rng.standard_normal((B, C, H, W), dtype=np.float32)
+    noise = rng.standard_normal((n_noise, B, C, H, W), dtype=np.float32)
+    z = rng.standard_normal((B, C, H, W), dtype=np.float32)
+    return x_T, noise, z
+
+
+def sd_digest(sd):
+    h = hashlib.sha256()
+    for k in sorted(sd):
+        h.update(k.encode())
+        h.update(np.ascontiguousarray(sd[k].numpy()).tobytes()[:4096])
+    return h.hexdigest()
+
+
+def build_reference(cfg, yaml_dict):
+    """Instantiate reference LatentDiffusion from a reference-format config dict."""
+    ref_shim.install()
+    from lidm.utils.misc_utils import instantiate_from_config
+    y = ref_shim.to_attrdict(yaml_dict)
+    y.model.params.first_stage_config.params.pop("ckpt_path", None)
+    y.model.params["use_ema"] = False
+    model = instantiate_from_config(y.model)
+    model.eval()
+    return model
+
+
+def load_synthetic(model, cfg, seed=WEIGHT_SEED):
+    sd = random_state_dict(cfg, seed)
+    ref_sd = model.state_dict()
+    # every synthetic key must exist with the same shape in the reference
+    for k, v in sd.items():
+        assert k in ref_sd, f"synthetic key {k} not in reference state_dict"
+        assert tuple(ref_sd[k].shape) == tuple(v.shape), (k, ref_sd[k].shape, v.shape)
+    # every reference tensor of the U-Net / decode side must be covered
+    covered = set(sd)
+    for k in ref_sd:
+        if k.startswith("model.diffusion_model.") or k.startswith("first_stage_model.decoder.") \
+                or k.startswith("first_stage_model.post_quant_conv.") or k.startswith("first_stage_model.quantize."):
+            assert k in covered, f"reference key {k} missing from synthetic spec"
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    return sd
+
+
+def tiny_yaml(cfg):
+    u, a = cfg.unet, cfg.ae
+    return {"model": {"target": "lidm.models.diffusion.ddpm.LatentDiffusion", "params": {
+        "linear_start": cfg.linear_start, "linear_end": cfg.linear_end, "num_timesteps_cond": 1,
+        "log_every_t": 200, "timesteps": cfg.timesteps, "image_size": list(cfg.image_size),
+        "channels": cfg.channels, "first_stage_key": "image",
+        "unet_config": {"target": "lidm.modules.diffusion.openaimodel.UNetModel", "params": {
+            "image_size": list(u.image_size), "in_channels": u.in_channels, "out_channels": u.out_channels,
+            "model_channels": u.model_channels, "attention_resolutions": list(u.attention_resolutions),
+            "num_res_blocks": u.num_res_blocks, "channel_mult": list(u.channel_mult),
+            "num_head_channels": u.num_head_channels, "lib_name": "lidm"}},
+        "first_stage_config": {"target": "lidm.models.autoencoder.VQModelInterface", "params": {
+            "embed_dim": a.embed_dim, "n_embed": a.n_embed, "lib_name": "lidm", "use_mask": a.use_mask,
+            "ddconfig": {"double_z": False, "z_channels": a.z_channels, "in_channels": a.in_channels,
+                         "out_ch": a.out_ch, "ch": a.ch, "ch_mult": list(a.ch_mult),
+                         "strides": [list(s) for s in a.strides], "num_res_blocks": a.num_res_blocks,
+                         "attn_levels": [], "dropout": 0.0},
+            "lossconfig": {"target": "torch.nn.Identity"}}},
+        "cond_stage_config": "__is_unconditional__"}}}
+
+
+@torch.no_grad()
+def run_reference(model, cfg, B, S_short, out):
+    """Execute the reference API on the synthetic inputs and collect outputs into `out`."""
+    from lidm.models.diffusion import ddim as ref_ddim
+    from lidm.utils import lidar_utils as ref_lu
+    x_T, noise, z = inputs_for(cfg, B, S_short + 2)
+    x_T_t, z_t = torch.from_numpy(x_T), torch.from_numpy(z)
+    shape = cfg.latent_shape
+
+    # (1) one U-Net evaluation through the reference's own hook (apply_model), two timesteps
+    for t_val in (501, 21):
+        t = torch.full((B,), t_val, dtype=torch.long)
+        out[f"eps_t{t_val}"] = model.apply_model(x_T_t, t, None).numpy()
+
+    # (2) DDIM schedules as the sampler itself builds them
+    sampler = ref_ddim.DDIMSampler(model)
+    for S, eta in ((50, 0.0), (50, 1.0), (S_short, 0.0), (S_short, 1.0)):
+        sampler.make_schedule(ddim_num_steps=S, ddim_eta=eta, verbose=False)
+        n = len(sampler.ddim_timesteps)
+        tab = np.zeros((n, 4), dtype=np.float32)
+        for i in range(n):
+            tab[i, 0] = torch.full((1,), sampler.ddim_alphas[i]).item()
+            tab[i, 1] = torch.full((1,), sampler.ddim_alphas_prev[i]).item()
+            tab[i, 2] = torch.full((1,), sampler.ddim_sigmas[i]).item()
+            tab[i, 3] = torch.full((1,), sampler.ddim_sqrt_one_minus_alphas[i]).item()
+        out[f"ddim_S{S}_eta{int(eta)}_timesteps"] = np.asarray(sampler.ddim_timesteps, dtype=np.int64)
+        out[f"ddim_S{S}_eta{int(eta)}_table"] = tab
+
+    # (3) short free-running DDIM, eta=0, with a spy on apply_model (teacher-forcing data)
+    rec = []
+    orig_apply = model.apply_model
+
+    def spy(x, t, c, *a, **k):
+        e = orig_apply(x, t, c, *a, **k)
+        rec.append((x.clone(), t.clone(), e.clone()))
+        return e
+
+    model.apply_model = spy
+    samples, inter = sampler.sample(S_short, batch_size=B, shape=shape, eta=0.0, x_T=x_T_t.clone(), verbose=False)
+    out["ddim_eta0_final"] = samples.numpy()
+    out["ddim_eta0_xt"] = np.stack([r[0].numpy() for r in rec])
+    out["ddim_eta0_t"] = np.stack([r[1].numpy() for r in rec])
+    out["ddim_eta0_eps"] = np.stack([r[2].numpy() for r in rec])
+
+    # (4) eta=1 with injected noise (ddim.py:202 draws noise_like once per step)
+    rec.clear()
+    it = iter(list(noise))
+    orig_noise_like = ref_ddim.noise_like
+    ref_ddim.noise_like = lambda shape_, device, repeat=False: torch.from_numpy(next(it))
+    try:
+        samples1, _ = sampler.sample(S_short, batch_size=B, shape=shape, eta=1.0, x_T=x_T_t.clone(), verbose=False)
+    finally:
+        ref_ddim.noise_like = orig_noise_like
+        model.apply_model = orig_apply
+    out["ddim_eta1_final"] = samples1.numpy()
+
+    # (5) first stage decode, quantised and not; VQ indices through the quantiser itself
+    out["decode_q"] = model.decode_first_stage(z_t).numpy()
+    out["decode_nq"] = model.decode_first_stage(z_t, force_not_quantize=True).numpy()
+    _, _, (_, _, idx) = model.first_stage_model.quantize(z_t)
+    out["vq_idx"] = idx.numpy().astype(np.int32)
+
+    # (6) back-projection of the decoded image exactly as scripts/sample.py:29-35 does
+    ds = dict(fov=list(cfg.dataset.fov), depth_range=list(cfg.dataset.depth_range),
+              depth_scale=cfg.dataset.depth_scale, log_scale=cfg.dataset.log_scale)
+    # synthetic range image with a realistic spread (decoded random-init images sit near 0)
+    rng = np.random.Generator(np.random.PCG64(INPUT_SEED + 1))
+    H, W = out["decode_q"].shape[-2:]
+    img = np.clip(rng.standard_normal((H, W), dtype=np.float32) * 0.6, -1.2, 1.2).astype(np.float32)
+    out["bp_img"] = img
+    unit = (np.clip(img, -1.0, 1.0) + 1.0) / 2.0
+    pcd, _, _ = ref_lu.range2pcd(unit, **ds)
+    out["bp_pcd"] = pcd
+    out["bp_xyz"] = ref_lu.range2xyz(unit, **ds)
+
+
+def make(name, cfg, yaml_dict, B, S_short):
+    model = build_reference(cfg, yaml_dict)
+    sd = load_synthetic(model, cfg)
+    out = {"weights_digest": np.frombuffer(sd_digest(sd).encode(), dtype=np.uint8),
+           "weight_seed": np.int64(WEIGHT_SEED), "input_seed": np.int64(INPUT_SEED),
+           "B": np.int64(B), "S_short": np.int64(S_short)}
+    run_reference(model, cfg, B, S_short, out)
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB; keys={sorted(out)}")
+
+
+def main():
+    torch.set_num_threads(os.cpu_count())
+    torch.manual_seed(0)
+    import yaml
+    tiny = cfgmod.tiny()
+    make("tiny", tiny, tiny_yaml(tiny), B=2, S_short=4)
+    with open(os.path.join(ref_shim.REFERENCE_ROOT, "models/lidm/kitti/uncond/config.yaml")) as f:
+        y = yaml.safe_load(f)
+    full = cfgmod.from_reference_dict(y)
+    make("kitti_uncond", full, y, B=1, S_short=4)
+
+
+if __name__ == "__main__":
+    main()
