@@ -1,0 +1,128 @@
+/* lidm_b200.h — C ABI of the B200-native LiDM sampling path (liblidm_b200.so).
+ *
+ * The reference (AlanLiangC/LiDAR-Layout) has no FFI layer: the path sits behind a plain Python object API.
+ * Each entry point below names the reference interface (file:line under the reference tree) whose GPU work it
+ * replaces; the Python mirror in lidar_layout_b200/ keeps the reference signatures and calls these through ctypes
+ * (see INTEGRATION.md for the binding a reference maintainer would add).
+ *
+ * Conventions: extern "C"; returns 0 on success, a negative code on failure (never throws); message via
+ * lidm_last_error(); plain pointers and sizes only.  Unless stated otherwise pointers are DEVICE pointers to
+ * contiguous fp32 NCHW tensors exactly as PyTorch lays them out, borrowed only for the duration of the call; all
+ * work is enqueued on the caller's `stream` (a cudaStream_t passed as void*) and is asynchronous to the host.
+ * A handle owns packed weights and workspaces for one device and is not thread-safe.  There is no CPU fallback.
+ */
+#ifndef LIDM_B200_H_
+#define LIDM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LIDM_OK 0
+#define LIDM_ERR_INVALID (-1)   /* bad argument / unsupported configuration */
+#define LIDM_ERR_CUDA (-2)      /* CUDA runtime / driver failure */
+#define LIDM_ERR_STATE (-3)     /* call order violated (e.g. forward before finalize) or missing weight */
+
+#define LIDM_MAX_LEVELS 8
+
+typedef struct lidm_handle lidm_handle;
+
+/* Mirrors the YAML blocks the reference instantiates from (models/lidm/kitti/uncond/config.yaml):
+ * model.params.unet_config.params (UNetModel.__init__, lidm/modules/diffusion/openaimodel.py:445-470) and
+ * model.params.first_stage_config.params (+ddconfig) (VQModel.__init__, lidm/models/ae/autoencoder.py:15-50;
+ * Decoder.__init__, lidm/modules/diffusion/model_lidm.py:315-383). */
+typedef struct lidm_config {
+  /* U-Net */
+  int32_t in_channels, out_channels, model_channels, num_res_blocks, num_head_channels;
+  int32_t n_channel_mult;
+  int32_t channel_mult[LIDM_MAX_LEVELS];
+  int32_t n_attention_resolutions;
+  int32_t attention_resolutions[LIDM_MAX_LEVELS];
+  int32_t latent_h, latent_w;
+  /* first stage (decode side) */
+  int32_t embed_dim, n_embed, z_channels, ae_ch, ae_out_ch, ae_num_res_blocks, ae_use_mask;
+  int32_t ae_n_ch_mult;
+  int32_t ae_ch_mult[LIDM_MAX_LEVELS];
+  int32_t ae_strides[LIDM_MAX_LEVELS][2]; /* ae_n_ch_mult-1 entries (h, w) */
+  float scale_factor;                     /* LatentDiffusion.scale_factor (ddpm.py:438,725) */
+} lidm_config;
+
+/* Last error message for `h` (or, with h == NULL, for the calling thread's last failed lidm_create / stateless call). */
+const char* lidm_last_error(const lidm_handle* h);
+
+/* instantiate_from_config(config.model) (lidm/utils/misc_utils.py:118) for the supported topology. */
+int lidm_create(const lidm_config* cfg, lidm_handle** out);
+void lidm_destroy(lidm_handle* h);
+
+/* model.load_state_dict(sd, strict=False) (scripts/sample.py:268-273): one call per state-dict tensor, keys in the
+ * reference scheme (`model.diffusion_model.*`, `model_ema.*`, `first_stage_model.*`).  `data` is fp32, HOST or
+ * DEVICE memory; it is copied before the call returns.  Unknown keys are ignored (strict=False). */
+int lidm_load_weight(lidm_handle* h, const char* name, const float* data, int32_t ndim, const int64_t* shape);
+
+/* Packs weights into kernel layouts (bf16, [Cout][tap][Cin]); use_ema != 0 selects the LitEma shadow
+ * (`model_ema.<name without dots>`, lidm/modules/ema.py:16-21) where present — the one-time equivalent of
+ * DDPM.ema_scope (ddpm.py:174-187).  Fails with LIDM_ERR_STATE and names the first missing tensor. */
+int lidm_finalize_weights(lidm_handle* h, int32_t use_ema);
+
+/* LatentDiffusion.apply_model -> DiffusionWrapper.forward -> UNetModel.forward
+ * (ddpm.py:900, 2313; openaimodel.py:719-751), unconditional.  x: (B,C,H,W) fp32, t: (B,) int64, eps_out: (B,C,H,W). */
+int lidm_unet_forward(lidm_handle* h, const float* x, const int64_t* t, float* eps_out, int32_t B, void* stream);
+
+/* DDIMSampler.p_sample_ddim update arithmetic (lidm/models/diffusion/ddim.py:191-206), stateless:
+ * pred_x0 = (x - sqrt(1-a_t) eps)/sqrt(a_t); x_prev = sqrt(a_prev) pred_x0 + sqrt(1-a_prev-sigma^2) eps + sigma noise T.
+ * noise and pred_x0 may be NULL. n = element count. Bit-exact with the reference's fp32 op order. */
+int lidm_ddim_step(const float* x, const float* eps, const float* noise, float a_t, float a_prev, float sigma_t,
+                   float sqrt_one_minus_at, float temperature, float* x_prev, float* pred_x0, int64_t n, void* stream);
+
+/* DDIMSampler.ddim_sampling loop (ddim.py:115-165), unconditional, whole loop on the device with the DDIM update
+ * fused into the U-Net's last conv epilogue.  x_inout: x_T in, x_0 estimate out, (B,C,H,W).
+ * timesteps: HOST int64[n_steps] ascending (ddim_timesteps); sched: HOST float[n_steps*4] rows
+ * {a_t, a_prev, sigma_t, sqrt_one_minus_at} indexed like the reference's `index` (the loop walks them backwards).
+ * noise: NULL (eta = 0) or DEVICE fp32 (n_steps,B,C,H,W) consumed in loop order (first row = first iteration).
+ * pred_x0_out: NULL or DEVICE (B,C,H,W) receiving the last step's pred_x0. */
+int lidm_ddim_sample(lidm_handle* h, float* x_inout, const int64_t* timesteps, const float* sched, int32_t n_steps,
+                     const float* noise, float temperature, float* pred_x0_out, int32_t B, void* stream);
+
+/* LatentDiffusion.decode_first_stage -> VQModelInterface.decode (ddpm.py:717-775, autoencoder.py:290-302):
+ * z/scale_factor -> [quantize] -> post_quant_conv -> Decoder -> [use_mask].  z: (B,C,h,w); img_out: (B,1 or out_ch,H,W)
+ * fp32; idx_out: NULL or int32 (B*h*w) codebook indices (-1 when force_not_quantize). */
+int lidm_vq_decode(lidm_handle* h, const float* z, int32_t force_not_quantize, float* img_out, int32_t* idx_out,
+                   int32_t B, void* stream);
+
+/* Output geometry of lidm_vq_decode for this config: channels, height, width of img_out. */
+int lidm_image_shape(const lidm_handle* h, int32_t* c, int32_t* hh, int32_t* ww);
+
+/* custom_to_pcd + range2xyz / range2pcd geometry (scripts/sample.py:29-35, lidm/utils/lidar_utils.py:134-204),
+ * stateless.  img: (B,H,W) fp32 in [-1,1] (clipped and mapped to [0,1] like custom_to_pcd) or, with input_is_unit != 0,
+ * already in [0,1] (the argument range2pcd/range2xyz themselves take); xyz_out: (B,3,H,W) fp32 with -1 where masked (range2xyz);
+ * mask_out: NULL or uint8 (B,H,W), 1 where depth_min < depth < depth_max (the points range2pcd keeps). */
+int lidm_backproject(const float* img, int32_t B, int32_t H, int32_t W, float fov_up_deg, float fov_down_deg,
+                     float depth_min, float depth_max, float depth_scale, int32_t log_scale, int32_t input_is_unit,
+                     float* xyz_out, uint8_t* mask_out, void* stream);
+
+/* ---- operator-level entry points (the same kernels the model uses; exposed for parity tests and reuse) ---------
+ * All tensors fp32 NCHW device pointers; conversions to the internal channels-last bf16 layout happen inside. */
+
+/* CircularConv2d.forward (lidm/modules/basic.py:52-59): circular pad (pad_l,pad_r) on W, zero pad (pad_t,pad_b) on H,
+ * conv stride `stride`.  weight: (Cout,Cin,kh,kw), bias: (Cout) or NULL, residual: NULL or (B,Cout,Ho,Wo) added. */
+int lidm_op_circular_conv2d(const float* x, int32_t B, int32_t Cin, int32_t H, int32_t W, const float* weight,
+                            const float* bias, int32_t Cout, int32_t kh, int32_t kw, int32_t pad_l, int32_t pad_r,
+                            int32_t pad_t, int32_t pad_b, int32_t stride, const float* residual, float* out,
+                            void* stream);
+
+/* GroupNorm32 (+SiLU) (lidm/modules/basic.py:339-341, openaimodel.py:205-207). */
+int lidm_op_groupnorm(const float* x, int32_t B, int32_t C, int32_t H, int32_t W, const float* gamma,
+                      const float* beta, float eps, int32_t groups, int32_t silu, float* out, void* stream);
+
+/* QKVAttentionLegacy.forward (openaimodel.py:358-374): qkv (B, heads*3*32, T) -> out (B, heads*32, T). */
+int lidm_op_qkv_attention_legacy(const float* qkv, int32_t B, int32_t heads, int32_t T, float* out, void* stream);
+
+/* Number of kernels this library has launched so far in the process (bench.py's gpu_launches). */
+int64_t lidm_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIDM_B200_H_ */

@@ -1,0 +1,223 @@
+// Fused flash-style attention for head dim 32 on tcgen05 / TMEM / TMA (sm_100a).
+//
+// Replaces QKVAttentionLegacy.forward (reference lidm/modules/diffusion/openaimodel.py:358-374): per head
+//   w = softmax_fp32((q s)^T (k s)),  a = w v,   s = ch^-1/4  (folded into the packed qkv weights),
+// without materialising the (B*heads, T, T) score tensor.  One CTA = one 128-query tile of one (sample, head):
+//   S (128x128 fp32, TMEM cols 0..127)  = Q K^T      2 x tcgen05.mma  M128 N128 K16   (operands 64B-swizzled)
+//   P = exp2(S*log2e - m) -> bf16 -> smem (128B-swizzled, K-major A operand)
+//   O_tile (128x32 fp32, TMEM cols 128..159) = P V   8 x tcgen05.mma  M128 N32  K16   (V^T tile K-major)
+// and the 4 softmax warps fold O_tile into fp32 registers with the online-softmax rescale.  K/V tiles stream
+// through a 2-stage TMA ring; two CTAs are co-resident per SM so one CTA's MMAs overlap the other's softmax.
+// Inputs: qk (B,T,2C) = [q all heads | k all heads], vt (B,C,T) — both written by the qkv GEMM epilogue.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace lidm {
+
+namespace {
+
+constexpr int D = 32;
+constexpr int BQ = 128;
+constexpr int BKV = 128;
+constexpr int KV_STAGES = 2;
+constexpr int Q_BYTES = BQ * D * 2;        // 8 KiB, rows of 64 B (SWIZZLE_64B)
+constexpr int K_BYTES = BKV * D * 2;       // 8 KiB
+constexpr int V_BYTES = D * BKV * 2;       // 8 KiB = 2 atoms of (32 rows x 128 B)
+constexpr int P_BYTES = BQ * BKV * 2;      // 32 KiB = 2 atoms of (128 rows x 128 B)
+constexpr int OFF_Q = 0;
+constexpr int OFF_K = OFF_Q + Q_BYTES;
+constexpr int OFF_V = OFF_K + KV_STAGES * K_BYTES;
+constexpr int OFF_P = OFF_V + KV_STAGES * V_BYTES;
+constexpr int OFF_BAR = OFF_P + P_BYTES;
+constexpr int SMEM_TOTAL = OFF_BAR + 256 + 1024;
+constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t O_COL = 128;
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(192)
+attention_d32_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmVT,
+                     bf16* __restrict__ out, int out_ld, int T, int C) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* kv_full = q_full + 1;
+  uint64_t* kv_empty = kv_full + KV_STAGES;
+  uint64_t* s_ready = kv_empty + KV_STAGES;
+  uint64_t* p_ready = s_ready + 1;
+  uint64_t* o_ready = p_ready + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_ready + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BQ;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int nkv = T / BKV;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmQK);
+    prefetch_tensormap(&tmVT);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    mbar_init(s_ready, 1);
+    mbar_init(p_ready, 128);
+    mbar_init(o_ready, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, Q_BYTES);
+      tma_load_3d(smem + OFF_Q, &tmQK, q_full, head * D, q0, b);
+      int s = 0; uint32_t ph = 0;
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&kv_full[s], K_BYTES + V_BYTES);
+        tma_load_3d(smem + OFF_K + s * K_BYTES, &tmQK, &kv_full[s], C + head * D, j * BKV, b);
+        tma_load_3d(smem + OFF_V + s * V_BYTES, &tmVT, &kv_full[s], j * BKV, head * D, b);
+        tma_load_3d(smem + OFF_V + s * V_BYTES + V_BYTES / 2, &tmVT, &kv_full[s], j * BKV + 64, head * D, b);
+        if (++s == KV_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV);
+      constexpr uint32_t idesc_o = make_idesc_bf16(BQ, D);
+      const uint64_t qdesc = make_kmajor_desc<64>(smem_u32(smem + OFF_Q));
+      const uint64_t pdesc = make_kmajor_desc<128>(smem_u32(smem + OFF_P));
+      mbar_wait(q_full, 0);
+      int s = 0; uint32_t ph = 0;
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(&kv_full[s], ph);
+        tcgen05_fence_after();
+        const uint64_t kdesc = make_kmajor_desc<64>(smem_u32(smem + OFF_K + s * K_BYTES));
+        umma_bf16_ss(tmem_base, qdesc, kdesc, idesc_s, 0);
+        umma_bf16_ss(tmem_base, qdesc + 2, kdesc + 2, idesc_s, 1);
+        umma_commit(s_ready);
+        mbar_wait(p_ready, j & 1);
+        tcgen05_fence_after();
+        const uint64_t vdesc = make_kmajor_desc<128>(smem_u32(smem + OFF_V + s * V_BYTES));
+#pragma unroll
+        for (int kk = 0; kk < BKV / 16; ++kk) {
+          const uint64_t pa = pdesc + (uint64_t)(((kk >> 2) * (P_BYTES / 2) + (kk & 3) * 32) >> 4);
+          const uint64_t vb = vdesc + (uint64_t)(((kk >> 2) * (V_BYTES / 2) + (kk & 3) * 32) >> 4);
+          umma_bf16_ss(tmem_base + O_COL, pa, vb, idesc_o, kk != 0);
+        }
+        umma_commit(o_ready);
+        umma_commit(&kv_empty[s]);
+        if (++s == KV_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax + output warps
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
+    constexpr float LOG2E = 1.4426950408889634f;
+    float m = -INFINITY, l = 0.f;
+    float o[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) o[i] = 0.f;
+    uint8_t* prow = smem + OFF_P + row * 128;
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(s_ready, j & 1);
+      tcgen05_fence_after();
+      float mx = m;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t raw[32];
+        tmem_ld_32x32b_x32(trow + c * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
+      }
+      const float alpha = ex2((m - mx) * LOG2E);  // m = -inf on the first tile -> 0
+      m = mx;
+      const float mb = mx * LOG2E;
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t raw[32];
+        tmem_ld_32x32b_x32(trow + c * 32, raw);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = ex2(fmaf(__uint_as_float(raw[2 * i]), LOG2E, -mb));
+          const float p1 = ex2(fmaf(__uint_as_float(raw[2 * i + 1]), LOG2E, -mb));
+          sum += p0 + p1;
+          pk[i] = pack_bf16(p0, p1);
+        }
+        // P[row][c*32 .. c*32+31] -> K-atom (c>>1), 16-byte chunks (c&1)*4 .. +3, XOR-swizzled with (row & 7)
+        uint8_t* base = prow + (c >> 1) * (P_BYTES / 2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int chunk = ((c & 1) * 4 + i) ^ (row & 7);
+          *reinterpret_cast<uint4*>(base + chunk * 16) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        }
+      }
+      l = l * alpha + sum;
+      fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tcgen05_fence_before();
+      mbar_arrive(p_ready);
+      // fold the previous accumulator while the PV MMA runs
+#pragma unroll
+      for (int i = 0; i < D; ++i) o[i] *= alpha;
+      mbar_wait(o_ready, j & 1);
+      tcgen05_fence_after();
+      {
+        uint32_t raw[32];
+        tmem_ld_32x32b_x32(trow + O_COL, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < D; ++i) o[i] += __uint_as_float(raw[i]);
+      }
+      tcgen05_fence_before();
+    }
+    const float inv = 1.f / l;
+    bf16* op = out + ((size_t)b * T + q0 + row) * out_ld + head * D;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 u;
+      u.x = pack_bf16(o[8 * i + 0] * inv, o[8 * i + 1] * inv);
+      u.y = pack_bf16(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
+      u.z = pack_bf16(o[8 * i + 4] * inv, o[8 * i + 5] * inv);
+      u.w = pack_bf16(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
+      reinterpret_cast<uint4*>(op)[i] = u;
+    }
+  }
+  __syncthreads();
+  if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+}  // namespace
+
+void launch_attention_d32(const bf16* qk, const bf16* vt, const View& out, int B, int T, int heads, cudaStream_t s) {
+  const int C = heads * D;
+  LIDM_REQUIRE(T % 128 == 0, "attention: T must be a multiple of 128");
+  LIDM_REQUIRE(out.hl == 0 && out.hr == 0 && out.H * out.W == T && out.B == B && out.C == C, "attention out view");
+  LIDM_REQUIRE(out.ld % 8 == 0, "attention out ld");
+  static bool configured = false;
+  if (!configured) {
+    LIDM_CUDA_CHECK(cudaFuncSetAttribute(attention_d32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    configured = true;
+  }
+  CUtensorMap tmQK = make_tma_3d(qk, 2 * C, T, B, (uint64_t)2 * C * 2, (uint64_t)T * 2 * C * 2, D, 128, 64);
+  CUtensorMap tmVT = make_tma_3d(vt, T, C, B, (uint64_t)T * 2, (uint64_t)C * T * 2, 64, D, 128);
+  dim3 grid(T / BQ, heads, B);
+  attention_d32_kernel<<<grid, 192, SMEM_TOTAL, s>>>(tmQK, tmVT, out.p, out.ld, T, C);
+  LIDM_CUDA_CHECK(cudaGetLastError());
+  LIDM_COUNT_LAUNCH(1);
+}
+
+}  // namespace lidm

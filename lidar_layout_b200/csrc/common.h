@@ -1,0 +1,132 @@
+// Host-side shared declarations: tensor views, error plumbing, TMA descriptor creation, kernel launchers.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <stdexcept>
+#include <string>
+
+namespace lidm {
+
+typedef __nv_bfloat16 bf16;
+
+extern std::atomic<int64_t> g_launch_count;
+#define LIDM_COUNT_LAUNCH(n) (::lidm::g_launch_count.fetch_add((n), std::memory_order_relaxed))
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define LIDM_CUDA_CHECK(expr)                                                                              \
+  do {                                                                                                     \
+    cudaError_t _e = (expr);                                                                               \
+    if (_e != cudaSuccess)                                                                                 \
+      throw ::lidm::Error(-2, std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " + __FILE__ + \
+                                  ":" + std::to_string(__LINE__));                                         \
+  } while (0)
+
+#define LIDM_REQUIRE(cond, msg)                                                                            \
+  do {                                                                                                     \
+    if (!(cond)) throw ::lidm::Error(-1, std::string("invalid argument: ") + (msg) + " [" #cond "]");      \
+  } while (0)
+
+// Channels-last bf16 activation view with materialised circular halo columns:
+// physical shape (B, H, W + hl + hr, ld) where column hl+w holds logical pixel w, the hl leftmost columns hold
+// logical pixels W-hl..W-1 and the hr rightmost hold logical pixels 0..hr-1.  `p` already includes the channel
+// offset of the view inside a wider (concatenated) buffer; `ld` is the channel stride of one pixel (elements).
+struct View {
+  bf16* p = nullptr;
+  int B = 0, H = 0, W = 0, C = 0;
+  int hl = 0, hr = 0;
+  int ld = 0;
+  int Wp() const { return W + hl + hr; }
+  size_t pix_index(int b, int h, int w) const { return ((size_t)(b * H + h) * Wp() + (w + hl)); }
+};
+
+// ---- TMA maps (cuTensorMapEncodeTiled through the runtime's driver entry point; no -lcuda link) -------
+CUtensorMap make_tma_act(const View& v, int box_c, int box_w, int box_h, int swizzle_bytes);
+CUtensorMap make_tma_3d(const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                        uint64_t stride2_bytes, uint32_t b0, uint32_t b1, int swizzle_bytes);
+
+// ---- implicit-GEMM convolution (gemm_conv.cu) ------------------------------------------------------------
+struct ConvTaps {
+  int n = 1;
+  int8_t dx[9] = {0};
+  int8_t dy[9] = {0};
+};
+
+struct GemmEpilogue {
+  const float* bias = nullptr;     // [N] fp32 or null
+  const float* rowadd = nullptr;   // per-sample additive term (timestep embedding): [B][rowadd_ld] or null
+  int rowadd_ld = 0;               // 0 => same row for every sample
+  View residual;                   // optional bf16 residual (p == null => none), same logical shape as out
+  View out;                        // bf16 NHWC output (p == null => none); halos are written when hl/hr > 0
+  // columns >= split_n go, transposed, to out_t[(b * (N - split_n) + (n - split_n)) * HW + pixel]  (V^T for attention)
+  int split_n = 1 << 30;
+  bf16* out_t = nullptr;
+  float* out_f32_nchw = nullptr;   // optional fp32 NCHW output (B, N, H, W)
+  float* out_f32_nhwc = nullptr;   // optional fp32 channels-last output (B, H, W, N) (no halo)
+  // fused DDIM update (only with out_f32_nchw semantics; eps itself is still written to out_f32_nchw if non-null)
+  const float* ddim_x = nullptr;   // x_t fp32 NCHW
+  const float* ddim_noise = nullptr;
+  float* ddim_x_prev = nullptr;
+  float* ddim_pred_x0 = nullptr;
+  const float* ddim_coef = nullptr;  // device pointer to 5 floats: a_t, a_prev, sigma_t, sqrt(1-a_t), temperature
+};
+
+// B operand: K-major bf16 rows [n_alloc][ld] (ld >= ntaps*Cin elements); batched => one matrix per sample.
+struct GemmB {
+  const bf16* p = nullptr;
+  int n_alloc = 0;          // rows available (multiple of the N tile; padding rows are zero)
+  int64_t ld = 0;           // row stride in elements (0 => ntaps*Cin)
+  int64_t batch_stride = 0; // elements between per-sample matrices (0 => shared weights)
+};
+
+// A: activation view (taps applied on the halo'd view).  N = logical output channels.
+void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wt, int N, const GemmEpilogue& ep,
+                      cudaStream_t stream);
+
+// ---- normalisation (norm.cu) -----------------------------------------------------------------------------
+void launch_groupnorm(const View& x, const View& y, const float* gamma, const float* beta, float eps, int groups,
+                      bool silu, float* partials /* workspace >= B*groups*2*GN_MAX_CHUNKS floats */, cudaStream_t s);
+constexpr int GN_MAX_CHUNKS = 64;
+
+// ---- attention (attention.cu) ----------------------------------------------------------------------------
+// qk: (B, T, 2C) bf16 [q(all heads) | k(all heads)], vt: (B, C, T) bf16, out: (B, T, C) view (channel = head*32+c)
+void launch_attention_d32(const bf16* qk, const bf16* vt, const View& out, int B, int T, int heads, cudaStream_t s);
+
+// ---- elementwise (elementwise.cu) ------------------------------------------------------------------------
+void launch_ddim_step(const float* x, const float* eps, const float* noise, const float* coef_dev, float* x_prev,
+                      float* pred_x0, int64_t n, cudaStream_t s);
+void launch_backproject(const float* img, int B, int H, int W, float fov_up_deg, float fov_down_deg, float dmin,
+                        float dmax, float depth_scale, int log_scale, int input_is_unit, float* xyz, uint8_t* mask,
+                        cudaStream_t s);
+void launch_im2col_nchw_f32(const float* x, int B, int C, int H, int W, int kh, int kw, int pl, int pt, bf16* out,
+                            int kpad, cudaStream_t s);
+void launch_im2col_nhwc(const View& x, int kh, int kw, int stride, int pl, int pt, int Ho, int Wo, bf16* out,
+                        cudaStream_t s);
+void launch_upsample_nearest2x(const View& x, const View& y, cudaStream_t s);
+void launch_upsample_bilinear(const View& x, const View& y, cudaStream_t s);
+void launch_copy_with_halo(const View& x, const View& y, cudaStream_t s);
+void launch_softmax_rows(const float* s, bf16* p, int64_t rows, int cols, cudaStream_t st);
+void launch_vq(const float* z, int B, int C, int HW, const float* codebook, const float* cb_norm, int n_embed,
+               int quantize, const float* pq_w, const float* pq_b, float scale, float* out, int32_t* idx,
+               cudaStream_t s);
+void launch_codebook_norm(const float* codebook, int n_embed, int dim, float* out, cudaStream_t s);
+void launch_time_embed(const int64_t* t_dev, int nt, int model_ch, const float* w0, const float* b0, const float* w2,
+                       const float* b2, int ted, float* tmp /* nt*ted */, float* emb_silu /* nt*ted */,
+                       cudaStream_t s);
+void launch_linear_rows(const float* x, int nt, int K, const float* w, const float* b, int N, float* out,
+                        cudaStream_t s);
+void launch_pack_conv_weight(const float* w, int cout, int cin, int kh, int kw, int n_alloc, int k_alloc,
+                             const int* row_perm, const float* row_scale_rows, float row_scale, int n_scaled_rows,
+                             bf16* out, cudaStream_t s);
+void launch_mask_select(const float* dec, int B, int HW, float* out, cudaStream_t s);
+void launch_f32_to_nhwc_bf16(const float* x, int B, int C, int HW, const View& y, cudaStream_t s);
+void launch_nhwc_bf16_to_f32_nchw(const View& x, float* y, cudaStream_t s);
+
+}  // namespace lidm

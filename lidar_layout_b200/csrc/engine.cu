@@ -1,0 +1,1247 @@
+// Host engine + C ABI (include/lidm_b200.h): weight store/packing, static activation planning, the U-Net and
+// decoder launch plans, the on-device DDIM loop.  Mirrors, for the unconditional LiDM sampling path,
+//   UNetModel.forward                 reference lidm/modules/diffusion/openaimodel.py:719-751
+//   ResBlock / AttentionBlock         openaimodel.py:256-276 / 320-326
+//   Decoder.forward, ResnetBlock, AttnBlock, Upsample   lidm/modules/diffusion/model_lidm.py:385-417,127-147,184-208,57-61
+//   VQModelInterface.decode           lidm/models/ae/autoencoder.py:290-302
+//   DDIMSampler.ddim_sampling         lidm/models/diffusion/ddim.py:115-165
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/lidm_b200.h"
+#include "common.h"
+
+namespace lidm {
+
+std::atomic<int64_t> g_launch_count{0};
+
+namespace {
+
+thread_local std::string tls_error;
+
+typedef std::function<void(cudaStream_t)> Op;
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------------------
+// Plan-time arena allocator (first fit + coalescing).  Buffers are assigned once when a plan is built; stream
+// order makes reuse after `release` safe.
+class ArenaPlanner {
+ public:
+  size_t alloc(size_t bytes) {
+    bytes = align_up(bytes, 1024);
+    for (size_t i = 0; i < free_.size(); ++i) {
+      if (free_[i].second >= bytes) {
+        const size_t off = free_[i].first;
+        if (free_[i].second == bytes) free_.erase(free_.begin() + i);
+        else { free_[i].first += bytes; free_[i].second -= bytes; }
+        return off;
+      }
+    }
+    const size_t off = top_;
+    top_ += bytes;
+    high_ = std::max(high_, top_);
+    return off;
+  }
+  void release(size_t off, size_t bytes) {
+    bytes = align_up(bytes, 1024);
+    free_.emplace_back(off, bytes);
+    std::sort(free_.begin(), free_.end());
+    for (size_t i = 0; i + 1 < free_.size();) {
+      if (free_[i].first + free_[i].second == free_[i + 1].first) {
+        free_[i].second += free_[i + 1].second;
+        free_.erase(free_.begin() + i + 1);
+      } else ++i;
+    }
+    if (!free_.empty() && free_.back().first + free_.back().second == top_) {
+      top_ = free_.back().first;
+      free_.pop_back();
+    }
+  }
+  size_t high() const { return high_; }
+
+ private:
+  std::vector<std::pair<size_t, size_t>> free_;
+  size_t top_ = 0, high_ = 0;
+};
+
+struct Buf { size_t off = 0, bytes = 0; };
+
+struct DevTensor {
+  float* p = nullptr;
+  std::vector<int64_t> shape;
+  int64_t numel = 0;
+};
+
+struct ConvW {
+  bf16* w = nullptr;
+  float* bias = nullptr;
+  int cout = 0, cin = 0, kh = 1, kw = 1;
+  int n_alloc = 0, k_alloc = 0;
+};
+struct NormW { float* gamma = nullptr; float* beta = nullptr; int C = 0; };
+struct ResW { NormW n1, n2; ConvW c1, c2, skip; bool has_skip = false; int emb_off = -1; int cin = 0, cout = 0; };
+struct AttnW { NormW n; ConvW qkv, proj; int ch = 0, heads = 0; };
+struct Layer {
+  enum Kind { CONV, RES, ATTN, DOWN, UP } kind;
+  ResW r; AttnW a; ConvW c;
+  int cin = 0, cout = 0;
+};
+struct DecLevel { std::vector<ResW> blocks; int kh = 1, kw = 4; bool has_up = false; int sh = 1, sw = 1; ConvW up; int ch = 0; };
+
+ConvTaps taps_rect(int kh, int kw, int pl, int pt) {
+  ConvTaps t;
+  t.n = kh * kw;
+  for (int ky = 0; ky < kh; ++ky)
+    for (int kx = 0; kx < kw; ++kx) { t.dy[ky * kw + kx] = (int8_t)(ky - pt); t.dx[ky * kw + kx] = (int8_t)(kx - pl); }
+  return t;
+}
+ConvTaps taps_1x1() { ConvTaps t; t.n = 1; return t; }
+
+int round_n_alloc(int cout) {
+  if (cout >= 128) return (cout + 127) / 128 * 128;
+  if (cout > 16) return (cout + 63) / 64 * 64;
+  return 16;
+}
+
+struct Plan {
+  int B = 0;
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  std::vector<Op> ops;
+  float* gn_partials = nullptr;
+  // launch-time IO (closures read these when they run)
+  const float* x = nullptr;         // U-Net input / decoder latent (fp32 NCHW)
+  float* out = nullptr;             // eps_out / img_out
+  int32_t* idx_out = nullptr;
+  int quantize = 1;
+  const float* rowadd_base = nullptr;
+  int rowadd_ld = 0;
+  const float* ddim_noise = nullptr;
+  float* ddim_x_prev = nullptr;
+  float* ddim_pred_x0 = nullptr;
+  const float* ddim_coef = nullptr;
+  ~Plan() {
+    if (arena) cudaFree(arena);
+    if (gn_partials) cudaFree(gn_partials);
+  }
+};
+
+}  // namespace
+}  // namespace lidm
+
+using namespace lidm;
+
+struct lidm_handle {
+  lidm_config cfg{};
+  std::string error;
+  bool finalized = false;
+  std::unordered_map<std::string, DevTensor> raw;     // fp32 state-dict tensors on the device
+  std::vector<void*> owned;                           // packed weight allocations
+  // U-Net
+  std::vector<std::vector<Layer>> in_blocks, out_blocks;
+  std::vector<Layer> mid_block;
+  std::vector<int> in_chans;                          // channels of hs[k]
+  NormW out_norm; ConvW out_conv;
+  float *te_w0 = nullptr, *te_b0 = nullptr, *te_w2 = nullptr, *te_b2 = nullptr;
+  float *emb_w = nullptr, *emb_b = nullptr;           // concatenated emb_layers Linear weights [emb_total][ted]
+  int emb_total = 0, ted = 0;
+  // decoder
+  float *codebook = nullptr, *cb_norm = nullptr, *pq_w = nullptr, *pq_b = nullptr;
+  ConvW dec_conv_in, dec_conv_out;
+  ResW dec_mid1, dec_mid2;
+  AttnW dec_attn;
+  std::vector<DecLevel> dec_levels;                   // indexed by i_level
+  NormW dec_norm_out;
+  int dec_top = 0, dec_last = 0, img_h = 0, img_w = 0;
+  // plans
+  std::map<int, std::unique_ptr<Plan>> unet_plans, dec_plans;
+  // time-embedding scratch
+  float *te_tmp = nullptr, *te_emb = nullptr, *emb_out = nullptr;
+  int64_t* t_dev = nullptr;
+  int te_rows = 0;
+  float* coef_dev = nullptr; int coef_rows = 0;
+  float *xa = nullptr, *xb = nullptr; size_t xbuf_elems = 0;
+
+  ~lidm_handle() {
+    for (auto& kv : raw) cudaFree(kv.second.p);
+    for (void* p : owned) cudaFree(p);
+    cudaFree(te_tmp); cudaFree(te_emb); cudaFree(emb_out); cudaFree(t_dev); cudaFree(coef_dev);
+    cudaFree(xa); cudaFree(xb);
+  }
+};
+
+namespace lidm {
+namespace {
+
+template <class T>
+T* dev_alloc(lidm_handle* h, size_t n) {
+  void* p = nullptr;
+  LIDM_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+  if (h) h->owned.push_back(p);
+  return reinterpret_cast<T*>(p);
+}
+
+// ------------------------------------------------------------------------------------------- weight lookup
+const DevTensor& find_raw(lidm_handle* h, const std::string& name, bool use_ema) {
+  if (use_ema) {
+    // LitEma buffer name: parameter name relative to DDPM.model with the dots removed (lidm/modules/ema.py:16-21)
+    const std::string pre = "model.";
+    if (name.compare(0, pre.size(), pre) == 0) {
+      std::string s = name.substr(pre.size());
+      s.erase(std::remove(s.begin(), s.end(), '.'), s.end());
+      auto it = h->raw.find("model_ema." + s);
+      if (it != h->raw.end()) return it->second;
+    }
+  }
+  auto it = h->raw.find(name);
+  if (it == h->raw.end()) throw Error(LIDM_ERR_STATE, "missing weight tensor '" + name + "'");
+  return it->second;
+}
+
+struct Packer {
+  lidm_handle* h;
+  bool ema;
+  cudaStream_t s = 0;
+
+  float* f32(const std::string& name, int64_t expect_numel) {
+    const DevTensor& t = find_raw(h, name, ema);
+    if (t.numel != expect_numel)
+      throw Error(LIDM_ERR_STATE, "weight '" + name + "' has " + std::to_string(t.numel) + " elements, expected " +
+                                      std::to_string(expect_numel));
+    float* p = dev_alloc<float>(h, (size_t)t.numel);
+    LIDM_CUDA_CHECK(cudaMemcpyAsync(p, t.p, t.numel * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return p;
+  }
+  NormW norm(const std::string& prefix, int C) {
+    NormW n;
+    n.C = C;
+    n.gamma = f32(prefix + ".weight", C);
+    n.beta = f32(prefix + ".bias", C);
+    return n;
+  }
+  // k_alloc_override: K of the packed matrix (for im2col'd operands padded to a multiple of 64)
+  ConvW conv(const std::string& prefix, int cout, int cin, int kh, int kw, int k_alloc_override = 0) {
+    const DevTensor& t = find_raw(h, prefix + ".weight", ema);
+    if (t.numel != (int64_t)cout * cin * kh * kw)
+      throw Error(LIDM_ERR_STATE, "weight '" + prefix + ".weight' has unexpected size");
+    ConvW c;
+    c.cout = cout; c.cin = cin; c.kh = kh; c.kw = kw;
+    c.n_alloc = round_n_alloc(cout);
+    c.k_alloc = k_alloc_override ? k_alloc_override : kh * kw * cin;
+    c.w = dev_alloc<bf16>(h, (size_t)c.n_alloc * c.k_alloc);
+    launch_pack_conv_weight(t.p, cout, cin, kh, kw, c.n_alloc, c.k_alloc, nullptr, nullptr, 1.f, 0, c.w, s);
+    c.bias = f32(prefix + ".bias", cout);
+    return c;
+  }
+};
+
+// ------------------------------------------------------------------------------------------- plan builder
+struct Builder {
+  lidm_handle* h;
+  Plan* P;
+  ArenaPlanner ap;
+  bool dry;
+
+  View act(int B, int H, int W, int C, int hl, int hr, Buf* buf) {
+    View v;
+    v.B = B; v.H = H; v.W = W; v.C = C; v.hl = hl; v.hr = hr; v.ld = C;
+    buf->bytes = (size_t)B * H * (W + hl + hr) * C * sizeof(bf16);
+    buf->off = ap.alloc(buf->bytes);
+    v.p = reinterpret_cast<bf16*>(P->arena + buf->off);
+    return v;
+  }
+  template <class T>
+  T* raw(size_t n, Buf* buf) {
+    buf->bytes = n * sizeof(T);
+    buf->off = ap.alloc(buf->bytes);
+    return reinterpret_cast<T*>(P->arena + buf->off);
+  }
+  void release(const Buf& b) { ap.release(b.off, b.bytes); }
+  void op(Op f) { if (!dry) P->ops.push_back(std::move(f)); }
+
+  static View chan_slice(const View& v, int c0, int C) {
+    View s = v;
+    s.p = v.p + c0;
+    s.C = C;
+    return s;
+  }
+
+  void gemm(const View& a, const ConvTaps& taps, const ConvW& w, const GemmEpilogue& ep) {
+    GemmB b; b.p = w.w; b.n_alloc = w.n_alloc; b.ld = w.k_alloc;
+    const int N = w.cout;
+    op([=](cudaStream_t s) { launch_conv_gemm(a, taps, b, N, ep, s); });
+  }
+  void groupnorm(const View& x, const View& y, const NormW& n, float eps, bool silu) {
+    Plan* P_ = P;
+    op([=](cudaStream_t s) { launch_groupnorm(x, y, n.gamma, n.beta, eps, 32, silu, P_->gn_partials, s); });
+  }
+
+  // ResBlock._forward (openaimodel.py:256-276) / ResnetBlock.forward (model_lidm.py:127-147, temb None)
+  void res_block(const ResW& r, const View& x, const View& dst, int kh, int kw, int pl, int pr, int pt, float eps) {
+    const int B = x.B, H = x.H, W = x.W;
+    Buf bg1, bh, bg2, bsk;
+    View g1 = act(B, H, W, r.cin, pl, pr, &bg1);
+    groupnorm(x, g1, r.n1, eps, true);
+    View hmid = act(B, H, W, r.cout, 0, 0, &bh);
+    {
+      GemmEpilogue ep;
+      ep.bias = r.c1.bias;
+      ep.out = hmid;
+      GemmB b; b.p = r.c1.w; b.n_alloc = r.c1.n_alloc; b.ld = r.c1.k_alloc;
+      const ConvTaps taps = taps_rect(kh, kw, pl, pt);
+      const int N = r.cout, emb_off = r.emb_off;
+      Plan* P_ = P;
+      op([=](cudaStream_t s) {
+        GemmEpilogue e = ep;
+        if (emb_off >= 0) { e.rowadd = P_->rowadd_base + emb_off; e.rowadd_ld = P_->rowadd_ld; }
+        launch_conv_gemm(g1, taps, b, N, e, s);
+      });
+    }
+    release(bg1);
+    View g2 = act(B, H, W, r.cout, pl, pr, &bg2);
+    groupnorm(hmid, g2, r.n2, eps, true);
+    release(bh);
+    View resid = x;
+    if (r.has_skip) {
+      View sk = act(B, H, W, r.cout, 0, 0, &bsk);
+      GemmEpilogue ep;
+      ep.bias = r.skip.bias;
+      ep.out = sk;
+      gemm(x, taps_1x1(), r.skip, ep);
+      resid = sk;
+    }
+    {
+      GemmEpilogue ep;
+      ep.bias = r.c2.bias;
+      ep.residual = resid;
+      ep.out = dst;
+      gemm(g2, taps_rect(kh, kw, pl, pt), r.c2, ep);
+    }
+    release(bg2);
+    if (r.has_skip) release(bsk);
+  }
+
+  // AttentionBlock._forward + QKVAttentionLegacy (openaimodel.py:320-326, 358-374)
+  void attn_block(const AttnW& a, const View& x, const View& dst) {
+    const int B = x.B, H = x.H, W = x.W, C = a.ch, T = H * W;
+    Buf bg, bqk, bvt, ba;
+    View g = act(B, H, W, C, 0, 0, &bg);
+    groupnorm(x, g, a.n, 1e-5f, false);
+    View qk = act(B, H, W, 2 * C, 0, 0, &bqk);
+    bf16* vt = raw<bf16>((size_t)B * C * T, &bvt);
+    {
+      GemmEpilogue ep;
+      ep.bias = a.qkv.bias;
+      ep.out = qk;
+      ep.split_n = 2 * C;
+      ep.out_t = vt;
+      gemm(g, taps_1x1(), a.qkv, ep);
+    }
+    release(bg);
+    View ao = act(B, H, W, C, 0, 0, &ba);
+    const int heads = a.heads;
+    op([=](cudaStream_t s) { launch_attention_d32(qk.p, vt, ao, B, T, heads, s); });
+    release(bqk);
+    release(bvt);
+    {
+      GemmEpilogue ep;
+      ep.bias = a.proj.bias;
+      ep.residual = x;
+      ep.out = dst;
+      gemm(ao, taps_1x1(), a.proj, ep);
+    }
+    release(ba);
+  }
+
+  // AttnBlock.forward (model_lidm.py:184-208): single head, d = C, scale C^-1/2 folded into the packed q rows
+  void dec_attn_block(const AttnW& a, const View& x, const View& dst) {
+    const int B = x.B, H = x.H, W = x.W, C = a.ch, T = H * W;
+    Buf bg, bqk, bvt, bs, bp, ba;
+    View g = act(B, H, W, C, 0, 0, &bg);
+    groupnorm(x, g, a.n, 1e-6f, false);
+    View qk = act(B, H, W, 2 * C, 0, 0, &bqk);
+    bf16* vt = raw<bf16>((size_t)B * C * T, &bvt);
+    {
+      GemmEpilogue ep;
+      ep.bias = a.qkv.bias;
+      ep.out = qk;
+      ep.split_n = 2 * C;
+      ep.out_t = vt;
+      gemm(g, taps_1x1(), a.qkv, ep);
+    }
+    release(bg);
+    float* S = raw<float>((size_t)B * T * T, &bs);
+    {
+      View q = chan_slice(qk, 0, C);
+      GemmB kb; kb.p = qk.p + C; kb.n_alloc = T; kb.ld = 2 * C; kb.batch_stride = (int64_t)T * 2 * C;
+      GemmEpilogue ep;
+      ep.out_f32_nhwc = S;
+      op([=](cudaStream_t s) { launch_conv_gemm(q, taps_1x1(), kb, T, ep, s); });
+    }
+    bf16* Pm = raw<bf16>((size_t)B * T * T, &bp);
+    op([=](cudaStream_t s) { launch_softmax_rows(S, Pm, (int64_t)B * T, T, s); });
+    release(bs);
+    View ao = act(B, H, W, C, 0, 0, &ba);
+    {
+      View pv; pv.p = Pm; pv.B = B; pv.H = T / 128; pv.W = 128; pv.C = T; pv.ld = T;
+      GemmB vb; vb.p = vt; vb.n_alloc = C; vb.ld = T; vb.batch_stride = (int64_t)C * T;
+      GemmEpilogue ep;
+      View o2 = ao; o2.H = T / 128; o2.W = 128;
+      ep.out = o2;
+      op([=](cudaStream_t s) { launch_conv_gemm(pv, taps_1x1(), vb, C, ep, s); });
+    }
+    release(bp); release(bqk); release(bvt);
+    {
+      GemmEpilogue ep;
+      ep.bias = a.proj.bias;
+      ep.residual = x;
+      ep.out = dst;
+      gemm(ao, taps_1x1(), a.proj, ep);
+    }
+    release(ba);
+  }
+
+  // Downsample.forward (openaimodel.py:159-161): circular 3x3 stride 2 via channels-last im2col + GEMM
+  void down(const ConvW& c, const View& x, const View& dst) {
+    const int B = x.B, Ho = x.H / 2, Wo = x.W / 2;
+    Buf bc;
+    bf16* col = raw<bf16>((size_t)B * Ho * Wo * 9 * x.C, &bc);
+    op([=](cudaStream_t s) { launch_im2col_nhwc(x, 3, 3, 2, 1, 1, Ho, Wo, col, s); });
+    View a; a.p = col; a.B = B; a.H = Ho; a.W = Wo; a.C = 9 * x.C; a.ld = 9 * x.C;
+    GemmEpilogue ep;
+    ep.bias = c.bias;
+    ep.out = dst;
+    gemm(a, taps_1x1(), c, ep);
+    release(bc);
+  }
+
+  // Upsample.forward (openaimodel.py:108-118): nearest x2 then circular 3x3
+  void up(const ConvW& c, const View& x, const View& dst) {
+    Buf bu;
+    View u = act(x.B, x.H * 2, x.W * 2, x.C, 1, 1, &bu);
+    op([=](cudaStream_t s) { launch_upsample_nearest2x(x, u, s); });
+    GemmEpilogue ep;
+    ep.bias = c.bias;
+    ep.out = dst;
+    gemm(u, taps_rect(3, 3, 1, 1), c, ep);
+    release(bu);
+  }
+};
+
+// ------------------------------------------------------------------------------------------- U-Net plan
+void build_unet_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
+  Builder b{h, P, ArenaPlanner(), dry};
+  const lidm_config& cfg = h->cfg;
+  const int B = P->B;
+  const int n_in = (int)h->in_blocks.size(), n_out = (int)h->out_blocks.size();
+  // resolution of every input block's output
+  std::vector<int> rh(n_in), rw(n_in);
+  {
+    int H = cfg.latent_h, W = cfg.latent_w;
+    for (int k = 0; k < n_in; ++k) {
+      if (h->in_blocks[k][0].kind == Layer::DOWN) { H /= 2; W /= 2; }
+      rh[k] = H; rw[k] = W;
+    }
+  }
+  // concat buffers: output block i consumes cat[h_prev (Ca) | hs[n_in-1-i] (Cb)]
+  std::vector<View> cat(n_out);
+  std::vector<Buf> catbuf(n_out);
+  std::vector<int> Ca(n_out);
+  {
+    int ch_prev = h->mid_block.back().cout;
+    for (int i = 0; i < n_out; ++i) {
+      const int k = n_in - 1 - i;
+      Ca[i] = ch_prev;
+      cat[i] = b.act(B, rh[k], rw[k], ch_prev + h->in_chans[k], 0, 0, &catbuf[i]);
+      ch_prev = h->out_blocks[i][0].cout;
+    }
+  }
+  auto run_layers = [&](const std::vector<Layer>& layers, View x, const View& dst) {
+    Buf prev_buf; bool have_prev = false;
+    for (size_t j = 0; j < layers.size(); ++j) {
+      const Layer& L = layers[j];
+      const bool last = (j + 1 == layers.size());
+      int Ho = x.H, Wo = x.W;
+      if (L.kind == Layer::DOWN) { Ho /= 2; Wo /= 2; }
+      if (L.kind == Layer::UP) { Ho *= 2; Wo *= 2; }
+      Buf ob; View o;
+      if (last) o = dst;
+      else o = b.act(B, Ho, Wo, L.cout, 0, 0, &ob);
+      switch (L.kind) {
+        case Layer::RES: b.res_block(L.r, x, o, 3, 3, 1, 1, 1, 1e-5f); break;
+        case Layer::ATTN: b.attn_block(L.a, x, o); break;
+        case Layer::DOWN: b.down(L.c, x, o); break;
+        case Layer::UP: b.up(L.c, x, o); break;
+        case Layer::CONV: throw Error(LIDM_ERR_INVALID, "unexpected conv layer");
+      }
+      if (have_prev) b.release(prev_buf);
+      prev_buf = ob; have_prev = !last;
+      x = o;
+    }
+  };
+
+  // input_blocks[0]: conv 3x3 in_channels -> model_channels via fp32-NCHW im2col (K padded to 128)
+  {
+    const int H = cfg.latent_h, W = cfg.latent_w, kpad = h->in_blocks[0][0].c.k_alloc;
+    Buf bc;
+    bf16* col = b.raw<bf16>((size_t)B * H * W * kpad, &bc);
+    const int Cin = cfg.in_channels;
+    b.op([=](cudaStream_t s) { launch_im2col_nchw_f32(P->x, B, Cin, H, W, 3, 3, 1, 1, col, kpad, s); });
+    View a; a.p = col; a.B = B; a.H = H; a.W = W; a.C = kpad; a.ld = kpad;
+    GemmEpilogue ep;
+    ep.bias = h->in_blocks[0][0].c.bias;
+    ep.out = Builder::chan_slice(cat[n_out - 1], Ca[n_out - 1], h->in_chans[0]);
+    b.gemm(a, taps_1x1(), h->in_blocks[0][0].c, ep);
+    b.release(bc);
+  }
+  for (int k = 1; k < n_in; ++k) {
+    const int iprev = n_out - 1 - (k - 1), icur = n_out - 1 - k;
+    View x = Builder::chan_slice(cat[iprev], Ca[iprev], h->in_chans[k - 1]);
+    View dst = Builder::chan_slice(cat[icur], Ca[icur], h->in_chans[k]);
+    run_layers(h->in_blocks[k], x, dst);
+  }
+  {
+    View x = Builder::chan_slice(cat[0], Ca[0], h->in_chans[n_in - 1]);
+    View dst = Builder::chan_slice(cat[0], 0, Ca[0]);
+    run_layers(h->mid_block, x, dst);
+  }
+  Buf bfinal;
+  View hfinal;
+  for (int i = 0; i < n_out; ++i) {
+    View dst;
+    if (i + 1 < n_out) dst = Builder::chan_slice(cat[i + 1], 0, Ca[i + 1]);
+    else { hfinal = b.act(B, cfg.latent_h, cfg.latent_w, h->out_blocks[i].back().cout, 0, 0, &bfinal); dst = hfinal; }
+    run_layers(h->out_blocks[i], cat[i], dst);
+    b.release(catbuf[i]);
+  }
+  // out: GroupNorm32 + SiLU + conv3x3 (zero-init in the reference) -> eps (fp32 NCHW) [+ fused DDIM update]
+  {
+    Buf bg;
+    View g = b.act(B, hfinal.H, hfinal.W, hfinal.C, 1, 1, &bg);
+    b.groupnorm(hfinal, g, h->out_norm, 1e-5f, true);
+    GemmB wb; wb.p = h->out_conv.w; wb.n_alloc = h->out_conv.n_alloc; wb.ld = h->out_conv.k_alloc;
+    const float* bias = h->out_conv.bias;
+    const int N = h->out_conv.cout;
+    const ConvTaps taps = taps_rect(3, 3, 1, 1);
+    b.op([=](cudaStream_t s) {
+      GemmEpilogue ep;
+      ep.bias = bias;
+      ep.out_f32_nchw = P->out;
+      if (P->ddim_x_prev != nullptr) {
+        ep.ddim_x = P->x; ep.ddim_noise = P->ddim_noise; ep.ddim_x_prev = P->ddim_x_prev;
+        ep.ddim_pred_x0 = P->ddim_pred_x0; ep.ddim_coef = P->ddim_coef;
+      }
+      launch_conv_gemm(g, taps, wb, N, ep, s);
+    });
+    b.release(bg);
+    b.release(bfinal);
+  }
+  *high = b.ap.high();
+}
+
+// ------------------------------------------------------------------------------------------- decoder plan
+void build_dec_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
+  Builder b{h, P, ArenaPlanner(), dry};
+  const lidm_config& cfg = h->cfg;
+  const int B = P->B, lh = cfg.latent_h, lw = cfg.latent_w, zc = cfg.z_channels;
+  Buf bzq, bcol;
+  float* zq = b.raw<float>((size_t)B * zc * lh * lw, &bzq);
+  {
+    const float inv_scale = 1.0f / cfg.scale_factor;
+    const int n_embed = cfg.n_embed;
+    b.op([=](cudaStream_t s) {
+      launch_vq(P->x, B, zc, lh * lw, h->codebook, h->cb_norm, n_embed, P->quantize, h->pq_w, h->pq_b, inv_scale, zq,
+                P->idx_out, s);
+    });
+  }
+  const int kpad = h->dec_conv_in.k_alloc;
+  bf16* col = b.raw<bf16>((size_t)B * lh * lw * kpad, &bcol);
+  b.op([=](cudaStream_t s) { launch_im2col_nchw_f32(zq, B, zc, lh, lw, 3, 3, 1, 1, col, kpad, s); });
+  b.release(bzq);
+  Buf bx;
+  View x = b.act(B, lh, lw, h->dec_top, 0, 0, &bx);
+  {
+    View a; a.p = col; a.B = B; a.H = lh; a.W = lw; a.C = kpad; a.ld = kpad;
+    GemmEpilogue ep;
+    ep.bias = h->dec_conv_in.bias;
+    ep.out = x;
+    b.gemm(a, taps_1x1(), h->dec_conv_in, ep);
+  }
+  b.release(bcol);
+  auto step = [&](std::function<void(const View&, const View&)> f, int Ho, int Wo, int C, int hl, int hr) {
+    Buf bo;
+    View o = b.act(B, Ho, Wo, C, hl, hr, &bo);
+    f(x, o);
+    b.release(bx);
+    bx = bo; x = o;
+  };
+  step([&](const View& i, const View& o) { b.res_block(h->dec_mid1, i, o, 3, 3, 1, 1, 1, 1e-6f); }, lh, lw, h->dec_top, 0, 0);
+  step([&](const View& i, const View& o) { b.dec_attn_block(h->dec_attn, i, o); }, lh, lw, h->dec_top, 0, 0);
+  step([&](const View& i, const View& o) { b.res_block(h->dec_mid2, i, o, 3, 3, 1, 1, 1, 1e-6f); }, lh, lw, h->dec_top, 0, 0);
+  int H = lh, W = lw;
+  for (int lv = cfg.ae_n_ch_mult - 1; lv >= 0; --lv) {
+    const DecLevel& L = h->dec_levels[lv];
+    const int pl = L.kw == 3 ? 1 : 1, pr = L.kw == 3 ? 1 : 2, pt = L.kh == 3 ? 1 : 0;
+    for (const ResW& r : L.blocks)
+      step([&](const View& i, const View& o) { b.res_block(r, i, o, L.kh, L.kw, pl, pr, pt, 1e-6f); }, H, W, r.cout, 0, 0);
+    if (L.has_up) {
+      // Upsample.forward (model_lidm.py:57-61): bilinear align_corners=True, then circular conv
+      const int Ho = H * L.sh, Wo = W * L.sw;
+      const int ukh = L.up.kh, ukw = L.up.kw;
+      const int uh = (ukw - 1) / 2, upt = (ukh - 1) / 2;
+      step([&](const View& i, const View& o) { b.op([=](cudaStream_t s) { launch_upsample_bilinear(i, o, s); }); }, Ho, Wo,
+           L.ch, uh, uh);
+      H = Ho; W = Wo;
+      step([&](const View& i, const View& o) {
+        GemmEpilogue ep;
+        ep.bias = L.up.bias;
+        ep.out = o;
+        b.gemm(i, taps_rect(ukh, ukw, uh, upt), L.up, ep);
+      }, H, W, L.ch, 0, 0);
+    }
+  }
+  // norm_out + swish + conv_out (1,4), pad (1,2)
+  {
+    Buf bg;
+    View g = b.act(B, H, W, h->dec_last, 1, 2, &bg);
+    b.groupnorm(x, g, h->dec_norm_out, 1e-6f, true);
+    b.release(bx);
+    GemmB wb; wb.p = h->dec_conv_out.w; wb.n_alloc = h->dec_conv_out.n_alloc; wb.ld = h->dec_conv_out.k_alloc;
+    const float* bias = h->dec_conv_out.bias;
+    const int N = h->dec_conv_out.cout;
+    const ConvTaps taps = taps_rect(1, 4, 1, 0);
+    if (cfg.ae_use_mask) {
+      Buf bd;
+      float* dec = b.raw<float>((size_t)B * N * H * W, &bd);
+      b.op([=](cudaStream_t s) {
+        GemmEpilogue ep; ep.bias = bias; ep.out_f32_nchw = dec;
+        launch_conv_gemm(g, taps, wb, N, ep, s);
+      });
+      const int HW = H * W;
+      b.op([=](cudaStream_t s) { launch_mask_select(dec, B, HW, P->out, s); });
+      b.release(bd);
+    } else {
+      b.op([=](cudaStream_t s) {
+        GemmEpilogue ep; ep.bias = bias; ep.out_f32_nchw = P->out;
+        launch_conv_gemm(g, taps, wb, N, ep, s);
+      });
+    }
+    b.release(bg);
+  }
+  *high = b.ap.high();
+}
+
+Plan* get_plan(lidm_handle* h, std::map<int, std::unique_ptr<Plan>>& cache, int B,
+               void (*pass)(lidm_handle*, Plan*, bool, size_t*)) {
+  auto it = cache.find(B);
+  if (it != cache.end()) return it->second.get();
+  std::unique_ptr<Plan> P(new Plan());
+  P->B = B;
+  size_t high = 0;
+  pass(h, P.get(), true, &high);
+  P->arena_bytes = high;
+  LIDM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&P->arena), std::max<size_t>(high, 1024)));
+  LIDM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&P->gn_partials), (size_t)B * 32 * 2 * GN_MAX_CHUNKS * sizeof(float)));
+  size_t high2 = 0;
+  pass(h, P.get(), false, &high2);
+  if (high2 != high) throw Error(LIDM_ERR_STATE, "internal: non-deterministic activation plan");
+  Plan* ret = P.get();
+  cache[B] = std::move(P);
+  return ret;
+}
+
+void run_plan(Plan* P, cudaStream_t s) {
+  for (auto& f : P->ops) f(s);
+}
+
+// ------------------------------------------------------------------------------------------- finalize
+ResW pack_res(Packer& pk, const std::string& p, int cin, int cout, int kh, int kw, bool unet) {
+  ResW r;
+  r.cin = cin; r.cout = cout;
+  if (unet) {
+    r.n1 = pk.norm(p + ".in_layers.0", cin);
+    r.c1 = pk.conv(p + ".in_layers.2", cout, cin, kh, kw);
+    r.n2 = pk.norm(p + ".out_layers.0", cout);
+    r.c2 = pk.conv(p + ".out_layers.3", cout, cout, kh, kw);
+    if (cin != cout) { r.has_skip = true; r.skip = pk.conv(p + ".skip_connection", cout, cin, 1, 1); }
+  } else {
+    r.n1 = pk.norm(p + ".norm1", cin);
+    r.c1 = pk.conv(p + ".conv1", cout, cin, kh, kw);
+    r.n2 = pk.norm(p + ".norm2", cout);
+    r.c2 = pk.conv(p + ".conv2", cout, cout, kh, kw);
+    if (cin != cout) { r.has_skip = true; r.skip = pk.conv(p + ".nin_shortcut", cout, cin, 1, 1); }
+  }
+  return r;
+}
+
+// qkv Conv1d of AttentionBlock: legacy channel order [head][q|k|v][ch] -> packed rows [q all heads | k all heads | v],
+// q and k rows (and biases) pre-multiplied by ch^-1/4 (openaimodel.py:367-370).
+AttnW pack_unet_attn(Packer& pk, const std::string& p, int ch, int heads) {
+  lidm_handle* h = pk.h;
+  AttnW a;
+  a.ch = ch; a.heads = heads;
+  const int d = ch / heads;
+  if (d != 32) throw Error(LIDM_ERR_INVALID, "attention head dim must be 32 (num_head_channels)");
+  a.n = pk.norm(p + ".norm", ch);
+  const DevTensor& w = find_raw(h, p + ".qkv.weight", pk.ema);
+  const DevTensor& bsrc = find_raw(h, p + ".qkv.bias", pk.ema);
+  if (w.numel != (int64_t)3 * ch * ch || bsrc.numel != 3 * ch) throw Error(LIDM_ERR_STATE, "qkv weight size: " + p);
+  std::vector<int> perm(3 * ch);
+  for (int part = 0; part < 3; ++part)
+    for (int hd = 0; hd < heads; ++hd)
+      for (int c = 0; c < d; ++c) perm[part * ch + hd * d + c] = hd * 3 * d + part * d + c;
+  int* perm_dev = dev_alloc<int>(h, perm.size());
+  LIDM_CUDA_CHECK(cudaMemcpyAsync(perm_dev, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice, pk.s));
+  const float scale = 1.0f / std::sqrt(std::sqrt((float)d));
+  ConvW c;
+  c.cout = 3 * ch; c.cin = ch; c.kh = c.kw = 1;
+  c.n_alloc = round_n_alloc(3 * ch); c.k_alloc = ch;
+  c.w = dev_alloc<bf16>(h, (size_t)c.n_alloc * c.k_alloc);
+  launch_pack_conv_weight(w.p, 3 * ch, ch, 1, 1, c.n_alloc, c.k_alloc, perm_dev, nullptr, scale, 2 * ch, c.w, pk.s);
+  std::vector<float> bh(3 * ch), bp(3 * ch);
+  LIDM_CUDA_CHECK(cudaMemcpyAsync(bh.data(), bsrc.p, bh.size() * sizeof(float), cudaMemcpyDeviceToHost, pk.s));
+  LIDM_CUDA_CHECK(cudaStreamSynchronize(pk.s));
+  for (int i = 0; i < 3 * ch; ++i) bp[i] = bh[perm[i]] * (i < 2 * ch ? scale : 1.0f);
+  c.bias = dev_alloc<float>(h, bp.size());
+  LIDM_CUDA_CHECK(cudaMemcpy(c.bias, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice));
+  a.qkv = c;
+  a.proj = pk.conv(p + ".proj_out", ch, ch, 1, 1);
+  return a;
+}
+
+// Decoder AttnBlock: separate q/k/v 1x1 convs -> one packed [q * C^-1/2 | k | v] matrix
+AttnW pack_dec_attn(Packer& pk, const std::string& p, int ch) {
+  lidm_handle* h = pk.h;
+  AttnW a;
+  a.ch = ch; a.heads = 1;
+  a.n = pk.norm(p + ".norm", ch);
+  ConvW c;
+  c.cout = 3 * ch; c.cin = ch; c.kh = c.kw = 1;
+  c.n_alloc = round_n_alloc(3 * ch); c.k_alloc = ch;
+  if (c.n_alloc != 3 * ch) throw Error(LIDM_ERR_INVALID, "decoder attention channels must be a multiple of 128");
+  c.w = dev_alloc<bf16>(h, (size_t)c.n_alloc * c.k_alloc);
+  c.bias = dev_alloc<float>(h, 3 * ch);
+  const char* names[3] = {".q", ".k", ".v"};
+  const float scale = 1.0f / std::sqrt((float)ch);
+  std::vector<float> bh(ch);
+  for (int i = 0; i < 3; ++i) {
+    const DevTensor& w = find_raw(h, p + names[i] + ".weight", pk.ema);
+    const DevTensor& bsrc = find_raw(h, p + names[i] + ".bias", pk.ema);
+    if (w.numel != (int64_t)ch * ch || bsrc.numel != ch) throw Error(LIDM_ERR_STATE, "decoder attention weight size");
+    launch_pack_conv_weight(w.p, ch, ch, 1, 1, ch, ch, nullptr, nullptr, i == 0 ? scale : 1.f, i == 0 ? ch : 0,
+                            c.w + (size_t)i * ch * ch, pk.s);
+    LIDM_CUDA_CHECK(cudaMemcpy(bh.data(), bsrc.p, ch * sizeof(float), cudaMemcpyDeviceToHost));
+    if (i == 0) for (float& v : bh) v *= scale;
+    LIDM_CUDA_CHECK(cudaMemcpy(c.bias + (size_t)i * ch, bh.data(), ch * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  a.qkv = c;
+  a.proj = pk.conv(p + ".proj_out", ch, ch, 1, 1);
+  return a;
+}
+
+bool in_list(const int32_t* v, int n, int x) {
+  for (int i = 0; i < n; ++i) if (v[i] == x) return true;
+  return false;
+}
+
+void finalize(lidm_handle* h, bool use_ema) {
+  const lidm_config& cfg = h->cfg;
+  Packer pk{h, use_ema};
+  const std::string U = "model.diffusion_model.";
+  const int mc = cfg.model_channels, ted = mc * 4;
+  h->ted = ted;
+  h->te_w0 = pk.f32(U + "time_embed.0.weight", (int64_t)ted * mc);
+  h->te_b0 = pk.f32(U + "time_embed.0.bias", ted);
+  h->te_w2 = pk.f32(U + "time_embed.2.weight", (int64_t)ted * ted);
+  h->te_b2 = pk.f32(U + "time_embed.2.bias", ted);
+
+  // ---- U-Net topology, exactly as UNetModel.__init__ walks it (openaimodel.py:516-687)
+  std::vector<std::pair<std::string, ResW*>> emb_layers;
+  h->in_blocks.clear(); h->out_blocks.clear(); h->mid_block.clear(); h->in_chans.clear();
+  {
+    Layer L; L.kind = Layer::CONV; L.cin = cfg.in_channels; L.cout = mc;
+    const int kpad = (9 * cfg.in_channels + 63) / 64 * 64;
+    L.c = pk.conv(U + "input_blocks.0.0", mc, cfg.in_channels, 3, 3, kpad);
+    h->in_blocks.push_back({L});
+    h->in_chans.push_back(mc);
+  }
+  int ch = mc, ds = 1;
+  auto make_res = [&](const std::string& p, int cin, int cout) {
+    Layer L; L.kind = Layer::RES; L.cin = cin; L.cout = cout;
+    L.r = pack_res(pk, p, cin, cout, 3, 3, true);
+    return L;
+  };
+  auto make_attn = [&](const std::string& p, int c) {
+    Layer L; L.kind = Layer::ATTN; L.cin = L.cout = c;
+    L.a = pack_unet_attn(pk, p, c, c / cfg.num_head_channels);
+    return L;
+  };
+  for (int level = 0; level < cfg.n_channel_mult; ++level) {
+    const int mult = cfg.channel_mult[level];
+    for (int r = 0; r < cfg.num_res_blocks; ++r) {
+      const std::string p = U + "input_blocks." + std::to_string(h->in_blocks.size());
+      std::vector<Layer> layers;
+      layers.push_back(make_res(p + ".0", ch, mult * mc));
+      ch = mult * mc;
+      if (in_list(cfg.attention_resolutions, cfg.n_attention_resolutions, ds)) layers.push_back(make_attn(p + ".1", ch));
+      h->in_blocks.push_back(layers);
+      h->in_chans.push_back(ch);
+    }
+    if (level != cfg.n_channel_mult - 1) {
+      const std::string p = U + "input_blocks." + std::to_string(h->in_blocks.size());
+      Layer L; L.kind = Layer::DOWN; L.cin = L.cout = ch;
+      L.c = pk.conv(p + ".0.op", ch, ch, 3, 3);
+      h->in_blocks.push_back({L});
+      h->in_chans.push_back(ch);
+      ds *= 2;
+    }
+  }
+  h->mid_block.push_back(make_res(U + "middle_block.0", ch, ch));
+  h->mid_block.push_back(make_attn(U + "middle_block.1", ch));
+  h->mid_block.push_back(make_res(U + "middle_block.2", ch, ch));
+  {
+    std::vector<int> chans = h->in_chans;
+    for (int level = cfg.n_channel_mult - 1; level >= 0; --level) {
+      const int mult = cfg.channel_mult[level];
+      for (int i = 0; i <= cfg.num_res_blocks; ++i) {
+        const int ich = chans.back();
+        chans.pop_back();
+        const std::string p = U + "output_blocks." + std::to_string(h->out_blocks.size());
+        std::vector<Layer> layers;
+        layers.push_back(make_res(p + ".0", ch + ich, mc * mult));
+        ch = mc * mult;
+        int j = 1;
+        if (in_list(cfg.attention_resolutions, cfg.n_attention_resolutions, ds))
+          layers.push_back(make_attn(p + "." + std::to_string(j++), ch));
+        if (level && i == cfg.num_res_blocks) {
+          Layer L; L.kind = Layer::UP; L.cin = L.cout = ch;
+          L.c = pk.conv(p + "." + std::to_string(j++) + ".conv", ch, ch, 3, 3);
+          layers.push_back(L);
+          ds /= 2;
+        }
+        h->out_blocks.push_back(layers);
+      }
+    }
+  }
+  h->out_norm = pk.norm(U + "out.0", ch);
+  h->out_conv = pk.conv(U + "out.2", cfg.out_channels, mc, 3, 3);
+  if (ch != mc) throw Error(LIDM_ERR_INVALID, "U-Net must end at model_channels");
+
+  // ---- emb_layers: one concatenated [emb_total][ted] fp32 matrix, evaluated once per step for all ResBlocks
+  {
+    std::vector<std::pair<std::string, ResW*>> all;
+    auto collect = [&](std::vector<Layer>& layers, const std::string& p) {
+      for (size_t j = 0; j < layers.size(); ++j)
+        if (layers[j].kind == Layer::RES) all.emplace_back(p + "." + std::to_string(j), &layers[j].r);
+    };
+    for (size_t i = 0; i < h->in_blocks.size(); ++i) collect(h->in_blocks[i], U + "input_blocks." + std::to_string(i));
+    collect(h->mid_block, U + "middle_block");
+    for (size_t i = 0; i < h->out_blocks.size(); ++i) collect(h->out_blocks[i], U + "output_blocks." + std::to_string(i));
+    int total = 0;
+    for (auto& e : all) { e.second->emb_off = total; total += e.second->cout; }
+    h->emb_total = total;
+    h->emb_w = dev_alloc<float>(h, (size_t)total * ted);
+    h->emb_b = dev_alloc<float>(h, total);
+    for (auto& e : all) {
+      const DevTensor& w = find_raw(h, e.first + ".emb_layers.1.weight", use_ema);
+      const DevTensor& bb = find_raw(h, e.first + ".emb_layers.1.bias", use_ema);
+      if (w.numel != (int64_t)e.second->cout * ted || bb.numel != e.second->cout)
+        throw Error(LIDM_ERR_STATE, "emb_layers size mismatch at " + e.first);
+      LIDM_CUDA_CHECK(cudaMemcpy(h->emb_w + (size_t)e.second->emb_off * ted, w.p, w.numel * sizeof(float), cudaMemcpyDeviceToDevice));
+      LIDM_CUDA_CHECK(cudaMemcpy(h->emb_b + e.second->emb_off, bb.p, bb.numel * sizeof(float), cudaMemcpyDeviceToDevice));
+    }
+  }
+
+  // ---- first stage (decode side)
+  const std::string A = "first_stage_model.";
+  if (cfg.embed_dim != 8 || cfg.z_channels != 8) throw Error(LIDM_ERR_INVALID, "embed_dim and z_channels must be 8");
+  h->codebook = pk.f32(A + "quantize.embedding.weight", (int64_t)cfg.n_embed * cfg.embed_dim);
+  h->cb_norm = dev_alloc<float>(h, cfg.n_embed);
+  launch_codebook_norm(h->codebook, cfg.n_embed, cfg.embed_dim, h->cb_norm, 0);
+  h->pq_w = pk.f32(A + "post_quant_conv.weight", (int64_t)cfg.z_channels * cfg.embed_dim);
+  h->pq_b = pk.f32(A + "post_quant_conv.bias", cfg.z_channels);
+  const std::string D = A + "decoder.";
+  const int nres = cfg.ae_n_ch_mult;
+  int block_in = cfg.ae_ch * cfg.ae_ch_mult[nres - 1];
+  h->dec_top = block_in;
+  h->dec_conv_in = pk.conv(D + "conv_in", block_in, cfg.z_channels, 3, 3, (9 * cfg.z_channels + 63) / 64 * 64);
+  h->dec_mid1 = pack_res(pk, D + "mid.block_1", block_in, block_in, 3, 3, false);
+  h->dec_attn = pack_dec_attn(pk, D + "mid.attn_1", block_in);
+  h->dec_mid2 = pack_res(pk, D + "mid.block_2", block_in, block_in, 3, 3, false);
+  h->dec_levels.assign(nres, DecLevel());
+  int H = cfg.latent_h, W = cfg.latent_w;
+  for (int lv = nres - 1; lv >= 0; --lv) {
+    DecLevel& L = h->dec_levels[lv];
+    if (lv > 0) {
+      L.sh = cfg.ae_strides[lv - 1][0]; L.sw = cfg.ae_strides[lv - 1][1];
+      if (L.sh == 2 && L.sw == 2) { L.kh = 3; L.kw = 3; }
+      else if (L.sh == 1 && L.sw == 2) { L.kh = 1; L.kw = 4; }
+      else throw Error(LIDM_ERR_INVALID, "unsupported decoder stride");
+      L.has_up = true;
+    } else { L.kh = 1; L.kw = 4; }
+    const int block_out = cfg.ae_ch * cfg.ae_ch_mult[lv];
+    for (int i = 0; i <= cfg.ae_num_res_blocks; ++i) {
+      L.blocks.push_back(pack_res(pk, D + "up." + std::to_string(lv) + ".block." + std::to_string(i), block_in, block_out, L.kh, L.kw, false));
+      block_in = block_out;
+    }
+    L.ch = block_in;
+    if (L.has_up) {
+      const int ukh = (L.sh == 2) ? 3 : 1, ukw = (L.sh == 2) ? 3 : 5;   // UPSAMPLE_STRIDE2KERNEL_DICT (model_lidm.py:44)
+      L.up = pk.conv(D + "up." + std::to_string(lv) + ".upsample.conv", block_in, block_in, ukh, ukw);
+      H *= L.sh; W *= L.sw;
+    }
+  }
+  h->dec_last = block_in;
+  h->img_h = H; h->img_w = W;
+  h->dec_norm_out = pk.norm(D + "norm_out", block_in);
+  h->dec_conv_out = pk.conv(D + "conv_out", cfg.ae_out_ch, block_in, 1, 4);
+  if (cfg.ae_use_mask && cfg.ae_out_ch != 2) throw Error(LIDM_ERR_INVALID, "use_mask needs out_ch == 2");
+  LIDM_CUDA_CHECK(cudaDeviceSynchronize());
+  // raw fp32 copies are no longer needed
+  for (auto& kv : h->raw) cudaFree(kv.second.p);
+  h->raw.clear();
+  h->finalized = true;
+}
+
+void ensure_time_buffers(lidm_handle* h, int rows) {
+  if (rows <= h->te_rows) return;
+  cudaFree(h->te_tmp); cudaFree(h->te_emb); cudaFree(h->emb_out); cudaFree(h->t_dev);
+  h->te_tmp = h->te_emb = h->emb_out = nullptr; h->t_dev = nullptr; h->te_rows = 0;
+  LIDM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&h->te_tmp), (size_t)rows * h->ted * sizeof(float)));
+  LIDM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&h->te_emb), (size_t)rows * h->ted * sizeof(float)));
+  LIDM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&h->emb_out), (size_t)rows * h->emb_total * sizeof(float)));
+  LIDM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&h->t_dev), (size_t)rows * sizeof(int64_t)));
+  h->te_rows = rows;
+}
+
+// timestep_embedding -> time_embed -> all emb_layers (basic.py:278-296, openaimodel.py:732-733, 262)
+void run_time_embed(lidm_handle* h, const int64_t* t_dev, int rows, cudaStream_t s) {
+  launch_time_embed(t_dev, rows, h->cfg.model_channels, h->te_w0, h->te_b0, h->te_w2, h->te_b2, h->ted, h->te_tmp,
+                    h->te_emb, s);
+  launch_linear_rows(h->te_emb, rows, h->ted, h->emb_w, h->emb_b, h->emb_total, h->emb_out, s);
+}
+
+void require_ready(lidm_handle* h, int B) {
+  if (h == nullptr) throw Error(LIDM_ERR_INVALID, "null handle");
+  if (!h->finalized) throw Error(LIDM_ERR_STATE, "lidm_finalize_weights has not been called");
+  if (B <= 0) throw Error(LIDM_ERR_INVALID, "batch size must be positive");
+}
+
+template <class F>
+int guarded(lidm_handle* h, F&& f) {
+  try {
+    f();
+    return LIDM_OK;
+  } catch (const Error& e) {
+    (h ? h->error : tls_error) = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    (h ? h->error : tls_error) = e.what();
+    return LIDM_ERR_INVALID;
+  }
+}
+
+__global__ void qkv_legacy_to_internal_kernel(const float* __restrict__ qkv, int B, int heads, int T, float scale,
+                                              bf16* __restrict__ qk, bf16* __restrict__ vt) {
+  // qkv: (B, heads*96, T) with channel = head*96 + part*32 + c
+  const int C = heads * 32;
+  const int64_t total = (int64_t)B * heads * 96 * T;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int t = (int)(i % T);
+    int64_t r = i / T;
+    const int chn = (int)(r % (heads * 96));
+    const int b = (int)(r / (heads * 96));
+    const int hd = chn / 96, part = (chn % 96) / 32, c = chn % 32;
+    const float v = qkv[i];
+    if (part < 2) qk[((size_t)b * T + t) * (2 * C) + part * C + hd * 32 + c] = __float2bfloat16(v * scale);
+    else vt[((size_t)b * C + hd * 32 + c) * T + t] = __float2bfloat16(v);
+  }
+}
+
+struct TmpBufs {
+  std::vector<void*> p;
+  template <class T> T* get(size_t n) {
+    void* q = nullptr;
+    LIDM_CUDA_CHECK(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
+    p.push_back(q);
+    return reinterpret_cast<T*>(q);
+  }
+  ~TmpBufs() { for (void* q : p) cudaFree(q); }
+};
+
+}  // namespace
+}  // namespace lidm
+
+// =========================================================================================================
+// C ABI
+// =========================================================================================================
+extern "C" {
+
+const char* lidm_last_error(const lidm_handle* h) { return h ? h->error.c_str() : tls_error.c_str(); }
+
+int64_t lidm_launch_count(void) { return g_launch_count.load(); }
+
+int lidm_create(const lidm_config* cfg, lidm_handle** out) {
+  return guarded(nullptr, [&] {
+    LIDM_REQUIRE(cfg != nullptr && out != nullptr, "null argument");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      throw Error(LIDM_ERR_CUDA, "no CUDA device available: this library has no CPU fallback");
+    cudaDeviceProp prop;
+    int dev = 0;
+    LIDM_CUDA_CHECK(cudaGetDevice(&dev));
+    LIDM_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) throw Error(LIDM_ERR_CUDA, std::string("sm_100a (B200) required, found ") + prop.name);
+    LIDM_REQUIRE(cfg->n_channel_mult >= 1 && cfg->n_channel_mult <= LIDM_MAX_LEVELS, "n_channel_mult");
+    LIDM_REQUIRE(cfg->ae_n_ch_mult >= 1 && cfg->ae_n_ch_mult <= LIDM_MAX_LEVELS, "ae_n_ch_mult");
+    LIDM_REQUIRE(cfg->model_channels % 64 == 0, "model_channels must be a multiple of 64");
+    LIDM_REQUIRE(cfg->num_head_channels == 32, "num_head_channels must be 32");
+    LIDM_REQUIRE(cfg->ae_ch % 64 == 0, "ae ch must be a multiple of 64");
+    LIDM_REQUIRE(cfg->latent_h > 0 && cfg->latent_w > 0 && cfg->scale_factor != 0.f, "latent shape / scale_factor");
+    const int down = 1 << (cfg->n_channel_mult - 1);
+    LIDM_REQUIRE(cfg->latent_h % down == 0 && cfg->latent_w % down == 0, "latent not divisible by U-Net downsampling");
+    const int lw = cfg->latent_w / down, lh = cfg->latent_h / down;
+    LIDM_REQUIRE((lw >= 128 ? lw % 128 == 0 : (128 % lw == 0 && lh % (128 / lw) == 0)),
+                 "coarsest U-Net level must tile into 128-pixel patches");
+    lidm_handle* h = new lidm_handle();
+    h->cfg = *cfg;
+    *out = h;
+  });
+}
+
+void lidm_destroy(lidm_handle* h) { delete h; }
+
+int lidm_load_weight(lidm_handle* h, const char* name, const float* data, int32_t ndim, const int64_t* shape) {
+  return guarded(h, [&] {
+    LIDM_REQUIRE(h != nullptr && name != nullptr && data != nullptr && ndim >= 0 && ndim <= 8, "bad argument");
+    if (h->finalized) throw Error(LIDM_ERR_STATE, "weights already finalized");
+    DevTensor t;
+    t.numel = 1;
+    for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); t.numel *= shape[i]; }
+    LIDM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&t.p), std::max<int64_t>(t.numel, 1) * sizeof(float)));
+    cudaError_t e = cudaMemcpy(t.p, data, t.numel * sizeof(float), cudaMemcpyDefault);
+    if (e != cudaSuccess) { cudaFree(t.p); LIDM_CUDA_CHECK(e); }
+    auto it = h->raw.find(name);
+    if (it != h->raw.end()) { cudaFree(it->second.p); h->raw.erase(it); }
+    h->raw.emplace(name, std::move(t));
+  });
+}
+
+int lidm_finalize_weights(lidm_handle* h, int32_t use_ema) {
+  return guarded(h, [&] {
+    LIDM_REQUIRE(h != nullptr, "null handle");
+    if (h->finalized) throw Error(LIDM_ERR_STATE, "weights already finalized");
+    finalize(h, use_ema != 0);
+  });
+}
+
+int lidm_image_shape(const lidm_handle* h, int32_t* c, int32_t* hh, int32_t* ww) {
+  if (h == nullptr || !h->finalized) return LIDM_ERR_STATE;
+  if (c) *c = h->cfg.ae_use_mask ? 1 : h->cfg.ae_out_ch;
+  if (hh) *hh = h->img_h;
+  if (ww) *ww = h->img_w;
+  return LIDM_OK;
+}
+
+int lidm_unet_forward(lidm_handle* h, const float* x, const int64_t* t, float* eps_out, int32_t B, void* stream) {
+  return guarded(h, [&] {
+    require_ready(h, B);
+    LIDM_REQUIRE(x != nullptr && t != nullptr && eps_out != nullptr, "null tensor");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    Plan* P = get_plan(h, h->unet_plans, B, build_unet_plan_pass);
+    ensure_time_buffers(h, B);
+    run_time_embed(h, t, B, s);
+    P->x = x; P->out = eps_out;
+    P->rowadd_base = h->emb_out; P->rowadd_ld = h->emb_total;
+    P->ddim_x_prev = nullptr; P->ddim_noise = nullptr; P->ddim_pred_x0 = nullptr; P->ddim_coef = nullptr;
+    run_plan(P, s);
+  });
+}
+
+int lidm_ddim_step(const float* x, const float* eps, const float* noise, float a_t, float a_prev, float sigma_t,
+                   float sqrt_one_minus_at, float temperature, float* x_prev, float* pred_x0, int64_t n, void* stream) {
+  return guarded(nullptr, [&] {
+    LIDM_REQUIRE(x != nullptr && eps != nullptr && x_prev != nullptr && n >= 0, "null tensor");
+    if (n == 0) return;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    static thread_local float* coef_dev = nullptr;
+    if (coef_dev == nullptr) LIDM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&coef_dev), 5 * sizeof(float) * 64));
+    static thread_local int slot = 0;
+    slot = (slot + 1) % 64;
+    const float c[5] = {a_t, a_prev, sigma_t, sqrt_one_minus_at, temperature};
+    LIDM_CUDA_CHECK(cudaMemcpyAsync(coef_dev + slot * 5, c, sizeof(c), cudaMemcpyHostToDevice, s));
+    launch_ddim_step(x, eps, noise, coef_dev + slot * 5, x_prev, pred_x0, n, s);
+  });
+}
+
+int lidm_ddim_sample(lidm_handle* h, float* x_inout, const int64_t* timesteps, const float* sched, int32_t n_steps,
+                     const float* noise, float temperature, float* pred_x0_out, int32_t B, void* stream) {
+  return guarded(h, [&] {
+    require_ready(h, B);
+    LIDM_REQUIRE(x_inout != nullptr && timesteps != nullptr && sched != nullptr && n_steps > 0, "null argument");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const lidm_config& cfg = h->cfg;
+    for (int i = 0; i < n_steps; ++i)
+      LIDM_REQUIRE(timesteps[i] >= 0, "negative timestep");
+    Plan* P = get_plan(h, h->unet_plans, B, build_unet_plan_pass);
+    ensure_time_buffers(h, n_steps);
+    const size_t elems = (size_t)B * cfg.in_channels * cfg.latent_h * cfg.latent_w;
+    if (elems > h->xbuf_elems) {
+      cudaFree(h->xa); cudaFree(h->xb); h->xa = h->xb = nullptr; h->xbuf_elems = 0;
+      LIDM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&h->xa), elems * sizeof(float)));
+      LIDM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&h->xb), elems * sizeof(float)));
+      h->xbuf_elems = elems;
+    }
+    if (n_steps > h->coef_rows) {
+      cudaFree(h->coef_dev); h->coef_dev = nullptr; h->coef_rows = 0;
+      LIDM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&h->coef_dev), (size_t)n_steps * 5 * sizeof(float)));
+      h->coef_rows = n_steps;
+    }
+    // loop order: i-th iteration uses index = n_steps-1-i (np.flip(ddim_timesteps), ddim.py:136-143)
+    std::vector<int64_t> t_loop(n_steps);
+    std::vector<float> coef((size_t)n_steps * 5);
+    for (int i = 0; i < n_steps; ++i) {
+      const int index = n_steps - 1 - i;
+      t_loop[i] = timesteps[index];
+      for (int k = 0; k < 4; ++k) coef[(size_t)i * 5 + k] = sched[(size_t)index * 4 + k];
+      coef[(size_t)i * 5 + 4] = temperature;
+    }
+    // pageable -> device copies are staged by the runtime before returning, so the host vectors may go out of scope
+    LIDM_CUDA_CHECK(cudaMemcpyAsync(h->t_dev, t_loop.data(), n_steps * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    LIDM_CUDA_CHECK(cudaMemcpyAsync(h->coef_dev, coef.data(), coef.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+    run_time_embed(h, h->t_dev, n_steps, s);   // all steps' embeddings at once (t is uniform over the batch)
+    LIDM_CUDA_CHECK(cudaMemcpyAsync(h->xa, x_inout, elems * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    float* cur = h->xa;
+    float* nxt = h->xb;
+    for (int i = 0; i < n_steps; ++i) {
+      P->x = cur; P->out = nullptr;
+      P->rowadd_base = h->emb_out + (size_t)i * h->emb_total; P->rowadd_ld = 0;
+      P->ddim_x_prev = nxt;
+      P->ddim_noise = noise ? noise + (size_t)i * elems : nullptr;
+      P->ddim_pred_x0 = (i == n_steps - 1) ? pred_x0_out : nullptr;
+      P->ddim_coef = h->coef_dev + (size_t)i * 5;
+      run_plan(P, s);
+      std::swap(cur, nxt);
+    }
+    LIDM_CUDA_CHECK(cudaMemcpyAsync(x_inout, cur, elems * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  });
+}
+
+int lidm_vq_decode(lidm_handle* h, const float* z, int32_t force_not_quantize, float* img_out, int32_t* idx_out,
+                   int32_t B, void* stream) {
+  return guarded(h, [&] {
+    require_ready(h, B);
+    LIDM_REQUIRE(z != nullptr && img_out != nullptr, "null tensor");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    Plan* P = get_plan(h, h->dec_plans, B, build_dec_plan_pass);
+    P->x = z; P->out = img_out; P->idx_out = idx_out; P->quantize = force_not_quantize ? 0 : 1;
+    run_plan(P, s);
+  });
+}
+
+int lidm_backproject(const float* img, int32_t B, int32_t H, int32_t W, float fov_up_deg, float fov_down_deg,
+                     float depth_min, float depth_max, float depth_scale, int32_t log_scale, int32_t input_is_unit,
+                     float* xyz_out, uint8_t* mask_out, void* stream) {
+  return guarded(nullptr, [&] {
+    LIDM_REQUIRE(img != nullptr && xyz_out != nullptr, "null tensor");
+    launch_backproject(img, B, H, W, fov_up_deg, fov_down_deg, depth_min, depth_max, depth_scale, log_scale, input_is_unit,
+                       xyz_out, mask_out, reinterpret_cast<cudaStream_t>(stream));
+  });
+}
+
+int lidm_op_circular_conv2d(const float* x, int32_t B, int32_t Cin, int32_t H, int32_t W, const float* weight,
+                            const float* bias, int32_t Cout, int32_t kh, int32_t kw, int32_t pad_l, int32_t pad_r,
+                            int32_t pad_t, int32_t pad_b, int32_t stride, const float* residual, float* out,
+                            void* stream) {
+  return guarded(nullptr, [&] {
+    LIDM_REQUIRE(x && weight && out && B > 0 && Cin > 0 && Cout > 0 && stride >= 1, "bad argument");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int Ho = (H + pad_t + pad_b - kh) / stride + 1, Wo = (W + pad_l + pad_r - kw) / stride + 1;
+    TmpBufs tmp;
+    const int n_alloc = round_n_alloc(Cout);
+    const bool implicit = stride == 1 && Cin % 64 == 0 && Ho == H && Wo == W;
+    const int K = kh * kw * Cin;
+    const int k_alloc = implicit ? K : (K + 63) / 64 * 64;
+    bf16* wp = tmp.get<bf16>((size_t)n_alloc * k_alloc);
+    launch_pack_conv_weight(weight, Cout, Cin, kh, kw, n_alloc, k_alloc, nullptr, nullptr, 1.f, 0, wp, s);
+    GemmB wb; wb.p = wp; wb.n_alloc = n_alloc; wb.ld = k_alloc;
+    GemmEpilogue ep;
+    ep.bias = bias;
+    ep.out_f32_nchw = out;
+    View rv;
+    if (residual != nullptr) {
+      rv.B = B; rv.H = Ho; rv.W = Wo; rv.C = Cout; rv.ld = (Cout + 7) / 8 * 8;
+      rv.p = tmp.get<bf16>((size_t)B * Ho * Wo * rv.ld);
+      launch_f32_to_nhwc_bf16(residual, B, Cout, Ho * Wo, rv, s);
+      ep.residual = rv;
+    }
+    if (implicit) {
+      View a; a.B = B; a.H = H; a.W = W; a.C = Cin; a.ld = Cin; a.hl = pad_l; a.hr = pad_r;
+      a.p = tmp.get<bf16>((size_t)B * H * a.Wp() * Cin);
+      launch_f32_to_nhwc_bf16(x, B, Cin, H * W, a, s);
+      launch_conv_gemm(a, taps_rect(kh, kw, pad_l, pad_t), wb, Cout, ep, s);
+    } else {
+      bf16* col = tmp.get<bf16>((size_t)B * Ho * Wo * k_alloc);
+      if (Cin % 8 == 0 && k_alloc == K) {
+        View a; a.B = B; a.H = H; a.W = W; a.C = Cin; a.ld = Cin;
+        a.p = tmp.get<bf16>((size_t)B * H * W * Cin);
+        launch_f32_to_nhwc_bf16(x, B, Cin, H * W, a, s);
+        launch_im2col_nhwc(a, kh, kw, stride, pad_l, pad_t, Ho, Wo, col, s);
+      } else {
+        LIDM_REQUIRE(stride == 1 && Ho == H && Wo == W, "small-channel im2col path supports stride 1 'same' convs only");
+        launch_im2col_nchw_f32(x, B, Cin, H, W, kh, kw, pad_l, pad_t, col, k_alloc, s);
+      }
+      View a; a.p = col; a.B = B; a.H = Ho; a.W = Wo; a.C = k_alloc; a.ld = k_alloc;
+      launch_conv_gemm(a, taps_1x1(), wb, Cout, ep, s);
+    }
+    LIDM_CUDA_CHECK(cudaStreamSynchronize(s));
+  });
+}
+
+int lidm_op_groupnorm(const float* x, int32_t B, int32_t C, int32_t H, int32_t W, const float* gamma,
+                      const float* beta, float eps, int32_t groups, int32_t silu, float* out, void* stream) {
+  return guarded(nullptr, [&] {
+    LIDM_REQUIRE(x && gamma && beta && out && B > 0, "bad argument");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    TmpBufs tmp;
+    View a; a.B = B; a.H = H; a.W = W; a.C = C; a.ld = C;
+    a.p = tmp.get<bf16>((size_t)B * H * W * C);
+    View y = a; y.hl = 1; y.hr = 2;
+    y.p = tmp.get<bf16>((size_t)B * H * y.Wp() * C);
+    float* partials = tmp.get<float>((size_t)B * groups * 2 * GN_MAX_CHUNKS);
+    launch_f32_to_nhwc_bf16(x, B, C, H * W, a, s);
+    launch_groupnorm(a, y, gamma, beta, eps, groups, silu != 0, partials, s);
+    launch_nhwc_bf16_to_f32_nchw(y, out, s);
+    LIDM_CUDA_CHECK(cudaStreamSynchronize(s));
+  });
+}
+
+int lidm_op_qkv_attention_legacy(const float* qkv, int32_t B, int32_t heads, int32_t T, float* out, void* stream) {
+  return guarded(nullptr, [&] {
+    LIDM_REQUIRE(qkv && out && B > 0 && heads > 0 && T > 0 && T % 128 == 0, "bad argument (T must be a multiple of 128)");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const int C = heads * 32;
+    TmpBufs tmp;
+    bf16* qk = tmp.get<bf16>((size_t)B * T * 2 * C);
+    bf16* vt = tmp.get<bf16>((size_t)B * C * T);
+    const float scale = 1.0f / std::sqrt(std::sqrt(32.0f));
+    qkv_legacy_to_internal_kernel<<<148 * 8, 256, 0, s>>>(qkv, B, heads, T, scale, qk, vt);
+    LIDM_CUDA_CHECK(cudaGetLastError());
+    View o; o.B = B; o.H = T / 128; o.W = 128; o.C = C; o.ld = C;
+    o.p = tmp.get<bf16>((size_t)B * T * C);
+    launch_attention_d32(qk, vt, o, B, T, heads, s);
+    launch_nhwc_bf16_to_f32_nchw(o, out, s);
+    LIDM_CUDA_CHECK(cudaStreamSynchronize(s));
+  });
+}
+
+}  // extern "C"

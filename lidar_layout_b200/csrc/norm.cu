@@ -1,0 +1,170 @@
+// GroupNorm (+ optional SiLU) over channels-last bf16 activations, fp32 statistics.
+// Replaces GroupNorm32 / normalization() + nn.SiLU (reference lidm/modules/basic.py:324-341, eps 1e-5) in the
+// U-Net and Normalize() + nonlinearity() (reference lidm/modules/diffusion/model_lidm.py:35-41, eps 1e-6) in the
+// decoder.  HBM-bound: pass 1 reads x once (per-CTA partial sums, combined in a fixed order => deterministic),
+// pass 2 reads x once more and writes y (with its circular halo columns) once.  Works on concatenated views
+// (ld > C), so the U-Net's skip `torch.cat` (openaimodel.py:745) is never materialised separately.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace lidm {
+
+namespace {
+
+// Each thread owns one 8-channel (16-byte) column `cv` of the tensor and walks pixels with a fixed stride.
+// cpg = channels per group.  If cpg >= 8 the 8 channels fall in one group, otherwise in 8/cpg groups.
+template <int NSUB>  // number of groups inside one 8-channel vector: 1, 2 or 4
+__global__ void gn_stats_kernel(const bf16* __restrict__ x, int HW_phys_rows /*unused*/, int H, int W, int hl, int Wp,
+                                int ld, int C, int cpg, int groups, int pix_per_cta, float* __restrict__ partials,
+                                int nchunks) {
+  extern __shared__ float sh[];  // [groups][2]
+  const int b = blockIdx.y;
+  const int chunk = blockIdx.x;
+  const int vec_per_pix = C >> 3;
+  const int cv = threadIdx.x % vec_per_pix;
+  const int prow = threadIdx.x / vec_per_pix;
+  const int pstride = blockDim.x / vec_per_pix;
+  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  float s[NSUB], q[NSUB];
+#pragma unroll
+  for (int i = 0; i < NSUB; ++i) { s[i] = 0.f; q[i] = 0.f; }
+  const int HW = H * W;
+  const int p0 = chunk * pix_per_cta;
+  const int p1 = min(HW, p0 + pix_per_cta);
+  if (prow < pstride) {
+    for (int pix = p0 + prow; pix < p1; pix += pstride) {
+      const int h = pix / W, w = pix - h * W;
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + ((size_t)(b * H + h) * Wp + (w + hl)) * ld) + cv);
+      const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16(uu[i]);
+        if constexpr (NSUB == 8) {  // generic: one accumulator per channel, group resolved at the end
+          s[2 * i] += f.x; q[2 * i] += f.x * f.x;
+          s[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
+        } else {
+          constexpr int per = 8 / NSUB;  // channels per sub-group
+          const int sub = (2 * i) / per;
+          s[sub] += f.x + f.y;
+          q[sub] += f.x * f.x + f.y * f.y;
+        }
+      }
+    }
+  }
+  const int g0 = (cv * 8) / cpg;
+#pragma unroll
+  for (int i = 0; i < NSUB; ++i) {
+    const int g = (NSUB == 8) ? (cv * 8 + i) / cpg : g0 + i;
+    atomicAdd(&sh[g * 2 + 0], s[i]);
+    atomicAdd(&sh[g * 2 + 1], q[i]);
+  }
+  __syncthreads();
+  float* out = partials + ((size_t)b * nchunks + chunk) * groups * 2;
+  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) out[i] = sh[i];
+}
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.f + __expf(-v)); }
+
+__global__ void gn_apply_kernel(const bf16* __restrict__ x, int H, int W, int xhl, int xWp, int xld, bf16* __restrict__ y,
+                                int yhl, int yhr, int yWp, int yld, int C, int cpg, int groups,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
+                                const float* __restrict__ partials, int nchunks, int pix_per_cta) {
+  extern __shared__ float sh[];  // mean[groups], rstd[groups]
+  const int b = blockIdx.y;
+  const int HW = H * W;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float s = 0.f, q = 0.f;
+    const float* pp = partials + (size_t)b * nchunks * groups * 2 + g * 2;
+    for (int c = 0; c < nchunks; ++c) { s += pp[(size_t)c * groups * 2]; q += pp[(size_t)c * groups * 2 + 1]; }
+    const float n = (float)HW * (float)cpg;
+    const float mean = s / n;
+    const float var = fmaxf(q / n - mean * mean, 0.f);
+    sh[g] = mean;
+    sh[groups + g] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  const int vec_per_pix = C >> 3;
+  const int cv = threadIdx.x % vec_per_pix;
+  const int prow = threadIdx.x / vec_per_pix;
+  const int pstride = blockDim.x / vec_per_pix;
+  if (prow >= pstride) return;
+  float sc[8], sf[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cv * 8 + j;
+    const int g = c / cpg;
+    const float ga = __ldg(gamma + c) * sh[groups + g];
+    sc[j] = ga;
+    sf[j] = __ldg(beta + c) - sh[g] * ga;
+  }
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(HW, p0 + pix_per_cta);
+  for (int pix = p0 + prow; pix < p1; pix += pstride) {
+    const int h = pix / W, w = pix - h * W;
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + ((size_t)(b * H + h) * xWp + (w + xhl)) * xld) + cv);
+    const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+    uint32_t oo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = unpack_bf16(uu[i]);
+      float a = f.x * sc[2 * i] + sf[2 * i];
+      float c = f.y * sc[2 * i + 1] + sf[2 * i + 1];
+      if (silu) { a = silu_f(a); c = silu_f(c); }
+      oo[i] = pack_bf16(a, c);
+    }
+    const uint4 o = make_uint4(oo[0], oo[1], oo[2], oo[3]);
+    const size_t rowbase = (size_t)(b * H + h) * yWp;
+    reinterpret_cast<uint4*>(y + (rowbase + w + yhl) * yld)[cv] = o;
+    if (w < yhr) reinterpret_cast<uint4*>(y + (rowbase + W + yhl + w) * yld)[cv] = o;
+    if (w >= W - yhl) reinterpret_cast<uint4*>(y + (rowbase + (w - (W - yhl))) * yld)[cv] = o;
+  }
+}
+
+}  // namespace
+
+void launch_groupnorm(const View& x, const View& y, const float* gamma, const float* beta, float eps, int groups,
+                      bool silu, float* partials, cudaStream_t s) {
+  const int C = x.C;
+  LIDM_REQUIRE(C % 8 == 0 && C % groups == 0, "C must be a multiple of 8 and of the group count");
+  LIDM_REQUIRE(y.C == C && y.B == x.B && y.H == x.H && y.W == x.W, "GroupNorm in/out shape mismatch");
+  LIDM_REQUIRE(x.ld % 8 == 0 && y.ld % 8 == 0, "ld alignment");
+  const int cpg = C / groups;
+  const bool regular = cpg >= 8 ? (cpg % 8 == 0) : (8 % cpg == 0 && cpg >= 2);
+  const int vec = C / 8;
+  int threads = (256 % vec == 0) ? 256 : ((384 % vec == 0) ? 384 : 0);
+  if (threads == 0) { LIDM_REQUIRE(vec <= 1024, "C too large"); threads = vec; }
+  const int HW = x.H * x.W;
+  // enough CTAs to fill the machine, at most GN_MAX_CHUNKS partials per sample
+  int nchunks = (148 * 8 + x.B - 1) / x.B;
+  if (nchunks > GN_MAX_CHUNKS) nchunks = GN_MAX_CHUNKS;
+  const int pstride = threads / vec;
+  int max_chunks = (HW + pstride - 1) / pstride;
+  if (nchunks > max_chunks) nchunks = max_chunks;
+  if (nchunks < 1) nchunks = 1;
+  const int pix_per_cta = (HW + nchunks - 1) / nchunks;
+  nchunks = (HW + pix_per_cta - 1) / pix_per_cta;
+  dim3 grid(nchunks, x.B);
+  const size_t shbytes = groups * 2 * sizeof(float);
+  const int nsub = !regular ? 8 : (cpg >= 8 ? 1 : 8 / cpg);
+  if (nsub == 8)
+    gn_stats_kernel<8><<<grid, threads, shbytes, s>>>(x.p, 0, x.H, x.W, x.hl, x.Wp(), x.ld, C, cpg, groups, pix_per_cta,
+                                                       partials, nchunks);
+  else if (nsub == 1)
+    gn_stats_kernel<1><<<grid, threads, shbytes, s>>>(x.p, 0, x.H, x.W, x.hl, x.Wp(), x.ld, C, cpg, groups, pix_per_cta,
+                                                       partials, nchunks);
+  else if (nsub == 2)
+    gn_stats_kernel<2><<<grid, threads, shbytes, s>>>(x.p, 0, x.H, x.W, x.hl, x.Wp(), x.ld, C, cpg, groups, pix_per_cta,
+                                                       partials, nchunks);
+  else
+    gn_stats_kernel<4><<<grid, threads, shbytes, s>>>(x.p, 0, x.H, x.W, x.hl, x.Wp(), x.ld, C, cpg, groups, pix_per_cta,
+                                                       partials, nchunks);
+  LIDM_CUDA_CHECK(cudaGetLastError());
+  gn_apply_kernel<<<grid, threads, shbytes, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, y.hl, y.hr, y.Wp(), y.ld, C,
+                                                 cpg, groups, gamma, beta, eps, silu ? 1 : 0, partials, nchunks,
+                                                 pix_per_cta);
+  LIDM_CUDA_CHECK(cudaGetLastError());
+  LIDM_COUNT_LAUNCH(2);
+}
+
+}  // namespace lidm

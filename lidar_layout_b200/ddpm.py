@@ -1,0 +1,224 @@
+"""LatentDiffusion with the reference's sampling-side interface (lidm/models/diffusion/ddpm.py), B200-native.
+
+Only what the sampling path touches is mirrored: construction from the reference YAML, load_state_dict,
+ema_scope, apply_model, decode_first_stage, q_sample, sample / p_sample_loop (ancestral DDPM), sample_log, the
+schedule buffers the samplers read, and the attribute chain scripts/sample.py uses
+(`model.model.diffusion_model.image_size`, `.in_channels`, `model.cond_stage_model`).  Training code is out of scope.
+"""
+from __future__ import annotations
+
+from contextlib import contextmanager
+from types import SimpleNamespace
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import ops, schedule
+from .config import LidmConfig, from_reference_dict, from_yaml
+from .engine import Engine
+
+
+def extract_into_tensor(a, t, x_shape):
+    """lidm/modules/basic.py:219-222."""
+    b, *_ = t.shape
+    out = a.gather(-1, t)
+    return out.reshape(b, *((1,) * (len(x_shape) - 1)))
+
+
+class _FirstStage:
+    """Stands in for VQModelInterface on the attribute paths samplers use (`first_stage_model.quantize`)."""
+
+    def __init__(self, owner):
+        self._owner = owner
+
+    def quantize(self, z):
+        raise NotImplementedError("stand-alone quantize() is not exposed; use decode_first_stage")
+
+    def decode(self, h, force_not_quantize=False):
+        return self._owner.engine.vq_decode(h, force_not_quantize)
+
+
+class LatentDiffusion:
+    """Drop-in for the sampling-side API of lidm.models.diffusion.ddpm.LatentDiffusion."""
+
+    def __init__(self, cfg: LidmConfig, device: Optional[torch.device] = None, use_ema: bool = True):
+        self.cfg = cfg
+        self.engine = Engine(cfg, device)
+        self.device = self.engine.device
+        self.use_ema = use_ema
+        self.parameterization = cfg.parameterization
+        if self.parameterization != "eps":
+            raise NotImplementedError("only eps-parameterisation is supported")
+        self.channels = cfg.channels
+        self.image_size = list(cfg.image_size)
+        self.scale_factor = cfg.scale_factor
+        self.cond_stage_model = None
+        self.clip_denoised = False          # LatentDiffusion sets this (ddpm.py:466)
+        self.log_every_t = 100
+        self.v_posterior = 0.0
+        self.first_stage_model = _FirstStage(self)
+        # `model.model.diffusion_model.{image_size,in_channels}` (scripts/sample.py:91-93)
+        self.model = SimpleNamespace(diffusion_model=SimpleNamespace(image_size=list(cfg.unet.image_size),
+                                                                     in_channels=cfg.unet.in_channels),
+                                     conditioning_key=cfg.conditioning_key)
+        self.register_schedule()
+
+    # ---- construction ---------------------------------------------------------------------------------
+    @classmethod
+    def from_config(cls, config, device=None, use_ema=True) -> "LatentDiffusion":
+        """config: path to a reference YAML, or the parsed dict (what OmegaConf.load would give)."""
+        cfg = from_yaml(config) if isinstance(config, str) else from_reference_dict(config)
+        return cls(cfg, device, use_ema)
+
+    def register_schedule(self):
+        """DDPM.register_schedule (ddpm.py:120-160)."""
+        c = self.cfg
+        bufs = schedule.ddpm_buffers(c.beta_schedule, c.timesteps, c.linear_start, c.linear_end,
+                                     v_posterior=self.v_posterior)
+        self.num_timesteps = int(bufs["betas"].shape[0])
+        for k, v in bufs.items():
+            setattr(self, k, v.to(self.device))
+
+    def load_state_dict(self, sd, strict: bool = False):
+        """model.load_state_dict(sd, strict=False) (scripts/sample.py:271).  EMA selection (ema_scope) is folded
+        into the one-time weight packing: with use_ema the `model_ema.*` shadow tensors win where present."""
+        if "state_dict" in sd and not any(k.startswith("model.") for k in sd):
+            sd = sd["state_dict"]
+        self.engine.load_state_dict(sd, use_ema=self.use_ema)
+        return [], []
+
+    def cuda(self, *a, **k):
+        return self
+
+    def eval(self):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    @contextmanager
+    def ema_scope(self, context=None):
+        """DDPM.ema_scope (ddpm.py:174-187): a no-op here, the EMA weights were selected when packing."""
+        yield None
+
+    # ---- per-step hook --------------------------------------------------------------------------------
+    @torch.no_grad()
+    def apply_model(self, x_noisy, t, cond, return_ids=False):
+        """ddpm.py:900-1000 -> DiffusionWrapper.forward (:2313) -> UNetModel.forward, unconditional."""
+        if isinstance(cond, dict):
+            has = any(v is not None and v != [None] for v in cond.values())
+        elif isinstance(cond, (list, tuple)):
+            has = any(v is not None for v in cond)
+        else:
+            has = cond is not None
+        if has:
+            raise NotImplementedError("conditioned sampling is not on the B200 path yet")
+        assert not return_ids
+        return self.engine.unet_forward(x_noisy, t)
+
+    @torch.no_grad()
+    def decode_first_stage(self, z, predict_cids=False, force_not_quantize=False):
+        """ddpm.py:717-775 -> VQModelInterface.decode (autoencoder.py:290-302); 1/scale_factor applied in-kernel."""
+        if predict_cids:
+            raise NotImplementedError("predict_cids is not used by the sampling path")
+        return self.engine.vq_decode(z, force_not_quantize=force_not_quantize)
+
+    def q_sample(self, x_start, t, noise=None):
+        """DDPM.q_sample (ddpm.py:306-309)."""
+        noise = torch.randn_like(x_start) if noise is None else noise
+        return (extract_into_tensor(self.sqrt_alphas_cumprod, t, x_start.shape) * x_start +
+                extract_into_tensor(self.sqrt_one_minus_alphas_cumprod, t, x_start.shape) * noise)
+
+    # ---- ancestral DDPM sampling (scripts/sample.py --vanilla) ------------------------------------------
+    def predict_start_from_noise(self, x_t, t, noise):
+        """ddpm.py:219-223."""
+        return (extract_into_tensor(self.sqrt_recip_alphas_cumprod, t, x_t.shape) * x_t -
+                extract_into_tensor(self.sqrt_recipm1_alphas_cumprod, t, x_t.shape) * noise)
+
+    def q_posterior(self, x_start, x_t, t):
+        """ddpm.py:225-232."""
+        mean = (extract_into_tensor(self.posterior_mean_coef1, t, x_t.shape) * x_start +
+                extract_into_tensor(self.posterior_mean_coef2, t, x_t.shape) * x_t)
+        var = extract_into_tensor(self.posterior_variance, t, x_t.shape)
+        logvar = extract_into_tensor(self.posterior_log_variance_clipped, t, x_t.shape)
+        return mean, var, logvar
+
+    @torch.no_grad()
+    def p_mean_variance(self, x, c, t, clip_denoised: bool, quantize_denoised=False, return_x0=False):
+        """ddpm.py:1059-1088 (eps parameterisation)."""
+        model_out = self.apply_model(x, t, c)
+        x_recon = self.predict_start_from_noise(x, t=t, noise=model_out)
+        if clip_denoised:
+            x_recon.clamp_(-1., 1.)
+        if quantize_denoised:
+            raise NotImplementedError("quantize_denoised")
+        mean, var, logvar = self.q_posterior(x_start=x_recon, x_t=x, t=t)
+        return (mean, var, logvar, x_recon) if return_x0 else (mean, var, logvar)
+
+    @torch.no_grad()
+    def p_sample(self, x, c, t, clip_denoised=False, repeat_noise=False, return_x0=False, temperature=1.,
+                 noise_dropout=0., quantize_denoised=False):
+        """ddpm.py:1090-1119."""
+        b = x.shape[0]
+        outputs = self.p_mean_variance(x=x, c=c, t=t, clip_denoised=clip_denoised, return_x0=return_x0,
+                                       quantize_denoised=quantize_denoised)
+        mean, _, logvar = outputs[:3]
+        noise = torch.randn(x.shape, device=x.device) * temperature
+        if noise_dropout > 0.:
+            noise = torch.nn.functional.dropout(noise, p=noise_dropout)
+        nonzero_mask = (1 - (t == 0).float()).reshape(b, *((1,) * (len(x.shape) - 1)))
+        out = mean + nonzero_mask * (0.5 * logvar).exp() * noise
+        return (out, outputs[3]) if return_x0 else out
+
+    @torch.no_grad()
+    def p_sample_loop(self, cond, shape, return_intermediates=False, x_T=None, verbose=True, callback=None,
+                      timesteps=None, quantize_denoised=False, mask=None, x0=None, img_callback=None, start_T=None,
+                      log_every_t=None):
+        """ddpm.py:1177-1226."""
+        log_every_t = log_every_t or self.log_every_t
+        b = shape[0]
+        img = torch.randn(shape, device=self.device) if x_T is None else x_T
+        intermediates = [img]
+        timesteps = self.num_timesteps if timesteps is None else timesteps
+        if start_T is not None:
+            timesteps = min(timesteps, start_T)
+        if mask is not None:
+            assert x0 is not None and x0.shape[2:3] == mask.shape[2:3]
+        for i in reversed(range(0, timesteps)):
+            ts = torch.full((b,), i, device=self.device, dtype=torch.long)
+            img = self.p_sample(img, cond, ts, clip_denoised=self.clip_denoised, quantize_denoised=quantize_denoised)
+            if mask is not None:
+                img_orig = self.q_sample(x0, ts)
+                img = img_orig * mask + (1. - mask) * img
+            if i % log_every_t == 0 or i == timesteps - 1:
+                intermediates.append(img)
+            if callback: callback(i)
+            if img_callback: img_callback(img, i)
+        return (img, intermediates) if return_intermediates else img
+
+    @torch.no_grad()
+    def sample(self, cond, batch_size=16, return_intermediates=False, x_T=None, verbose=True, timesteps=None,
+               quantize_denoised=False, mask=None, x0=None, shape=None, **kwargs):
+        """ddpm.py:1228-1244."""
+        if shape is None:
+            shape = (batch_size, self.channels, *self.image_size)
+        return self.p_sample_loop(cond, shape, return_intermediates=return_intermediates, x_T=x_T, verbose=verbose,
+                                  timesteps=timesteps, quantize_denoised=quantize_denoised, mask=mask, x0=x0)
+
+    @torch.no_grad()
+    def sample_log(self, cond, batch_size, ddim, ddim_steps, **kwargs):
+        """ddpm.py:1246-1258."""
+        if ddim:
+            from .ddim import DDIMSampler
+            ddim_sampler = DDIMSampler(self)
+            shape = (self.channels, *self.image_size)
+            return ddim_sampler.sample(ddim_steps, batch_size, shape, cond, verbose=False, **kwargs)
+        return self.sample(cond=cond, batch_size=batch_size, return_intermediates=True, **kwargs)
+
+
+def range_images_to_points(x, dataset_cfg):
+    """custom_to_pcd for a whole batch on the device (scripts/sample.py:29-35): x (B,1,H,W) in [-1,1] ->
+    xyz (B,3,H,W) fp32 with -1 where masked, mask (B,H,W) uint8."""
+    return ops.backproject(x, dataset_cfg.fov, dataset_cfg.depth_range, dataset_cfg.depth_scale,
+                           dataset_cfg.log_scale, return_mask=True)

@@ -1,0 +1,91 @@
+"""Operator-level entry points (same kernels the model uses), torch CUDA tensors in / out.
+Each mirrors one reference primitive; see include/lidm_b200.h for the file:line citations."""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from .engine import _f32c, _stream_ptr
+
+
+def circular_conv2d(x, weight, bias=None, padding: Optional[Sequence[int]] = None, stride: int = 1, residual=None):
+    """CircularConv2d.forward (reference lidm/modules/basic.py:52-59).  padding = (left, right, top, bottom)."""
+    x, weight = _f32c(x, "x"), _f32c(weight, "weight")
+    B, Cin, H, W = x.shape
+    Cout, Cin2, kh, kw = weight.shape
+    assert Cin == Cin2
+    pl, pr, pt, pb = padding if padding is not None else (0, 0, 0, 0)
+    Ho = (H + pt + pb - kh) // stride + 1
+    Wo = (W + pl + pr - kw) // stride + 1
+    out = torch.empty((B, Cout, Ho, Wo), dtype=torch.float32, device=x.device)
+    b = _f32c(bias, "bias") if bias is not None else None
+    r = _f32c(residual, "residual") if residual is not None else None
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.lidm_op_circular_conv2d(x.data_ptr(), B, Cin, H, W, weight.data_ptr(),
+                                               b.data_ptr() if b is not None else None, Cout, kh, kw, pl, pr, pt, pb,
+                                               stride, r.data_ptr() if r is not None else None, out.data_ptr(),
+                                               _stream_ptr(x.device)))
+    return out
+
+
+def group_norm(x, gamma, beta, eps=1e-5, groups=32, silu=False):
+    """GroupNorm32 (+ SiLU) (reference lidm/modules/basic.py:339-341)."""
+    x, gamma, beta = _f32c(x, "x"), _f32c(gamma, "gamma"), _f32c(beta, "beta")
+    B, C, H, W = x.shape
+    out = torch.empty_like(x)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.lidm_op_groupnorm(x.data_ptr(), B, C, H, W, gamma.data_ptr(), beta.data_ptr(), float(eps),
+                                         groups, int(silu), out.data_ptr(), _stream_ptr(x.device)))
+    return out
+
+
+def qkv_attention_legacy(qkv, n_heads):
+    """QKVAttentionLegacy.forward (reference lidm/modules/diffusion/openaimodel.py:358-374), head dim 32."""
+    qkv = _f32c(qkv, "qkv")
+    B, width, T = qkv.shape
+    assert width == n_heads * 96, "head dim must be 32"
+    out = torch.empty((B, n_heads * 32, T), dtype=torch.float32, device=qkv.device)
+    lib = _lib.load()
+    with torch.cuda.device(qkv.device):
+        _lib.check(lib.lidm_op_qkv_attention_legacy(qkv.data_ptr(), B, n_heads, T, out.data_ptr(),
+                                                    _stream_ptr(qkv.device)))
+    return out
+
+
+def ddim_step(x, e_t, coef, noise=None, temperature=1.0):
+    """p_sample_ddim update (reference lidm/models/diffusion/ddim.py:191-206).  coef = (a_t, a_prev, sigma_t,
+    sqrt_one_minus_at).  Returns (x_prev, pred_x0)."""
+    x, e_t = _f32c(x, "x"), _f32c(e_t, "e_t")
+    nz = _f32c(noise, "noise") if noise is not None else None
+    x_prev, pred_x0 = torch.empty_like(x), torch.empty_like(x)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.lidm_ddim_step(x.data_ptr(), e_t.data_ptr(), nz.data_ptr() if nz is not None else None,
+                                      float(coef[0]), float(coef[1]), float(coef[2]), float(coef[3]),
+                                      float(temperature), x_prev.data_ptr(), pred_x0.data_ptr(), x.numel(),
+                                      _stream_ptr(x.device)))
+    return x_prev, pred_x0
+
+
+def backproject(img, fov, depth_range, depth_scale, log_scale=True, return_mask=True, input_is_unit=False):
+    """range2xyz on the device: img (B,H,W) or (B,1,H,W) fp32 in [-1,1] -> xyz (B,3,H,W) fp32 (-1 where masked),
+    mask (B,H,W) uint8 (reference lidm/utils/lidar_utils.py:175-204 + scripts/sample.py:29-35)."""
+    img = _f32c(img, "img")
+    if img.dim() == 4:
+        assert img.shape[1] == 1
+        img = img[:, 0]
+    img = img.contiguous()
+    B, H, W = img.shape
+    xyz = torch.empty((B, 3, H, W), dtype=torch.float32, device=img.device)
+    mask = torch.empty((B, H, W), dtype=torch.uint8, device=img.device) if return_mask else None
+    lib = _lib.load()
+    with torch.cuda.device(img.device):
+        _lib.check(lib.lidm_backproject(img.data_ptr(), B, H, W, float(fov[0]), float(fov[1]), float(depth_range[0]),
+                                        float(depth_range[1]), float(depth_scale), int(bool(log_scale)),
+                                        int(bool(input_is_unit)), xyz.data_ptr(), mask.data_ptr() if mask is not None else None,
+                                        _stream_ptr(img.device)))
+    return (xyz, mask) if return_mask else xyz
