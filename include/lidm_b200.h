@@ -122,6 +122,12 @@ int lidm_op_qkv_attention_legacy(const float* qkv, int32_t B, int32_t heads, int
 /* Number of kernels this library has launched so far in the process (bench.py's gpu_launches). */
 int64_t lidm_launch_count(void);
 
+/* Per-op CUDA-event profiler for bench.py's roofline line.  Between begin and end every op of a model-level call
+ * is bracketed by events on the launching stream.  Arrays of 4: {conv-gemm, groupnorm, attention, other};
+ * ms = summed device time, flops / bytes = summed ALGORITHMIC work, launches = kernels launched. */
+int lidm_profile_begin(void);
+int lidm_profile_end(double* ms, double* flops, double* bytes, int64_t* launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,7 +40,7 @@ EXPORTS = [
     "lidm_last_error", "lidm_create", "lidm_destroy", "lidm_load_weight", "lidm_finalize_weights",
     "lidm_unet_forward", "lidm_ddim_step", "lidm_ddim_sample", "lidm_vq_decode", "lidm_image_shape",
     "lidm_backproject", "lidm_op_circular_conv2d", "lidm_op_groupnorm", "lidm_op_qkv_attention_legacy",
-    "lidm_launch_count",
+    "lidm_launch_count", "lidm_profile_begin", "lidm_profile_end",
 ]
 
 _lib = None
@@ -79,6 +79,9 @@ def load() -> ctypes.CDLL:
     lib.lidm_op_qkv_attention_legacy.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]
     lib.lidm_launch_count.restype = c_int64
     lib.lidm_launch_count.argtypes = []
+    lib.lidm_profile_begin.argtypes = []
+    lib.lidm_profile_end.argtypes = [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(ctypes.c_double),
+                                     POINTER(c_int64)]
     _lib = lib
     return lib
 
@@ -91,3 +94,16 @@ def check(code: int, handle=None):
 
 def launch_count() -> int:
     return int(load().lidm_launch_count())
+
+
+def profile_begin():
+    check(load().lidm_profile_begin())
+
+
+def profile_end():
+    """-> dict category -> dict(ms, flops, bytes, launches)."""
+    arr = lambda t: (t * 4)()
+    ms, fl, by, ln = arr(ctypes.c_double), arr(ctypes.c_double), arr(ctypes.c_double), arr(c_int64)
+    check(load().lidm_profile_end(ms, fl, by, ln))
+    names = ["conv_gemm", "groupnorm", "attention", "other"]
+    return {n: dict(ms=ms[i], flops=fl[i], bytes=by[i], launches=int(ln[i])) for i, n in enumerate(names)}

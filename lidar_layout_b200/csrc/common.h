@@ -16,6 +16,10 @@ typedef __nv_bfloat16 bf16;
 extern std::atomic<int64_t> g_launch_count;
 #define LIDM_COUNT_LAUNCH(n) (::lidm::g_launch_count.fetch_add((n), std::memory_order_relaxed))
 
+// Optional per-launch CUDA-event profiler (bench.py's roofline numbers): categories 0 conv-gemm, 1 groupnorm,
+// 2 attention, 3 other.  Off by default; zero cost when off.
+enum ProfCat { PROF_GEMM = 0, PROF_NORM = 1, PROF_ATTN = 2, PROF_OTHER = 3, PROF_NCAT = 4 };
+
 struct Error : std::runtime_error {
   int code;
   Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}

@@ -26,7 +26,22 @@ namespace {
 
 thread_local std::string tls_error;
 
-typedef std::function<void(cudaStream_t)> Op;
+struct Op {
+  std::function<void(cudaStream_t)> fn;
+  int cat;
+  double flops, bytes;
+};
+
+// ---- optional per-op CUDA-event profiler (bench.py roofline) ----
+struct ProfState {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;            // pairs
+  std::vector<int> cat;
+  double flops[PROF_NCAT] = {0, 0, 0, 0}, bytes[PROF_NCAT] = {0, 0, 0, 0};
+  int64_t launches[PROF_NCAT] = {0, 0, 0, 0};
+} g_prof;
+
+double gemm_flops(const View& a, int ntaps, int N) { return 2.0 * a.B * a.H * a.W * (double)N * ntaps * a.C; }
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -265,7 +280,9 @@ struct Builder {
     return reinterpret_cast<T*>(P->arena + buf->off);
   }
   void release(const Buf& b) { ap.release(b.off, b.bytes); }
-  void op(Op f) { if (!dry) P->ops.push_back(std::move(f)); }
+  void op(std::function<void(cudaStream_t)> f, int cat = PROF_OTHER, double flops = 0, double bytes = 0) {
+    if (!dry) P->ops.push_back(Op{std::move(f), cat, flops, bytes});
+  }
 
   static View chan_slice(const View& v, int c0, int C) {
     View s = v;
@@ -277,11 +294,12 @@ struct Builder {
   void gemm(const View& a, const ConvTaps& taps, const ConvW& w, const GemmEpilogue& ep) {
     GemmB b; b.p = w.w; b.n_alloc = w.n_alloc; b.ld = w.k_alloc;
     const int N = w.cout;
-    op([=](cudaStream_t s) { launch_conv_gemm(a, taps, b, N, ep, s); });
+    op([=](cudaStream_t s) { launch_conv_gemm(a, taps, b, N, ep, s); }, PROF_GEMM, gemm_flops(a, taps.n, N));
   }
   void groupnorm(const View& x, const View& y, const NormW& n, float eps, bool silu) {
     Plan* P_ = P;
-    op([=](cudaStream_t s) { launch_groupnorm(x, y, n.gamma, n.beta, eps, 32, silu, P_->gn_partials, s); });
+    op([=](cudaStream_t s) { launch_groupnorm(x, y, n.gamma, n.beta, eps, 32, silu, P_->gn_partials, s); }, PROF_NORM, 0,
+       4.0 * x.B * x.H * x.W * x.C);
   }
 
   // ResBlock._forward (openaimodel.py:256-276) / ResnetBlock.forward (model_lidm.py:127-147, temb None)
@@ -303,7 +321,7 @@ struct Builder {
         GemmEpilogue e = ep;
         if (emb_off >= 0) { e.rowadd = P_->rowadd_base + emb_off; e.rowadd_ld = P_->rowadd_ld; }
         launch_conv_gemm(g1, taps, b, N, e, s);
-      });
+      }, PROF_GEMM, gemm_flops(g1, taps.n, N));
     }
     release(bg1);
     View g2 = act(B, H, W, r.cout, pl, pr, &bg2);
@@ -348,7 +366,8 @@ struct Builder {
     release(bg);
     View ao = act(B, H, W, C, 0, 0, &ba);
     const int heads = a.heads;
-    op([=](cudaStream_t s) { launch_attention_d32(qk.p, vt, ao, B, T, heads, s); });
+    op([=](cudaStream_t s) { launch_attention_d32(qk.p, vt, ao, B, T, heads, s); }, PROF_ATTN,
+       4.0 * B * heads * (double)T * T * 32);
     release(bqk);
     release(bvt);
     {
@@ -384,7 +403,7 @@ struct Builder {
       GemmB kb; kb.p = qk.p + C; kb.n_alloc = T; kb.ld = 2 * C; kb.batch_stride = (int64_t)T * 2 * C;
       GemmEpilogue ep;
       ep.out_f32_nhwc = S;
-      op([=](cudaStream_t s) { launch_conv_gemm(q, taps_1x1(), kb, T, ep, s); });
+      op([=](cudaStream_t s) { launch_conv_gemm(q, taps_1x1(), kb, T, ep, s); }, PROF_GEMM, gemm_flops(q, 1, T));
     }
     bf16* Pm = raw<bf16>((size_t)B * T * T, &bp);
     op([=](cudaStream_t s) { launch_softmax_rows(S, Pm, (int64_t)B * T, T, s); });
@@ -396,7 +415,7 @@ struct Builder {
       GemmEpilogue ep;
       View o2 = ao; o2.H = T / 128; o2.W = 128;
       ep.out = o2;
-      op([=](cudaStream_t s) { launch_conv_gemm(pv, taps_1x1(), vb, C, ep, s); });
+      op([=](cudaStream_t s) { launch_conv_gemm(pv, taps_1x1(), vb, C, ep, s); }, PROF_GEMM, gemm_flops(pv, 1, C));
     }
     release(bp); release(bqk); release(bvt);
     {
@@ -540,7 +559,7 @@ void build_unet_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
         ep.ddim_pred_x0 = P->ddim_pred_x0; ep.ddim_coef = P->ddim_coef;
       }
       launch_conv_gemm(g, taps, wb, N, ep, s);
-    });
+    }, PROF_GEMM, gemm_flops(g, taps.n, N));
     b.release(bg);
     b.release(bfinal);
   }
@@ -624,7 +643,7 @@ void build_dec_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
       b.op([=](cudaStream_t s) {
         GemmEpilogue ep; ep.bias = bias; ep.out_f32_nchw = dec;
         launch_conv_gemm(g, taps, wb, N, ep, s);
-      });
+      }, PROF_GEMM, gemm_flops(g, taps.n, N));
       const int HW = H * W;
       b.op([=](cudaStream_t s) { launch_mask_select(dec, B, HW, P->out, s); });
       b.release(bd);
@@ -632,7 +651,7 @@ void build_dec_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
       b.op([=](cudaStream_t s) {
         GemmEpilogue ep; ep.bias = bias; ep.out_f32_nchw = P->out;
         launch_conv_gemm(g, taps, wb, N, ep, s);
-      });
+      }, PROF_GEMM, gemm_flops(g, taps.n, N));
     }
     b.release(bg);
   }
@@ -659,7 +678,22 @@ Plan* get_plan(lidm_handle* h, std::map<int, std::unique_ptr<Plan>>& cache, int 
 }
 
 void run_plan(Plan* P, cudaStream_t s) {
-  for (auto& f : P->ops) f(s);
+  if (!g_prof.on) {
+    for (auto& o : P->ops) o.fn(s);
+    return;
+  }
+  for (auto& o : P->ops) {
+    cudaEvent_t a, b;
+    LIDM_CUDA_CHECK(cudaEventCreate(&a));
+    LIDM_CUDA_CHECK(cudaEventCreate(&b));
+    LIDM_CUDA_CHECK(cudaEventRecord(a, s));
+    const int64_t before = g_launch_count.load();
+    o.fn(s);
+    LIDM_CUDA_CHECK(cudaEventRecord(b, s));
+    g_prof.ev.push_back(a); g_prof.ev.push_back(b); g_prof.cat.push_back(o.cat);
+    g_prof.flops[o.cat] += o.flops; g_prof.bytes[o.cat] += o.bytes;
+    g_prof.launches[o.cat] += g_launch_count.load() - before;
+  }
 }
 
 // ------------------------------------------------------------------------------------------- finalize
@@ -988,6 +1022,30 @@ extern "C" {
 const char* lidm_last_error(const lidm_handle* h) { return h ? h->error.c_str() : tls_error.c_str(); }
 
 int64_t lidm_launch_count(void) { return g_launch_count.load(); }
+
+int lidm_profile_begin(void) {
+  return guarded(nullptr, [&] {
+    for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
+    g_prof = ProfState();
+    g_prof.on = true;
+  });
+}
+
+int lidm_profile_end(double* ms, double* flops, double* bytes, int64_t* launches) {
+  return guarded(nullptr, [&] {
+    LIDM_REQUIRE(ms && flops && bytes && launches, "null output");
+    g_prof.on = false;
+    LIDM_CUDA_CHECK(cudaDeviceSynchronize());
+    for (int c = 0; c < PROF_NCAT; ++c) { ms[c] = 0; flops[c] = g_prof.flops[c]; bytes[c] = g_prof.bytes[c]; launches[c] = g_prof.launches[c]; }
+    for (size_t i = 0; i < g_prof.cat.size(); ++i) {
+      float t = 0;
+      LIDM_CUDA_CHECK(cudaEventElapsedTime(&t, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]));
+      ms[g_prof.cat[i]] += t;
+    }
+    for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
+    g_prof.ev.clear(); g_prof.cat.clear();
+  });
+}
 
 int lidm_create(const lidm_config* cfg, lidm_handle** out) {
   return guarded(nullptr, [&] {

@@ -12,56 +12,80 @@ namespace lidm {
 namespace {
 
 // Each thread owns one 8-channel (16-byte) column `cv` of the tensor and walks pixels with a fixed stride.
-// cpg = channels per group.  If cpg >= 8 the 8 channels fall in one group, otherwise in 8/cpg groups.
-template <int NSUB>  // number of groups inside one 8-channel vector: 1, 2 or 4
-__global__ void gn_stats_kernel(const bf16* __restrict__ x, int HW_phys_rows /*unused*/, int H, int W, int hl, int Wp,
-                                int ld, int C, int cpg, int groups, int pix_per_cta, float* __restrict__ partials,
-                                int nchunks) {
-  extern __shared__ float sh[];  // [groups][2]
+// cpg = channels per group.  If cpg >= 8 the 8 channels fall in one group, otherwise in 8/cpg groups; NSUB == 8 is
+// the generic path (one accumulator per channel).  All reductions run in a fixed order: results are bit-reproducible
+// and, because the chunking depends only on (H*W, C), independent of the batch size.
+template <int NSUB>
+__global__ void gn_stats_kernel(const bf16* __restrict__ x, int H, int W, int hl, int Wp, int ld, int C, int cpg,
+                                int groups, int pix_per_cta, float* __restrict__ partials, int nchunks) {
+  extern __shared__ float sh[];  // [blockDim][NSUB][2]
   const int b = blockIdx.y;
   const int chunk = blockIdx.x;
   const int vec_per_pix = C >> 3;
   const int cv = threadIdx.x % vec_per_pix;
   const int prow = threadIdx.x / vec_per_pix;
   const int pstride = blockDim.x / vec_per_pix;
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
   float s[NSUB], q[NSUB];
 #pragma unroll
   for (int i = 0; i < NSUB; ++i) { s[i] = 0.f; q[i] = 0.f; }
   const int HW = H * W;
   const int p0 = chunk * pix_per_cta;
   const int p1 = min(HW, p0 + pix_per_cta);
-  if (prow < pstride) {
-    for (int pix = p0 + prow; pix < p1; pix += pstride) {
-      const int h = pix / W, w = pix - h * W;
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + ((size_t)(b * H + h) * Wp + (w + hl)) * ld) + cv);
-      const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+  auto accum = [&](const uint4& u) {
+    const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = unpack_bf16(uu[i]);
-        if constexpr (NSUB == 8) {  // generic: one accumulator per channel, group resolved at the end
-          s[2 * i] += f.x; q[2 * i] += f.x * f.x;
-          s[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
-        } else {
-          constexpr int per = 8 / NSUB;  // channels per sub-group
-          const int sub = (2 * i) / per;
-          s[sub] += f.x + f.y;
-          q[sub] += f.x * f.x + f.y * f.y;
-        }
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = unpack_bf16(uu[i]);
+      if constexpr (NSUB == 8) {
+        s[2 * i] += f.x; q[2 * i] += f.x * f.x;
+        s[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
+      } else {
+        constexpr int per = 8 / NSUB;  // channels per sub-group
+        const int sub = (2 * i) / per;
+        s[sub] += f.x + f.y;
+        q[sub] += f.x * f.x + f.y * f.y;
       }
     }
+  };
+  auto addr = [&](int pix) {
+    const int h = pix / W, w = pix - h * W;
+    return reinterpret_cast<const uint4*>(x + ((size_t)(b * H + h) * Wp + (w + hl)) * ld) + cv;
+  };
+  if (prow < pstride) {
+    int pix = p0 + prow;
+    for (; pix + 3 * pstride < p1; pix += 4 * pstride) {   // 4 independent 16-byte loads in flight
+      const uint4 u0 = __ldg(addr(pix)), u1 = __ldg(addr(pix + pstride)), u2 = __ldg(addr(pix + 2 * pstride)),
+                  u3 = __ldg(addr(pix + 3 * pstride));
+      accum(u0); accum(u1); accum(u2); accum(u3);
+    }
+    for (; pix < p1; pix += pstride) accum(__ldg(addr(pix)));
   }
-  const int g0 = (cv * 8) / cpg;
 #pragma unroll
   for (int i = 0; i < NSUB; ++i) {
-    const int g = (NSUB == 8) ? (cv * 8 + i) / cpg : g0 + i;
-    atomicAdd(&sh[g * 2 + 0], s[i]);
-    atomicAdd(&sh[g * 2 + 1], q[i]);
+    sh[(threadIdx.x * NSUB + i) * 2 + 0] = s[i];
+    sh[(threadIdx.x * NSUB + i) * 2 + 1] = q[i];
   }
   __syncthreads();
-  float* out = partials + ((size_t)b * nchunks + chunk) * groups * 2;
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) out[i] = sh[i];
+  // one owner thread per group sums its contributors in a fixed order
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float ts = 0.f, tq = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg;) {
+      const int v = c >> 3;
+      int slot, step;
+      if (NSUB == 8) { slot = c & 7; step = 1; }
+      else if (NSUB == 1) { slot = 0; step = 8; }
+      else { slot = (c & 7) / (8 / NSUB); step = 8 / NSUB; }
+      for (int pr = 0; pr < pstride; ++pr) {
+        const int t = pr * vec_per_pix + v;
+        ts += sh[(t * NSUB + slot) * 2 + 0];
+        tq += sh[(t * NSUB + slot) * 2 + 1];
+      }
+      c += step;
+    }
+    float* out = partials + (((size_t)b * nchunks + chunk) * groups + g) * 2;
+    out[0] = ts;
+    out[1] = tq;
+  }
 }
 
 __device__ __forceinline__ float silu_f(float v) { return v / (1.f + __expf(-v)); }
@@ -100,9 +124,12 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int H, int W, int xh
   }
   const int p0 = blockIdx.x * pix_per_cta;
   const int p1 = min(HW, p0 + pix_per_cta);
-  for (int pix = p0 + prow; pix < p1; pix += pstride) {
+  auto addr = [&](int pix) {
     const int h = pix / W, w = pix - h * W;
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + ((size_t)(b * H + h) * xWp + (w + xhl)) * xld) + cv);
+    return reinterpret_cast<const uint4*>(x + ((size_t)(b * H + h) * xWp + (w + xhl)) * xld) + cv;
+  };
+  auto emit = [&](int pix, const uint4& u) {
+    const int h = pix / W, w = pix - h * W;
     const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
     uint32_t oo[4];
 #pragma unroll
@@ -118,7 +145,14 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int H, int W, int xh
     reinterpret_cast<uint4*>(y + (rowbase + w + yhl) * yld)[cv] = o;
     if (w < yhr) reinterpret_cast<uint4*>(y + (rowbase + W + yhl + w) * yld)[cv] = o;
     if (w >= W - yhl) reinterpret_cast<uint4*>(y + (rowbase + (w - (W - yhl))) * yld)[cv] = o;
+  };
+  int pix = p0 + prow;
+  for (; pix + 3 * pstride < p1; pix += 4 * pstride) {   // 4 independent 16-byte loads in flight
+    const uint4 u0 = __ldg(addr(pix)), u1 = __ldg(addr(pix + pstride)), u2 = __ldg(addr(pix + 2 * pstride)),
+                u3 = __ldg(addr(pix + 3 * pstride));
+    emit(pix, u0); emit(pix + pstride, u1); emit(pix + 2 * pstride, u2); emit(pix + 3 * pstride, u3);
   }
+  for (; pix < p1; pix += pstride) emit(pix, __ldg(addr(pix)));
 }
 
 }  // namespace
@@ -135,29 +169,28 @@ void launch_groupnorm(const View& x, const View& y, const float* gamma, const fl
   int threads = (256 % vec == 0) ? 256 : ((384 % vec == 0) ? 384 : 0);
   if (threads == 0) { LIDM_REQUIRE(vec <= 1024, "C too large"); threads = vec; }
   const int HW = x.H * x.W;
-  // enough CTAs to fill the machine, at most GN_MAX_CHUNKS partials per sample
-  int nchunks = (148 * 8 + x.B - 1) / x.B;
-  if (nchunks > GN_MAX_CHUNKS) nchunks = GN_MAX_CHUNKS;
+  // chunking depends on the tensor shape only (never on B): results are batch-invariant
   const int pstride = threads / vec;
-  int max_chunks = (HW + pstride - 1) / pstride;
-  if (nchunks > max_chunks) nchunks = max_chunks;
-  if (nchunks < 1) nchunks = 1;
-  const int pix_per_cta = (HW + nchunks - 1) / nchunks;
-  nchunks = (HW + pix_per_cta - 1) / pix_per_cta;
+  int pix_per_cta = HW <= 512 ? 32 : 64;
+  if (HW / pix_per_cta > GN_MAX_CHUNKS) pix_per_cta = (HW + GN_MAX_CHUNKS - 1) / GN_MAX_CHUNKS;
+  if (pix_per_cta < pstride) pix_per_cta = pstride;
+  const int nchunks = (HW + pix_per_cta - 1) / pix_per_cta;
+  LIDM_REQUIRE(nchunks <= GN_MAX_CHUNKS, "GroupNorm chunking");
   dim3 grid(nchunks, x.B);
-  const size_t shbytes = groups * 2 * sizeof(float);
   const int nsub = !regular ? 8 : (cpg >= 8 ? 1 : 8 / cpg);
+  const size_t shstats = (size_t)threads * nsub * 2 * sizeof(float);
+  const size_t shbytes = groups * 2 * sizeof(float);
   if (nsub == 8)
-    gn_stats_kernel<8><<<grid, threads, shbytes, s>>>(x.p, 0, x.H, x.W, x.hl, x.Wp(), x.ld, C, cpg, groups, pix_per_cta,
+    gn_stats_kernel<8><<<grid, threads, shstats, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, C, cpg, groups, pix_per_cta,
                                                        partials, nchunks);
   else if (nsub == 1)
-    gn_stats_kernel<1><<<grid, threads, shbytes, s>>>(x.p, 0, x.H, x.W, x.hl, x.Wp(), x.ld, C, cpg, groups, pix_per_cta,
+    gn_stats_kernel<1><<<grid, threads, shstats, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, C, cpg, groups, pix_per_cta,
                                                        partials, nchunks);
   else if (nsub == 2)
-    gn_stats_kernel<2><<<grid, threads, shbytes, s>>>(x.p, 0, x.H, x.W, x.hl, x.Wp(), x.ld, C, cpg, groups, pix_per_cta,
+    gn_stats_kernel<2><<<grid, threads, shstats, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, C, cpg, groups, pix_per_cta,
                                                        partials, nchunks);
   else
-    gn_stats_kernel<4><<<grid, threads, shbytes, s>>>(x.p, 0, x.H, x.W, x.hl, x.Wp(), x.ld, C, cpg, groups, pix_per_cta,
+    gn_stats_kernel<4><<<grid, threads, shstats, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, C, cpg, groups, pix_per_cta,
                                                        partials, nchunks);
   LIDM_CUDA_CHECK(cudaGetLastError());
   gn_apply_kernel<<<grid, threads, shbytes, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, y.hl, y.hr, y.Wp(), y.ld, C,
