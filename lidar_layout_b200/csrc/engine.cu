@@ -7,6 +7,8 @@
 //   DDIMSampler.ddim_sampling         lidm/models/diffusion/ddim.py:115-165
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -30,6 +32,7 @@ struct Op {
   std::function<void(cudaStream_t)> fn;
   int cat;
   double flops, bytes;
+  std::string label;
 };
 
 // ---- optional per-op CUDA-event profiler (bench.py roofline) ----
@@ -37,6 +40,8 @@ struct ProfState {
   bool on = false;
   std::vector<cudaEvent_t> ev;            // pairs
   std::vector<int> cat;
+  std::vector<std::string> label;
+  std::vector<double> op_flops, op_bytes;
   double flops[PROF_NCAT] = {0, 0, 0, 0}, bytes[PROF_NCAT] = {0, 0, 0, 0};
   int64_t launches[PROF_NCAT] = {0, 0, 0, 0};
 } g_prof;
@@ -280,8 +285,13 @@ struct Builder {
     return reinterpret_cast<T*>(P->arena + buf->off);
   }
   void release(const Buf& b) { ap.release(b.off, b.bytes); }
-  void op(std::function<void(cudaStream_t)> f, int cat = PROF_OTHER, double flops = 0, double bytes = 0) {
-    if (!dry) P->ops.push_back(Op{std::move(f), cat, flops, bytes});
+  void op(std::function<void(cudaStream_t)> f, int cat = PROF_OTHER, double flops = 0, double bytes = 0,
+          std::string label = std::string()) {
+    if (!dry) P->ops.push_back(Op{std::move(f), cat, flops, bytes, std::move(label)});
+  }
+  static std::string gemm_label(const View& a, int ntaps, int N) {
+    return "gemm taps" + std::to_string(ntaps) + " " + std::to_string(a.C) + "->" + std::to_string(N) + " @" +
+           std::to_string(a.H) + "x" + std::to_string(a.W);
   }
 
   static View chan_slice(const View& v, int c0, int C) {
@@ -294,12 +304,13 @@ struct Builder {
   void gemm(const View& a, const ConvTaps& taps, const ConvW& w, const GemmEpilogue& ep) {
     GemmB b; b.p = w.w; b.n_alloc = w.n_alloc; b.ld = w.k_alloc;
     const int N = w.cout;
-    op([=](cudaStream_t s) { launch_conv_gemm(a, taps, b, N, ep, s); }, PROF_GEMM, gemm_flops(a, taps.n, N));
+    op([=](cudaStream_t s) { launch_conv_gemm(a, taps, b, N, ep, s); }, PROF_GEMM, gemm_flops(a, taps.n, N), 0,
+       gemm_label(a, taps.n, N));
   }
   void groupnorm(const View& x, const View& y, const NormW& n, float eps, bool silu) {
     Plan* P_ = P;
     op([=](cudaStream_t s) { launch_groupnorm(x, y, n.gamma, n.beta, eps, 32, silu, P_->gn_partials, s); }, PROF_NORM, 0,
-       4.0 * x.B * x.H * x.W * x.C);
+       4.0 * x.B * x.H * x.W * x.C, "gn C" + std::to_string(x.C) + " @" + std::to_string(x.H) + "x" + std::to_string(x.W));
   }
 
   // ResBlock._forward (openaimodel.py:256-276) / ResnetBlock.forward (model_lidm.py:127-147, temb None)
@@ -321,7 +332,7 @@ struct Builder {
         GemmEpilogue e = ep;
         if (emb_off >= 0) { e.rowadd = P_->rowadd_base + emb_off; e.rowadd_ld = P_->rowadd_ld; }
         launch_conv_gemm(g1, taps, b, N, e, s);
-      }, PROF_GEMM, gemm_flops(g1, taps.n, N));
+      }, PROF_GEMM, gemm_flops(g1, taps.n, N), 0, gemm_label(g1, taps.n, N));
     }
     release(bg1);
     View g2 = act(B, H, W, r.cout, pl, pr, &bg2);
@@ -353,23 +364,41 @@ struct Builder {
     Buf bg, bqk, bvt, ba;
     View g = act(B, H, W, C, 0, 0, &bg);
     groupnorm(x, g, a.n, 1e-5f, false);
-    View qk = act(B, H, W, 2 * C, 0, 0, &bqk);
-    bf16* vt = raw<bf16>((size_t)B * C * T, &bvt);
-    {
-      GemmEpilogue ep;
-      ep.bias = a.qkv.bias;
-      ep.out = qk;
-      ep.split_n = 2 * C;
-      ep.out_t = vt;
-      gemm(g, taps_1x1(), a.qkv, ep);
-    }
-    release(bg);
-    View ao = act(B, H, W, C, 0, 0, &ba);
+    static const bool legacy = getenv("LIDM_ATTN_LEGACY") != nullptr;
     const int heads = a.heads;
-    op([=](cudaStream_t s) { launch_attention_d32(qk.p, vt, ao, B, T, heads, s); }, PROF_ATTN,
-       4.0 * B * heads * (double)T * T * 32);
-    release(bqk);
-    release(bvt);
+    View ao;
+    if (legacy) {
+      View qk = act(B, H, W, 2 * C, 0, 0, &bqk);
+      bf16* vt = raw<bf16>((size_t)B * C * T, &bvt);
+      {
+        GemmEpilogue ep;
+        ep.bias = a.qkv.bias;
+        ep.out = qk;
+        ep.split_n = 2 * C;
+        ep.out_t = vt;
+        gemm(g, taps_1x1(), a.qkv, ep);
+      }
+      release(bg);
+      ao = act(B, H, W, C, 0, 0, &ba);
+      op([=](cudaStream_t s) { launch_attention_d32(qk.p, vt, ao, B, T, heads, s); }, PROF_ATTN,
+         4.0 * B * heads * (double)T * T * 32);
+      release(bqk);
+      release(bvt);
+    } else {
+      // one packed (B,T,3C) = [q | k | v] tensor straight out of the qkv GEMM (TMA-store epilogue)
+      View qkv = act(B, H, W, 3 * C, 0, 0, &bqk);
+      {
+        GemmEpilogue ep;
+        ep.bias = a.qkv.bias;
+        ep.out = qkv;
+        gemm(g, taps_1x1(), a.qkv, ep);
+      }
+      release(bg);
+      ao = act(B, H, W, C, 0, 0, &ba);
+      op([=](cudaStream_t s) { launch_attention_d32_packed(qkv.p, ao, B, T, heads, s); }, PROF_ATTN,
+         4.0 * B * heads * (double)T * T * 32, 0, "attn T" + std::to_string(T) + " heads" + std::to_string(heads));
+      release(bqk);
+    }
     {
       GemmEpilogue ep;
       ep.bias = a.proj.bias;
@@ -691,6 +720,7 @@ void run_plan(Plan* P, cudaStream_t s) {
     o.fn(s);
     LIDM_CUDA_CHECK(cudaEventRecord(b, s));
     g_prof.ev.push_back(a); g_prof.ev.push_back(b); g_prof.cat.push_back(o.cat);
+    g_prof.label.push_back(o.label); g_prof.op_flops.push_back(o.flops); g_prof.op_bytes.push_back(o.bytes);
     g_prof.flops[o.cat] += o.flops; g_prof.bytes[o.cat] += o.bytes;
     g_prof.launches[o.cat] += g_launch_count.load() - before;
   }
@@ -984,7 +1014,7 @@ int guarded(lidm_handle* h, F&& f) {
 }
 
 __global__ void qkv_legacy_to_internal_kernel(const float* __restrict__ qkv, int B, int heads, int T, float scale,
-                                              bf16* __restrict__ qk, bf16* __restrict__ vt) {
+                                              bf16* __restrict__ qk, bf16* __restrict__ vt, int packed) {
   // qkv: (B, heads*96, T) with channel = head*96 + part*32 + c
   const int C = heads * 32;
   const int64_t total = (int64_t)B * heads * 96 * T;
@@ -995,6 +1025,10 @@ __global__ void qkv_legacy_to_internal_kernel(const float* __restrict__ qkv, int
     const int b = (int)(r / (heads * 96));
     const int hd = chn / 96, part = (chn % 96) / 32, c = chn % 32;
     const float v = qkv[i];
+    if (packed) {
+      qk[((size_t)b * T + t) * (3 * C) + part * C + hd * 32 + c] = __float2bfloat16(part < 2 ? v * scale : v);
+      continue;
+    }
     if (part < 2) qk[((size_t)b * T + t) * (2 * C) + part * C + hd * 32 + c] = __float2bfloat16(v * scale);
     else vt[((size_t)b * C + hd * 32 + c) * T + t] = __float2bfloat16(v);
   }
@@ -1037,13 +1071,18 @@ int lidm_profile_end(double* ms, double* flops, double* bytes, int64_t* launches
     g_prof.on = false;
     LIDM_CUDA_CHECK(cudaDeviceSynchronize());
     for (int c = 0; c < PROF_NCAT; ++c) { ms[c] = 0; flops[c] = g_prof.flops[c]; bytes[c] = g_prof.bytes[c]; launches[c] = g_prof.launches[c]; }
+    FILE* dump = nullptr;
+    if (const char* path = getenv("LIDM_PROFILE_DUMP")) dump = fopen(path, "a");
     for (size_t i = 0; i < g_prof.cat.size(); ++i) {
       float t = 0;
       LIDM_CUDA_CHECK(cudaEventElapsedTime(&t, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]));
       ms[g_prof.cat[i]] += t;
+      if (dump) fprintf(dump, "%d,%.4f,%.6g,%.6g,%s\n", g_prof.cat[i], t, g_prof.op_flops[i], g_prof.op_bytes[i],
+                        g_prof.label[i].c_str());
     }
+    if (dump) fclose(dump);
     for (cudaEvent_t e : g_prof.ev) cudaEventDestroy(e);
-    g_prof.ev.clear(); g_prof.cat.clear();
+    g_prof.ev.clear(); g_prof.cat.clear(); g_prof.label.clear(); g_prof.op_flops.clear(); g_prof.op_bytes.clear();
   });
 }
 
@@ -1289,14 +1328,16 @@ int lidm_op_qkv_attention_legacy(const float* qkv, int32_t B, int32_t heads, int
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const int C = heads * 32;
     TmpBufs tmp;
-    bf16* qk = tmp.get<bf16>((size_t)B * T * 2 * C);
+    static const bool legacy = getenv("LIDM_ATTN_LEGACY") != nullptr;
+    bf16* qk = tmp.get<bf16>((size_t)B * T * 3 * C);
     bf16* vt = tmp.get<bf16>((size_t)B * C * T);
     const float scale = 1.0f / std::sqrt(std::sqrt(32.0f));
-    qkv_legacy_to_internal_kernel<<<148 * 8, 256, 0, s>>>(qkv, B, heads, T, scale, qk, vt);
+    qkv_legacy_to_internal_kernel<<<148 * 8, 256, 0, s>>>(qkv, B, heads, T, scale, qk, vt, legacy ? 0 : 1);
     LIDM_CUDA_CHECK(cudaGetLastError());
     View o; o.B = B; o.H = T / 128; o.W = 128; o.C = C; o.ld = C;
     o.p = tmp.get<bf16>((size_t)B * T * C);
-    launch_attention_d32(qk, vt, o, B, T, heads, s);
+    if (legacy) launch_attention_d32(qk, vt, o, B, T, heads, s);
+    else launch_attention_d32_packed(qk, o, B, T, heads, s);
     launch_nhwc_bf16_to_f32_nchw(o, out, s);
     LIDM_CUDA_CHECK(cudaStreamSynchronize(s));
   });

@@ -11,6 +11,8 @@
 // Warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue.
 // Epilogue fusions: bias, per-sample timestep-embedding add, residual add, halo write, transposed V^T store for
 // attention, fp32 NCHW/NHWC stores, and the DDIM update (ddim.py:191-206) for the U-Net's final conv.
+#include <cstdlib>
+
 #include "common.h"
 #include "ddim_math.cuh"
 #include "ptx.cuh"
@@ -287,6 +289,398 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+// =====================================================================================================
+// Persistent variant: one CTA per SM walks tiles (m fastest, so concurrently running CTAs share the weight tile in
+// L2); two TMEM accumulator buffers let the MMA warp start tile i+1 while the epilogue warps drain tile i; the
+// tile's bias + timestep-embedding row is staged once in shared memory; bf16 outputs leave through a swizzled
+// shared-memory staging buffer and TMA stores (full 128-byte lines), double-buffered across tiles.
+template <int BN, int STAGES>
+struct PersistLayout {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int B_STRIDE = (B_STAGE_BYTES + 1023) / 1024 * 1024;
+  static constexpr int A_OFF = 0;
+  static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
+  static constexpr int OUT_BOXES = BN >= 64 ? BN / 64 : 0;          // 64-channel TMA store boxes per tile
+  static constexpr int OUT_BUF_BYTES = OUT_BOXES * BM * 128;        // bf16 staging for one tile
+  static constexpr int OUT_BUFS = BN > 128 ? 1 : 2;                 // staging buffers (double-buffered when they fit)
+  static constexpr int OUT_OFF = B_OFF + STAGES * B_STRIDE;
+  static constexpr int BIAS_OFF = OUT_OFF + OUT_BUFS * OUT_BUF_BYTES;
+  static constexpr int BAR_OFF = BIAS_OFF + 2 * (BN < 32 ? 32 : BN) * 4;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+  static constexpr uint32_t ACC_COLS = BN;                          // TMEM columns per accumulator buffer
+  static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ CUtensorMap tmO, const GemmKernelParams p, int num_m_tiles,
+                         int num_tiles, int use_tma_store) {
+  using L = PersistLayout<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* sbias = reinterpret_cast<float*>(smem + L::BIAS_OFF);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_it = p.ntaps * p.kchunks;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+    if (use_tma_store) prefetch_tensormap(&tmO);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, L::TMEM_COLS); tmem_relinquish(); }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile % num_m_tiles, n0 = (tile / num_m_tiles) * BN;
+        const int b = m_tile / p.tiles_per_img;
+        const int r = m_tile - b * p.tiles_per_img;
+        const int th = r / p.tiles_w;
+        const int h0 = th * p.Hbox, w0 = (r - th * p.tiles_w) * p.Wbox;
+        int it = 0;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const int x = w0 + p.hl + p.dx[tap], y = h0 + p.dy[tap];
+          for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + L::B_STAGE_BYTES);
+            tma_load_4d(smem + L::A_OFF + s * A_STAGE_BYTES, &tmA, &full_bar[s], kc * BK, x, y, b);
+            tma_load_3d(smem + L::B_OFF + s * L::B_STRIDE, &tmB, &full_bar[s], it * BK, n0, p.wt_batched ? b : 0);
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      int s = 0; uint32_t ph = 0;
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const int ab = lt & 1;
+        mbar_wait(&tempty_bar[ab], ((lt >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t d = tmem_base + ab * L::ACC_COLS;
+        for (int it = 0; it < num_it; ++it) {
+          mbar_wait(&full_bar[s], ph);
+          tcgen05_fence_after();
+          const uint64_t adesc = make_kmajor_desc<128>(smem_u32(smem + L::A_OFF + s * A_STAGE_BYTES));
+          const uint64_t bdesc = make_kmajor_desc<128>(smem_u32(smem + L::B_OFF + s * L::B_STRIDE));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_bf16_ss(d, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+          umma_commit(&empty_bar[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull_bar[ab]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int e = threadIdx.x - 64;   // 0..127
+    const int hh = row / p.Wbox;
+    const int ww = row - hh * p.Wbox;
+    const int HW = p.H * p.W;
+    float coef[5] = {0, 0, 0, 0, 0};
+    if (p.ddim_x_prev != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) coef[i] = __ldg(p.ddim_coef + i);
+    }
+    constexpr int CH = BN < 32 ? BN : 32;
+    constexpr int SB = BN < 32 ? 32 : BN;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const int ab = lt & 1;
+      const int m_tile = tile % num_m_tiles, n0 = (tile / num_m_tiles) * BN;
+      const int b = m_tile / p.tiles_per_img;
+      const int r = m_tile - b * p.tiles_per_img;
+      const int th = r / p.tiles_w;
+      const int h0 = th * p.Hbox, w0 = (r - th * p.tiles_w) * p.Wbox;
+      const int h = h0 + hh, w = w0 + ww;
+      const int pix = h * p.W + w;
+      // stage bias + per-sample row (timestep embedding) for this tile's columns
+      for (int i = e; i < BN; i += 128) {
+        const int n = n0 + i;
+        float v = 0.f;
+        if (n < p.N) {
+          if (p.bias != nullptr) v = __ldg(p.bias + n);
+          if (p.rowadd != nullptr) v += __ldg(p.rowadd + (size_t)b * p.rowadd_ld + n);
+        }
+        sbias[ab * SB + i] = v;
+      }
+      if (use_tma_store && e == 0) tma_store_wait_read<L::OUT_BUFS - 1>();   // this tile's staging buffer is free
+      named_bar_sync(1, 128);
+      const uint32_t taddr_row = tmem_base + ab * L::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+      uint8_t* stage_out = smem + L::OUT_OFF + (L::OUT_BUFS == 2 ? ab : 0) * L::OUT_BUF_BYTES;
+      if constexpr (BN >= 64) {
+        if (use_tma_store) {
+          // Fast path (bf16 output through TMA stores): the residual row is requested before the accumulator is
+          // even ready, the whole accumulator row is pulled out of TMEM with back-to-back loads and one wait, and
+          // the TMEM buffer is handed back to the MMA warp before any arithmetic or store happens.
+          constexpr int HALF = BN > 128 ? 128 : BN;      // columns handled per register batch
+          constexpr int NH = BN / HALF;
+          constexpr int NCH = HALF / 32;
+          const bool has_res = p.res != nullptr;
+          const bf16* rp = has_res ? p.res + ((size_t)(b * p.H + h) * p.res_Wp + (w + p.res_hl)) * p.res_ld + n0 : nullptr;
+#pragma unroll
+          for (int hf = 0; hf < NH; ++hf) {
+            uint4 rres[NCH][4];
+            if (has_res) {
+#pragma unroll
+              for (int c = 0; c < NCH; ++c) {
+                if (n0 + hf * HALF + c * 32 < p.N) {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i)
+                    rres[c][i] = __ldg(reinterpret_cast<const uint4*>(rp + hf * HALF + c * 32) + i);
+                }
+              }
+            }
+            if (hf == 0) {
+              mbar_wait(&tfull_bar[ab], (lt >> 1) & 1);
+              tcgen05_fence_after();
+            }
+            uint32_t raw[NCH][32];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) tmem_ld_32x32b_x32(taddr_row + hf * HALF + c * 32, raw[c]);
+            tmem_ld_wait();
+            if (hf == NH - 1) {
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty_bar[ab]);
+            }
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+              const int cc = hf * HALF + c * 32;   // column offset inside the tile
+              if (n0 + cc < p.N) {
+                float v[32];
+                const float4* sb4 = reinterpret_cast<const float4*>(sbias + ab * SB + cc);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 t = sb4[j];
+                  v[4 * j] = __uint_as_float(raw[c][4 * j]) + t.x;
+                  v[4 * j + 1] = __uint_as_float(raw[c][4 * j + 1]) + t.y;
+                  v[4 * j + 2] = __uint_as_float(raw[c][4 * j + 2]) + t.z;
+                  v[4 * j + 3] = __uint_as_float(raw[c][4 * j + 3]) + t.w;
+                }
+                if (has_res) {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    float2 f;
+                    f = unpack_bf16(rres[c][i].x); v[i * 8 + 0] += f.x; v[i * 8 + 1] += f.y;
+                    f = unpack_bf16(rres[c][i].y); v[i * 8 + 2] += f.x; v[i * 8 + 3] += f.y;
+                    f = unpack_bf16(rres[c][i].z); v[i * 8 + 4] += f.x; v[i * 8 + 5] += f.y;
+                    f = unpack_bf16(rres[c][i].w); v[i * 8 + 6] += f.x; v[i * 8 + 7] += f.y;
+                  }
+                }
+                uint8_t* box = stage_out + (cc >> 6) * (BM * 128) + row * 128;
+                const int cbase = (cc & 63) >> 3;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  uint4 pk;
+                  pk.x = pack_bf16(v[i * 8 + 0], v[i * 8 + 1]);
+                  pk.y = pack_bf16(v[i * 8 + 2], v[i * 8 + 3]);
+                  pk.z = pack_bf16(v[i * 8 + 4], v[i * 8 + 5]);
+                  pk.w = pack_bf16(v[i * 8 + 6], v[i * 8 + 7]);
+                  *reinterpret_cast<uint4*>(box + (((cbase + i) ^ (row & 7)) << 4)) = pk;
+                }
+              }
+            }
+          }
+          fence_proxy_async();          // staging writes -> visible to the TMA engine
+          named_bar_sync(2, 128);
+          if (e == 0) {
+#pragma unroll
+            for (int j = 0; j < L::OUT_BOXES; ++j)
+              if (n0 + j * 64 < p.N)
+                tma_store_4d(&tmO, stage_out + j * (BM * 128), n0 + j * 64, w0, h0, b);
+            tma_store_commit();
+          }
+          continue;
+        }
+      }
+      mbar_wait(&tfull_bar[ab], (lt >> 1) & 1);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += CH) {
+        const int n = n0 + c0;
+        const bool live = n < p.N;   // warp-uniform
+        uint4 rres[4];
+        const bool has_res = live && p.res != nullptr && CH == 32;
+        if (has_res) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(
+              p.res + ((size_t)(b * p.H + h) * p.res_Wp + (w + p.res_hl)) * p.res_ld + n);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rres[i] = __ldg(r4 + i);
+        }
+        float v[CH];
+        {
+          uint32_t raw[CH];
+          if constexpr (CH == 32) tmem_ld_32x32b_x32(taddr_row + c0, raw);
+          else tmem_ld_32x32b_x16(taddr_row + c0, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(raw[j]);
+        }
+        if (c0 + CH >= BN) {   // last TMEM read of this tile: hand the accumulator back to the MMA warp
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[ab]);
+        }
+        if (!live) continue;
+        {
+          const float4* sb4 = reinterpret_cast<const float4*>(sbias + ab * SB + c0);
+#pragma unroll
+          for (int j = 0; j < CH / 4; ++j) {
+            const float4 t = sb4[j];
+            v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+          }
+        }
+        if (has_res) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float2 f;
+            f = unpack_bf16(rres[i].x); v[i * 8 + 0] += f.x; v[i * 8 + 1] += f.y;
+            f = unpack_bf16(rres[i].y); v[i * 8 + 2] += f.x; v[i * 8 + 3] += f.y;
+            f = unpack_bf16(rres[i].z); v[i * 8 + 4] += f.x; v[i * 8 + 5] += f.y;
+            f = unpack_bf16(rres[i].w); v[i * 8 + 6] += f.x; v[i * 8 + 7] += f.y;
+          }
+        } else if (p.res != nullptr) {
+          const bf16* rp = p.res + ((size_t)(b * p.H + h) * p.res_Wp + (w + p.res_hl)) * p.res_ld + n;
+#pragma unroll
+          for (int j = 0; j < CH; ++j)
+            if (n + j < p.N) v[j] += __bfloat162float(rp[j]);
+        }
+
+        if (n >= p.split_n) {
+          bf16* ot = p.out_t + ((size_t)b * (p.N - p.split_n) + (n - p.split_n)) * HW + pix;
+#pragma unroll
+          for (int j = 0; j < CH; ++j) ot[(size_t)j * HW] = __float2bfloat16(v[j]);
+        } else if (p.out != nullptr) {
+          if constexpr (CH == 32) {
+            uint4 pk[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              pk[i].x = pack_bf16(v[i * 8 + 0], v[i * 8 + 1]);
+              pk[i].y = pack_bf16(v[i * 8 + 2], v[i * 8 + 3]);
+              pk[i].z = pack_bf16(v[i * 8 + 4], v[i * 8 + 5]);
+              pk[i].w = pack_bf16(v[i * 8 + 6], v[i * 8 + 7]);
+            }
+            if (use_tma_store) {
+              // staging layout = TMA box [pixel row][64 ch] (128 B rows, 128B swizzle): chunk16 ^= (row & 7)
+              uint8_t* box = stage_out + (c0 >> 6) * (BM * 128) + row * 128;
+              const int cbase = (c0 & 63) >> 3;   // first 16-byte chunk of this 32-channel group inside the row
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<uint4*>(box + (((cbase + i) ^ (row & 7)) << 4)) = pk[i];
+            } else {
+              const size_t rowbase = (size_t)(b * p.H + h) * p.out_Wp;
+              uint4* o = reinterpret_cast<uint4*>(p.out + (rowbase + w + p.out_hl) * p.out_ld + n);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) o[i] = pk[i];
+              if (w < p.out_hr) {
+                uint4* o2 = reinterpret_cast<uint4*>(p.out + (rowbase + p.W + p.out_hl + w) * p.out_ld + n);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o2[i] = pk[i];
+              }
+              if (w >= p.W - p.out_hl) {
+                uint4* o2 = reinterpret_cast<uint4*>(p.out + (rowbase + (w - (p.W - p.out_hl))) * p.out_ld + n);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) o2[i] = pk[i];
+              }
+            }
+          } else {
+            bf16* o = p.out + ((size_t)(b * p.H + h) * p.out_Wp + (w + p.out_hl)) * p.out_ld + n;
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (n + j < p.N) o[j] = __float2bfloat16(v[j]);
+          }
+        }
+        if (p.out_f32_nhwc != nullptr) {
+          float* o = p.out_f32_nhwc + ((size_t)b * HW + pix) * p.N + n;
+          if (CH == 32 && n + 32 <= p.N) {
+            float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+            for (int i = 0; i < CH / 4; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (n + j < p.N) o[j] = v[j];
+          }
+        }
+        if (p.out_f32_nchw != nullptr || p.ddim_x_prev != nullptr) {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            if (n + j < p.N) {
+              const size_t idx = ((size_t)b * p.N + (n + j)) * HW + pix;
+              if (p.out_f32_nchw != nullptr) p.out_f32_nchw[idx] = v[j];
+              if (p.ddim_x_prev != nullptr) {
+                const float nz = p.ddim_noise != nullptr ? p.ddim_noise[idx] : 0.f;
+                float xp, x0;
+                ddim_update(p.ddim_x[idx], v[j], nz, coef, xp, x0);
+                p.ddim_x_prev[idx] = xp;
+                if (p.ddim_pred_x0 != nullptr) p.ddim_pred_x0[idx] = x0;
+              }
+            }
+          }
+        }
+      }
+      if (use_tma_store) {
+        fence_proxy_async();          // staging writes -> visible to the TMA engine
+        named_bar_sync(2, 128);
+        if (e == 0) {
+#pragma unroll
+          for (int j = 0; j < L::OUT_BOXES; ++j)
+            if (n0 + j * 64 < p.N)
+              tma_store_4d(&tmO, stage_out + j * (BM * 128), n0 + j * 64, w0, h0, b);
+          tma_store_commit();
+        }
+      }
+    }
+    if (use_tma_store && e == 0) tma_store_wait<0>();   // smem must outlive the in-flight stores
+    tcgen05_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, L::TMEM_COLS); }
+}
+
+template <int BN, int STAGES>
+void launch_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmKernelParams& p,
+                    int num_m_tiles, int num_tiles, int use_tma_store, cudaStream_t stream) {
+  using L = PersistLayout<BN, STAGES>;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    LIDM_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_persist_kernel<BN, STAGES>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    int dev = 0;
+    LIDM_CUDA_CHECK(cudaGetDevice(&dev));
+    LIDM_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  conv_gemm_persist_kernel<BN, STAGES><<<grid, 192, L::TOTAL, stream>>>(tmA, tmB, tmO, p, num_m_tiles, num_tiles,
+                                                                       use_tma_store);
+  LIDM_CUDA_CHECK(cudaGetLastError());
+  LIDM_COUNT_LAUNCH(1);
+}
+
 template <int BN, int STAGES>
 void launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKernelParams& p, dim3 grid,
                  cudaStream_t stream) {
@@ -322,7 +716,14 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
     LIDM_REQUIRE(-taps.dx[t] <= a.hl && taps.dx[t] <= a.hr, "tap exceeds the materialised halo");
   }
   int BN;
-  if (n_alloc % 128 == 0) BN = 128;
+  static const int force_bn = getenv("LIDM_GEMM_BN") ? atoi(getenv("LIDM_GEMM_BN")) : 0;
+  if (n_alloc % 256 == 0 && force_bn != 128 && ep.out_t == nullptr) {
+    // 128x256 tiles halve the B-operand traffic per MAC; take them unless wave quantisation on 148 SMs eats the gain
+    const long m_tiles = (long)a.B * (H / Hbox) * (W / Wbox);
+    auto eff = [&](long tiles) { const long rounds = (tiles + 147) / 148; return (double)tiles / (double)(rounds * 148); };
+    const double e256 = eff(m_tiles * (n_alloc / 256)) * 1.10, e128 = eff(m_tiles * (n_alloc / 128));
+    BN = (e256 >= e128 || force_bn == 256) ? 256 : 128;
+  } else if (n_alloc % 128 == 0) BN = 128;
   else if (n_alloc % 64 == 0) BN = 64;
   else { LIDM_REQUIRE(n_alloc % 16 == 0, "n_alloc must be a multiple of 16"); BN = 16; }
   LIDM_REQUIRE(N <= n_alloc, "N > n_alloc");
@@ -361,10 +762,25 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
   CUtensorMap tmB = make_tma_3d(wt, Ktot, (uint64_t)n_alloc, wt_batched ? (uint64_t)a.B : 1, wld * 2,
                                 wt_batched ? (uint64_t)wtb.batch_stride * 2 : wld * 2 * (uint64_t)n_alloc, BK, BN,
                                 128);
-  dim3 grid(a.B * p.tiles_per_img, n_alloc / BN);
-  if (BN == 128) launch_impl<128, 3>(tmA, tmB, p, grid, stream);
-  else if (BN == 64) launch_impl<64, 4>(tmA, tmB, p, grid, stream);
-  else launch_impl<16, 4>(tmA, tmB, p, grid, stream);
+  static const bool legacy = getenv("LIDM_GEMM_LEGACY") != nullptr;
+  if (legacy) {
+    LIDM_REQUIRE(BN != 256, "legacy kernel has no 256-wide tile (set LIDM_GEMM_BN=128)");
+    dim3 grid(a.B * p.tiles_per_img, n_alloc / BN);
+    if (BN == 128) launch_impl<128, 3>(tmA, tmB, p, grid, stream);
+    else if (BN == 64) launch_impl<64, 4>(tmA, tmB, p, grid, stream);
+    else launch_impl<16, 4>(tmA, tmB, p, grid, stream);
+    return;
+  }
+  const int num_m_tiles = a.B * p.tiles_per_img;
+  const int num_tiles = num_m_tiles * (n_alloc / BN);
+  const int use_tma_store = (ep.out.p != nullptr && ep.out.hl == 0 && ep.out.hr == 0 && ep.out_t == nullptr && BN >= 64)
+                                ? 1 : 0;
+  CUtensorMap tmO = tmA;
+  if (use_tma_store) tmO = make_tma_act(ep.out, 64, Wbox, Hbox, 128);
+  if (BN == 256) launch_persist<256, 3>(tmA, tmB, tmO, p, num_m_tiles, num_tiles, use_tma_store, stream);
+  else if (BN == 128) launch_persist<128, 4>(tmA, tmB, tmO, p, num_m_tiles, num_tiles, use_tma_store, stream);
+  else if (BN == 64) launch_persist<64, 6>(tmA, tmB, tmO, p, num_m_tiles, num_tiles, use_tma_store, stream);
+  else launch_persist<16, 6>(tmA, tmB, tmO, p, num_m_tiles, num_tiles, use_tma_store, stream);
 }
 
 }  // namespace lidm
