@@ -194,7 +194,7 @@ def run_gpu_arm(args):
     cfg = C.kitti_uncond()
     B = args.batch
     sd = random_state_dict(cfg, 0)
-    model = L.LatentDiffusion(cfg, device=dev, use_ema=False)
+    model = L.LatentDiffusion(cfg, device=dev, use_ema=False, precision=args.precision)
     model.load_state_dict(sd)
     sampler = L.DDIMSampler(model)
     sampler.make_schedule(DDIM_STEPS, ddim_eta=0.0)
@@ -310,7 +310,8 @@ def run_gpu_arm(args):
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (3-way bf16 operand split, fp32 accumulate and residual stream)",
+            "data": "synthetic",
             "config": workload_config(B, world),
             "ms_per_unet_step": unet_ms,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -333,6 +334,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="samples per GPU per step (BASELINE config 2: 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+                    help="bf16 = headline tensor-core path; fp32 = precise operand-split mode (parity mode)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -47,6 +47,10 @@ typedef struct lidm_config {
   int32_t ae_ch_mult[LIDM_MAX_LEVELS];
   int32_t ae_strides[LIDM_MAX_LEVELS][2]; /* ae_n_ch_mult-1 entries (h, w) */
   float scale_factor;                     /* LatentDiffusion.scale_factor (ddpm.py:438,725) */
+  /* 0 = bf16 tensor-core path (north_star bf16 budget: eps within 2e-2);
+   * 1 = precise "fp32-class" path: every GEMM runs as a 3-way bf16 operand split x*w = xh*wh + xl*wh + xh*wl on the
+   *     same tcgen05 kernel with an fp32 residual stream (north_star fp32 bars: eps within 1e-3, image within 1e-2) */
+  int32_t precision;
 } lidm_config;
 
 /* Last error message for `h` (or, with h == NULL, for the calling thread's last failed lidm_create / stateless call). */

@@ -33,6 +33,7 @@ class CConfig(ctypes.Structure):
         ("ae_n_ch_mult", c_int32), ("ae_ch_mult", c_int32 * MAX_LEVELS),
         ("ae_strides", (c_int32 * 2) * MAX_LEVELS),
         ("scale_factor", c_float),
+        ("precision", c_int32),
     ]
 
 

@@ -75,6 +75,10 @@ class LidmConfig:
     scale_factor: float = 1.0
     parameterization: str = "eps"
     conditioning_key: Optional[str] = None
+    # numeric mode of the CUDA path (not a reference option): "bf16" = plain bf16 tensor-core GEMMs (north_star bf16
+    # budget, eps within 2e-2); "fp32" = precise mode, every GEMM as a 3-way bf16 operand split with an fp32 residual
+    # stream (north_star fp32 bars: eps within 1e-3, final image within 1e-2), about 3x the GEMM work
+    precision: str = "bf16"
     unet: UNetConfig = field(default_factory=UNetConfig)
     ae: AEConfig = field(default_factory=AEConfig)
     dataset: DatasetConfig = field(default_factory=DatasetConfig)

@@ -47,6 +47,11 @@ struct View {
   int B = 0, H = 0, W = 0, C = 0;
   int hl = 0, hr = 0;
   int ld = 0;
+  // precise ("fp32-class") mode: the value is carried as two bf16 planes x = hi + lo; hi occupies channels
+  // [0, C) of the view, lo occupies [lo_off, lo_off + C) (lo_off == 0 => ordinary single-plane tensor)
+  int lo_off = 0;
+  int cphys = 0;   // physical channel extent when it is not derivable (im2col'd hi/lo operands); 0 => derived
+  int Cphys() const { return cphys ? cphys : (lo_off ? lo_off + C : C); }
   int Wp() const { return W + hl + hr; }
   size_t pix_index(int b, int h, int w) const { return ((size_t)(b * H + h) * Wp() + (w + hl)); }
 };
@@ -61,6 +66,14 @@ struct ConvTaps {
   int n = 1;
   int8_t dx[9] = {0};
   int8_t dy[9] = {0};
+  int cstep = 0;   // channels between consecutive taps inside an im2col'd operand (0 => taps are spatial shifts)
+};
+
+// fp32 channels-last tensor (no halo): the residual stream of the precise mode
+struct ViewF {
+  float* p = nullptr;
+  int B = 0, H = 0, W = 0, C = 0;
+  int ld = 0;
 };
 
 struct GemmEpilogue {
@@ -74,6 +87,9 @@ struct GemmEpilogue {
   bf16* out_t = nullptr;
   float* out_f32_nchw = nullptr;   // optional fp32 NCHW output (B, N, H, W)
   float* out_f32_nhwc = nullptr;   // optional fp32 channels-last output (B, H, W, N) (no halo)
+  int out_f32_ld = 0;              // channel stride of out_f32_nhwc (0 => N)
+  const float* res_f32 = nullptr;  // optional fp32 channels-last residual, channel stride res_f32_ld
+  int res_f32_ld = 0;
   // fused DDIM update (only with out_f32_nchw semantics; eps itself is still written to out_f32_nchw if non-null)
   const float* ddim_x = nullptr;   // x_t fp32 NCHW
   const float* ddim_noise = nullptr;
@@ -86,8 +102,13 @@ struct GemmEpilogue {
 struct GemmB {
   const bf16* p = nullptr;
   int n_alloc = 0;          // rows available (multiple of the N tile; padding rows are zero)
-  int64_t ld = 0;           // row stride in elements (0 => ntaps*Cin)
+  int64_t ld = 0;           // row stride in elements (0 => ntaps*nseg*Cin)
   int64_t batch_stride = 0; // elements between per-sample matrices (0 => shared weights)
+  // operand-split segments per tap (precise mode, x*w = xh*wh + xl*wh + xh*wl): packed K order [tap][seg][Cin]
+  //   1: [w]                      A single plane
+  //   2: [w_hi, w_lo]             A single plane (exact bf16 values, e.g. attention output)
+  //   3: [w_hi, w_hi, w_lo]       A = hi/lo planes: segments read (hi, lo, hi)
+  int nseg = 1;
 };
 
 // A: activation view (taps applied on the halo'd view).  N = logical output channels.
@@ -132,6 +153,19 @@ void launch_pack_conv_weight(const float* w, int cout, int cin, int kh, int kw, 
                              const int* row_perm, const float* row_scale_rows, float row_scale, int n_scaled_rows,
                              bf16* out, cudaStream_t s);
 void launch_mask_select(const float* dec, int B, int HW, float* out, cudaStream_t s);
+
+// ---- precise ("fp32-class") mode helpers (precise.cu): fp32 stream tensors <-> bf16 hi/lo planes -------------
+// y.lo_off > 0 => write hi and lo planes (x = hi + lo, both bf16), else a single rounded plane.  Halos are written.
+void launch_split_f32(const ViewF& x, const View& y, cudaStream_t s);
+void launch_groupnorm_f32(const ViewF& x, const View& y, const float* gamma, const float* beta, float eps, int groups,
+                          bool silu, float* partials, cudaStream_t s);
+void launch_upsample_bilinear_f32(const ViewF& x, const View& y, cudaStream_t s);
+void launch_im2col_nchw_f32_hl(const float* x, int B, int C, int H, int W, int kh, int kw, int pl, int pt, bf16* out,
+                               int kpad, cudaStream_t s);
+void launch_reorder_weight_f32(const float* w, int cout, int cin, int taps, int kpad, float* out, cudaStream_t s);
+// packed K order [tap][seg][cin]; seg values per GemmB::nseg
+void launch_pack_conv_weight_split(const float* w, int cout, int cin, int kh, int kw, int n_alloc, int nseg,
+                                   const int* row_perm, float row_scale, int n_scaled_rows, bf16* out, cudaStream_t s);
 void launch_f32_to_nhwc_bf16(const float* x, int B, int C, int HW, const View& y, cudaStream_t s);
 void launch_nhwc_bf16_to_f32_nchw(const View& x, float* y, cudaStream_t s);
 

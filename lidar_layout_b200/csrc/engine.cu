@@ -105,6 +105,7 @@ struct ConvW {
   float* bias = nullptr;
   int cout = 0, cin = 0, kh = 1, kw = 1;
   int n_alloc = 0, k_alloc = 0;
+  int nseg = 1;   // operand-split segments per tap (precise mode: 3 for hi/lo inputs, 2 for exact-bf16 inputs)
 };
 struct NormW { float* gamma = nullptr; float* beta = nullptr; int C = 0; };
 struct ResW { NormW n1, n2; ConvW c1, c2, skip; bool has_skip = false; int emb_off = -1; int cin = 0, cout = 0; };
@@ -230,6 +231,7 @@ struct Packer {
   lidm_handle* h;
   bool ema;
   cudaStream_t s = 0;
+  bool precise = false;
 
   float* f32(const std::string& name, int64_t expect_numel) {
     const DevTensor& t = find_raw(h, name, ema);
@@ -248,16 +250,35 @@ struct Packer {
     return n;
   }
   // k_alloc_override: K of the packed matrix (for im2col'd operands padded to a multiple of 64)
-  ConvW conv(const std::string& prefix, int cout, int cin, int kh, int kw, int k_alloc_override = 0) {
+  // k_alloc_override: per-plane K of an im2col'd small-channel operand (padded to a multiple of 64)
+  // nseg_p: operand-split segments used in precise mode (3: hi/lo activations, 2: exact bf16 activations)
+  ConvW conv(const std::string& prefix, int cout, int cin, int kh, int kw, int k_alloc_override = 0, int nseg_p = 3) {
     const DevTensor& t = find_raw(h, prefix + ".weight", ema);
     if (t.numel != (int64_t)cout * cin * kh * kw)
       throw Error(LIDM_ERR_STATE, "weight '" + prefix + ".weight' has unexpected size");
     ConvW c;
     c.cout = cout; c.cin = cin; c.kh = kh; c.kw = kw;
     c.n_alloc = round_n_alloc(cout);
-    c.k_alloc = k_alloc_override ? k_alloc_override : kh * kw * cin;
-    c.w = dev_alloc<bf16>(h, (size_t)c.n_alloc * c.k_alloc);
-    launch_pack_conv_weight(t.p, cout, cin, kh, kw, c.n_alloc, c.k_alloc, nullptr, nullptr, 1.f, 0, c.w, s);
+    c.nseg = precise ? nseg_p : 1;
+    if (!precise) {
+      c.k_alloc = k_alloc_override ? k_alloc_override : kh * kw * cin;
+      c.w = dev_alloc<bf16>(h, (size_t)c.n_alloc * c.k_alloc);
+      launch_pack_conv_weight(t.p, cout, cin, kh, kw, c.n_alloc, c.k_alloc, nullptr, nullptr, 1.f, 0, c.w, s);
+    } else if (k_alloc_override) {
+      // K layout [seg][kpad]: reorder to fp32 [cout][kpad] (k = tap*cin + c) and split-pack it as a 1x1 conv
+      float* tmp = nullptr;
+      LIDM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&tmp), (size_t)cout * k_alloc_override * sizeof(float)));
+      launch_reorder_weight_f32(t.p, cout, cin, kh * kw, k_alloc_override, tmp, s);
+      c.k_alloc = c.nseg * k_alloc_override;
+      c.w = dev_alloc<bf16>(h, (size_t)c.n_alloc * c.k_alloc);
+      launch_pack_conv_weight_split(tmp, cout, k_alloc_override, 1, 1, c.n_alloc, c.nseg, nullptr, 1.f, 0, c.w, s);
+      LIDM_CUDA_CHECK(cudaStreamSynchronize(s));
+      cudaFree(tmp);
+    } else {
+      c.k_alloc = kh * kw * c.nseg * cin;
+      c.w = dev_alloc<bf16>(h, (size_t)c.n_alloc * c.k_alloc);
+      launch_pack_conv_weight_split(t.p, cout, cin, kh, kw, c.n_alloc, c.nseg, nullptr, 1.f, 0, c.w, s);
+    }
     c.bias = f32(prefix + ".bias", cout);
     return c;
   }
@@ -302,10 +323,199 @@ struct Builder {
   }
 
   void gemm(const View& a, const ConvTaps& taps, const ConvW& w, const GemmEpilogue& ep) {
-    GemmB b; b.p = w.w; b.n_alloc = w.n_alloc; b.ld = w.k_alloc;
+    GemmB b; b.p = w.w; b.n_alloc = w.n_alloc; b.ld = w.k_alloc; b.nseg = w.nseg;
     const int N = w.cout;
-    op([=](cudaStream_t s) { launch_conv_gemm(a, taps, b, N, ep, s); }, PROF_GEMM, gemm_flops(a, taps.n, N), 0,
-       gemm_label(a, taps.n, N));
+    op([=](cudaStream_t s) { launch_conv_gemm(a, taps, b, N, ep, s); }, PROF_GEMM, gemm_flops(a, taps.n, N) * w.nseg, 0,
+       gemm_label(a, taps.n * w.nseg, N));
+  }
+
+  // =============================================================================================== precise mode
+  // fp32 residual stream (ViewF) between GEMMs; GEMM inputs are bf16 hi/lo planes (View with lo_off = C).
+  ViewF actf(int B, int H, int W, int C, Buf* buf) {
+    ViewF v;
+    v.B = B; v.H = H; v.W = W; v.C = C; v.ld = C;
+    buf->bytes = (size_t)B * H * W * C * sizeof(float);
+    buf->off = ap.alloc(buf->bytes);
+    v.p = reinterpret_cast<float*>(P->arena + buf->off);
+    return v;
+  }
+  View act_hl(int B, int H, int W, int C, int hl, int hr, Buf* buf) {
+    View v;
+    v.B = B; v.H = H; v.W = W; v.C = C; v.hl = hl; v.hr = hr; v.ld = 2 * C; v.lo_off = C;
+    buf->bytes = (size_t)B * H * (W + hl + hr) * 2 * C * sizeof(bf16);
+    buf->off = ap.alloc(buf->bytes);
+    v.p = reinterpret_cast<bf16*>(P->arena + buf->off);
+    return v;
+  }
+  static ViewF chan_slice_f(const ViewF& v, int c0, int C) {
+    ViewF s = v;
+    s.p = v.p + c0;
+    s.C = C;
+    return s;
+  }
+  void groupnorm_f(const ViewF& x, const View& y, const NormW& n, float eps, bool silu) {
+    Plan* P_ = P;
+    op([=](cudaStream_t s) { launch_groupnorm_f32(x, y, n.gamma, n.beta, eps, 32, silu, P_->gn_partials, s); }, PROF_NORM,
+       0, 8.0 * x.B * x.H * x.W * x.C, "gn(f32) C" + std::to_string(x.C) + " @" + std::to_string(x.H) + "x" + std::to_string(x.W));
+  }
+  static void set_out_f(GemmEpilogue& ep, const ViewF& dst) { ep.out_f32_nhwc = dst.p; ep.out_f32_ld = dst.ld; }
+  static void set_res_f(GemmEpilogue& ep, const ViewF& r) { ep.res_f32 = r.p; ep.res_f32_ld = r.ld; }
+
+  void res_block_p(const ResW& r, const ViewF& x, const ViewF& dst, int kh, int kw, int pl, int pr, int pt, float eps) {
+    const int B = x.B, H = x.H, W = x.W;
+    Buf bg1, bh, bg2, bsk, bxs;
+    View g1 = act_hl(B, H, W, r.cin, pl, pr, &bg1);
+    groupnorm_f(x, g1, r.n1, eps, true);
+    ViewF hmid = actf(B, H, W, r.cout, &bh);
+    {
+      GemmEpilogue ep;
+      ep.bias = r.c1.bias;
+      set_out_f(ep, hmid);
+      GemmB b; b.p = r.c1.w; b.n_alloc = r.c1.n_alloc; b.ld = r.c1.k_alloc; b.nseg = r.c1.nseg;
+      const ConvTaps taps = taps_rect(kh, kw, pl, pt);
+      const int N = r.cout, emb_off = r.emb_off;
+      Plan* P_ = P;
+      op([=](cudaStream_t s) {
+        GemmEpilogue e = ep;
+        if (emb_off >= 0) { e.rowadd = P_->rowadd_base + emb_off; e.rowadd_ld = P_->rowadd_ld; }
+        launch_conv_gemm(g1, taps, b, N, e, s);
+      }, PROF_GEMM, gemm_flops(g1, taps.n, N) * b.nseg, 0, gemm_label(g1, taps.n * b.nseg, N));
+    }
+    release(bg1);
+    View g2 = act_hl(B, H, W, r.cout, pl, pr, &bg2);
+    groupnorm_f(hmid, g2, r.n2, eps, true);
+    release(bh);
+    ViewF resid = x;
+    if (r.has_skip) {
+      View xs = act_hl(B, H, W, r.cin, 0, 0, &bxs);
+      op([=](cudaStream_t s) { launch_split_f32(x, xs, s); });
+      ViewF sk = actf(B, H, W, r.cout, &bsk);
+      GemmEpilogue ep;
+      ep.bias = r.skip.bias;
+      set_out_f(ep, sk);
+      gemm(xs, taps_1x1(), r.skip, ep);
+      release(bxs);
+      resid = sk;
+    }
+    {
+      GemmEpilogue ep;
+      ep.bias = r.c2.bias;
+      set_res_f(ep, resid);
+      set_out_f(ep, dst);
+      gemm(g2, taps_rect(kh, kw, pl, pt), r.c2, ep);
+    }
+    release(bg2);
+    if (r.has_skip) release(bsk);
+  }
+
+  void attn_block_p(const AttnW& a, const ViewF& x, const ViewF& dst) {
+    const int B = x.B, H = x.H, W = x.W, C = a.ch, T = H * W;
+    Buf bg, bqk, ba;
+    View g = act_hl(B, H, W, C, 0, 0, &bg);
+    groupnorm_f(x, g, a.n, 1e-5f, false);
+    View qkv = act(B, H, W, 3 * C, 0, 0, &bqk);
+    {
+      GemmEpilogue ep;
+      ep.bias = a.qkv.bias;
+      ep.out = qkv;
+      gemm(g, taps_1x1(), a.qkv, ep);
+    }
+    release(bg);
+    View ao = act(B, H, W, C, 0, 0, &ba);
+    const int heads = a.heads;
+    op([=](cudaStream_t s) { launch_attention_d32_packed(qkv.p, ao, B, T, heads, s); }, PROF_ATTN,
+       4.0 * B * heads * (double)T * T * 32, 0, "attn T" + std::to_string(T) + " heads" + std::to_string(heads));
+    release(bqk);
+    {
+      GemmEpilogue ep;
+      ep.bias = a.proj.bias;
+      set_res_f(ep, x);
+      set_out_f(ep, dst);
+      gemm(ao, taps_1x1(), a.proj, ep);
+    }
+    release(ba);
+  }
+
+  void dec_attn_block_p(const AttnW& a, const ViewF& x, const ViewF& dst) {
+    const int B = x.B, H = x.H, W = x.W, C = a.ch, T = H * W;
+    Buf bg, bqk, bvt, bs, bp, ba;
+    View g = act_hl(B, H, W, C, 0, 0, &bg);
+    groupnorm_f(x, g, a.n, 1e-6f, false);
+    View qk = act(B, H, W, 2 * C, 0, 0, &bqk);
+    bf16* vt = raw<bf16>((size_t)B * C * T, &bvt);
+    {
+      GemmEpilogue ep;
+      ep.bias = a.qkv.bias;
+      ep.out = qk;
+      ep.split_n = 2 * C;
+      ep.out_t = vt;
+      gemm(g, taps_1x1(), a.qkv, ep);
+    }
+    release(bg);
+    float* S = raw<float>((size_t)B * T * T, &bs);
+    {
+      View q = chan_slice(qk, 0, C);
+      GemmB kb; kb.p = qk.p + C; kb.n_alloc = T; kb.ld = 2 * C; kb.batch_stride = (int64_t)T * 2 * C;
+      GemmEpilogue ep;
+      ep.out_f32_nhwc = S;
+      op([=](cudaStream_t s) { launch_conv_gemm(q, taps_1x1(), kb, T, ep, s); }, PROF_GEMM, gemm_flops(q, 1, T));
+    }
+    bf16* Pm = raw<bf16>((size_t)B * T * T, &bp);
+    op([=](cudaStream_t s) { launch_softmax_rows(S, Pm, (int64_t)B * T, T, s); });
+    release(bs);
+    View ao = act(B, H, W, C, 0, 0, &ba);
+    {
+      View pv; pv.p = Pm; pv.B = B; pv.H = T / 128; pv.W = 128; pv.C = T; pv.ld = T;
+      GemmB vb; vb.p = vt; vb.n_alloc = C; vb.ld = T; vb.batch_stride = (int64_t)C * T;
+      GemmEpilogue ep;
+      View o2 = ao; o2.H = T / 128; o2.W = 128;
+      ep.out = o2;
+      op([=](cudaStream_t s) { launch_conv_gemm(pv, taps_1x1(), vb, C, ep, s); }, PROF_GEMM, gemm_flops(pv, 1, C));
+    }
+    release(bp); release(bqk); release(bvt);
+    {
+      GemmEpilogue ep;
+      ep.bias = a.proj.bias;
+      set_res_f(ep, x);
+      set_out_f(ep, dst);
+      gemm(ao, taps_1x1(), a.proj, ep);
+    }
+    release(ba);
+  }
+
+  void down_p(const ConvW& c, const ViewF& x, const ViewF& dst) {
+    const int B = x.B, Ho = x.H / 2, Wo = x.W / 2, C = x.C;
+    Buf bxs, bc;
+    View xs = act_hl(B, x.H, x.W, C, 0, 0, &bxs);
+    op([=](cudaStream_t s) { launch_split_f32(x, xs, s); });
+    bf16* col = raw<bf16>((size_t)B * Ho * Wo * 9 * 2 * C, &bc);
+    View xs2 = xs; xs2.C = 2 * C; xs2.lo_off = 0;      // im2col moves both planes as one 2C-channel tensor
+    op([=](cudaStream_t s) { launch_im2col_nhwc(xs2, 3, 3, 2, 1, 1, Ho, Wo, col, s); });
+    release(bxs);
+    View a; a.p = col; a.B = B; a.H = Ho; a.W = Wo; a.C = C; a.ld = 18 * C; a.lo_off = C; a.cphys = 18 * C;
+    ConvTaps taps; taps.n = 9; taps.cstep = 2 * C;     // row = [tap][hi C | lo C]
+    GemmEpilogue ep;
+    ep.bias = c.bias;
+    set_out_f(ep, dst);
+    gemm(a, taps, c, ep);
+    release(bc);
+  }
+
+  void up_p(const ConvW& c, const ViewF& x, const ViewF& dst) {
+    const int C = x.C;
+    Buf bxs, bu;
+    View xs = act_hl(x.B, x.H, x.W, C, 0, 0, &bxs);
+    op([=](cudaStream_t s) { launch_split_f32(x, xs, s); });
+    View u = act_hl(x.B, x.H * 2, x.W * 2, C, 1, 1, &bu);
+    View xs2 = xs; xs2.C = 2 * C; xs2.lo_off = 0;
+    View u2 = u; u2.C = 2 * C; u2.lo_off = 0;
+    op([=](cudaStream_t s) { launch_upsample_nearest2x(xs2, u2, s); });
+    release(bxs);
+    GemmEpilogue ep;
+    ep.bias = c.bias;
+    set_out_f(ep, dst);
+    gemm(u, taps_rect(3, 3, 1, 1), c, ep);
+    release(bu);
   }
   void groupnorm(const View& x, const View& y, const NormW& n, float eps, bool silu) {
     Plan* P_ = P;
@@ -687,6 +897,202 @@ void build_dec_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
   *high = b.ap.high();
 }
 
+// ------------------------------------------------------------------------------------------- precise plans
+void build_unet_plan_pass_p(lidm_handle* h, Plan* P, bool dry, size_t* high) {
+  Builder b{h, P, ArenaPlanner(), dry};
+  const lidm_config& cfg = h->cfg;
+  const int B = P->B;
+  const int n_in = (int)h->in_blocks.size(), n_out = (int)h->out_blocks.size();
+  std::vector<int> rh(n_in), rw(n_in);
+  {
+    int H = cfg.latent_h, W = cfg.latent_w;
+    for (int k = 0; k < n_in; ++k) {
+      if (h->in_blocks[k][0].kind == Layer::DOWN) { H /= 2; W /= 2; }
+      rh[k] = H; rw[k] = W;
+    }
+  }
+  std::vector<ViewF> cat(n_out);
+  std::vector<Buf> catbuf(n_out);
+  std::vector<int> Ca(n_out);
+  {
+    int ch_prev = h->mid_block.back().cout;
+    for (int i = 0; i < n_out; ++i) {
+      const int k = n_in - 1 - i;
+      Ca[i] = ch_prev;
+      cat[i] = b.actf(B, rh[k], rw[k], ch_prev + h->in_chans[k], &catbuf[i]);
+      ch_prev = h->out_blocks[i][0].cout;
+    }
+  }
+  auto run_layers = [&](const std::vector<Layer>& layers, ViewF x, const ViewF& dst) {
+    Buf prev_buf; bool have_prev = false;
+    for (size_t j = 0; j < layers.size(); ++j) {
+      const Layer& L = layers[j];
+      const bool last = (j + 1 == layers.size());
+      int Ho = x.H, Wo = x.W;
+      if (L.kind == Layer::DOWN) { Ho /= 2; Wo /= 2; }
+      if (L.kind == Layer::UP) { Ho *= 2; Wo *= 2; }
+      Buf ob; ViewF o;
+      if (last) o = dst;
+      else o = b.actf(B, Ho, Wo, L.cout, &ob);
+      switch (L.kind) {
+        case Layer::RES: b.res_block_p(L.r, x, o, 3, 3, 1, 1, 1, 1e-5f); break;
+        case Layer::ATTN: b.attn_block_p(L.a, x, o); break;
+        case Layer::DOWN: b.down_p(L.c, x, o); break;
+        case Layer::UP: b.up_p(L.c, x, o); break;
+        case Layer::CONV: throw Error(LIDM_ERR_INVALID, "unexpected conv layer");
+      }
+      if (have_prev) b.release(prev_buf);
+      prev_buf = ob; have_prev = !last;
+      x = o;
+    }
+  };
+  {
+    const int H = cfg.latent_h, W = cfg.latent_w;
+    const ConvW& cw = h->in_blocks[0][0].c;
+    const int kpad = cw.k_alloc / cw.nseg;
+    Buf bc;
+    bf16* col = b.raw<bf16>((size_t)B * H * W * 2 * kpad, &bc);
+    const int Cin = cfg.in_channels;
+    b.op([=](cudaStream_t s) { launch_im2col_nchw_f32_hl(P->x, B, Cin, H, W, 3, 3, 1, 1, col, kpad, s); });
+    View a; a.p = col; a.B = B; a.H = H; a.W = W; a.C = kpad; a.ld = 2 * kpad; a.lo_off = kpad;
+    GemmEpilogue ep;
+    ep.bias = cw.bias;
+    Builder::set_out_f(ep, Builder::chan_slice_f(cat[n_out - 1], Ca[n_out - 1], h->in_chans[0]));
+    b.gemm(a, taps_1x1(), cw, ep);
+    b.release(bc);
+  }
+  for (int k = 1; k < n_in; ++k) {
+    const int iprev = n_out - 1 - (k - 1), icur = n_out - 1 - k;
+    run_layers(h->in_blocks[k], Builder::chan_slice_f(cat[iprev], Ca[iprev], h->in_chans[k - 1]),
+               Builder::chan_slice_f(cat[icur], Ca[icur], h->in_chans[k]));
+  }
+  run_layers(h->mid_block, Builder::chan_slice_f(cat[0], Ca[0], h->in_chans[n_in - 1]),
+             Builder::chan_slice_f(cat[0], 0, Ca[0]));
+  Buf bfinal;
+  ViewF hfinal;
+  for (int i = 0; i < n_out; ++i) {
+    ViewF dst;
+    if (i + 1 < n_out) dst = Builder::chan_slice_f(cat[i + 1], 0, Ca[i + 1]);
+    else { hfinal = b.actf(B, cfg.latent_h, cfg.latent_w, h->out_blocks[i].back().cout, &bfinal); dst = hfinal; }
+    run_layers(h->out_blocks[i], cat[i], dst);
+    b.release(catbuf[i]);
+  }
+  {
+    Buf bg;
+    View g = b.act_hl(B, hfinal.H, hfinal.W, hfinal.C, 1, 1, &bg);
+    b.groupnorm_f(hfinal, g, h->out_norm, 1e-5f, true);
+    GemmB wb; wb.p = h->out_conv.w; wb.n_alloc = h->out_conv.n_alloc; wb.ld = h->out_conv.k_alloc; wb.nseg = h->out_conv.nseg;
+    const float* bias = h->out_conv.bias;
+    const int N = h->out_conv.cout;
+    const ConvTaps taps = taps_rect(3, 3, 1, 1);
+    b.op([=](cudaStream_t s) {
+      GemmEpilogue ep;
+      ep.bias = bias;
+      ep.out_f32_nchw = P->out;
+      if (P->ddim_x_prev != nullptr) {
+        ep.ddim_x = P->x; ep.ddim_noise = P->ddim_noise; ep.ddim_x_prev = P->ddim_x_prev;
+        ep.ddim_pred_x0 = P->ddim_pred_x0; ep.ddim_coef = P->ddim_coef;
+      }
+      launch_conv_gemm(g, taps, wb, N, ep, s);
+    }, PROF_GEMM, gemm_flops(g, taps.n, N) * wb.nseg);
+    b.release(bg);
+    b.release(bfinal);
+  }
+  *high = b.ap.high();
+}
+
+void build_dec_plan_pass_p(lidm_handle* h, Plan* P, bool dry, size_t* high) {
+  Builder b{h, P, ArenaPlanner(), dry};
+  const lidm_config& cfg = h->cfg;
+  const int B = P->B, lh = cfg.latent_h, lw = cfg.latent_w, zc = cfg.z_channels;
+  Buf bzq, bcol;
+  float* zq = b.raw<float>((size_t)B * zc * lh * lw, &bzq);
+  {
+    const float inv_scale = 1.0f / cfg.scale_factor;
+    const int n_embed = cfg.n_embed;
+    b.op([=](cudaStream_t s) {
+      launch_vq(P->x, B, zc, lh * lw, h->codebook, h->cb_norm, n_embed, P->quantize, h->pq_w, h->pq_b, inv_scale, zq,
+                P->idx_out, s);
+    });
+  }
+  const int kpad = h->dec_conv_in.k_alloc / h->dec_conv_in.nseg;
+  bf16* col = b.raw<bf16>((size_t)B * lh * lw * 2 * kpad, &bcol);
+  b.op([=](cudaStream_t s) { launch_im2col_nchw_f32_hl(zq, B, zc, lh, lw, 3, 3, 1, 1, col, kpad, s); });
+  b.release(bzq);
+  Buf bx;
+  ViewF x = b.actf(B, lh, lw, h->dec_top, &bx);
+  {
+    View a; a.p = col; a.B = B; a.H = lh; a.W = lw; a.C = kpad; a.ld = 2 * kpad; a.lo_off = kpad;
+    GemmEpilogue ep;
+    ep.bias = h->dec_conv_in.bias;
+    Builder::set_out_f(ep, x);
+    b.gemm(a, taps_1x1(), h->dec_conv_in, ep);
+  }
+  b.release(bcol);
+  auto step = [&](std::function<void(const ViewF&, const ViewF&)> f, int Ho, int Wo, int C) {
+    Buf bo;
+    ViewF o = b.actf(B, Ho, Wo, C, &bo);
+    f(x, o);
+    b.release(bx);
+    bx = bo; x = o;
+  };
+  step([&](const ViewF& i, const ViewF& o) { b.res_block_p(h->dec_mid1, i, o, 3, 3, 1, 1, 1, 1e-6f); }, lh, lw, h->dec_top);
+  step([&](const ViewF& i, const ViewF& o) { b.dec_attn_block_p(h->dec_attn, i, o); }, lh, lw, h->dec_top);
+  step([&](const ViewF& i, const ViewF& o) { b.res_block_p(h->dec_mid2, i, o, 3, 3, 1, 1, 1, 1e-6f); }, lh, lw, h->dec_top);
+  int H = lh, W = lw;
+  for (int lv = cfg.ae_n_ch_mult - 1; lv >= 0; --lv) {
+    const DecLevel& L = h->dec_levels[lv];
+    const int pl = 1, pr = L.kw == 3 ? 1 : 2, pt = L.kh == 3 ? 1 : 0;
+    for (const ResW& r : L.blocks)
+      step([&](const ViewF& i, const ViewF& o) { b.res_block_p(r, i, o, L.kh, L.kw, pl, pr, pt, 1e-6f); }, H, W, r.cout);
+    if (L.has_up) {
+      const int Ho = H * L.sh, Wo = W * L.sw;
+      const int ukh = L.up.kh, ukw = L.up.kw;
+      const int uh = (ukw - 1) / 2, upt = (ukh - 1) / 2;
+      step([&](const ViewF& i, const ViewF& o) {
+        Buf bu;
+        View u = b.act_hl(B, Ho, Wo, L.ch, uh, uh, &bu);
+        b.op([=](cudaStream_t s) { launch_upsample_bilinear_f32(i, u, s); });
+        GemmEpilogue ep;
+        ep.bias = L.up.bias;
+        Builder::set_out_f(ep, o);
+        b.gemm(u, taps_rect(ukh, ukw, uh, upt), L.up, ep);
+        b.release(bu);
+      }, Ho, Wo, L.ch);
+      H = Ho; W = Wo;
+    }
+  }
+  {
+    Buf bg;
+    View g = b.act_hl(B, H, W, h->dec_last, 1, 2, &bg);
+    b.groupnorm_f(x, g, h->dec_norm_out, 1e-6f, true);
+    b.release(bx);
+    GemmB wb; wb.p = h->dec_conv_out.w; wb.n_alloc = h->dec_conv_out.n_alloc; wb.ld = h->dec_conv_out.k_alloc;
+    wb.nseg = h->dec_conv_out.nseg;
+    const float* bias = h->dec_conv_out.bias;
+    const int N = h->dec_conv_out.cout;
+    const ConvTaps taps = taps_rect(1, 4, 1, 0);
+    if (cfg.ae_use_mask) {
+      Buf bd;
+      float* dec = b.raw<float>((size_t)B * N * H * W, &bd);
+      b.op([=](cudaStream_t s) {
+        GemmEpilogue ep; ep.bias = bias; ep.out_f32_nchw = dec;
+        launch_conv_gemm(g, taps, wb, N, ep, s);
+      }, PROF_GEMM, gemm_flops(g, taps.n, N) * wb.nseg);
+      const int HW = H * W;
+      b.op([=](cudaStream_t s) { launch_mask_select(dec, B, HW, P->out, s); });
+      b.release(bd);
+    } else {
+      b.op([=](cudaStream_t s) {
+        GemmEpilogue ep; ep.bias = bias; ep.out_f32_nchw = P->out;
+        launch_conv_gemm(g, taps, wb, N, ep, s);
+      }, PROF_GEMM, gemm_flops(g, taps.n, N) * wb.nseg);
+    }
+    b.release(bg);
+  }
+  *high = b.ap.high();
+}
+
 Plan* get_plan(lidm_handle* h, std::map<int, std::unique_ptr<Plan>>& cache, int B,
                void (*pass)(lidm_handle*, Plan*, bool, size_t*)) {
   auto it = cache.find(B);
@@ -767,9 +1173,14 @@ AttnW pack_unet_attn(Packer& pk, const std::string& p, int ch, int heads) {
   const float scale = 1.0f / std::sqrt(std::sqrt((float)d));
   ConvW c;
   c.cout = 3 * ch; c.cin = ch; c.kh = c.kw = 1;
-  c.n_alloc = round_n_alloc(3 * ch); c.k_alloc = ch;
+  c.n_alloc = round_n_alloc(3 * ch);
+  c.nseg = pk.precise ? 3 : 1;
+  c.k_alloc = c.nseg * ch;
   c.w = dev_alloc<bf16>(h, (size_t)c.n_alloc * c.k_alloc);
-  launch_pack_conv_weight(w.p, 3 * ch, ch, 1, 1, c.n_alloc, c.k_alloc, perm_dev, nullptr, scale, 2 * ch, c.w, pk.s);
+  if (pk.precise)
+    launch_pack_conv_weight_split(w.p, 3 * ch, ch, 1, 1, c.n_alloc, 3, perm_dev, scale, 2 * ch, c.w, pk.s);
+  else
+    launch_pack_conv_weight(w.p, 3 * ch, ch, 1, 1, c.n_alloc, c.k_alloc, perm_dev, nullptr, scale, 2 * ch, c.w, pk.s);
   std::vector<float> bh(3 * ch), bp(3 * ch);
   LIDM_CUDA_CHECK(cudaMemcpyAsync(bh.data(), bsrc.p, bh.size() * sizeof(float), cudaMemcpyDeviceToHost, pk.s));
   LIDM_CUDA_CHECK(cudaStreamSynchronize(pk.s));
@@ -777,7 +1188,7 @@ AttnW pack_unet_attn(Packer& pk, const std::string& p, int ch, int heads) {
   c.bias = dev_alloc<float>(h, bp.size());
   LIDM_CUDA_CHECK(cudaMemcpy(c.bias, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice));
   a.qkv = c;
-  a.proj = pk.conv(p + ".proj_out", ch, ch, 1, 1);
+  a.proj = pk.conv(p + ".proj_out", ch, ch, 1, 1, 0, 2);   // its input (attention output) is exact bf16
   return a;
 }
 
@@ -789,7 +1200,9 @@ AttnW pack_dec_attn(Packer& pk, const std::string& p, int ch) {
   a.n = pk.norm(p + ".norm", ch);
   ConvW c;
   c.cout = 3 * ch; c.cin = ch; c.kh = c.kw = 1;
-  c.n_alloc = round_n_alloc(3 * ch); c.k_alloc = ch;
+  c.n_alloc = round_n_alloc(3 * ch);
+  c.nseg = pk.precise ? 3 : 1;
+  c.k_alloc = c.nseg * ch;
   if (c.n_alloc != 3 * ch) throw Error(LIDM_ERR_INVALID, "decoder attention channels must be a multiple of 128");
   c.w = dev_alloc<bf16>(h, (size_t)c.n_alloc * c.k_alloc);
   c.bias = dev_alloc<float>(h, 3 * ch);
@@ -800,14 +1213,18 @@ AttnW pack_dec_attn(Packer& pk, const std::string& p, int ch) {
     const DevTensor& w = find_raw(h, p + names[i] + ".weight", pk.ema);
     const DevTensor& bsrc = find_raw(h, p + names[i] + ".bias", pk.ema);
     if (w.numel != (int64_t)ch * ch || bsrc.numel != ch) throw Error(LIDM_ERR_STATE, "decoder attention weight size");
-    launch_pack_conv_weight(w.p, ch, ch, 1, 1, ch, ch, nullptr, nullptr, i == 0 ? scale : 1.f, i == 0 ? ch : 0,
-                            c.w + (size_t)i * ch * ch, pk.s);
+    if (pk.precise)
+      launch_pack_conv_weight_split(w.p, ch, ch, 1, 1, ch, 3, nullptr, i == 0 ? scale : 1.f, i == 0 ? ch : 0,
+                                    c.w + (size_t)i * ch * c.k_alloc, pk.s);
+    else
+      launch_pack_conv_weight(w.p, ch, ch, 1, 1, ch, ch, nullptr, nullptr, i == 0 ? scale : 1.f, i == 0 ? ch : 0,
+                              c.w + (size_t)i * ch * ch, pk.s);
     LIDM_CUDA_CHECK(cudaMemcpy(bh.data(), bsrc.p, ch * sizeof(float), cudaMemcpyDeviceToHost));
     if (i == 0) for (float& v : bh) v *= scale;
     LIDM_CUDA_CHECK(cudaMemcpy(c.bias + (size_t)i * ch, bh.data(), ch * sizeof(float), cudaMemcpyHostToDevice));
   }
   a.qkv = c;
-  a.proj = pk.conv(p + ".proj_out", ch, ch, 1, 1);
+  a.proj = pk.conv(p + ".proj_out", ch, ch, 1, 1, 0, 2);
   return a;
 }
 
@@ -819,6 +1236,7 @@ bool in_list(const int32_t* v, int n, int x) {
 void finalize(lidm_handle* h, bool use_ema) {
   const lidm_config& cfg = h->cfg;
   Packer pk{h, use_ema};
+  pk.precise = cfg.precision != 0;
   const std::string U = "model.diffusion_model.";
   const int mc = cfg.model_channels, ted = mc * 4;
   h->ted = ted;
@@ -1154,7 +1572,7 @@ int lidm_unet_forward(lidm_handle* h, const float* x, const int64_t* t, float* e
     require_ready(h, B);
     LIDM_REQUIRE(x != nullptr && t != nullptr && eps_out != nullptr, "null tensor");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    Plan* P = get_plan(h, h->unet_plans, B, build_unet_plan_pass);
+    Plan* P = get_plan(h, h->unet_plans, B, h->cfg.precision ? build_unet_plan_pass_p : build_unet_plan_pass);
     ensure_time_buffers(h, B);
     run_time_embed(h, t, B, s);
     P->x = x; P->out = eps_out;
@@ -1189,7 +1607,7 @@ int lidm_ddim_sample(lidm_handle* h, float* x_inout, const int64_t* timesteps, c
     const lidm_config& cfg = h->cfg;
     for (int i = 0; i < n_steps; ++i)
       LIDM_REQUIRE(timesteps[i] >= 0, "negative timestep");
-    Plan* P = get_plan(h, h->unet_plans, B, build_unet_plan_pass);
+    Plan* P = get_plan(h, h->unet_plans, B, h->cfg.precision ? build_unet_plan_pass_p : build_unet_plan_pass);
     ensure_time_buffers(h, n_steps);
     const size_t elems = (size_t)B * cfg.in_channels * cfg.latent_h * cfg.latent_w;
     if (elems > h->xbuf_elems) {
@@ -1239,7 +1657,7 @@ int lidm_vq_decode(lidm_handle* h, const float* z, int32_t force_not_quantize, f
     require_ready(h, B);
     LIDM_REQUIRE(z != nullptr && img_out != nullptr, "null tensor");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    Plan* P = get_plan(h, h->dec_plans, B, build_dec_plan_pass);
+    Plan* P = get_plan(h, h->dec_plans, B, h->cfg.precision ? build_dec_plan_pass_p : build_dec_plan_pass);
     P->x = z; P->out = img_out; P->idx_out = idx_out; P->quantize = force_not_quantize ? 0 : 1;
     run_plan(P, s);
   });

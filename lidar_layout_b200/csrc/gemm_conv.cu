@@ -28,8 +28,10 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
 struct GemmKernelParams {
   int tiles_w, tiles_per_img, Wbox, Hbox;
   int hl;
-  int ntaps;
-  int8_t dx[9], dy[9];
+  int ntaps;                 // virtual taps = spatial taps x operand-split segments (<= 27)
+  int8_t dx[27], dy[27];
+  int a_coff[27];            // channel offset of the A plane read by this virtual tap (hi / lo plane)
+  int b_koff[27];            // first K column of this virtual tap in the B matrix
   int kchunks;
   int N, H, W;
   int wt_batched;
@@ -38,6 +40,9 @@ struct GemmKernelParams {
   int rowadd_ld;
   const bf16* res;
   int res_ld, res_hl, res_Wp;
+  const float* res_f32;      // fp32 channels-last residual (precise mode), no halo
+  int res_f32_ld;
+  int out_f32_ld;            // channel stride of out_f32_nhwc (concat views)
   bf16* out;
   int out_ld, out_hl, out_hr, out_Wp;
   int split_n;
@@ -50,244 +55,6 @@ struct GemmKernelParams {
   float* ddim_pred_x0;
   const float* ddim_coef;
 };
-
-template <int BN, int STAGES>
-struct SmemLayout {
-  static constexpr int B_STAGE_BYTES = BN * BK * 2;
-  static constexpr int A_OFF = 0;
-  static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
-  static constexpr int BAR_OFF = B_OFF + STAGES * ((B_STAGE_BYTES + 1023) / 1024 * 1024);
-  static constexpr int B_STRIDE = (B_STAGE_BYTES + 1023) / 1024 * 1024;
-  static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // + manual 1 KiB alignment slack
-};
-
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(192)
-conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const GemmKernelParams p) {
-  using L = SmemLayout<BN, STAGES>;
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* accum_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-
-  const int m_tile = blockIdx.x;
-  const int n0 = blockIdx.y * BN;
-  const int b = m_tile / p.tiles_per_img;
-  const int r = m_tile - b * p.tiles_per_img;
-  const int th = r / p.tiles_w;
-  const int h0 = th * p.Hbox;
-  const int w0 = (r - th * p.tiles_w) * p.Wbox;
-  const int num_it = p.ntaps * p.kchunks;
-
-  if (threadIdx.x == 0) {
-    prefetch_tensormap(&tmA);
-    prefetch_tensormap(&tmB);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    mbar_init(accum_bar, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
-  }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      int it = 0;
-      for (int tap = 0; tap < p.ntaps; ++tap) {
-        const int x = w0 + p.hl + p.dx[tap];
-        const int y = h0 + p.dy[tap];
-        for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + L::B_STAGE_BYTES);
-          tma_load_4d(smem + L::A_OFF + s * A_STAGE_BYTES, &tmA, &full_bar[s], kc * BK, x, y, b);
-          tma_load_3d(smem + L::B_OFF + s * L::B_STRIDE, &tmB, &full_bar[s], it * BK, n0, p.wt_batched ? b : 0);
-          if (++s == STAGES) { s = 0; ph ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
-      int s = 0;
-      uint32_t ph = 0;
-      for (int it = 0; it < num_it; ++it) {
-        mbar_wait(&full_bar[s], ph);
-        tcgen05_fence_after();
-        const uint64_t adesc = make_kmajor_desc<128>(smem_u32(smem + L::A_OFF + s * A_STAGE_BYTES));
-        const uint64_t bdesc = make_kmajor_desc<128>(smem_u32(smem + L::B_OFF + s * L::B_STRIDE));
-#pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 bf16 = 32 bytes along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
-          umma_bf16_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
-        }
-        umma_commit(&empty_bar[s]);  // frees this smem stage once the MMAs above have read it
-        if (++s == STAGES) { s = 0; ph ^= 1; }
-      }
-      umma_commit(accum_bar);  // accumulator complete
-    }
-  } else {
-    // ------------------------------------------------------------------ epilogue warps (TMEM -> regs -> global)
-    mbar_wait(accum_bar, 0);
-    tcgen05_fence_after();
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    const int row = q * 32 + lane;
-    const int hh = row / p.Wbox;
-    const int h = h0 + hh;
-    const int w = w0 + (row - hh * p.Wbox);
-    const int HW = p.H * p.W;
-    const int pix = h * p.W + w;
-    const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-
-    float coef[5] = {0, 0, 0, 0, 0};
-    if (p.ddim_x_prev != nullptr) {
-#pragma unroll
-      for (int i = 0; i < 5; ++i) coef[i] = __ldg(p.ddim_coef + i);
-    }
-
-    constexpr int CH = BN < 32 ? BN : 32;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += CH) {
-      float v[CH];
-      {
-        uint32_t raw[CH];
-        if constexpr (CH == 32) tmem_ld_32x32b_x32(taddr_row + c0, raw);
-        else tmem_ld_32x32b_x16(taddr_row + c0, raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(raw[j]);
-      }
-      const int n = n0 + c0;
-      if (n >= p.N) break;  // padded columns (warp-uniform)
-      if (p.bias != nullptr) {
-#pragma unroll
-        for (int j = 0; j < CH; ++j)
-          if (n + j < p.N) v[j] += __ldg(p.bias + n + j);
-      }
-      if (p.rowadd != nullptr) {
-        const float* ra = p.rowadd + (size_t)b * p.rowadd_ld + n;
-#pragma unroll
-        for (int j = 0; j < CH; ++j)
-          if (n + j < p.N) v[j] += __ldg(ra + j);
-      }
-      if (p.res != nullptr) {
-        const bf16* rp = p.res + ((size_t)(b * p.H + h) * p.res_Wp + (w + p.res_hl)) * p.res_ld + n;
-        if constexpr (CH == 32) {
-          const uint4* r4 = reinterpret_cast<const uint4*>(rp);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint4 u = __ldg(r4 + i);
-            float2 f;
-            f = unpack_bf16(u.x); v[i * 8 + 0] += f.x; v[i * 8 + 1] += f.y;
-            f = unpack_bf16(u.y); v[i * 8 + 2] += f.x; v[i * 8 + 3] += f.y;
-            f = unpack_bf16(u.z); v[i * 8 + 4] += f.x; v[i * 8 + 5] += f.y;
-            f = unpack_bf16(u.w); v[i * 8 + 6] += f.x; v[i * 8 + 7] += f.y;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < CH; ++j)
-            if (n + j < p.N) v[j] += __bfloat162float(rp[j]);
-        }
-      }
-
-      if (n >= p.split_n) {
-        // transposed bf16 store (V^T for the attention kernel): lanes = consecutive pixels => coalesced per channel
-        bf16* ot = p.out_t + ((size_t)b * (p.N - p.split_n) + (n - p.split_n)) * HW + pix;
-#pragma unroll
-        for (int j = 0; j < CH; ++j) ot[(size_t)j * HW] = __float2bfloat16(v[j]);
-      } else if (p.out != nullptr) {
-        if constexpr (CH == 32) {
-          uint4 pk[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            pk[i].x = pack_bf16(v[i * 8 + 0], v[i * 8 + 1]);
-            pk[i].y = pack_bf16(v[i * 8 + 2], v[i * 8 + 3]);
-            pk[i].z = pack_bf16(v[i * 8 + 4], v[i * 8 + 5]);
-            pk[i].w = pack_bf16(v[i * 8 + 6], v[i * 8 + 7]);
-          }
-          const size_t rowbase = (size_t)(b * p.H + h) * p.out_Wp;
-          uint4* o = reinterpret_cast<uint4*>(p.out + (rowbase + w + p.out_hl) * p.out_ld + n);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) o[i] = pk[i];
-          if (w < p.out_hr) {  // right halo holds logical pixels 0..hr-1
-            uint4* o2 = reinterpret_cast<uint4*>(p.out + (rowbase + p.W + p.out_hl + w) * p.out_ld + n);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) o2[i] = pk[i];
-          }
-          if (w >= p.W - p.out_hl) {  // left halo holds logical pixels W-hl..W-1
-            uint4* o2 = reinterpret_cast<uint4*>(p.out + (rowbase + (w - (p.W - p.out_hl))) * p.out_ld + n);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) o2[i] = pk[i];
-          }
-        } else {
-          bf16* o = p.out + ((size_t)(b * p.H + h) * p.out_Wp + (w + p.out_hl)) * p.out_ld + n;
-#pragma unroll
-          for (int j = 0; j < CH; ++j)
-            if (n + j < p.N) o[j] = __float2bfloat16(v[j]);
-        }
-      }
-      if (p.out_f32_nhwc != nullptr) {
-        float* o = p.out_f32_nhwc + ((size_t)b * HW + pix) * p.N + n;
-        if constexpr (CH == 32) {
-          if (n + 32 <= p.N) {
-            float4* o4 = reinterpret_cast<float4*>(o);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < CH; ++j)
-              if (n + j < p.N) o[j] = v[j];
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < CH; ++j)
-            if (n + j < p.N) o[j] = v[j];
-        }
-      }
-      if (p.out_f32_nchw != nullptr || p.ddim_x_prev != nullptr) {
-#pragma unroll
-        for (int j = 0; j < CH; ++j) {
-          if (n + j < p.N) {
-            const size_t idx = ((size_t)b * p.N + (n + j)) * HW + pix;
-            if (p.out_f32_nchw != nullptr) p.out_f32_nchw[idx] = v[j];
-            if (p.ddim_x_prev != nullptr) {
-              const float nz = p.ddim_noise != nullptr ? p.ddim_noise[idx] : 0.f;
-              float xp, x0;
-              ddim_update(p.ddim_x[idx], v[j], nz, coef, xp, x0);
-              p.ddim_x_prev[idx] = xp;
-              if (p.ddim_pred_x0 != nullptr) p.ddim_pred_x0[idx] = x0;
-            }
-          }
-        }
-      }
-    }
-    tcgen05_fence_before();
-  }
-
-  __syncthreads();
-  if (warp == 1) {
-    tcgen05_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
-  }
-}
 
 // =====================================================================================================
 // Persistent variant: one CTA per SM walks tiles (m fastest, so concurrently running CTAs share the weight tile in
@@ -360,8 +127,9 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
             mbar_wait(&empty_bar[s], ph ^ 1);
             mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + L::B_STAGE_BYTES);
-            tma_load_4d(smem + L::A_OFF + s * A_STAGE_BYTES, &tmA, &full_bar[s], kc * BK, x, y, b);
-            tma_load_3d(smem + L::B_OFF + s * L::B_STRIDE, &tmB, &full_bar[s], it * BK, n0, p.wt_batched ? b : 0);
+            tma_load_4d(smem + L::A_OFF + s * A_STAGE_BYTES, &tmA, &full_bar[s], p.a_coff[tap] + kc * BK, x, y, b);
+            tma_load_3d(smem + L::B_OFF + s * L::B_STRIDE, &tmB, &full_bar[s], p.b_koff[tap] + kc * BK, n0,
+                        p.wt_batched ? b : 0);
             if (++s == STAGES) { s = 0; ph ^= 1; }
           }
         }
@@ -568,6 +336,21 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           for (int j = 0; j < CH; ++j)
             if (n + j < p.N) v[j] += __bfloat162float(rp[j]);
         }
+        if (p.res_f32 != nullptr) {
+          const float* rp = p.res_f32 + ((size_t)b * HW + pix) * p.res_f32_ld + n;
+          if (CH == 32 && n + 32 <= p.N) {
+            const float4* r4 = reinterpret_cast<const float4*>(rp);
+#pragma unroll
+            for (int i = 0; i < CH / 4; ++i) {
+              const float4 t = __ldg(r4 + i);
+              v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (n + j < p.N) v[j] += __ldg(rp + j);
+          }
+        }
 
         if (n >= p.split_n) {
           bf16* ot = p.out_t + ((size_t)b * (p.N - p.split_n) + (n - p.split_n)) * HW + pix;
@@ -614,7 +397,7 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
         }
         if (p.out_f32_nhwc != nullptr) {
-          float* o = p.out_f32_nhwc + ((size_t)b * HW + pix) * p.N + n;
+          float* o = p.out_f32_nhwc + ((size_t)b * HW + pix) * p.out_f32_ld + n;
           if (CH == 32 && n + 32 <= p.N) {
             float4* o4 = reinterpret_cast<float4*>(o);
 #pragma unroll
@@ -681,21 +464,6 @@ void launch_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtens
   LIDM_COUNT_LAUNCH(1);
 }
 
-template <int BN, int STAGES>
-void launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKernelParams& p, dim3 grid,
-                 cudaStream_t stream) {
-  using L = SmemLayout<BN, STAGES>;
-  static bool configured = false;
-  if (!configured) {
-    LIDM_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         L::TOTAL));
-    configured = true;
-  }
-  conv_gemm_kernel<BN, STAGES><<<grid, 192, L::TOTAL, stream>>>(tmA, tmB, p);
-  LIDM_CUDA_CHECK(cudaGetLastError());
-  LIDM_COUNT_LAUNCH(1);
-}
-
 }  // namespace
 
 void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int N, const GemmEpilogue& ep,
@@ -707,12 +475,14 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
   LIDM_REQUIRE(a.C % BK == 0, "Cin must be a multiple of 64 (use the im2col path otherwise)");
   LIDM_REQUIRE(a.ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a.p) & 15) == 0, "activation view must be 16B aligned");
   LIDM_REQUIRE(taps.n >= 1 && taps.n <= 9, "1..9 taps");
+  const int nseg = wtb.nseg;
+  LIDM_REQUIRE(nseg >= 1 && nseg <= 3 && (nseg != 3 || a.lo_off > 0), "operand-split segments");
   const int W = a.W, H = a.H;
   LIDM_REQUIRE((W <= BM && BM % W == 0) || (W % BM == 0), "W must divide or be a multiple of 128");
   const int Wbox = W < BM ? W : BM;
   const int Hbox = BM / Wbox;
   LIDM_REQUIRE(H % Hbox == 0, "H must be a multiple of 128/W");
-  for (int t = 0; t < taps.n; ++t) {
+  for (int t = 0; t < taps.n && taps.cstep == 0; ++t) {
     LIDM_REQUIRE(-taps.dx[t] <= a.hl && taps.dx[t] <= a.hr, "tap exceeds the materialised halo");
   }
   int BN;
@@ -733,8 +503,16 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
   p.tiles_w = W / Wbox;
   p.tiles_per_img = p.tiles_w * (H / Hbox);
   p.Wbox = Wbox; p.Hbox = Hbox; p.hl = a.hl;
-  p.ntaps = taps.n;
-  for (int t = 0; t < 9; ++t) { p.dx[t] = taps.dx[t]; p.dy[t] = taps.dy[t]; }
+  p.ntaps = taps.n * nseg;
+  for (int t = 0; t < taps.n; ++t) {
+    for (int sg = 0; sg < nseg; ++sg) {
+      const int vt = t * nseg + sg;
+      p.dx[vt] = taps.cstep ? 0 : taps.dx[t];
+      p.dy[vt] = taps.cstep ? 0 : taps.dy[t];
+      p.a_coff[vt] = t * taps.cstep + ((nseg == 3 && sg == 1) ? a.lo_off : 0);
+      p.b_koff[vt] = vt * a.C;
+    }
+  }
   p.kchunks = a.C / BK;
   p.N = N; p.H = H; p.W = W;
   p.wt_batched = wt_batched ? 1 : 0;
@@ -752,28 +530,23 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
   p.split_n = ep.split_n; p.out_t = ep.out_t;
   if (ep.out_t != nullptr) LIDM_REQUIRE(ep.split_n % BN == 0, "split_n must be tile aligned");
   p.out_f32_nchw = ep.out_f32_nchw; p.out_f32_nhwc = ep.out_f32_nhwc;
+  p.out_f32_ld = ep.out_f32_ld ? ep.out_f32_ld : N;
+  p.res_f32 = ep.res_f32; p.res_f32_ld = ep.res_f32_ld;
+  if (ep.res_f32 != nullptr) LIDM_REQUIRE(ep.out.p == nullptr || ep.out.hl + ep.out.hr > 0 || true, "fp32 residual");
   p.ddim_x = ep.ddim_x; p.ddim_noise = ep.ddim_noise; p.ddim_x_prev = ep.ddim_x_prev;
   p.ddim_pred_x0 = ep.ddim_pred_x0; p.ddim_coef = ep.ddim_coef;
 
-  const uint64_t Ktot = (uint64_t)taps.n * a.C;
+  const uint64_t Ktot = (uint64_t)taps.n * nseg * a.C;
   CUtensorMap tmA = make_tma_act(a, BK, Wbox, Hbox, 128);
   const uint64_t wld = wtb.ld != 0 ? (uint64_t)wtb.ld : Ktot;
   LIDM_REQUIRE(wld >= Ktot && wld % 8 == 0 && (reinterpret_cast<uintptr_t>(wt) & 15) == 0, "weight operand alignment");
   CUtensorMap tmB = make_tma_3d(wt, Ktot, (uint64_t)n_alloc, wt_batched ? (uint64_t)a.B : 1, wld * 2,
                                 wt_batched ? (uint64_t)wtb.batch_stride * 2 : wld * 2 * (uint64_t)n_alloc, BK, BN,
                                 128);
-  static const bool legacy = getenv("LIDM_GEMM_LEGACY") != nullptr;
-  if (legacy) {
-    LIDM_REQUIRE(BN != 256, "legacy kernel has no 256-wide tile (set LIDM_GEMM_BN=128)");
-    dim3 grid(a.B * p.tiles_per_img, n_alloc / BN);
-    if (BN == 128) launch_impl<128, 3>(tmA, tmB, p, grid, stream);
-    else if (BN == 64) launch_impl<64, 4>(tmA, tmB, p, grid, stream);
-    else launch_impl<16, 4>(tmA, tmB, p, grid, stream);
-    return;
-  }
   const int num_m_tiles = a.B * p.tiles_per_img;
   const int num_tiles = num_m_tiles * (n_alloc / BN);
-  const int use_tma_store = (ep.out.p != nullptr && ep.out.hl == 0 && ep.out.hr == 0 && ep.out_t == nullptr && BN >= 64)
+  const int use_tma_store = (ep.out.p != nullptr && ep.out.hl == 0 && ep.out.hr == 0 && ep.out_t == nullptr && BN >= 64 &&
+                             ep.res_f32 == nullptr && ep.out_f32_nhwc == nullptr && ep.out_f32_nchw == nullptr)
                                 ? 1 : 0;
   CUtensorMap tmO = tmA;
   if (use_tma_store) tmO = make_tma_act(ep.out, 64, Wbox, Hbox, 128);

@@ -42,7 +42,11 @@ class _FirstStage:
 class LatentDiffusion:
     """Drop-in for the sampling-side API of lidm.models.diffusion.ddpm.LatentDiffusion."""
 
-    def __init__(self, cfg: LidmConfig, device: Optional[torch.device] = None, use_ema: bool = True):
+    def __init__(self, cfg: LidmConfig, device: Optional[torch.device] = None, use_ema: bool = True,
+                 precision: Optional[str] = None):
+        if precision is not None:
+            import dataclasses
+            cfg = dataclasses.replace(cfg, precision=precision)
         self.cfg = cfg
         self.engine = Engine(cfg, device)
         self.device = self.engine.device
@@ -66,10 +70,11 @@ class LatentDiffusion:
 
     # ---- construction ---------------------------------------------------------------------------------
     @classmethod
-    def from_config(cls, config, device=None, use_ema=True) -> "LatentDiffusion":
-        """config: path to a reference YAML, or the parsed dict (what OmegaConf.load would give)."""
+    def from_config(cls, config, device=None, use_ema=True, precision=None) -> "LatentDiffusion":
+        """config: path to a reference YAML, or the parsed dict (what OmegaConf.load would give).
+        precision: None / "bf16" (fast path) or "fp32" (precise operand-split path)."""
         cfg = from_yaml(config) if isinstance(config, str) else from_reference_dict(config)
-        return cls(cfg, device, use_ema)
+        return cls(cfg, device, use_ema, precision)
 
     def register_schedule(self):
         """DDPM.register_schedule (ddpm.py:120-160)."""

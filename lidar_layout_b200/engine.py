@@ -51,6 +51,9 @@ def to_cconfig(cfg: LidmConfig) -> _lib.CConfig:
     for i, s in enumerate(a.strides):
         c.ae_strides[i][0], c.ae_strides[i][1] = s
     c.scale_factor = float(cfg.scale_factor)
+    if cfg.precision not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    c.precision = 1 if cfg.precision == "fp32" else 0
     return c
 
 

@@ -108,12 +108,17 @@ def check_attn():
 
 
 def _model(name):
-    import numpy as np, torch
+    import numpy as np, torch, dataclasses
     from lidar_layout_b200 import config as C
     from lidar_layout_b200.engine import Engine
     from lidar_layout_b200.weights import random_state_dict
+    precise = name.endswith("_p")
+    name = name[:-2] if precise else name
     cfg = C.tiny() if name == "tiny" else C.kitti_uncond()
+    if precise:
+        cfg = dataclasses.replace(cfg, precision="fp32")
     g = np.load(os.path.join(ROOT, f"tests/golden/{name}.npz"))
+    name = name + ("_p" if precise else "")
     t0 = time.time()
     sd = random_state_dict(cfg, 0)
     eng = Engine(cfg).load_state_dict(sd)
@@ -126,6 +131,7 @@ def _check_model(name):
     import numpy as np, torch
     from oracle.make_golden import inputs_for
     cfg, g, eng, sd = _model(name)
+    name = name + "" 
     B, S = int(g["B"]), int(g["S_short"])
     x_T, noise, z = inputs_for(cfg, B, S + 2)
     for tv in (501, 21):
@@ -153,6 +159,14 @@ def check_tiny():
 
 def check_kitti():
     _check_model("kitti_uncond")
+
+
+def check_tiny_p():
+    _check_model("tiny_p")
+
+
+def check_kitti_p():
+    _check_model("kitti_uncond_p")
 
 
 CHECKS = ["backproject", "ddim", "gn", "conv", "attn", "tiny", "kitti"]
