@@ -76,10 +76,15 @@ struct PersistLayout {
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;
   static constexpr uint32_t ACC_COLS = BN;                          // TMEM columns per accumulator buffer
   static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  // epilogue warps: 4 cover the 128 TMEM lanes; wide tiles use two such groups, each draining half of the columns
+  static constexpr int EPI_WARPS = BN >= 64 ? 8 : 4;
+  static constexpr int EPI_THREADS = EPI_WARPS * 32;
+  static constexpr int THREADS = 64 + EPI_THREADS;
+  static constexpr int COLS = BN / (EPI_WARPS / 4);                 // columns drained by one epilogue thread
 };
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__((PersistLayout<BN, STAGES>::THREADS), 1)
 conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmO, const GemmKernelParams p, int num_m_tiles,
                          int num_tiles, int use_tma_store) {
@@ -102,7 +107,7 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     prefetch_tensormap(&tmB);
     if (use_tma_store) prefetch_tensormap(&tmO);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], L::EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, L::TMEM_COLS); tmem_relinquish(); }
@@ -161,9 +166,11 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   } else {
     // ------------------------------------------------------------------ epilogue warps
-    const int q = warp & 3;
+    const int q = warp & 3;              // TMEM lane quadrant this warp may access
+    const int wg = (warp - 2) >> 2;      // column group (0 or 1)
+    const int col_lo = wg * L::COLS;     // this thread drains tile columns [col_lo, col_lo + COLS)
     const int row = q * 32 + lane;
-    const int e = threadIdx.x - 64;   // 0..127
+    const int e = threadIdx.x - 64;      // 0..EPI_THREADS-1
     const int hh = row / p.Wbox;
     const int ww = row - hh * p.Wbox;
     const int HW = p.H * p.W;
@@ -185,7 +192,7 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int h = h0 + hh, w = w0 + ww;
       const int pix = h * p.W + w;
       // stage bias + per-sample row (timestep embedding) for this tile's columns
-      for (int i = e; i < BN; i += 128) {
+      for (int i = e; i < BN; i += L::EPI_THREADS) {
         const int n = n0 + i;
         float v = 0.f;
         if (n < p.N) {
@@ -195,7 +202,7 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         sbias[ab * SB + i] = v;
       }
       if (use_tma_store && e == 0) tma_store_wait_read<L::OUT_BUFS - 1>();   // this tile's staging buffer is free
-      named_bar_sync(1, 128);
+      named_bar_sync(1, L::EPI_THREADS);
       const uint32_t taddr_row = tmem_base + ab * L::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
       uint8_t* stage_out = smem + L::OUT_OFF + (L::OUT_BUFS == 2 ? ab : 0) * L::OUT_BUF_BYTES;
       if constexpr (BN >= 64) {
@@ -203,18 +210,19 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           // Fast path (bf16 output through TMA stores): the residual row is requested before the accumulator is
           // even ready, the whole accumulator row is pulled out of TMEM with back-to-back loads and one wait, and
           // the TMEM buffer is handed back to the MMA warp before any arithmetic or store happens.
-          constexpr int HALF = BN > 128 ? 128 : BN;      // columns handled per register batch
-          constexpr int NH = BN / HALF;
+          constexpr int HALF = L::COLS > 64 ? 64 : L::COLS;   // columns per register batch
+          constexpr int NH = L::COLS / HALF;
           constexpr int NCH = HALF / 32;
           const bool has_res = p.res != nullptr;
-          const bf16* rp = has_res ? p.res + ((size_t)(b * p.H + h) * p.res_Wp + (w + p.res_hl)) * p.res_ld + n0 : nullptr;
+          const bf16* rp = has_res ? p.res + ((size_t)(b * p.H + h) * p.res_Wp + (w + p.res_hl)) * p.res_ld + n0 + col_lo
+                                   : nullptr;
 #pragma unroll
           for (int hf = 0; hf < NH; ++hf) {
             uint4 rres[NCH][4];
             if (has_res) {
 #pragma unroll
               for (int c = 0; c < NCH; ++c) {
-                if (n0 + hf * HALF + c * 32 < p.N) {
+                if (n0 + col_lo + hf * HALF + c * 32 < p.N) {
 #pragma unroll
                   for (int i = 0; i < 4; ++i)
                     rres[c][i] = __ldg(reinterpret_cast<const uint4*>(rp + hf * HALF + c * 32) + i);
@@ -227,7 +235,7 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
             uint32_t raw[NCH][32];
 #pragma unroll
-            for (int c = 0; c < NCH; ++c) tmem_ld_32x32b_x32(taddr_row + hf * HALF + c * 32, raw[c]);
+            for (int c = 0; c < NCH; ++c) tmem_ld_32x32b_x32(taddr_row + col_lo + hf * HALF + c * 32, raw[c]);
             tmem_ld_wait();
             if (hf == NH - 1) {
               tcgen05_fence_before();
@@ -236,7 +244,7 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
-              const int cc = hf * HALF + c * 32;   // column offset inside the tile
+              const int cc = col_lo + hf * HALF + c * 32;   // column offset inside the tile
               if (n0 + cc < p.N) {
                 float v[32];
                 const float4* sb4 = reinterpret_cast<const float4*>(sbias + ab * SB + cc);
@@ -273,7 +281,7 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
           }
           fence_proxy_async();          // staging writes -> visible to the TMA engine
-          named_bar_sync(2, 128);
+          named_bar_sync(2, L::EPI_THREADS);
           if (e == 0) {
 #pragma unroll
             for (int j = 0; j < L::OUT_BOXES; ++j)
@@ -287,7 +295,7 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       mbar_wait(&tfull_bar[ab], (lt >> 1) & 1);
       tcgen05_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += CH) {
+      for (int c0 = col_lo; c0 < col_lo + L::COLS; c0 += CH) {
         const int n = n0 + c0;
         const bool live = n < p.N;   // warp-uniform
         uint4 rres[4];
@@ -307,7 +315,7 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
           for (int j = 0; j < CH; ++j) v[j] = __uint_as_float(raw[j]);
         }
-        if (c0 + CH >= BN) {   // last TMEM read of this tile: hand the accumulator back to the MMA warp
+        if (c0 + CH >= col_lo + L::COLS) {   // last TMEM read of this thread: hand the accumulator back to the MMA warp
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[ab]);
@@ -425,17 +433,6 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
         }
       }
-      if (use_tma_store) {
-        fence_proxy_async();          // staging writes -> visible to the TMA engine
-        named_bar_sync(2, 128);
-        if (e == 0) {
-#pragma unroll
-          for (int j = 0; j < L::OUT_BOXES; ++j)
-            if (n0 + j * 64 < p.N)
-              tma_store_4d(&tmO, stage_out + j * (BM * 128), n0 + j * 64, w0, h0, b);
-          tma_store_commit();
-        }
-      }
     }
     if (use_tma_store && e == 0) tma_store_wait<0>();   // smem must outlive the in-flight stores
     tcgen05_fence_before();
@@ -458,7 +455,7 @@ void launch_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtens
     LIDM_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  conv_gemm_persist_kernel<BN, STAGES><<<grid, 192, L::TOTAL, stream>>>(tmA, tmB, tmO, p, num_m_tiles, num_tiles,
+  conv_gemm_persist_kernel<BN, STAGES><<<grid, L::THREADS, L::TOTAL, stream>>>(tmA, tmB, tmO, p, num_m_tiles, num_tiles,
                                                                        use_tma_store);
   LIDM_CUDA_CHECK(cudaGetLastError());
   LIDM_COUNT_LAUNCH(1);
@@ -491,7 +488,7 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
     // 128x256 tiles halve the B-operand traffic per MAC; take them unless wave quantisation on 148 SMs eats the gain
     const long m_tiles = (long)a.B * (H / Hbox) * (W / Wbox);
     auto eff = [&](long tiles) { const long rounds = (tiles + 147) / 148; return (double)tiles / (double)(rounds * 148); };
-    const double e256 = eff(m_tiles * (n_alloc / 256)) * 1.10, e128 = eff(m_tiles * (n_alloc / 128));
+    const double e256 = eff(m_tiles * (n_alloc / 256)) * 1.30, e128 = eff(m_tiles * (n_alloc / 128));
     BN = (e256 >= e128 || force_bn == 256) ? 256 : 128;
   } else if (n_alloc % 128 == 0) BN = 128;
   else if (n_alloc % 64 == 0) BN = 64;
