@@ -47,6 +47,19 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// 2^x on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax polynomial, max relative error 7.6e-5, far below the
+// bf16 rounding of P): takes a share of the exponentials off the MUFU pipe, which bounds this kernel (head dim 32:
+// one exponential per 128 tensor-core flops).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;             // 1.5 * 2^23: the integer part of x lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);       // f in [-0.5, 0.5]
+  float p = fmaf(0.05520551f, f, 0.24261397f);
+  p = fmaf(p, f, 0.69325477f);
+  p = fmaf(p, f, 0.9999277f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 __global__ void __launch_bounds__(192)
 attention_d32_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmVT,
                      bf16* __restrict__ out, int out_ld, int T, int C) {
@@ -675,6 +688,287 @@ attention_d32_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 
 }  // namespace v3
 
+// =====================================================================================================
+// v4: NG 128-row query tiles per CTA (one softmax warpgroup each) sharing every K/V tile of BKV_ keys; nothing in
+// the softmax loop waits on the P*V product:
+//   * O accumulates in TMEM across the whole K/V loop (tcgen05.mma accumulate); the running max is only refreshed,
+//     and O rescaled in place (tcgen05.ld / scale / tcgen05.st), when some row's max grew by more than 2^8 — the
+//     result is exact because the row sum l is kept against the same (stale) max.
+//   * P is double-buffered in shared memory; S needs a single TMEM buffer per group because each softmax thread
+//     drains its whole S row into registers first and hands the buffer straight back.
+//   * the MMA thread is event driven: it polls (mbarrier.test_wait) the barriers of all groups and issues whichever
+//     of S_g(j+1) / P_g(j)V(j) is ready; the groups are started a fraction of a tile apart and stay out of phase,
+//     so one group's MUFU-bound exp phase overlaps the others' TMEM-load / max / store phases.
+//   <2,128>: 2 groups x 168 registers (whole 128-column rows in registers);  <4,64>: 4 groups x 112 registers —
+//   twice the softmax warps per scheduler for latency hiding.
+// TMEM: S_g at columns g*BKV_, O_g at NG*BKV_ + g*32.
+namespace v4 {
+
+constexpr int KV_ST = 4;
+constexpr float RESCALE_LOG2 = 8.f;
+
+template <int NG, int BKV_>
+struct Cfg {
+  static constexpr int KB = BKV_ * 64;                        // bytes of one K (or V) tile
+  static constexpr int PB = BQ * BKV_ * 2;                    // bytes of one P buffer
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + NG * Q_BYTES;
+  static constexpr int OFF_V = OFF_K + KV_ST * KB;
+  static constexpr int OFF_P = OFF_V + KV_ST * KB;            // [group][buffer]
+  static constexpr int OFF_BAR = OFF_P + NG * 2 * PB;
+  static constexpr int SMEM_TOTAL = OFF_BAR + 512 + 1024;
+  static constexpr uint32_t O_COL = NG * BKV_;
+  static constexpr uint32_t TMEM_COLS = 512;
+  static constexpr int THREADS = 128 + NG * 128;
+  static constexpr int NCH = BKV_ / 32;                       // 32-column chunks per S row
+  static_assert(NG * BKV_ + NG * 32 <= 512, "TMEM budget");
+  static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
+};
+
+template <int NG, int BKV_, bool POLY>
+__global__ void __launch_bounds__((Cfg<NG, BKV_>::THREADS), 1)
+attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                        bf16* __restrict__ out, int out_ld, int T, int C) {
+  using L = Cfg<NG, BKV_>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* kv_full = q_full + 1;          // [KV_ST]
+  uint64_t* kv_empty = kv_full + KV_ST;    // [KV_ST]
+  uint64_t* s_ready = kv_empty + KV_ST;    // [NG]
+  uint64_t* s_free = s_ready + NG;         // [NG]
+  uint64_t* p_ready = s_free + NG;         // [NG][2 buffers]
+  uint64_t* pv_done = p_ready + 2 * NG;    // [NG][2 buffers]
+  uint64_t* stagger = pv_done + 2 * NG;    // [NG]: group g-1 -> group g, once per CTA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stagger + NG);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (NG * BQ);
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int nkv = T / BKV_;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmQ);
+    prefetch_tensormap(&tmKV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KV_ST; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int g = 0; g < NG; ++g) { mbar_init(&s_ready[g], 1); mbar_init(&s_free[g], 4); mbar_init(&stagger[g], 4); }
+    for (int i = 0; i < 2 * NG; ++i) { mbar_init(&p_ready[i], 4); mbar_init(&pv_done[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, L::TMEM_COLS); tmem_relinquish(); }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    if (NG == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(q_full, NG * Q_BYTES);
+#pragma unroll
+        for (int i = 0; i < NG; i += 2)                                       // 256 query rows per box
+          tma_load_3d(smem + L::OFF_Q + i * Q_BYTES, &tmQ, q_full, head * D, q0 + i * BQ, b);
+        int s = 0; uint32_t ph = 0;
+        for (int j = 0; j < nkv; ++j) {
+          mbar_wait(&kv_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&kv_full[s], 2 * L::KB);
+          tma_load_3d(smem + L::OFF_K + s * L::KB, &tmKV, &kv_full[s], C + head * D, j * BKV_, b);
+          tma_load_3d(smem + L::OFF_V + s * L::KB, &tmKV, &kv_full[s], 2 * C + head * D, j * BKV_, b);
+          if (++s == KV_ST) { s = 0; ph ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV_);
+        constexpr uint32_t idesc_o = make_idesc_bf16(BQ, D) | (1u << 16);     // V is an MN-major B operand
+        int js[NG], jp[NG];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) js[g] = jp[g] = 0;
+        int released = 0;                      // K/V tiles handed back to the TMA warp
+        mbar_wait(q_full, 0);
+        const long long t0 = clock64();
+        int remaining = NG * nkv;
+        while (remaining > 0) {
+#pragma unroll
+          for (int g = 0; g < NG; ++g) {
+            if (js[g] < nkv) {
+              const int j = js[g], st = j % KV_ST;
+              bool ok = mbar_test_wait(&kv_full[st], (j / KV_ST) & 1);
+              if (ok && j > 0) ok = mbar_test_wait(&s_free[g], (j - 1) & 1);
+              if (ok) {
+                tcgen05_fence_after();
+                const uint64_t qdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_Q + g * Q_BYTES));
+                const uint64_t kdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_K + st * L::KB));
+                const uint32_t d = tmem_base + g * BKV_;
+                umma_bf16_ss(d, qdesc, kdesc, idesc_s, 0);
+                umma_bf16_ss(d, qdesc + 2, kdesc + 2, idesc_s, 1);
+                umma_commit(&s_ready[g]);
+                js[g] = j + 1;
+              }
+            }
+            if (jp[g] < js[g]) {
+              const int j = jp[g], st = j % KV_ST, pb = g * 2 + (j & 1);
+              if (mbar_test_wait(&p_ready[pb], (j >> 1) & 1)) {
+                tcgen05_fence_after();
+                const uint64_t vdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_V + st * L::KB));
+                const uint64_t pdesc = make_kmajor_desc<128>(smem_u32(smem + L::OFF_P + pb * L::PB));
+                const uint32_t dO = tmem_base + L::O_COL + g * 32;
+#pragma unroll
+                for (int kk = 0; kk < BKV_ / 16; ++kk) {
+                  const uint64_t pa = pdesc + (uint64_t)(((kk >> 2) * (BQ * 128) + (kk & 3) * 32) >> 4);
+                  const uint64_t vb = vdesc + (uint64_t)((kk * 1024) >> 4);
+                  umma_bf16_ss(dO, pa, vb, idesc_o, (j > 0 || kk != 0) ? 1u : 0u);
+                }
+                umma_commit(&pv_done[pb]);
+                jp[g] = j + 1;
+                --remaining;
+                int jmin = jp[0];
+#pragma unroll
+                for (int gg = 1; gg < NG; ++gg) jmin = jp[gg] < jmin ? jp[gg] : jmin;
+                if (jmin > released) { umma_commit(&kv_empty[released % KV_ST]); ++released; }   // every group is past it
+              }
+            }
+          }
+          if (clock64() - t0 > 4000000000LL) {
+            printf("lidm: attention v4 MMA loop timeout block(%d,%d,%d)\n", blockIdx.x, blockIdx.y, blockIdx.z);
+            __trap();
+          }
+        }
+      }
+    }
+  } else {
+    if (NG == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    const int g = (warp - 4) >> 2;                 // softmax group = query tile
+    const int qd = warp & 3;                       // TMEM lane quadrant
+    const int row = qd * 32 + lane;                // row inside the 128-row tile
+    const uint32_t tS = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + g * BKV_;
+    const uint32_t tO = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + L::O_COL + g * 32;
+    const uint32_t sbase = smem_u32(smem);
+    constexpr float LOG2E = 1.4426950408889634f;
+    float m = 0.f, l = 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(&s_ready[g], j & 1);
+      tcgen05_fence_after();
+      uint32_t sv[L::NCH][32];
+#pragma unroll
+      for (int c = 0; c < L::NCH; ++c) tmem_ld_32x32b_x32(tS + c * 32, sv[c]);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[g]);      // S_g(j+1) may overwrite the TMEM buffer now
+      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < L::NCH; ++c) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          m0 = max3(m0, __uint_as_float(sv[c][8 * i + 0]), __uint_as_float(sv[c][8 * i + 1]));
+          m1 = max3(m1, __uint_as_float(sv[c][8 * i + 2]), __uint_as_float(sv[c][8 * i + 3]));
+          m2 = max3(m2, __uint_as_float(sv[c][8 * i + 4]), __uint_as_float(sv[c][8 * i + 5]));
+          m3 = max3(m3, __uint_as_float(sv[c][8 * i + 6]), __uint_as_float(sv[c][8 * i + 7]));
+        }
+      }
+      const float r = max3(fmaxf(m0, m1), m2, m3);
+      if (j == 0) {
+        m = r;
+      } else if (__any_sync(0xffffffffu, (r - m) * LOG2E > RESCALE_LOG2)) {
+        // rare: refresh the running max of every row of this warp and rescale O in TMEM
+        const int pj = j - 1;
+        mbar_wait(&pv_done[g * 2 + (pj & 1)], (pj >> 1) & 1);      // every P*V issued so far has completed
+        tcgen05_fence_after();
+        const float mn = fmaxf(m, r);
+        const float alpha = ex2((m - mn) * LOG2E);
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(tO, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st_32x32b_x32(tO, o);
+        tmem_st_wait();
+        l *= alpha;
+        m = mn;
+      }
+      if (j >= 2) mbar_wait(&pv_done[g * 2 + (j & 1)], ((j - 2) >> 1) & 1);   // P buffer (j & 1) is free again
+      if (j == 0 && g > 0 && nkv > 1) mbar_wait(&stagger[g], 0);               // start a fraction of a tile apart
+      const float mb = m * LOG2E;
+      const uint32_t prow = sbase + L::OFF_P + (g * 2 + (j & 1)) * L::PB + row * 128;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < L::NCH; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          const float p0 = ex2(fmaf(__uint_as_float(sv[c][2 * i]), LOG2E, -mb));
+          const float p1 = ex2(fmaf(__uint_as_float(sv[c][2 * i + 1]), LOG2E, -mb));
+          const float p2 = ex2(fmaf(__uint_as_float(sv[c][2 * i + 2]), LOG2E, -mb));
+          const float p3 = POLY ? ex2_poly(fmaf(__uint_as_float(sv[c][2 * i + 3]), LOG2E, -mb))
+                                : ex2(fmaf(__uint_as_float(sv[c][2 * i + 3]), LOG2E, -mb));
+          s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+          pk[i] = pack_bf16(p0, p1);
+          pk[i + 1] = pack_bf16(p2, p3);
+        }
+        const uint32_t base = prow + (c >> 1) * (BQ * 128);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int chunk = ((c & 1) * 4 + i) ^ (row & 7);
+          st_shared_v4(base + chunk * 16, pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        }
+        if (c == L::NCH / NG - 1 + (L::NCH / NG == 0) && j == 0 && g + 1 < NG && lane == 0) mbar_arrive(&stagger[g + 1]);
+      }
+      l += (s0 + s1) + (s2 + s3);
+      fence_proxy_async();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[g * 2 + (j & 1)]);
+    }
+    {
+      const int pj = nkv - 1;
+      mbar_wait(&pv_done[g * 2 + (pj & 1)], (pj >> 1) & 1);
+      tcgen05_fence_after();
+    }
+    uint32_t o[32];
+    tmem_ld_32x32b_x32(tO, o);
+    tmem_ld_wait();
+    tcgen05_fence_before();
+    const float inv = 1.f / l;
+    bf16* op = out + ((size_t)b * T + q0 + g * 128 + row) * out_ld + head * D;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 u;
+      u.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+      u.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+      u.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+      u.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+      reinterpret_cast<uint4*>(op)[i] = u;
+    }
+  }
+  __syncthreads();
+  if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, L::TMEM_COLS); }
+}
+
+template <int NG, int BKV_, bool POLY>
+void launch(const bf16* qkv, const View& out, int B, int T, int heads, cudaStream_t s) {
+  using L = Cfg<NG, BKV_>;
+  const int C = heads * D;
+  static bool configured = false;
+  if (!configured) {
+    LIDM_CUDA_CHECK(cudaFuncSetAttribute(attention_d32_v4_kernel<NG, BKV_, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L::SMEM_TOTAL));
+    configured = true;
+  }
+  CUtensorMap tmQ = make_tma_3d(qkv, 3 * C, T, B, (uint64_t)3 * C * 2, (uint64_t)T * 3 * C * 2, D, 256, 64);
+  CUtensorMap tmKV = make_tma_3d(qkv, 3 * C, T, B, (uint64_t)3 * C * 2, (uint64_t)T * 3 * C * 2, D, BKV_, 64);
+  dim3 grid(T / (NG * BQ), heads, B);
+  attention_d32_v4_kernel<NG, BKV_, POLY><<<grid, L::THREADS, L::SMEM_TOTAL, s>>>(tmQ, tmKV, out.p, out.ld, T, C);
+  LIDM_CUDA_CHECK(cudaGetLastError());
+  LIDM_COUNT_LAUNCH(1);
+}
+
+}  // namespace v4
+
 }  // namespace
 
 void launch_attention_d32(const bf16* qk, const bf16* vt, const View& out, int B, int T, int heads, cudaStream_t s) {
@@ -709,6 +1003,15 @@ void launch_attention_d32_packed(const bf16* qkv, const View& out, int B, int T,
   }
   CUtensorMap tm = make_tma_3d(qkv, 3 * C, T, B, (uint64_t)3 * C * 2, (uint64_t)T * 3 * C * 2, D, 128, 64);
   static const bool use_v2 = getenv("LIDM_ATTN_V2") != nullptr;
+  static const bool use_v3 = getenv("LIDM_ATTN_V3") != nullptr;
+  // LIDM_ATTN_V4=1 moves a quarter of the exponentials onto the FMA pipe (ex2_poly); measured slower on B200 (the
+  // softmax warps are issue/latency bound, not MUFU bound), so it stays off by default.
+  static const int v4_mode = getenv("LIDM_ATTN_V4") ? atoi(getenv("LIDM_ATTN_V4")) : 0;
+  if (!use_v2 && !use_v3 && T % 256 == 0) {
+    if (v4_mode == 1) v4::launch<2, 128, true>(qkv, out, B, T, heads, s);
+    else v4::launch<2, 128, false>(qkv, out, B, T, heads, s);
+    return;
+  }
   if (T % 256 == 0 && !use_v2) {
     static bool configured3 = false;
     if (!configured3) {
