@@ -25,6 +25,7 @@ class UNetConfig:
     num_heads: int = -1
     lib_name: str = "lidm"
     use_spatial_transformer: bool = False
+    transformer_depth: int = 1
     context_dim: Optional[int] = None
     use_scale_shift_norm: bool = False
     resblock_updown: bool = False
@@ -149,16 +150,39 @@ def from_yaml(path: str) -> LidmConfig:
         return from_reference_dict(yaml.safe_load(f))
 
 
+def kitti_cam2lidar() -> LidmConfig:
+    """Cross-attention conditioned KITTI-360 LiDM (reference models/lidm/kitti/{cam2lidar,text2lidar}/config.yaml):
+    same U-Net with SpatialTransformer blocks in place of AttentionBlocks, context_dim 512."""
+    return LidmConfig(conditioning_key="crossattn",
+                      unet=UNetConfig(use_spatial_transformer=True, context_dim=512),
+                      dataset=DatasetConfig(depth_scale=56.0, log_scale=False))
+
+
+def kitti_sem2lidar() -> LidmConfig:
+    """Concat-conditioned KITTI-360 LiDM (reference models/lidm/kitti/sem2lidar/config.yaml): the 8-channel
+    rescaled semantic map is concatenated to the latent, U-Net in_channels 16."""
+    return LidmConfig(conditioning_key="concat", unet=UNetConfig(in_channels=16))
+
+
 def kitti_uncond() -> LidmConfig:
     """The released unconditional KITTI-360 LiDM config (reference models/lidm/kitti/uncond/config.yaml)."""
     return LidmConfig()
 
 
-def tiny(image_size=(8, 64), model_channels=64, channel_mult=(1, 2), n_embed=512) -> LidmConfig:
-    """A small same-topology config for fast tests (same op types, fewer channels/levels)."""
+def tiny(image_size=(8, 64), model_channels=64, channel_mult=(1, 2), n_embed=512, cond: Optional[str] = None,
+         context_dim: int = 48, concat_channels: int = 4) -> LidmConfig:
+    """A small same-topology config for fast tests (same op types, fewer channels/levels).
+    cond: None (unconditional), "crossattn" (SpatialTransformer blocks) or "concat"."""
+    kw = {}
+    if cond == "crossattn":
+        kw = dict(use_spatial_transformer=True, context_dim=context_dim)
+    elif cond == "concat":
+        kw = dict(in_channels=8 + concat_channels)
+    elif cond is not None:
+        raise ValueError(cond)
     unet = UNetConfig(image_size=image_size, model_channels=model_channels, channel_mult=channel_mult,
-                      attention_resolutions=(2, 1), num_res_blocks=1, num_head_channels=32)
+                      attention_resolutions=(2, 1), num_res_blocks=1, num_head_channels=32, **kw)
     ae = AEConfig(n_embed=n_embed, ch=64, ch_mult=(1, 2, 2), strides=((1, 2), (2, 2)), num_res_blocks=1)
     H, W = image_size
-    return LidmConfig(timesteps=1000, image_size=image_size, unet=unet, ae=ae,
+    return LidmConfig(timesteps=1000, image_size=image_size, unet=unet, ae=ae, conditioning_key=cond,
                       dataset=DatasetConfig(size=(H * 2, W * 4)))

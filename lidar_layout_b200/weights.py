@@ -50,11 +50,20 @@ def unet_blocks(cfg: UNetConfig):
       ("conv", cin, cout)              3x3 circular conv (input_blocks.0)
       ("res", cin, cout)               ResBlock
       ("attn", ch, heads)              AttentionBlock
+      ("st", ch, heads, depth, ctx)    SpatialTransformer (use_spatial_transformer; lidm/modules/attention.py:218-261)
       ("down", ch)                     Downsample (conv 3x3 stride 2)
       ("up", ch)                       Upsample (nearest x2 + conv 3x3)
     """
-    if cfg.use_spatial_transformer or cfg.use_scale_shift_norm or cfg.resblock_updown:
-        raise NotImplementedError("only the unconditional AttentionBlock U-Net is on the B200 path (round 1)")
+    if cfg.use_scale_shift_norm or cfg.resblock_updown:
+        raise NotImplementedError("use_scale_shift_norm / resblock_updown U-Nets are not on the B200 path")
+    if cfg.use_spatial_transformer and cfg.context_dim is None:
+        raise ValueError("use_spatial_transformer needs context_dim (openaimodel.py:474-475)")
+
+    def attn_layer(ch):
+        heads = ch // cfg.num_head_channels
+        if cfg.use_spatial_transformer:
+            return ("st", ch, heads, cfg.transformer_depth, cfg.context_dim)
+        return ("attn", ch, heads)
     mc = cfg.model_channels
     inputs = [[("conv", cfg.in_channels, mc)]]
     chans = [mc]
@@ -64,14 +73,14 @@ def unet_blocks(cfg: UNetConfig):
             layers = [("res", ch, mult * mc)]
             ch = mult * mc
             if ds in cfg.attention_resolutions:
-                layers.append(("attn", ch, ch // cfg.num_head_channels))
+                layers.append(attn_layer(ch))
             inputs.append(layers)
             chans.append(ch)
         if level != len(cfg.channel_mult) - 1:
             inputs.append([("down", ch)])
             chans.append(ch)
             ds *= 2
-    middle = [("res", ch, ch), ("attn", ch, ch // cfg.num_head_channels), ("res", ch, ch)]
+    middle = [("res", ch, ch), attn_layer(ch), ("res", ch, ch)]
     outputs = []
     for level, mult in list(enumerate(cfg.channel_mult))[::-1]:
         for i in range(cfg.num_res_blocks + 1):
@@ -79,7 +88,7 @@ def unet_blocks(cfg: UNetConfig):
             layers = [("res", ch + ich, mc * mult)]
             ch = mc * mult
             if ds in cfg.attention_resolutions:
-                layers.append(("attn", ch, ch // cfg.num_head_channels))
+                layers.append(attn_layer(ch))
             if level and i == cfg.num_res_blocks:
                 layers.append(("up", ch))
                 ds //= 2
@@ -107,6 +116,22 @@ def _block_spec(spec, prefix, layers, ted):
             _norm(spec, p + ".norm", ch)
             _conv1d(spec, p + ".qkv", 3 * ch, ch)
             _conv1d(spec, p + ".proj_out", ch, ch, zero_init=True)
+        elif kind == "st":
+            _, ch, heads, depth, ctx = layer
+            _norm(spec, p + ".norm", ch)
+            _conv(spec, p + ".proj_in", ch, ch, 1, 1)
+            for d in range(depth):
+                b = f"{p}.transformer_blocks.{d}"
+                for a, kdim in (("attn1", ch), ("attn2", ctx)):
+                    spec[f"{b}.{a}.to_q.weight"] = ((ch, ch), "conv")
+                    spec[f"{b}.{a}.to_k.weight"] = ((ch, kdim), "conv")
+                    spec[f"{b}.{a}.to_v.weight"] = ((ch, kdim), "conv")
+                    _linear(spec, f"{b}.{a}.to_out.0", ch, ch)
+                _linear(spec, f"{b}.ff.net.0.proj", 8 * ch, ch)
+                _linear(spec, f"{b}.ff.net.2", ch, 4 * ch)
+                for n in ("norm1", "norm2", "norm3"):
+                    _norm(spec, f"{b}.{n}", ch)
+            _conv(spec, p + ".proj_out", ch, ch, 1, 1, zero_init=True)
         elif kind == "down":
             _conv(spec, p + ".op", layer[1], layer[1], 3, 3)
         elif kind == "up":

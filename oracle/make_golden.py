@@ -76,6 +76,23 @@ def load_synthetic(model, cfg, seed=WEIGHT_SEED):
 
 
 def tiny_yaml(cfg):
+    """Reference-format config dict for a LidmConfig.  Conditioned configs name '__is_first_stage__' as the cond stage
+    (the condition encoders are outside the sampling path: callers hand apply_model / DDIMSampler.sample the
+    already-encoded conditioning tensor), with the conditioning key spelled out."""
+    u, a = cfg.unet, cfg.ae
+    y = _uncond_yaml(cfg)
+    if cfg.conditioning_key is not None:
+        mp = y["model"]["params"]
+        mp["cond_stage_config"] = "__is_first_stage__"
+        mp["conditioning_key"] = cfg.conditioning_key
+        mp["cond_stage_trainable"] = False
+        if u.use_spatial_transformer:
+            mp["unet_config"]["params"].update(use_spatial_transformer=True, context_dim=u.context_dim,
+                                               transformer_depth=u.transformer_depth)
+    return y
+
+
+def _uncond_yaml(cfg):
     u, a = cfg.unet, cfg.ae
     return {"model": {"target": "lidm.models.diffusion.ddpm.LatentDiffusion", "params": {
         "linear_start": cfg.linear_start, "linear_end": cfg.linear_end, "num_timesteps_cond": 1,
@@ -172,6 +189,89 @@ def run_reference(model, cfg, B, S_short, out):
     out["bp_xyz"] = ref_lu.range2xyz(unit, **ds)
 
 
+def cond_inputs_for(cfg, B, L, seed=INPUT_SEED + 7):
+    """Synthetic conditioning: crossattn -> (context, unconditional context) (B, L, context_dim);
+    concat -> (c_concat, None) (B, in_channels - channels, H, W)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    C, H, W = cfg.latent_shape
+    if cfg.conditioning_key == "crossattn":
+        d = cfg.unet.context_dim
+        return rng.standard_normal((B, L, d), dtype=np.float32), rng.standard_normal((B, L, d), dtype=np.float32)
+    if cfg.conditioning_key == "concat":
+        return rng.standard_normal((B, cfg.unet.in_channels - C, H, W), dtype=np.float32), None
+    raise ValueError(cfg.conditioning_key)
+
+
+CFG_SCALE = 2.5
+
+
+@torch.no_grad()
+def run_reference_cond(model, cfg, B, S_short, L, out, full=True):
+    """Conditioned sampling through the reference API: apply_model with a conditioning tensor, DDIMSampler.sample
+    with `conditioning`, and (crossattn) classifier-free guidance (ddim.py:173-180)."""
+    from lidm.models.diffusion import ddim as ref_ddim
+    x_T, noise, _ = inputs_for(cfg, B, S_short + 2)
+    cond, uncond = cond_inputs_for(cfg, B, L)
+    x_T_t, c_t = torch.from_numpy(x_T), torch.from_numpy(cond)
+    uc_t = torch.from_numpy(uncond) if uncond is not None else None
+    out["L"] = np.int64(L)
+    for t_val in (501, 21):
+        t = torch.full((B,), t_val, dtype=torch.long)
+        out[f"eps_t{t_val}"] = model.apply_model(x_T_t, t, c_t).numpy()
+    if not full:
+        return
+    sampler = ref_ddim.DDIMSampler(model)
+    rec = []
+    orig_apply = model.apply_model
+
+    def spy(x, t, c, *a, **k):
+        e = orig_apply(x, t, c, *a, **k)
+        rec.append((x.clone(), t.clone(), e.clone()))
+        return e
+
+    model.apply_model = spy
+    try:
+        samples, _ = sampler.sample(S_short, batch_size=B, shape=cfg.latent_shape, conditioning=c_t, eta=0.0,
+                                    x_T=x_T_t.clone(), verbose=False)
+        out["ddim_eta0_final"] = samples.numpy()
+        out["ddim_eta0_xt"] = np.stack([r[0].numpy() for r in rec])
+        out["ddim_eta0_eps"] = np.stack([r[2].numpy() for r in rec])
+        if uc_t is not None:
+            rec.clear()
+            samples, _ = sampler.sample(S_short, batch_size=B, shape=cfg.latent_shape, conditioning=c_t, eta=0.0,
+                                        x_T=x_T_t.clone(), verbose=False, unconditional_guidance_scale=CFG_SCALE,
+                                        unconditional_conditioning=uc_t)
+            out["ddim_cfg_final"] = samples.numpy()
+            out["cfg_scale"] = np.float32(CFG_SCALE)
+            # the (2B) batched [uncond | cond] eps of the first step, as apply_model returned it
+            out["ddim_cfg_eps2b_step0"] = rec[0][2].numpy()
+            # eta=1 + guidance + injected noise
+            it = iter(list(noise))
+            orig_noise_like = ref_ddim.noise_like
+            ref_ddim.noise_like = lambda shape_, device, repeat=False: torch.from_numpy(next(it))
+            try:
+                samples, _ = sampler.sample(S_short, batch_size=B, shape=cfg.latent_shape, conditioning=c_t, eta=1.0,
+                                            x_T=x_T_t.clone(), verbose=False,
+                                            unconditional_guidance_scale=CFG_SCALE, unconditional_conditioning=uc_t)
+            finally:
+                ref_ddim.noise_like = orig_noise_like
+            out["ddim_cfg_eta1_final"] = samples.numpy()
+    finally:
+        model.apply_model = orig_apply
+
+
+def make_cond(name, cfg, yaml_dict, B, S_short, L, full=True):
+    model = build_reference(cfg, yaml_dict)
+    sd = load_synthetic(model, cfg)
+    out = {"weights_digest": np.frombuffer(sd_digest(sd).encode(), dtype=np.uint8),
+           "weight_seed": np.int64(WEIGHT_SEED), "input_seed": np.int64(INPUT_SEED),
+           "B": np.int64(B), "S_short": np.int64(S_short)}
+    run_reference_cond(model, cfg, B, S_short, L, out, full=full)
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB; keys={sorted(out)}")
+
+
 def make(name, cfg, yaml_dict, B, S_short):
     model = build_reference(cfg, yaml_dict)
     sd = load_synthetic(model, cfg)
@@ -185,7 +285,22 @@ def make(name, cfg, yaml_dict, B, S_short):
     print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB; keys={sorted(out)}")
 
 
+def main_cond():
+    """Conditioned fixtures."""
+    torch.set_num_threads(os.cpu_count())
+    torch.manual_seed(0)
+    for name, cfg, L in (("tiny_crossattn", cfgmod.tiny(cond="crossattn"), 5), ("tiny_concat", cfgmod.tiny(cond="concat"), 0)):
+        make_cond(name, cfg, tiny_yaml(cfg), B=2, S_short=4, L=L)
+    # full-size cross-attention U-Net (models/lidm/kitti/cam2lidar): eps only, two context lengths (camera: 4 tokens,
+    # text: 77 tokens)
+    full = cfgmod.kitti_cam2lidar()
+    make_cond("kitti_cam2lidar_L4", full, tiny_yaml(full), B=1, S_short=0, L=4, full=False)
+    make_cond("kitti_cam2lidar_L77", full, tiny_yaml(full), B=1, S_short=0, L=77, full=False)
+
+
 def main():
+    if "--cond" in sys.argv:
+        return main_cond()
     torch.set_num_threads(os.cpu_count())
     torch.manual_seed(0)
     import yaml

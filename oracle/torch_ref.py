@@ -167,7 +167,58 @@ def _attnblock(sd, p, x, heads):
     return (x + h).reshape(b, c, *spatial)
 
 
-def _run_block(sd, prefix, layers, h, emb):
+def layer_norm(x, w, b, eps=1e-5):
+    return F.layer_norm(x, (x.shape[-1],), w, b, eps)
+
+
+def _cross_attention(sd, p, x, context, heads):
+    """CrossAttention.forward, lidm/modules/attention.py:170-193 (mask None; to_q/k/v have no bias;
+    scale = dim_head ** -0.5, :158; softmax in the input dtype)."""
+    q = F.linear(x, sd[p + ".to_q.weight"])
+    context = x if context is None else context
+    k = F.linear(context, sd[p + ".to_k.weight"])
+    v = F.linear(context, sd[p + ".to_v.weight"])
+    b, n, inner = q.shape
+    d = inner // heads
+
+    def split(t):   # 'b n (h d) -> (b h) n d'
+        return t.reshape(b, t.shape[1], heads, d).permute(0, 2, 1, 3).reshape(b * heads, t.shape[1], d)
+
+    q, k, v = split(q), split(k), split(v)
+    sim = torch.einsum("bid,bjd->bij", q, k) * (d ** -0.5)
+    attn = sim.softmax(dim=-1)
+    out = torch.einsum("bij,bjd->bid", attn, v)
+    out = out.reshape(b, heads, n, d).permute(0, 2, 1, 3).reshape(b, n, inner)   # '(b h) n d -> b n (h d)'
+    return F.linear(out, sd[p + ".to_out.0.weight"], sd[p + ".to_out.0.bias"])
+
+
+def _basic_transformer_block(sd, p, x, context, heads):
+    """BasicTransformerBlock._forward, lidm/modules/attention.py:211-215; FeedForward with GEGLU (:36-65)."""
+    x = _cross_attention(sd, p + ".attn1", layer_norm(x, sd[p + ".norm1.weight"], sd[p + ".norm1.bias"]), None, heads) + x
+    x = _cross_attention(sd, p + ".attn2", layer_norm(x, sd[p + ".norm2.weight"], sd[p + ".norm2.bias"]), context, heads) + x
+    h = layer_norm(x, sd[p + ".norm3.weight"], sd[p + ".norm3.bias"])
+    h = F.linear(h, sd[p + ".ff.net.0.proj.weight"], sd[p + ".ff.net.0.proj.bias"])
+    a, gate = h.chunk(2, dim=-1)
+    h = a * F.gelu(gate)
+    h = F.linear(h, sd[p + ".ff.net.2.weight"], sd[p + ".ff.net.2.bias"])
+    return h + x
+
+
+def _spatial_transformer(sd, p, x, context, heads, depth):
+    """SpatialTransformer.forward, lidm/modules/attention.py:250-261 (Normalize = GroupNorm(32, eps 1e-6), :76)."""
+    b, c, h, w = x.shape
+    x_in = x
+    x = group_norm(x, sd[p + ".norm.weight"], sd[p + ".norm.bias"], 1e-6)
+    x = F.conv2d(x, sd[p + ".proj_in.weight"], sd[p + ".proj_in.bias"])
+    x = x.reshape(b, c, h * w).permute(0, 2, 1)
+    for d in range(depth):
+        x = _basic_transformer_block(sd, f"{p}.transformer_blocks.{d}", x, context, heads)
+    x = x.permute(0, 2, 1).reshape(b, c, h, w)
+    x = F.conv2d(x, sd[p + ".proj_out.weight"], sd[p + ".proj_out.bias"])
+    return x + x_in
+
+
+def _run_block(sd, prefix, layers, h, emb, context=None):
     for j, layer in enumerate(layers):
         p = f"{prefix}.{j}"
         kind = layer[0]
@@ -177,6 +228,8 @@ def _run_block(sd, prefix, layers, h, emb):
             h = _resblock(sd, p, h, emb)
         elif kind == "attn":
             h = _attnblock(sd, p, h, layer[2])
+        elif kind == "st":
+            h = _spatial_transformer(sd, p, h, context, layer[2], layer[3])
         elif kind == "down":   # Downsample.forward openaimodel.py:159-161
             h = circular_conv2d(h, sd[p + ".op.weight"], sd[p + ".op.bias"], (1, 1, 1, 1), stride=2)
         elif kind == "up":     # Upsample.forward openaimodel.py:108-118
@@ -187,8 +240,8 @@ def _run_block(sd, prefix, layers, h, emb):
 
 @torch.no_grad()
 def unet_forward(sd: Dict[str, torch.Tensor], cfg: UNetConfig, x: torch.Tensor, timesteps: torch.Tensor,
-                 prefix: str = UNET_PREFIX) -> torch.Tensor:
-    """UNetModel.forward, lidm/modules/diffusion/openaimodel.py:719-751."""
+                 context: Optional[torch.Tensor] = None, prefix: str = UNET_PREFIX) -> torch.Tensor:
+    """UNetModel.forward, lidm/modules/diffusion/openaimodel.py:719-751 (context = cross-attention conditioning)."""
     inputs, middle, outputs, _ = unet_blocks(cfg)
     t_emb = timestep_embedding(timesteps, cfg.model_channels)
     emb = F.linear(t_emb, sd[prefix + "time_embed.0.weight"], sd[prefix + "time_embed.0.bias"])
@@ -196,12 +249,12 @@ def unet_forward(sd: Dict[str, torch.Tensor], cfg: UNetConfig, x: torch.Tensor, 
     hs = []
     h = x.float()
     for i, layers in enumerate(inputs):
-        h = _run_block(sd, f"{prefix}input_blocks.{i}", layers, h, emb)
+        h = _run_block(sd, f"{prefix}input_blocks.{i}", layers, h, emb, context)
         hs.append(h)
-    h = _run_block(sd, f"{prefix}middle_block", middle, h, emb)
+    h = _run_block(sd, f"{prefix}middle_block", middle, h, emb, context)
     for i, layers in enumerate(outputs):
         h = torch.cat([h, hs.pop()], dim=1)
-        h = _run_block(sd, f"{prefix}output_blocks.{i}", layers, h, emb)
+        h = _run_block(sd, f"{prefix}output_blocks.{i}", layers, h, emb, context)
     h = F.silu(group_norm(h, sd[prefix + "out.0.weight"], sd[prefix + "out.0.bias"], 1e-5))
     return circular_conv2d(h, sd[prefix + "out.2.weight"], sd[prefix + "out.2.bias"], (1, 1, 1, 1))
 
@@ -317,8 +370,34 @@ def ddim_step(x, e_t, coef, noise=None, temperature=1.0):
 
 
 @torch.no_grad()
-def ddim_sample(sd, cfg: LidmConfig, S, x_T, eta=0.0, noise=None, temperature=1.0, record=None):
-    """DDIMSampler.sample / ddim_sampling, ddim.py:57-165, unconditional.
+def apply_model(sd, cfg: LidmConfig, x, t, cond=None):
+    """LatentDiffusion.apply_model (ddpm.py:900-1000) -> DiffusionWrapper.forward (ddpm.py:2313-2339) for the
+    conditioning keys None / 'concat' / 'crossattn' with a single conditioning tensor."""
+    if cfg.conditioning_key is None or cond is None:
+        return unet_forward(sd, cfg.unet, x, t)
+    if cfg.conditioning_key == "concat":
+        return unet_forward(sd, cfg.unet, torch.cat([x, cond], dim=1), t)
+    if cfg.conditioning_key == "crossattn":
+        return unet_forward(sd, cfg.unet, x, t, context=cond)
+    raise NotImplementedError(cfg.conditioning_key)
+
+
+@torch.no_grad()
+def guided_eps(sd, cfg: LidmConfig, x, t, cond, unconditional_conditioning=None, unconditional_guidance_scale=1.0):
+    """The eps prediction of DDIMSampler.p_sample_ddim incl. classifier-free guidance, ddim.py:173-180."""
+    if unconditional_conditioning is None or unconditional_guidance_scale == 1.0:
+        return apply_model(sd, cfg, x, t, cond)
+    x_in = torch.cat([x] * 2)
+    t_in = torch.cat([t] * 2)
+    c_in = torch.cat([unconditional_conditioning, cond])
+    e_u, e_c = apply_model(sd, cfg, x_in, t_in, c_in).chunk(2)
+    return e_u + unconditional_guidance_scale * (e_c - e_u)
+
+
+@torch.no_grad()
+def ddim_sample(sd, cfg: LidmConfig, S, x_T, eta=0.0, noise=None, temperature=1.0, record=None, cond=None,
+                unconditional_conditioning=None, unconditional_guidance_scale=1.0):
+    """DDIMSampler.sample / ddim_sampling, ddim.py:57-165.
     noise: optional (n_steps,B,C,H,W) pre-generated tensor used for the sigma_t * randn term (in loop order).
     record: optional list; receives (x_t, t, eps, pred_x0, x_prev) per step."""
     ts, table = ddim_schedule(cfg, S, eta)
@@ -327,7 +406,7 @@ def ddim_sample(sd, cfg: LidmConfig, S, x_T, eta=0.0, noise=None, temperature=1.
     for i, step in enumerate(np.flip(ts)):
         index = n - i - 1
         t = torch.full((img.shape[0],), int(step), dtype=torch.long)
-        e_t = unet_forward(sd, cfg.unet, img, t)
+        e_t = guided_eps(sd, cfg, img, t, cond, unconditional_conditioning, unconditional_guidance_scale)
         nz = None if noise is None else noise[i]
         x_prev, pred_x0 = ddim_step(img, e_t, table[index], nz, temperature)
         if record is not None:
