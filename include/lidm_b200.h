@@ -51,6 +51,14 @@ typedef struct lidm_config {
    * 1 = precise "fp32-class" path: every GEMM runs as a 3-way bf16 operand split x*w = xh*wh + xl*wh + xh*wl on the
    *     same tcgen05 kernel with an fp32 residual stream (north_star fp32 bars: eps within 1e-3, image within 1e-2) */
   int32_t precision;
+  /* conditioning (DiffusionWrapper.forward, ddpm.py:2313-2339):
+   * latent_channels: channels of x_t / eps; in_channels - latent_channels > 0 channels come from a 'concat' conditioning
+   *   tensor (0 means latent_channels == in_channels).
+   * use_spatial_transformer / context_dim / transformer_depth: UNetModel's cross-attention options
+   *   (openaimodel.py:465-467): SpatialTransformer blocks replace the AttentionBlocks and take a (B, L, context_dim)
+   *   context. */
+  int32_t latent_channels;
+  int32_t use_spatial_transformer, context_dim, transformer_depth;
 } lidm_config;
 
 /* Last error message for `h` (or, with h == NULL, for the calling thread's last failed lidm_create / stateless call). */
@@ -74,6 +82,14 @@ int lidm_finalize_weights(lidm_handle* h, int32_t use_ema);
  * (ddpm.py:900, 2313; openaimodel.py:719-751), unconditional.  x: (B,C,H,W) fp32, t: (B,) int64, eps_out: (B,C,H,W). */
 int lidm_unet_forward(lidm_handle* h, const float* x, const int64_t* t, float* eps_out, int32_t B, void* stream);
 
+/* The same hook for conditioned models (DiffusionWrapper.forward, ddpm.py:2313-2339):
+ *   'concat'    : c_concat (B, in_channels - latent_channels, H, W) is concatenated to x on the channel axis;
+ *   'crossattn' : context (B, ctx_len, context_dim) feeds every SpatialTransformer's cross-attention
+ *                 (lidm/modules/attention.py:170-261); ctx_len is free (camera: 4 tokens, text: 77).
+ * Pass NULL / 0 for the conditioning the model does not take; a mismatch is LIDM_ERR_INVALID. */
+int lidm_unet_forward_cond(lidm_handle* h, const float* x, const int64_t* t, const float* c_concat, const float* context,
+                           int32_t ctx_len, float* eps_out, int32_t B, void* stream);
+
 /* DDIMSampler.p_sample_ddim update arithmetic (lidm/models/diffusion/ddim.py:191-206), stateless:
  * pred_x0 = (x - sqrt(1-a_t) eps)/sqrt(a_t); x_prev = sqrt(a_prev) pred_x0 + sqrt(1-a_prev-sigma^2) eps + sigma noise T.
  * noise and pred_x0 may be NULL. n = element count. Bit-exact with the reference's fp32 op order. */
@@ -88,6 +104,17 @@ int lidm_ddim_step(const float* x, const float* eps, const float* noise, float a
  * pred_x0_out: NULL or DEVICE (B,C,H,W) receiving the last step's pred_x0. */
 int lidm_ddim_sample(lidm_handle* h, float* x_inout, const int64_t* timesteps, const float* sched, int32_t n_steps,
                      const float* noise, float temperature, float* pred_x0_out, int32_t B, void* stream);
+
+/* The same loop for conditioned models, with optional classifier-free guidance (ddim.py:173-180): when an
+ * unconditional twin of the conditioning is given and guidance_scale != 1, every step evaluates the U-Net once on the
+ * 2B batch [uncond | cond] and steps with e_u + guidance_scale * (e_c - e_u). */
+int lidm_ddim_sample_cond(lidm_handle* h, float* x_inout, const int64_t* timesteps, const float* sched, int32_t n_steps,
+                          const float* noise, float temperature, float* pred_x0_out, int32_t B, const float* c_concat,
+                          const float* context, int32_t ctx_len, const float* uncond_concat, const float* uncond_context,
+                          float guidance_scale, void* stream);
+
+/* e_t = e_t_uncond + scale * (e_t - e_t_uncond) (ddim.py:180), stateless: eps2 = (2, n) [uncond | cond] -> eps_out (n). */
+int lidm_cfg_combine(const float* eps2, float guidance_scale, float* eps_out, int64_t n, void* stream);
 
 /* LatentDiffusion.decode_first_stage -> VQModelInterface.decode (ddpm.py:717-775, autoencoder.py:290-302):
  * z/scale_factor -> [quantize] -> post_quant_conv -> Decoder -> [use_mask].  z: (B,C,h,w); img_out: (B,1 or out_ch,H,W)

@@ -34,12 +34,15 @@ class CConfig(ctypes.Structure):
         ("ae_strides", (c_int32 * 2) * MAX_LEVELS),
         ("scale_factor", c_float),
         ("precision", c_int32),
+        ("latent_channels", c_int32),
+        ("use_spatial_transformer", c_int32), ("context_dim", c_int32), ("transformer_depth", c_int32),
     ]
 
 
 EXPORTS = [
     "lidm_last_error", "lidm_create", "lidm_destroy", "lidm_load_weight", "lidm_finalize_weights",
-    "lidm_unet_forward", "lidm_ddim_step", "lidm_ddim_sample", "lidm_vq_decode", "lidm_image_shape",
+    "lidm_unet_forward", "lidm_unet_forward_cond", "lidm_ddim_step", "lidm_ddim_sample", "lidm_ddim_sample_cond",
+    "lidm_cfg_combine", "lidm_vq_decode", "lidm_image_shape",
     "lidm_backproject", "lidm_op_circular_conv2d", "lidm_op_groupnorm", "lidm_op_qkv_attention_legacy",
     "lidm_launch_count", "lidm_profile_begin", "lidm_profile_end",
 ]
@@ -64,6 +67,12 @@ def load() -> ctypes.CDLL:
     lib.lidm_load_weight.argtypes = [c_void_p, c_char_p, c_void_p, c_int32, POINTER(c_int64)]
     lib.lidm_finalize_weights.argtypes = [c_void_p, c_int32]
     lib.lidm_unet_forward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]
+    lib.lidm_unet_forward_cond.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32,
+                                           c_void_p]
+    lib.lidm_ddim_sample_cond.argtypes = [c_void_p, c_void_p, POINTER(c_int64), POINTER(c_float), c_int32, c_void_p,
+                                          c_float, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
+                                          c_float, c_void_p]
+    lib.lidm_cfg_combine.argtypes = [c_void_p, c_float, c_void_p, c_int64, c_void_p]
     lib.lidm_ddim_step.argtypes = [c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_float,
                                    c_void_p, c_void_p, c_int64, c_void_p]
     lib.lidm_ddim_sample.argtypes = [c_void_p, c_void_p, POINTER(c_int64), POINTER(c_float), c_int32, c_void_p,

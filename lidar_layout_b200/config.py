@@ -170,7 +170,7 @@ def kitti_uncond() -> LidmConfig:
 
 
 def tiny(image_size=(8, 64), model_channels=64, channel_mult=(1, 2), n_embed=512, cond: Optional[str] = None,
-         context_dim: int = 48, concat_channels: int = 4) -> LidmConfig:
+         context_dim: int = 64, concat_channels: int = 4) -> LidmConfig:
     """A small same-topology config for fast tests (same op types, fewer channels/levels).
     cond: None (unconditional), "crossattn" (SpatialTransformer blocks) or "concat"."""
     kw = {}

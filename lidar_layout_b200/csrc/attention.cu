@@ -728,7 +728,7 @@ struct Cfg {
 template <int NG, int BKV_, bool POLY>
 __global__ void __launch_bounds__((Cfg<NG, BKV_>::THREADS), 1)
 attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                        bf16* __restrict__ out, int out_ld, int T, int C) {
+                        bf16* __restrict__ out, int out_ld, int T, int q_col, int k_col, int v_col, int kv_len) {
   using L = Cfg<NG, BKV_>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -747,7 +747,7 @@ attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   const int q0 = blockIdx.x * (NG * BQ);
   const int head = blockIdx.y;
   const int b = blockIdx.z;
-  const int nkv = T / BKV_;
+  const int nkv = (kv_len + BKV_ - 1) / BKV_;   // rows past kv_len are zero-filled by TMA and masked to -inf below
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tmQ);
@@ -771,13 +771,13 @@ attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         mbar_arrive_expect_tx(q_full, NG * Q_BYTES);
 #pragma unroll
         for (int i = 0; i < NG; i += 2)                                       // 256 query rows per box
-          tma_load_3d(smem + L::OFF_Q + i * Q_BYTES, &tmQ, q_full, head * D, q0 + i * BQ, b);
+          tma_load_3d(smem + L::OFF_Q + i * Q_BYTES, &tmQ, q_full, q_col + head * D, q0 + i * BQ, b);
         int s = 0; uint32_t ph = 0;
         for (int j = 0; j < nkv; ++j) {
           mbar_wait(&kv_empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&kv_full[s], 2 * L::KB);
-          tma_load_3d(smem + L::OFF_K + s * L::KB, &tmKV, &kv_full[s], C + head * D, j * BKV_, b);
-          tma_load_3d(smem + L::OFF_V + s * L::KB, &tmKV, &kv_full[s], 2 * C + head * D, j * BKV_, b);
+          tma_load_3d(smem + L::OFF_K + s * L::KB, &tmKV, &kv_full[s], k_col + head * D, j * BKV_, b);
+          tma_load_3d(smem + L::OFF_V + s * L::KB, &tmKV, &kv_full[s], v_col + head * D, j * BKV_, b);
           if (++s == KV_ST) { s = 0; ph ^= 1; }
         }
       }
@@ -860,6 +860,15 @@ attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[g]);      // S_g(j+1) may overwrite the TMEM buffer now
+      if (kv_len - j * BKV_ < BKV_) {               // ragged last tile (cross-attention context): mask the padding keys
+        const int valid = kv_len - j * BKV_;
+#pragma unroll
+        for (int c = 0; c < L::NCH; ++c) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= valid) sv[c][i] = 0xff800000u;   // -inf
+        }
+      }
       float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
       for (int c = 0; c < L::NCH; ++c) {
@@ -949,20 +958,23 @@ attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, L::TMEM_COLS); }
 }
 
+// q: (B, T, q_ld) rows with the heads at columns q_col + head*32; k / v: (B, kv_rows, kv_ld) rows at columns k_col / v_col.
 template <int NG, int BKV_, bool POLY>
-void launch(const bf16* qkv, const View& out, int B, int T, int heads, cudaStream_t s) {
+void launch(const bf16* q, int q_ld, int q_col, const bf16* kv, int kv_ld, int k_col, int v_col, int kv_rows, const View& out,
+            int B, int T, int heads, cudaStream_t s) {
   using L = Cfg<NG, BKV_>;
-  const int C = heads * D;
   static bool configured = false;
   if (!configured) {
-    LIDM_CUDA_CHECK(cudaFuncSetAttribute(attention_d32_v4_kernel<NG, BKV_, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         L::SMEM_TOTAL));
+    LIDM_CUDA_CHECK(cudaFuncSetAttribute(attention_d32_v4_kernel<NG, BKV_, POLY>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_TOTAL));
     configured = true;
   }
-  CUtensorMap tmQ = make_tma_3d(qkv, 3 * C, T, B, (uint64_t)3 * C * 2, (uint64_t)T * 3 * C * 2, D, 256, 64);
-  CUtensorMap tmKV = make_tma_3d(qkv, 3 * C, T, B, (uint64_t)3 * C * 2, (uint64_t)T * 3 * C * 2, D, BKV_, 64);
+  LIDM_REQUIRE(T % (NG * BQ) == 0 && kv_rows >= 1, "attention tile shape");
+  CUtensorMap tmQ = make_tma_3d(q, q_ld, T, B, (uint64_t)q_ld * 2, (uint64_t)T * q_ld * 2, D, NG >= 2 ? 256 : 128, 64);
+  CUtensorMap tmKV = make_tma_3d(kv, kv_ld, kv_rows, B, (uint64_t)kv_ld * 2, (uint64_t)kv_rows * kv_ld * 2, D, BKV_, 64);
   dim3 grid(T / (NG * BQ), heads, B);
-  attention_d32_v4_kernel<NG, BKV_, POLY><<<grid, L::THREADS, L::SMEM_TOTAL, s>>>(tmQ, tmKV, out.p, out.ld, T, C);
+  attention_d32_v4_kernel<NG, BKV_, POLY><<<grid, L::THREADS, L::SMEM_TOTAL, s>>>(tmQ, tmKV, out.p, out.ld, T, q_col, k_col,
+                                                                                v_col, kv_rows);
   LIDM_CUDA_CHECK(cudaGetLastError());
   LIDM_COUNT_LAUNCH(1);
 }
@@ -1008,8 +1020,8 @@ void launch_attention_d32_packed(const bf16* qkv, const View& out, int B, int T,
   // softmax warps are issue/latency bound, not MUFU bound), so it stays off by default.
   static const int v4_mode = getenv("LIDM_ATTN_V4") ? atoi(getenv("LIDM_ATTN_V4")) : 0;
   if (!use_v2 && !use_v3 && T % 256 == 0) {
-    if (v4_mode == 1) v4::launch<2, 128, true>(qkv, out, B, T, heads, s);
-    else v4::launch<2, 128, false>(qkv, out, B, T, heads, s);
+    if (v4_mode == 1) v4::launch<2, 128, true>(qkv, 3 * C, 0, qkv, 3 * C, C, 2 * C, T, out, B, T, heads, s);
+    else v4::launch<2, 128, false>(qkv, 3 * C, 0, qkv, 3 * C, C, 2 * C, T, out, B, T, heads, s);
     return;
   }
   if (T % 256 == 0 && !use_v2) {
@@ -1030,6 +1042,15 @@ void launch_attention_d32_packed(const bf16* qkv, const View& out, int B, int T,
   v2::attention_d32_v2_kernel<<<grid, 192, v2::SMEM_TOTAL2, s>>>(tm, out.p, out.ld, T, C);
   LIDM_CUDA_CHECK(cudaGetLastError());
   LIDM_COUNT_LAUNCH(1);
+}
+
+// CrossAttention.forward core (reference lidm/modules/attention.py:170-193) for head dim 32: q (B,T,q_ld) against a
+// short context k/v (B, L, kv_ld), L not necessarily a multiple of 128 (TMA zero-fills, the kernel masks).
+void launch_cross_attention_d32(const bf16* q, int q_ld, const bf16* kv, int kv_ld, int k_col, int v_col, int L,
+                                const View& out, int B, int T, int heads, cudaStream_t s) {
+  LIDM_REQUIRE(T % 128 == 0 && L >= 1, "cross attention: T must be a multiple of 128");
+  if (T % 256 == 0) v4::launch<2, 128, false>(q, q_ld, 0, kv, kv_ld, k_col, v_col, L, out, B, T, heads, s);
+  else v4::launch<1, 128, false>(q, q_ld, 0, kv, kv_ld, k_col, v_col, L, out, B, T, heads, s);
 }
 
 }  // namespace lidm

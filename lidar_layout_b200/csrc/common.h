@@ -126,6 +126,23 @@ void launch_attention_d32(const bf16* qk, const bf16* vt, const View& out, int B
 // qkv: (B, T, 3C) bf16 = [q | k | v] (plain qkv GEMM output); V consumed as an MN-major tcgen05 operand
 void launch_attention_d32_packed(const bf16* qkv, const View& out, int B, int T, int heads, cudaStream_t s);
 
+// q (B,T,q_ld) bf16 (heads at columns head*32, softmax scale already folded in); k / v rows of the context
+// (B, L, kv_ld) at columns k_col / v_col; out (B,T,C) view.  Any L >= 1 (ragged last tile is masked).
+void launch_cross_attention_d32(const bf16* q, int q_ld, const bf16* kv, int kv_ld, int k_col, int v_col, int L,
+                                const View& out, int B, int T, int heads, cudaStream_t s);
+
+// ---- transformer pieces (transformer.cu) -------------------------------------------------------------------
+// nn.LayerNorm over the channel dimension of every pixel/token (eps 1e-5), bf16 in / bf16 out, fp32 statistics
+void launch_layernorm(const View& x, const View& y, const float* gamma, const float* beta, float eps, cudaStream_t s);
+// GEGLU (lidm/modules/attention.py:36-44): y[..., i] = h[..., i] * gelu(h[..., C + i]), exact (erf) GELU; h has 2C channels
+void launch_geglu(const View& h, const View& y, cudaStream_t s);
+// fp32 (rows, cols) -> bf16 (rows_pad, cols) with zero rows appended
+void launch_f32_rows_to_bf16(const float* x, int64_t rows, int64_t rows_pad, int cols, bf16* y, cudaStream_t s);
+// classifier-free guidance + DDIM update (ddim.py:173-206): e = e_u + scale (e_c - e_u), then ddim_update(x, e, ...)
+// eps2: (2, n) = [uncond | cond]; eps_out (optional) receives the guided eps
+void launch_cfg_ddim_step(const float* x, const float* eps2, float scale, const float* noise, const float* coef_dev,
+                          float* x_prev, float* pred_x0, float* eps_out, int64_t n, cudaStream_t s);
+
 // ---- elementwise (elementwise.cu) ------------------------------------------------------------------------
 void launch_ddim_step(const float* x, const float* eps, const float* noise, const float* coef_dev, float* x_prev,
                       float* pred_x0, int64_t n, cudaStream_t s);

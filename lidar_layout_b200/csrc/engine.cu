@@ -110,9 +110,18 @@ struct ConvW {
 struct NormW { float* gamma = nullptr; float* beta = nullptr; int C = 0; };
 struct ResW { NormW n1, n2; ConvW c1, c2, skip; bool has_skip = false; int emb_off = -1; int cin = 0, cout = 0; };
 struct AttnW { NormW n; ConvW qkv, proj; int ch = 0, heads = 0; };
+// BasicTransformerBlock / SpatialTransformer weights (reference lidm/modules/attention.py:196-261)
+struct STBlockW {
+  NormW n1, n2, n3;           // LayerNorms
+  ConvW qkv1, out1;           // attn1: packed [q | k | v] rows (q, k pre-scaled by d^-1/4), to_out.0
+  ConvW q2, out2;             // attn2: to_q (pre-scaled by d^-1/2), to_out.0; k / v come from the shared context GEMM
+  ConvW ff0, ff2;             // GEGLU proj (C -> 8C), Linear (4C -> C)
+  int kv_col = 0;             // column of this block's K rows inside the context K/V matrix (V at kv_col + C)
+};
+struct STW { NormW n; ConvW proj_in, proj_out; std::vector<STBlockW> blocks; int ch = 0, heads = 0; };
 struct Layer {
-  enum Kind { CONV, RES, ATTN, DOWN, UP } kind;
-  ResW r; AttnW a; ConvW c;
+  enum Kind { CONV, RES, ATTN, DOWN, UP, ST } kind;
+  ResW r; AttnW a; ConvW c; STW st;
   int cin = 0, cout = 0;
 };
 struct DecLevel { std::vector<ResW> blocks; int kh = 1, kw = 4; bool has_up = false; int sh = 1, sw = 1; ConvW up; int ch = 0; };
@@ -139,7 +148,10 @@ struct Plan {
   std::vector<Op> ops;
   float* gn_partials = nullptr;
   // launch-time IO (closures read these when they run)
-  const float* x = nullptr;         // U-Net input / decoder latent (fp32 NCHW)
+  const float* x = nullptr;         // U-Net latent x_t / decoder latent (fp32 NCHW)
+  const float* xin = nullptr;       // U-Net conv-in source: x itself, or the assembled [x | c_concat] tensor
+  const float* context = nullptr;   // cross-attention context (B, ctx_len, context_dim) fp32, or null
+  int ctx_len = 0;
   float* out = nullptr;             // eps_out / img_out
   int32_t* idx_out = nullptr;
   int quantize = 1;
@@ -171,6 +183,12 @@ struct lidm_handle {
   std::vector<Layer> mid_block;
   std::vector<int> in_chans;                          // channels of hs[k]
   NormW out_norm; ConvW out_conv;
+  bool has_st = false;                                // SpatialTransformer U-Net (cross-attention conditioning)
+  bf16* ctx_w = nullptr; int ctx_n = 0;               // every block's [to_k ; to_v] rows stacked: [ctx_n][context_dim]
+  int latent_channels = 0;                            // channels of x / eps (in_channels - latent = concat channels)
+  float* xcat = nullptr; size_t xcat_elems = 0;       // assembled [x | c_concat] (and the 2B classifier-free batch)
+  float* ctx2 = nullptr; size_t ctx2_elems = 0;       // [uncond ; cond] context for classifier-free guidance
+  float* eps2 = nullptr; size_t eps2_elems = 0;       // (2B) eps of the guidance batch
   float *te_w0 = nullptr, *te_b0 = nullptr, *te_w2 = nullptr, *te_b2 = nullptr;
   float *emb_w = nullptr, *emb_b = nullptr;           // concatenated emb_layers Linear weights [emb_total][ted]
   int emb_total = 0, ted = 0;
@@ -183,7 +201,7 @@ struct lidm_handle {
   NormW dec_norm_out;
   int dec_top = 0, dec_last = 0, img_h = 0, img_w = 0;
   // plans
-  std::map<int, std::unique_ptr<Plan>> unet_plans, dec_plans;
+  std::map<int64_t, std::unique_ptr<Plan>> unet_plans, dec_plans;   // key = B | ctx_len << 24
   // time-embedding scratch
   float *te_tmp = nullptr, *te_emb = nullptr, *emb_out = nullptr;
   int64_t* t_dev = nullptr;
@@ -195,7 +213,7 @@ struct lidm_handle {
     for (auto& kv : raw) cudaFree(kv.second.p);
     for (void* p : owned) cudaFree(p);
     cudaFree(te_tmp); cudaFree(te_emb); cudaFree(emb_out); cudaFree(t_dev); cudaFree(coef_dev);
-    cudaFree(xa); cudaFree(xb);
+    cudaFree(xa); cudaFree(xb); cudaFree(xcat); cudaFree(ctx2); cudaFree(eps2);
   }
 };
 
@@ -283,6 +301,27 @@ struct Packer {
     return c;
   }
 };
+
+// nn.Linear / 1x1 weights stacked row-wise into one K-major bf16 matrix [n_alloc][cin]; part i may be scaled.
+struct LinPart { std::string name; float scale; };
+ConvW pack_stacked_linear(Packer& pk, const std::vector<LinPart>& parts, int cout_each, int cin, const std::string& bias_name) {
+  lidm_handle* h = pk.h;
+  if (pk.precise) throw Error(LIDM_ERR_INVALID, "the precise (fp32-class) mode does not cover SpatialTransformer U-Nets");
+  ConvW c;
+  c.cout = cout_each * (int)parts.size(); c.cin = cin; c.kh = c.kw = 1;
+  c.n_alloc = round_n_alloc(c.cout);
+  c.k_alloc = cin;
+  c.w = dev_alloc<bf16>(h, (size_t)c.n_alloc * cin);
+  LIDM_CUDA_CHECK(cudaMemsetAsync(c.w, 0, (size_t)c.n_alloc * cin * sizeof(bf16), pk.s));
+  for (size_t i = 0; i < parts.size(); ++i) {
+    const DevTensor& w = find_raw(h, parts[i].name, pk.ema);
+    if (w.numel != (int64_t)cout_each * cin) throw Error(LIDM_ERR_STATE, "weight '" + parts[i].name + "' has unexpected size");
+    launch_pack_conv_weight(w.p, cout_each, cin, 1, 1, cout_each, cin, nullptr, nullptr, parts[i].scale,
+                            parts[i].scale != 1.f ? cout_each : 0, c.w + i * (size_t)cout_each * cin, pk.s);
+  }
+  c.bias = bias_name.empty() ? nullptr : pk.f32(bias_name, c.cout);
+  return c;
+}
 
 // ------------------------------------------------------------------------------------------- plan builder
 struct Builder {
@@ -667,6 +706,84 @@ struct Builder {
     release(ba);
   }
 
+  void layernorm(const View& x, const View& y, const NormW& n) {
+    op([=](cudaStream_t s) { launch_layernorm(x, y, n.gamma, n.beta, 1e-5f, s); }, PROF_NORM, 0,
+       4.0 * x.B * x.H * x.W * x.C, "ln C" + std::to_string(x.C) + " @" + std::to_string(x.H) + "x" + std::to_string(x.W));
+  }
+  void lin(const View& a, const ConvW& w, const View& out, const View* residual = nullptr) {
+    GemmEpilogue ep;
+    ep.bias = w.bias;
+    if (residual) ep.residual = *residual;
+    ep.out = out;
+    gemm(a, taps_1x1(), w, ep);
+  }
+
+  // SpatialTransformer.forward / BasicTransformerBlock._forward / CrossAttention.forward / GEGLU
+  // (lidm/modules/attention.py:250-261, 211-215, 170-193, 36-44).  ctx_kv: every block's K | V rows of the context,
+  // (B * ctx_len padded to 128 rows, ctx_n) bf16, produced once per U-Net evaluation by one GEMM.
+  void st_block(const STW& t, const View& x, const View& dst, const bf16* ctx_kv, int ctx_n, int ctx_len) {
+    const int B = x.B, H = x.H, W = x.W, C = t.ch, T = H * W, heads = t.heads;
+    Buf bg, bh;
+    View g = act(B, H, W, C, 0, 0, &bg);
+    groupnorm(x, g, t.n, 1e-6f, false);
+    View hcur = act(B, H, W, C, 0, 0, &bh);
+    lin(g, t.proj_in, hcur);
+    release(bg);
+    for (const STBlockW& k : t.blocks) {
+      // x = attn1(norm1(x)) + x   (self-attention)
+      Buf bn, bqkv, bao, bh1;
+      View n1 = act(B, H, W, C, 0, 0, &bn);
+      layernorm(hcur, n1, k.n1);
+      View qkv = act(B, H, W, 3 * C, 0, 0, &bqkv);
+      lin(n1, k.qkv1, qkv);
+      release(bn);
+      View ao = act(B, H, W, C, 0, 0, &bao);
+      op([=](cudaStream_t s) { launch_attention_d32_packed(qkv.p, ao, B, T, heads, s); }, PROF_ATTN,
+         4.0 * B * heads * (double)T * T * 32, 0, "attn T" + std::to_string(T) + " heads" + std::to_string(heads));
+      release(bqkv);
+      View h1 = act(B, H, W, C, 0, 0, &bh1);
+      lin(ao, k.out1, h1, &hcur);
+      release(bao);
+      release(bh);
+      // x = attn2(norm2(x), context) + x   (cross-attention)
+      Buf bn2, bq2, bao2, bh2;
+      View n2 = act(B, H, W, C, 0, 0, &bn2);
+      layernorm(h1, n2, k.n2);
+      View q2 = act(B, H, W, C, 0, 0, &bq2);
+      lin(n2, k.q2, q2);
+      release(bn2);
+      View ao2 = act(B, H, W, C, 0, 0, &bao2);
+      const int kv_col = k.kv_col;
+      op([=](cudaStream_t s) {
+        launch_cross_attention_d32(q2.p, q2.ld, ctx_kv, ctx_n, kv_col, kv_col + C, ctx_len, ao2, B, T, heads, s);
+      }, PROF_ATTN, 4.0 * B * heads * (double)T * ctx_len * 32, 0,
+         "xattn T" + std::to_string(T) + " L" + std::to_string(ctx_len) + " heads" + std::to_string(heads));
+      release(bq2);
+      View h2 = act(B, H, W, C, 0, 0, &bh2);
+      lin(ao2, k.out2, h2, &h1);
+      release(bao2);
+      release(bh1);
+      // x = ff(norm3(x)) + x   (GEGLU feed-forward)
+      Buf bn3, bff, bgl, bh3;
+      View n3 = act(B, H, W, C, 0, 0, &bn3);
+      layernorm(h2, n3, k.n3);
+      View ffh = act(B, H, W, 8 * C, 0, 0, &bff);
+      lin(n3, k.ff0, ffh);
+      release(bn3);
+      View ffg = act(B, H, W, 4 * C, 0, 0, &bgl);
+      op([=](cudaStream_t s) { launch_geglu(ffh, ffg, s); }, PROF_OTHER, 0, 24.0 * B * T * C,
+         "geglu C" + std::to_string(C) + " @" + std::to_string(H) + "x" + std::to_string(W));
+      release(bff);
+      View h3 = act(B, H, W, C, 0, 0, &bh3);
+      lin(ffg, k.ff2, h3, &h2);
+      release(bgl);
+      release(bh2);
+      hcur = h3; bh = bh3;
+    }
+    lin(hcur, t.proj_out, dst, &x);
+    release(bh);
+  }
+
   // Downsample.forward (openaimodel.py:159-161): circular 3x3 stride 2 via channels-last im2col + GEMM
   void down(const ConvW& c, const View& x, const View& dst) {
     const int B = x.B, Ho = x.H / 2, Wo = x.W / 2;
@@ -722,6 +839,30 @@ void build_unet_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
       ch_prev = h->out_blocks[i][0].cout;
     }
   }
+  // cross-attention context: fp32 (B, L, context_dim) -> bf16 rows (padded to a multiple of 128) -> one GEMM against the
+  // stacked [to_k ; to_v] rows of every transformer block -> ctx_kv (rows, ctx_n)
+  const bf16* ctx_kv = nullptr;
+  Buf bctx_kv;
+  const int ctx_len = P->ctx_len;
+  if (h->has_st) {
+    if (ctx_len <= 0) throw Error(LIDM_ERR_INVALID, "this U-Net needs a cross-attention context");
+    const int D = cfg.context_dim;
+    const int64_t rows = (int64_t)B * ctx_len, rows_pad = (rows + 127) / 128 * 128;
+    Buf bc16;
+    bf16* c16 = b.raw<bf16>((size_t)rows_pad * D, &bc16);
+    b.op([=](cudaStream_t s) { launch_f32_rows_to_bf16(P->context, rows, rows_pad, D, c16, s); });
+    bf16* kv = b.raw<bf16>((size_t)rows_pad * h->ctx_n, &bctx_kv);
+    View a; a.p = c16; a.B = 1; a.H = 1; a.W = (int)rows_pad; a.C = D; a.ld = D;
+    View o; o.p = kv; o.B = 1; o.H = 1; o.W = (int)rows_pad; o.C = h->ctx_n; o.ld = h->ctx_n;
+    GemmB wb; wb.p = h->ctx_w; wb.n_alloc = h->ctx_n; wb.ld = D;
+    GemmEpilogue ep;
+    ep.out = o;
+    const int N = h->ctx_n;
+    b.op([=](cudaStream_t s) { launch_conv_gemm(a, taps_1x1(), wb, N, ep, s); }, PROF_GEMM, gemm_flops(a, 1, N), 0,
+         "gemm context kv " + std::to_string(D) + "->" + std::to_string(N) + " rows" + std::to_string(rows_pad));
+    b.release(bc16);
+    ctx_kv = kv;
+  }
   auto run_layers = [&](const std::vector<Layer>& layers, View x, const View& dst) {
     Buf prev_buf; bool have_prev = false;
     for (size_t j = 0; j < layers.size(); ++j) {
@@ -736,6 +877,7 @@ void build_unet_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
       switch (L.kind) {
         case Layer::RES: b.res_block(L.r, x, o, 3, 3, 1, 1, 1, 1e-5f); break;
         case Layer::ATTN: b.attn_block(L.a, x, o); break;
+        case Layer::ST: b.st_block(L.st, x, o, ctx_kv, h->ctx_n, ctx_len); break;
         case Layer::DOWN: b.down(L.c, x, o); break;
         case Layer::UP: b.up(L.c, x, o); break;
         case Layer::CONV: throw Error(LIDM_ERR_INVALID, "unexpected conv layer");
@@ -752,7 +894,7 @@ void build_unet_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
     Buf bc;
     bf16* col = b.raw<bf16>((size_t)B * H * W * kpad, &bc);
     const int Cin = cfg.in_channels;
-    b.op([=](cudaStream_t s) { launch_im2col_nchw_f32(P->x, B, Cin, H, W, 3, 3, 1, 1, col, kpad, s); });
+    b.op([=](cudaStream_t s) { launch_im2col_nchw_f32(P->xin, B, Cin, H, W, 3, 3, 1, 1, col, kpad, s); });
     View a; a.p = col; a.B = B; a.H = H; a.W = W; a.C = kpad; a.ld = kpad;
     GemmEpilogue ep;
     ep.bias = h->in_blocks[0][0].c.bias;
@@ -802,6 +944,7 @@ void build_unet_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
     b.release(bg);
     b.release(bfinal);
   }
+  if (h->has_st) b.release(bctx_kv);
   *high = b.ap.high();
 }
 
@@ -937,6 +1080,7 @@ void build_unet_plan_pass_p(lidm_handle* h, Plan* P, bool dry, size_t* high) {
       switch (L.kind) {
         case Layer::RES: b.res_block_p(L.r, x, o, 3, 3, 1, 1, 1, 1e-5f); break;
         case Layer::ATTN: b.attn_block_p(L.a, x, o); break;
+        case Layer::ST: throw Error(LIDM_ERR_INVALID, "precise mode does not cover SpatialTransformer U-Nets");
         case Layer::DOWN: b.down_p(L.c, x, o); break;
         case Layer::UP: b.up_p(L.c, x, o); break;
         case Layer::CONV: throw Error(LIDM_ERR_INVALID, "unexpected conv layer");
@@ -953,7 +1097,7 @@ void build_unet_plan_pass_p(lidm_handle* h, Plan* P, bool dry, size_t* high) {
     Buf bc;
     bf16* col = b.raw<bf16>((size_t)B * H * W * 2 * kpad, &bc);
     const int Cin = cfg.in_channels;
-    b.op([=](cudaStream_t s) { launch_im2col_nchw_f32_hl(P->x, B, Cin, H, W, 3, 3, 1, 1, col, kpad, s); });
+    b.op([=](cudaStream_t s) { launch_im2col_nchw_f32_hl(P->xin, B, Cin, H, W, 3, 3, 1, 1, col, kpad, s); });
     View a; a.p = col; a.B = B; a.H = H; a.W = W; a.C = kpad; a.ld = 2 * kpad; a.lo_off = kpad;
     GemmEpilogue ep;
     ep.bias = cw.bias;
@@ -1093,12 +1237,14 @@ void build_dec_plan_pass_p(lidm_handle* h, Plan* P, bool dry, size_t* high) {
   *high = b.ap.high();
 }
 
-Plan* get_plan(lidm_handle* h, std::map<int, std::unique_ptr<Plan>>& cache, int B,
-               void (*pass)(lidm_handle*, Plan*, bool, size_t*)) {
-  auto it = cache.find(B);
+Plan* get_plan(lidm_handle* h, std::map<int64_t, std::unique_ptr<Plan>>& cache, int B,
+               void (*pass)(lidm_handle*, Plan*, bool, size_t*), int ctx_len = 0) {
+  const int64_t key = (int64_t)B | ((int64_t)ctx_len << 24);
+  auto it = cache.find(key);
   if (it != cache.end()) return it->second.get();
   std::unique_ptr<Plan> P(new Plan());
   P->B = B;
+  P->ctx_len = ctx_len;
   size_t high = 0;
   pass(h, P.get(), true, &high);
   P->arena_bytes = high;
@@ -1108,7 +1254,7 @@ Plan* get_plan(lidm_handle* h, std::map<int, std::unique_ptr<Plan>>& cache, int 
   pass(h, P.get(), false, &high2);
   if (high2 != high) throw Error(LIDM_ERR_STATE, "internal: non-deterministic activation plan");
   Plan* ret = P.get();
-  cache[B] = std::move(P);
+  cache[key] = std::move(P);
   return ret;
 }
 
@@ -1239,6 +1385,9 @@ void finalize(lidm_handle* h, bool use_ema) {
   pk.precise = cfg.precision != 0;
   const std::string U = "model.diffusion_model.";
   const int mc = cfg.model_channels, ted = mc * 4;
+  h->latent_channels = cfg.latent_channels > 0 ? cfg.latent_channels : cfg.in_channels;
+  LIDM_REQUIRE(h->latent_channels <= cfg.in_channels && h->latent_channels == cfg.out_channels,
+               "latent channels must equal out_channels and not exceed in_channels");
   h->ted = ted;
   h->te_w0 = pk.f32(U + "time_embed.0.weight", (int64_t)ted * mc);
   h->te_b0 = pk.f32(U + "time_embed.0.bias", ted);
@@ -1261,11 +1410,50 @@ void finalize(lidm_handle* h, bool use_ema) {
     L.r = pack_res(pk, p, cin, cout, 3, 3, true);
     return L;
   };
+  std::vector<std::pair<std::string, int>> st_blocks;   // (transformer block prefix, channels) in packing order
   auto make_attn = [&](const std::string& p, int c) {
-    Layer L; L.kind = Layer::ATTN; L.cin = L.cout = c;
-    L.a = pack_unet_attn(pk, p, c, c / cfg.num_head_channels);
+    Layer L; L.cin = L.cout = c;
+    if (!cfg.use_spatial_transformer) {
+      L.kind = Layer::ATTN;
+      L.a = pack_unet_attn(pk, p, c, c / cfg.num_head_channels);
+      return L;
+    }
+    // SpatialTransformer(ch, num_heads = ch / num_head_channels, dim_head = num_head_channels) (openaimodel.py:546-561)
+    L.kind = Layer::ST;
+    STW& t = L.st;
+    t.ch = c; t.heads = c / cfg.num_head_channels;
+    const float d = (float)cfg.num_head_channels;
+    const float s4 = 1.0f / std::sqrt(std::sqrt(d)), s2 = 1.0f / std::sqrt(d);
+    t.n = pk.norm(p + ".norm", c);
+    t.proj_in = pk.conv(p + ".proj_in", c, c, 1, 1);
+    t.proj_out = pk.conv(p + ".proj_out", c, c, 1, 1);
+    for (int k = 0; k < cfg.transformer_depth; ++k) {
+      const std::string bp = p + ".transformer_blocks." + std::to_string(k);
+      STBlockW w;
+      w.n1 = pk.norm(bp + ".norm1", c); w.n2 = pk.norm(bp + ".norm2", c); w.n3 = pk.norm(bp + ".norm3", c);
+      // softmax(q k^T * d^-1/2) (attention.py:158,183): d^-1/4 folded into the q and k rows of the self-attention,
+      // d^-1/2 into the q rows of the cross-attention (its k rows live in the shared context matrix)
+      w.qkv1 = pack_stacked_linear(pk, {{bp + ".attn1.to_q.weight", s4}, {bp + ".attn1.to_k.weight", s4},
+                                        {bp + ".attn1.to_v.weight", 1.f}}, c, c, "");
+      w.out1 = pack_stacked_linear(pk, {{bp + ".attn1.to_out.0.weight", 1.f}}, c, c, bp + ".attn1.to_out.0.bias");
+      w.q2 = pack_stacked_linear(pk, {{bp + ".attn2.to_q.weight", s2}}, c, c, "");
+      w.out2 = pack_stacked_linear(pk, {{bp + ".attn2.to_out.0.weight", 1.f}}, c, c, bp + ".attn2.to_out.0.bias");
+      w.ff0 = pack_stacked_linear(pk, {{bp + ".ff.net.0.proj.weight", 1.f}}, 8 * c, c, bp + ".ff.net.0.proj.bias");
+      w.ff2 = pack_stacked_linear(pk, {{bp + ".ff.net.2.weight", 1.f}}, c, 4 * c, bp + ".ff.net.2.bias");
+      w.kv_col = h->ctx_n;
+      h->ctx_n += 2 * c;
+      st_blocks.emplace_back(bp, c);
+      t.blocks.push_back(w);
+    }
     return L;
   };
+  h->has_st = cfg.use_spatial_transformer != 0;
+  h->ctx_n = 0;
+  if (h->has_st) {
+    LIDM_REQUIRE(cfg.context_dim > 0 && cfg.context_dim % 64 == 0, "context_dim must be a positive multiple of 64");
+    LIDM_REQUIRE(cfg.transformer_depth >= 1, "transformer_depth");
+    LIDM_REQUIRE(!pk.precise, "precise mode does not cover SpatialTransformer U-Nets");
+  }
   for (int level = 0; level < cfg.n_channel_mult; ++level) {
     const int mult = cfg.channel_mult[level];
     for (int r = 0; r < cfg.num_res_blocks; ++r) {
@@ -1310,6 +1498,21 @@ void finalize(lidm_handle* h, bool use_ema) {
           ds /= 2;
         }
         h->out_blocks.push_back(layers);
+      }
+    }
+  }
+  if (h->has_st) {
+    // one K-major matrix holding every transformer block's [to_k ; to_v] rows: the context is projected once per U-Net
+    // evaluation by a single GEMM
+    const int D = cfg.context_dim;
+    h->ctx_w = dev_alloc<bf16>(h, (size_t)h->ctx_n * D);
+    size_t row = 0;
+    for (auto& sb : st_blocks) {
+      for (const char* nm : {".attn2.to_k.weight", ".attn2.to_v.weight"}) {
+        const DevTensor& w = find_raw(h, sb.first + nm, use_ema);
+        if (w.numel != (int64_t)sb.second * D) throw Error(LIDM_ERR_STATE, "weight '" + sb.first + nm + "' has unexpected size");
+        launch_pack_conv_weight(w.p, sb.second, D, 1, 1, sb.second, D, nullptr, nullptr, 1.f, 0, h->ctx_w + row * D, pk.s);
+        row += sb.second;
       }
     }
   }
@@ -1452,6 +1655,41 @@ __global__ void qkv_legacy_to_internal_kernel(const float* __restrict__ qkv, int
   }
 }
 
+// Which conditioning tensors this model takes (DiffusionWrapper.forward, ddpm.py:2313-2339).
+void check_conditioning(lidm_handle* h, const float* c_concat, const float* context, int ctx_len) {
+  const bool wants_concat = h->cfg.in_channels > h->latent_channels;
+  if (wants_concat != (c_concat != nullptr))
+    throw Error(LIDM_ERR_INVALID, wants_concat ? "this model is concat-conditioned: c_concat is required"
+                                               : "this model takes no concat conditioning");
+  if (h->has_st != (context != nullptr && ctx_len > 0))
+    throw Error(LIDM_ERR_INVALID, h->has_st ? "this model is cross-attention conditioned: a context (B, L, context_dim) is required"
+                                            : "this model takes no cross-attention context");
+}
+
+// DiffusionWrapper 'concat': xc = torch.cat([x] + c_concat, dim=1).  Writes rows [row0, row0 + B) of the assembled
+// (rows_total, in_channels, H, W) buffer and returns the buffer (or x itself when there is nothing to concatenate).
+const float* assemble_input(lidm_handle* h, const float* x, const float* c_concat, int B, int row0, int rows_total,
+                            cudaStream_t s, bool force_copy = false) {
+  const lidm_config& cfg = h->cfg;
+  const size_t HW = (size_t)cfg.latent_h * cfg.latent_w;
+  const int Cl = h->latent_channels, Cin = cfg.in_channels;
+  if (Cin == Cl && !force_copy) return x;
+  const size_t need = (size_t)rows_total * Cin * HW;
+  if (need > h->xcat_elems) {
+    LIDM_CUDA_CHECK(cudaStreamSynchronize(s));
+    cudaFree(h->xcat); h->xcat = nullptr; h->xcat_elems = 0;
+    LIDM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&h->xcat), need * sizeof(float)));
+    h->xcat_elems = need;
+  }
+  float* dst = h->xcat + (size_t)row0 * Cin * HW;
+  LIDM_CUDA_CHECK(cudaMemcpy2DAsync(dst, Cin * HW * sizeof(float), x, Cl * HW * sizeof(float), Cl * HW * sizeof(float), B,
+                                    cudaMemcpyDeviceToDevice, s));
+  if (Cin > Cl)
+    LIDM_CUDA_CHECK(cudaMemcpy2DAsync(dst + Cl * HW, Cin * HW * sizeof(float), c_concat, (Cin - Cl) * HW * sizeof(float),
+                                      (Cin - Cl) * HW * sizeof(float), B, cudaMemcpyDeviceToDevice, s));
+  return h->xcat;
+}
+
 struct TmpBufs {
   std::vector<void*> p;
   template <class T> T* get(size_t n) {
@@ -1567,19 +1805,28 @@ int lidm_image_shape(const lidm_handle* h, int32_t* c, int32_t* hh, int32_t* ww)
   return LIDM_OK;
 }
 
-int lidm_unet_forward(lidm_handle* h, const float* x, const int64_t* t, float* eps_out, int32_t B, void* stream) {
+int lidm_unet_forward_cond(lidm_handle* h, const float* x, const int64_t* t, const float* c_concat, const float* context,
+                           int32_t ctx_len, float* eps_out, int32_t B, void* stream) {
   return guarded(h, [&] {
     require_ready(h, B);
     LIDM_REQUIRE(x != nullptr && t != nullptr && eps_out != nullptr, "null tensor");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    Plan* P = get_plan(h, h->unet_plans, B, h->cfg.precision ? build_unet_plan_pass_p : build_unet_plan_pass);
+    check_conditioning(h, c_concat, context, ctx_len);
+    Plan* P = get_plan(h, h->unet_plans, B, h->cfg.precision ? build_unet_plan_pass_p : build_unet_plan_pass,
+                       h->has_st ? ctx_len : 0);
     ensure_time_buffers(h, B);
     run_time_embed(h, t, B, s);
     P->x = x; P->out = eps_out;
+    P->xin = assemble_input(h, x, c_concat, B, 0, B, s);
+    P->context = context;
     P->rowadd_base = h->emb_out; P->rowadd_ld = h->emb_total;
     P->ddim_x_prev = nullptr; P->ddim_noise = nullptr; P->ddim_pred_x0 = nullptr; P->ddim_coef = nullptr;
     run_plan(P, s);
   });
+}
+
+int lidm_unet_forward(lidm_handle* h, const float* x, const int64_t* t, float* eps_out, int32_t B, void* stream) {
+  return lidm_unet_forward_cond(h, x, t, nullptr, nullptr, 0, eps_out, B, stream);
 }
 
 int lidm_ddim_step(const float* x, const float* eps, const float* noise, float a_t, float a_prev, float sigma_t,
@@ -1598,8 +1845,10 @@ int lidm_ddim_step(const float* x, const float* eps, const float* noise, float a
   });
 }
 
-int lidm_ddim_sample(lidm_handle* h, float* x_inout, const int64_t* timesteps, const float* sched, int32_t n_steps,
-                     const float* noise, float temperature, float* pred_x0_out, int32_t B, void* stream) {
+int lidm_ddim_sample_cond(lidm_handle* h, float* x_inout, const int64_t* timesteps, const float* sched, int32_t n_steps,
+                          const float* noise, float temperature, float* pred_x0_out, int32_t B, const float* c_concat,
+                          const float* context, int32_t ctx_len, const float* uncond_concat, const float* uncond_context,
+                          float guidance_scale, void* stream) {
   return guarded(h, [&] {
     require_ready(h, B);
     LIDM_REQUIRE(x_inout != nullptr && timesteps != nullptr && sched != nullptr && n_steps > 0, "null argument");
@@ -1607,9 +1856,20 @@ int lidm_ddim_sample(lidm_handle* h, float* x_inout, const int64_t* timesteps, c
     const lidm_config& cfg = h->cfg;
     for (int i = 0; i < n_steps; ++i)
       LIDM_REQUIRE(timesteps[i] >= 0, "negative timestep");
-    Plan* P = get_plan(h, h->unet_plans, B, h->cfg.precision ? build_unet_plan_pass_p : build_unet_plan_pass);
+    check_conditioning(h, c_concat, context, ctx_len);
+    const bool wants_concat = cfg.in_channels > h->latent_channels;
+    // classifier-free guidance (ddim.py:173-180) needs the unconditional twin of every conditioning tensor
+    const bool guided = (uncond_concat != nullptr || uncond_context != nullptr) && guidance_scale != 1.0f;
+    if (guided) {
+      LIDM_REQUIRE(!wants_concat || uncond_concat != nullptr, "guidance: unconditional concat tensor missing");
+      LIDM_REQUIRE(!h->has_st || uncond_context != nullptr, "guidance: unconditional context missing");
+    }
+    const int Bp = guided ? 2 * B : B;       // batch the U-Net plan runs at
+    const int L = h->has_st ? ctx_len : 0;
+    Plan* P = get_plan(h, h->unet_plans, Bp, h->cfg.precision ? build_unet_plan_pass_p : build_unet_plan_pass, L);
     ensure_time_buffers(h, n_steps);
-    const size_t elems = (size_t)B * cfg.in_channels * cfg.latent_h * cfg.latent_w;
+    const size_t HW = (size_t)cfg.latent_h * cfg.latent_w;
+    const size_t elems = (size_t)B * h->latent_channels * HW;
     if (elems > h->xbuf_elems) {
       cudaFree(h->xa); cudaFree(h->xb); h->xa = h->xb = nullptr; h->xbuf_elems = 0;
       LIDM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&h->xa), elems * sizeof(float)));
@@ -1620,6 +1880,25 @@ int lidm_ddim_sample(lidm_handle* h, float* x_inout, const int64_t* timesteps, c
       cudaFree(h->coef_dev); h->coef_dev = nullptr; h->coef_rows = 0;
       LIDM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&h->coef_dev), (size_t)n_steps * 5 * sizeof(float)));
       h->coef_rows = n_steps;
+    }
+    const float* ctx_run = context;
+    if (guided) {
+      if (2 * elems > h->eps2_elems) {
+        cudaFree(h->eps2); h->eps2 = nullptr; h->eps2_elems = 0;
+        LIDM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&h->eps2), 2 * elems * sizeof(float)));
+        h->eps2_elems = 2 * elems;
+      }
+      if (h->has_st) {   // c_in = torch.cat([unconditional_conditioning, c])
+        const size_t ce = (size_t)B * ctx_len * cfg.context_dim;
+        if (2 * ce > h->ctx2_elems) {
+          cudaFree(h->ctx2); h->ctx2 = nullptr; h->ctx2_elems = 0;
+          LIDM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&h->ctx2), 2 * ce * sizeof(float)));
+          h->ctx2_elems = 2 * ce;
+        }
+        LIDM_CUDA_CHECK(cudaMemcpyAsync(h->ctx2, uncond_context, ce * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        LIDM_CUDA_CHECK(cudaMemcpyAsync(h->ctx2 + ce, context, ce * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        ctx_run = h->ctx2;
+      }
     }
     // loop order: i-th iteration uses index = n_steps-1-i (np.flip(ddim_timesteps), ddim.py:136-143)
     std::vector<int64_t> t_loop(n_steps);
@@ -1638,16 +1917,44 @@ int lidm_ddim_sample(lidm_handle* h, float* x_inout, const int64_t* timesteps, c
     float* cur = h->xa;
     float* nxt = h->xb;
     for (int i = 0; i < n_steps; ++i) {
-      P->x = cur; P->out = nullptr;
+      P->x = cur;
+      P->context = ctx_run;
       P->rowadd_base = h->emb_out + (size_t)i * h->emb_total; P->rowadd_ld = 0;
-      P->ddim_x_prev = nxt;
-      P->ddim_noise = noise ? noise + (size_t)i * elems : nullptr;
-      P->ddim_pred_x0 = (i == n_steps - 1) ? pred_x0_out : nullptr;
-      P->ddim_coef = h->coef_dev + (size_t)i * 5;
-      run_plan(P, s);
+      const float* nz = noise ? noise + (size_t)i * elems : nullptr;
+      float* px0 = (i == n_steps - 1) ? pred_x0_out : nullptr;
+      if (!guided) {
+        P->xin = assemble_input(h, cur, c_concat, B, 0, B, s);
+        P->out = nullptr;
+        P->ddim_x_prev = nxt; P->ddim_noise = nz; P->ddim_pred_x0 = px0;
+        P->ddim_coef = h->coef_dev + (size_t)i * 5;
+        run_plan(P, s);
+      } else {
+        // x_in = torch.cat([x] * 2); c_in = torch.cat([uncond, cond]); one 2B evaluation, then the guided update
+        assemble_input(h, cur, uncond_concat, B, 0, 2 * B, s, true);
+        P->xin = assemble_input(h, cur, c_concat, B, B, 2 * B, s, true);
+        P->out = h->eps2;
+        P->ddim_x_prev = nullptr; P->ddim_noise = nullptr; P->ddim_pred_x0 = nullptr; P->ddim_coef = nullptr;
+        run_plan(P, s);
+        launch_cfg_ddim_step(cur, h->eps2, guidance_scale, nz, h->coef_dev + (size_t)i * 5, nxt, px0, nullptr,
+                             (int64_t)elems, s);
+      }
       std::swap(cur, nxt);
     }
     LIDM_CUDA_CHECK(cudaMemcpyAsync(x_inout, cur, elems * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  });
+}
+
+int lidm_ddim_sample(lidm_handle* h, float* x_inout, const int64_t* timesteps, const float* sched, int32_t n_steps,
+                     const float* noise, float temperature, float* pred_x0_out, int32_t B, void* stream) {
+  return lidm_ddim_sample_cond(h, x_inout, timesteps, sched, n_steps, noise, temperature, pred_x0_out, B, nullptr, nullptr,
+                               0, nullptr, nullptr, 1.0f, stream);
+}
+
+int lidm_cfg_combine(const float* eps2, float guidance_scale, float* eps_out, int64_t n, void* stream) {
+  return guarded(nullptr, [&] {
+    LIDM_REQUIRE(eps2 != nullptr && eps_out != nullptr && n > 0, "null tensor");
+    launch_cfg_ddim_step(nullptr, eps2, guidance_scale, nullptr, nullptr, nullptr, nullptr, eps_out, n,
+                         reinterpret_cast<cudaStream_t>(stream));
   });
 }
 

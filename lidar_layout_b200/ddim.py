@@ -97,10 +97,18 @@ class DDIMSampler(object):
             table = self.ddim_table[:subset_end]
         total_steps = timesteps.shape[0]
         intermediates = {'x_inter': [img], 'pred_x0': [img]}
-        fused = (cond is None and callback is None and img_callback is None and not quantize_denoised
-                 and mask is None and score_corrector is None and noise_dropout == 0.
-                 and (unconditional_conditioning is None or unconditional_guidance_scale == 1.))
+        fused = (callback is None and img_callback is None and not quantize_denoised
+                 and mask is None and score_corrector is None and noise_dropout == 0.)
         if fused:
+            # conditioning tensors for the on-device loop (+ their unconditional twins for classifier-free guidance)
+            cond_kw = {}
+            if cond is not None:
+                c_concat, context = self.model.split_conditioning(cond)
+                guided = unconditional_conditioning is not None and unconditional_guidance_scale != 1.
+                uc_concat, uc_context = (self.model.split_conditioning(unconditional_conditioning) if guided
+                                         else (None, None))
+                cond_kw = dict(c_concat=c_concat, context=context, uncond_concat=uc_concat, uncond_context=uc_context,
+                               guidance_scale=float(unconditional_guidance_scale) if guided else 1.0)
             # the reference draws one randn(shape) per step in loop order (ddim.py:202) whatever eta is
             noise = torch.stack([torch.randn(shape, device=device) for _ in range(total_steps)])
             use_noise = bool(np.any(table[:, 2] != 0))
@@ -112,7 +120,8 @@ class DDIMSampler(object):
                 i0, i1 = total_steps - 1 - hi, total_steps - 1 - stop      # loop iterations [i0, i1]
                 img, pred_x0 = self.model.engine.ddim_sample(
                     img, timesteps[stop:hi + 1], table[stop:hi + 1],
-                    noise=noise[i0:i1 + 1] if use_noise else None, temperature=temperature, want_pred_x0=True)
+                    noise=noise[i0:i1 + 1] if use_noise else None, temperature=temperature, want_pred_x0=True,
+                    **cond_kw)
                 intermediates['x_inter'].append(img)
                 intermediates['pred_x0'].append(pred_x0)
                 hi = stop - 1
@@ -146,10 +155,18 @@ class DDIMSampler(object):
         """reference ddim.py:167-206, one step (eps from the U-Net kernels, update from lidm_ddim_step)."""
         if use_original_steps:
             raise NotImplementedError("use_original_steps is not supported on the B200 path")
-        if unconditional_conditioning is not None and unconditional_guidance_scale != 1.:
-            raise NotImplementedError("classifier-free guidance needs a conditioned U-Net (not on the B200 path yet)")
         table = self.ddim_table if table is None else table
-        e_t = self.model.apply_model(x, t, c)
+        if unconditional_conditioning is None or unconditional_guidance_scale == 1.:
+            e_t = self.model.apply_model(x, t, c)
+        else:
+            # ddim.py:175-180: one 2B evaluation on [uncond | cond], then e_u + s (e_c - e_u)
+            x_in = torch.cat([x] * 2)
+            t_in = torch.cat([t] * 2)
+            if isinstance(c, dict):
+                c_in = {k: [torch.cat([unconditional_conditioning[k][i], c[k][i]]) for i in range(len(c[k]))] for k in c}
+            else:
+                c_in = torch.cat([unconditional_conditioning, c])
+            e_t = self.model.engine.cfg_combine(self.model.apply_model(x_in, t_in, c_in), unconditional_guidance_scale)
         if score_corrector is not None:
             assert self.model.parameterization == "eps"
             e_t = score_corrector.modify_score(self.model, e_t, x, t, c, **corrector_kwargs)

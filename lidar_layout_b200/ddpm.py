@@ -108,19 +108,40 @@ class LatentDiffusion:
         yield None
 
     # ---- per-step hook --------------------------------------------------------------------------------
+    def split_conditioning(self, cond):
+        """The dispatch of apply_model + DiffusionWrapper.forward (ddpm.py:900-909, 2313-2339) for the conditioning
+        keys None / 'concat' / 'crossattn' / 'hybrid': cond (tensor, list or {'c_concat': [...], 'c_crossattn': [...]})
+        -> (c_concat (B,Cc,H,W) or None, context (B,L,D) or None)."""
+        key = self.model.conditioning_key
+        if isinstance(cond, dict):
+            pass
+        else:
+            if cond is None or (isinstance(cond, (list, tuple)) and all(c is None for c in cond)):
+                cond = {}
+            else:
+                if not isinstance(cond, (list, tuple)):
+                    cond = [cond]
+                cond = {"c_concat" if key == "concat" else "c_crossattn": list(cond)}
+        c_concat = cond.get("c_concat")
+        c_cross = cond.get("c_crossattn")
+        if key is None:
+            if c_concat or c_cross:
+                raise ValueError("this model is unconditional (conditioning_key None) but a conditioning was given")
+            return None, None
+        cc = torch.cat(list(c_concat), dim=1) if (c_concat and key in ("concat", "hybrid")) else None
+        cx = torch.cat(list(c_cross), dim=1) if (c_cross and key in ("crossattn", "hybrid")) else None
+        if key in ("concat", "hybrid") and cc is None:
+            raise ValueError(f"conditioning_key {key!r} needs c_concat")
+        if key in ("crossattn", "hybrid") and cx is None:
+            raise ValueError(f"conditioning_key {key!r} needs c_crossattn")
+        return cc, cx
+
     @torch.no_grad()
     def apply_model(self, x_noisy, t, cond, return_ids=False):
-        """ddpm.py:900-1000 -> DiffusionWrapper.forward (:2313) -> UNetModel.forward, unconditional."""
-        if isinstance(cond, dict):
-            has = any(v is not None and v != [None] for v in cond.values())
-        elif isinstance(cond, (list, tuple)):
-            has = any(v is not None for v in cond)
-        else:
-            has = cond is not None
-        if has:
-            raise NotImplementedError("conditioned sampling is not on the B200 path yet")
+        """ddpm.py:900-1000 -> DiffusionWrapper.forward (:2313) -> UNetModel.forward."""
         assert not return_ids
-        return self.engine.unet_forward(x_noisy, t)
+        c_concat, context = self.split_conditioning(cond)
+        return self.engine.unet_forward(x_noisy, t, c_concat=c_concat, context=context)
 
     @torch.no_grad()
     def decode_first_stage(self, z, predict_cids=False, force_not_quantize=False):

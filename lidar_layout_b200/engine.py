@@ -27,12 +27,19 @@ def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
 
 def to_cconfig(cfg: LidmConfig) -> _lib.CConfig:
     u, a = cfg.unet, cfg.ae
-    if u.use_spatial_transformer or cfg.conditioning_key is not None:
-        raise NotImplementedError("conditioned U-Nets (SpatialTransformer / concat) are not on the B200 path yet")
+    if cfg.conditioning_key not in (None, "concat", "crossattn", "hybrid"):
+        raise NotImplementedError(f"conditioning_key {cfg.conditioning_key!r} is not on the B200 path "
+                                  "(supported: None, 'concat', 'crossattn', 'hybrid')")
     if u.use_scale_shift_norm or u.resblock_updown or not u.conv_resample:
         raise NotImplementedError("unsupported UNetModel option for the B200 path")
-    if tuple(u.image_size) != tuple(cfg.image_size) or u.in_channels != cfg.channels:
+    if tuple(u.image_size) != tuple(cfg.image_size) or u.in_channels < cfg.channels:
         raise ValueError("unet image_size/in_channels must match the latent shape")
+    if (u.in_channels > cfg.channels) != (cfg.conditioning_key in ("concat", "hybrid")):
+        raise ValueError("unet in_channels exceeds the latent channels only for concat / hybrid conditioning")
+    if u.use_spatial_transformer and (u.context_dim is None or isinstance(u.context_dim, (list, tuple))):
+        raise NotImplementedError("use_spatial_transformer needs a single integer context_dim")
+    if bool(u.use_spatial_transformer) != (cfg.conditioning_key in ("crossattn", "hybrid")):
+        raise ValueError("crossattn / hybrid conditioning needs use_spatial_transformer (and vice versa)")
     c = _lib.CConfig()
     c.in_channels, c.out_channels, c.model_channels = u.in_channels, u.out_channels, u.model_channels
     c.num_res_blocks, c.num_head_channels = u.num_res_blocks, u.num_head_channels
@@ -54,6 +61,10 @@ def to_cconfig(cfg: LidmConfig) -> _lib.CConfig:
     if cfg.precision not in ("bf16", "fp32"):
         raise ValueError("precision must be 'bf16' or 'fp32'")
     c.precision = 1 if cfg.precision == "fp32" else 0
+    c.latent_channels = cfg.channels
+    c.use_spatial_transformer = int(bool(u.use_spatial_transformer))
+    c.context_dim = int(u.context_dim or 0)
+    c.transformer_depth = int(u.transformer_depth)
     return c
 
 
@@ -101,18 +112,52 @@ class Engine:
         return self
 
     # ---- raw calls ------------------------------------------------------------------------------------
-    def unet_forward(self, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+    def _cond_ptrs(self, B, c_concat, context, what="conditioning"):
+        """Validate / normalise the two conditioning tensors -> (c_concat, context, ctx_len); tensors are returned so the
+        caller keeps them alive for the duration of the call."""
+        u = self.cfg.unet
+        if c_concat is not None:
+            c_concat = _f32c(c_concat, "c_concat")
+            exp = (B, u.in_channels - self.cfg.channels) + tuple(self.cfg.image_size)
+            if tuple(c_concat.shape) != exp:
+                raise ValueError(f"{what}: c_concat must have shape {exp}, got {tuple(c_concat.shape)}")
+        L = 0
+        if context is not None:
+            context = _f32c(context, "context")
+            if context.dim() != 3 or context.shape[0] != B or context.shape[2] != u.context_dim:
+                raise ValueError(f"{what}: context must be (B={B}, L, {u.context_dim}), got {tuple(context.shape)}")
+            L = int(context.shape[1])
+        return c_concat, context, L
+
+    def unet_forward(self, x: torch.Tensor, t: torch.Tensor, c_concat: Optional[torch.Tensor] = None,
+                     context: Optional[torch.Tensor] = None) -> torch.Tensor:
         x = _f32c(x, "x")
         t = t.to(device=x.device, dtype=torch.int64).contiguous()
         out = torch.empty_like(x)
+        c_concat, context, L = self._cond_ptrs(x.shape[0], c_concat, context)
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.lidm_unet_forward(self._h, x.data_ptr(), t.data_ptr(), out.data_ptr(), x.shape[0],
-                                                   _stream_ptr(self.device)), self._h)
+            _lib.check(self._lib.lidm_unet_forward_cond(
+                self._h, x.data_ptr(), t.data_ptr(), c_concat.data_ptr() if c_concat is not None else None,
+                context.data_ptr() if context is not None else None, L, out.data_ptr(), x.shape[0],
+                _stream_ptr(self.device)), self._h)
+        return out
+
+    def cfg_combine(self, eps2: torch.Tensor, scale: float) -> torch.Tensor:
+        """e_u + scale * (e_c - e_u) for eps2 = cat([e_u, e_c]) (ddim.py:179-180)."""
+        eps2 = _f32c(eps2, "eps2")
+        out = torch.empty((eps2.shape[0] // 2,) + tuple(eps2.shape[1:]), dtype=torch.float32, device=eps2.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.lidm_cfg_combine(eps2.data_ptr(), float(scale), out.data_ptr(), out.numel(),
+                                                  _stream_ptr(self.device)))
         return out
 
     def ddim_sample(self, x_T: torch.Tensor, timesteps: np.ndarray, table: np.ndarray,
-                    noise: Optional[torch.Tensor] = None, temperature: float = 1.0, want_pred_x0: bool = False):
-        """Whole DDIM loop on the device.  timesteps ascending int64 [n]; table float32 [n,4]."""
+                    noise: Optional[torch.Tensor] = None, temperature: float = 1.0, want_pred_x0: bool = False,
+                    c_concat: Optional[torch.Tensor] = None, context: Optional[torch.Tensor] = None,
+                    uncond_concat: Optional[torch.Tensor] = None, uncond_context: Optional[torch.Tensor] = None,
+                    guidance_scale: float = 1.0):
+        """Whole DDIM loop on the device.  timesteps ascending int64 [n]; table float32 [n,4].  Optional conditioning
+        (concat tensor and / or cross-attention context) and classifier-free guidance against its unconditional twin."""
         x = _f32c(x_T, "x_T").clone()
         n = int(len(timesteps))
         ts = np.ascontiguousarray(timesteps, dtype=np.int64)
@@ -124,11 +169,18 @@ class Engine:
             assert noise.shape == (n,) + tuple(x.shape), "noise must be (n_steps, B, C, H, W)"
             nz_ptr = noise.data_ptr()
         pred = torch.empty_like(x) if want_pred_x0 else None
+        B = x.shape[0]
+        c_concat, context, L = self._cond_ptrs(B, c_concat, context)
+        uncond_concat, uncond_context, Lu = self._cond_ptrs(B, uncond_concat, uncond_context, "unconditional conditioning")
+        if uncond_context is not None and Lu != L:
+            raise ValueError("the unconditional context must have the same length as the context")
+        ptr = lambda t: t.data_ptr() if t is not None else None
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.lidm_ddim_sample(
+            _lib.check(self._lib.lidm_ddim_sample_cond(
                 self._h, x.data_ptr(), ts.ctypes.data_as(ctypes.POINTER(c_int64)),
                 tab.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), n, nz_ptr, float(temperature),
-                pred.data_ptr() if pred is not None else None, x.shape[0], _stream_ptr(self.device)), self._h)
+                ptr(pred), B, ptr(c_concat), ptr(context), L, ptr(uncond_concat), ptr(uncond_context),
+                float(guidance_scale), _stream_ptr(self.device)), self._h)
         return x, pred
 
     def image_shape(self):
