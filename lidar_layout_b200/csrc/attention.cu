@@ -694,14 +694,20 @@ attention_d32_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 //   * O accumulates in TMEM across the whole K/V loop (tcgen05.mma accumulate); the running max is only refreshed,
 //     and O rescaled in place (tcgen05.ld / scale / tcgen05.st), when some row's max grew by more than 2^8 — the
 //     result is exact because the row sum l is kept against the same (stale) max.
-//   * P is double-buffered in shared memory; S needs a single TMEM buffer per group because each softmax thread
-//     drains its whole S row into registers first and hands the buffer straight back.
+//   * P never touches shared memory: the softmax threads write it (bf16 pairs) into tensor memory with tcgen05.st and
+//     the P*V product takes its A operand from there (tcgen05.mma [d], [a_tmem], b_desc).  With P in shared memory the
+//     N=32 P*V instructions are bound by streaming the 32 KiB P tile through the shared-memory port (measured 45 clk
+//     per M128 N32 K16 instruction against 16 ideal, tests/microbench/umma_rate.cu) on top of the 32 KiB the softmax
+//     warps store, and the single MMA-issuing thread — tcgen05.mma issue blocks until the instruction is accepted —
+//     became the critical path of the whole kernel.
+//   * S needs a single TMEM buffer per group because each softmax thread drains its whole S row into registers first
+//     and hands the buffer straight back.
 //   * the MMA thread is event driven: it polls (mbarrier.test_wait) the barriers of all groups and issues whichever
 //     of S_g(j+1) / P_g(j)V(j) is ready; the groups are started a fraction of a tile apart and stay out of phase,
 //     so one group's MUFU-bound exp phase overlaps the others' TMEM-load / max / store phases.
 //   <2,128>: 2 groups x 168 registers (whole 128-column rows in registers);  <4,64>: 4 groups x 112 registers —
 //   twice the softmax warps per scheduler for latency hiding.
-// TMEM: S_g at columns g*BKV_, O_g at NG*BKV_ + g*32.
+// TMEM: S_g at columns g*BKV_, P_g (BKV_/2 columns) at NG*BKV_ + g*BKV_/2, O_g at NG*BKV_*3/2 + g*32.
 namespace v4 {
 
 constexpr int KV_ST = 4;
@@ -710,18 +716,17 @@ constexpr float RESCALE_LOG2 = 8.f;
 template <int NG, int BKV_>
 struct Cfg {
   static constexpr int KB = BKV_ * 64;                        // bytes of one K (or V) tile
-  static constexpr int PB = BQ * BKV_ * 2;                    // bytes of one P buffer
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + NG * Q_BYTES;
   static constexpr int OFF_V = OFF_K + KV_ST * KB;
-  static constexpr int OFF_P = OFF_V + KV_ST * KB;            // [group][buffer]
-  static constexpr int OFF_BAR = OFF_P + NG * 2 * PB;
+  static constexpr int OFF_BAR = OFF_V + KV_ST * KB;
   static constexpr int SMEM_TOTAL = OFF_BAR + 512 + 1024;
-  static constexpr uint32_t O_COL = NG * BKV_;
-  static constexpr uint32_t TMEM_COLS = 512;
+  static constexpr uint32_t P_COL = NG * BKV_;
+  static constexpr uint32_t O_COL = P_COL + NG * (BKV_ / 2);
+  static constexpr uint32_t TMEM_COLS = (O_COL + NG * 32) <= 256 ? 256 : 512;
   static constexpr int THREADS = 128 + NG * 128;
   static constexpr int NCH = BKV_ / 32;                       // 32-column chunks per S row
-  static_assert(NG * BKV_ + NG * 32 <= 512, "TMEM budget");
+  static_assert(O_COL + NG * 32 <= 512, "TMEM budget");
   static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
 };
 
@@ -737,9 +742,9 @@ attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint64_t* kv_empty = kv_full + KV_ST;    // [KV_ST]
   uint64_t* s_ready = kv_empty + KV_ST;    // [NG]
   uint64_t* s_free = s_ready + NG;         // [NG]
-  uint64_t* p_ready = s_free + NG;         // [NG][2 buffers]
-  uint64_t* pv_done = p_ready + 2 * NG;    // [NG][2 buffers]
-  uint64_t* stagger = pv_done + 2 * NG;    // [NG]: group g-1 -> group g, once per CTA
+  uint64_t* p_ready = s_free + NG;         // [NG]
+  uint64_t* pv_done = p_ready + NG;        // [NG]
+  uint64_t* stagger = pv_done + NG;        // [NG]: group g-1 -> group g, once per CTA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stagger + NG);
 
   const int warp = threadIdx.x >> 5;
@@ -755,7 +760,7 @@ attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     mbar_init(q_full, 1);
     for (int s = 0; s < KV_ST; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     for (int g = 0; g < NG; ++g) { mbar_init(&s_ready[g], 1); mbar_init(&s_free[g], 4); mbar_init(&stagger[g], 4); }
-    for (int i = 0; i < 2 * NG; ++i) { mbar_init(&p_ready[i], 4); mbar_init(&pv_done[i], 1); }
+    for (int i = 0; i < NG; ++i) { mbar_init(&p_ready[i], 4); mbar_init(&pv_done[i], 1); }
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, L::TMEM_COLS); tmem_relinquish(); }
@@ -789,6 +794,10 @@ attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 #pragma unroll
         for (int g = 0; g < NG; ++g) js[g] = jp[g] = 0;
         int released = 0;                      // K/V tiles handed back to the TMA warp
+#ifdef LIDM_ATTN_TRACE
+        const bool trc = blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 40;
+        long long tS[2][8], tPV[2][8];
+#endif
         mbar_wait(q_full, 0);
         const long long t0 = clock64();
         int remaining = NG * nkv;
@@ -807,23 +816,28 @@ attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                 umma_bf16_ss(d, qdesc, kdesc, idesc_s, 0);
                 umma_bf16_ss(d, qdesc + 2, kdesc + 2, idesc_s, 1);
                 umma_commit(&s_ready[g]);
+#ifdef LIDM_ATTN_TRACE
+                if (trc && j < 8) tS[g][j] = clock64();
+#endif
                 js[g] = j + 1;
               }
             }
             if (jp[g] < js[g]) {
-              const int j = jp[g], st = j % KV_ST, pb = g * 2 + (j & 1);
-              if (mbar_test_wait(&p_ready[pb], (j >> 1) & 1)) {
+              const int j = jp[g], st = j % KV_ST;
+              if (mbar_test_wait(&p_ready[g], j & 1)) {
                 tcgen05_fence_after();
                 const uint64_t vdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_V + st * L::KB));
-                const uint64_t pdesc = make_kmajor_desc<128>(smem_u32(smem + L::OFF_P + pb * L::PB));
+                const uint32_t tP = tmem_base + L::P_COL + g * (BKV_ / 2);
                 const uint32_t dO = tmem_base + L::O_COL + g * 32;
 #pragma unroll
                 for (int kk = 0; kk < BKV_ / 16; ++kk) {
-                  const uint64_t pa = pdesc + (uint64_t)(((kk >> 2) * (BQ * 128) + (kk & 3) * 32) >> 4);
                   const uint64_t vb = vdesc + (uint64_t)((kk * 1024) >> 4);
-                  umma_bf16_ss(dO, pa, vb, idesc_o, (j > 0 || kk != 0) ? 1u : 0u);
+                  umma_bf16_ts(dO, tP + kk * 8, vb, idesc_o, (j > 0 || kk != 0) ? 1u : 0u);   // 16 bf16 = 8 columns
                 }
-                umma_commit(&pv_done[pb]);
+                umma_commit(&pv_done[g]);
+#ifdef LIDM_ATTN_TRACE
+                if (trc && j < 8) tPV[g][j] = clock64();
+#endif
                 jp[g] = j + 1;
                 --remaining;
                 int jmin = jp[0];
@@ -838,6 +852,11 @@ attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             __trap();
           }
         }
+#ifdef LIDM_ATTN_TRACE
+        if (trc && nkv >= 8)
+          for (int j = 0; j < 8; ++j)
+            printf("mma j%d: S0 %lld S1 %lld PV0 %lld PV1 %lld\n", j, tS[0][j] - t0, tS[1][j] - t0, tPV[0][j] - t0, tPV[1][j] - t0);
+#endif
       }
     }
   } else {
@@ -847,12 +866,25 @@ attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const int row = qd * 32 + lane;                // row inside the 128-row tile
     const uint32_t tS = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + g * BKV_;
     const uint32_t tO = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + L::O_COL + g * 32;
-    const uint32_t sbase = smem_u32(smem);
+    const uint32_t tP = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + L::P_COL + g * (BKV_ / 2);
     constexpr float LOG2E = 1.4426950408889634f;
     float m = 0.f, l = 0.f;
+#ifdef LIDM_ATTN_TRACE
+    long long tr[6] = {0, 0, 0, 0, 0, 0};
+    long long tc = clock64();
+    const long long tbeg = tc;
+    long long tsr[8], tpr[8];
+#define TR(k) { const long long tn = clock64(); tr[k] += tn - tc; tc = tn; }
+#else
+#define TR(k)
+#endif
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(&s_ready[g], j & 1);
       tcgen05_fence_after();
+      TR(0)
+#ifdef LIDM_ATTN_TRACE
+      if (j < 8) tsr[j] = clock64() - tbeg;
+#endif
       uint32_t sv[L::NCH][32];
 #pragma unroll
       for (int c = 0; c < L::NCH; ++c) tmem_ld_32x32b_x32(tS + c * 32, sv[c]);
@@ -860,6 +892,7 @@ attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[g]);      // S_g(j+1) may overwrite the TMEM buffer now
+      TR(1)
       if (kv_len - j * BKV_ < BKV_) {               // ragged last tile (cross-attention context): mask the padding keys
         const int valid = kv_len - j * BKV_;
 #pragma unroll
@@ -881,12 +914,12 @@ attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         }
       }
       const float r = max3(fmaxf(m0, m1), m2, m3);
+      TR(2)
       if (j == 0) {
         m = r;
       } else if (__any_sync(0xffffffffu, (r - m) * LOG2E > RESCALE_LOG2)) {
         // rare: refresh the running max of every row of this warp and rescale O in TMEM
-        const int pj = j - 1;
-        mbar_wait(&pv_done[g * 2 + (pj & 1)], (pj >> 1) & 1);      // every P*V issued so far has completed
+        mbar_wait(&pv_done[g], (j - 1) & 1);   // every P*V issued so far has completed
         tcgen05_fence_after();
         const float mn = fmaxf(m, r);
         const float alpha = ex2((m - mn) * LOG2E);
@@ -900,14 +933,13 @@ attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         l *= alpha;
         m = mn;
       }
-      if (j >= 2) mbar_wait(&pv_done[g * 2 + (j & 1)], ((j - 2) >> 1) & 1);   // P buffer (j & 1) is free again
       if (j == 0 && g > 0 && nkv > 1) mbar_wait(&stagger[g], 0);               // start a fraction of a tile apart
       const float mb = m * LOG2E;
-      const uint32_t prow = sbase + L::OFF_P + (g * 2 + (j & 1)) * L::PB + row * 128;
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      uint32_t pkk[32];
 #pragma unroll
       for (int c = 0; c < L::NCH; ++c) {
-        uint32_t pk[16];
+        uint32_t* pk = &pkk[(c & 1) * 16];
 #pragma unroll
         for (int i = 0; i < 16; i += 2) {
           const float p0 = ex2(fmaf(__uint_as_float(sv[c][2 * i]), LOG2E, -mb));
@@ -919,25 +951,39 @@ attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           pk[i] = pack_bf16(p0, p1);
           pk[i + 1] = pack_bf16(p2, p3);
         }
-        const uint32_t base = prow + (c >> 1) * (BQ * 128);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int chunk = ((c & 1) * 4 + i) ^ (row & 7);
-          st_shared_v4(base + chunk * 16, pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        if (c & 1) {
+          if (c == 1 && j > 0) {
+            // P_g(j-1) V(j-1) must have drained P before it is overwritten; by now half of this tile's exponentials
+            // are done, so the wait is normally free
+            TR(4)
+            mbar_wait(&pv_done[g], (j - 1) & 1);
+            tcgen05_fence_after();
+            TR(3)
+          }
+          tmem_st_32x32b_x32(tP + (c >> 1) * 32, pkk);   // 64 keys = 32 columns of bf16 pairs
         }
         if (c == L::NCH / NG - 1 + (L::NCH / NG == 0) && j == 0 && g + 1 < NG && lane == 0) mbar_arrive(&stagger[g + 1]);
       }
       l += (s0 + s1) + (s2 + s3);
-      fence_proxy_async();
+      TR(4)
+      tmem_st_wait();
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_ready[g * 2 + (j & 1)]);
+      if (lane == 0) mbar_arrive(&p_ready[g]);
+      TR(5)
+#ifdef LIDM_ATTN_TRACE
+      if (j < 8) tpr[j] = clock64() - tbeg;
+#endif
     }
-    {
-      const int pj = nkv - 1;
-      mbar_wait(&pv_done[g * 2 + (pj & 1)], (pj >> 1) & 1);
-      tcgen05_fence_after();
-    }
+#ifdef LIDM_ATTN_TRACE
+    if (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 40 && lane == 0 && (warp == 4 || warp == 8))
+      for (int j = 0; j < 8 && nkv >= 8; ++j) printf("smx warp %d j%d: s_ready seen %lld  p_ready sent %lld\n", warp, j, tsr[j], tpr[j]);
+    if (blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 40 && lane == 0 && (warp == 4 || warp == 8))
+      printf("attn trace warp %d nkv %d: wait_s %lld  ldS %lld  max %lld  wait_pv %lld  exp %lld  arrive %lld (clk per tile)\n",
+             warp, nkv, tr[0] / nkv, tr[1] / nkv, tr[2] / nkv, tr[3] / nkv, tr[4] / nkv, tr[5] / nkv);
+#endif
+    mbar_wait(&pv_done[g], (nkv - 1) & 1);
+    tcgen05_fence_after();
     uint32_t o[32];
     tmem_ld_32x32b_x32(tO, o);
     tmem_ld_wait();

@@ -71,7 +71,7 @@ def test_range2pcd_dropin(model, golden_tiny):
 
 def test_error_behaviour(model):
     import lidar_layout_b200 as L
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):     # an unconditional model handed a conditioning tensor
         model.apply_model(torch.zeros(1, 8, 8, 64).cuda(), torch.zeros(1, dtype=torch.long).cuda(), torch.zeros(1, 4, 512))
     with pytest.raises(ValueError):
         model.engine.unet_forward(torch.zeros(1, 8, 8, 64), torch.zeros(1, dtype=torch.long))     # CPU tensor
