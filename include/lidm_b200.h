@@ -133,6 +133,16 @@ int lidm_backproject(const float* img, int32_t B, int32_t H, int32_t W, float fo
                      float depth_min, float depth_max, float depth_scale, int32_t log_scale, int32_t input_is_unit,
                      float* xyz_out, uint8_t* mask_out, void* stream);
 
+/* custom_to_pil (scripts/sample.py:38-45), stateless: out[i] = uint8(255 * (clip(x[i], -1, 1) + 1) / 2), the exact fp32
+ * op order and truncation of the reference.  x: n fp32 values (16-byte aligned), out: n bytes. */
+int lidm_to_uint8_image(const float* x, uint8_t* out, int64_t n, void* stream);
+
+/* The `pcd[mask, :]` gather of range2pcd / custom_to_pcd (lidar_utils.py:169-171, scripts/sample.py:29-35) for a whole
+ * batch: xyz (B,3,HW) fp32 and mask (B,HW) uint8 as lidm_backproject wrote them -> points (B,HW,3) fp32 where block b
+ * starts with its counts[b] valid points in row-major pixel order (numpy boolean-index order); counts: int32 (B). */
+int lidm_compact_points(const float* xyz, const uint8_t* mask, int32_t B, int32_t HW, float* points, int32_t* counts,
+                        void* stream);
+
 /* ---- operator-level entry points (the same kernels the model uses; exposed for parity tests and reuse) ---------
  * All tensors fp32 NCHW device pointers; conversions to the internal channels-last bf16 layout happen inside. */
 

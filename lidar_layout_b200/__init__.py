@@ -5,6 +5,7 @@ A drop-in for one hot path of AlanLiangC/LiDAR-Layout behind its own Python API:
     lidm.models.diffusion.ddpm.LatentDiffusion         -> lidar_layout_b200.LatentDiffusion
     lidm.models.diffusion.ddim.DDIMSampler             -> lidar_layout_b200.DDIMSampler
     lidm.utils.lidar_utils.range2pcd / range2xyz       -> lidar_layout_b200.range2pcd / range2xyz
+    scripts/sample.py custom_to_pil / custom_to_pcd / save_logs -> lidar_layout_b200.postprocess.*
 All GPU work goes through the C ABI in include/lidm_b200.h (liblidm_b200.so, hand-written sm_100a kernels).
 Importing the package never touches the GPU; using it without the built library or without a B200 raises.
 """
@@ -26,7 +27,7 @@ def __getattr__(name):
     if name in ("Engine",):
         from .engine import Engine
         return Engine
-    if name in ("ops", "engine", "ddim", "ddpm", "lidar_utils"):
+    if name in ("ops", "engine", "ddim", "ddpm", "lidar_utils", "postprocess", "parallel"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

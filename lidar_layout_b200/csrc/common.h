@@ -143,6 +143,13 @@ void launch_f32_rows_to_bf16(const float* x, int64_t rows, int64_t rows_pad, int
 void launch_cfg_ddim_step(const float* x, const float* eps2, float scale, const float* noise, const float* coef_dev,
                           float* x_prev, float* pred_x0, float* eps_out, int64_t n, cudaStream_t s);
 
+// ---- sample post-processing (postprocess.cu) ----------------------------------------------------------------
+void launch_to_uint8_image(const float* x, uint8_t* y, int64_t n, cudaStream_t s);
+// xyz (B,3,HW) + mask (B,HW) -> points (B, HW, 3) with the valid points of sample b packed, in pixel order, at the
+// front of block b; counts (B) = number of valid points per sample
+void launch_compact_points(const float* xyz, const uint8_t* mask, int B, int HW, float* points, int32_t* counts,
+                           cudaStream_t s);
+
 // ---- elementwise (elementwise.cu) ------------------------------------------------------------------------
 void launch_ddim_step(const float* x, const float* eps, const float* noise, const float* coef_dev, float* x_prev,
                       float* pred_x0, int64_t n, cudaStream_t s);

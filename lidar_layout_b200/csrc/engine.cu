@@ -1980,6 +1980,21 @@ int lidm_backproject(const float* img, int32_t B, int32_t H, int32_t W, float fo
   });
 }
 
+int lidm_to_uint8_image(const float* x, uint8_t* out, int64_t n, void* stream) {
+  return guarded(nullptr, [&] {
+    LIDM_REQUIRE(x != nullptr && out != nullptr, "null tensor");
+    launch_to_uint8_image(x, out, n, reinterpret_cast<cudaStream_t>(stream));
+  });
+}
+
+int lidm_compact_points(const float* xyz, const uint8_t* mask, int32_t B, int32_t HW, float* points, int32_t* counts,
+                        void* stream) {
+  return guarded(nullptr, [&] {
+    LIDM_REQUIRE(xyz != nullptr && mask != nullptr && points != nullptr && counts != nullptr, "null tensor");
+    launch_compact_points(xyz, mask, B, HW, points, counts, reinterpret_cast<cudaStream_t>(stream));
+  });
+}
+
 int lidm_op_circular_conv2d(const float* x, int32_t B, int32_t Cin, int32_t H, int32_t W, const float* weight,
                             const float* bias, int32_t Cout, int32_t kh, int32_t kw, int32_t pad_l, int32_t pad_r,
                             int32_t pad_t, int32_t pad_b, int32_t stride, const float* residual, float* out,

@@ -89,3 +89,30 @@ def backproject(img, fov, depth_range, depth_scale, log_scale=True, return_mask=
                                         int(bool(input_is_unit)), xyz.data_ptr(), mask.data_ptr() if mask is not None else None,
                                         _stream_ptr(img.device)))
     return (xyz, mask) if return_mask else xyz
+
+
+def to_uint8_image(x):
+    """custom_to_pil's array (reference scripts/sample.py:38-45): uint8(255 * (clip(x,-1,1)+1)/2), same shape as x."""
+    x = _f32c(x, "x")
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.lidm_to_uint8_image(x.data_ptr(), out.data_ptr(), x.numel(), _stream_ptr(x.device)))
+    return out
+
+
+def compact_points(xyz, mask):
+    """`pcd[mask, :]` for a batch (reference lidm/utils/lidar_utils.py:169-171): xyz (B,3,H,W) fp32, mask (B,H,W) uint8 ->
+    (points (B, H*W, 3) fp32 with each sample's valid points packed first in pixel order, counts (B,) int32)."""
+    xyz = _f32c(xyz, "xyz")
+    if mask.dtype != torch.uint8 or not mask.is_cuda:
+        raise ValueError("mask must be a CUDA uint8 tensor")
+    mask = mask.contiguous()
+    B, _, H, W = xyz.shape
+    points = torch.empty((B, H * W, 3), dtype=torch.float32, device=xyz.device)
+    counts = torch.empty((B,), dtype=torch.int32, device=xyz.device)
+    lib = _lib.load()
+    with torch.cuda.device(xyz.device):
+        _lib.check(lib.lidm_compact_points(xyz.data_ptr(), mask.data_ptr(), B, H * W, points.data_ptr(), counts.data_ptr(),
+                                           _stream_ptr(xyz.device)))
+    return points, counts
