@@ -96,6 +96,17 @@ class ClockSampler:
         return out
 
 
+def captured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed
+    `ncu --set full` capture (profiles/roofline_traffic.json); None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["traffic_bytes_per_launch_mean"])
+    except Exception:
+        return None
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -285,7 +296,8 @@ def run_gpu_arm(args):
             "bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM conv, all U-Net launches of one DDIM-50 loop)",
             "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
             "frac": ach / peaks["bf16_tflops_sustained"], "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
-            "traffic": None,
+            "traffic": captured_traffic(),
+            "traffic_unit": "bytes per launch (mean of the 12 launches in profiles/roofline_traffic.json)",
             "launches": g["launches"], "avg_launch_ms": g["ms"] / max(g["launches"], 1),
             "share_of_step": {k: v["ms"] / max(sum(x["ms"] for x in prof_unet.values()), 1e-9) for k, v in prof_unet.items()},
             "groupnorm_GBps": (prof_unet["groupnorm"]["bytes"] / (prof_unet["groupnorm"]["ms"] * 1e-3) / 1e9
