@@ -215,10 +215,90 @@ def ae_param_spec(cfg: AEConfig, prefix: str = AE_PREFIX) -> "OrderedDict[str, T
     return spec
 
 
+DOWNSAMPLE_STRIDE2KERNEL = {(1, 2): (3, 3), (1, 4): (3, 5), (2, 1): (3, 3), (2, 2): (3, 3)}
+DOWNSAMPLE_STRIDE2PAD = {(1, 2): (0, 1, 1, 1), (1, 4): (1, 1, 1, 1), (2, 1): (1, 1, 1, 1), (2, 2): (0, 1, 0, 1)}
+
+
+def encoder_levels(cfg: AEConfig):
+    """Encoder topology (reference model_lidm.py:222-282): list over i_level of dicts
+    {blocks:[(cin,cout)], stride:None|(sh,sw), ch}; ResnetBlocks use the default 3x3 kernel."""
+    if cfg.attn_levels:
+        raise NotImplementedError("encoder level attention is not used by the named configs")
+    in_ch_mult = (1,) + tuple(cfg.ch_mult)
+    nres = len(cfg.ch_mult)
+    levels = []
+    block_in = cfg.ch
+    for i_level in range(nres):
+        block_in = cfg.ch * in_ch_mult[i_level]
+        block_out = cfg.ch * cfg.ch_mult[i_level]
+        blocks = []
+        for _ in range(cfg.num_res_blocks):
+            blocks.append((block_in, block_out))
+            block_in = block_out
+        stride = tuple(cfg.strides[i_level]) if i_level != nres - 1 else None
+        levels.append(dict(blocks=blocks, stride=stride, ch=block_in))
+    return levels, block_in
+
+
+def ae_encoder_param_spec(cfg: AEConfig, prefix: str = AE_PREFIX) -> "OrderedDict[str, Tuple[tuple, str]]":
+    """Encode-side tensors of VQModelInterface (Encoder + quant_conv; model_lidm.py:222-312, autoencoder.py:42-49)."""
+    spec: OrderedDict = OrderedDict()
+    e = prefix + "encoder."
+    levels, top = encoder_levels(cfg)
+    _conv(spec, e + "conv_in", cfg.ch, cfg.in_channels, 3, 3)
+    for i_level, lv in enumerate(levels):
+        for i_block, (cin, cout) in enumerate(lv["blocks"]):
+            _resnet_spec(spec, e + f"down.{i_level}.block.{i_block}", cin, cout, (3, 3))
+        if lv["stride"] is not None:
+            k = DOWNSAMPLE_STRIDE2KERNEL[lv["stride"]]
+            _conv(spec, e + f"down.{i_level}.downsample.conv", lv["ch"], lv["ch"], k[0], k[1])
+    _resnet_spec(spec, e + "mid.block_1", top, top, (3, 3))
+    _norm(spec, e + "mid.attn_1.norm", top)
+    for n in ("q", "k", "v", "proj_out"):
+        _conv(spec, e + f"mid.attn_1.{n}", top, top, 1, 1)
+    _resnet_spec(spec, e + "mid.block_2", top, top, (3, 3))
+    _norm(spec, e + "norm_out", top)
+    _conv(spec, e + "conv_out", cfg.z_channels, top, 3, 3)
+    _conv(spec, prefix + "quant_conv", cfg.embed_dim, cfg.z_channels, 1, 1)
+    return spec
+
+
 def param_spec(cfg: LidmConfig):
     spec = unet_param_spec(cfg.unet)
     spec.update(ae_param_spec(cfg.ae))
     return spec
+
+
+def _draw(rng, shape, kind, zero_init_scale, codebook_std):
+    n = int(np.prod(shape))
+    if kind in ("conv", "conv_zero"):
+        fan_in = int(np.prod(shape[1:]))
+        b = 1.0 / np.sqrt(fan_in)
+        a = (rng.random(n, dtype=np.float32) * 2.0 - 1.0) * np.float32(b)
+        if kind == "conv_zero":
+            a = a * np.float32(zero_init_scale)
+    elif kind == "bias":
+        a = (rng.random(n, dtype=np.float32) * 2.0 - 1.0) * np.float32(0.05)
+    elif kind == "gamma":
+        a = 1.0 + 0.1 * rng.standard_normal(n, dtype=np.float32)
+    elif kind == "beta":
+        a = 0.1 * rng.standard_normal(n, dtype=np.float32)
+    elif kind == "codebook":
+        a = np.float32(codebook_std) * rng.standard_normal(n, dtype=np.float32)
+    else:  # pragma: no cover
+        raise ValueError(kind)
+    return np.ascontiguousarray(a.astype(np.float32).reshape(shape))
+
+
+def random_encoder_state_dict(cfg: LidmConfig, seed: int = 0, as_torch: bool = True):
+    """Synthetic encode-side tensors (Encoder + quant_conv), drawn from their own generator so that the sampling-side
+    state-dict of `random_state_dict` (and the digest of the committed fixtures) does not depend on them."""
+    rng = np.random.Generator(np.random.PCG64(seed + 7919))
+    out = OrderedDict((name, _draw(rng, shape, kind, 1.0, 1.0)) for name, (shape, kind) in ae_encoder_param_spec(cfg.ae).items())
+    if as_torch:
+        import torch
+        return OrderedDict((k, torch.from_numpy(v)) for k, v in out.items())
+    return out
 
 
 def random_state_dict(cfg: LidmConfig, seed: int = 0, zero_init_scale: float = 1.0,

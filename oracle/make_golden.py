@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from lidar_layout_b200 import config as cfgmod            # noqa: E402
-from lidar_layout_b200.weights import param_spec, random_state_dict  # noqa: E402
+from lidar_layout_b200.weights import param_spec, random_encoder_state_dict, random_state_dict  # noqa: E402
 from oracle import ref_shim                               # noqa: E402
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
@@ -285,6 +285,52 @@ def make(name, cfg, yaml_dict, B, S_short):
     print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB; keys={sorted(out)}")
 
 
+def ae_images_for(cfg, B, seed=INPUT_SEED + 3):
+    """Synthetic range images in the dataset's value range: log-depth-like values in [-1, 1], 20 % empty pixels (-1)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    H, W = cfg.dataset.size
+    x = np.clip(rng.standard_normal((B, cfg.ae.in_channels, H, W), dtype=np.float32) * 0.5, -1.0, 1.0)
+    x[rng.random((B, cfg.ae.in_channels, H, W)) < 0.2] = -1.0
+    return x.astype(np.float32)
+
+
+@torch.no_grad()
+def make_ae(name, cfg, yaml_dict, B):
+    """First-stage autoencoder: VQModelInterface.encode and the encode -> decode round trip
+    through the reference's own LatentDiffusion.encode_first_stage / decode_first_stage."""
+    model = build_reference(cfg, yaml_dict)
+    sd = load_synthetic(model, cfg)
+    esd = random_encoder_state_dict(cfg, WEIGHT_SEED)
+    ref_sd = model.state_dict()
+    for k, v in esd.items():
+        assert k in ref_sd and tuple(ref_sd[k].shape) == tuple(v.shape), k
+    for k in ref_sd:
+        if k.startswith("first_stage_model.encoder.") or k.startswith("first_stage_model.quant_conv."):
+            assert k in esd, f"reference key {k} missing from the encoder spec"
+    model.load_state_dict(esd, strict=False)
+    x = torch.from_numpy(ae_images_for(cfg, B))
+    out = {"B": np.int64(B), "weight_seed": np.int64(WEIGHT_SEED),
+           "weights_digest": np.frombuffer(sd_digest({**sd, **esd}).encode(), dtype=np.uint8)}
+    z = model.encode_first_stage(x)
+    out["encode"] = z.numpy()
+    out["encoding_scaled"] = model.get_first_stage_encoding(z).numpy()
+    out["recon_q"] = model.decode_first_stage(z).numpy()
+    out["recon_nq"] = model.decode_first_stage(z, force_not_quantize=True).numpy()
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB; keys={sorted(out)}")
+
+
+def main_ae():
+    torch.set_num_threads(os.cpu_count())
+    import yaml
+    tiny = cfgmod.tiny()
+    make_ae("tiny_ae", tiny, tiny_yaml(tiny), B=2)
+    with open(os.path.join(ref_shim.REFERENCE_ROOT, "models/lidm/kitti/uncond/config.yaml")) as f:
+        y = yaml.safe_load(f)
+    make_ae("kitti_ae", cfgmod.from_reference_dict(y), y, B=1)
+
+
 def main_cond():
     """Conditioned fixtures."""
     torch.set_num_threads(os.cpu_count())
@@ -301,6 +347,8 @@ def main_cond():
 def main():
     if "--cond" in sys.argv:
         return main_cond()
+    if "--ae" in sys.argv:
+        return main_ae()
     torch.set_num_threads(os.cpu_count())
     torch.manual_seed(0)
     import yaml

@@ -22,8 +22,8 @@ import torch
 import torch.nn.functional as F
 
 from lidar_layout_b200.config import AEConfig, LidmConfig, UNetConfig
-from lidar_layout_b200.weights import (AE_PREFIX, UNET_PREFIX, UPSAMPLE_STRIDE2KERNEL, decoder_levels,
-                                       unet_blocks)
+from lidar_layout_b200.weights import (AE_PREFIX, DOWNSAMPLE_STRIDE2PAD, UNET_PREFIX, UPSAMPLE_STRIDE2KERNEL,
+                                       decoder_levels, encoder_levels, unet_blocks)
 
 # --------------------------------------------------------------------------------------
 # schedules
@@ -330,6 +330,38 @@ def decoder_forward(sd, cfg: AEConfig, z, prefix: str = AE_PREFIX + "decoder."):
             h = circular_conv2d(h, sd[p + ".weight"], sd[p + ".bias"], UPSAMPLE_STRIDE2PAD[stride])
     h = silu(group_norm(h, sd[prefix + "norm_out.weight"], sd[prefix + "norm_out.bias"], 1e-6))
     return circular_conv2d(h, sd[prefix + "conv_out.weight"], sd[prefix + "conv_out.bias"], (1, 2, 0, 0))
+
+
+@torch.no_grad()
+def encoder_forward(sd, cfg: AEConfig, x, prefix: str = AE_PREFIX + "encoder."):
+    """Encoder.forward, model_lidm.py:284-312 (ResnetBlocks with the default 3x3 kernel; Downsample = strided
+    CircularConv2d with the asymmetric pads of DOWNSAMPLE_STRIDE2PAD_DICT, :64-65)."""
+    levels, _ = encoder_levels(cfg)
+    h = circular_conv2d(x, sd[prefix + "conv_in.weight"], sd[prefix + "conv_in.bias"], (1, 1, 1, 1))
+    for i_level, lv in enumerate(levels):
+        for i_block in range(cfg.num_res_blocks):
+            h = _resnet_block(sd, prefix + f"down.{i_level}.block.{i_block}", h, (3, 3))
+        if lv["stride"] is not None:
+            p = prefix + f"down.{i_level}.downsample.conv"
+            h = circular_conv2d(h, sd[p + ".weight"], sd[p + ".bias"], DOWNSAMPLE_STRIDE2PAD[lv["stride"]], stride=lv["stride"])
+    h = _resnet_block(sd, prefix + "mid.block_1", h, (3, 3))
+    h = _attn_block(sd, prefix + "mid.attn_1", h)
+    h = _resnet_block(sd, prefix + "mid.block_2", h, (3, 3))
+    h = silu(group_norm(h, sd[prefix + "norm_out.weight"], sd[prefix + "norm_out.bias"], 1e-6))
+    return circular_conv2d(h, sd[prefix + "conv_out.weight"], sd[prefix + "conv_out.bias"], (1, 1, 1, 1))
+
+
+@torch.no_grad()
+def encode_first_stage(sd, cfg: LidmConfig, x):
+    """LatentDiffusion.encode_first_stage (ddpm.py:837-...) -> VQModelInterface.encode (autoencoder.py:285-288):
+    quant_conv(encoder(x)), NOT quantised (the quantiser sits in decode); scale via get_first_stage_encoding."""
+    h = encoder_forward(sd, cfg.ae, x)
+    return F.conv2d(h, sd[AE_PREFIX + "quant_conv.weight"], sd[AE_PREFIX + "quant_conv.bias"])
+
+
+def get_first_stage_encoding(cfg: LidmConfig, z):
+    """ddpm.py:546-556 for a tensor posterior: scale_factor * z."""
+    return cfg.scale_factor * z
 
 
 @torch.no_grad()
