@@ -59,6 +59,7 @@ typedef struct lidm_config {
    *   context. */
   int32_t latent_channels;
   int32_t use_spatial_transformer, context_dim, transformer_depth;
+  int32_t ae_in_channels;                  /* first-stage ddconfig.in_channels (encoder input), 0 => 1 */
 } lidm_config;
 
 /* Last error message for `h` (or, with h == NULL, for the calling thread's last failed lidm_create / stateless call). */
@@ -121,6 +122,12 @@ int lidm_cfg_combine(const float* eps2, float guidance_scale, float* eps_out, in
  * fp32; idx_out: NULL or int32 (B*h*w) codebook indices (-1 when force_not_quantize). */
 int lidm_vq_decode(lidm_handle* h, const float* z, int32_t force_not_quantize, float* img_out, int32_t* idx_out,
                    int32_t B, void* stream);
+
+/* LatentDiffusion.encode_first_stage -> VQModelInterface.encode (ddpm.py:837, autoencoder.py:285-288): Encoder
+ * (model_lidm.py:284-312) + quant_conv, NOT quantised (the quantiser sits in decode) and not yet multiplied by
+ * scale_factor (get_first_stage_encoding, ddpm.py:546-556).  img: (B, in_channels, H, W) fp32; z_out: (B, embed_dim, h, w).
+ * Needs first_stage_model.encoder.* / quant_conv.* in the loaded state-dict (LIDM_ERR_STATE otherwise). */
+int lidm_vq_encode(lidm_handle* h, const float* img, float* z_out, int32_t B, void* stream);
 
 /* Output geometry of lidm_vq_decode for this config: channels, height, width of img_out. */
 int lidm_image_shape(const lidm_handle* h, int32_t* c, int32_t* hh, int32_t* ww);

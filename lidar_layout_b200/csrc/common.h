@@ -158,8 +158,9 @@ void launch_backproject(const float* img, int B, int H, int W, float fov_up_deg,
                         cudaStream_t s);
 void launch_im2col_nchw_f32(const float* x, int B, int C, int H, int W, int kh, int kw, int pl, int pt, bf16* out,
                             int kpad, cudaStream_t s);
+// stride = vertical stride; stride_w = horizontal stride (0 => same as stride)
 void launch_im2col_nhwc(const View& x, int kh, int kw, int stride, int pl, int pt, int Ho, int Wo, bf16* out,
-                        cudaStream_t s);
+                        cudaStream_t s, int stride_w = 0);
 void launch_upsample_nearest2x(const View& x, const View& y, cudaStream_t s);
 void launch_upsample_bilinear(const View& x, const View& y, cudaStream_t s);
 void launch_copy_with_halo(const View& x, const View& y, cudaStream_t s);

@@ -144,7 +144,7 @@ __global__ void im2col_nchw_f32_kernel(const float* __restrict__ x, int B, int C
 
 // generic channels-last im2col (strided convs): out[(b,ho,wo)][tap*C + c]; 16-byte vectors
 __global__ void im2col_nhwc_kernel(const bf16* __restrict__ x, int B, int H, int W, int hl, int Wp, int ld, int C,
-                                   int kh, int kw, int stride, int pl, int pt, int Ho, int Wo, bf16* __restrict__ out) {
+                                   int kh, int kw, int sh, int sw, int pl, int pt, int Ho, int Wo, bf16* __restrict__ out) {
   const int vec = C >> 3;
   const int taps = kh * kw;
   const int64_t total = (int64_t)B * Ho * Wo * taps * vec;
@@ -158,8 +158,8 @@ __global__ void im2col_nhwc_kernel(const bf16* __restrict__ x, int B, int H, int
     const int ho = (int)(r % Ho);
     const int b = (int)(r / Ho);
     const int ky = tap / kw, kx = tap - ky * kw;
-    const int hs = ho * stride + ky - pt;
-    int ws = (wo * stride + kx - pl) % W;
+    const int hs = ho * sh + ky - pt;
+    int ws = (wo * sw + kx - pl) % W;
     if (ws < 0) ws += W;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (hs >= 0 && hs < H) v = __ldg(reinterpret_cast<const uint4*>(x + ((size_t)(b * H + hs) * Wp + (ws + hl)) * ld) + cv);
@@ -496,11 +496,11 @@ void launch_im2col_nchw_f32(const float* x, int B, int C, int H, int W, int kh, 
 }
 
 void launch_im2col_nhwc(const View& x, int kh, int kw, int stride, int pl, int pt, int Ho, int Wo, bf16* out,
-                        cudaStream_t s) {
+                        cudaStream_t s, int stride_w) {
   LIDM_REQUIRE(x.C % 8 == 0, "im2col: C % 8");
   const int64_t total = (int64_t)x.B * Ho * Wo * kh * kw * (x.C / 8);
   im2col_nhwc_kernel<<<grid_for(total, 256), 256, 0, s>>>(x.p, x.B, x.H, x.W, x.hl, x.Wp(), x.ld, x.C, kh, kw, stride,
-                                                          pl, pt, Ho, Wo, out);
+                                                          stride_w > 0 ? stride_w : stride, pl, pt, Ho, Wo, out);
   LIDM_CUDA_CHECK(cudaGetLastError());
   LIDM_COUNT_LAUNCH(1);
 }

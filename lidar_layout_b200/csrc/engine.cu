@@ -124,6 +124,7 @@ struct Layer {
   ResW r; AttnW a; ConvW c; STW st;
   int cin = 0, cout = 0;
 };
+struct EncLevel { std::vector<ResW> blocks; bool has_down = false; int sh = 1, sw = 1, pl = 0, pt = 0; ConvW down; int ch = 0; };
 struct DecLevel { std::vector<ResW> blocks; int kh = 1, kw = 4; bool has_up = false; int sh = 1, sw = 1; ConvW up; int ch = 0; };
 
 ConvTaps taps_rect(int kh, int kw, int pl, int pt) {
@@ -200,8 +201,16 @@ struct lidm_handle {
   std::vector<DecLevel> dec_levels;                   // indexed by i_level
   NormW dec_norm_out;
   int dec_top = 0, dec_last = 0, img_h = 0, img_w = 0;
+  // encoder (optional: packed when the state-dict carries first_stage_model.encoder.*)
+  bool has_encoder = false;
+  ConvW enc_conv_in, enc_conv_out;                    // conv_out has quant_conv folded in
+  std::vector<EncLevel> enc_levels;
+  ResW enc_mid1, enc_mid2;
+  AttnW enc_attn;
+  NormW enc_norm_out;
+  int enc_top = 0;
   // plans
-  std::map<int64_t, std::unique_ptr<Plan>> unet_plans, dec_plans;   // key = B | ctx_len << 24
+  std::map<int64_t, std::unique_ptr<Plan>> unet_plans, dec_plans, enc_plans;   // key = B | ctx_len << 24
   // time-embedding scratch
   float *te_tmp = nullptr, *te_emb = nullptr, *emb_out = nullptr;
   int64_t* t_dev = nullptr;
@@ -798,6 +807,22 @@ struct Builder {
     release(bc);
   }
 
+  // Downsample.forward of the first-stage encoder (model_lidm.py:68-83): CircularConv2d kernel (kh,kw), stride (sh,sw),
+  // circular pad (pl, .) on W / zero pad (pt, .) on H — channels-last im2col + GEMM
+  void down_strided(const ConvW& c, const View& x, const View& dst, int sh, int sw, int pl, int pt) {
+    const int B = x.B, Ho = dst.H, Wo = dst.W, taps = c.kh * c.kw;
+    Buf bc;
+    bf16* col = raw<bf16>((size_t)B * Ho * Wo * taps * x.C, &bc);
+    const int kh = c.kh, kw = c.kw;
+    op([=](cudaStream_t s) { launch_im2col_nhwc(x, kh, kw, sh, pl, pt, Ho, Wo, col, s, sw); });
+    View a; a.p = col; a.B = B; a.H = Ho; a.W = Wo; a.C = taps * x.C; a.ld = taps * x.C;
+    GemmEpilogue ep;
+    ep.bias = c.bias;
+    ep.out = dst;
+    gemm(a, taps_1x1(), c, ep);
+    release(bc);
+  }
+
   // Upsample.forward (openaimodel.py:108-118): nearest x2 then circular 3x3
   void up(const ConvW& c, const View& x, const View& dst) {
     Buf bu;
@@ -1035,6 +1060,64 @@ void build_dec_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
         launch_conv_gemm(g, taps, wb, N, ep, s);
       }, PROF_GEMM, gemm_flops(g, taps.n, N));
     }
+    b.release(bg);
+  }
+  *high = b.ap.high();
+}
+
+// ------------------------------------------------------------------------------------------- encoder plan
+// Encoder.forward + quant_conv (model_lidm.py:284-312, autoencoder.py:285-288); image (B,Cin,H,W) fp32 -> (B,embed,h,w)
+void build_enc_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
+  Builder b{h, P, ArenaPlanner(), dry};
+  const lidm_config& cfg = h->cfg;
+  const int B = P->B;
+  int H = h->img_h, W = h->img_w;
+  const int kpad = h->enc_conv_in.k_alloc;
+  Buf bcol, bx;
+  bf16* col = b.raw<bf16>((size_t)B * H * W * kpad, &bcol);
+  const int Cin = cfg.ae_in_channels;
+  b.op([=](cudaStream_t s) { launch_im2col_nchw_f32(P->x, B, Cin, H, W, 3, 3, 1, 1, col, kpad, s); });
+  View x = b.act(B, H, W, cfg.ae_ch, 0, 0, &bx);
+  {
+    View a; a.p = col; a.B = B; a.H = H; a.W = W; a.C = kpad; a.ld = kpad;
+    GemmEpilogue ep;
+    ep.bias = h->enc_conv_in.bias;
+    ep.out = x;
+    b.gemm(a, taps_1x1(), h->enc_conv_in, ep);
+  }
+  b.release(bcol);
+  auto step = [&](std::function<void(const View&, const View&)> f, int Ho, int Wo, int C) {
+    Buf bo;
+    View o = b.act(B, Ho, Wo, C, 0, 0, &bo);
+    f(x, o);
+    b.release(bx);
+    bx = bo; x = o;
+  };
+  for (const EncLevel& L : h->enc_levels) {
+    for (const ResW& r : L.blocks)
+      step([&](const View& i, const View& o) { b.res_block(r, i, o, 3, 3, 1, 1, 1, 1e-6f); }, H, W, r.cout);
+    if (L.has_down) {
+      const int Ho = H / L.sh, Wo = W / L.sw;
+      step([&](const View& i, const View& o) { b.down_strided(L.down, i, o, L.sh, L.sw, L.pl, L.pt); }, Ho, Wo, L.ch);
+      H = Ho; W = Wo;
+    }
+  }
+  step([&](const View& i, const View& o) { b.res_block(h->enc_mid1, i, o, 3, 3, 1, 1, 1, 1e-6f); }, H, W, h->enc_top);
+  step([&](const View& i, const View& o) { b.dec_attn_block(h->enc_attn, i, o); }, H, W, h->enc_top);
+  step([&](const View& i, const View& o) { b.res_block(h->enc_mid2, i, o, 3, 3, 1, 1, 1, 1e-6f); }, H, W, h->enc_top);
+  {
+    Buf bg;
+    View g = b.act(B, H, W, h->enc_top, 1, 1, &bg);
+    b.groupnorm(x, g, h->enc_norm_out, 1e-6f, true);
+    b.release(bx);
+    GemmB wb; wb.p = h->enc_conv_out.w; wb.n_alloc = h->enc_conv_out.n_alloc; wb.ld = h->enc_conv_out.k_alloc;
+    const float* bias = h->enc_conv_out.bias;
+    const int N = h->enc_conv_out.cout;
+    const ConvTaps taps = taps_rect(3, 3, 1, 1);
+    b.op([=](cudaStream_t s) {
+      GemmEpilogue ep; ep.bias = bias; ep.out_f32_nchw = P->out;
+      launch_conv_gemm(g, taps, wb, N, ep, s);
+    }, PROF_GEMM, gemm_flops(g, taps.n, N));
     b.release(bg);
   }
   *high = b.ap.high();
@@ -1589,6 +1672,78 @@ void finalize(lidm_handle* h, bool use_ema) {
   h->dec_norm_out = pk.norm(D + "norm_out", block_in);
   h->dec_conv_out = pk.conv(D + "conv_out", cfg.ae_out_ch, block_in, 1, 4);
   if (cfg.ae_use_mask && cfg.ae_out_ch != 2) throw Error(LIDM_ERR_INVALID, "use_mask needs out_ch == 2");
+  // ---- first stage (encode side), only when the state-dict carries it
+  h->has_encoder = h->raw.count(A + "encoder.conv_in.weight") != 0;
+  if (h->has_encoder && !pk.precise) {
+    const std::string E = A + "encoder.";
+    h->enc_conv_in = pk.conv(E + "conv_in", cfg.ae_ch, cfg.ae_in_channels, 3, 3, (9 * cfg.ae_in_channels + 63) / 64 * 64);
+    h->enc_levels.assign(nres, EncLevel());
+    int bin = cfg.ae_ch;
+    for (int lv = 0; lv < nres; ++lv) {
+      EncLevel& L = h->enc_levels[lv];
+      bin = cfg.ae_ch * (lv == 0 ? 1 : cfg.ae_ch_mult[lv - 1]);
+      const int bout = cfg.ae_ch * cfg.ae_ch_mult[lv];
+      for (int i = 0; i < cfg.ae_num_res_blocks; ++i) {
+        L.blocks.push_back(pack_res(pk, E + "down." + std::to_string(lv) + ".block." + std::to_string(i), bin, bout, 3, 3, false));
+        bin = bout;
+      }
+      L.ch = bin;
+      if (lv != nres - 1) {
+        L.has_down = true;
+        L.sh = cfg.ae_strides[lv][0]; L.sw = cfg.ae_strides[lv][1];
+        // DOWNSAMPLE_STRIDE2{KERNEL,PAD}_DICT (model_lidm.py:64-65): (1,2) -> 3x3, pad (0,1,1,1); (2,2) -> 3x3, pad (0,1,0,1)
+        if (L.sh == 1 && L.sw == 2) { L.pl = 0; L.pt = 1; }
+        else if (L.sh == 2 && L.sw == 2) { L.pl = 0; L.pt = 0; }
+        else throw Error(LIDM_ERR_INVALID, "unsupported encoder stride");
+        L.down = pk.conv(E + "down." + std::to_string(lv) + ".downsample.conv", bin, bin, 3, 3);
+      }
+    }
+    h->enc_top = bin;
+    h->enc_mid1 = pack_res(pk, E + "mid.block_1", bin, bin, 3, 3, false);
+    h->enc_attn = pack_dec_attn(pk, E + "mid.attn_1", bin);
+    h->enc_mid2 = pack_res(pk, E + "mid.block_2", bin, bin, 3, 3, false);
+    h->enc_norm_out = pk.norm(E + "norm_out", bin);
+    // quant_conv (1x1, z_channels -> embed_dim) folded into conv_out: W' = Wq Wo, b' = Wq bo + bq (fp32 on the host)
+    {
+      const DevTensor& wo = find_raw(h, E + "conv_out.weight", use_ema);
+      const DevTensor& bo = find_raw(h, E + "conv_out.bias", use_ema);
+      const DevTensor& wq = find_raw(h, A + "quant_conv.weight", use_ema);
+      const DevTensor& bq = find_raw(h, A + "quant_conv.bias", use_ema);
+      const int zc = cfg.z_channels, ed = cfg.embed_dim;
+      const int64_t kk = (int64_t)bin * 9;
+      if (wo.numel != zc * kk || bo.numel != zc || wq.numel != (int64_t)ed * zc || bq.numel != ed)
+        throw Error(LIDM_ERR_STATE, "encoder conv_out / quant_conv weight size");
+      std::vector<float> Wo(wo.numel), Bo(zc), Wq(wq.numel), Bq(ed), Wf((size_t)ed * kk), Bf(ed);
+      LIDM_CUDA_CHECK(cudaMemcpy(Wo.data(), wo.p, Wo.size() * 4, cudaMemcpyDeviceToHost));
+      LIDM_CUDA_CHECK(cudaMemcpy(Bo.data(), bo.p, Bo.size() * 4, cudaMemcpyDeviceToHost));
+      LIDM_CUDA_CHECK(cudaMemcpy(Wq.data(), wq.p, Wq.size() * 4, cudaMemcpyDeviceToHost));
+      LIDM_CUDA_CHECK(cudaMemcpy(Bq.data(), bq.p, Bq.size() * 4, cudaMemcpyDeviceToHost));
+      for (int o = 0; o < ed; ++o) {
+        double bacc = Bq[o];
+        for (int m = 0; m < zc; ++m) bacc += (double)Wq[o * zc + m] * Bo[m];
+        Bf[o] = (float)bacc;
+        for (int64_t k = 0; k < kk; ++k) {
+          double acc = 0;
+          for (int m = 0; m < zc; ++m) acc += (double)Wq[o * zc + m] * Wo[m * kk + k];
+          Wf[o * kk + k] = (float)acc;
+        }
+      }
+      int64_t wshape[4] = {ed, bin, 3, 3}, bshape[1] = {ed};
+      auto put = [&](const std::string& name, const std::vector<float>& v, int nd, const int64_t* shp) {
+        DevTensor t; t.numel = (int64_t)v.size();
+        for (int i = 0; i < nd; ++i) t.shape.push_back(shp[i]);
+        LIDM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&t.p), v.size() * 4));
+        LIDM_CUDA_CHECK(cudaMemcpy(t.p, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+        auto it = h->raw.find(name);
+        if (it != h->raw.end()) { cudaFree(it->second.p); h->raw.erase(it); }
+        h->raw.emplace(name, std::move(t));
+      };
+      put(E + "conv_out_q.weight", Wf, 4, wshape);
+      put(E + "conv_out_q.bias", Bf, 1, bshape);
+      Packer pk2{h, false};
+      h->enc_conv_out = pk2.conv(E + "conv_out_q", ed, bin, 3, 3);
+    }
+  }
   LIDM_CUDA_CHECK(cudaDeviceSynchronize());
   // raw fp32 copies are no longer needed
   for (auto& kv : h->raw) cudaFree(kv.second.p);
@@ -1767,6 +1922,8 @@ int lidm_create(const lidm_config* cfg, lidm_handle** out) {
                  "coarsest U-Net level must tile into 128-pixel patches");
     lidm_handle* h = new lidm_handle();
     h->cfg = *cfg;
+    if (h->cfg.ae_in_channels <= 0) h->cfg.ae_in_channels = 1;
+    if (h->cfg.transformer_depth <= 0) h->cfg.transformer_depth = 1;
     *out = h;
   });
 }
@@ -1794,6 +1951,20 @@ int lidm_finalize_weights(lidm_handle* h, int32_t use_ema) {
     LIDM_REQUIRE(h != nullptr, "null handle");
     if (h->finalized) throw Error(LIDM_ERR_STATE, "weights already finalized");
     finalize(h, use_ema != 0);
+  });
+}
+
+int lidm_vq_encode(lidm_handle* h, const float* img, float* z_out, int32_t B, void* stream) {
+  return guarded(h, [&] {
+    require_ready(h, B);
+    LIDM_REQUIRE(img != nullptr && z_out != nullptr, "null tensor");
+    if (h->cfg.precision) throw Error(LIDM_ERR_INVALID, "the precise mode does not cover the first-stage encoder");
+    if (!h->has_encoder)
+      throw Error(LIDM_ERR_STATE, "no encoder weights were loaded (first_stage_model.encoder.* / quant_conv.* missing from the state-dict)");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    Plan* P = get_plan(h, h->enc_plans, B, build_enc_plan_pass);
+    P->x = img; P->out = z_out;
+    run_plan(P, s);
   });
 }
 

@@ -38,6 +38,9 @@ class _FirstStage:
     def decode(self, h, force_not_quantize=False):
         return self._owner.engine.vq_decode(h, force_not_quantize)
 
+    def encode(self, x):
+        return self._owner.engine.vq_encode(x)
+
 
 class LatentDiffusion:
     """Drop-in for the sampling-side API of lidm.models.diffusion.ddpm.LatentDiffusion."""
@@ -149,6 +152,15 @@ class LatentDiffusion:
         if predict_cids:
             raise NotImplementedError("predict_cids is not used by the sampling path")
         return self.engine.vq_decode(z, force_not_quantize=force_not_quantize)
+
+    @torch.no_grad()
+    def encode_first_stage(self, x):
+        """ddpm.py:837-... -> VQModelInterface.encode (autoencoder.py:285-288): quant_conv(encoder(x)), not quantised."""
+        return self.engine.vq_encode(x)
+
+    def get_first_stage_encoding(self, encoder_posterior):
+        """ddpm.py:546-556 for a tensor posterior."""
+        return self.scale_factor * encoder_posterior
 
     def q_sample(self, x_start, t, noise=None):
         """DDPM.q_sample (ddpm.py:306-309)."""

@@ -65,6 +65,7 @@ def to_cconfig(cfg: LidmConfig) -> _lib.CConfig:
     c.use_spatial_transformer = int(bool(u.use_spatial_transformer))
     c.context_dim = int(u.context_dim or 0)
     c.transformer_depth = int(u.transformer_depth)
+    c.ae_in_channels = int(a.in_channels)
     return c
 
 
@@ -97,7 +98,7 @@ class Engine:
                 if not (name.startswith("model.diffusion_model.") or name.startswith("model_ema.")
                         or name.startswith("first_stage_model.")):
                     continue
-                if name.startswith("first_stage_model.encoder.") or name.startswith("first_stage_model.loss."):
+                if name.startswith("first_stage_model.loss."):
                     continue
                 if isinstance(t, np.ndarray):
                     t = torch.from_numpy(t)
@@ -182,6 +183,19 @@ class Engine:
                 ptr(pred), B, ptr(c_concat), ptr(context), L, ptr(uncond_concat), ptr(uncond_context),
                 float(guidance_scale), _stream_ptr(self.device)), self._h)
         return x, pred
+
+    def vq_encode(self, img: torch.Tensor) -> torch.Tensor:
+        """VQModelInterface.encode: quant_conv(encoder(img)), (B, in_channels, H, W) -> (B, embed_dim, h, w)."""
+        img = _f32c(img, "img")
+        c, H, W = self.image_shape()
+        if img.dim() != 4 or tuple(img.shape[1:]) != (self.cfg.ae.in_channels, H, W):
+            raise ValueError(f"img must be (B, {self.cfg.ae.in_channels}, {H}, {W}), got {tuple(img.shape)}")
+        z = torch.empty((img.shape[0], self.cfg.ae.embed_dim) + tuple(self.cfg.image_size), dtype=torch.float32,
+                        device=img.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.lidm_vq_encode(self._h, img.data_ptr(), z.data_ptr(), img.shape[0],
+                                                _stream_ptr(self.device)), self._h)
+        return z
 
     def image_shape(self):
         c, h, w = c_int32(), c_int32(), c_int32()

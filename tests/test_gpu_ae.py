@@ -1,0 +1,69 @@
+"""GPU (-m gpu): first-stage encoder through the C ABI against fixtures of the UNMODIFIED
+reference (tests/golden/{tiny_ae,kitti_ae}.npz): VQModelInterface.encode and the encode -> decode round trip.
+bf16 tensor-core path: the encoder is a stack of ~25 convs + 20 GroupNorms, same error budget as the decoder."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from lidar_layout_b200 import config as C
+from lidar_layout_b200.weights import random_encoder_state_dict, random_state_dict
+from oracle import torch_ref as R
+from oracle.make_golden import ae_images_for
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel(a, b):
+    return R.rel_l2(a.detach().cpu(), b)
+
+
+@pytest.fixture(scope="module", params=["tiny_ae", "kitti_ae"])
+def setup(request, built_lib):
+    import lidar_layout_b200 as L
+    name = request.param
+    cfg = C.tiny() if name == "tiny_ae" else C.kitti_uncond()
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    model = L.LatentDiffusion(cfg, use_ema=False)
+    model.load_state_dict({**random_state_dict(cfg, 0), **random_encoder_state_dict(cfg, 0)})
+    return name, cfg, g, model
+
+
+def test_encode_first_stage(setup):
+    name, cfg, g, model = setup
+    x = torch.from_numpy(ae_images_for(cfg, int(g["B"]))).cuda()
+    z = model.encode_first_stage(x)
+    assert z.shape == g["encode"].shape
+    e = rel(z, g["encode"])
+    print(f"[{name}] encode rel {e:.3e}")
+    assert e < 3e-2
+    assert torch.equal(model.get_first_stage_encoding(z), cfg.scale_factor * z)
+    # deterministic and batch-invariant
+    z1 = model.encode_first_stage(x[:1])
+    assert torch.equal(z1[0], z[0])
+
+
+def test_round_trip(setup):
+    name, cfg, g, model = setup
+    x = torch.from_numpy(ae_images_for(cfg, int(g["B"]))).cuda()
+    z = model.encode_first_stage(x)
+    rec = model.decode_first_stage(z, force_not_quantize=True)
+    e = rel(rec, g["recon_nq"])
+    print(f"[{name}] encode->decode (not quantised) rel {e:.3e}")
+    assert e < 8e-2      # measured 6.0e-2 on the full-size AE: the 2e-2 encode error re-amplified by the bf16 decoder (2.4e-2 alone)
+    # quantised decode of the reference's own latent: VQ indices are discrete, covered by test_gpu_model
+    rec_q = model.decode_first_stage(torch.from_numpy(g["encode"]).cuda())
+    assert rel(rec_q, g["recon_q"]) < 4e-2
+
+
+def test_encoder_needs_its_weights(built_lib):
+    import lidar_layout_b200 as L
+    from lidar_layout_b200._lib import LidmError
+    cfg = C.tiny()
+    model = L.LatentDiffusion(cfg, use_ema=False)
+    model.load_state_dict(random_state_dict(cfg, 0))       # sampling-side tensors only
+    with pytest.raises(LidmError):
+        model.encode_first_stage(torch.zeros(1, 1, *cfg.dataset.size).cuda())
