@@ -51,8 +51,12 @@ struct View {
   // [0, C) of the view, lo occupies [lo_off, lo_off + C) (lo_off == 0 => ordinary single-plane tensor)
   int lo_off = 0;
   int cphys = 0;   // physical channel extent when it is not derivable (im2col'd hi/lo operands); 0 => derived
+  // row pitch in pixels of `ld` elements when it differs from W + hl + hr (GEMM outputs only): lets a GEMM write every
+  // second pixel of every second row of a 2x larger tensor (ld = 2 * ld_big, wpitch = 2 * W_big / 2 ... see Builder::up)
+  int wpitch = 0;
   int Cphys() const { return cphys ? cphys : (lo_off ? lo_off + C : C); }
   int Wp() const { return W + hl + hr; }
+  int pitch() const { return wpitch ? wpitch : Wp(); }
   size_t pix_index(int b, int h, int w) const { return ((size_t)(b * H + h) * Wp() + (w + hl)); }
 };
 

@@ -122,6 +122,7 @@ struct STW { NormW n; ConvW proj_in, proj_out; std::vector<STBlockW> blocks; int
 struct Layer {
   enum Kind { CONV, RES, ATTN, DOWN, UP, ST } kind;
   ResW r; AttnW a; ConvW c; STW st;
+  ConvW cpar[4];   // UP: the 3x3 conv after nearest x2, folded into one 2x2 conv per output parity (py * 2 + px)
   int cin = 0, cout = 0;
 };
 struct EncLevel { std::vector<ResW> blocks; bool has_down = false; int sh = 1, sw = 1, pl = 0, pt = 0; ConvW down; int ch = 0; };
@@ -823,7 +824,34 @@ struct Builder {
     release(bc);
   }
 
-  // Upsample.forward (openaimodel.py:108-118): nearest x2 then circular 3x3
+  // Upsample.forward (openaimodel.py:108-118), nearest x2 followed by the circular 3x3 conv, without materialising
+  // the 4x tensor: output pixel (2h+py, 2w+px) only ever sees input rows {h-1+py, h+py} and columns {w-1+px, w+px}, so each
+  // of the four output parities is a 2x2 conv on the low-resolution input whose taps are sums of the 3x3 taps
+  // (cpar[py*2+px], folded in fp32 at pack time): 16 C^2 instead of 36 C^2 MACs per input pixel.  Each GEMM writes its
+  // parity straight into the 2x output through a strided view (ld and row pitch doubled).
+  void up_folded(const ConvW* cpar, const ConvW& c, const View& x, const View& dst) {
+    if (dst.hl + dst.hr != 0 || dst.wpitch != 0) throw Error(LIDM_ERR_INVALID, "internal: upsample output must be halo-free");
+    Buf bx;
+    View xh = act(x.B, x.H, x.W, x.C, 1, 1, &bx);
+    op([=](cudaStream_t s) { launch_copy_with_halo(x, xh, s); });
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        ConvTaps t;
+        t.n = 4;
+        for (int a = 0; a < 2; ++a)
+          for (int bb = 0; bb < 2; ++bb) { t.dy[a * 2 + bb] = (int8_t)(a - 1 + py); t.dx[a * 2 + bb] = (int8_t)(bb - 1 + px); }
+        View o = dst;
+        o.H = x.H; o.W = x.W;
+        o.p = dst.p + (size_t)(py * dst.W + px) * dst.ld;
+        o.ld = 2 * dst.ld;
+        o.wpitch = dst.W;                 // one output row pair = 2 * dst.W pixels of dst.ld = dst.W pixels of 2 * dst.ld
+        GemmEpilogue ep;
+        ep.bias = c.bias;
+        ep.out = o;
+        gemm(xh, t, cpar[py * 2 + px], ep);
+      }
+    release(bx);
+  }
   void up(const ConvW& c, const View& x, const View& dst) {
     Buf bu;
     View u = act(x.B, x.H * 2, x.W * 2, x.C, 1, 1, &bu);
@@ -904,7 +932,10 @@ void build_unet_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
         case Layer::ATTN: b.attn_block(L.a, x, o); break;
         case Layer::ST: b.st_block(L.st, x, o, ctx_kv, h->ctx_n, ctx_len); break;
         case Layer::DOWN: b.down(L.c, x, o); break;
-        case Layer::UP: b.up(L.c, x, o); break;
+        case Layer::UP:
+          if (L.cpar[0].w != nullptr) b.up_folded(L.cpar, L.c, x, o);
+          else b.up(L.c, x, o);
+          break;
         case Layer::CONV: throw Error(LIDM_ERR_INVALID, "unexpected conv layer");
       }
       if (have_prev) b.release(prev_buf);
@@ -1457,6 +1488,58 @@ AttnW pack_dec_attn(Packer& pk, const std::string& p, int ch) {
   return a;
 }
 
+// The 3x3 conv that follows a nearest x2 upsample, folded into four 2x2 convs (one per output parity): tap (a, b) of
+// parity (py, px) is the sum of the 3x3 taps that land on the same low-resolution pixel.  Summed in fp32 on the host,
+// then packed like any other conv weight.
+void fold_upsample_conv(Packer& pk, const std::string& prefix, int ch, ConvW* out4) {
+  lidm_handle* h = pk.h;
+  const DevTensor& w = find_raw(h, prefix + ".weight", pk.ema);
+  if (w.numel != (int64_t)ch * ch * 9) throw Error(LIDM_ERR_STATE, "weight '" + prefix + ".weight' has unexpected size");
+  std::vector<float> W3((size_t)w.numel), W2((size_t)ch * ch * 4);
+  LIDM_CUDA_CHECK(cudaMemcpy(W3.data(), w.p, W3.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  // rows of the 3x3 kernel feeding 2x2 row a:  parity 0: a=0 -> {0}, a=1 -> {1,2};  parity 1: a=0 -> {0,1}, a=1 -> {2}
+  auto span = [](int parity, int a, int* lo, int* hi) {
+    if (parity == 0) { *lo = a == 0 ? 0 : 1; *hi = a == 0 ? 0 : 2; }
+    else { *lo = a == 0 ? 0 : 2; *hi = a == 0 ? 1 : 2; }
+  };
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      for (size_t oc = 0; oc < (size_t)ch * ch; ++oc) {
+        const float* s3 = &W3[oc * 9];
+        for (int a = 0; a < 2; ++a)
+          for (int b = 0; b < 2; ++b) {
+            int y0, y1, x0, x1;
+            span(py, a, &y0, &y1);
+            span(px, b, &x0, &x1);
+            float acc = 0.f;
+            for (int ky = y0; ky <= y1; ++ky)
+              for (int kx = x0; kx <= x1; ++kx) acc += s3[ky * 3 + kx];
+            W2[oc * 4 + a * 2 + b] = acc;
+          }
+      }
+      const std::string name = prefix + "_fold" + std::to_string(py * 2 + px);
+      DevTensor t;
+      t.numel = (int64_t)W2.size();
+      t.shape = {ch, ch, 2, 2};
+      LIDM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&t.p), W2.size() * sizeof(float)));
+      LIDM_CUDA_CHECK(cudaMemcpy(t.p, W2.data(), W2.size() * sizeof(float), cudaMemcpyHostToDevice));
+      auto it = h->raw.find(name + ".weight");
+      if (it != h->raw.end()) { cudaFree(it->second.p); h->raw.erase(it); }
+      h->raw.emplace(name + ".weight", std::move(t));
+      // bias: shared with the 3x3 conv (Packer::conv copies it per call)
+      const DevTensor& b3 = find_raw(h, prefix + ".bias", pk.ema);
+      DevTensor tb;
+      tb.numel = b3.numel; tb.shape = b3.shape;
+      LIDM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&tb.p), b3.numel * sizeof(float)));
+      LIDM_CUDA_CHECK(cudaMemcpy(tb.p, b3.p, b3.numel * sizeof(float), cudaMemcpyDeviceToDevice));
+      auto itb = h->raw.find(name + ".bias");
+      if (itb != h->raw.end()) { cudaFree(itb->second.p); h->raw.erase(itb); }
+      h->raw.emplace(name + ".bias", std::move(tb));
+      Packer pk2{h, false, pk.s};
+      out4[py * 2 + px] = pk2.conv(name, ch, ch, 2, 2);
+    }
+}
+
 bool in_list(const int32_t* v, int n, int x) {
   for (int i = 0; i < n; ++i) if (v[i] == x) return true;
   return false;
@@ -1576,7 +1659,10 @@ void finalize(lidm_handle* h, bool use_ema) {
           layers.push_back(make_attn(p + "." + std::to_string(j++), ch));
         if (level && i == cfg.num_res_blocks) {
           Layer L; L.kind = Layer::UP; L.cin = L.cout = ch;
-          L.c = pk.conv(p + "." + std::to_string(j++) + ".conv", ch, ch, 3, 3);
+          const std::string cp = p + "." + std::to_string(j++) + ".conv";
+          L.c = pk.conv(cp, ch, ch, 3, 3);
+          static const bool no_fold = getenv("LIDM_NO_UPSAMPLE_FOLD") != nullptr;
+          if (!pk.precise && !no_fold) fold_upsample_conv(pk, cp, ch, L.cpar);
           layers.push_back(L);
           ds /= 2;
         }

@@ -471,6 +471,8 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
   LIDM_REQUIRE(a.p != nullptr && wt != nullptr, "null operand");
   LIDM_REQUIRE(a.C % BK == 0, "Cin must be a multiple of 64 (use the im2col path otherwise)");
   LIDM_REQUIRE(a.ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a.p) & 15) == 0, "activation view must be 16B aligned");
+  LIDM_REQUIRE(a.wpitch == 0 && ep.residual.wpitch == 0 && (ep.out.wpitch == 0 || ep.out.hl + ep.out.hr == 0),
+               "a row pitch override is supported on halo-free outputs only");
   LIDM_REQUIRE(taps.n >= 1 && taps.n <= 9, "1..9 taps");
   const int nseg = wtb.nseg;
   LIDM_REQUIRE(nseg >= 1 && nseg <= 3 && (nseg != 3 || a.lo_off > 0), "operand-split segments");
@@ -522,7 +524,7 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
   if (ep.out.p != nullptr) {
     LIDM_REQUIRE(ep.out.H == H && ep.out.W == W && ep.out.B == a.B, "output shape mismatch");
     LIDM_REQUIRE(ep.out.ld % 8 == 0 && (reinterpret_cast<uintptr_t>(ep.out.p) & 15) == 0, "output alignment");
-    p.out = ep.out.p; p.out_ld = ep.out.ld; p.out_hl = ep.out.hl; p.out_hr = ep.out.hr; p.out_Wp = ep.out.Wp();
+    p.out = ep.out.p; p.out_ld = ep.out.ld; p.out_hl = ep.out.hl; p.out_hr = ep.out.hr; p.out_Wp = ep.out.pitch();
   }
   p.split_n = ep.split_n; p.out_t = ep.out_t;
   if (ep.out_t != nullptr) LIDM_REQUIRE(ep.split_n % BN == 0, "split_n must be tile aligned");

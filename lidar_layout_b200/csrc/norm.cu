@@ -4,6 +4,8 @@
 // decoder.  HBM-bound: pass 1 reads x once (per-CTA partial sums, combined in a fixed order => deterministic),
 // pass 2 reads x once more and writes y (with its circular halo columns) once.  Works on concatenated views
 // (ld > C), so the U-Net's skip `torch.cat` (openaimodel.py:745) is never materialised separately.
+#include <cstdlib>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -155,6 +157,108 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int H, int W, int xh
   for (; pix < p1; pix += pstride) emit(pix, __ldg(addr(pix)));
 }
 
+// One-pass GroupNorm for tensors whose per-(sample, group-chunk) slab fits in registers: one CTA owns `gpc` whole groups
+// (gpc * cpg channels, vec = gpc * cpg / 8 sixteen-byte vectors per pixel) of one sample, every thread keeps its NV
+// vectors in registers between the statistics and the normalisation, so x is read once and y written once (4 bytes per
+// element instead of 6) in a single launch.  Reductions run in a fixed order (per-thread partials -> fixed lane
+// assignment -> xor-shuffle tree): bit-reproducible and, one sample per CTA, independent of the batch size.
+template <int NV>
+__global__ void __launch_bounds__(512)
+gn_fused_kernel(const bf16* __restrict__ x, int H, int W, int xhl, int xWp, int xld, bf16* __restrict__ y, int yhl, int yhr,
+                int yWp, int yld, int cpg, int gpc, const float* __restrict__ gamma, const float* __restrict__ beta,
+                float eps, int silu) {
+  __shared__ float2 red[512];
+  __shared__ float2 stat[32];   // (mean, rstd) per local group
+  const int b = blockIdx.y;
+  const int c0 = blockIdx.x * gpc * cpg;
+  const int vec = (gpc * cpg) >> 3, vg = cpg >> 3;
+  const int PR = blockDim.x / vec;                 // pixel rows walked in parallel
+  const int nthr = PR * vec;
+  const bool active = threadIdx.x < nthr;
+  const int cv = threadIdx.x % vec, prow = threadIdx.x / vec;
+  const int HW = H * W;
+  auto xaddr = [&](int pix) {
+    const int h = pix / W, w = pix - h * W;
+    return reinterpret_cast<const uint4*>(x + ((size_t)(b * H + h) * xWp + (w + xhl)) * xld + c0) + cv;
+  };
+  uint4 v[NV];
+  float sm = 0.f, sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int pix = prow + k * PR;
+    v[k] = make_uint4(0, 0, 0, 0);
+    if (active && pix < HW) v[k] = __ldg(xaddr(pix));
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const uint32_t uu[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = unpack_bf16(uu[i]);
+      sm += f.x + f.y;
+      sq += f.x * f.x + f.y * f.y;
+    }
+  }
+  red[threadIdx.x] = make_float2(sm, sq);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int g = warp; g < gpc; g += nwarps) {
+    float ts = 0.f, tq = 0.f;
+    const int n_contrib = PR * vg;
+    for (int i = lane; i < n_contrib; i += 32) {
+      const int pr = i / vg, vi = i - pr * vg;
+      const float2 r = red[pr * vec + g * vg + vi];
+      ts += r.x; tq += r.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ts += __shfl_xor_sync(0xffffffffu, ts, o);
+      tq += __shfl_xor_sync(0xffffffffu, tq, o);
+    }
+    if (lane == 0) {
+      const float n = (float)HW * (float)cpg;
+      const float mean = ts / n;
+      const float var = fmaxf(tq / n - mean * mean, 0.f);
+      stat[g] = make_float2(mean, rsqrtf(var + eps));
+    }
+  }
+  __syncthreads();
+  if (!active) return;
+  float sc[8], sf[8];
+  {
+    const float2 st = stat[cv / vg];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + cv * 8 + j;
+      const float ga = __ldg(gamma + c) * st.y;
+      sc[j] = ga;
+      sf[j] = __ldg(beta + c) - st.x * ga;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int pix = prow + k * PR;
+    if (pix >= HW) break;
+    const int h = pix / W, w = pix - h * W;
+    const uint32_t uu[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+    uint32_t oo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = unpack_bf16(uu[i]);
+      float a = f.x * sc[2 * i] + sf[2 * i];
+      float c = f.y * sc[2 * i + 1] + sf[2 * i + 1];
+      if (silu) { a = silu_f(a); c = silu_f(c); }
+      oo[i] = pack_bf16(a, c);
+    }
+    const uint4 o = make_uint4(oo[0], oo[1], oo[2], oo[3]);
+    const size_t rowbase = (size_t)(b * H + h) * yWp;
+    uint4* yp = reinterpret_cast<uint4*>(y + (rowbase + w + yhl) * yld + c0) + cv;
+    *yp = o;
+    if (w < yhr) *(reinterpret_cast<uint4*>(y + (rowbase + W + yhl + w) * yld + c0) + cv) = o;
+    if (w >= W - yhl) *(reinterpret_cast<uint4*>(y + (rowbase + (w - (W - yhl))) * yld + c0) + cv) = o;
+  }
+}
+
 }  // namespace
 
 void launch_groupnorm(const View& x, const View& y, const float* gamma, const float* beta, float eps, int groups,
@@ -169,6 +273,38 @@ void launch_groupnorm(const View& x, const View& y, const float* gamma, const fl
   int threads = (256 % vec == 0) ? 256 : ((384 % vec == 0) ? 384 : 0);
   if (threads == 0) { LIDM_REQUIRE(vec <= 1024, "C too large"); threads = vec; }
   const int HW = x.H * x.W;
+  // one-pass register-resident kernel when a group chunk of one sample fits (the U-Net's tensors): pick the widest chunk
+  // (most contiguous bytes per pixel) that keeps <= 16 vectors per thread and still fills the GPU
+  static const bool two_pass = getenv("LIDM_GN_TWO_PASS") != nullptr;
+  // (measured on B200, B=64: wins 20-25 % on the 4x32 level, loses on larger maps where the two-pass kernels' second
+  // read hits L2 and their higher occupancy matters more than the saved pass)
+  if (!two_pass && cpg % 8 == 0 && (cpg & (cpg - 1)) == 0 && HW <= 128) {
+    const int vg = cpg / 8;
+    int best = 0;
+    for (int gpc = 1; gpc <= groups; gpc *= 2) {
+      const int v = gpc * vg;
+      if (v > 512) break;
+      const int pr = 512 / v;
+      const int nv = (HW + pr - 1) / pr;
+      if (nv > 16) break;
+      if (gpc > 1 && (long)x.B * (groups / gpc) < 296 && gpc * cpg * 2 > 64) break;   // keep >= 2 CTAs per SM once rows are >= 64 B
+      best = gpc;
+    }
+    if (best > 0) {
+      const int v = best * vg, pr = 512 / v, nv = (HW + pr - 1) / pr;
+      dim3 grid(groups / best, x.B);
+#define GN_FUSED(NV)                                                                                                  \
+  gn_fused_kernel<NV><<<grid, 512, 0, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, y.hl, y.hr, y.Wp(), y.ld, cpg, best, \
+                                           gamma, beta, eps, silu ? 1 : 0)
+      if (nv <= 4) GN_FUSED(4);
+      else if (nv <= 8) GN_FUSED(8);
+      else GN_FUSED(16);
+#undef GN_FUSED
+      LIDM_CUDA_CHECK(cudaGetLastError());
+      LIDM_COUNT_LAUNCH(1);
+      return;
+    }
+  }
   // chunking depends on the tensor shape only (never on B): results are batch-invariant
   const int pstride = threads / vec;
   int pix_per_cta = HW <= 512 ? 32 : 64;
