@@ -122,23 +122,33 @@ __global__ void backproject_kernel(const float* __restrict__ img, int H, int W, 
 // out[(b*H*W + h*W + w) * kpad + (ky*kw + kx)*C + c] = x[b][c][h+ky-pt][(w+kx-pl) mod W]  (0 outside H)
 __global__ void im2col_nchw_f32_kernel(const float* __restrict__ x, int B, int C, int H, int W, int kh, int kw, int pl,
                                        int pt, bf16* __restrict__ out, int kpad) {
-  const int64_t total = (int64_t)B * H * W * kpad;
+  // one thread = 8 consecutive k of one pixel (a 16-byte store); kpad is a multiple of 8
+  const int kv = kpad >> 3;
+  const int64_t total = (int64_t)B * H * W * kv;
+  const int K = kh * kw * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int k = (int)(i % kpad);
-    const int64_t pixg = i / kpad;
-    const int w = (int)(pixg % W);
-    const int h = (int)((pixg / W) % H);
-    const int b = (int)(pixg / ((int64_t)W * H));
-    float v = 0.f;
-    if (k < kh * kw * C) {
-      const int tap = k / C, c = k - tap * C;
-      const int ky = tap / kw, kx = tap - ky * kw;
-      const int hs = h + ky - pt;
-      int ws = (w + kx - pl) % W;
-      if (ws < 0) ws += W;
-      if (hs >= 0 && hs < H) v = x[(((int64_t)b * C + c) * H + hs) * W + ws];
+    const int k0 = (int)(i % kv) * 8;
+    const int pixg = (int)(i / kv);
+    const int w = pixg % W;
+    const int h = (pixg / W) % H;
+    const int b = pixg / (W * H);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + j;
+      v[j] = 0.f;
+      if (k < K) {
+        const int tap = k / C, c = k - tap * C;
+        const int ky = tap / kw, kx = tap - ky * kw;
+        const int hs = h + ky - pt;
+        int ws = w + kx - pl;
+        ws = ws < 0 ? ws + W : (ws >= W ? ws - W : ws);
+        if (hs >= 0 && hs < H) v[j] = __ldg(x + (((size_t)b * C + c) * H + hs) * W + ws);
+      }
     }
-    out[i] = __float2bfloat16(v);
+    uint4 o;
+    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+    reinterpret_cast<uint4*>(out)[i] = o;
   }
 }
 
@@ -488,8 +498,8 @@ void launch_backproject(const float* img, int B, int H, int W, float fov_up_deg,
 
 void launch_im2col_nchw_f32(const float* x, int B, int C, int H, int W, int kh, int kw, int pl, int pt, bf16* out,
                             int kpad, cudaStream_t s) {
-  LIDM_REQUIRE(kh * kw * C <= kpad, "im2col: kpad too small");
-  const int64_t total = (int64_t)B * H * W * kpad;
+  LIDM_REQUIRE(kh * kw * C <= kpad && kpad % 8 == 0 && pl < W && kw - 1 - pl < W, "im2col: kpad too small / not a multiple of 8");
+  const int64_t total = (int64_t)B * H * W * (kpad / 8);
   im2col_nchw_f32_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, B, C, H, W, kh, kw, pl, pt, out, kpad);
   LIDM_CUDA_CHECK(cudaGetLastError());
   LIDM_COUNT_LAUNCH(1);
