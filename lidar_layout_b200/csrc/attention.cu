@@ -758,7 +758,7 @@ attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     prefetch_tensormap(&tmQ);
     prefetch_tensormap(&tmKV);
     mbar_init(q_full, 1);
-    for (int s = 0; s < KV_ST; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < KV_ST; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], NG); }
     for (int g = 0; g < NG; ++g) { mbar_init(&s_ready[g], 1); mbar_init(&s_free[g], 4); mbar_init(&stagger[g], 4); }
     for (int i = 0; i < NG; ++i) { mbar_init(&p_ready[i], 4); mbar_init(&pv_done[i], 1); }
     fence_barrier_init();
@@ -786,77 +786,55 @@ attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           if (++s == KV_ST) { s = 0; ph ^= 1; }
         }
       }
-    } else if (warp == 1) {
+    } else if (warp - 1 < NG) {
+      // one MMA-issuing thread per group (tcgen05.mma issue blocks until the tensor pipe accepts the instruction, so a
+      // single thread serving both groups delays one group's S / P*V behind the other's): each polls only its own
+      // barriers; a K/V stage goes back to the TMA warp when every group has committed its P*V on it
       if (lane == 0) {
+        const int g = warp - 1;
         constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV_);
         constexpr uint32_t idesc_o = make_idesc_bf16(BQ, D) | (1u << 16);     // V is an MN-major B operand
-        int js[NG], jp[NG];
-#pragma unroll
-        for (int g = 0; g < NG; ++g) js[g] = jp[g] = 0;
-        int released = 0;                      // K/V tiles handed back to the TMA warp
-#ifdef LIDM_ATTN_TRACE
-        const bool trc = blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 40;
-        long long tS[2][8], tPV[2][8];
-#endif
+        int js = 0, jp = 0;
         mbar_wait(q_full, 0);
         const long long t0 = clock64();
-        int remaining = NG * nkv;
-        while (remaining > 0) {
-#pragma unroll
-          for (int g = 0; g < NG; ++g) {
-            if (js[g] < nkv) {
-              const int j = js[g], st = j % KV_ST;
-              bool ok = mbar_test_wait(&kv_full[st], (j / KV_ST) & 1);
-              if (ok && j > 0) ok = mbar_test_wait(&s_free[g], (j - 1) & 1);
-              if (ok) {
-                tcgen05_fence_after();
-                const uint64_t qdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_Q + g * Q_BYTES));
-                const uint64_t kdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_K + st * L::KB));
-                const uint32_t d = tmem_base + g * BKV_;
-                umma_bf16_ss(d, qdesc, kdesc, idesc_s, 0);
-                umma_bf16_ss(d, qdesc + 2, kdesc + 2, idesc_s, 1);
-                umma_commit(&s_ready[g]);
-#ifdef LIDM_ATTN_TRACE
-                if (trc && j < 8) tS[g][j] = clock64();
-#endif
-                js[g] = j + 1;
-              }
+        const uint64_t qdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_Q + g * Q_BYTES));
+        const uint32_t dS = tmem_base + g * BKV_;
+        const uint32_t tP = tmem_base + L::P_COL + g * (BKV_ / 2);
+        const uint32_t dO = tmem_base + L::O_COL + g * 32;
+        while (jp < nkv) {
+          if (js < nkv) {
+            const int j = js, st = j % KV_ST;
+            bool ok = mbar_test_wait(&kv_full[st], (j / KV_ST) & 1);
+            if (ok && j > 0) ok = mbar_test_wait(&s_free[g], (j - 1) & 1);
+            if (ok) {
+              tcgen05_fence_after();
+              const uint64_t kdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_K + st * L::KB));
+              umma_bf16_ss(dS, qdesc, kdesc, idesc_s, 0);
+              umma_bf16_ss(dS, qdesc + 2, kdesc + 2, idesc_s, 1);
+              umma_commit(&s_ready[g]);
+              js = j + 1;
             }
-            if (jp[g] < js[g]) {
-              const int j = jp[g], st = j % KV_ST;
-              if (mbar_test_wait(&p_ready[g], j & 1)) {
-                tcgen05_fence_after();
-                const uint64_t vdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_V + st * L::KB));
-                const uint32_t tP = tmem_base + L::P_COL + g * (BKV_ / 2);
-                const uint32_t dO = tmem_base + L::O_COL + g * 32;
+          }
+          if (jp < js) {
+            const int j = jp, st = j % KV_ST;
+            if (mbar_test_wait(&p_ready[g], j & 1)) {
+              tcgen05_fence_after();
+              const uint64_t vdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_V + st * L::KB));
 #pragma unroll
-                for (int kk = 0; kk < BKV_ / 16; ++kk) {
-                  const uint64_t vb = vdesc + (uint64_t)((kk * 1024) >> 4);
-                  umma_bf16_ts(dO, tP + kk * 8, vb, idesc_o, (j > 0 || kk != 0) ? 1u : 0u);   // 16 bf16 = 8 columns
-                }
-                umma_commit(&pv_done[g]);
-#ifdef LIDM_ATTN_TRACE
-                if (trc && j < 8) tPV[g][j] = clock64();
-#endif
-                jp[g] = j + 1;
-                --remaining;
-                int jmin = jp[0];
-#pragma unroll
-                for (int gg = 1; gg < NG; ++gg) jmin = jp[gg] < jmin ? jp[gg] : jmin;
-                if (jmin > released) { umma_commit(&kv_empty[released % KV_ST]); ++released; }   // every group is past it
+              for (int kk = 0; kk < BKV_ / 16; ++kk) {
+                const uint64_t vb = vdesc + (uint64_t)((kk * 1024) >> 4);
+                umma_bf16_ts(dO, tP + kk * 8, vb, idesc_o, (j > 0 || kk != 0) ? 1u : 0u);   // 16 bf16 = 8 columns
               }
+              umma_commit(&pv_done[g]);
+              umma_commit(&kv_empty[st]);      // this group is done with K/V tile j
+              jp = j + 1;
             }
           }
           if (clock64() - t0 > 4000000000LL) {
-            printf("lidm: attention v4 MMA loop timeout block(%d,%d,%d)\n", blockIdx.x, blockIdx.y, blockIdx.z);
+            printf("lidm: attention v4 MMA loop timeout block(%d,%d,%d) group %d\n", blockIdx.x, blockIdx.y, blockIdx.z, g);
             __trap();
           }
         }
-#ifdef LIDM_ATTN_TRACE
-        if (trc && nkv >= 8)
-          for (int j = 0; j < 8; ++j)
-            printf("mma j%d: S0 %lld S1 %lld PV0 %lld PV1 %lld\n", j, tS[0][j] - t0, tS[1][j] - t0, tPV[0][j] - t0, tPV[1][j] - t0);
-#endif
       }
     }
   } else {
