@@ -123,6 +123,11 @@ int lidm_cfg_combine(const float* eps2, float guidance_scale, float* eps_out, in
 int lidm_vq_decode(lidm_handle* h, const float* z, int32_t force_not_quantize, float* img_out, int32_t* idx_out,
                    int32_t B, void* stream);
 
+/* first_stage_model.quantize(z) (taming VectorQuantizer2.forward, arithmetic as lidm/models/ae/vq.py:66-79; used by the
+ * samplers' quantize_x0 / quantize_denoised options, ddim.py:199, ddpm.py:1081): nearest codebook entry per latent pixel.
+ * z: (B, embed_dim, h, w); zq_out: same shape (z + (e_idx - z), the straight-through value); idx_out: NULL or int32 (B*h*w). */
+int lidm_vq_quantize(lidm_handle* h, const float* z, float* zq_out, int32_t* idx_out, int32_t B, void* stream);
+
 /* LatentDiffusion.encode_first_stage -> VQModelInterface.encode (ddpm.py:837, autoencoder.py:285-288): Encoder
  * (model_lidm.py:284-312) + quant_conv, NOT quantised (the quantiser sits in decode) and not yet multiplied by
  * scale_factor (get_first_stage_encoding, ddpm.py:546-556).  img: (B, in_channels, H, W) fp32; z_out: (B, embed_dim, h, w).

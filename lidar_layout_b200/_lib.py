@@ -43,7 +43,7 @@ class CConfig(ctypes.Structure):
 EXPORTS = [
     "lidm_last_error", "lidm_create", "lidm_destroy", "lidm_load_weight", "lidm_finalize_weights",
     "lidm_unet_forward", "lidm_unet_forward_cond", "lidm_ddim_step", "lidm_ddim_sample", "lidm_ddim_sample_cond",
-    "lidm_cfg_combine", "lidm_vq_decode", "lidm_vq_encode", "lidm_image_shape",
+    "lidm_cfg_combine", "lidm_vq_decode", "lidm_vq_encode", "lidm_vq_quantize", "lidm_image_shape",
     "lidm_backproject", "lidm_to_uint8_image", "lidm_compact_points", "lidm_op_circular_conv2d", "lidm_op_groupnorm", "lidm_op_qkv_attention_legacy",
     "lidm_launch_count", "lidm_profile_begin", "lidm_profile_end",
 ]
@@ -79,6 +79,7 @@ def load() -> ctypes.CDLL:
     lib.lidm_ddim_sample.argtypes = [c_void_p, c_void_p, POINTER(c_int64), POINTER(c_float), c_int32, c_void_p,
                                      c_float, c_void_p, c_int32, c_void_p]
     lib.lidm_vq_decode.argtypes = [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p]
+    lib.lidm_vq_quantize.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]
     lib.lidm_vq_encode.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_void_p]
     lib.lidm_image_shape.argtypes = [c_void_p, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]
     lib.lidm_backproject.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_float, c_float, c_float, c_float, c_float,

@@ -324,6 +324,11 @@ __global__ void vq_kernel(const float* __restrict__ z, int C, int HW, int64_t np
   }
   if (!active) return;
   if (idx_out != nullptr) idx_out[pix] = quantize ? best : -1;
+  if (pq_w == nullptr) {   // quantiser only (VectorQuantizer2.forward's z_q)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) out[(b * C + c) * HW + hw] = q[c];
+    return;
+  }
   // post_quant_conv: 1x1 conv embed_dim -> z_channels (fp32)
   for (int co = 0; co < C; ++co) {
     float acc = __ldg(pq_b + co);

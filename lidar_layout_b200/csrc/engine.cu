@@ -2040,6 +2040,16 @@ int lidm_finalize_weights(lidm_handle* h, int32_t use_ema) {
   });
 }
 
+int lidm_vq_quantize(lidm_handle* h, const float* z, float* zq_out, int32_t* idx_out, int32_t B, void* stream) {
+  return guarded(h, [&] {
+    require_ready(h, B);
+    LIDM_REQUIRE(z != nullptr && zq_out != nullptr, "null tensor");
+    const lidm_config& cfg = h->cfg;
+    launch_vq(z, B, cfg.z_channels, cfg.latent_h * cfg.latent_w, h->codebook, h->cb_norm, cfg.n_embed, 1, nullptr, nullptr,
+              1.0f, zq_out, idx_out, reinterpret_cast<cudaStream_t>(stream));
+  });
+}
+
 int lidm_vq_encode(lidm_handle* h, const float* img, float* z_out, int32_t B, void* stream) {
   return guarded(h, [&] {
     require_ready(h, B);

@@ -33,7 +33,9 @@ class _FirstStage:
         self._owner = owner
 
     def quantize(self, z):
-        raise NotImplementedError("stand-alone quantize() is not exposed; use decode_first_stage")
+        """VectorQuantizer2.forward's return convention: (z_q, loss, (perplexity, min_encodings, indices))."""
+        zq, idx = self._owner.engine.vq_quantize(z)
+        return zq, None, (None, None, idx.long())
 
     def decode(self, h, force_not_quantize=False):
         return self._owner.engine.vq_decode(h, force_not_quantize)
@@ -190,7 +192,7 @@ class LatentDiffusion:
         if clip_denoised:
             x_recon.clamp_(-1., 1.)
         if quantize_denoised:
-            raise NotImplementedError("quantize_denoised")
+            x_recon, _, _ = self.first_stage_model.quantize(x_recon)
         mean, var, logvar = self.q_posterior(x_start=x_recon, x_t=x, t=t)
         return (mean, var, logvar, x_recon) if return_x0 else (mean, var, logvar)
 

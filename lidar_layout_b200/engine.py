@@ -184,6 +184,16 @@ class Engine:
                 float(guidance_scale), _stream_ptr(self.device)), self._h)
         return x, pred
 
+    def vq_quantize(self, z: torch.Tensor):
+        """first_stage_model.quantize(z): (z_q, indices int32 (B*h*w,))."""
+        z = _f32c(z, "z")
+        zq = torch.empty_like(z)
+        idx = torch.empty((z.shape[0] * z.shape[2] * z.shape[3],), dtype=torch.int32, device=z.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.lidm_vq_quantize(self._h, z.data_ptr(), zq.data_ptr(), idx.data_ptr(), z.shape[0],
+                                                  _stream_ptr(self.device)), self._h)
+        return zq, idx
+
     def vq_encode(self, img: torch.Tensor) -> torch.Tensor:
         """VQModelInterface.encode: quant_conv(encoder(img)), (B, in_channels, H, W) -> (B, embed_dim, h, w)."""
         img = _f32c(img, "img")

@@ -386,15 +386,18 @@ def decode_first_stage(sd, cfg: LidmConfig, z, force_not_quantize=False, return_
 # --------------------------------------------------------------------------------------
 
 
-def ddim_step(x, e_t, coef, noise=None, temperature=1.0):
+def ddim_step(x, e_t, coef, noise=None, temperature=1.0, quantize=None):
     """DDIMSampler.p_sample_ddim arithmetic, lidm/models/diffusion/ddim.py:191-206.
-    coef = (a_t, a_prev, sigma_t, sqrt_one_minus_at) float32 scalars."""
+    coef = (a_t, a_prev, sigma_t, sqrt_one_minus_at) float32 scalars.  quantize: optional callable applied to pred_x0
+    (quantize_denoised, ddim.py:198-199)."""
     b = x.shape[0]
     a_t = torch.full((b, 1, 1, 1), float(coef[0]))
     a_prev = torch.full((b, 1, 1, 1), float(coef[1]))
     sigma_t = torch.full((b, 1, 1, 1), float(coef[2]))
     sqrt_one_minus_at = torch.full((b, 1, 1, 1), float(coef[3]))
     pred_x0 = (x - sqrt_one_minus_at * e_t) / a_t.sqrt()
+    if quantize is not None:
+        pred_x0 = quantize(pred_x0)
     dir_xt = (1.0 - a_prev - sigma_t ** 2).sqrt() * e_t
     n = torch.zeros_like(x) if noise is None else noise
     x_prev = a_prev.sqrt() * pred_x0 + dir_xt + sigma_t * n * temperature
@@ -428,7 +431,7 @@ def guided_eps(sd, cfg: LidmConfig, x, t, cond, unconditional_conditioning=None,
 
 @torch.no_grad()
 def ddim_sample(sd, cfg: LidmConfig, S, x_T, eta=0.0, noise=None, temperature=1.0, record=None, cond=None,
-                unconditional_conditioning=None, unconditional_guidance_scale=1.0):
+                unconditional_conditioning=None, unconditional_guidance_scale=1.0, quantize_x0=False):
     """DDIMSampler.sample / ddim_sampling, ddim.py:57-165.
     noise: optional (n_steps,B,C,H,W) pre-generated tensor used for the sigma_t * randn term (in loop order).
     record: optional list; receives (x_t, t, eps, pred_x0, x_prev) per step."""
@@ -440,7 +443,8 @@ def ddim_sample(sd, cfg: LidmConfig, S, x_T, eta=0.0, noise=None, temperature=1.
         t = torch.full((img.shape[0],), int(step), dtype=torch.long)
         e_t = guided_eps(sd, cfg, img, t, cond, unconditional_conditioning, unconditional_guidance_scale)
         nz = None if noise is None else noise[i]
-        x_prev, pred_x0 = ddim_step(img, e_t, table[index], nz, temperature)
+        qf = (lambda p: vq_quantize(p, sd[AE_PREFIX + "quantize.embedding.weight"])[0]) if quantize_x0 else None
+        x_prev, pred_x0 = ddim_step(img, e_t, table[index], nz, temperature, quantize=qf)
         if record is not None:
             record.append((img, t, e_t, pred_x0, x_prev))
         img = x_prev
