@@ -1,14 +1,13 @@
 // Fused flash-style attention for head dim 32 on tcgen05 / TMEM / TMA (sm_100a).
 //
-// Replaces QKVAttentionLegacy.forward (reference lidm/modules/diffusion/openaimodel.py:358-374): per head
-//   w = softmax_fp32((q s)^T (k s)),  a = w v,   s = ch^-1/4  (folded into the packed qkv weights),
-// without materialising the (B*heads, T, T) score tensor.  One CTA = one 128-query tile of one (sample, head):
-//   S (128x128 fp32, TMEM cols 0..127)  = Q K^T      2 x tcgen05.mma  M128 N128 K16   (operands 64B-swizzled)
-//   P = exp2(S*log2e - m) -> bf16 -> smem (128B-swizzled, K-major A operand)
-//   O_tile (128x32 fp32, TMEM cols 128..159) = P V   8 x tcgen05.mma  M128 N32  K16   (V^T tile K-major)
-// and the 4 softmax warps fold O_tile into fp32 registers with the online-softmax rescale.  K/V tiles stream
-// through a 2-stage TMA ring; two CTAs are co-resident per SM so one CTA's MMAs overlap the other's softmax.
-// Inputs: qk (B,T,2C) = [q all heads | k all heads], vt (B,C,T) — both written by the qkv GEMM epilogue.
+// Replaces QKVAttentionLegacy.forward (reference lidm/modules/diffusion/openaimodel.py:358-374) and the core of
+// CrossAttention.forward (reference lidm/modules/attention.py:170-193): per head
+//   w = softmax_fp32((q s)^T (k s)),  a = w v,   s = ch^-1/4  (folded into the packed q / k weight rows),
+// without materialising the (B*heads, T, T) score tensor.  q / k / v are read straight out of the packed (B, T, 3C)
+// output of the qkv GEMM (or, for cross-attention, q from its own GEMM and k / v from the context projection); V is
+// consumed as an MN-major tcgen05 operand, so nothing is transposed.
+//   v4 (T a multiple of 256): two 128-row query tiles per CTA, P and O resident in tensor memory — see namespace v4.
+//   v2 (T = 128 and odd multiples): one query tile per CTA, two CTAs per SM, P through swizzled shared memory.
 #include <cstdlib>
 
 #include "common.h"
@@ -21,17 +20,9 @@ namespace {
 constexpr int D = 32;
 constexpr int BQ = 128;
 constexpr int BKV = 128;
-constexpr int KV_STAGES = 2;
 constexpr int Q_BYTES = BQ * D * 2;        // 8 KiB, rows of 64 B (SWIZZLE_64B)
 constexpr int K_BYTES = BKV * D * 2;       // 8 KiB
-constexpr int V_BYTES = D * BKV * 2;       // 8 KiB = 2 atoms of (32 rows x 128 B)
 constexpr int P_BYTES = BQ * BKV * 2;      // 32 KiB = 2 atoms of (128 rows x 128 B)
-constexpr int OFF_Q = 0;
-constexpr int OFF_K = OFF_Q + Q_BYTES;
-constexpr int OFF_V = OFF_K + KV_STAGES * K_BYTES;
-constexpr int OFF_P = OFF_V + KV_STAGES * V_BYTES;
-constexpr int OFF_BAR = OFF_P + P_BYTES;
-constexpr int SMEM_TOTAL = OFF_BAR + 256 + 1024;
 constexpr uint32_t TMEM_COLS = 256;
 constexpr uint32_t O_COL = 128;
 
@@ -58,167 +49,6 @@ __device__ __forceinline__ float ex2_poly(float x) {
   p = fmaf(p, f, 0.69325477f);
   p = fmaf(p, f, 0.9999277f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-
-__global__ void __launch_bounds__(192)
-attention_d32_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmVT,
-                     bf16* __restrict__ out, int out_ld, int T, int C) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* kv_full = q_full + 1;
-  uint64_t* kv_empty = kv_full + KV_STAGES;
-  uint64_t* s_ready = kv_empty + KV_STAGES;
-  uint64_t* p_ready = s_ready + 1;
-  uint64_t* o_ready = p_ready + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_ready + 1);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * BQ;
-  const int head = blockIdx.y;
-  const int b = blockIdx.z;
-  const int nkv = T / BKV;
-
-  if (threadIdx.x == 0) {
-    prefetch_tensormap(&tmQK);
-    prefetch_tensormap(&tmVT);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    mbar_init(s_ready, 1);
-    mbar_init(p_ready, 128);
-    mbar_init(o_ready, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, Q_BYTES);
-      tma_load_3d(smem + OFF_Q, &tmQK, q_full, head * D, q0, b);
-      int s = 0; uint32_t ph = 0;
-      for (int j = 0; j < nkv; ++j) {
-        mbar_wait(&kv_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&kv_full[s], K_BYTES + V_BYTES);
-        tma_load_3d(smem + OFF_K + s * K_BYTES, &tmQK, &kv_full[s], C + head * D, j * BKV, b);
-        tma_load_3d(smem + OFF_V + s * V_BYTES, &tmVT, &kv_full[s], j * BKV, head * D, b);
-        tma_load_3d(smem + OFF_V + s * V_BYTES + V_BYTES / 2, &tmVT, &kv_full[s], j * BKV + 64, head * D, b);
-        if (++s == KV_STAGES) { s = 0; ph ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV);
-      constexpr uint32_t idesc_o = make_idesc_bf16(BQ, D);
-      const uint64_t qdesc = make_kmajor_desc<64>(smem_u32(smem + OFF_Q));
-      const uint64_t pdesc = make_kmajor_desc<128>(smem_u32(smem + OFF_P));
-      mbar_wait(q_full, 0);
-      int s = 0; uint32_t ph = 0;
-      for (int j = 0; j < nkv; ++j) {
-        mbar_wait(&kv_full[s], ph);
-        tcgen05_fence_after();
-        const uint64_t kdesc = make_kmajor_desc<64>(smem_u32(smem + OFF_K + s * K_BYTES));
-        umma_bf16_ss(tmem_base, qdesc, kdesc, idesc_s, 0);
-        umma_bf16_ss(tmem_base, qdesc + 2, kdesc + 2, idesc_s, 1);
-        umma_commit(s_ready);
-        mbar_wait(p_ready, j & 1);
-        tcgen05_fence_after();
-        const uint64_t vdesc = make_kmajor_desc<128>(smem_u32(smem + OFF_V + s * V_BYTES));
-#pragma unroll
-        for (int kk = 0; kk < BKV / 16; ++kk) {
-          const uint64_t pa = pdesc + (uint64_t)(((kk >> 2) * (P_BYTES / 2) + (kk & 3) * 32) >> 4);
-          const uint64_t vb = vdesc + (uint64_t)(((kk >> 2) * (V_BYTES / 2) + (kk & 3) * 32) >> 4);
-          umma_bf16_ss(tmem_base + O_COL, pa, vb, idesc_o, kk != 0);
-        }
-        umma_commit(o_ready);
-        umma_commit(&kv_empty[s]);
-        if (++s == KV_STAGES) { s = 0; ph ^= 1; }
-      }
-    }
-  } else {
-    // ---------------------------------------------------------------- softmax + output warps
-    const int qd = warp & 3;
-    const int row = qd * 32 + lane;
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
-    constexpr float LOG2E = 1.4426950408889634f;
-    float m = -INFINITY, l = 0.f;
-    float o[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) o[i] = 0.f;
-    uint8_t* prow = smem + OFF_P + row * 128;
-    for (int j = 0; j < nkv; ++j) {
-      mbar_wait(s_ready, j & 1);
-      tcgen05_fence_after();
-      float mx = m;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t raw[32];
-        tmem_ld_32x32b_x32(trow + c * 32, raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
-      }
-      const float alpha = ex2((m - mx) * LOG2E);  // m = -inf on the first tile -> 0
-      m = mx;
-      const float mb = mx * LOG2E;
-      float sum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t raw[32];
-        tmem_ld_32x32b_x32(trow + c * 32, raw);
-        tmem_ld_wait();
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float p0 = ex2(fmaf(__uint_as_float(raw[2 * i]), LOG2E, -mb));
-          const float p1 = ex2(fmaf(__uint_as_float(raw[2 * i + 1]), LOG2E, -mb));
-          sum += p0 + p1;
-          pk[i] = pack_bf16(p0, p1);
-        }
-        // P[row][c*32 .. c*32+31] -> K-atom (c>>1), 16-byte chunks (c&1)*4 .. +3, XOR-swizzled with (row & 7)
-        uint8_t* base = prow + (c >> 1) * (P_BYTES / 2);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int chunk = ((c & 1) * 4 + i) ^ (row & 7);
-          *reinterpret_cast<uint4*>(base + chunk * 16) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-        }
-      }
-      l = l * alpha + sum;
-      fence_proxy_async();       // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      tcgen05_fence_before();
-      mbar_arrive(p_ready);
-      // fold the previous accumulator while the PV MMA runs
-#pragma unroll
-      for (int i = 0; i < D; ++i) o[i] *= alpha;
-      mbar_wait(o_ready, j & 1);
-      tcgen05_fence_after();
-      {
-        uint32_t raw[32];
-        tmem_ld_32x32b_x32(trow + O_COL, raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < D; ++i) o[i] += __uint_as_float(raw[i]);
-      }
-      tcgen05_fence_before();
-    }
-    const float inv = 1.f / l;
-    bf16* op = out + ((size_t)b * T + q0 + row) * out_ld + head * D;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 u;
-      u.x = pack_bf16(o[8 * i + 0] * inv, o[8 * i + 1] * inv);
-      u.y = pack_bf16(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
-      u.z = pack_bf16(o[8 * i + 4] * inv, o[8 * i + 5] * inv);
-      u.w = pack_bf16(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
-      reinterpret_cast<uint4*>(op)[i] = u;
-    }
-  }
-  __syncthreads();
-  if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
 // =====================================================================================================
@@ -467,226 +297,6 @@ attention_d32_v2_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restr
 
 }  // namespace v2
 
-// =====================================================================================================
-// v3: two 128-row query tiles per CTA (one softmax warpgroup each) sharing every K/V tile, one CTA per SM.
-//   * TMEM (512 columns): S[g][buf] = 4 x 128 columns, O_tile aliased onto the first 32 columns of the dead S.
-//   * Each softmax thread pulls its whole 128-column S row out of TMEM ONCE (four back-to-back tcgen05.ld, one
-//     wait) and keeps it in registers for the max, the exp and the bf16 pack: half the TMEM reads of v2, and the
-//     K/V shared-memory traffic per query row is halved as well.
-namespace v3 {
-
-constexpr int KV_ST = 3;
-constexpr int OFF_Q = 0;                                  // 256 rows x 64 B
-constexpr int OFF_K = OFF_Q + 2 * Q_BYTES;
-constexpr int OFF_V = OFF_K + KV_ST * K_BYTES;
-constexpr int OFF_P = OFF_V + KV_ST * K_BYTES;            // 2 groups x 32 KiB
-constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
-constexpr int SMEM_TOTAL = OFF_BAR + 512 + 1024;
-constexpr uint32_t TMEM_COLS = 512;
-
-// 384 threads = 3 warpgroups: WG0 = {TMA warp, MMA warp, 2 idle warps} shrinks to 40 registers/thread with setmaxnreg,
-// WG1 / WG2 = the two softmax groups grow to 224 so a whole 128-column S row fits in registers.
-__global__ void __launch_bounds__(384, 1)
-attention_d32_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                        bf16* __restrict__ out, int out_ld, int T, int C) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* kv_full = q_full + 1;          // [KV_ST]
-  uint64_t* kv_empty = kv_full + KV_ST;    // [KV_ST]
-  uint64_t* s_ready = kv_empty + KV_ST;    // [2 groups][2 buffers]
-  uint64_t* p_ready = s_ready + 4;         // [2]
-  uint64_t* o_ready = p_ready + 2;         // [2]
-  uint64_t* o_free = o_ready + 2;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 256;
-  const int head = blockIdx.y;
-  const int b = blockIdx.z;
-  const int nkv = T / BKV;
-
-  if (threadIdx.x == 0) {
-    prefetch_tensormap(&tmQ);
-    prefetch_tensormap(&tmKV);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < KV_ST; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    for (int i = 0; i < 4; ++i) mbar_init(&s_ready[i], 1);
-    for (int g = 0; g < 2; ++g) { mbar_init(&p_ready[g], 128); mbar_init(&o_ready[g], 1); mbar_init(&o_free[g], 128); }
-    fence_barrier_init();
-  }
-  if (warp == 1) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, 2 * Q_BYTES);
-      tma_load_3d(smem + OFF_Q, &tmQ, q_full, head * D, q0, b);            // 256 query rows in one box
-      int s = 0; uint32_t ph = 0;
-      for (int j = 0; j < nkv; ++j) {
-        mbar_wait(&kv_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&kv_full[s], 2 * K_BYTES);
-        tma_load_3d(smem + OFF_K + s * K_BYTES, &tmKV, &kv_full[s], C + head * D, j * BKV, b);
-        tma_load_3d(smem + OFF_V + s * K_BYTES, &tmKV, &kv_full[s], 2 * C + head * D, j * BKV, b);
-        if (++s == KV_ST) { s = 0; ph ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV);
-      constexpr uint32_t idesc_o = make_idesc_bf16(BQ, D) | (1u << 16);     // V is an MN-major B operand
-      auto issue_s = [&](int g, int j, int s) {
-        const uint64_t qdesc = make_kmajor_desc<64>(smem_u32(smem + OFF_Q + g * Q_BYTES));
-        const uint64_t kdesc = make_kmajor_desc<64>(smem_u32(smem + OFF_K + s * K_BYTES));
-        const uint32_t d = tmem_base + (g * 2 + (j & 1)) * 128;
-        umma_bf16_ss(d, qdesc, kdesc, idesc_s, 0);
-        umma_bf16_ss(d, qdesc + 2, kdesc + 2, idesc_s, 1);
-        umma_commit(&s_ready[g * 2 + (j & 1)]);
-      };
-      mbar_wait(q_full, 0);
-      int s = 0;                         // stage of tile j
-      int s1 = 0; uint32_t ph1 = 0;      // stage / phase of tile j+1
-      mbar_wait(&kv_full[0], 0);
-      tcgen05_fence_after();
-      issue_s(0, 0, 0);
-      issue_s(1, 0, 0);
-      if (++s1 == KV_ST) { s1 = 0; ph1 ^= 1; }
-      for (int j = 0; j < nkv; ++j) {
-        if (j + 1 < nkv) {
-          mbar_wait(&kv_full[s1], ph1);
-          for (int g = 0; g < 2; ++g) {
-            if (j >= 1) mbar_wait(&o_free[g], (j - 1) & 1);   // S_g(j+1) reuses the buffer of S_g(j-1) / O_g(j-1)
-            tcgen05_fence_after();
-            issue_s(g, j + 1, s1);
-          }
-          if (++s1 == KV_ST) { s1 = 0; ph1 ^= 1; }
-        }
-        const uint64_t vdesc = make_kmajor_desc<64>(smem_u32(smem + OFF_V + s * K_BYTES));
-        for (int g = 0; g < 2; ++g) {
-          mbar_wait(&p_ready[g], j & 1);
-          tcgen05_fence_after();
-          const uint64_t pdesc = make_kmajor_desc<128>(smem_u32(smem + OFF_P + g * P_BYTES));
-          const uint32_t dO = tmem_base + (g * 2 + (j & 1)) * 128;
-#pragma unroll
-          for (int kk = 0; kk < BKV / 16; ++kk) {
-            const uint64_t pa = pdesc + (uint64_t)(((kk >> 2) * (P_BYTES / 2) + (kk & 3) * 32) >> 4);
-            const uint64_t vb = vdesc + (uint64_t)((kk * 1024) >> 4);
-            umma_bf16_ss(dO, pa, vb, idesc_o, kk != 0);
-          }
-          umma_commit(&o_ready[g]);
-        }
-        umma_commit(&kv_empty[s]);
-        if (++s == KV_ST) s = 0;
-      }
-    }
-  }
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-    const int g = (warp - 4) >> 2;                 // softmax group = query tile
-    const int qd = warp & 3;                       // TMEM lane quadrant
-    const int row = qd * 32 + lane;                // row inside the 128-row tile
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + g * 256;
-    constexpr float LOG2E = 1.4426950408889634f;
-    float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
-    float o[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) o[i] = 0.f;
-    uint8_t* prow = smem + OFF_P + g * P_BYTES + row * 128;
-    for (int j = 0; j < nkv; ++j) {
-      const uint32_t tS = trow + (j & 1) * 128;
-      mbar_wait(&s_ready[g * 2 + (j & 1)], (j >> 1) & 1);
-      tcgen05_fence_after();
-      uint32_t sv[4][32];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_32x32b_x32(tS + c * 32, sv[c]);
-      tmem_ld_wait();
-      float m0 = m, m1 = m, m2 = m, m3 = m;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          m0 = max3(m0, __uint_as_float(sv[c][8 * i + 0]), __uint_as_float(sv[c][8 * i + 1]));
-          m1 = max3(m1, __uint_as_float(sv[c][8 * i + 2]), __uint_as_float(sv[c][8 * i + 3]));
-          m2 = max3(m2, __uint_as_float(sv[c][8 * i + 4]), __uint_as_float(sv[c][8 * i + 5]));
-          m3 = max3(m3, __uint_as_float(sv[c][8 * i + 6]), __uint_as_float(sv[c][8 * i + 7]));
-        }
-      }
-      const float mx = max3(fmaxf(m0, m1), m2, m3);
-      const float alpha = ex2((m - mx) * LOG2E);
-      m = mx;
-      const float mb = mx * LOG2E;
-      if (j > 0) {
-        // fold O_tile(j-1); this also guarantees PV(j-1) has finished reading P before it is rewritten below
-        mbar_wait(&o_ready[g], (j - 1) & 1);
-        tcgen05_fence_after();
-        uint32_t raw[32];
-        tmem_ld_32x32b_x32(trow + ((j - 1) & 1) * 128, raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < D; ++i) o[i] = o[i] * alpha_prev + __uint_as_float(raw[i]);
-        tcgen05_fence_before();
-        mbar_arrive(&o_free[g]);
-      }
-      alpha_prev = alpha;
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          const float p0 = ex2(fmaf(__uint_as_float(sv[c][2 * i]), LOG2E, -mb));
-          const float p1 = ex2(fmaf(__uint_as_float(sv[c][2 * i + 1]), LOG2E, -mb));
-          const float p2 = ex2(fmaf(__uint_as_float(sv[c][2 * i + 2]), LOG2E, -mb));
-          const float p3 = ex2(fmaf(__uint_as_float(sv[c][2 * i + 3]), LOG2E, -mb));
-          s0 += p0; s1 += p1; s2 += p2; s3 += p3;
-          pk[i] = pack_bf16(p0, p1);
-          pk[i + 1] = pack_bf16(p2, p3);
-        }
-        uint8_t* base = prow + (c >> 1) * (P_BYTES / 2);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int chunk = ((c & 1) * 4 + i) ^ (row & 7);
-          *reinterpret_cast<uint4*>(base + chunk * 16) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-        }
-      }
-      l = l * alpha + ((s0 + s1) + (s2 + s3));
-      fence_proxy_async();
-      tcgen05_fence_before();
-      mbar_arrive(&p_ready[g]);
-    }
-    mbar_wait(&o_ready[g], (nkv - 1) & 1);
-    tcgen05_fence_after();
-    {
-      uint32_t raw[32];
-      tmem_ld_32x32b_x32(trow + ((nkv - 1) & 1) * 128, raw);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < D; ++i) o[i] = o[i] * alpha_prev + __uint_as_float(raw[i]);
-    }
-    tcgen05_fence_before();
-    const float inv = 1.f / l;
-    bf16* op = out + ((size_t)b * T + q0 + g * 128 + row) * out_ld + head * D;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 u;
-      u.x = pack_bf16(o[8 * i + 0] * inv, o[8 * i + 1] * inv);
-      u.y = pack_bf16(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
-      u.z = pack_bf16(o[8 * i + 4] * inv, o[8 * i + 5] * inv);
-      u.w = pack_bf16(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
-      reinterpret_cast<uint4*>(op)[i] = u;
-    }
-  }
-  __syncthreads();
-  if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
-}
-
-}  // namespace v3
 
 // =====================================================================================================
 // v4: NG 128-row query tiles per CTA (one softmax warpgroup each) sharing every K/V tile of BKV_ keys; nothing in
@@ -1007,25 +617,6 @@ void launch(const bf16* q, int q_ld, int q_col, const bf16* kv, int kv_ld, int k
 
 }  // namespace
 
-void launch_attention_d32(const bf16* qk, const bf16* vt, const View& out, int B, int T, int heads, cudaStream_t s) {
-  const int C = heads * D;
-  LIDM_REQUIRE(T % 128 == 0, "attention: T must be a multiple of 128");
-  LIDM_REQUIRE(out.hl == 0 && out.hr == 0 && out.H * out.W == T && out.B == B && out.C == C, "attention out view");
-  LIDM_REQUIRE(out.ld % 8 == 0, "attention out ld");
-  static bool configured = false;
-  if (!configured) {
-    LIDM_CUDA_CHECK(cudaFuncSetAttribute(attention_d32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    configured = true;
-  }
-  CUtensorMap tmQK = make_tma_3d(qk, 2 * C, T, B, (uint64_t)2 * C * 2, (uint64_t)T * 2 * C * 2, D, 128, 64);
-  CUtensorMap tmVT = make_tma_3d(vt, T, C, B, (uint64_t)T * 2, (uint64_t)C * T * 2, 64, D, 128);
-  dim3 grid(T / BQ, heads, B);
-  attention_d32_kernel<<<grid, 192, SMEM_TOTAL, s>>>(tmQK, tmVT, out.p, out.ld, T, C);
-  LIDM_CUDA_CHECK(cudaGetLastError());
-  LIDM_COUNT_LAUNCH(1);
-}
-
-// qkv: (B, T, 3C) bf16 = [q (all heads) | k | v], q and k pre-scaled by ch^-1/4
 void launch_attention_d32_packed(const bf16* qkv, const View& out, int B, int T, int heads, cudaStream_t s) {
   const int C = heads * D;
   LIDM_REQUIRE(T % 128 == 0, "attention: T must be a multiple of 128");
@@ -1038,28 +629,14 @@ void launch_attention_d32_packed(const bf16* qkv, const View& out, int B, int T,
     configured = true;
   }
   CUtensorMap tm = make_tma_3d(qkv, 3 * C, T, B, (uint64_t)3 * C * 2, (uint64_t)T * 3 * C * 2, D, 128, 64);
-  static const bool use_v2 = getenv("LIDM_ATTN_V2") != nullptr;
-  static const bool use_v3 = getenv("LIDM_ATTN_V3") != nullptr;
   // LIDM_ATTN_V4=1 moves a quarter of the exponentials onto the FMA pipe (ex2_poly); measured slower on B200 (the
-  // softmax warps are issue/latency bound, not MUFU bound), so it stays off by default.
+  // softmax warps are issue/latency bound, not MUFU bound), so it stays off by default.  LIDM_ATTN_V2 forces the
+  // one-tile-per-CTA kernel (the T = 128 path) everywhere.
+  static const bool use_v2 = getenv("LIDM_ATTN_V2") != nullptr;
   static const int v4_mode = getenv("LIDM_ATTN_V4") ? atoi(getenv("LIDM_ATTN_V4")) : 0;
-  if (!use_v2 && !use_v3 && T % 256 == 0) {
+  if (!use_v2 && T % 256 == 0) {
     if (v4_mode == 1) v4::launch<2, 128, true>(qkv, 3 * C, 0, qkv, 3 * C, C, 2 * C, T, out, B, T, heads, s);
     else v4::launch<2, 128, false>(qkv, 3 * C, 0, qkv, 3 * C, C, 2 * C, T, out, B, T, heads, s);
-    return;
-  }
-  if (T % 256 == 0 && !use_v2) {
-    static bool configured3 = false;
-    if (!configured3) {
-      LIDM_CUDA_CHECK(cudaFuncSetAttribute(v3::attention_d32_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           v3::SMEM_TOTAL));
-      configured3 = true;
-    }
-    CUtensorMap tmQ = make_tma_3d(qkv, 3 * C, T, B, (uint64_t)3 * C * 2, (uint64_t)T * 3 * C * 2, D, 256, 64);
-    dim3 grid3(T / 256, heads, B);
-    v3::attention_d32_v3_kernel<<<grid3, 384, v3::SMEM_TOTAL, s>>>(tmQ, tm, out.p, out.ld, T, C);
-    LIDM_CUDA_CHECK(cudaGetLastError());
-    LIDM_COUNT_LAUNCH(1);
     return;
   }
   dim3 grid(T / BQ, heads, B);

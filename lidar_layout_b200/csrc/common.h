@@ -125,8 +125,6 @@ void launch_groupnorm(const View& x, const View& y, const float* gamma, const fl
 constexpr int GN_MAX_CHUNKS = 64;
 
 // ---- attention (attention.cu) ----------------------------------------------------------------------------
-// qk: (B, T, 2C) bf16 [q(all heads) | k(all heads)], vt: (B, C, T) bf16, out: (B, T, C) view (channel = head*32+c)
-void launch_attention_d32(const bf16* qk, const bf16* vt, const View& out, int B, int T, int heads, cudaStream_t s);
 // qkv: (B, T, 3C) bf16 = [q | k | v] (plain qkv GEMM output); V consumed as an MN-major tcgen05 operand
 void launch_attention_d32_packed(const bf16* qkv, const View& out, int B, int T, int heads, cudaStream_t s);
 

@@ -620,44 +620,23 @@ struct Builder {
   // AttentionBlock._forward + QKVAttentionLegacy (openaimodel.py:320-326, 358-374)
   void attn_block(const AttnW& a, const View& x, const View& dst) {
     const int B = x.B, H = x.H, W = x.W, C = a.ch, T = H * W;
-    Buf bg, bqk, bvt, ba;
+    Buf bg, bqk, ba;
     View g = act(B, H, W, C, 0, 0, &bg);
     groupnorm(x, g, a.n, 1e-5f, false);
-    static const bool legacy = getenv("LIDM_ATTN_LEGACY") != nullptr;
     const int heads = a.heads;
-    View ao;
-    if (legacy) {
-      View qk = act(B, H, W, 2 * C, 0, 0, &bqk);
-      bf16* vt = raw<bf16>((size_t)B * C * T, &bvt);
-      {
-        GemmEpilogue ep;
-        ep.bias = a.qkv.bias;
-        ep.out = qk;
-        ep.split_n = 2 * C;
-        ep.out_t = vt;
-        gemm(g, taps_1x1(), a.qkv, ep);
-      }
-      release(bg);
-      ao = act(B, H, W, C, 0, 0, &ba);
-      op([=](cudaStream_t s) { launch_attention_d32(qk.p, vt, ao, B, T, heads, s); }, PROF_ATTN,
-         4.0 * B * heads * (double)T * T * 32);
-      release(bqk);
-      release(bvt);
-    } else {
-      // one packed (B,T,3C) = [q | k | v] tensor straight out of the qkv GEMM (TMA-store epilogue)
-      View qkv = act(B, H, W, 3 * C, 0, 0, &bqk);
-      {
-        GemmEpilogue ep;
-        ep.bias = a.qkv.bias;
-        ep.out = qkv;
-        gemm(g, taps_1x1(), a.qkv, ep);
-      }
-      release(bg);
-      ao = act(B, H, W, C, 0, 0, &ba);
-      op([=](cudaStream_t s) { launch_attention_d32_packed(qkv.p, ao, B, T, heads, s); }, PROF_ATTN,
-         4.0 * B * heads * (double)T * T * 32, 0, "attn T" + std::to_string(T) + " heads" + std::to_string(heads));
-      release(bqk);
+    // one packed (B,T,3C) = [q | k | v] tensor straight out of the qkv GEMM (TMA-store epilogue)
+    View qkv = act(B, H, W, 3 * C, 0, 0, &bqk);
+    {
+      GemmEpilogue ep;
+      ep.bias = a.qkv.bias;
+      ep.out = qkv;
+      gemm(g, taps_1x1(), a.qkv, ep);
     }
+    release(bg);
+    View ao = act(B, H, W, C, 0, 0, &ba);
+    op([=](cudaStream_t s) { launch_attention_d32_packed(qkv.p, ao, B, T, heads, s); }, PROF_ATTN,
+       4.0 * B * heads * (double)T * T * 32, 0, "attn T" + std::to_string(T) + " heads" + std::to_string(heads));
+    release(bqk);
     {
       GemmEpilogue ep;
       ep.bias = a.proj.bias;
@@ -1876,8 +1855,8 @@ int guarded(lidm_handle* h, F&& f) {
 }
 
 __global__ void qkv_legacy_to_internal_kernel(const float* __restrict__ qkv, int B, int heads, int T, float scale,
-                                              bf16* __restrict__ qk, bf16* __restrict__ vt, int packed) {
-  // qkv: (B, heads*96, T) with channel = head*96 + part*32 + c
+                                              bf16* __restrict__ out) {
+  // qkv: (B, heads*96, T) with channel = head*96 + part*32 + c  ->  packed (B, T, 3C) bf16 = [q | k | v], q and k scaled
   const int C = heads * 32;
   const int64_t total = (int64_t)B * heads * 96 * T;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1887,12 +1866,7 @@ __global__ void qkv_legacy_to_internal_kernel(const float* __restrict__ qkv, int
     const int b = (int)(r / (heads * 96));
     const int hd = chn / 96, part = (chn % 96) / 32, c = chn % 32;
     const float v = qkv[i];
-    if (packed) {
-      qk[((size_t)b * T + t) * (3 * C) + part * C + hd * 32 + c] = __float2bfloat16(part < 2 ? v * scale : v);
-      continue;
-    }
-    if (part < 2) qk[((size_t)b * T + t) * (2 * C) + part * C + hd * 32 + c] = __float2bfloat16(v * scale);
-    else vt[((size_t)b * C + hd * 32 + c) * T + t] = __float2bfloat16(v);
+    out[((size_t)b * T + t) * (3 * C) + part * C + hd * 32 + c] = __float2bfloat16(part < 2 ? v * scale : v);
   }
 }
 
@@ -2335,16 +2309,13 @@ int lidm_op_qkv_attention_legacy(const float* qkv, int32_t B, int32_t heads, int
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     const int C = heads * 32;
     TmpBufs tmp;
-    static const bool legacy = getenv("LIDM_ATTN_LEGACY") != nullptr;
     bf16* qk = tmp.get<bf16>((size_t)B * T * 3 * C);
-    bf16* vt = tmp.get<bf16>((size_t)B * C * T);
     const float scale = 1.0f / std::sqrt(std::sqrt(32.0f));
-    qkv_legacy_to_internal_kernel<<<148 * 8, 256, 0, s>>>(qkv, B, heads, T, scale, qk, vt, legacy ? 0 : 1);
+    qkv_legacy_to_internal_kernel<<<148 * 8, 256, 0, s>>>(qkv, B, heads, T, scale, qk);
     LIDM_CUDA_CHECK(cudaGetLastError());
     View o; o.B = B; o.H = T / 128; o.W = 128; o.C = C; o.ld = C;
     o.p = tmp.get<bf16>((size_t)B * T * C);
-    if (legacy) launch_attention_d32(qk, vt, o, B, T, heads, s);
-    else launch_attention_d32_packed(qk, o, B, T, heads, s);
+    launch_attention_d32_packed(qk, o, B, T, heads, s);
     launch_nhwc_bf16_to_f32_nchw(o, out, s);
     LIDM_CUDA_CHECK(cudaStreamSynchronize(s));
   });
