@@ -54,6 +54,14 @@ struct View {
   // row pitch in pixels of `ld` elements when it differs from W + hl + hr (GEMM outputs only): lets a GEMM write every
   // second pixel of every second row of a 2x larger tensor (ld = 2 * ld_big, wpitch = 2 * W_big / 2 ... see Builder::up)
   int wpitch = 0;
+  // GroupNorm statistics produced by the GEMM that wrote this tensor: per (sample, 128-pixel tile, 8-channel granule)
+  // partial (sum, sum of squares) of the stored bf16 values, layout gst[(b * gst_slots + slot) * gst_ld + granule * 2 + {0,1}]
+  // with `gst` already offset to the first granule of this (channel-sliced) view; null => none
+  float* gst = nullptr;
+  float* gst_base = nullptr;   // start of the statistics buffer (granule 0 of the underlying tensor): plan-time bookkeeping
+  int gst_ld = 0;      // floats per (sample, slot) row = 2 * granules of the underlying buffer
+  int gst_slots = 0;   // slots per sample (= H * W / 128 of the buffer)
+  int gst_slot0 = 0;   // first slot this GEMM writes (output parity of a folded upsample conv)
   int Cphys() const { return cphys ? cphys : (lo_off ? lo_off + C : C); }
   int Wp() const { return W + hl + hr; }
   int pitch() const { return wpitch ? wpitch : Wp(); }
@@ -119,10 +127,17 @@ struct GemmB {
 void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wt, int N, const GemmEpilogue& ep,
                       cudaStream_t stream);
 
+// True when launch_conv_gemm will take the TMA-store epilogue for this output, the one that can also emit the
+// GroupNorm granule statistics of View::gst.
+bool conv_gemm_emits_gstats(const GemmEpilogue& ep, int n_alloc);
+
 // ---- normalisation (norm.cu) -----------------------------------------------------------------------------
 void launch_groupnorm(const View& x, const View& y, const float* gamma, const float* beta, float eps, int groups,
                       bool silu, float* partials /* workspace >= B*groups*2*GN_MAX_CHUNKS floats */, cudaStream_t s);
 constexpr int GN_MAX_CHUNKS = 64;
+// same, with the statistics taken from x.gst (written by the producing GEMMs' epilogues): one pass over x
+void launch_groupnorm_from_gstats(const View& x, const View& y, const float* gamma, const float* beta, float eps, int groups,
+                                  bool silu, cudaStream_t s);
 
 // ---- attention (attention.cu) ----------------------------------------------------------------------------
 // qkv: (B, T, 3C) bf16 = [q | k | v] (plain qkv GEMM output); V consumed as an MN-major tcgen05 operand

@@ -339,14 +339,48 @@ struct Builder {
   Plan* P;
   ArenaPlanner ap;
   bool dry;
+  // GroupNorm statistics written by GEMM epilogues (View::gst): which 8-channel granules of each statistics buffer have
+  // been produced so far in plan order; a GroupNorm whose whole input is covered skips its statistics pass
+  std::map<const float*, std::vector<char>> gst_cover;
+  bool gst_enabled = getenv("LIDM_NO_GN_FUSE") == nullptr;
 
   View act(int B, int H, int W, int C, int hl, int hr, Buf* buf) {
     View v;
     v.B = B; v.H = H; v.W = W; v.C = C; v.hl = hl; v.hr = hr; v.ld = C;
-    buf->bytes = (size_t)B * H * (W + hl + hr) * C * sizeof(bf16);
+    const size_t act_bytes = align_up((size_t)B * H * (W + hl + hr) * C * sizeof(bf16), 256);
+    // halo-free tensors made of whole 128-pixel tiles get a statistics side buffer [B][H*W/128][C/8][2] floats
+    const bool want_gst = gst_enabled && h->cfg.precision == 0 && hl == 0 && hr == 0 && C % 8 == 0 && (H * W) % 128 == 0;
+    const size_t gst_bytes = want_gst ? (size_t)B * (H * W / 128) * (C / 8) * 2 * sizeof(float) : 0;
+    buf->bytes = act_bytes + gst_bytes;
     buf->off = ap.alloc(buf->bytes);
     v.p = reinterpret_cast<bf16*>(P->arena + buf->off);
+    if (want_gst) {
+      v.gst = reinterpret_cast<float*>(P->arena + buf->off + act_bytes);
+      v.gst_ld = (C / 8) * 2;
+      v.gst_slots = H * W / 128;
+      gst_cover[v.gst] = std::vector<char>(C / 8, 0);
+      v.gst_base = v.gst;
+    }
     return v;
+  }
+  bool gst_covered(const View& x) const {
+    if (x.gst == nullptr || x.gst_base == nullptr || x.C % 8 != 0) return false;
+    auto it = gst_cover.find(x.gst_base);
+    if (it == gst_cover.end()) return false;
+    const int g0 = (int)((x.gst - x.gst_base) / 2);
+    for (int g = g0; g < g0 + x.C / 8; ++g)
+      if (g >= (int)it->second.size() || !it->second[g]) return false;
+    return true;
+  }
+  void gst_mark(const View& o, int N, int slot0, int nslots) {
+    // a buffer is covered granule by granule; parity-strided outputs (folded upsample) cover a granule only once all four
+    // parities have been written, which up_folded does back to back, so marking on the last parity is enough
+    if (o.gst == nullptr || o.gst_base == nullptr) return;
+    if (slot0 + nslots < o.gst_slots) return;
+    auto it = gst_cover.find(o.gst_base);
+    if (it == gst_cover.end()) return;
+    const int g0 = (int)((o.gst - o.gst_base) / 2);
+    for (int g = g0; g < g0 + N / 8 && g < (int)it->second.size(); ++g) it->second[g] = 1;
   }
   template <class T>
   T* raw(size_t n, Buf* buf) {
@@ -368,12 +402,22 @@ struct Builder {
     View s = v;
     s.p = v.p + c0;
     s.C = C;
+    if (v.gst != nullptr) s.gst = (c0 % 8 == 0) ? v.gst + (c0 / 8) * 2 : nullptr;
     return s;
   }
 
-  void gemm(const View& a, const ConvTaps& taps, const ConvW& w, const GemmEpilogue& ep) {
+  // decide at plan time whether this GEMM's epilogue also writes the GroupNorm statistics of its output
+  void prep_gst(GemmEpilogue& ep, int N, int n_alloc) {
+    if (ep.out.gst == nullptr) return;
+    if (N % 8 == 0 && conv_gemm_emits_gstats(ep, n_alloc)) gst_mark(ep.out, N, ep.out.gst_slot0, ep.out.H * ep.out.W / 128);
+    else ep.out.gst = nullptr;
+  }
+
+  void gemm(const View& a, const ConvTaps& taps, const ConvW& w, const GemmEpilogue& ep_in) {
     GemmB b; b.p = w.w; b.n_alloc = w.n_alloc; b.ld = w.k_alloc; b.nseg = w.nseg;
     const int N = w.cout;
+    GemmEpilogue ep = ep_in;
+    prep_gst(ep, N, w.n_alloc);
     op([=](cudaStream_t s) { launch_conv_gemm(a, taps, b, N, ep, s); }, PROF_GEMM, gemm_flops(a, taps.n, N) * w.nseg, 0,
        gemm_label(a, taps.n * w.nseg, N));
   }
@@ -568,8 +612,15 @@ struct Builder {
   }
   void groupnorm(const View& x, const View& y, const NormW& n, float eps, bool silu) {
     Plan* P_ = P;
+    const std::string label = "gn C" + std::to_string(x.C) + " @" + std::to_string(x.H) + "x" + std::to_string(x.W);
+    if (x.C % 32 == 0 && (x.C / 32) % 8 == 0 && x.hl == 0 && x.hr == 0 && gst_covered(x)) {
+      // every producer of x left its granule statistics behind: one pass (read x, write y)
+      op([=](cudaStream_t s) { launch_groupnorm_from_gstats(x, y, n.gamma, n.beta, eps, 32, silu, s); }, PROF_NORM, 0,
+         4.0 * x.B * x.H * x.W * x.C, label);
+      return;
+    }
     op([=](cudaStream_t s) { launch_groupnorm(x, y, n.gamma, n.beta, eps, 32, silu, P_->gn_partials, s); }, PROF_NORM, 0,
-       4.0 * x.B * x.H * x.W * x.C, "gn C" + std::to_string(x.C) + " @" + std::to_string(x.H) + "x" + std::to_string(x.W));
+       4.0 * x.B * x.H * x.W * x.C, label);
   }
 
   // ResBlock._forward (openaimodel.py:256-276) / ResnetBlock.forward (model_lidm.py:127-147, temb None)
@@ -583,6 +634,7 @@ struct Builder {
       GemmEpilogue ep;
       ep.bias = r.c1.bias;
       ep.out = hmid;
+      prep_gst(ep, r.cout, r.c1.n_alloc);
       GemmB b; b.p = r.c1.w; b.n_alloc = r.c1.n_alloc; b.ld = r.c1.k_alloc;
       const ConvTaps taps = taps_rect(kh, kw, pl, pt);
       const int N = r.cout, emb_off = r.emb_off;
@@ -680,7 +732,7 @@ struct Builder {
       View pv; pv.p = Pm; pv.B = B; pv.H = T / 128; pv.W = 128; pv.C = T; pv.ld = T;
       GemmB vb; vb.p = vt; vb.n_alloc = C; vb.ld = T; vb.batch_stride = (int64_t)C * T;
       GemmEpilogue ep;
-      View o2 = ao; o2.H = T / 128; o2.W = 128;
+      View o2 = ao; o2.H = T / 128; o2.W = 128; o2.gst = nullptr;
       ep.out = o2;
       op([=](cudaStream_t s) { launch_conv_gemm(pv, taps_1x1(), vb, C, ep, s); }, PROF_GEMM, gemm_flops(pv, 1, C));
     }
@@ -824,6 +876,7 @@ struct Builder {
         o.p = dst.p + (size_t)(py * dst.W + px) * dst.ld;
         o.ld = 2 * dst.ld;
         o.wpitch = dst.W;                 // one output row pair = 2 * dst.W pixels of dst.ld = dst.W pixels of 2 * dst.ld
+        o.gst_slot0 = (py * 2 + px) * (x.H * x.W / 128);   // each parity fills its own quarter of the statistics slots
         GemmEpilogue ep;
         ep.bias = c.bias;
         ep.out = o;

@@ -45,6 +45,8 @@ struct GemmKernelParams {
   int out_f32_ld;            // channel stride of out_f32_nhwc (concat views)
   bf16* out;
   int out_ld, out_hl, out_hr, out_Wp;
+  float* gst;                // GroupNorm granule statistics of the output (View::gst), or null
+  int gst_ld, gst_slots, gst_slot0;
   int split_n;
   bf16* out_t;
   float* out_f32_nchw;
@@ -289,6 +291,40 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 tma_store_4d(&tmO, stage_out + j * (BM * 128), n0 + j * 64, w0, h0, b);
             tma_store_commit();
           }
+          if (p.gst != nullptr) {
+            // GroupNorm statistics of this tile from the staged (bf16-rounded) values: TPG consecutive lanes share one
+            // 8-channel granule and walk rows sub, sub + TPG, ...; fixed-order shuffle tree -> deterministic
+            // (8 lanes per granule whatever the tile width, so the summation order — and with it the result, bit for
+            // bit — does not depend on which BN the launcher picked for this batch size)
+            constexpr int GRAN = BN / 8;
+            constexpr int TPG = 8;
+            const int gi = e / TPG, sub = e % TPG;
+            float gs = 0.f, gq = 0.f;
+            if (gi < GRAN) {
+              const uint8_t* gbox = stage_out + (gi >> 3) * (BM * 128);
+#pragma unroll 4
+              for (int rr = sub; rr < BM; rr += TPG) {
+                const uint4 u = *reinterpret_cast<const uint4*>(gbox + rr * 128 + (((gi & 7) ^ (rr & 7)) << 4));
+                const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 f = unpack_bf16(uu[i]);
+                  gs += f.x + f.y;
+                  gq += f.x * f.x + f.y * f.y;
+                }
+              }
+            }
+#pragma unroll
+            for (int o = TPG / 2; o > 0; o >>= 1) {
+              gs += __shfl_xor_sync(0xffffffffu, gs, o);
+              gq += __shfl_xor_sync(0xffffffffu, gq, o);
+            }
+            if (sub == 0 && gi < GRAN && n0 + gi * 8 < p.N) {
+              float* dst = p.gst + ((size_t)b * p.gst_slots + p.gst_slot0 + r) * p.gst_ld + (size_t)(n0 / 8 + gi) * 2;
+              dst[0] = gs;
+              dst[1] = gq;
+            }
+          }
           continue;
         }
       }
@@ -463,6 +499,11 @@ void launch_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtens
 
 }  // namespace
 
+bool conv_gemm_emits_gstats(const GemmEpilogue& ep, int n_alloc) {
+  return ep.out.p != nullptr && ep.out.gst != nullptr && ep.out.hl == 0 && ep.out.hr == 0 && ep.out_t == nullptr &&
+         n_alloc % 64 == 0 && ep.res_f32 == nullptr && ep.out_f32_nhwc == nullptr && ep.out_f32_nchw == nullptr;
+}
+
 void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int N, const GemmEpilogue& ep,
                       cudaStream_t stream) {
   const bf16* wt = wtb.p;
@@ -549,6 +590,11 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
                                 ? 1 : 0;
   CUtensorMap tmO = tmA;
   if (use_tma_store) tmO = make_tma_act(ep.out, 64, Wbox, Hbox, 128);
+  if (use_tma_store && ep.out.gst != nullptr) {
+    LIDM_REQUIRE(Wbox * Hbox == 128 && N % 8 == 0 && ep.out.gst_slots >= ep.out.gst_slot0 + p.tiles_per_img,
+                 "GroupNorm statistics need whole 128-pixel tiles inside one sample");
+    p.gst = ep.out.gst; p.gst_ld = ep.out.gst_ld; p.gst_slots = ep.out.gst_slots; p.gst_slot0 = ep.out.gst_slot0;
+  }
   if (BN == 256) launch_persist<256, 3>(tmA, tmB, tmO, p, num_m_tiles, num_tiles, use_tma_store, stream);
   else if (BN == 128) launch_persist<128, 4>(tmA, tmB, tmO, p, num_m_tiles, num_tiles, use_tma_store, stream);
   else if (BN == 64) launch_persist<64, 6>(tmA, tmB, tmO, p, num_m_tiles, num_tiles, use_tma_store, stream);

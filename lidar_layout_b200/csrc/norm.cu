@@ -90,7 +90,7 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, int H, int W, int hl
   }
 }
 
-__device__ __forceinline__ float silu_f(float v) { return v / (1.f + __expf(-v)); }
+__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.f + __expf(-v)); }
 
 __global__ void gn_apply_kernel(const bf16* __restrict__ x, int H, int W, int xhl, int xWp, int xld, bf16* __restrict__ y,
                                 int yhl, int yhr, int yWp, int yld, int C, int cpg, int groups,
@@ -162,6 +162,83 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int H, int W, int xh
 // vectors in registers between the statistics and the normalisation, so x is read once and y written once (4 bytes per
 // element instead of 6) in a single launch.  Reductions run in a fixed order (per-thread partials -> fixed lane
 // assignment -> xor-shuffle tree): bit-reproducible and, one sample per CTA, independent of the batch size.
+// gn_apply with the statistics reduced from the producers' granule partials (View::gst) instead of a stats pass.
+__global__ void gn_apply_gst_kernel(const bf16* __restrict__ x, int H, int W, int xhl, int xWp, int xld, bf16* __restrict__ y,
+                                    int yhl, int yhr, int yWp, int yld, int C, int cpg, int groups,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
+                                    const float* __restrict__ gst, int gst_ld, int gst_slots, int pix_per_cta) {
+  extern __shared__ float sh[];  // mean[groups], rstd[groups]
+  const int b = blockIdx.y;
+  const int HW = H * W;
+  const int gpg = cpg >> 3;      // granules per group
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float s = 0.f, q = 0.f;
+    const float2* pp = reinterpret_cast<const float2*>(gst + (size_t)b * gst_slots * gst_ld) + (size_t)g * gpg;
+    const int row2 = gst_ld >> 1;
+    int sl = 0;
+    for (; sl + 4 <= gst_slots; sl += 4) {          // 4 slots' loads in flight; summed in slot order
+      for (int k = 0; k < gpg; ++k) {
+        const float2 a0 = __ldg(pp + (size_t)sl * row2 + k), a1 = __ldg(pp + (size_t)(sl + 1) * row2 + k),
+                     a2 = __ldg(pp + (size_t)(sl + 2) * row2 + k), a3 = __ldg(pp + (size_t)(sl + 3) * row2 + k);
+        s += a0.x; q += a0.y; s += a1.x; q += a1.y; s += a2.x; q += a2.y; s += a3.x; q += a3.y;
+      }
+    }
+    for (; sl < gst_slots; ++sl)
+      for (int k = 0; k < gpg; ++k) { const float2 a = __ldg(pp + (size_t)sl * row2 + k); s += a.x; q += a.y; }
+    const float n = (float)HW * (float)cpg;
+    const float mean = s / n;
+    const float var = fmaxf(q / n - mean * mean, 0.f);
+    sh[g] = mean;
+    sh[groups + g] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  const int vec_per_pix = C >> 3;
+  const int cv = threadIdx.x % vec_per_pix;
+  const int prow = threadIdx.x / vec_per_pix;
+  const int pstride = blockDim.x / vec_per_pix;
+  if (prow >= pstride) return;
+  float sc[8], sf[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cv * 8 + j;
+    const int g = c / cpg;
+    const float ga = __ldg(gamma + c) * sh[groups + g];
+    sc[j] = ga;
+    sf[j] = __ldg(beta + c) - sh[g] * ga;
+  }
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(HW, p0 + pix_per_cta);
+  auto addr = [&](int pix) {
+    const int h = pix / W, w = pix - h * W;
+    return reinterpret_cast<const uint4*>(x + ((size_t)(b * H + h) * xWp + (w + xhl)) * xld) + cv;
+  };
+  auto emit = [&](int pix, const uint4& u) {
+    const int h = pix / W, w = pix - h * W;
+    const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+    uint32_t oo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = unpack_bf16(uu[i]);
+      float a = f.x * sc[2 * i] + sf[2 * i];
+      float c = f.y * sc[2 * i + 1] + sf[2 * i + 1];
+      if (silu) { a = silu_f(a); c = silu_f(c); }
+      oo[i] = pack_bf16(a, c);
+    }
+    const uint4 o = make_uint4(oo[0], oo[1], oo[2], oo[3]);
+    const size_t rowbase = (size_t)(b * H + h) * yWp;
+    reinterpret_cast<uint4*>(y + (rowbase + w + yhl) * yld)[cv] = o;
+    if (w < yhr) reinterpret_cast<uint4*>(y + (rowbase + W + yhl + w) * yld)[cv] = o;
+    if (w >= W - yhl) reinterpret_cast<uint4*>(y + (rowbase + (w - (W - yhl))) * yld)[cv] = o;
+  };
+  int pix = p0 + prow;
+  for (; pix + 3 * pstride < p1; pix += 4 * pstride) {
+    const uint4 u0 = __ldg(addr(pix)), u1 = __ldg(addr(pix + pstride)), u2 = __ldg(addr(pix + 2 * pstride)),
+                u3 = __ldg(addr(pix + 3 * pstride));
+    emit(pix, u0); emit(pix + pstride, u1); emit(pix + 2 * pstride, u2); emit(pix + 3 * pstride, u3);
+  }
+  for (; pix < p1; pix += pstride) emit(pix, __ldg(addr(pix)));
+}
+
 template <int NV>
 __global__ void __launch_bounds__(512)
 gn_fused_kernel(const bf16* __restrict__ x, int H, int W, int xhl, int xWp, int xld, bf16* __restrict__ y, int yhl, int yhr,
@@ -334,6 +411,34 @@ void launch_groupnorm(const View& x, const View& y, const float* gamma, const fl
                                                  pix_per_cta);
   LIDM_CUDA_CHECK(cudaGetLastError());
   LIDM_COUNT_LAUNCH(2);
+}
+
+void launch_groupnorm_from_gstats(const View& x, const View& y, const float* gamma, const float* beta, float eps, int groups,
+                                  bool silu, cudaStream_t s) {
+  const int C = x.C;
+  LIDM_REQUIRE(x.gst != nullptr && C % groups == 0 && (C / groups) % 8 == 0, "granule statistics need 8 | channels per group");
+  LIDM_REQUIRE(y.C == C && y.B == x.B && y.H == x.H && y.W == x.W && x.ld % 8 == 0 && y.ld % 8 == 0, "GroupNorm shapes");
+  const int cpg = C / groups;
+  const int vec = C / 8;
+  int threads = (256 % vec == 0) ? 256 : ((384 % vec == 0) ? 384 : 0);
+  if (threads == 0) { LIDM_REQUIRE(vec <= 1024, "C too large"); threads = vec; }
+  const int HW = x.H * x.W;
+  const int pstride = threads / vec;
+  // no reduction in this kernel, so the split is free to depend on the batch: aim at one resident wave of CTAs
+  const int resident = 148 * (2048 / threads);
+  int nchunks = resident / x.B;
+  if (nchunks < 1) nchunks = 1;
+  if (nchunks > HW / pstride) nchunks = HW / pstride > 0 ? HW / pstride : 1;
+  int pix_per_cta = (HW + nchunks - 1) / nchunks;
+  pix_per_cta = (pix_per_cta + pstride - 1) / pstride * pstride;
+  nchunks = (HW + pix_per_cta - 1) / pix_per_cta;
+  dim3 grid(nchunks, x.B);
+  gn_apply_gst_kernel<<<grid, threads, groups * 2 * sizeof(float), s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, y.hl, y.hr,
+                                                                       y.Wp(), y.ld, C, cpg, groups, gamma, beta, eps,
+                                                                       silu ? 1 : 0, x.gst, x.gst_ld, x.gst_slots,
+                                                                       pix_per_cta);
+  LIDM_CUDA_CHECK(cudaGetLastError());
+  LIDM_COUNT_LAUNCH(1);
 }
 
 }  // namespace lidm
