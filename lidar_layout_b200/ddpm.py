@@ -26,6 +26,13 @@ def extract_into_tensor(a, t, x_shape):
     return out.reshape(b, *((1,) * (len(x_shape) - 1)))
 
 
+def noise_like(shape, device, repeat=False):
+    """lidm/modules/basic.py:393-396 (the RNG draw of p_sample; module-level like the reference so callers can swap it)."""
+    if repeat:
+        return torch.randn((1, *shape[1:]), device=device).repeat(shape[0], *((1,) * (len(shape) - 1)))
+    return torch.randn(shape, device=device)
+
+
 class _FirstStage:
     """Stands in for VQModelInterface on the attribute paths samplers use (`first_stage_model.quantize`)."""
 
@@ -204,7 +211,7 @@ class LatentDiffusion:
         outputs = self.p_mean_variance(x=x, c=c, t=t, clip_denoised=clip_denoised, return_x0=return_x0,
                                        quantize_denoised=quantize_denoised)
         mean, _, logvar = outputs[:3]
-        noise = torch.randn(x.shape, device=x.device) * temperature
+        noise = noise_like(x.shape, x.device, repeat_noise) * temperature
         if noise_dropout > 0.:
             noise = torch.nn.functional.dropout(noise, p=noise_dropout)
         nonzero_mask = (1 - (t == 0).float()).reshape(b, *((1,) * (len(x.shape) - 1)))

@@ -331,6 +331,46 @@ def main_ae():
     make_ae("kitti_ae", cfgmod.from_reference_dict(y), y, B=1)
 
 
+@torch.no_grad()
+def make_ddpm(name, cfg, yaml_dict, B, steps):
+    """Ancestral sampling: LatentDiffusion.sample(..., timesteps=steps) with the per-step
+    noise of p_sample (ddpm.py:1106) injected, recorded with a spy on apply_model."""
+    model = build_reference(cfg, yaml_dict)
+    from lidm.models.diffusion import ddpm as ref_ddpm
+    sd = load_synthetic(model, cfg)
+    x_T, noise, _ = inputs_for(cfg, B, steps)
+    rec = []
+    orig_apply = model.apply_model
+
+    def spy(x, t, c, *a, **k):
+        e = orig_apply(x, t, c, *a, **k)
+        rec.append((x.clone(), t.clone(), e.clone()))
+        return e
+
+    model.apply_model = spy
+    it = iter(list(noise))
+    orig_noise_like = ref_ddpm.noise_like
+    ref_ddpm.noise_like = lambda shape_, device, repeat=False: torch.from_numpy(next(it))
+    try:
+        out_img = model.sample(None, batch_size=B, x_T=torch.from_numpy(x_T).clone(), timesteps=steps)
+    finally:
+        ref_ddpm.noise_like = orig_noise_like
+        model.apply_model = orig_apply
+    out = {"B": np.int64(B), "steps": np.int64(steps), "weight_seed": np.int64(WEIGHT_SEED),
+           "weights_digest": np.frombuffer(sd_digest(sd).encode(), dtype=np.uint8),
+           "final": out_img.numpy(), "xt": np.stack([r[0].numpy() for r in rec]),
+           "t": np.stack([r[1].numpy() for r in rec]), "eps": np.stack([r[2].numpy() for r in rec])}
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB; keys={sorted(out)}")
+
+
+def main_ddpm():
+    torch.set_num_threads(os.cpu_count())
+    tiny = cfgmod.tiny()
+    make_ddpm("tiny_ddpm", tiny, tiny_yaml(tiny), B=2, steps=5)
+
+
 def main_cond():
     """Conditioned fixtures."""
     torch.set_num_threads(os.cpu_count())
@@ -349,6 +389,8 @@ def main():
         return main_cond()
     if "--ae" in sys.argv:
         return main_ae()
+    if "--ddpm" in sys.argv:
+        return main_ddpm()
     torch.set_num_threads(os.cpu_count())
     torch.manual_seed(0)
     import yaml

@@ -452,6 +452,47 @@ def ddim_sample(sd, cfg: LidmConfig, S, x_T, eta=0.0, noise=None, temperature=1.
 
 
 # --------------------------------------------------------------------------------------
+# ancestral DDPM sampling (ddpm.py)
+# --------------------------------------------------------------------------------------
+
+
+def _extract(a, t, x_shape):
+    """extract_into_tensor, lidm/modules/basic.py:219-222."""
+    b = t.shape[0]
+    return a.gather(-1, t).reshape(b, *((1,) * (len(x_shape) - 1)))
+
+
+def ddpm_p_sample(sched, x, eps, t, noise, temperature=1.0, clip_denoised=False):
+    """LatentDiffusion.p_sample given the model output (ddpm.py:1090-1119 with p_mean_variance :1059-1088,
+    predict_start_from_noise :219-223, q_posterior :225-232), eps parameterisation."""
+    x_recon = _extract(sched["sqrt_recip_alphas_cumprod"], t, x.shape) * x - \
+        _extract(sched["sqrt_recipm1_alphas_cumprod"], t, x.shape) * eps
+    if clip_denoised:
+        x_recon = x_recon.clamp(-1.0, 1.0)
+    mean = _extract(sched["posterior_mean_coef1"], t, x.shape) * x_recon + \
+        _extract(sched["posterior_mean_coef2"], t, x.shape) * x
+    logvar = _extract(sched["posterior_log_variance_clipped"], t, x.shape)
+    nz = noise * temperature
+    nonzero_mask = (1 - (t == 0).float()).reshape(x.shape[0], *((1,) * (len(x.shape) - 1)))
+    return mean + nonzero_mask * (0.5 * logvar).exp() * nz
+
+
+@torch.no_grad()
+def ddpm_sample(sd, cfg: LidmConfig, x_T, timesteps, noise, cond=None, record=None):
+    """LatentDiffusion.sample -> p_sample_loop (ddpm.py:1228-1244, 1177-1226): ancestral sampling over
+    t = timesteps-1 .. 0 with pre-generated per-step noise (noise[i] for the i-th iteration)."""
+    sched = register_schedule(cfg)
+    img = x_T
+    for i, tv in enumerate(reversed(range(0, timesteps))):
+        t = torch.full((img.shape[0],), tv, dtype=torch.long)
+        eps = apply_model(sd, cfg, img, t, cond)
+        if record is not None:
+            record.append((img, t, eps))
+        img = ddpm_p_sample(sched, img, eps, t, noise[i])
+    return img
+
+
+# --------------------------------------------------------------------------------------
 # back-projection (lidar_utils.py, numpy)
 # --------------------------------------------------------------------------------------
 
