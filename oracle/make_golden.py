@@ -365,10 +365,37 @@ def make_ddpm(name, cfg, yaml_dict, B, steps):
     print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB; keys={sorted(out)}")
 
 
+@torch.no_grad()
+def make_inpaint(name, cfg, yaml_dict, B, S):
+    """DDIM inpainting blend (ddim.py:146-149): img = q_sample(x0, t) * mask + (1 - mask) * img before every step;
+    q_sample's randn_like draws are injected."""
+    model = build_reference(cfg, yaml_dict)
+    from lidm.models.diffusion import ddim as ref_ddim
+    sd = load_synthetic(model, cfg)
+    x_T, noise, x0 = inputs_for(cfg, B, S)
+    rng = np.random.Generator(np.random.PCG64(INPUT_SEED + 11))
+    mask = (rng.random((B, 1) + tuple(cfg.latent_shape[1:])) < 0.5).astype(np.float32)
+    it = iter(list(noise))
+    orig = torch.randn_like
+    torch.randn_like = lambda t, *a, **k: torch.from_numpy(next(it))
+    try:
+        sampler = ref_ddim.DDIMSampler(model)
+        out_img, _ = sampler.sample(S, batch_size=B, shape=cfg.latent_shape, eta=0.0, x_T=torch.from_numpy(x_T).clone(),
+                                    mask=torch.from_numpy(mask), x0=torch.from_numpy(x0), verbose=False)
+    finally:
+        torch.randn_like = orig
+    out = {"B": np.int64(B), "S": np.int64(S), "mask": mask, "final": out_img.numpy(),
+           "weights_digest": np.frombuffer(sd_digest(sd).encode(), dtype=np.uint8)}
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB; keys={sorted(out)}")
+
+
 def main_ddpm():
     torch.set_num_threads(os.cpu_count())
     tiny = cfgmod.tiny()
     make_ddpm("tiny_ddpm", tiny, tiny_yaml(tiny), B=2, steps=5)
+    make_inpaint("tiny_inpaint", tiny, tiny_yaml(tiny), B=2, S=4)
 
 
 def main_cond():

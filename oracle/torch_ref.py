@@ -430,8 +430,17 @@ def guided_eps(sd, cfg: LidmConfig, x, t, cond, unconditional_conditioning=None,
 
 
 @torch.no_grad()
+def q_sample(cfg: LidmConfig, x_start, t, noise):
+    """DDPM.q_sample, ddpm.py:306-309."""
+    sched = register_schedule(cfg)
+    return (_extract(sched["sqrt_alphas_cumprod"], t, x_start.shape) * x_start +
+            _extract(sched["sqrt_one_minus_alphas_cumprod"], t, x_start.shape) * noise)
+
+
+@torch.no_grad()
 def ddim_sample(sd, cfg: LidmConfig, S, x_T, eta=0.0, noise=None, temperature=1.0, record=None, cond=None,
-                unconditional_conditioning=None, unconditional_guidance_scale=1.0, quantize_x0=False):
+                unconditional_conditioning=None, unconditional_guidance_scale=1.0, quantize_x0=False, mask=None, x0=None,
+                q_noise=None):
     """DDIMSampler.sample / ddim_sampling, ddim.py:57-165.
     noise: optional (n_steps,B,C,H,W) pre-generated tensor used for the sigma_t * randn term (in loop order).
     record: optional list; receives (x_t, t, eps, pred_x0, x_prev) per step."""
@@ -441,6 +450,8 @@ def ddim_sample(sd, cfg: LidmConfig, S, x_T, eta=0.0, noise=None, temperature=1.
     for i, step in enumerate(np.flip(ts)):
         index = n - i - 1
         t = torch.full((img.shape[0],), int(step), dtype=torch.long)
+        if mask is not None:   # inpainting blend, ddim.py:146-149 (q_noise[i]: the randn_like draw of q_sample)
+            img = q_sample(cfg, x0, t, q_noise[i]) * mask + (1.0 - mask) * img
         e_t = guided_eps(sd, cfg, img, t, cond, unconditional_conditioning, unconditional_guidance_scale)
         nz = None if noise is None else noise[i]
         qf = (lambda p: vq_quantize(p, sd[AE_PREFIX + "quantize.embedding.weight"])[0]) if quantize_x0 else None

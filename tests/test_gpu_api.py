@@ -139,3 +139,20 @@ def test_quantize_and_quantize_x0(model):
     # comparison against the fp32 oracle is not meaningful beyond finiteness
     got, _ = sampler.sample(4, batch_size=2, shape=cfg.latent_shape, eta=0.0, x_T=x.cuda(), quantize_x0=True)
     assert torch.isfinite(got).all()
+
+
+def test_ddim_inpainting_against_reference(model, monkeypatch):
+    """DDIMSampler.sample(mask=, x0=) (ddim.py:146-149) with q_sample's randn_like draws injected (tiny_inpaint.npz)."""
+    import os
+    import lidar_layout_b200 as L
+    from oracle import torch_ref as R
+    from oracle.make_golden import inputs_for
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiny_inpaint.npz"))
+    cfg = model.cfg
+    B, S = int(g["B"]), int(g["S"])
+    x_T, noise, x0 = inputs_for(cfg, B, S)
+    it = iter([torch.from_numpy(n).cuda() for n in noise])
+    monkeypatch.setattr(torch, "randn_like", lambda t, *a, **k: next(it))
+    z, _ = L.DDIMSampler(model).sample(S, batch_size=B, shape=cfg.latent_shape, eta=0.0, x_T=torch.from_numpy(x_T).cuda(),
+                                       mask=torch.from_numpy(g["mask"]).cuda(), x0=torch.from_numpy(x0).cuda())
+    assert R.rel_l2(z.cpu(), g["final"]) < 1e-2
