@@ -326,6 +326,281 @@ constexpr float RESCALE_LOG2 = 8.f;
 template <int NG, int BKV_>
 struct Cfg {
   static constexpr int KB = BKV_ * 64;                        // bytes of one K (or V) tile
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + NG * Q_BYTES;
+  static constexpr int OFF_V = OFF_K + KV_ST * KB;
+  static constexpr int OFF_BAR = OFF_V + KV_ST * KB;
+  static constexpr int SMEM_TOTAL = OFF_BAR + 512 + 1024;
+  static constexpr uint32_t P_COL = NG * BKV_;
+  static constexpr uint32_t O_COL = P_COL + NG * (BKV_ / 2);
+  static constexpr uint32_t TMEM_COLS = (O_COL + NG * 32) <= 256 ? 256 : 512;
+  static constexpr int THREADS = 128 + NG * 128;
+  static constexpr int NCH = BKV_ / 32;                       // 32-column chunks per S row
+  static_assert(O_COL + NG * 32 <= 512, "TMEM budget");
+  static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
+};
+
+template <int NG, int BKV_, bool POLY>
+__global__ void __launch_bounds__((Cfg<NG, BKV_>::THREADS), 1)
+attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                        bf16* __restrict__ out, int out_ld, int T, int q_col, int k_col, int v_col, int kv_len) {
+  using L = Cfg<NG, BKV_>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* kv_full = q_full + 1;          // [KV_ST]
+  uint64_t* kv_empty = kv_full + KV_ST;    // [KV_ST]
+  uint64_t* s_ready = kv_empty + KV_ST;    // [NG]
+  uint64_t* s_free = s_ready + NG;         // [NG]
+  uint64_t* p_ready = s_free + NG;         // [NG]
+  uint64_t* pv_done = p_ready + NG;        // [NG]
+  uint64_t* stagger = pv_done + NG;        // [NG]: group g-1 -> group g, once per CTA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stagger + NG);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (NG * BQ);
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int nkv = (kv_len + BKV_ - 1) / BKV_;   // rows past kv_len are zero-filled by TMA and masked to -inf below
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmQ);
+    prefetch_tensormap(&tmKV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KV_ST; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], NG); }
+    for (int g = 0; g < NG; ++g) { mbar_init(&s_ready[g], 1); mbar_init(&s_free[g], 4); mbar_init(&stagger[g], 4); }
+    for (int i = 0; i < NG; ++i) { mbar_init(&p_ready[i], 4); mbar_init(&pv_done[i], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, L::TMEM_COLS); tmem_relinquish(); }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    if (NG == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(q_full, NG * Q_BYTES);
+#pragma unroll
+        for (int i = 0; i < NG; i += 2)                                       // 256 query rows per box
+          tma_load_3d(smem + L::OFF_Q + i * Q_BYTES, &tmQ, q_full, q_col + head * D, q0 + i * BQ, b);
+        int s = 0; uint32_t ph = 0;
+        for (int j = 0; j < nkv; ++j) {
+          mbar_wait(&kv_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&kv_full[s], 2 * L::KB);
+          tma_load_3d(smem + L::OFF_K + s * L::KB, &tmKV, &kv_full[s], k_col + head * D, j * BKV_, b);
+          tma_load_3d(smem + L::OFF_V + s * L::KB, &tmKV, &kv_full[s], v_col + head * D, j * BKV_, b);
+          if (++s == KV_ST) { s = 0; ph ^= 1; }
+        }
+      }
+    } else if (warp - 1 < NG) {
+      // one MMA-issuing thread per group (tcgen05.mma issue blocks until the tensor pipe accepts the instruction, so a
+      // single thread serving both groups delays one group's S / P*V behind the other's): each polls only its own
+      // barriers; a K/V stage goes back to the TMA warp when every group has committed its P*V on it
+      if (lane == 0) {
+        const int g = warp - 1;
+        constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV_);
+        constexpr uint32_t idesc_o = make_idesc_bf16(BQ, D) | (1u << 16);     // V is an MN-major B operand
+        int js = 0, jp = 0;
+        mbar_wait(q_full, 0);
+        const long long t0 = clock64();
+        const uint64_t qdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_Q + g * Q_BYTES));
+        const uint32_t dS = tmem_base + g * BKV_;
+        const uint32_t tP = tmem_base + L::P_COL + g * (BKV_ / 2);
+        const uint32_t dO = tmem_base + L::O_COL + g * 32;
+        while (jp < nkv) {
+          if (js < nkv) {
+            const int j = js, st = j % KV_ST;
+            bool ok = mbar_test_wait(&kv_full[st], (j / KV_ST) & 1);
+            if (ok && j > 0) ok = mbar_test_wait(&s_free[g], (j - 1) & 1);
+            if (ok) {
+              tcgen05_fence_after();
+              const uint64_t kdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_K + st * L::KB));
+              umma_bf16_ss(dS, qdesc, kdesc, idesc_s, 0);
+              umma_bf16_ss(dS, qdesc + 2, kdesc + 2, idesc_s, 1);
+              umma_commit(&s_ready[g]);
+              js = j + 1;
+            }
+          }
+          if (jp < js) {
+            const int j = jp, st = j % KV_ST;
+            if (mbar_test_wait(&p_ready[g], j & 1)) {
+              tcgen05_fence_after();
+              const uint64_t vdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_V + st * L::KB));
+#pragma unroll
+              for (int kk = 0; kk < BKV_ / 16; ++kk) {
+                const uint64_t vb = vdesc + (uint64_t)((kk * 1024) >> 4);
+                umma_bf16_ts(dO, tP + kk * 8, vb, idesc_o, (j > 0 || kk != 0) ? 1u : 0u);   // 16 bf16 = 8 columns
+              }
+              umma_commit(&pv_done[g]);
+              umma_commit(&kv_empty[st]);      // this group is done with K/V tile j
+              jp = j + 1;
+            }
+          }
+          if (clock64() - t0 > 4000000000LL) {
+            printf("lidm: attention v4 MMA loop timeout block(%d,%d,%d) group %d\n", blockIdx.x, blockIdx.y, blockIdx.z, g);
+            __trap();
+          }
+        }
+      }
+    }
+  } else {
+    if (NG == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    const int g = (warp - 4) >> 2;                 // softmax group = query tile
+    const int qd = warp & 3;                       // TMEM lane quadrant
+    const int row = qd * 32 + lane;                // row inside the 128-row tile
+    const uint32_t tS = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + g * BKV_;
+    const uint32_t tO = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + L::O_COL + g * 32;
+    const uint32_t tP = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + L::P_COL + g * (BKV_ / 2);
+    constexpr float LOG2E = 1.4426950408889634f;
+    float m = 0.f, l = 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(&s_ready[g], j & 1);
+      tcgen05_fence_after();
+      uint32_t sv[L::NCH][32];
+#pragma unroll
+      for (int c = 0; c < L::NCH; ++c) tmem_ld_32x32b_x32(tS + c * 32, sv[c]);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[g]);      // S_g(j+1) may overwrite the TMEM buffer now
+      if (kv_len - j * BKV_ < BKV_) {               // ragged last tile (cross-attention context): mask the padding keys
+        const int valid = kv_len - j * BKV_;
+#pragma unroll
+        for (int c = 0; c < L::NCH; ++c) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= valid) sv[c][i] = 0xff800000u;   // -inf
+        }
+      }
+      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < L::NCH; ++c) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          m0 = max3(m0, __uint_as_float(sv[c][8 * i + 0]), __uint_as_float(sv[c][8 * i + 1]));
+          m1 = max3(m1, __uint_as_float(sv[c][8 * i + 2]), __uint_as_float(sv[c][8 * i + 3]));
+          m2 = max3(m2, __uint_as_float(sv[c][8 * i + 4]), __uint_as_float(sv[c][8 * i + 5]));
+          m3 = max3(m3, __uint_as_float(sv[c][8 * i + 6]), __uint_as_float(sv[c][8 * i + 7]));
+        }
+      }
+      const float r = max3(fmaxf(m0, m1), m2, m3);
+      if (j == 0) {
+        m = r;
+      } else if (__any_sync(0xffffffffu, (r - m) * LOG2E > RESCALE_LOG2)) {
+        // rare: refresh the running max of every row of this warp and rescale O in TMEM
+        mbar_wait(&pv_done[g], (j - 1) & 1);   // every P*V issued so far has completed
+        tcgen05_fence_after();
+        const float mn = fmaxf(m, r);
+        const float alpha = ex2((m - mn) * LOG2E);
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(tO, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st_32x32b_x32(tO, o);
+        tmem_st_wait();
+        l *= alpha;
+        m = mn;
+      }
+      if (j == 0 && g > 0 && nkv > 1) mbar_wait(&stagger[g], 0);               // start a fraction of a tile apart
+      const float mb = m * LOG2E;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      uint32_t pkk[32];
+#pragma unroll
+      for (int c = 0; c < L::NCH; ++c) {
+        uint32_t* pk = &pkk[(c & 1) * 16];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          const float p0 = ex2(fmaf(__uint_as_float(sv[c][2 * i]), LOG2E, -mb));
+          const float p1 = ex2(fmaf(__uint_as_float(sv[c][2 * i + 1]), LOG2E, -mb));
+          const float p2 = ex2(fmaf(__uint_as_float(sv[c][2 * i + 2]), LOG2E, -mb));
+          const float p3 = POLY ? ex2_poly(fmaf(__uint_as_float(sv[c][2 * i + 3]), LOG2E, -mb))
+                                : ex2(fmaf(__uint_as_float(sv[c][2 * i + 3]), LOG2E, -mb));
+          s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+          pk[i] = pack_bf16(p0, p1);
+          pk[i + 1] = pack_bf16(p2, p3);
+        }
+        if (c & 1) {
+          if (c == 1 && j > 0) {
+            // P_g(j-1) V(j-1) must have drained P before it is overwritten; by now half of this tile's exponentials
+            // are done, so the wait is normally free
+            mbar_wait(&pv_done[g], (j - 1) & 1);
+            tcgen05_fence_after();
+          }
+          tmem_st_32x32b_x32(tP + (c >> 1) * 32, pkk);   // 64 keys = 32 columns of bf16 pairs
+        }
+        if (c == L::NCH / NG - 1 + (L::NCH / NG == 0) && j == 0 && g + 1 < NG && lane == 0) mbar_arrive(&stagger[g + 1]);
+      }
+      l += (s0 + s1) + (s2 + s3);
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_ready[g]);
+    }
+    mbar_wait(&pv_done[g], (nkv - 1) & 1);
+    tcgen05_fence_after();
+    uint32_t o[32];
+    tmem_ld_32x32b_x32(tO, o);
+    tmem_ld_wait();
+    tcgen05_fence_before();
+    const float inv = 1.f / l;
+    bf16* op = out + ((size_t)b * T + q0 + g * 128 + row) * out_ld + head * D;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 u;
+      u.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+      u.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+      u.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+      u.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+      reinterpret_cast<uint4*>(op)[i] = u;
+    }
+  }
+  __syncthreads();
+  if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, L::TMEM_COLS); }
+}
+
+// q: (B, T, q_ld) rows with the heads at columns q_col + head*32; k / v: (B, kv_rows, kv_ld) rows at columns k_col / v_col.
+template <int NG, int BKV_, bool POLY>
+void launch(const bf16* q, int q_ld, int q_col, const bf16* kv, int kv_ld, int k_col, int v_col, int kv_rows, const View& out,
+            int B, int T, int heads, cudaStream_t s) {
+  using L = Cfg<NG, BKV_>;
+  static bool configured = false;
+  if (!configured) {
+    LIDM_CUDA_CHECK(cudaFuncSetAttribute(attention_d32_v4_kernel<NG, BKV_, POLY>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_TOTAL));
+    configured = true;
+  }
+  LIDM_REQUIRE(T % (NG * BQ) == 0 && kv_rows >= 1, "attention tile shape");
+  CUtensorMap tmQ = make_tma_3d(q, q_ld, T, B, (uint64_t)q_ld * 2, (uint64_t)T * q_ld * 2, D, NG >= 2 ? 256 : 128, 64);
+  CUtensorMap tmKV = make_tma_3d(kv, kv_ld, kv_rows, B, (uint64_t)kv_ld * 2, (uint64_t)kv_rows * kv_ld * 2, D, BKV_, 64);
+  dim3 grid(T / (NG * BQ), heads, B);
+  attention_d32_v4_kernel<NG, BKV_, POLY><<<grid, L::THREADS, L::SMEM_TOTAL, s>>>(tmQ, tmKV, out.p, out.ld, T, q_col, k_col,
+                                                                                v_col, kv_rows);
+  LIDM_CUDA_CHECK(cudaGetLastError());
+  LIDM_COUNT_LAUNCH(1);
+}
+
+}  // namespace v4
+
+// =====================================================================================================
+// v5: the v4 pipeline as a persistent kernel for SHORT work items (T = 512: 4 K/V tiles; cross-attention contexts: 1):
+// one CTA per SM walks (query block, head, sample) items; TMEM, barriers and the K/V ring live across items (cumulative
+// phases), the next item's queries load into a second buffer, so its loads and first S = Q K^T overlap the current
+// item's tail; and the two softmax warps that share a scheduler take strict turns at the exponential phase (mbarrier
+// ping-pong), so each runs it at the full MUFU rate.  Measured on B200 (same box, B = 64): T = 512 145 -> 128 us;
+// T = 2048 794 -> 840 us, which is why long items stay on v4 (one item per CTA, staggered free-running groups).
+namespace v5 {
+
+constexpr int KV_ST = 4;
+constexpr float RESCALE_LOG2 = 8.f;
+
+template <int NG, int BKV_>
+struct Cfg {
+  static constexpr int KB = BKV_ * 64;                        // bytes of one K (or V) tile
   static constexpr int OFF_Q = 0;                             // two buffers: the next work item's queries load early
   static constexpr int OFF_K = OFF_Q + 2 * NG * Q_BYTES;
   static constexpr int OFF_V = OFF_K + KV_ST * KB;
@@ -340,9 +615,9 @@ struct Cfg {
   static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
 };
 
-template <int NG, int BKV_, bool POLY, bool PERSIST>
+template <int NG, int BKV_, bool POLY>
 __global__ void __launch_bounds__((Cfg<NG, BKV_>::THREADS), 1)
-attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                         bf16* __restrict__ out, int out_ld, int T, int q_col, int k_col, int v_col, int kv_len,
                         int n_qblk, int heads, int n_items) {
   using L = Cfg<NG, BKV_>;
@@ -357,7 +632,8 @@ attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint64_t* p_ready = s_free + NG;         // [NG]
   uint64_t* pv_done = p_ready + NG;        // [NG]
   uint64_t* stagger = pv_done + NG;        // [NG]: group g-1 -> group g, once per CTA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stagger + NG);
+  uint64_t* xu_go = stagger + NG;          // [2 groups][4 schedulers]: exp-phase ping-pong between the two warps of a scheduler
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xu_go + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -365,8 +641,7 @@ attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   // persistent CTA: work item = (query block, head, sample); this CTA takes items blockIdx.x, blockIdx.x + gridDim.x, ...
   // TMEM, the barriers and the K/V ring live across items (all phases are counted cumulatively), so the next item's
   // Q / K / V loads and its first S = Q K^T overlap the tail of the current one
-  // (PERSIST = false: exactly one item per CTA, the item loops below compile away)
-  const int n_my = PERSIST ? (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 1;
+  const int n_my = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   auto item_coords = [&](int it, int& q0, int& head, int& b) {
     const int item = it * gridDim.x + blockIdx.x;
     const int qb = item % n_qblk;
@@ -383,6 +658,7 @@ attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     for (int s = 0; s < KV_ST; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], NG); }
     for (int g = 0; g < NG; ++g) { mbar_init(&s_ready[g], 1); mbar_init(&s_free[g], 4); mbar_init(&stagger[g], 4); }
     for (int i = 0; i < NG; ++i) { mbar_init(&p_ready[i], 4); mbar_init(&pv_done[i], 1); }
+    for (int i = 0; i < 8; ++i) mbar_init(&xu_go[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, L::TMEM_COLS); tmem_relinquish(); }
@@ -473,7 +749,7 @@ attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             }
           }
           if (clock64() - t0 > 8000000000LL) {
-            printf("lidm: attention v4 MMA loop timeout block %d group %d (S %d, PV %d of %d)\n", blockIdx.x, g, ns, np, total);
+            printf("lidm: attention v5 MMA loop timeout block %d group %d (S %d, PV %d of %d)\n", blockIdx.x, g, ns, np, total);
             __trap();
           }
         }
@@ -490,6 +766,7 @@ attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     constexpr float LOG2E = 1.4426950408889634f;
     int n = 0;                                     // cumulative tile index over this CTA's items (barrier phases)
     const bool restagger = nkv >= 8;
+    constexpr bool PINGPONG = NG == 2;
     for (int it = 0; it < n_my; ++it) {
     int q0, head, b;
     item_coords(it, q0, head, b);
@@ -545,7 +822,15 @@ attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
       // start the groups a fraction of a tile apart (and, on long items, re-establish the offset at every item: the
       // phase relation is only neutrally stable and drifts back towards lock-step otherwise)
-      if (j == 0 && g > 0 && nkv > 1 && (it == 0 || restagger)) mbar_wait(&stagger[g], restagger ? (it & 1) : 0);
+      // exp-phase ping-pong: warp 4+q (group 0) and warp 8+q (group 1) share scheduler q and its MUFU unit; they take
+      // strict turns at the exponential phase (A(0), B(0), A(1), B(1), ...), so each runs it at the full MUFU rate
+      // while the other drains TMEM / takes the row max / waits for S, instead of both halving each other's rate
+      if (PINGPONG) {
+        if (g == 0) { if (n > 0) mbar_wait(&xu_go[qd], (n - 1) & 1); }
+        else mbar_wait(&xu_go[4 + qd], n & 1);
+      } else if (j == 0 && g > 0 && nkv > 1 && (it == 0 || restagger)) {
+        mbar_wait(&stagger[g], restagger ? (it & 1) : 0);
+      }
       const float mb = m * LOG2E;
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
       uint32_t pkk[32];
@@ -572,9 +857,10 @@ attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           }
           tmem_st_32x32b_x32(tP + (c >> 1) * 32, pkk);   // 64 keys = 32 columns of bf16 pairs
         }
-        if (c == L::NCH / NG - 1 + (L::NCH / NG == 0) && j == 0 && (it == 0 || restagger) && g + 1 < NG && lane == 0)
+        if (!PINGPONG && c == L::NCH / NG - 1 + (L::NCH / NG == 0) && j == 0 && (it == 0 || restagger) && g + 1 < NG && lane == 0)
           mbar_arrive(&stagger[g + 1]);
       }
+      if (PINGPONG && lane == 0) mbar_arrive(&xu_go[(g == 0 ? 4 : 0) + qd]);   // hand the MUFU unit to the partner warp
       l += (s0 + s1) + (s2 + s3);
       tmem_st_wait();
       tcgen05_fence_before();
@@ -611,9 +897,7 @@ void launch(const bf16* q, int q_ld, int q_col, const bf16* kv, int kv_ld, int k
   using L = Cfg<NG, BKV_>;
   static bool configured = false;
   if (!configured) {
-    LIDM_CUDA_CHECK(cudaFuncSetAttribute(attention_d32_v4_kernel<NG, BKV_, POLY, true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_TOTAL));
-    LIDM_CUDA_CHECK(cudaFuncSetAttribute(attention_d32_v4_kernel<NG, BKV_, POLY, false>,
+    LIDM_CUDA_CHECK(cudaFuncSetAttribute(attention_d32_v5_kernel<NG, BKV_, POLY>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_TOTAL));
     configured = true;
   }
@@ -628,21 +912,14 @@ void launch(const bf16* q, int q_ld, int q_col, const bf16* kv, int kv_ld, int k
     LIDM_CUDA_CHECK(cudaGetDevice(&dev));
     LIDM_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  // short items (few K/V tiles, e.g. T = 512 or a cross-attention context): one persistent CTA per SM walks them, so the
-  // next item's loads and first S overlap the current item's tail; long items (measured at T = 2048, 16 tiles) run
-  // 3 % faster one item per CTA, where the hardware scheduler back-fills SMs as they drain
-  const int nkv_tiles = (kv_rows + BKV_ - 1) / BKV_;
-  if (nkv_tiles >= 8 || n_items <= num_sms)
-    attention_d32_v4_kernel<NG, BKV_, POLY, false><<<n_items, L::THREADS, L::SMEM_TOTAL, s>>>(
-        tmQ, tmKV, out.p, out.ld, T, q_col, k_col, v_col, kv_rows, n_qblk, heads, n_items);
-  else
-    attention_d32_v4_kernel<NG, BKV_, POLY, true><<<num_sms, L::THREADS, L::SMEM_TOTAL, s>>>(
-        tmQ, tmKV, out.p, out.ld, T, q_col, k_col, v_col, kv_rows, n_qblk, heads, n_items);
+  const int grid = n_items < num_sms ? n_items : num_sms;     // one persistent CTA per SM
+  attention_d32_v5_kernel<NG, BKV_, POLY><<<grid, L::THREADS, L::SMEM_TOTAL, s>>>(tmQ, tmKV, out.p, out.ld, T, q_col, k_col,
+                                                                                v_col, kv_rows, n_qblk, heads, n_items);
   LIDM_CUDA_CHECK(cudaGetLastError());
   LIDM_COUNT_LAUNCH(1);
 }
 
-}  // namespace v4
+}  // namespace v5
 
 }  // namespace
 
@@ -664,7 +941,8 @@ void launch_attention_d32_packed(const bf16* qkv, const View& out, int B, int T,
   static const bool use_v2 = getenv("LIDM_ATTN_V2") != nullptr;
   static const int v4_mode = getenv("LIDM_ATTN_V4") ? atoi(getenv("LIDM_ATTN_V4")) : 0;
   if (!use_v2 && T % 256 == 0) {
-    if (v4_mode == 1) v4::launch<2, 128, true>(qkv, 3 * C, 0, qkv, 3 * C, C, 2 * C, T, out, B, T, heads, s);
+    if (T / 128 < 8) v5::launch<2, 128, false>(qkv, 3 * C, 0, qkv, 3 * C, C, 2 * C, T, out, B, T, heads, s);
+    else if (v4_mode == 1) v4::launch<2, 128, true>(qkv, 3 * C, 0, qkv, 3 * C, C, 2 * C, T, out, B, T, heads, s);
     else v4::launch<2, 128, false>(qkv, 3 * C, 0, qkv, 3 * C, C, 2 * C, T, out, B, T, heads, s);
     return;
   }
@@ -679,8 +957,8 @@ void launch_attention_d32_packed(const bf16* qkv, const View& out, int B, int T,
 void launch_cross_attention_d32(const bf16* q, int q_ld, const bf16* kv, int kv_ld, int k_col, int v_col, int L,
                                 const View& out, int B, int T, int heads, cudaStream_t s) {
   LIDM_REQUIRE(T % 128 == 0 && L >= 1, "cross attention: T must be a multiple of 128");
-  if (T % 256 == 0) v4::launch<2, 128, false>(q, q_ld, 0, kv, kv_ld, k_col, v_col, L, out, B, T, heads, s);
-  else v4::launch<1, 128, false>(q, q_ld, 0, kv, kv_ld, k_col, v_col, L, out, B, T, heads, s);
+  if (T % 256 == 0) v5::launch<2, 128, false>(q, q_ld, 0, kv, kv_ld, k_col, v_col, L, out, B, T, heads, s);
+  else v5::launch<1, 128, false>(q, q_ld, 0, kv, kv_ld, k_col, v_col, L, out, B, T, heads, s);
 }
 
 }  // namespace lidm
