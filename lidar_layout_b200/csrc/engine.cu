@@ -163,7 +163,20 @@ struct Plan {
   float* ddim_x_prev = nullptr;
   float* ddim_pred_x0 = nullptr;
   const float* ddim_coef = nullptr;
+  // CUDA graphs of this plan (the DDIM loop replays one per step): valid while the launch-time IO pointers are unchanged
+  struct GraphSlot {
+    cudaGraphExec_t exec = nullptr;
+    std::vector<const void*> key;
+    int64_t kernels = 0;
+  };
+  GraphSlot gslot[3];
+  bool warmed = false;              // ran eagerly at least once (lazy one-time kernel attribute setup happens there)
+  std::vector<const void*> io_key() const {
+    return {x, xin, context, out, idx_out, rowadd_base, reinterpret_cast<const void*>((intptr_t)rowadd_ld), ddim_noise,
+            ddim_x_prev, ddim_pred_x0, ddim_coef, reinterpret_cast<const void*>((intptr_t)quantize)};
+  }
   ~Plan() {
+    for (auto& g : gslot) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (arena) cudaFree(arena);
     if (gn_partials) cudaFree(gn_partials);
   }
@@ -218,12 +231,19 @@ struct lidm_handle {
   int te_rows = 0;
   float* coef_dev = nullptr; int coef_rows = 0;
   float *xa = nullptr, *xb = nullptr; size_t xbuf_elems = 0;
+  // per-step staging the graphed DDIM loop reads through fixed addresses: this step's emb_layers row, coefficients,
+  // noise slice; pred_x0 scratch
+  float *emb_cur = nullptr, *coef_cur = nullptr, *noise_cur = nullptr, *pred_scratch = nullptr;
+  size_t stage_elems = 0;
+  cudaStream_t cap_stream = nullptr;
 
   ~lidm_handle() {
     for (auto& kv : raw) cudaFree(kv.second.p);
     for (void* p : owned) cudaFree(p);
     cudaFree(te_tmp); cudaFree(te_emb); cudaFree(emb_out); cudaFree(t_dev); cudaFree(coef_dev);
     cudaFree(xa); cudaFree(xb); cudaFree(xcat); cudaFree(ctx2); cudaFree(eps2);
+    cudaFree(emb_cur); cudaFree(coef_cur); cudaFree(noise_cur); cudaFree(pred_scratch);
+    if (cap_stream) cudaStreamDestroy(cap_stream);
   }
 };
 
@@ -1424,6 +1444,43 @@ void run_plan(Plan* P, cudaStream_t s) {
   }
 }
 
+// Replays the plan as a CUDA graph (captured on a private stream the first time the same IO pointers come round): at
+// small batches the ~160-400 launches of one U-Net evaluation cost more host time than device time.
+void run_plan_graphed(lidm_handle* h, Plan* P, int slot, cudaStream_t s) {
+  static const bool no_graph = getenv("LIDM_NO_GRAPH") != nullptr;
+  if (g_prof.on || no_graph || !P->warmed) {
+    run_plan(P, s);
+    P->warmed = true;
+    return;
+  }
+  Plan::GraphSlot& g = P->gslot[slot];
+  const std::vector<const void*> key = P->io_key();
+  if (g.exec == nullptr || g.key != key) {
+    if (h->cap_stream == nullptr) LIDM_CUDA_CHECK(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    LIDM_CUDA_CHECK(cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+    const int64_t before = g_launch_count.load();
+    cudaGraph_t graph = nullptr;
+    try {
+      run_plan(P, h->cap_stream);
+    } catch (...) {
+      cudaStreamEndCapture(h->cap_stream, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    LIDM_CUDA_CHECK(cudaStreamEndCapture(h->cap_stream, &graph));
+    const int64_t kernels = g_launch_count.load() - before;
+    g_launch_count.fetch_sub(kernels);          // captured, not launched
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    LIDM_CUDA_CHECK(e);
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    g.exec = exec; g.key = key; g.kernels = kernels;
+  }
+  LIDM_CUDA_CHECK(cudaGraphLaunch(g.exec, s));
+  g_launch_count.fetch_add(g.kernels);
+}
+
 // ------------------------------------------------------------------------------------------- finalize
 ResW pack_res(Packer& pk, const std::string& p, int cin, int cout, int kh, int kw, bool unet) {
   ResW r;
@@ -2175,6 +2232,16 @@ int lidm_ddim_sample_cond(lidm_handle* h, float* x_inout, const int64_t* timeste
       LIDM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&h->coef_dev), (size_t)n_steps * 5 * sizeof(float)));
       h->coef_rows = n_steps;
     }
+    if (h->emb_cur == nullptr) {
+      LIDM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&h->emb_cur), (size_t)h->emb_total * sizeof(float)));
+      LIDM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&h->coef_cur), 8 * sizeof(float)));
+    }
+    if (elems > h->stage_elems) {
+      cudaFree(h->noise_cur); cudaFree(h->pred_scratch); h->noise_cur = h->pred_scratch = nullptr; h->stage_elems = 0;
+      LIDM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&h->noise_cur), elems * sizeof(float)));
+      LIDM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&h->pred_scratch), elems * sizeof(float)));
+      h->stage_elems = elems;
+    }
     const float* ctx_run = context;
     if (guided) {
       if (2 * elems > h->eps2_elems) {
@@ -2211,29 +2278,37 @@ int lidm_ddim_sample_cond(lidm_handle* h, float* x_inout, const int64_t* timeste
     float* cur = h->xa;
     float* nxt = h->xb;
     for (int i = 0; i < n_steps; ++i) {
-      P->x = cur;
+      // this step's timestep-embedding row, coefficients and noise slice go to fixed staging addresses, so the same two
+      // CUDA graphs (x ping-pong parity) replay the whole loop
+      LIDM_CUDA_CHECK(cudaMemcpyAsync(h->emb_cur, h->emb_out + (size_t)i * h->emb_total, (size_t)h->emb_total * sizeof(float),
+                                      cudaMemcpyDeviceToDevice, s));
+      LIDM_CUDA_CHECK(cudaMemcpyAsync(h->coef_cur, h->coef_dev + (size_t)i * 5, 5 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      if (noise) LIDM_CUDA_CHECK(cudaMemcpyAsync(h->noise_cur, noise + (size_t)i * elems, elems * sizeof(float),
+                                                 cudaMemcpyDeviceToDevice, s));
       P->context = ctx_run;
-      P->rowadd_base = h->emb_out + (size_t)i * h->emb_total; P->rowadd_ld = 0;
-      const float* nz = noise ? noise + (size_t)i * elems : nullptr;
-      float* px0 = (i == n_steps - 1) ? pred_x0_out : nullptr;
+      P->rowadd_base = h->emb_cur; P->rowadd_ld = 0;
+      const float* nz = noise ? h->noise_cur : nullptr;
       if (!guided) {
+        P->x = cur;
         P->xin = assemble_input(h, cur, c_concat, B, 0, B, s);
         P->out = nullptr;
-        P->ddim_x_prev = nxt; P->ddim_noise = nz; P->ddim_pred_x0 = px0;
-        P->ddim_coef = h->coef_dev + (size_t)i * 5;
-        run_plan(P, s);
+        P->ddim_x_prev = nxt; P->ddim_noise = nz; P->ddim_pred_x0 = h->pred_scratch;
+        P->ddim_coef = h->coef_cur;
+        run_plan_graphed(h, P, (cur == h->xa) ? 0 : 1, s);
       } else {
         // x_in = torch.cat([x] * 2); c_in = torch.cat([uncond, cond]); one 2B evaluation, then the guided update
         assemble_input(h, cur, uncond_concat, B, 0, 2 * B, s, true);
         P->xin = assemble_input(h, cur, c_concat, B, B, 2 * B, s, true);
+        P->x = P->xin;
         P->out = h->eps2;
         P->ddim_x_prev = nullptr; P->ddim_noise = nullptr; P->ddim_pred_x0 = nullptr; P->ddim_coef = nullptr;
-        run_plan(P, s);
-        launch_cfg_ddim_step(cur, h->eps2, guidance_scale, nz, h->coef_dev + (size_t)i * 5, nxt, px0, nullptr,
-                             (int64_t)elems, s);
+        run_plan_graphed(h, P, 2, s);
+        launch_cfg_ddim_step(cur, h->eps2, guidance_scale, nz, h->coef_cur, nxt, h->pred_scratch, nullptr, (int64_t)elems, s);
       }
       std::swap(cur, nxt);
     }
+    if (pred_x0_out != nullptr)
+      LIDM_CUDA_CHECK(cudaMemcpyAsync(pred_x0_out, h->pred_scratch, elems * sizeof(float), cudaMemcpyDeviceToDevice, s));
     LIDM_CUDA_CHECK(cudaMemcpyAsync(x_inout, cur, elems * sizeof(float), cudaMemcpyDeviceToDevice, s));
   });
 }
