@@ -97,6 +97,9 @@ struct GemmEpilogue {
   // columns >= split_n go, transposed, to out_t[(b * (N - split_n) + (n - split_n)) * HW + pixel]  (V^T for attention)
   int split_n = 1 << 30;
   bf16* out_t = nullptr;
+  // GEGLU fused into the epilogue: the B rows are packed as blocks of [16 value rows | 16 gate rows]; `out` has N/2
+  // channels and receives value * gelu(gate) (exact erf GELU)
+  bool geglu = false;
   float* out_f32_nchw = nullptr;   // optional fp32 NCHW output (B, N, H, W)
   float* out_f32_nhwc = nullptr;   // optional fp32 channels-last output (B, H, W, N) (no halo)
   int out_f32_ld = 0;              // channel stride of out_f32_nhwc (0 => N)
@@ -151,8 +154,6 @@ void launch_cross_attention_d32(const bf16* q, int q_ld, const bf16* kv, int kv_
 // ---- transformer pieces (transformer.cu) -------------------------------------------------------------------
 // nn.LayerNorm over the channel dimension of every pixel/token (eps 1e-5), bf16 in / bf16 out, fp32 statistics
 void launch_layernorm(const View& x, const View& y, const float* gamma, const float* beta, float eps, cudaStream_t s);
-// GEGLU (lidm/modules/attention.py:36-44): y[..., i] = h[..., i] * gelu(h[..., C + i]), exact (erf) GELU; h has 2C channels
-void launch_geglu(const View& h, const View& y, cudaStream_t s);
 // fp32 (rows, cols) -> bf16 (rows_pad, cols) with zero rows appended
 void launch_f32_rows_to_bf16(const float* x, int64_t rows, int64_t rows_pad, int cols, bf16* y, cudaStream_t s);
 // classifier-free guidance + DDIM update (ddim.py:173-206): e = e_u + scale (e_c - e_u), then ddim_update(x, e, ...)

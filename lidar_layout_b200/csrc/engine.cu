@@ -353,6 +353,37 @@ ConvW pack_stacked_linear(Packer& pk, const std::vector<LinPart>& parts, int cou
   return c;
 }
 
+// GEGLU projection (Linear dim -> 2 * inner, output = x * gelu(gate), lidm/modules/attention.py:36-44) packed for the fused
+// epilogue: output rows interleaved in blocks of [16 value rows | 16 gate rows], bias permuted alike.
+ConvW pack_geglu_linear(Packer& pk, const std::string& prefix, int cout, int cin) {
+  lidm_handle* h = pk.h;
+  const DevTensor& w = find_raw(h, prefix + ".weight", pk.ema);
+  const DevTensor& bsrc = find_raw(h, prefix + ".bias", pk.ema);
+  if (w.numel != (int64_t)cout * cin || bsrc.numel != cout || cout % 32 != 0)
+    throw Error(LIDM_ERR_STATE, "GEGLU projection weight size: " + prefix);
+  const int inner = cout / 2;
+  std::vector<int> perm(cout);
+  for (int r = 0; r < cout; ++r) {
+    const int blk = r / 32, i = r % 32;
+    perm[r] = i < 16 ? blk * 16 + i : inner + blk * 16 + (i - 16);
+  }
+  int* perm_dev = dev_alloc<int>(h, perm.size());
+  LIDM_CUDA_CHECK(cudaMemcpyAsync(perm_dev, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice, pk.s));
+  ConvW c;
+  c.cout = cout; c.cin = cin; c.kh = c.kw = 1;
+  c.n_alloc = round_n_alloc(cout);
+  c.k_alloc = cin;
+  c.w = dev_alloc<bf16>(h, (size_t)c.n_alloc * cin);
+  launch_pack_conv_weight(w.p, cout, cin, 1, 1, c.n_alloc, cin, perm_dev, nullptr, 1.f, 0, c.w, pk.s);
+  std::vector<float> bh(cout), bp(cout);
+  LIDM_CUDA_CHECK(cudaMemcpyAsync(bh.data(), bsrc.p, cout * sizeof(float), cudaMemcpyDeviceToHost, pk.s));
+  LIDM_CUDA_CHECK(cudaStreamSynchronize(pk.s));
+  for (int r = 0; r < cout; ++r) bp[r] = bh[perm[r]];
+  c.bias = dev_alloc<float>(h, cout);
+  LIDM_CUDA_CHECK(cudaMemcpy(c.bias, bp.data(), cout * sizeof(float), cudaMemcpyHostToDevice));
+  return c;
+}
+
 // ------------------------------------------------------------------------------------------- plan builder
 struct Builder {
   lidm_handle* h;
@@ -825,16 +856,19 @@ struct Builder {
       release(bao2);
       release(bh1);
       // x = ff(norm3(x)) + x   (GEGLU feed-forward)
-      Buf bn3, bff, bgl, bh3;
+      Buf bn3, bgl, bh3;
       View n3 = act(B, H, W, C, 0, 0, &bn3);
       layernorm(h2, n3, k.n3);
-      View ffh = act(B, H, W, 8 * C, 0, 0, &bff);
-      lin(n3, k.ff0, ffh);
-      release(bn3);
       View ffg = act(B, H, W, 4 * C, 0, 0, &bgl);
-      op([=](cudaStream_t s) { launch_geglu(ffh, ffg, s); }, PROF_OTHER, 0, 24.0 * B * T * C,
-         "geglu C" + std::to_string(C) + " @" + std::to_string(H) + "x" + std::to_string(W));
-      release(bff);
+      {
+        GemmEpilogue ep;                 // proj + GEGLU in one GEMM: the (B,T,8C) intermediate never reaches HBM
+        ep.bias = k.ff0.bias;
+        ep.out = ffg;
+        ep.out.gst = nullptr;
+        ep.geglu = true;
+        gemm(n3, taps_1x1(), k.ff0, ep);
+      }
+      release(bn3);
       View h3 = act(B, H, W, C, 0, 0, &bh3);
       lin(ffg, k.ff2, h3, &h2);
       release(bgl);
@@ -1693,7 +1727,7 @@ void finalize(lidm_handle* h, bool use_ema) {
       w.out1 = pack_stacked_linear(pk, {{bp + ".attn1.to_out.0.weight", 1.f}}, c, c, bp + ".attn1.to_out.0.bias");
       w.q2 = pack_stacked_linear(pk, {{bp + ".attn2.to_q.weight", s2}}, c, c, "");
       w.out2 = pack_stacked_linear(pk, {{bp + ".attn2.to_out.0.weight", 1.f}}, c, c, bp + ".attn2.to_out.0.bias");
-      w.ff0 = pack_stacked_linear(pk, {{bp + ".ff.net.0.proj.weight", 1.f}}, 8 * c, c, bp + ".ff.net.0.proj.bias");
+      w.ff0 = pack_geglu_linear(pk, bp + ".ff.net.0.proj", 8 * c, c);
       w.ff2 = pack_stacked_linear(pk, {{bp + ".ff.net.2.weight", 1.f}}, c, 4 * c, bp + ".ff.net.2.bias");
       w.kv_col = h->ctx_n;
       h->ctx_n += 2 * c;

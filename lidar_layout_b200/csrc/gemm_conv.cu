@@ -45,6 +45,7 @@ struct GemmKernelParams {
   int out_f32_ld;            // channel stride of out_f32_nhwc (concat views)
   bf16* out;
   int out_ld, out_hl, out_hr, out_Wp;
+  int geglu;                 // GEGLU epilogue: columns come in blocks of [16 values | 16 gates], out = value * gelu(gate)
   float* gst;                // GroupNorm granule statistics of the output (View::gst), or null
   int gst_ld, gst_slots, gst_slot0;
   int split_n;
@@ -57,6 +58,20 @@ struct GemmKernelParams {
   float* ddim_pred_x0;
   const float* ddim_coef;
 };
+
+// Exact-form GELU 0.5 g (1 + erf(g / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below the
+// bf16 rounding of the output) on two MUFU ops + 8 FMAs instead of erff()'s ~30 instructions: the GEGLU epilogue runs it
+// 64 times per thread and tile.
+__device__ __forceinline__ float gelu_erf_fast(float g) {
+  const float x = fabsf(g) * 0.70710678118654752440f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, x, 1.f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = 1.f - poly * t * __expf(-x * x);
+  return 0.5f * g * (1.f + copysignf(e, g));
+}
 
 // =====================================================================================================
 // Persistent variant: one CTA per SM walks tiles (m fastest, so concurrently running CTAs share the weight tile in
@@ -268,6 +283,27 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                     f = unpack_bf16(rres[c][i].w); v[i * 8 + 6] += f.x; v[i * 8 + 7] += f.y;
                   }
                 }
+                if (p.geglu) {
+                  // GEGLU (lidm/modules/attention.py:36-44) fused: the weight rows were interleaved at pack time so that
+                  // every 32-column chunk holds 16 values followed by their 16 gates; 16 outputs leave per chunk
+                  const int oc = cc >> 1;
+                  uint8_t* gb = stage_out + (oc >> 6) * (BM * 128) + row * 128;
+                  const int gbase = (oc & 63) >> 3;
+#pragma unroll
+                  for (int i = 0; i < 2; ++i) {
+                    float o[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                      const float gt = v[16 + i * 8 + k];
+                      o[k] = v[i * 8 + k] * gelu_erf_fast(gt);
+                    }
+                    uint4 pk;
+                    pk.x = pack_bf16(o[0], o[1]); pk.y = pack_bf16(o[2], o[3]);
+                    pk.z = pack_bf16(o[4], o[5]); pk.w = pack_bf16(o[6], o[7]);
+                    *reinterpret_cast<uint4*>(gb + (((gbase + i) ^ (row & 7)) << 4)) = pk;
+                  }
+                  continue;
+                }
                 uint8_t* box = stage_out + (cc >> 6) * (BM * 128) + row * 128;
                 const int cbase = (cc & 63) >> 3;
 #pragma unroll
@@ -285,10 +321,17 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           fence_proxy_async();          // staging writes -> visible to the TMA engine
           named_bar_sync(2, L::EPI_THREADS);
           if (e == 0) {
+            if (p.geglu) {
 #pragma unroll
-            for (int j = 0; j < L::OUT_BOXES; ++j)
-              if (n0 + j * 64 < p.N)
-                tma_store_4d(&tmO, stage_out + j * (BM * 128), n0 + j * 64, w0, h0, b);
+              for (int j = 0; j < L::OUT_BOXES / 2; ++j)
+                if ((n0 >> 1) + j * 64 < (p.N >> 1))
+                  tma_store_4d(&tmO, stage_out + j * (BM * 128), (n0 >> 1) + j * 64, w0, h0, b);
+            } else {
+#pragma unroll
+              for (int j = 0; j < L::OUT_BOXES; ++j)
+                if (n0 + j * 64 < p.N)
+                  tma_store_4d(&tmO, stage_out + j * (BM * 128), n0 + j * 64, w0, h0, b);
+            }
             tma_store_commit();
           }
           if (p.gst != nullptr) {
@@ -590,6 +633,11 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
                                 ? 1 : 0;
   CUtensorMap tmO = tmA;
   if (use_tma_store) tmO = make_tma_act(ep.out, 64, Wbox, Hbox, 128);
+  if (ep.geglu) {
+    LIDM_REQUIRE(use_tma_store && BN >= 128 && N % 128 == 0 && ep.out.C == N / 2 && ep.residual.p == nullptr && ep.out.gst == nullptr,
+                 "GEGLU epilogue needs a bf16 TMA-store output of N/2 channels and 128-column tiles");
+    p.geglu = 1;
+  }
   if (use_tma_store && ep.out.gst != nullptr) {
     LIDM_REQUIRE(Wbox * Hbox == 128 && N % 8 == 0 && ep.out.gst_slots >= ep.out.gst_slot0 + p.tiles_per_img,
                  "GroupNorm statistics need whole 128-pixel tiles inside one sample");

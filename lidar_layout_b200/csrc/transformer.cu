@@ -1,4 +1,5 @@
-// Memory-bound pieces of the SpatialTransformer path (reference lidm/modules/attention.py:36-44, 196-215) and the
+// Memory-bound pieces of the SpatialTransformer path (reference lidm/modules/attention.py:196-215; the GEGLU gate is
+// fused into the producing GEMM's epilogue, gemm_conv.cu) and the
 // classifier-free-guidance update (reference lidm/models/diffusion/ddim.py:173-206).  Channels-last bf16 activations,
 // fp32 arithmetic.  HBM-bound: every kernel reads its input once and writes its output once.
 #include "common.h"
@@ -79,27 +80,6 @@ __global__ void layernorm_kernel(const bf16* __restrict__ x, int64_t xstride_tok
   }
 }
 
-__device__ __forceinline__ float gelu_erf(float g) { return 0.5f * g * (1.f + erff(g * 0.70710678118654752440f)); }
-
-__global__ void geglu_kernel(const bf16* __restrict__ h, int hld, bf16* __restrict__ y, int yld, int C, int64_t tokens) {
-  const int vec = C >> 3;
-  const int64_t total = tokens * vec;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % vec);
-    const int64_t tok = i / vec;
-    const uint4 a = __ldg(reinterpret_cast<const uint4*>(h + (size_t)tok * hld) + cv);
-    const uint4 g = __ldg(reinterpret_cast<const uint4*>(h + (size_t)tok * hld + C) + cv);
-    const uint32_t av[4] = {a.x, a.y, a.z, a.w}, gv[4] = {g.x, g.y, g.z, g.w};
-    uint32_t o[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 af = unpack_bf16(av[k]), gf = unpack_bf16(gv[k]);
-      o[k] = pack_bf16(af.x * gelu_erf(gf.x), af.y * gelu_erf(gf.y));
-    }
-    reinterpret_cast<uint4*>(y + (size_t)tok * yld)[cv] = make_uint4(o[0], o[1], o[2], o[3]);
-  }
-}
-
 __global__ void f32_rows_to_bf16_kernel(const float* __restrict__ x, int64_t n_valid, int64_t n_total, bf16* __restrict__ y) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_total; i += (int64_t)gridDim.x * blockDim.x)
     y[i] = __float2bfloat16(i < n_valid ? x[i] : 0.f);
@@ -147,15 +127,6 @@ void launch_layernorm(const View& x, const View& y, const float* gamma, const fl
   else if (vec <= 4) LN_LAUNCH(4);
   else LN_LAUNCH(8);
 #undef LN_LAUNCH
-  LIDM_CUDA_CHECK(cudaGetLastError());
-  LIDM_COUNT_LAUNCH(1);
-}
-
-void launch_geglu(const View& h, const View& y, cudaStream_t s) {
-  LIDM_REQUIRE(h.C == 2 * y.C && y.C % 8 == 0 && h.B == y.B && h.H == y.H && h.W == y.W, "GEGLU shapes");
-  LIDM_REQUIRE(h.hl + h.hr + y.hl + y.hr == 0 && h.ld % 8 == 0 && y.ld % 8 == 0, "GEGLU views have no halo");
-  const int64_t tokens = (int64_t)h.B * h.H * h.W;
-  geglu_kernel<<<grid_for(tokens * (y.C / 8), 256), 256, 0, s>>>(h.p, h.ld, y.p, y.ld, y.C, tokens);
   LIDM_CUDA_CHECK(cudaGetLastError());
   LIDM_COUNT_LAUNCH(1);
 }
