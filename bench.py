@@ -114,9 +114,19 @@ def dist_env():
     return rank, world, local
 
 
-def workload_config(B, world):
-    return {"workload": "unconditional LiDM KITTI-360 64x1024 (models/lidm/kitti/uncond, f_c2_p4 AE, random-init), "
-                        "DDIM-50 eta=0 + VQ decode + back-projection",
+WORKLOADS = {
+    # name: (config factory name, description, GFLOP per sample: 50 U-Net evaluations + VQ + decoder)
+    "uncond": ("kitti_uncond", "unconditional LiDM KITTI-360 64x1024 (models/lidm/kitti/uncond, f_c2_p4 AE, random-init), "
+                               "DDIM-50 eta=0 + VQ decode + back-projection", SAMPLE_GFLOP),
+    # BASELINE config 3(A): the cross-attention conditioned U-Net (SpatialTransformer blocks), synthetic (B,4,512) context
+    "cam2lidar": ("kitti_cam2lidar", "cross-attention conditioned LiDM KITTI-360 64x1024 (models/lidm/kitti/cam2lidar, "
+                                     "SpatialTransformer U-Net, context (B,4,512) synthetic, random-init), DDIM-50 eta=0 + "
+                                     "VQ decode + back-projection", 50 * 240.6 + 0.537 + 119.06),
+}
+
+
+def workload_config(B, world, name="uncond"):
+    return {"workload": WORKLOADS[name][1],
             "batch_per_gpu": B, "global_batch": B * world, "ddim_steps": DDIM_STEPS,
             "l2": "working set per step (GBs of activations + 0.5 GB weights) >> 126 MB L2",
             "parallelism": f"batch-sharded x{world}, one all-gather of range images"}
@@ -202,7 +212,7 @@ def run_gpu_arm(args):
     from lidar_layout_b200 import _lib, config as C, parallel
     from lidar_layout_b200.weights import random_state_dict
 
-    cfg = C.kitti_uncond()
+    cfg = getattr(C, WORKLOADS[args.workload][0])()
     B = args.batch
     sd = random_state_dict(cfg, 0)
     model = L.LatentDiffusion(cfg, device=dev, use_ema=False, precision=args.precision)
@@ -217,9 +227,15 @@ def run_gpu_arm(args):
     x_T_host = parallel.local_slice(x_T_global, rank, world).pin_memory()
     x_T_dev = x_T_host.to(dev)
     eng = model.engine
+    cond_kw, cond = {}, None
+    if cfg.conditioning_key == "crossattn":
+        gctx = torch.Generator().manual_seed(1007)
+        ctx_global = torch.randn((global_B, 4, cfg.unet.context_dim), generator=gctx)
+        cond = parallel.local_slice(ctx_global, rank, world).to(dev)
+        cond_kw = dict(context=cond)
 
     def device_step():
-        z, _ = eng.ddim_sample(x_T_dev, ts, table)
+        z, _ = eng.ddim_sample(x_T_dev, ts, table, **cond_kw)
         img = eng.vq_decode(z)
         xyz, mask = L.ops.backproject(img, ds.fov, ds.depth_range, ds.depth_scale, ds.log_scale)
         if world > 1:
@@ -233,7 +249,7 @@ def run_gpu_arm(args):
         # the call sequence a reference user makes (scripts/sample.py:89-110,129), host buffers in and out
         x = x_T_host.to(dev, non_blocking=True)
         with model.ema_scope("Plotting"):
-            z, _ = sampler.sample(DDIM_STEPS, batch_size=B, shape=cfg.latent_shape, eta=0.0, x_T=x)
+            z, _ = sampler.sample(DDIM_STEPS, batch_size=B, shape=cfg.latent_shape, eta=0.0, x_T=x, conditioning=cond)
         img = model.decode_first_stage(z)
         xyz, mask = L.ops.backproject(img, ds.fov, ds.depth_range, ds.depth_scale, ds.log_scale)
         if world > 1:
@@ -283,7 +299,7 @@ def run_gpu_arm(args):
     if rank == 0:
         torch.cuda.synchronize()
         _lib.profile_begin()
-        z, _ = eng.ddim_sample(x_T_dev, ts, table)
+        z, _ = eng.ddim_sample(x_T_dev, ts, table, **cond_kw)
         prof_unet = _lib.profile_end()
         _lib.profile_begin()
         img = eng.vq_decode(z)
@@ -305,11 +321,11 @@ def run_gpu_arm(args):
             "attention_TFLOPs": (prof_unet["attention"]["flops"] / (prof_unet["attention"]["ms"] * 1e-3) / 1e12
                                  if prof_unet["attention"]["ms"] > 0 else None),
             "decoder_ms": sum(v["ms"] for v in prof_dec.values()),
-            "whole_pipeline_frac_of_tensor_peak": value / world * SAMPLE_GFLOP / 1e3 / peaks["bf16_tflops_sustained"],
+            "whole_pipeline_frac_of_tensor_peak": value / world * WORKLOADS[args.workload][2] / 1e3 / peaks["bf16_tflops_sustained"],
         }
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "uncond":
         threads = os.cpu_count() or 1
         v, detail = cpu_samples_per_sec(cfg, sd, 10, 2, threads)
         cpu = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
@@ -324,7 +340,7 @@ def run_gpu_arm(args):
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (3-way bf16 operand split, fp32 accumulate and residual stream)",
             "data": "synthetic",
-            "config": workload_config(B, world),
+            "config": workload_config(B, world, args.workload),
             "ms_per_unet_step": unet_ms,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
@@ -346,6 +362,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="samples per GPU per step (BASELINE config 2: 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="uncond", choices=sorted(WORKLOADS),
+                    help="uncond = the headline (BASELINE config 2); cam2lidar = BASELINE config 3(A), reported beside it")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
                     help="bf16 = headline tensor-core path; fp32 = precise operand-split mode (parity mode)")
     args = ap.parse_args()
