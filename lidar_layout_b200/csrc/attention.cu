@@ -404,46 +404,39 @@ attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         const int g = warp - 1;
         constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV_);
         constexpr uint32_t idesc_o = make_idesc_bf16(BQ, D) | (1u << 16);     // V is an MN-major B operand
-        int js = 0, jp = 0;
+        // Per group the events come in a fixed order — s_free(j) (the softmax warps have drained S(j)) always precedes
+        // p_ready(j) — so the issuer simply blocks on them in turn: S(j+1) as soon as S(j) is drained, then P(j) V(j).
+        // mbarrier.try_wait parks the thread in hardware; a polling loop here would steal issue slots from the two
+        // softmax warps that share this warp's scheduler, and with them stall their whole group.
         mbar_wait(q_full, 0);
-        const long long t0 = clock64();
         const uint64_t qdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_Q + g * Q_BYTES));
         const uint32_t dS = tmem_base + g * BKV_;
         const uint32_t tP = tmem_base + L::P_COL + g * (BKV_ / 2);
         const uint32_t dO = tmem_base + L::O_COL + g * 32;
-        while (jp < nkv) {
-          if (js < nkv) {
-            const int j = js, st = j % KV_ST;
-            bool ok = mbar_test_wait(&kv_full[st], (j / KV_ST) & 1);
-            if (ok && j > 0) ok = mbar_test_wait(&s_free[g], (j - 1) & 1);
-            if (ok) {
-              tcgen05_fence_after();
-              const uint64_t kdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_K + st * L::KB));
-              umma_bf16_ss(dS, qdesc, kdesc, idesc_s, 0);
-              umma_bf16_ss(dS, qdesc + 2, kdesc + 2, idesc_s, 1);
-              umma_commit(&s_ready[g]);
-              js = j + 1;
-            }
-          }
-          if (jp < js) {
-            const int j = jp, st = j % KV_ST;
-            if (mbar_test_wait(&p_ready[g], j & 1)) {
-              tcgen05_fence_after();
-              const uint64_t vdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_V + st * L::KB));
+        auto issue_s = [&](int j) {
+          const int st = j % KV_ST;
+          mbar_wait(&kv_full[st], (j / KV_ST) & 1);
+          if (j > 0) mbar_wait(&s_free[g], (j - 1) & 1);
+          tcgen05_fence_after();
+          const uint64_t kdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_K + st * L::KB));
+          umma_bf16_ss(dS, qdesc, kdesc, idesc_s, 0);
+          umma_bf16_ss(dS, qdesc + 2, kdesc + 2, idesc_s, 1);
+          umma_commit(&s_ready[g]);
+        };
+        issue_s(0);
+        for (int j = 0; j < nkv; ++j) {
+          if (j + 1 < nkv) issue_s(j + 1);
+          const int st = j % KV_ST;
+          mbar_wait(&p_ready[g], j & 1);
+          tcgen05_fence_after();
+          const uint64_t vdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_V + st * L::KB));
 #pragma unroll
-              for (int kk = 0; kk < BKV_ / 16; ++kk) {
-                const uint64_t vb = vdesc + (uint64_t)((kk * 1024) >> 4);
-                umma_bf16_ts(dO, tP + kk * 8, vb, idesc_o, (j > 0 || kk != 0) ? 1u : 0u);   // 16 bf16 = 8 columns
-              }
-              umma_commit(&pv_done[g]);
-              umma_commit(&kv_empty[st]);      // this group is done with K/V tile j
-              jp = j + 1;
-            }
+          for (int kk = 0; kk < BKV_ / 16; ++kk) {
+            const uint64_t vb = vdesc + (uint64_t)((kk * 1024) >> 4);
+            umma_bf16_ts(dO, tP + kk * 8, vb, idesc_o, (j > 0 || kk != 0) ? 1u : 0u);   // 16 bf16 = 8 columns
           }
-          if (clock64() - t0 > 4000000000LL) {
-            printf("lidm: attention v4 MMA loop timeout block(%d,%d,%d) group %d\n", blockIdx.x, blockIdx.y, blockIdx.z, g);
-            __trap();
-          }
+          umma_commit(&pv_done[g]);
+          umma_commit(&kv_empty[st]);      // this group is done with K/V tile j
         }
       }
     }
