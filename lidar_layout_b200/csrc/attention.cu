@@ -38,17 +38,56 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-// 2^x on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax polynomial, max relative error 7.6e-5, far below the
-// bf16 rounding of P): takes a share of the exponentials off the MUFU pipe, which bounds this kernel (head dim 32:
-// one exponential per 128 tensor-core flops).
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -125.f);
-  const float t = x + 12582912.f;             // 1.5 * 2^23: the integer part of x lands in the low mantissa bits
-  const float f = x - (t - 12582912.f);       // f in [-0.5, 0.5]
-  float p = fmaf(0.05520551f, f, 0.24261397f);
-  p = fmaf(p, f, 0.69325477f);
-  p = fmaf(p, f, 0.9999277f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+// Blackwell's packed fp32 pair instructions (FFMA2 / FADD2): one issue slot for two lanes of work, which is what the
+// softmax warps run short of (per score: scale+subtract, exponential, row sum, bf16 pack, row max).
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7}; "
+      "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd;}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd;}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
+// 2^x for a pair on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax polynomial, max relative error 7.6e-5, far
+// below the bf16 rounding of P): takes a share of the exponentials off the MUFU pipe, which bounds this kernel (head
+// dim 32: one exponential per 128 tensor-core flops).  5 issue slots per element against MUFU's 8 busy clocks.
+__device__ __forceinline__ void ex2_poly2(float& y0, float& y1, float x0, float x1) {
+  constexpr float MAGIC = 12582912.f;         // 1.5 * 2^23: the integer part of x lands in the low mantissa bits
+  x0 = fmaxf(x0, -125.f);
+  x1 = fmaxf(x1, -125.f);
+  float t0, t1, u0, u1, f0, f1, p0, p1;
+  add2(t0, t1, x0, x1, MAGIC, MAGIC);
+  add2(u0, u1, t0, t1, -MAGIC, -MAGIC);
+  add2(f0, f1, x0, x1, -u0, -u1);             // f in [-0.5, 0.5]
+  fma2(p0, p1, f0, f1, 0.05520551f, 0.05520551f, 0.24261397f, 0.24261397f);
+  fma2(p0, p1, p0, p1, f0, f1, 0.69325477f, 0.69325477f);
+  fma2(p0, p1, p0, p1, f0, f1, 0.9999277f, 0.9999277f);
+  y0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  y1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
+// One 32-score chunk of a row: p = 2^(s*log2e - mb) as 16 bf16 pairs into pk, row sums into (s0..s3).  POLYP of every
+// 8 pairs (evenly spread) take the polynomial instead of MUFU.EX2.
+template <int POLYP>
+__device__ __forceinline__ void exp_chunk(const uint32_t (&sv)[32], float mb, uint32_t* pk, float& s0, float& s1,
+                                          float& s2, float& s3) {
+  constexpr float LOG2E = 1.4426950408889634f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float x0, x1, p0, p1;
+    fma2(x0, x1, __uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1]), LOG2E, LOG2E, -mb, -mb);
+    if (((i & 7) * POLYP) % 8 < POLYP) {
+      ex2_poly2(p0, p1, x0, x1);
+    } else {
+      p0 = ex2(x0);
+      p1 = ex2(x1);
+    }
+    if (i & 1) add2(s2, s3, s2, s3, p0, p1);
+    else add2(s0, s1, s0, s1, p0, p1);
+    pk[i] = pack_bf16(p0, p1);
+  }
 }
 
 // =====================================================================================================
@@ -340,7 +379,7 @@ struct Cfg {
   static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
 };
 
-template <int NG, int BKV_, bool POLY>
+template <int NG, int BKV_, int POLYP>
 __global__ void __launch_bounds__((Cfg<NG, BKV_>::THREADS), 1)
 attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                         bf16* __restrict__ out, int out_ld, int T, int q_col, int k_col, int v_col, int kv_len) {
@@ -506,17 +545,7 @@ attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 #pragma unroll
       for (int c = 0; c < L::NCH; ++c) {
         uint32_t* pk = &pkk[(c & 1) * 16];
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          const float p0 = ex2(fmaf(__uint_as_float(sv[c][2 * i]), LOG2E, -mb));
-          const float p1 = ex2(fmaf(__uint_as_float(sv[c][2 * i + 1]), LOG2E, -mb));
-          const float p2 = ex2(fmaf(__uint_as_float(sv[c][2 * i + 2]), LOG2E, -mb));
-          const float p3 = POLY ? ex2_poly(fmaf(__uint_as_float(sv[c][2 * i + 3]), LOG2E, -mb))
-                                : ex2(fmaf(__uint_as_float(sv[c][2 * i + 3]), LOG2E, -mb));
-          s0 += p0; s1 += p1; s2 += p2; s3 += p3;
-          pk[i] = pack_bf16(p0, p1);
-          pk[i + 1] = pack_bf16(p2, p3);
-        }
+        exp_chunk<POLYP>(sv[c], mb, pk, s0, s1, s2, s3);
         if (c & 1) {
           if (c == 1 && j > 0) {
             // P_g(j-1) V(j-1) must have drained P before it is overwritten; by now half of this tile's exponentials
@@ -557,13 +586,13 @@ attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 }
 
 // q: (B, T, q_ld) rows with the heads at columns q_col + head*32; k / v: (B, kv_rows, kv_ld) rows at columns k_col / v_col.
-template <int NG, int BKV_, bool POLY>
+template <int NG, int BKV_, int POLYP>
 void launch(const bf16* q, int q_ld, int q_col, const bf16* kv, int kv_ld, int k_col, int v_col, int kv_rows, const View& out,
             int B, int T, int heads, cudaStream_t s) {
   using L = Cfg<NG, BKV_>;
   static bool configured = false;
   if (!configured) {
-    LIDM_CUDA_CHECK(cudaFuncSetAttribute(attention_d32_v4_kernel<NG, BKV_, POLY>,
+    LIDM_CUDA_CHECK(cudaFuncSetAttribute(attention_d32_v4_kernel<NG, BKV_, POLYP>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_TOTAL));
     configured = true;
   }
@@ -571,7 +600,7 @@ void launch(const bf16* q, int q_ld, int q_col, const bf16* kv, int kv_ld, int k
   CUtensorMap tmQ = make_tma_3d(q, q_ld, T, B, (uint64_t)q_ld * 2, (uint64_t)T * q_ld * 2, D, NG >= 2 ? 256 : 128, 64);
   CUtensorMap tmKV = make_tma_3d(kv, kv_ld, kv_rows, B, (uint64_t)kv_ld * 2, (uint64_t)kv_rows * kv_ld * 2, D, BKV_, 64);
   dim3 grid(T / (NG * BQ), heads, B);
-  attention_d32_v4_kernel<NG, BKV_, POLY><<<grid, L::THREADS, L::SMEM_TOTAL, s>>>(tmQ, tmKV, out.p, out.ld, T, q_col, k_col,
+  attention_d32_v4_kernel<NG, BKV_, POLYP><<<grid, L::THREADS, L::SMEM_TOTAL, s>>>(tmQ, tmKV, out.p, out.ld, T, q_col, k_col,
                                                                                 v_col, kv_rows);
   LIDM_CUDA_CHECK(cudaGetLastError());
   LIDM_COUNT_LAUNCH(1);
@@ -608,7 +637,7 @@ struct Cfg {
   static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
 };
 
-template <int NG, int BKV_, bool POLY>
+template <int NG, int BKV_, int POLYP>
 __global__ void __launch_bounds__((Cfg<NG, BKV_>::THREADS), 1)
 attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                         bf16* __restrict__ out, int out_ld, int T, int q_col, int k_col, int v_col, int kv_len,
@@ -830,17 +859,7 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 #pragma unroll
       for (int c = 0; c < L::NCH; ++c) {
         uint32_t* pk = &pkk[(c & 1) * 16];
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          const float p0 = ex2(fmaf(__uint_as_float(sv[c][2 * i]), LOG2E, -mb));
-          const float p1 = ex2(fmaf(__uint_as_float(sv[c][2 * i + 1]), LOG2E, -mb));
-          const float p2 = ex2(fmaf(__uint_as_float(sv[c][2 * i + 2]), LOG2E, -mb));
-          const float p3 = POLY ? ex2_poly(fmaf(__uint_as_float(sv[c][2 * i + 3]), LOG2E, -mb))
-                                : ex2(fmaf(__uint_as_float(sv[c][2 * i + 3]), LOG2E, -mb));
-          s0 += p0; s1 += p1; s2 += p2; s3 += p3;
-          pk[i] = pack_bf16(p0, p1);
-          pk[i + 1] = pack_bf16(p2, p3);
-        }
+        exp_chunk<POLYP>(sv[c], mb, pk, s0, s1, s2, s3);
         if (c & 1) {
           if (c == 1 && j > 0) {
             // P_g(j-1) V(j-1) must have drained P before it is overwritten; by now half of this tile's exponentials
@@ -884,13 +903,13 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 }
 
 // q: (B, T, q_ld) rows with the heads at columns q_col + head*32; k / v: (B, kv_rows, kv_ld) rows at columns k_col / v_col.
-template <int NG, int BKV_, bool POLY>
+template <int NG, int BKV_, int POLYP>
 void launch(const bf16* q, int q_ld, int q_col, const bf16* kv, int kv_ld, int k_col, int v_col, int kv_rows, const View& out,
             int B, int T, int heads, cudaStream_t s) {
   using L = Cfg<NG, BKV_>;
   static bool configured = false;
   if (!configured) {
-    LIDM_CUDA_CHECK(cudaFuncSetAttribute(attention_d32_v5_kernel<NG, BKV_, POLY>,
+    LIDM_CUDA_CHECK(cudaFuncSetAttribute(attention_d32_v5_kernel<NG, BKV_, POLYP>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_TOTAL));
     configured = true;
   }
@@ -906,7 +925,7 @@ void launch(const bf16* q, int q_ld, int q_col, const bf16* kv, int kv_ld, int k
     LIDM_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = n_items < num_sms ? n_items : num_sms;     // one persistent CTA per SM
-  attention_d32_v5_kernel<NG, BKV_, POLY><<<grid, L::THREADS, L::SMEM_TOTAL, s>>>(tmQ, tmKV, out.p, out.ld, T, q_col, k_col,
+  attention_d32_v5_kernel<NG, BKV_, POLYP><<<grid, L::THREADS, L::SMEM_TOTAL, s>>>(tmQ, tmKV, out.p, out.ld, T, q_col, k_col,
                                                                                 v_col, kv_rows, n_qblk, heads, n_items);
   LIDM_CUDA_CHECK(cudaGetLastError());
   LIDM_COUNT_LAUNCH(1);
@@ -928,17 +947,27 @@ void launch_attention_d32_packed(const bf16* qkv, const View& out, int B, int T,
     configured = true;
   }
   CUtensorMap tm = make_tma_3d(qkv, 3 * C, T, B, (uint64_t)3 * C * 2, (uint64_t)T * 3 * C * 2, D, 128, 64);
-  // LIDM_ATTN_V4=1 moves a quarter of the exponentials onto the FMA pipe (ex2_poly); measured slower on B200 (the
-  // softmax warps are issue/latency bound, not MUFU bound), so it stays off by default.  LIDM_ATTN_V2 forces the
-  // one-tile-per-CTA kernel (the T = 128 path) everywhere.
+  // A quarter of the exponentials (2 of every 8 pairs) run as a polynomial on the FMA pipe.  Measured on B200
+  // (tests/microbench/pipe_rate.cu, exp_loop2.cu): the scheduler dispatches one warp instruction per clock and FFMA2 /
+  // FADD2 / F2FP / FMNMX3 hold it for two, so a polynomial pair costs 16 dispatch clocks - as many as the two MUFU.EX2
+  // it replaces keep the MUFU pipe busy - and the optimum is where both run out together: 2 of 8 (exp phase 2130 ->
+  // 1820 clk per tile pair in isolation; T = 2048 784 -> 738 us, T = 512 121 -> 119 us in the U-Net at B = 64);
+  // 3 of 8 is already slower.  LIDM_ATTN_POLY=0 turns it off (A/B runs); LIDM_ATTN_V2 forces the one-tile-per-CTA
+  // kernel (the T = 128 path) everywhere.
   static const bool use_v2 = getenv("LIDM_ATTN_V2") != nullptr;
-  static const int v4_mode = getenv("LIDM_ATTN_V4") ? atoi(getenv("LIDM_ATTN_V4")) : 0;
+  static const bool poly = getenv("LIDM_ATTN_POLY") ? atoi(getenv("LIDM_ATTN_POLY")) != 0 : true;
+#define LIDM_ATTN_ARGS qkv, 3 * C, 0, qkv, 3 * C, C, 2 * C, T, out, B, T, heads, s
   if (!use_v2 && T % 256 == 0) {
-    if (T / 128 < 8) v5::launch<2, 128, false>(qkv, 3 * C, 0, qkv, 3 * C, C, 2 * C, T, out, B, T, heads, s);
-    else if (v4_mode == 1) v4::launch<2, 128, true>(qkv, 3 * C, 0, qkv, 3 * C, C, 2 * C, T, out, B, T, heads, s);
-    else v4::launch<2, 128, false>(qkv, 3 * C, 0, qkv, 3 * C, C, 2 * C, T, out, B, T, heads, s);
+    if (T / 128 < 8) {
+      if (poly) v5::launch<2, 128, 2>(LIDM_ATTN_ARGS);
+      else v5::launch<2, 128, 0>(LIDM_ATTN_ARGS);
+    } else {
+      if (poly) v4::launch<2, 128, 2>(LIDM_ATTN_ARGS);
+      else v4::launch<2, 128, 0>(LIDM_ATTN_ARGS);
+    }
     return;
   }
+#undef LIDM_ATTN_ARGS
   dim3 grid(T / BQ, heads, B);
   v2::attention_d32_v2_kernel<<<grid, 192, v2::SMEM_TOTAL2, s>>>(tm, out.p, out.ld, T, C);
   LIDM_CUDA_CHECK(cudaGetLastError());
@@ -950,8 +979,8 @@ void launch_attention_d32_packed(const bf16* qkv, const View& out, int B, int T,
 void launch_cross_attention_d32(const bf16* q, int q_ld, const bf16* kv, int kv_ld, int k_col, int v_col, int L,
                                 const View& out, int B, int T, int heads, cudaStream_t s) {
   LIDM_REQUIRE(T % 128 == 0 && L >= 1, "cross attention: T must be a multiple of 128");
-  if (T % 256 == 0) v5::launch<2, 128, false>(q, q_ld, 0, kv, kv_ld, k_col, v_col, L, out, B, T, heads, s);
-  else v5::launch<1, 128, false>(q, q_ld, 0, kv, kv_ld, k_col, v_col, L, out, B, T, heads, s);
+  if (T % 256 == 0) v5::launch<2, 128, 0>(q, q_ld, 0, kv, kv_ld, k_col, v_col, L, out, B, T, heads, s);
+  else v5::launch<1, 128, 0>(q, q_ld, 0, kv, kv_ld, k_col, v_col, L, out, B, T, heads, s);
 }
 
 }  // namespace lidm

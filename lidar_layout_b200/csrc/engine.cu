@@ -1453,6 +1453,12 @@ Plan* get_plan(lidm_handle* h, std::map<int64_t, std::unique_ptr<Plan>>& cache, 
   size_t high2 = 0;
   pass(h, P.get(), false, &high2);
   if (high2 != high) throw Error(LIDM_ERR_STATE, "internal: non-deterministic activation plan");
+  // every plan owns its activation arena (GBs at large batches): keep a handful of shapes, drop the rest
+  constexpr size_t kMaxPlans = 6;
+  while (cache.size() >= kMaxPlans) {
+    LIDM_CUDA_CHECK(cudaDeviceSynchronize());     // nothing may still be running out of the arena we are about to free
+    cache.erase(cache.begin());
+  }
   Plan* ret = P.get();
   cache[key] = std::move(P);
   return ret;

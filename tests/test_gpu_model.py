@@ -110,3 +110,19 @@ def test_headline_batch_properties(built_lib):
     assert bool(torch.isfinite(e).all())
     e5 = eng.unet_forward(x[5:6], t[5:6])
     assert torch.equal(e5[0], e[5])
+
+
+def test_plan_cache_eviction_keeps_results(built_lib):
+    """The engine keeps a bounded number of per-batch-size plans (each owns an activation arena). Walking through
+    more batch sizes than it keeps must rebuild evicted plans transparently and reproduce the same bits."""
+    from lidar_layout_b200.engine import Engine
+    cfg = C.tiny()
+    eng = Engine(cfg).load_state_dict(random_state_dict(cfg, 0))
+    x_T, _, _ = inputs_for(cfg, 9, 1, seed=11)
+    x = torch.from_numpy(x_T).cuda()
+    t = torch.arange(9, device="cuda") * 100 + 3
+    first = {b: eng.unet_forward(x[:b], t[:b]).clone() for b in range(1, 10)}     # 9 shapes > cache bound
+    for b in (1, 5, 9, 2):
+        assert torch.equal(eng.unet_forward(x[:b], t[:b]), first[b])
+    img = {b: eng.vq_decode(x[:b]).clone() for b in range(1, 9)}
+    assert torch.equal(eng.vq_decode(x[:1]), img[1])
