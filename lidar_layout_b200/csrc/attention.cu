@@ -637,7 +637,7 @@ struct Cfg {
   static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
 };
 
-template <int NG, int BKV_, int POLYP>
+template <int NG, int BKV_, int POLYP, bool PP>
 __global__ void __launch_bounds__((Cfg<NG, BKV_>::THREADS), 1)
 attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                         bf16* __restrict__ out, int out_ld, int T, int q_col, int k_col, int v_col, int kv_len,
@@ -788,7 +788,7 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     constexpr float LOG2E = 1.4426950408889634f;
     int n = 0;                                     // cumulative tile index over this CTA's items (barrier phases)
     const bool restagger = nkv >= 8;
-    constexpr bool PINGPONG = NG == 2;
+    constexpr bool PINGPONG = PP;
     for (int it = 0; it < n_my; ++it) {
     int q0, head, b;
     item_coords(it, q0, head, b);
@@ -903,13 +903,13 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 }
 
 // q: (B, T, q_ld) rows with the heads at columns q_col + head*32; k / v: (B, kv_rows, kv_ld) rows at columns k_col / v_col.
-template <int NG, int BKV_, int POLYP>
+template <int NG, int BKV_, int POLYP, bool PP = (NG == 2)>
 void launch(const bf16* q, int q_ld, int q_col, const bf16* kv, int kv_ld, int k_col, int v_col, int kv_rows, const View& out,
             int B, int T, int heads, cudaStream_t s) {
   using L = Cfg<NG, BKV_>;
   static bool configured = false;
   if (!configured) {
-    LIDM_CUDA_CHECK(cudaFuncSetAttribute(attention_d32_v5_kernel<NG, BKV_, POLYP>,
+    LIDM_CUDA_CHECK(cudaFuncSetAttribute(attention_d32_v5_kernel<NG, BKV_, POLYP, PP>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_TOTAL));
     configured = true;
   }
@@ -925,7 +925,7 @@ void launch(const bf16* q, int q_ld, int q_col, const bf16* kv, int kv_ld, int k
     LIDM_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = n_items < num_sms ? n_items : num_sms;     // one persistent CTA per SM
-  attention_d32_v5_kernel<NG, BKV_, POLYP><<<grid, L::THREADS, L::SMEM_TOTAL, s>>>(tmQ, tmKV, out.p, out.ld, T, q_col, k_col,
+  attention_d32_v5_kernel<NG, BKV_, POLYP, PP><<<grid, L::THREADS, L::SMEM_TOTAL, s>>>(tmQ, tmKV, out.p, out.ld, T, q_col, k_col,
                                                                                 v_col, kv_rows, n_qblk, heads, n_items);
   LIDM_CUDA_CHECK(cudaGetLastError());
   LIDM_COUNT_LAUNCH(1);
@@ -962,8 +962,13 @@ void launch_attention_d32_packed(const bf16* qkv, const View& out, int B, int T,
       if (poly) v5::launch<2, 128, 2>(LIDM_ATTN_ARGS);
       else v5::launch<2, 128, 0>(LIDM_ATTN_ARGS);
     } else {
-      if (poly) v4::launch<2, 128, 2>(LIDM_ATTN_ARGS);
-      else v4::launch<2, 128, 0>(LIDM_ATTN_ARGS);
+      // long sequences: the same persistent kernel, but the two softmax groups free-run (staggered once per item)
+      // instead of taking turns - measured at T = 2048, B = 64: 715 us against 794 us with the ping-pong and 738 us for
+      // one item per CTA (v4, ~3.6 us of un-overlapped prologue/epilogue per item)
+      static const bool one_item = getenv("LIDM_ATTN_V4") != nullptr;
+      if (one_item) v4::launch<2, 128, 2>(LIDM_ATTN_ARGS);
+      else if (poly) v5::launch<2, 128, 2, false>(LIDM_ATTN_ARGS);
+      else v5::launch<2, 128, 0, false>(LIDM_ATTN_ARGS);
     }
     return;
   }

@@ -39,6 +39,7 @@ struct GemmKernelParams {
   const float* rowadd;
   int rowadd_ld;
   const bf16* res;
+  int n_fast;                // tile order: output-channel tiles of one pixel tile back to back (A read from HBM once)
   int res_ld, res_hl, res_Wp;
   const float* res_f32;      // fp32 channels-last residual (precise mode), no halo
   int res_f32_ld;
@@ -118,6 +119,7 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_it = p.ntaps * p.kchunks;
+  const int num_n_tiles = num_tiles / num_m_tiles;
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tmA);
@@ -138,7 +140,8 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (lane == 0) {
       int s = 0; uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile % num_m_tiles, n0 = (tile / num_m_tiles) * BN;
+        const int m_tile = p.n_fast ? tile / num_n_tiles : tile % num_m_tiles;
+        const int n0 = (p.n_fast ? tile % num_n_tiles : tile / num_m_tiles) * BN;
         const int b = m_tile / p.tiles_per_img;
         const int r = m_tile - b * p.tiles_per_img;
         const int th = r / p.tiles_w;
@@ -201,7 +204,8 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const int ab = lt & 1;
-      const int m_tile = tile % num_m_tiles, n0 = (tile / num_m_tiles) * BN;
+      const int m_tile = p.n_fast ? tile / num_n_tiles : tile % num_m_tiles;
+        const int n0 = (p.n_fast ? tile % num_n_tiles : tile / num_m_tiles) * BN;
       const int b = m_tile / p.tiles_per_img;
       const int r = m_tile - b * p.tiles_per_img;
       const int th = r / p.tiles_w;
@@ -628,6 +632,12 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
                                 128);
   const int num_m_tiles = a.B * p.tiles_per_img;
   const int num_tiles = num_m_tiles * (n_alloc / BN);
+  {
+    // 1x1 GEMMs are bound by memory, not the tensor pipe: walk the output-channel tiles of a pixel tile back to back so
+    // the A tile comes from HBM once and from L2 afterwards (LIDM_GEMM_NFAST=0 off, 2 = every GEMM; A/B switch)
+    static const int nfast = getenv("LIDM_GEMM_NFAST") ? atoi(getenv("LIDM_GEMM_NFAST")) : 1;
+    p.n_fast = (nfast == 2 || (nfast == 1 && p.ntaps == 1)) ? 1 : 0;
+  }
   const int use_tma_store = (ep.out.p != nullptr && ep.out.hl == 0 && ep.out.hr == 0 && ep.out_t == nullptr && BN >= 64 &&
                              ep.res_f32 == nullptr && ep.out_f32_nhwc == nullptr && ep.out_f32_nchw == nullptr)
                                 ? 1 : 0;

@@ -171,6 +171,25 @@ __global__ void gn_apply_gst_kernel(const bf16* __restrict__ x, int H, int W, in
   const int b = blockIdx.y;
   const int HW = H * W;
   const int gpg = cpg >> 3;      // granules per group
+  const int vec_per_pix = C >> 3;
+  const int cv = threadIdx.x % vec_per_pix;
+  const int prow = threadIdx.x / vec_per_pix;
+  const int pstride = blockDim.x / vec_per_pix;
+  const int p0 = blockIdx.x * pix_per_cta;
+  const int p1 = min(HW, p0 + pix_per_cta);
+  auto addr = [&](int pix) {
+    const int h = pix / W, w = pix - h * W;
+    return reinterpret_cast<const uint4*>(x + ((size_t)(b * H + h) * xWp + (w + xhl)) * xld) + cv;
+  };
+  // the first batch of activations does not depend on the statistics: request it before the statistics prologue so
+  // the two memory round trips overlap
+  int pix = p0 + prow;
+  const bool pre = prow < pstride && pix + 3 * pstride < p1;
+  uint4 u0 = make_uint4(0, 0, 0, 0), u1 = u0, u2 = u0, u3 = u0;
+  if (pre) {
+    u0 = __ldg(addr(pix)); u1 = __ldg(addr(pix + pstride)); u2 = __ldg(addr(pix + 2 * pstride));
+    u3 = __ldg(addr(pix + 3 * pstride));
+  }
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     float s = 0.f, q = 0.f;
     const float2* pp = reinterpret_cast<const float2*>(gst + (size_t)b * gst_slots * gst_ld) + (size_t)g * gpg;
@@ -192,10 +211,6 @@ __global__ void gn_apply_gst_kernel(const bf16* __restrict__ x, int H, int W, in
     sh[groups + g] = rsqrtf(var + eps);
   }
   __syncthreads();
-  const int vec_per_pix = C >> 3;
-  const int cv = threadIdx.x % vec_per_pix;
-  const int prow = threadIdx.x / vec_per_pix;
-  const int pstride = blockDim.x / vec_per_pix;
   if (prow >= pstride) return;
   float sc[8], sf[8];
 #pragma unroll
@@ -206,12 +221,6 @@ __global__ void gn_apply_gst_kernel(const bf16* __restrict__ x, int H, int W, in
     sc[j] = ga;
     sf[j] = __ldg(beta + c) - sh[g] * ga;
   }
-  const int p0 = blockIdx.x * pix_per_cta;
-  const int p1 = min(HW, p0 + pix_per_cta);
-  auto addr = [&](int pix) {
-    const int h = pix / W, w = pix - h * W;
-    return reinterpret_cast<const uint4*>(x + ((size_t)(b * H + h) * xWp + (w + xhl)) * xld) + cv;
-  };
   auto emit = [&](int pix, const uint4& u) {
     const int h = pix / W, w = pix - h * W;
     const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
@@ -230,10 +239,13 @@ __global__ void gn_apply_gst_kernel(const bf16* __restrict__ x, int H, int W, in
     if (w < yhr) reinterpret_cast<uint4*>(y + (rowbase + W + yhl + w) * yld)[cv] = o;
     if (w >= W - yhl) reinterpret_cast<uint4*>(y + (rowbase + (w - (W - yhl))) * yld)[cv] = o;
   };
-  int pix = p0 + prow;
+  if (pre) {
+    emit(pix, u0); emit(pix + pstride, u1); emit(pix + 2 * pstride, u2); emit(pix + 3 * pstride, u3);
+    pix += 4 * pstride;
+  }
   for (; pix + 3 * pstride < p1; pix += 4 * pstride) {
-    const uint4 u0 = __ldg(addr(pix)), u1 = __ldg(addr(pix + pstride)), u2 = __ldg(addr(pix + 2 * pstride)),
-                u3 = __ldg(addr(pix + 3 * pstride));
+    u0 = __ldg(addr(pix)); u1 = __ldg(addr(pix + pstride)); u2 = __ldg(addr(pix + 2 * pstride));
+    u3 = __ldg(addr(pix + 3 * pstride));
     emit(pix, u0); emit(pix + pstride, u1); emit(pix + 2 * pstride, u2); emit(pix + 3 * pstride, u3);
   }
   for (; pix < p1; pix += pstride) emit(pix, __ldg(addr(pix)));
