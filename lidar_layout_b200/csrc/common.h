@@ -93,6 +93,9 @@ struct GemmEpilogue {
   const float* rowadd = nullptr;   // per-sample additive term (timestep embedding): [B][rowadd_ld] or null
   int rowadd_ld = 0;               // 0 => same row for every sample
   View residual;                   // optional bf16 residual (p == null => none), same logical shape as out
+  // optional second A operand appended along K as one more (unshifted) tap: out += a2 * B[:, Kmain : Kmain + a2.C]
+  // (a ResBlock's 1x1 skip convolution folded into its second conv: one GEMM, no skip tensor written or re-read)
+  View a2;
   View out;                        // bf16 NHWC output (p == null => none); halos are written when hl/hr > 0
   // columns >= split_n go, transposed, to out_t[(b * (N - split_n) + (n - split_n)) * HW + pixel]  (V^T for attention)
   int split_n = 1 << 30;

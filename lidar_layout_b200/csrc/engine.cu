@@ -108,7 +108,7 @@ struct ConvW {
   int nseg = 1;   // operand-split segments per tap (precise mode: 3 for hi/lo inputs, 2 for exact-bf16 inputs)
 };
 struct NormW { float* gamma = nullptr; float* beta = nullptr; int C = 0; };
-struct ResW { NormW n1, n2; ConvW c1, c2, skip; bool has_skip = false; int emb_off = -1; int cin = 0, cout = 0; };
+struct ResW { NormW n1, n2; ConvW c1, c2, skip; ConvW c2s; /* conv2 with the 1x1 skip appended along K */ bool has_skip = false; int emb_off = -1; int cin = 0, cout = 0; };
 struct AttnW { NormW n; ConvW qkv, proj; int ch = 0, heads = 0; };
 // BasicTransformerBlock / SpatialTransformer weights (reference lidm/modules/attention.py:196-261)
 struct STBlockW {
@@ -700,6 +700,22 @@ struct Builder {
     View g2 = act(B, H, W, r.cout, pl, pr, &bg2);
     groupnorm(hmid, g2, r.n2, eps, true);
     release(bh);
+    static const bool no_fold = getenv("LIDM_NO_SKIP_FOLD") != nullptr;   // A/B switch
+    if (r.has_skip && r.c2s.w != nullptr && !no_fold && x.wpitch == 0) {
+      // out = conv2(h) + skip(x) as ONE GEMM: x rides along as one more K segment (GemmEpilogue::a2)
+      GemmEpilogue ep;
+      ep.bias = r.c2s.bias;
+      ep.a2 = x;
+      ep.out = dst;
+      prep_gst(ep, r.cout, r.c2s.n_alloc);
+      GemmB b; b.p = r.c2s.w; b.n_alloc = r.c2s.n_alloc; b.ld = r.c2s.k_alloc;
+      const ConvTaps taps = taps_rect(kh, kw, pl, pt);
+      const int N = r.cout;
+      op([=](cudaStream_t s) { launch_conv_gemm(g2, taps, b, N, ep, s); }, PROF_GEMM,
+         gemm_flops(g2, taps.n, N) + gemm_flops(x, 1, N), 0, gemm_label(g2, taps.n, N) + " +skip" + std::to_string(r.cin));
+      release(bg2);
+      return;
+    }
     View resid = x;
     if (r.has_skip) {
       View sk = act(B, H, W, r.cout, 0, 0, &bsk);
@@ -1537,6 +1553,30 @@ ResW pack_res(Packer& pk, const std::string& p, int cin, int cout, int kh, int k
     r.n2 = pk.norm(p + ".norm2", cout);
     r.c2 = pk.conv(p + ".conv2", cout, cout, kh, kw);
     if (cin != cout) { r.has_skip = true; r.skip = pk.conv(p + ".nin_shortcut", cout, cin, 1, 1); }
+  }
+  if (r.has_skip && !pk.precise && cin % 64 == 0 && cout % 64 == 0) {
+    // fold the 1x1 skip convolution into conv2: K = [kh*kw taps of h | x], bias = b2 + b_skip (ResBlock output =
+    // skip(x) + conv2(h)); the skip tensor is never written or re-read
+    lidm_handle* h = pk.h;
+    const std::string c2name = p + (unet ? ".out_layers.3" : ".conv2");
+    const DevTensor& t = find_raw(h, c2name + ".weight", pk.ema);
+    ConvW f;
+    f.cout = cout; f.cin = cout; f.kh = kh; f.kw = kw;
+    f.n_alloc = r.c2.n_alloc; f.nseg = 1;
+    f.k_alloc = kh * kw * cout + cin;
+    f.w = dev_alloc<bf16>(h, (size_t)f.n_alloc * f.k_alloc);
+    launch_pack_conv_weight(t.p, cout, cout, kh, kw, f.n_alloc, f.k_alloc, nullptr, nullptr, 1.f, 0, f.w, pk.s);
+    LIDM_CUDA_CHECK(cudaMemcpy2DAsync(f.w + (size_t)kh * kw * cout, (size_t)f.k_alloc * sizeof(bf16), r.skip.w,
+                                      (size_t)r.skip.k_alloc * sizeof(bf16), (size_t)cin * sizeof(bf16), r.skip.n_alloc,
+                                      cudaMemcpyDeviceToDevice, pk.s));
+    std::vector<float> b2(cout), bs(cout);
+    LIDM_CUDA_CHECK(cudaMemcpyAsync(b2.data(), r.c2.bias, cout * sizeof(float), cudaMemcpyDeviceToHost, pk.s));
+    LIDM_CUDA_CHECK(cudaMemcpyAsync(bs.data(), r.skip.bias, cout * sizeof(float), cudaMemcpyDeviceToHost, pk.s));
+    LIDM_CUDA_CHECK(cudaStreamSynchronize(pk.s));
+    for (int i = 0; i < cout; ++i) b2[i] += bs[i];
+    f.bias = dev_alloc<float>(h, cout);
+    LIDM_CUDA_CHECK(cudaMemcpy(f.bias, b2.data(), cout * sizeof(float), cudaMemcpyHostToDevice));
+    r.c2s = f;
   }
   return r;
 }

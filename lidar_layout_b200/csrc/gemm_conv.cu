@@ -33,6 +33,7 @@ struct GemmKernelParams {
   int a_coff[27];            // channel offset of the A plane read by this virtual tap (hi / lo plane)
   int b_koff[27];            // first K column of this virtual tap in the B matrix
   int kchunks;
+  int k2chunks, hl2, b2_koff;  // second A operand (GemmEpilogue::a2): K chunks, its left halo, its first B column
   int N, H, W;
   int wt_batched;
   const float* bias;
@@ -104,7 +105,8 @@ struct PersistLayout {
 template <int BN, int STAGES>
 __global__ void __launch_bounds__((PersistLayout<BN, STAGES>::THREADS), 1)
 conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const __grid_constant__ CUtensorMap tmO, const GemmKernelParams p, int num_m_tiles,
+                         const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmA2,
+                         const GemmKernelParams p, int num_m_tiles,
                          int num_tiles, int use_tma_store) {
   using L = PersistLayout<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
@@ -118,13 +120,14 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_it = p.ntaps * p.kchunks;
+  const int num_it = p.ntaps * p.kchunks + p.k2chunks;
   const int num_n_tiles = num_tiles / num_m_tiles;
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
     if (use_tma_store) prefetch_tensormap(&tmO);
+    if (p.k2chunks) prefetch_tensormap(&tmA2);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], L::EPI_WARPS); }
     fence_barrier_init();
@@ -157,6 +160,14 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                         p.wt_batched ? b : 0);
             if (++s == STAGES) { s = 0; ph ^= 1; }
           }
+        }
+        for (int kc = 0; kc < p.k2chunks; ++kc) {     // second A operand: one unshifted tap after the main K range
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + L::B_STAGE_BYTES);
+          tma_load_4d(smem + L::A_OFF + s * A_STAGE_BYTES, &tmA2, &full_bar[s], kc * BK, w0 + p.hl2, h0, b);
+          tma_load_3d(smem + L::B_OFF + s * L::B_STRIDE, &tmB, &full_bar[s], p.b2_koff + kc * BK, n0,
+                      p.wt_batched ? b : 0);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -526,7 +537,8 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 }
 
 template <int BN, int STAGES>
-void launch_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const GemmKernelParams& p,
+void launch_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmA2,
+                    const GemmKernelParams& p,
                     int num_m_tiles, int num_tiles, int use_tma_store, cudaStream_t stream) {
   using L = PersistLayout<BN, STAGES>;
   static int num_sms = 0;
@@ -538,7 +550,7 @@ void launch_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtens
     LIDM_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  conv_gemm_persist_kernel<BN, STAGES><<<grid, L::THREADS, L::TOTAL, stream>>>(tmA, tmB, tmO, p, num_m_tiles, num_tiles,
+  conv_gemm_persist_kernel<BN, STAGES><<<grid, L::THREADS, L::TOTAL, stream>>>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles,
                                                                        use_tma_store);
   LIDM_CUDA_CHECK(cudaGetLastError());
   LIDM_COUNT_LAUNCH(1);
@@ -623,8 +635,18 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
   p.ddim_x = ep.ddim_x; p.ddim_noise = ep.ddim_noise; p.ddim_x_prev = ep.ddim_x_prev;
   p.ddim_pred_x0 = ep.ddim_pred_x0; p.ddim_coef = ep.ddim_coef;
 
-  const uint64_t Ktot = (uint64_t)taps.n * nseg * a.C;
+  uint64_t Ktot = (uint64_t)taps.n * nseg * a.C;
   CUtensorMap tmA = make_tma_act(a, BK, Wbox, Hbox, 128);
+  CUtensorMap tmA2 = tmA;
+  if (ep.a2.p != nullptr) {
+    const View& a2 = ep.a2;
+    LIDM_REQUIRE(nseg == 1 && a2.H == H && a2.W == W && a2.B == a.B && a2.C % BK == 0 && a2.ld % 8 == 0 && a2.wpitch == 0 &&
+                     (reinterpret_cast<uintptr_t>(a2.p) & 15) == 0 && ep.residual.p == nullptr,
+                 "second A operand: same pixels, channels a multiple of 64, bf16 mode, no residual");
+    tmA2 = make_tma_act(a2, BK, Wbox, Hbox, 128);
+    p.k2chunks = a2.C / BK; p.hl2 = a2.hl; p.b2_koff = (int)Ktot;
+    Ktot += a2.C;
+  }
   const uint64_t wld = wtb.ld != 0 ? (uint64_t)wtb.ld : Ktot;
   LIDM_REQUIRE(wld >= Ktot && wld % 8 == 0 && (reinterpret_cast<uintptr_t>(wt) & 15) == 0, "weight operand alignment");
   CUtensorMap tmB = make_tma_3d(wt, Ktot, (uint64_t)n_alloc, wt_batched ? (uint64_t)a.B : 1, wld * 2,
@@ -655,10 +677,10 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
                  "GroupNorm statistics need whole 128-pixel tiles inside one sample");
     p.gst = ep.out.gst; p.gst_ld = ep.out.gst_ld; p.gst_slots = ep.out.gst_slots; p.gst_slot0 = ep.out.gst_slot0;
   }
-  if (BN == 256) launch_persist<256, 3>(tmA, tmB, tmO, p, num_m_tiles, num_tiles, use_tma_store, stream);
-  else if (BN == 128) launch_persist<128, 4>(tmA, tmB, tmO, p, num_m_tiles, num_tiles, use_tma_store, stream);
-  else if (BN == 64) launch_persist<64, 6>(tmA, tmB, tmO, p, num_m_tiles, num_tiles, use_tma_store, stream);
-  else launch_persist<16, 6>(tmA, tmB, tmO, p, num_m_tiles, num_tiles, use_tma_store, stream);
+  if (BN == 256) launch_persist<256, 3>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream);
+  else if (BN == 128) launch_persist<128, 4>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream);
+  else if (BN == 64) launch_persist<64, 6>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream);
+  else launch_persist<16, 6>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream);
 }
 
 }  // namespace lidm
