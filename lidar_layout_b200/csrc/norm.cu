@@ -437,7 +437,16 @@ void launch_groupnorm_from_gstats(const View& x, const View& y, const float* gam
   const int HW = x.H * x.W;
   const int pstride = threads / vec;
   // no reduction in this kernel, so the split is free to depend on the batch: aim at one resident wave of CTAs
-  const int resident = 148 * (2048 / threads);
+  // (the kernel's registers, not the thread count, limit residency: ask the runtime rather than assume 2048 threads/SM -
+  // a grid of 1.7 waves loses a quarter of the time to its ragged second wave)
+  static int occ_cache[33] = {0};
+  int& occ = occ_cache[threads / 32 <= 32 ? threads / 32 : 0];
+  if (occ == 0) {
+    LIDM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_apply_gst_kernel, threads,
+                                                                  groups * 2 * sizeof(float)));
+    if (occ < 1) occ = 1;
+  }
+  const int resident = 148 * occ;
   int nchunks = resident / x.B;
   if (nchunks < 1) nchunks = 1;
   if (nchunks > HW / pstride) nchunks = HW / pstride > 0 ? HW / pstride : 1;
