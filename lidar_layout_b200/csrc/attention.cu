@@ -728,52 +728,44 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         const int g = warp - 1;
         constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV_);
         constexpr uint32_t idesc_o = make_idesc_bf16(BQ, D) | (1u << 16);     // V is an MN-major B operand
-        // cumulative tile counters over all of this CTA's items: ns = next S to issue, np = next P*V to issue
-        int ns = 0, np = 0, it_s = 0, j_s = 0, j_p = 0;
+        // tiles are counted cumulatively over all of this CTA's items (barrier phases never reset); the issue order is
+        // fixed - S(n+1), then P(n) V(n) - and every wait parks the thread (mbar_wait), so the issuer takes no issue
+        // slots from the softmax warps that share its scheduler
         const int total = n_my * nkv;
-        const long long t0 = clock64();
         const uint32_t dS = tmem_base + g * BKV_;
         const uint32_t tP = tmem_base + L::P_COL + g * (BKV_ / 2);
         const uint32_t dO = tmem_base + L::O_COL + g * 32;
-        while (np < total) {
-          if (ns < total) {
-            const int st = ns % KV_ST;
-            bool ok = mbar_test_wait(&kv_full[st], (ns / KV_ST) & 1);
-            if (ok && j_s == 0) ok = mbar_test_wait(&q_full[it_s & 1], (it_s >> 1) & 1);
-            if (ok && ns > 0) ok = mbar_test_wait(&s_free[g], (ns - 1) & 1);
-            if (ok) {
-              tcgen05_fence_after();
-              const uint64_t qdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_Q + ((it_s & 1) * NG + g) * Q_BYTES));
-              const uint64_t kdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_K + st * L::KB));
-              umma_bf16_ss(dS, qdesc, kdesc, idesc_s, 0);
-              umma_bf16_ss(dS, qdesc + 2, kdesc + 2, idesc_s, 1);
-              umma_commit(&s_ready[g]);
-              if (j_s == nkv - 1) umma_commit(&q_empty[it_s & 1]);   // this group no longer reads the item's queries
-              ++ns;
-              if (++j_s == nkv) { j_s = 0; ++it_s; }
-            }
-          }
-          if (np < ns) {
-            const int st = np % KV_ST;
-            // p_ready of an item's first tile also implies that the softmax warps have read the previous item's O
-            if (mbar_test_wait(&p_ready[g], np & 1)) {
-              tcgen05_fence_after();
-              const uint64_t vdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_V + st * L::KB));
+        int it_s = 0, j_s = 0;                 // item / tile-in-item of the next S to issue
+        auto issue_s = [&](int ns) {
+          const int st = ns % KV_ST;
+          mbar_wait(&kv_full[st], (ns / KV_ST) & 1);
+          if (j_s == 0) mbar_wait(&q_full[it_s & 1], (it_s >> 1) & 1);
+          if (ns > 0) mbar_wait(&s_free[g], (ns - 1) & 1);
+          tcgen05_fence_after();
+          const uint64_t qdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_Q + ((it_s & 1) * NG + g) * Q_BYTES));
+          const uint64_t kdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_K + st * L::KB));
+          umma_bf16_ss(dS, qdesc, kdesc, idesc_s, 0);
+          umma_bf16_ss(dS, qdesc + 2, kdesc + 2, idesc_s, 1);
+          umma_commit(&s_ready[g]);
+          if (j_s == nkv - 1) umma_commit(&q_empty[it_s & 1]);   // this group no longer reads the item's queries
+          if (++j_s == nkv) { j_s = 0; ++it_s; }
+        };
+        if (total > 0) issue_s(0);
+        for (int np = 0, j_p = 0; np < total; ++np) {
+          if (np + 1 < total) issue_s(np + 1);
+          const int st = np % KV_ST;
+          // p_ready of an item's first tile also implies that the softmax warps have read the previous item's O
+          mbar_wait(&p_ready[g], np & 1);
+          tcgen05_fence_after();
+          const uint64_t vdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_V + st * L::KB));
 #pragma unroll
-              for (int kk = 0; kk < BKV_ / 16; ++kk) {
-                const uint64_t vb = vdesc + (uint64_t)((kk * 1024) >> 4);
-                umma_bf16_ts(dO, tP + kk * 8, vb, idesc_o, (j_p > 0 || kk != 0) ? 1u : 0u);   // 16 bf16 = 8 columns
-              }
-              umma_commit(&pv_done[g]);
-              umma_commit(&kv_empty[st]);      // this group is done with the K/V tile
-              ++np;
-              if (++j_p == nkv) j_p = 0;
-            }
+          for (int kk = 0; kk < BKV_ / 16; ++kk) {
+            const uint64_t vb = vdesc + (uint64_t)((kk * 1024) >> 4);
+            umma_bf16_ts(dO, tP + kk * 8, vb, idesc_o, (j_p > 0 || kk != 0) ? 1u : 0u);   // 16 bf16 = 8 columns
           }
-          if (clock64() - t0 > 8000000000LL) {
-            printf("lidm: attention v5 MMA loop timeout block %d group %d (S %d, PV %d of %d)\n", blockIdx.x, g, ns, np, total);
-            __trap();
-          }
+          umma_commit(&pv_done[g]);
+          umma_commit(&kv_empty[st]);      // this group is done with the K/V tile
+          if (++j_p == nkv) j_p = 0;
         }
       }
     }
