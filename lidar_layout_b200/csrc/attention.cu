@@ -6,7 +6,8 @@
 // without materialising the (B*heads, T, T) score tensor.  q / k / v are read straight out of the packed (B, T, 3C)
 // output of the qkv GEMM (or, for cross-attention, q from its own GEMM and k / v from the context projection); V is
 // consumed as an MN-major tcgen05 operand, so nothing is transposed.
-//   v4 (T a multiple of 256): two 128-row query tiles per CTA, P and O resident in tensor memory — see namespace v4.
+//   v5 (T a multiple of 256, cross-attention): persistent, two 128-row query tiles per work item, P and O resident in
+//      tensor memory - see namespace v5.
 //   v2 (T = 128 and odd multiples): one query tile per CTA, two CTAs per SM, P through swizzled shared memory.
 #include <cstdlib>
 
@@ -338,283 +339,30 @@ attention_d32_v2_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restr
 
 
 // =====================================================================================================
-// v4: NG 128-row query tiles per CTA (one softmax warpgroup each) sharing every K/V tile of BKV_ keys; nothing in
-// the softmax loop waits on the P*V product:
-//   * O accumulates in TMEM across the whole K/V loop (tcgen05.mma accumulate); the running max is only refreshed,
-//     and O rescaled in place (tcgen05.ld / scale / tcgen05.st), when some row's max grew by more than 2^8 — the
-//     result is exact because the row sum l is kept against the same (stale) max.
+// v5 (T a multiple of 256, and every cross-attention): persistent kernel, one CTA per SM walking (query block, head,
+// sample) work items; NG 128-row query tiles per item (one softmax warpgroup each) share every K/V tile of BKV_ keys.
+//   * O accumulates in TMEM across an item's whole K/V loop (tcgen05.mma accumulate); the running max is only
+//     refreshed, and O rescaled in place (tcgen05.ld / scale / tcgen05.st), when some row's max grew by more than 2^8 -
+//     the result is exact because the row sum l is kept against the same (stale) max.  Nothing in the softmax loop
+//     waits on the P*V product.
 //   * P never touches shared memory: the softmax threads write it (bf16 pairs) into tensor memory with tcgen05.st and
 //     the P*V product takes its A operand from there (tcgen05.mma [d], [a_tmem], b_desc).  With P in shared memory the
 //     N=32 P*V instructions are bound by streaming the 32 KiB P tile through the shared-memory port (measured 45 clk
 //     per M128 N32 K16 instruction against 16 ideal, tests/microbench/umma_rate.cu) on top of the 32 KiB the softmax
-//     warps store, and the single MMA-issuing thread — tcgen05.mma issue blocks until the instruction is accepted —
-//     became the critical path of the whole kernel.
+//     warps store.
 //   * S needs a single TMEM buffer per group because each softmax thread drains its whole S row into registers first
 //     and hands the buffer straight back.
-//   * the MMA thread is event driven: it polls (mbarrier.test_wait) the barriers of all groups and issues whichever
-//     of S_g(j+1) / P_g(j)V(j) is ready; the groups are started a fraction of a tile apart and stay out of phase,
-//     so one group's MUFU-bound exp phase overlaps the others' TMEM-load / max / store phases.
-//   <2,128>: 2 groups x 168 registers (whole 128-column rows in registers);  <4,64>: 4 groups x 112 registers —
-//   twice the softmax warps per scheduler for latency hiding.
+//   * one MMA-issuing thread per group (tcgen05.mma issue blocks until the tensor pipe accepts the instruction, so one
+//     thread serving both groups delays one group's S / P*V behind the other's), fixed issue order S(n+1), P(n)V(n),
+//     parked mbarrier waits.
+//   * TMEM, the barriers and the K/V ring live across items (cumulative phases) and the next item's queries load into
+//     a second buffer, so its loads and first S = Q K^T overlap the current item's tail (an item per CTA costs ~3.6 us
+//     of un-overlapped prologue/epilogue: T = 2048, B = 64: 738 -> 715 us).
+//   * the two softmax warps that share a scheduler either take strict turns at the exponential phase (PP: mbarrier
+//     ping-pong, short items: T = 512 145 -> 128 us) or free-run, started a fraction of a tile apart at every item
+//     (long items: T = 2048 715 us against 794 us with the ping-pong).
+//   * a quarter of the exponentials run as a packed polynomial on the FMA pipe (exp_chunk).
 // TMEM: S_g at columns g*BKV_, P_g (BKV_/2 columns) at NG*BKV_ + g*BKV_/2, O_g at NG*BKV_*3/2 + g*32.
-namespace v4 {
-
-constexpr int KV_ST = 4;
-constexpr float RESCALE_LOG2 = 8.f;
-
-template <int NG, int BKV_>
-struct Cfg {
-  static constexpr int KB = BKV_ * 64;                        // bytes of one K (or V) tile
-  static constexpr int OFF_Q = 0;
-  static constexpr int OFF_K = OFF_Q + NG * Q_BYTES;
-  static constexpr int OFF_V = OFF_K + KV_ST * KB;
-  static constexpr int OFF_BAR = OFF_V + KV_ST * KB;
-  static constexpr int SMEM_TOTAL = OFF_BAR + 512 + 1024;
-  static constexpr uint32_t P_COL = NG * BKV_;
-  static constexpr uint32_t O_COL = P_COL + NG * (BKV_ / 2);
-  static constexpr uint32_t TMEM_COLS = (O_COL + NG * 32) <= 256 ? 256 : 512;
-  static constexpr int THREADS = 128 + NG * 128;
-  static constexpr int NCH = BKV_ / 32;                       // 32-column chunks per S row
-  static_assert(O_COL + NG * 32 <= 512, "TMEM budget");
-  static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
-};
-
-template <int NG, int BKV_, int POLYP>
-__global__ void __launch_bounds__((Cfg<NG, BKV_>::THREADS), 1)
-attention_d32_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                        bf16* __restrict__ out, int out_ld, int T, int q_col, int k_col, int v_col, int kv_len) {
-  using L = Cfg<NG, BKV_>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
-  uint64_t* kv_full = q_full + 1;          // [KV_ST]
-  uint64_t* kv_empty = kv_full + KV_ST;    // [KV_ST]
-  uint64_t* s_ready = kv_empty + KV_ST;    // [NG]
-  uint64_t* s_free = s_ready + NG;         // [NG]
-  uint64_t* p_ready = s_free + NG;         // [NG]
-  uint64_t* pv_done = p_ready + NG;        // [NG]
-  uint64_t* stagger = pv_done + NG;        // [NG]: group g-1 -> group g, once per CTA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stagger + NG);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * (NG * BQ);
-  const int head = blockIdx.y;
-  const int b = blockIdx.z;
-  const int nkv = (kv_len + BKV_ - 1) / BKV_;   // rows past kv_len are zero-filled by TMA and masked to -inf below
-
-  if (threadIdx.x == 0) {
-    prefetch_tensormap(&tmQ);
-    prefetch_tensormap(&tmKV);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < KV_ST; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], NG); }
-    for (int g = 0; g < NG; ++g) { mbar_init(&s_ready[g], 1); mbar_init(&s_free[g], 4); mbar_init(&stagger[g], 4); }
-    for (int i = 0; i < NG; ++i) { mbar_init(&p_ready[i], 4); mbar_init(&pv_done[i], 1); }
-    fence_barrier_init();
-  }
-  if (warp == 1) { tmem_alloc(tmem_slot, L::TMEM_COLS); tmem_relinquish(); }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp < 4) {
-    if (NG == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-    if (warp == 0) {
-      if (lane == 0) {
-        mbar_arrive_expect_tx(q_full, NG * Q_BYTES);
-#pragma unroll
-        for (int i = 0; i < NG; i += 2)                                       // 256 query rows per box
-          tma_load_3d(smem + L::OFF_Q + i * Q_BYTES, &tmQ, q_full, q_col + head * D, q0 + i * BQ, b);
-        int s = 0; uint32_t ph = 0;
-        for (int j = 0; j < nkv; ++j) {
-          mbar_wait(&kv_empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&kv_full[s], 2 * L::KB);
-          tma_load_3d(smem + L::OFF_K + s * L::KB, &tmKV, &kv_full[s], k_col + head * D, j * BKV_, b);
-          tma_load_3d(smem + L::OFF_V + s * L::KB, &tmKV, &kv_full[s], v_col + head * D, j * BKV_, b);
-          if (++s == KV_ST) { s = 0; ph ^= 1; }
-        }
-      }
-    } else if (warp - 1 < NG) {
-      // one MMA-issuing thread per group (tcgen05.mma issue blocks until the tensor pipe accepts the instruction, so a
-      // single thread serving both groups delays one group's S / P*V behind the other's): each polls only its own
-      // barriers; a K/V stage goes back to the TMA warp when every group has committed its P*V on it
-      if (lane == 0) {
-        const int g = warp - 1;
-        constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV_);
-        constexpr uint32_t idesc_o = make_idesc_bf16(BQ, D) | (1u << 16);     // V is an MN-major B operand
-        // Per group the events come in a fixed order — s_free(j) (the softmax warps have drained S(j)) always precedes
-        // p_ready(j) — so the issuer simply blocks on them in turn: S(j+1) as soon as S(j) is drained, then P(j) V(j).
-        // mbarrier.try_wait parks the thread in hardware; a polling loop here would steal issue slots from the two
-        // softmax warps that share this warp's scheduler, and with them stall their whole group.
-        mbar_wait(q_full, 0);
-        const uint64_t qdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_Q + g * Q_BYTES));
-        const uint32_t dS = tmem_base + g * BKV_;
-        const uint32_t tP = tmem_base + L::P_COL + g * (BKV_ / 2);
-        const uint32_t dO = tmem_base + L::O_COL + g * 32;
-        auto issue_s = [&](int j) {
-          const int st = j % KV_ST;
-          mbar_wait(&kv_full[st], (j / KV_ST) & 1);
-          if (j > 0) mbar_wait(&s_free[g], (j - 1) & 1);
-          tcgen05_fence_after();
-          const uint64_t kdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_K + st * L::KB));
-          umma_bf16_ss(dS, qdesc, kdesc, idesc_s, 0);
-          umma_bf16_ss(dS, qdesc + 2, kdesc + 2, idesc_s, 1);
-          umma_commit(&s_ready[g]);
-        };
-        issue_s(0);
-        for (int j = 0; j < nkv; ++j) {
-          if (j + 1 < nkv) issue_s(j + 1);
-          const int st = j % KV_ST;
-          mbar_wait(&p_ready[g], j & 1);
-          tcgen05_fence_after();
-          const uint64_t vdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_V + st * L::KB));
-#pragma unroll
-          for (int kk = 0; kk < BKV_ / 16; ++kk) {
-            const uint64_t vb = vdesc + (uint64_t)((kk * 1024) >> 4);
-            umma_bf16_ts(dO, tP + kk * 8, vb, idesc_o, (j > 0 || kk != 0) ? 1u : 0u);   // 16 bf16 = 8 columns
-          }
-          umma_commit(&pv_done[g]);
-          umma_commit(&kv_empty[st]);      // this group is done with K/V tile j
-        }
-      }
-    }
-  } else {
-    if (NG == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-    const int g = (warp - 4) >> 2;                 // softmax group = query tile
-    const int qd = warp & 3;                       // TMEM lane quadrant
-    const int row = qd * 32 + lane;                // row inside the 128-row tile
-    const uint32_t tS = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + g * BKV_;
-    const uint32_t tO = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + L::O_COL + g * 32;
-    const uint32_t tP = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + L::P_COL + g * (BKV_ / 2);
-    constexpr float LOG2E = 1.4426950408889634f;
-    float m = 0.f, l = 0.f;
-    for (int j = 0; j < nkv; ++j) {
-      mbar_wait(&s_ready[g], j & 1);
-      tcgen05_fence_after();
-      uint32_t sv[L::NCH][32];
-#pragma unroll
-      for (int c = 0; c < L::NCH; ++c) tmem_ld_32x32b_x32(tS + c * 32, sv[c]);
-      tmem_ld_wait();
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[g]);      // S_g(j+1) may overwrite the TMEM buffer now
-      if (kv_len - j * BKV_ < BKV_) {               // ragged last tile (cross-attention context): mask the padding keys
-        const int valid = kv_len - j * BKV_;
-#pragma unroll
-        for (int c = 0; c < L::NCH; ++c) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i >= valid) sv[c][i] = 0xff800000u;   // -inf
-        }
-      }
-      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < L::NCH; ++c) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          m0 = max3(m0, __uint_as_float(sv[c][8 * i + 0]), __uint_as_float(sv[c][8 * i + 1]));
-          m1 = max3(m1, __uint_as_float(sv[c][8 * i + 2]), __uint_as_float(sv[c][8 * i + 3]));
-          m2 = max3(m2, __uint_as_float(sv[c][8 * i + 4]), __uint_as_float(sv[c][8 * i + 5]));
-          m3 = max3(m3, __uint_as_float(sv[c][8 * i + 6]), __uint_as_float(sv[c][8 * i + 7]));
-        }
-      }
-      const float r = max3(fmaxf(m0, m1), m2, m3);
-      if (j == 0) {
-        m = r;
-      } else if (__any_sync(0xffffffffu, (r - m) * LOG2E > RESCALE_LOG2)) {
-        // rare: refresh the running max of every row of this warp and rescale O in TMEM
-        mbar_wait(&pv_done[g], (j - 1) & 1);   // every P*V issued so far has completed
-        tcgen05_fence_after();
-        const float mn = fmaxf(m, r);
-        const float alpha = ex2((m - mn) * LOG2E);
-        uint32_t o[32];
-        tmem_ld_32x32b_x32(tO, o);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-        tmem_st_32x32b_x32(tO, o);
-        tmem_st_wait();
-        l *= alpha;
-        m = mn;
-      }
-      if (j == 0 && g > 0 && nkv > 1) mbar_wait(&stagger[g], 0);               // start a fraction of a tile apart
-      const float mb = m * LOG2E;
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      uint32_t pkk[32];
-#pragma unroll
-      for (int c = 0; c < L::NCH; ++c) {
-        uint32_t* pk = &pkk[(c & 1) * 16];
-        exp_chunk<POLYP>(sv[c], mb, pk, s0, s1, s2, s3);
-        if (c & 1) {
-          if (c == 1 && j > 0) {
-            // P_g(j-1) V(j-1) must have drained P before it is overwritten; by now half of this tile's exponentials
-            // are done, so the wait is normally free
-            mbar_wait(&pv_done[g], (j - 1) & 1);
-            tcgen05_fence_after();
-          }
-          tmem_st_32x32b_x32(tP + (c >> 1) * 32, pkk);   // 64 keys = 32 columns of bf16 pairs
-        }
-        if (c == L::NCH / NG - 1 + (L::NCH / NG == 0) && j == 0 && g + 1 < NG && lane == 0) mbar_arrive(&stagger[g + 1]);
-      }
-      l += (s0 + s1) + (s2 + s3);
-      tmem_st_wait();
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_ready[g]);
-    }
-    mbar_wait(&pv_done[g], (nkv - 1) & 1);
-    tcgen05_fence_after();
-    uint32_t o[32];
-    tmem_ld_32x32b_x32(tO, o);
-    tmem_ld_wait();
-    tcgen05_fence_before();
-    const float inv = 1.f / l;
-    bf16* op = out + ((size_t)b * T + q0 + g * 128 + row) * out_ld + head * D;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 u;
-      u.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
-      u.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
-      u.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
-      u.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
-      reinterpret_cast<uint4*>(op)[i] = u;
-    }
-  }
-  __syncthreads();
-  if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, L::TMEM_COLS); }
-}
-
-// q: (B, T, q_ld) rows with the heads at columns q_col + head*32; k / v: (B, kv_rows, kv_ld) rows at columns k_col / v_col.
-template <int NG, int BKV_, int POLYP>
-void launch(const bf16* q, int q_ld, int q_col, const bf16* kv, int kv_ld, int k_col, int v_col, int kv_rows, const View& out,
-            int B, int T, int heads, cudaStream_t s) {
-  using L = Cfg<NG, BKV_>;
-  static bool configured = false;
-  if (!configured) {
-    LIDM_CUDA_CHECK(cudaFuncSetAttribute(attention_d32_v4_kernel<NG, BKV_, POLYP>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_TOTAL));
-    configured = true;
-  }
-  LIDM_REQUIRE(T % (NG * BQ) == 0 && kv_rows >= 1, "attention tile shape");
-  CUtensorMap tmQ = make_tma_3d(q, q_ld, T, B, (uint64_t)q_ld * 2, (uint64_t)T * q_ld * 2, D, NG >= 2 ? 256 : 128, 64);
-  CUtensorMap tmKV = make_tma_3d(kv, kv_ld, kv_rows, B, (uint64_t)kv_ld * 2, (uint64_t)kv_rows * kv_ld * 2, D, BKV_, 64);
-  dim3 grid(T / (NG * BQ), heads, B);
-  attention_d32_v4_kernel<NG, BKV_, POLYP><<<grid, L::THREADS, L::SMEM_TOTAL, s>>>(tmQ, tmKV, out.p, out.ld, T, q_col, k_col,
-                                                                                v_col, kv_rows);
-  LIDM_CUDA_CHECK(cudaGetLastError());
-  LIDM_COUNT_LAUNCH(1);
-}
-
-}  // namespace v4
-
-// =====================================================================================================
-// v5: the v4 pipeline as a persistent kernel for SHORT work items (T = 512: 4 K/V tiles; cross-attention contexts: 1):
-// one CTA per SM walks (query block, head, sample) items; TMEM, barriers and the K/V ring live across items (cumulative
-// phases), the next item's queries load into a second buffer, so its loads and first S = Q K^T overlap the current
-// item's tail; and the two softmax warps that share a scheduler take strict turns at the exponential phase (mbarrier
-// ping-pong), so each runs it at the full MUFU rate.  Measured on B200 (same box, B = 64): T = 512 145 -> 128 us;
-// T = 2048 794 -> 840 us, which is why long items stay on v4 (one item per CTA, staggered free-running groups).
 namespace v5 {
 
 constexpr int KV_ST = 4;
@@ -954,12 +702,8 @@ void launch_attention_d32_packed(const bf16* qkv, const View& out, int B, int T,
       if (poly) v5::launch<2, 128, 2>(LIDM_ATTN_ARGS);
       else v5::launch<2, 128, 0>(LIDM_ATTN_ARGS);
     } else {
-      // long sequences: the same persistent kernel, but the two softmax groups free-run (staggered once per item)
-      // instead of taking turns - measured at T = 2048, B = 64: 715 us against 794 us with the ping-pong and 738 us for
-      // one item per CTA (v4, ~3.6 us of un-overlapped prologue/epilogue per item)
-      static const bool one_item = getenv("LIDM_ATTN_V4") != nullptr;
-      if (one_item) v4::launch<2, 128, 2>(LIDM_ATTN_ARGS);
-      else if (poly) v5::launch<2, 128, 2, false>(LIDM_ATTN_ARGS);
+      // long sequences: the same persistent kernel with free-running (staggered) softmax groups
+      if (poly) v5::launch<2, 128, 2, false>(LIDM_ATTN_ARGS);
       else v5::launch<2, 128, 0, false>(LIDM_ATTN_ARGS);
     }
     return;
