@@ -673,6 +673,123 @@ void launch(const bf16* q, int q_ld, int q_col, const bf16* kv, int kv_ld, int k
 
 }  // namespace v5
 
+// =====================================================================================================
+// Cross-attention against a handful of context tokens (cam2lidar: L = 4 camera tokens): the tensor-core kernel would
+// spend a whole 128-key tile, its barriers and 124 masked exponentials per row on L dot products.  Here one thread owns
+// one (pixel pair, head): q . k_l, softmax over l and sum_l p_l v_l in fp32 registers, K / V of the sample staged once
+// per CTA in shared memory as floats (rows padded to 33 per head: the heads of a warp hit different banks, the pixels
+// of a warp broadcast).  Memory-bound: reads q, writes the output, nothing else.
+namespace xs {
+
+constexpr int LMAX = 16;
+constexpr int HP = 33;   // padded floats per (token, head) row
+
+__global__ void __launch_bounds__(256)
+xattn_small_kernel(const bf16* __restrict__ q, int q_ld, const bf16* __restrict__ kv, int kv_ld, int k_col, int v_col, int L,
+                   bf16* __restrict__ out, int out_ld, int T, int heads) {
+  extern __shared__ float skv[];                     // K: [L][heads][HP], then V: same
+  const int b = blockIdx.y;
+  const int C = heads * D;
+  float* sk = skv;
+  float* sv = skv + L * heads * HP;
+  const int C8 = C >> 3;
+  for (int i = threadIdx.x; i < 2 * L * C8; i += blockDim.x) {     // 16-byte loads, all of a thread's in flight at once
+    const int isv = i >= L * C8;
+    const int r = isv ? i - L * C8 : i;
+    const int l = r / C8, c = (r - l * C8) * 8;
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(kv + ((size_t)b * L + l) * kv_ld + (isv ? v_col : k_col) + c));
+    float* dst = (isv ? sv : sk) + (l * heads + c / D) * HP + (c % D);
+    const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = unpack_bf16(uu[k]);
+      dst[2 * k] = f.x;
+      dst[2 * k + 1] = f.y;
+    }
+  }
+  __syncthreads();
+  constexpr float LOG2E = 1.4426950408889634f;
+  const int pairs = (T / 2) * heads;                 // work item = (pixel pair, head); heads fastest -> coalesced rows
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < pairs; idx += gridDim.x * blockDim.x) {
+    const int hd = idx % heads, t0 = (idx / heads) * 2;
+    float qf[2][D];
+#pragma unroll
+    for (int pp = 0; pp < 2; ++pp) {
+      const uint4* qp = reinterpret_cast<const uint4*>(q + ((size_t)b * T + t0 + pp) * q_ld + hd * D);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 u = __ldg(qp + i);
+        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = unpack_bf16(uu[k]);
+          qf[pp][i * 8 + 2 * k] = f.x;
+          qf[pp][i * 8 + 2 * k + 1] = f.y;
+        }
+      }
+    }
+    float sc[2][LMAX];
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) {
+      if (l < L) {
+        const float* kr = sk + (l * heads + hd) * HP;
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const float kd = kr[d];
+          a0 = fmaf(qf[0][d], kd, a0);
+          a1 = fmaf(qf[1][d], kd, a1);
+        }
+        sc[0][l] = a0; sc[1][l] = a1;
+        mx[0] = fmaxf(mx[0], a0); mx[1] = fmaxf(mx[1], a1);
+      }
+    }
+    float sum[2] = {0.f, 0.f};
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) {
+      if (l < L) {
+        sc[0][l] = ex2((sc[0][l] - mx[0]) * LOG2E); sum[0] += sc[0][l];
+        sc[1][l] = ex2((sc[1][l] - mx[1]) * LOG2E); sum[1] += sc[1][l];
+      }
+    }
+    float* of0 = qf[0];                              // q is dead: reuse its registers for the output rows
+    float* of1 = qf[1];
+#pragma unroll
+    for (int d = 0; d < D; ++d) { of0[d] = 0.f; of1[d] = 0.f; }
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) {
+      if (l < L) {
+        const float* vr = sv + (l * heads + hd) * HP;
+        const float p0 = sc[0][l], p1 = sc[1][l];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const float vd = vr[d];
+          of0[d] = fmaf(p0, vd, of0[d]);
+          of1[d] = fmaf(p1, vd, of1[d]);
+        }
+      }
+    }
+#pragma unroll
+    for (int pp = 0; pp < 2; ++pp) {
+      const float inv = 1.f / sum[pp];
+      const float* o = pp ? of1 : of0;
+      uint4* op = reinterpret_cast<uint4*>(out + ((size_t)b * T + t0 + pp) * out_ld + hd * D);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = pack_bf16(o[8 * i + 0] * inv, o[8 * i + 1] * inv);
+        u.y = pack_bf16(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
+        u.z = pack_bf16(o[8 * i + 4] * inv, o[8 * i + 5] * inv);
+        u.w = pack_bf16(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
+        op[i] = u;
+      }
+    }
+  }
+}
+
+}  // namespace xs
+
 }  // namespace
 
 void launch_attention_d32_packed(const bf16* qkv, const View& out, int B, int T, int heads, cudaStream_t s) {
@@ -720,6 +837,20 @@ void launch_attention_d32_packed(const bf16* qkv, const View& out, int B, int T,
 void launch_cross_attention_d32(const bf16* q, int q_ld, const bf16* kv, int kv_ld, int k_col, int v_col, int L,
                                 const View& out, int B, int T, int heads, cudaStream_t s) {
   LIDM_REQUIRE(T % 128 == 0 && L >= 1, "cross attention: T must be a multiple of 128");
+  static const bool no_small = getenv("LIDM_XATTN_TC") != nullptr;   // A/B switch: always take the tensor-core kernel
+  if (L <= xs::LMAX && !no_small && q_ld % 8 == 0 && out.ld % 8 == 0 && kv_ld % 8 == 0 && k_col % 8 == 0 && v_col % 8 == 0 &&
+      (size_t)2 * L * heads * xs::HP * sizeof(float) <= 48 * 1024) {
+    LIDM_REQUIRE(out.hl == 0 && out.hr == 0 && out.H * out.W == T && out.B == B && out.C == heads * D, "attention out view");
+    const int pairs = (T / 2) * heads;
+    int gx = (pairs + 255) / 256;
+    const int cap = (148 * 8 + B - 1) / B;           // ~4 waves at 2 CTAs per SM: measured faster than one long-running wave
+    if (gx > cap) gx = cap;
+    const size_t smem = (size_t)2 * L * heads * xs::HP * sizeof(float);
+    xs::xattn_small_kernel<<<dim3(gx, B), 256, smem, s>>>(q, q_ld, kv, kv_ld, k_col, v_col, L, out.p, out.ld, T, heads);
+    LIDM_CUDA_CHECK(cudaGetLastError());
+    LIDM_COUNT_LAUNCH(1);
+    return;
+  }
   if (T % 256 == 0) v5::launch<2, 128, 0>(q, q_ld, 0, kv, kv_ld, k_col, v_col, L, out, B, T, heads, s);
   else v5::launch<1, 128, 0>(q, q_ld, 0, kv, kv_ld, k_col, v_col, L, out, B, T, heads, s);
 }
