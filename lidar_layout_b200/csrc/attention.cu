@@ -6,9 +6,9 @@
 // without materialising the (B*heads, T, T) score tensor.  q / k / v are read straight out of the packed (B, T, 3C)
 // output of the qkv GEMM (or, for cross-attention, q from its own GEMM and k / v from the context projection); V is
 // consumed as an MN-major tcgen05 operand, so nothing is transposed.
-//   v5 (T a multiple of 256, cross-attention): persistent, two 128-row query tiles per work item, P and O resident in
-//      tensor memory - see namespace v5.
-//   v2 (T = 128 and odd multiples): one query tile per CTA, two CTAs per SM, P through swizzled shared memory.
+//   v5: persistent kernel, two 128-row query tiles per work item (one when T is an odd multiple of 128), P and O
+//       resident in tensor memory - see namespace v5.
+//   xs: CUDA-core kernel for cross-attention against a handful of context tokens.
 #include <cstdlib>
 
 #include "common.h"
@@ -20,12 +20,7 @@ namespace {
 
 constexpr int D = 32;
 constexpr int BQ = 128;
-constexpr int BKV = 128;
 constexpr int Q_BYTES = BQ * D * 2;        // 8 KiB, rows of 64 B (SWIZZLE_64B)
-constexpr int K_BYTES = BKV * D * 2;       // 8 KiB
-constexpr int P_BYTES = BQ * BKV * 2;      // 32 KiB = 2 atoms of (128 rows x 128 B)
-constexpr uint32_t TMEM_COLS = 256;
-constexpr uint32_t O_COL = 128;
 
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float r;
@@ -92,254 +87,7 @@ __device__ __forceinline__ void exp_chunk(const uint32_t (&sv)[32], float mb, ui
 }
 
 // =====================================================================================================
-// v2: one packed (B,T,3C) = [q | k | v] tensor (plain qkv GEMM output, no transposed V store).
-//   * V tile (128 keys x 32 d, 64-byte rows, SWIZZLE_64B) is consumed directly as an MN-major B operand.
-//   * S is double-buffered in TMEM (cols 0..127 / 128..255): the MMA warp issues S(j+1) while the softmax warps
-//     work on S(j); O_tile(j) = P(j) V(j) lands in the first 32 columns of the (dead) S(j) buffer.
-//   * The softmax warps defer folding O_tile(j) until after the row-max pass of tile j+1, so the PV latency is
-//     off their critical path; TMEM loads are software-pipelined (next chunk in flight while one is processed).
-namespace v2 {
-
-constexpr int KV_ST = 3;
-constexpr int OFF_Q2 = 0;
-constexpr int OFF_K2 = OFF_Q2 + Q_BYTES;
-constexpr int OFF_V2 = OFF_K2 + KV_ST * K_BYTES;
-constexpr int OFF_P2 = OFF_V2 + KV_ST * K_BYTES;     // V tile = 128 keys x 64 B = 8 KiB as well
-constexpr int OFF_BAR2 = OFF_P2 + P_BYTES;
-constexpr int SMEM_TOTAL2 = OFF_BAR2 + 256 + 1024;
-constexpr uint32_t TMEM_COLS2 = 256;
-
-// instruction descriptor with an MN-major B operand (bit 16)
-__host__ __device__ constexpr uint32_t make_idesc_bf16_bmn(int M, int N) { return make_idesc_bf16(M, N) | (1u << 16); }
-
-__global__ void __launch_bounds__(192, 2)
-attention_d32_v2_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, int out_ld, int T, int C) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR2);
-  uint64_t* kv_full = q_full + 1;
-  uint64_t* kv_empty = kv_full + KV_ST;
-  uint64_t* s_ready = kv_empty + KV_ST;   // [2]
-  uint64_t* p_ready = s_ready + 2;
-  uint64_t* o_ready = p_ready + 1;
-  uint64_t* o_free = o_ready + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * BQ;
-  const int head = blockIdx.y;
-  const int b = blockIdx.z;
-  const int nkv = T / BKV;
-
-  if (threadIdx.x == 0) {
-    prefetch_tensormap(&tmQKV);
-    mbar_init(o_free, 128);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < KV_ST; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    mbar_init(&s_ready[0], 1);
-    mbar_init(&s_ready[1], 1);
-    mbar_init(p_ready, 128);
-    mbar_init(o_ready, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) { tmem_alloc(tmem_slot, TMEM_COLS2); tmem_relinquish(); }
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, Q_BYTES);
-      tma_load_3d(smem + OFF_Q2, &tmQKV, q_full, head * D, q0, b);
-      int s = 0; uint32_t ph = 0;
-      for (int j = 0; j < nkv; ++j) {
-        mbar_wait(&kv_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&kv_full[s], 2 * K_BYTES);
-        tma_load_3d(smem + OFF_K2 + s * K_BYTES, &tmQKV, &kv_full[s], C + head * D, j * BKV, b);
-        tma_load_3d(smem + OFF_V2 + s * K_BYTES, &tmQKV, &kv_full[s], 2 * C + head * D, j * BKV, b);
-        if (++s == KV_ST) { s = 0; ph ^= 1; }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV);
-      constexpr uint32_t idesc_o = make_idesc_bf16_bmn(BQ, D);
-      const uint64_t qdesc = make_kmajor_desc<64>(smem_u32(smem + OFF_Q2));
-      const uint64_t pdesc = make_kmajor_desc<128>(smem_u32(smem + OFF_P2));
-      auto issue_s = [&](int j, int s) {
-        const uint64_t kdesc = make_kmajor_desc<64>(smem_u32(smem + OFF_K2 + s * K_BYTES));
-        const uint32_t d = tmem_base + (j & 1) * 128;
-        umma_bf16_ss(d, qdesc, kdesc, idesc_s, 0);
-        umma_bf16_ss(d, qdesc + 2, kdesc + 2, idesc_s, 1);
-        umma_commit(&s_ready[j & 1]);
-      };
-      mbar_wait(q_full, 0);
-      int s = 0; uint32_t ph = 0;        // stage / phase of tile j
-      int s1 = 0; uint32_t ph1 = 0;      // stage / phase of tile j+1 (the S prefetch)
-      mbar_wait(&kv_full[0], 0);
-      tcgen05_fence_after();
-      issue_s(0, 0);
-      if (++s1 == KV_ST) { s1 = 0; ph1 ^= 1; }
-      for (int j = 0; j < nkv; ++j) {
-        if (j + 1 < nkv) {
-          mbar_wait(&kv_full[s1], ph1);                       // K(j+1), V(j+1) landed
-          // S(j+1) reuses the TMEM buffer of S(j-1) / O_tile(j-1): wait until the softmax warps have folded it
-          if (j >= 1) mbar_wait(o_free, (j - 1) & 1);
-          tcgen05_fence_after();
-          issue_s(j + 1, s1);
-          if (++s1 == KV_ST) { s1 = 0; ph1 ^= 1; }
-        }
-        mbar_wait(p_ready, j & 1);                            // P(j) is in shared memory
-        tcgen05_fence_after();
-        // O_tile(j) = P(j) V(j): V is the MN-major operand: 8-key groups are 512 B apart, 16 keys per MMA = 1024 B
-        const uint64_t vdesc = make_kmajor_desc<64>(smem_u32(smem + OFF_V2 + s * K_BYTES));
-        const uint32_t dO = tmem_base + (j & 1) * 128;
-#pragma unroll
-        for (int kk = 0; kk < BKV / 16; ++kk) {
-          const uint64_t pa = pdesc + (uint64_t)(((kk >> 2) * (P_BYTES / 2) + (kk & 3) * 32) >> 4);
-          const uint64_t vb = vdesc + (uint64_t)((kk * 1024) >> 4);
-          umma_bf16_ss(dO, pa, vb, idesc_o, kk != 0);
-        }
-        umma_commit(o_ready);
-        umma_commit(&kv_empty[s]);
-        if (++s == KV_ST) { s = 0; ph ^= 1; }
-      }
-    }
-  } else {
-    const int qd = warp & 3;
-    const int row = qd * 32 + lane;
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(qd * 32) << 16);
-    constexpr float LOG2E = 1.4426950408889634f;
-    float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
-    float o[D];
-#pragma unroll
-    for (int i = 0; i < D; ++i) o[i] = 0.f;
-    uint8_t* prow = smem + OFF_P2 + row * 128;
-    for (int j = 0; j < nkv; ++j) {
-      const uint32_t tS = trow + (j & 1) * 128;
-      mbar_wait(&s_ready[j & 1], (j >> 1) & 1);
-      tcgen05_fence_after();
-      // ---- pass 1: row max; TMEM loads pipelined two deep, four independent 3-input max chains
-      float mx = m;
-      {
-        uint32_t ra[32], rb[32];
-        float m0 = m, m1 = m, m2 = m, m3 = m;
-        auto red = [&](const uint32_t (&r)[32]) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            m0 = max3(m0, __uint_as_float(r[8 * i + 0]), __uint_as_float(r[8 * i + 1]));
-            m1 = max3(m1, __uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3]));
-            m2 = max3(m2, __uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5]));
-            m3 = max3(m3, __uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7]));
-          }
-        };
-        tmem_ld_32x32b_x32(tS, ra);
-        tmem_ld_wait();
-        tmem_ld_32x32b_x32(tS + 32, rb);
-        red(ra);
-        tmem_ld_wait();
-        tmem_ld_32x32b_x32(tS + 64, ra);
-        red(rb);
-        tmem_ld_wait();
-        tmem_ld_32x32b_x32(tS + 96, rb);
-        red(ra);
-        tmem_ld_wait();
-        red(rb);
-        mx = max3(fmaxf(m0, m1), m2, m3);
-      }
-      const float alpha = ex2((m - mx) * LOG2E);
-      m = mx;
-      const float mb = mx * LOG2E;
-      // ---- fold O_tile(j-1) (its PV has had the whole max pass to finish); also frees P for rewriting
-      if (j > 0) {
-        mbar_wait(o_ready, (j - 1) & 1);
-        tcgen05_fence_after();
-        uint32_t raw[32];
-        tmem_ld_32x32b_x32(trow + ((j - 1) & 1) * 128, raw);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < D; ++i) o[i] = o[i] * alpha_prev + __uint_as_float(raw[i]);
-        tcgen05_fence_before();
-        mbar_arrive(o_free);      // the TMEM buffer of tile j-1 may be overwritten by S(j+1)
-      }
-      alpha_prev = alpha;
-      // ---- pass 2: P = exp2(S*log2e - m*log2e) -> bf16 -> swizzled smem; row sum in fp32
-      float sum = 0.f;
-      {
-        uint32_t ra[32], rb[32];
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        auto emit = [&](const uint32_t (&raw)[32], int c) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            const float p0 = ex2(fmaf(__uint_as_float(raw[2 * i]), LOG2E, -mb));
-            const float p1 = ex2(fmaf(__uint_as_float(raw[2 * i + 1]), LOG2E, -mb));
-            const float p2 = ex2(fmaf(__uint_as_float(raw[2 * i + 2]), LOG2E, -mb));
-            const float p3 = ex2(fmaf(__uint_as_float(raw[2 * i + 3]), LOG2E, -mb));
-            s0 += p0; s1 += p1; s2 += p2; s3 += p3;
-            pk[i] = pack_bf16(p0, p1);
-            pk[i + 1] = pack_bf16(p2, p3);
-          }
-          uint8_t* base = prow + (c >> 1) * (P_BYTES / 2);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int chunk = ((c & 1) * 4 + i) ^ (row & 7);
-            *reinterpret_cast<uint4*>(base + chunk * 16) = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-          }
-        };
-        tmem_ld_32x32b_x32(tS, ra);
-        tmem_ld_wait();
-        tmem_ld_32x32b_x32(tS + 32, rb);
-        emit(ra, 0);
-        tmem_ld_wait();
-        tmem_ld_32x32b_x32(tS + 64, ra);
-        emit(rb, 1);
-        tmem_ld_wait();
-        tmem_ld_32x32b_x32(tS + 96, rb);
-        emit(ra, 2);
-        tmem_ld_wait();
-        emit(rb, 3);
-        sum = (s0 + s1) + (s2 + s3);
-      }
-      l = l * alpha + sum;
-      fence_proxy_async();
-      tcgen05_fence_before();
-      mbar_arrive(p_ready);
-    }
-    // last tile's O
-    mbar_wait(o_ready, (nkv - 1) & 1);
-    tcgen05_fence_after();
-    {
-      uint32_t raw[32];
-      tmem_ld_32x32b_x32(trow + ((nkv - 1) & 1) * 128, raw);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < D; ++i) o[i] = o[i] * alpha_prev + __uint_as_float(raw[i]);
-    }
-    tcgen05_fence_before();
-    const float inv = 1.f / l;
-    bf16* op = out + ((size_t)b * T + q0 + row) * out_ld + head * D;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 u;
-      u.x = pack_bf16(o[8 * i + 0] * inv, o[8 * i + 1] * inv);
-      u.y = pack_bf16(o[8 * i + 2] * inv, o[8 * i + 3] * inv);
-      u.z = pack_bf16(o[8 * i + 4] * inv, o[8 * i + 5] * inv);
-      u.w = pack_bf16(o[8 * i + 6] * inv, o[8 * i + 7] * inv);
-      reinterpret_cast<uint4*>(op)[i] = u;
-    }
-  }
-  __syncthreads();
-  if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS2); }
-}
-
-}  // namespace v2
-
-
-// =====================================================================================================
-// v5 (T a multiple of 256, and every cross-attention): persistent kernel, one CTA per SM walking (query block, head,
+// v5 (every self-attention, and cross-attention against more than 16 context tokens): persistent kernel, one CTA per SM walking (query block, head,
 // sample) work items; NG 128-row query tiles per item (one softmax warpgroup each) share every K/V tile of BKV_ keys.
 //   * O accumulates in TMEM across an item's whole K/V loop (tcgen05.mma accumulate); the running max is only
 //     refreshed, and O rescaled in place (tcgen05.ld / scale / tcgen05.st), when some row's max grew by more than 2^8 -
@@ -797,39 +545,27 @@ void launch_attention_d32_packed(const bf16* qkv, const View& out, int B, int T,
   LIDM_REQUIRE(T % 128 == 0, "attention: T must be a multiple of 128");
   LIDM_REQUIRE(out.hl == 0 && out.hr == 0 && out.H * out.W == T && out.B == B && out.C == C, "attention out view");
   LIDM_REQUIRE(out.ld % 8 == 0, "attention out ld");
-  static bool configured = false;
-  if (!configured) {
-    LIDM_CUDA_CHECK(cudaFuncSetAttribute(v2::attention_d32_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         v2::SMEM_TOTAL2));
-    configured = true;
-  }
-  CUtensorMap tm = make_tma_3d(qkv, 3 * C, T, B, (uint64_t)3 * C * 2, (uint64_t)T * 3 * C * 2, D, 128, 64);
   // A quarter of the exponentials (2 of every 8 pairs) run as a polynomial on the FMA pipe.  Measured on B200
   // (tests/microbench/pipe_rate.cu, exp_loop2.cu): the scheduler dispatches one warp instruction per clock and FFMA2 /
   // FADD2 / F2FP / FMNMX3 hold it for two, so a polynomial pair costs 16 dispatch clocks - as many as the two MUFU.EX2
   // it replaces keep the MUFU pipe busy - and the optimum is where both run out together: 2 of 8 (exp phase 2130 ->
   // 1820 clk per tile pair in isolation; T = 2048 784 -> 738 us, T = 512 121 -> 119 us in the U-Net at B = 64);
-  // 3 of 8 is already slower.  LIDM_ATTN_POLY=0 turns it off (A/B runs); LIDM_ATTN_V2 forces the one-tile-per-CTA
-  // kernel (the T = 128 path) everywhere.
-  static const bool use_v2 = getenv("LIDM_ATTN_V2") != nullptr;
+  // 3 of 8 is already slower.  LIDM_ATTN_POLY=0 turns it off (A/B runs).
   static const bool poly = getenv("LIDM_ATTN_POLY") ? atoi(getenv("LIDM_ATTN_POLY")) != 0 : true;
 #define LIDM_ATTN_ARGS qkv, 3 * C, 0, qkv, 3 * C, C, 2 * C, T, out, B, T, heads, s
-  if (!use_v2 && T % 256 == 0) {
-    if (T / 128 < 8) {
-      if (poly) v5::launch<2, 128, 2>(LIDM_ATTN_ARGS);
-      else v5::launch<2, 128, 0>(LIDM_ATTN_ARGS);
-    } else {
-      // long sequences: the same persistent kernel with free-running (staggered) softmax groups
-      if (poly) v5::launch<2, 128, 2, false>(LIDM_ATTN_ARGS);
-      else v5::launch<2, 128, 0, false>(LIDM_ATTN_ARGS);
-    }
-    return;
+  // Free-running (staggered) softmax groups at every length: with the packed softmax and parked waits the strict
+  // ping-pong no longer pays even for short items (T = 512, same box: 125.0 us free-running, 128.5 us ping-pong); it
+  // stays available as the PP template flag and serves the single-tile cross-attention items.  Odd multiples of 128
+  // (T = 128: the 4x32 level) take one query tile per item; the persistent kernel beats a one-tile-per-CTA kernel with
+  // two CTAs per SM there too (35.4 against 39.5 us at B = 64).
+  if (T % 256 == 0) {
+    if (poly) v5::launch<2, 128, 2, false>(LIDM_ATTN_ARGS);
+    else v5::launch<2, 128, 0, false>(LIDM_ATTN_ARGS);
+  } else {
+    if (poly) v5::launch<1, 128, 2, false>(LIDM_ATTN_ARGS);
+    else v5::launch<1, 128, 0, false>(LIDM_ATTN_ARGS);
   }
 #undef LIDM_ATTN_ARGS
-  dim3 grid(T / BQ, heads, B);
-  v2::attention_d32_v2_kernel<<<grid, 192, v2::SMEM_TOTAL2, s>>>(tm, out.p, out.ld, T, C);
-  LIDM_CUDA_CHECK(cudaGetLastError());
-  LIDM_COUNT_LAUNCH(1);
 }
 
 // CrossAttention.forward core (reference lidm/modules/attention.py:170-193) for head dim 32: q (B,T,q_ld) against a
