@@ -66,7 +66,7 @@ __device__ __forceinline__ void ex2_poly2(float& y0, float& y1, float x0, float 
 
 // One 32-score chunk of a row: p = 2^(s*log2e - mb) as 16 bf16 pairs into pk, row sums into (s0..s3).  POLYP of every
 // 8 pairs (evenly spread) take the polynomial instead of MUFU.EX2.
-template <int POLYP>
+template <int POLYP, bool SUM>
 __device__ __forceinline__ void exp_chunk(const uint32_t (&sv)[32], float mb, uint32_t* pk, float& s0, float& s1,
                                           float& s2, float& s3) {
   constexpr float LOG2E = 1.4426950408889634f;
@@ -80,8 +80,10 @@ __device__ __forceinline__ void exp_chunk(const uint32_t (&sv)[32], float mb, ui
       p0 = ex2(x0);
       p1 = ex2(x1);
     }
-    if (i & 1) add2(s2, s3, s2, s3, p0, p1);
-    else add2(s0, s1, s0, s1, p0, p1);
+    if (SUM) {
+      if (i & 1) add2(s2, s3, s2, s3, p0, p1);
+      else add2(s0, s1, s0, s1, p0, p1);
+    }
     pk[i] = pack_bf16(p0, p1);
   }
 }
@@ -122,14 +124,16 @@ struct Cfg {
   static constexpr int OFF_Q = 0;                             // two buffers: the next work item's queries load early
   static constexpr int OFF_K = OFF_Q + 2 * NG * Q_BYTES;
   static constexpr int OFF_V = OFF_K + KV_ST * KB;
-  static constexpr int OFF_BAR = OFF_V + KV_ST * KB;
+  static constexpr int OFF_ONES = OFF_V + KV_ST * KB;          // constant second N-atom of the P*V B operand (row sums)
+  static constexpr int OFF_BAR = OFF_ONES + KB;
   static constexpr int SMEM_TOTAL = OFF_BAR + 512 + 1024;
   static constexpr uint32_t P_COL = NG * BKV_;
   static constexpr uint32_t O_COL = P_COL + NG * (BKV_ / 2);
-  static constexpr uint32_t TMEM_COLS = (O_COL + NG * 32) <= 256 ? 256 : 512;
+  static constexpr uint32_t O_STRIDE = 64;                    // 32 columns of O, column 32 = row sum (N = 48 P*V), padding
+  static constexpr uint32_t TMEM_COLS = (O_COL + NG * O_STRIDE) <= 256 ? 256 : 512;
   static constexpr int THREADS = 128 + NG * 128;
   static constexpr int NCH = BKV_ / 32;                       // 32-column chunks per S row
-  static_assert(O_COL + NG * 32 <= 512, "TMEM budget");
+  static_assert(O_COL + NG * O_STRIDE <= 512, "TMEM budget");
   static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
 };
 
@@ -139,6 +143,11 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                         bf16* __restrict__ out, int out_ld, int T, int q_col, int k_col, int v_col, int kv_len,
                         int n_qblk, int heads, int n_items) {
   using L = Cfg<NG, BKV_>;
+  // Row sums on the tensor pipe: the P*V product runs with N = 48, the B operand's second 32-column atom being a constant
+  // tile whose first column is all ones, so column 32 of O accumulates sum_k P[row][k] (of the bf16-rounded P the
+  // numerator uses) for free - an N = 48 instruction costs what N = 32 does - and the softmax warps drop one FADD2
+  // per element pair from their dispatch-bound exponential phase.
+  constexpr bool MMA_ROWSUM = true;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);   // [2]
@@ -180,6 +189,17 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, L::TMEM_COLS); tmem_relinquish(); }
+  if (MMA_ROWSUM) {
+    // ones atom: [BKV_ keys][32 columns] bf16, 64-byte rows, SWIZZLE_64B (16-byte chunk c of row r sits at chunk
+    // c ^ ((r >> 1) & 3)); column 0 = 1.0, the rest 0
+    uint4* ones = reinterpret_cast<uint4*>(smem + L::OFF_ONES);
+    for (int i = threadIdx.x; i < BKV_ * 4; i += blockDim.x) {
+      const int r = i >> 2, cphys = i & 3;
+      const int c = cphys ^ ((r >> 1) & 3);
+      ones[i] = make_uint4(c == 0 ? 0x00003f80u : 0u, 0u, 0u, 0u);   // bf16 1.0 in the low half = element 0
+    }
+    fence_proxy_async();
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -223,14 +243,14 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       if (lane == 0) {
         const int g = warp - 1;
         constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV_);
-        constexpr uint32_t idesc_o = make_idesc_bf16(BQ, D) | (1u << 16);     // V is an MN-major B operand
+        constexpr uint32_t idesc_o = make_idesc_bf16(BQ, MMA_ROWSUM ? 48 : D) | (1u << 16);   // V is an MN-major B operand
         // tiles are counted cumulatively over all of this CTA's items (barrier phases never reset); the issue order is
         // fixed - S(n+1), then P(n) V(n) - and every wait parks the thread (mbar_wait), so the issuer takes no issue
         // slots from the softmax warps that share its scheduler
         const int total = n_my * nkv;
         const uint32_t dS = tmem_base + g * BKV_;
         const uint32_t tP = tmem_base + L::P_COL + g * (BKV_ / 2);
-        const uint32_t dO = tmem_base + L::O_COL + g * 32;
+        const uint32_t dO = tmem_base + L::O_COL + g * L::O_STRIDE;
         int it_s = 0, j_s = 0;                 // item / tile-in-item of the next S to issue
         auto issue_s = [&](int ns) {
           const int st = ns % KV_ST;
@@ -253,7 +273,13 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           // p_ready of an item's first tile also implies that the softmax warps have read the previous item's O
           mbar_wait(&p_ready[g], np & 1);
           tcgen05_fence_after();
-          const uint64_t vdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_V + st * L::KB));
+          // MN-major B operand: 32-column atoms along N at the leading-byte-offset stride; the second atom is the
+          // constant ones tile, wherever this stage's V tile sits
+          uint64_t vdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_V + st * L::KB));
+          if (MMA_ROWSUM) {
+            const uint64_t lbo = (uint64_t)(L::OFF_ONES - (L::OFF_V + st * L::KB)) >> 4;
+            vdesc = (vdesc & ~(0x3FFFull << 16)) | (lbo << 16);
+          }
 #pragma unroll
           for (int kk = 0; kk < BKV_ / 16; ++kk) {
             const uint64_t vb = vdesc + (uint64_t)((kk * 1024) >> 4);
@@ -271,7 +297,7 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const int qd = warp & 3;                       // TMEM lane quadrant
     const int row = qd * 32 + lane;                // row inside the 128-row tile
     const uint32_t tS = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + g * BKV_;
-    const uint32_t tO = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + L::O_COL + g * 32;
+    const uint32_t tO = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + L::O_COL + g * L::O_STRIDE;
     const uint32_t tP = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + L::P_COL + g * (BKV_ / 2);
     constexpr float LOG2E = 1.4426950408889634f;
     int n = 0;                                     // cumulative tile index over this CTA's items (barrier phases)
@@ -326,6 +352,11 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 #pragma unroll
         for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
         tmem_st_32x32b_x32(tO, o);
+        if (MMA_ROWSUM) {
+          const uint32_t lr = tmem_ld_32x32b_x1(tO + 32);
+          tmem_ld_wait();
+          tmem_st_32x32b_x1(tO + 32, __float_as_uint(__uint_as_float(lr) * alpha));
+        }
         tmem_st_wait();
         l *= alpha;
         m = mn;
@@ -347,7 +378,7 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 #pragma unroll
       for (int c = 0; c < L::NCH; ++c) {
         uint32_t* pk = &pkk[(c & 1) * 16];
-        exp_chunk<POLYP>(sv[c], mb, pk, s0, s1, s2, s3);
+        exp_chunk<POLYP, !MMA_ROWSUM>(sv[c], mb, pk, s0, s1, s2, s3);
         if (c & 1) {
           if (c == 1 && j > 0) {
             // P_g(j-1) V(j-1) must have drained P before it is overwritten; by now half of this tile's exponentials
@@ -361,7 +392,7 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           mbar_arrive(&stagger[g + 1]);
       }
       if (PINGPONG && lane == 0) mbar_arrive(&xu_go[(g == 0 ? 4 : 0) + qd]);   // hand the MUFU unit to the partner warp
-      l += (s0 + s1) + (s2 + s3);
+      if (!MMA_ROWSUM) l += (s0 + s1) + (s2 + s3);
       tmem_st_wait();
       tcgen05_fence_before();
       __syncwarp();
@@ -371,6 +402,7 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     tcgen05_fence_after();
     uint32_t o[32];
     tmem_ld_32x32b_x32(tO, o);
+    if (MMA_ROWSUM) l = __uint_as_float(tmem_ld_32x32b_x1(tO + 32));
     tmem_ld_wait();
     tcgen05_fence_before();
     const float inv = 1.f / l;
@@ -550,8 +582,9 @@ void launch_attention_d32_packed(const bf16* qkv, const View& out, int B, int T,
   // FADD2 / F2FP / FMNMX3 hold it for two, so a polynomial pair costs 16 dispatch clocks - as many as the two MUFU.EX2
   // it replaces keep the MUFU pipe busy - and the optimum is where both run out together: 2 of 8 (exp phase 2130 ->
   // 1820 clk per tile pair in isolation; T = 2048 784 -> 738 us, T = 512 121 -> 119 us in the U-Net at B = 64);
-  // 3 of 8 is already slower.  LIDM_ATTN_POLY=0 turns it off (A/B runs).
-  static const bool poly = getenv("LIDM_ATTN_POLY") ? atoi(getenv("LIDM_ATTN_POLY")) != 0 : true;
+  // 3 of 8 is already slower (also with the row sums on the tensor pipe: T = 2048 703 us at 2 of 8, 711 us at 3 of 8).
+  // LIDM_ATTN_POLY=0 turns it off (A/B runs).
+  static const int poly = getenv("LIDM_ATTN_POLY") ? atoi(getenv("LIDM_ATTN_POLY")) : 2;
 #define LIDM_ATTN_ARGS qkv, 3 * C, 0, qkv, 3 * C, C, 2 * C, T, out, B, T, heads, s
   // Free-running (staggered) softmax groups at every length: with the packed softmax and parked waits the strict
   // ping-pong no longer pays even for short items (T = 512, same box: 125.0 us free-running, 128.5 us ping-pong); it
