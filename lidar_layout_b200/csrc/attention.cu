@@ -303,10 +303,36 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     int n = 0;                                     // cumulative tile index over this CTA's items (barrier phases)
     const bool restagger = nkv >= 8;
     constexpr bool PINGPONG = PP;
+    // An item's epilogue (read O and the row sums out of TMEM, normalise, store) is deferred into the NEXT item's first
+    // tile, after that tile's exponentials: the last P*V of the item completes while the softmax warps already work on
+    // the next item's S(0) (issued early thanks to the second Q buffer), instead of being waited for with nothing to do.
+    // p_ready of that first tile is only signalled after the read, so the P*V that overwrites O cannot overtake it.
+    int pq0 = 0, phead = 0, pb = 0;
+    bool pending = false;
+    float l = 0.f;
+    auto item_epilogue = [&]() {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(tO, o);
+      if (MMA_ROWSUM) l = __uint_as_float(tmem_ld_32x32b_x1(tO + 32));
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      const float inv = 1.f / l;
+      bf16* op = out + ((size_t)pb * T + pq0 + g * 128 + row) * out_ld + phead * D;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+        u.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+        u.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+        u.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+        reinterpret_cast<uint4*>(op)[i] = u;
+      }
+    };
     for (int it = 0; it < n_my; ++it) {
     int q0, head, b;
     item_coords(it, q0, head, b);
-    float m = 0.f, l = 0.f;
+    float m = 0.f;
+    float lcur = 0.f;                               // running row sum of this item when it is not taken from the MMA
     for (int j = 0; j < nkv; ++j, ++n) {
       mbar_wait(&s_ready[g], n & 1);
       tcgen05_fence_after();
@@ -358,7 +384,7 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           tmem_st_32x32b_x1(tO + 32, __float_as_uint(__uint_as_float(lr) * alpha));
         }
         tmem_st_wait();
-        l *= alpha;
+        lcur *= alpha;
         m = mn;
       }
       // start the groups a fraction of a tile apart (and, on long items, re-establish the offset at every item: the
@@ -380,9 +406,9 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         uint32_t* pk = &pkk[(c & 1) * 16];
         exp_chunk<POLYP, !MMA_ROWSUM>(sv[c], mb, pk, s0, s1, s2, s3);
         if (c & 1) {
-          if (c == 1 && j > 0) {
-            // P_g(j-1) V(j-1) must have drained P before it is overwritten; by now half of this tile's exponentials
-            // are done, so the wait is normally free
+          if (c == 1 && n > 0) {
+            // the previous P*V of this group (the previous tile's, or the previous item's last) must have drained P
+            // before it is overwritten; by now half of this tile's exponentials are done, so the wait is normally free
             mbar_wait(&pv_done[g], (n - 1) & 1);
             tcgen05_fence_after();
           }
@@ -392,31 +418,25 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           mbar_arrive(&stagger[g + 1]);
       }
       if (PINGPONG && lane == 0) mbar_arrive(&xu_go[(g == 0 ? 4 : 0) + qd]);   // hand the MUFU unit to the partner warp
-      if (!MMA_ROWSUM) l += (s0 + s1) + (s2 + s3);
+      if (!MMA_ROWSUM) lcur += (s0 + s1) + (s2 + s3);
       tmem_st_wait();
+      if (j == 0 && pending) {                      // previous item: its last P*V was waited for at c == 1 above
+        item_epilogue();
+        pending = false;
+      }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_ready[g]);
     }
-    mbar_wait(&pv_done[g], (n - 1) & 1);   // the item's last P*V (n already counts it)
-    tcgen05_fence_after();
-    uint32_t o[32];
-    tmem_ld_32x32b_x32(tO, o);
-    if (MMA_ROWSUM) l = __uint_as_float(tmem_ld_32x32b_x1(tO + 32));
-    tmem_ld_wait();
-    tcgen05_fence_before();
-    const float inv = 1.f / l;
-    bf16* op = out + ((size_t)b * T + q0 + g * 128 + row) * out_ld + head * D;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 u;
-      u.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
-      u.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
-      u.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
-      u.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
-      reinterpret_cast<uint4*>(op)[i] = u;
-    }
+    pq0 = q0; phead = head; pb = b;
+    if (!MMA_ROWSUM) l = lcur;
+    pending = true;
     }   // work items
+    if (pending) {
+      mbar_wait(&pv_done[g], (n - 1) & 1);   // the last item's last P*V (n already counts it)
+      tcgen05_fence_after();
+      item_epilogue();
+    }
   }
   __syncthreads();
   if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, L::TMEM_COLS); }
