@@ -155,6 +155,14 @@ int lidm_to_uint8_image(const float* x, uint8_t* out, int64_t n, void* stream);
 int lidm_compact_points(const float* xyz, const uint8_t* mask, int32_t B, int32_t HW, float* points, int32_t* counts,
                         void* stream);
 
+/* Forward of the reference's Chamfer-distance extension (lidm/eval/modules/chamfer3D/chamfer_cuda.cpp:13-15 ->
+ * chamfer3D.cu:12-155; chamfer2D/chamfer2D.cu:12-145; called from lidm/eval/metric_utils.py:414-440), stateless:
+ * xyz1 (B,N,dim), xyz2 (B,M,dim) fp32 device pointers, dim 2 or 3.  dist1 (B,N) / idx1 (B,N) int32: squared distance to
+ * and index of the nearest point of xyz2 for every point of xyz1; dist2 / idx2 (B,M) the same the other way round.
+ * Ties go to the lowest index; d = (dx*dx + dy*dy) + dz*dz with every operation rounded separately. */
+int lidm_chamfer_nn(const float* xyz1, const float* xyz2, int32_t B, int32_t N, int32_t M, int32_t dim, float* dist1,
+                    int32_t* idx1, float* dist2, int32_t* idx2, void* stream);
+
 /* ---- operator-level entry points (the same kernels the model uses; exposed for parity tests and reuse) ---------
  * All tensors fp32 NCHW device pointers; conversions to the internal channels-last bf16 layout happen inside. */
 

@@ -6,6 +6,7 @@ A drop-in for one hot path of AlanLiangC/LiDAR-Layout behind its own Python API:
     lidm.models.diffusion.ddim.DDIMSampler             -> lidar_layout_b200.DDIMSampler
     lidm.utils.lidar_utils.range2pcd / range2xyz       -> lidar_layout_b200.range2pcd / range2xyz
     scripts/sample.py custom_to_pil / custom_to_pcd / save_logs -> lidar_layout_b200.postprocess.*
+    lidm/eval/modules/chamfer{3D,2D} chamfer_3DDist / chamfer_2DDist (forward) -> lidar_layout_b200.eval_ops.*
 All GPU work goes through the C ABI in include/lidm_b200.h (liblidm_b200.so, hand-written sm_100a kernels).
 Importing the package never touches the GPU; using it without the built library or without a B200 raises.
 """
@@ -27,7 +28,7 @@ def __getattr__(name):
     if name in ("Engine",):
         from .engine import Engine
         return Engine
-    if name in ("ops", "engine", "ddim", "ddpm", "lidar_utils", "postprocess", "parallel"):
+    if name in ("ops", "engine", "ddim", "ddpm", "lidar_utils", "postprocess", "parallel", "eval_ops"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

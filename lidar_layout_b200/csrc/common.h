@@ -168,6 +168,8 @@ void launch_cfg_ddim_step(const float* x, const float* eps2, float scale, const 
 void launch_to_uint8_image(const float* x, uint8_t* y, int64_t n, cudaStream_t s);
 // xyz (B,3,HW) + mask (B,HW) -> points (B, HW, 3) with the valid points of sample b packed, in pixel order, at the
 // front of block b; counts (B) = number of valid points per sample
+// eval_kernels.cu: nearest point of set b (B,m,dim) for every point of set a (B,n,dim): squared distance + index
+void launch_nn_dist(const float* a, int n, const float* b, int m, int B, int dim, float* dist, int32_t* idx, cudaStream_t s);
 void launch_compact_points(const float* xyz, const uint8_t* mask, int B, int HW, float* points, int32_t* counts,
                            cudaStream_t s);
 

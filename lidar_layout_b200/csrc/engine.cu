@@ -2444,6 +2444,17 @@ int lidm_compact_points(const float* xyz, const uint8_t* mask, int32_t B, int32_
   });
 }
 
+int lidm_chamfer_nn(const float* xyz1, const float* xyz2, int32_t B, int32_t N, int32_t M, int32_t dim, float* dist1,
+                    int32_t* idx1, float* dist2, int32_t* idx2, void* stream) {
+  return guarded(nullptr, [&] {
+    LIDM_REQUIRE(xyz1 && xyz2 && dist1 && idx1 && dist2 && idx2, "null tensor");
+    LIDM_REQUIRE(B > 0 && N > 0 && M > 0 && (dim == 2 || dim == 3), "chamfer: B, N, M > 0 and dim 2 or 3");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    launch_nn_dist(xyz1, N, xyz2, M, B, dim, dist1, idx1, s);
+    launch_nn_dist(xyz2, M, xyz1, N, B, dim, dist2, idx2, s);
+  });
+}
+
 int lidm_op_circular_conv2d(const float* x, int32_t B, int32_t Cin, int32_t H, int32_t W, const float* weight,
                             const float* bias, int32_t Cout, int32_t kh, int32_t kw, int32_t pad_l, int32_t pad_r,
                             int32_t pad_t, int32_t pad_b, int32_t stride, const float* residual, float* out,
