@@ -57,3 +57,25 @@ def compute_pairwise_cd(x, y, module=None):
     yt = torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32)).cuda()
     dist1, dist2, _, _ = module(xt, yt)
     return ((dist1.mean() + dist2.mean()) / 2).item()
+
+
+def compute_pairwise_cd_batch(reference, samples):
+    """reference lidm/eval/metric_utils.py:426-444: one reference cloud (Nr,d) against a list of sample clouds (Ns_i,d),
+    d = 2 or 3.  Every cloud is padded to the longest one with far-away points (1e6), all pairs go through ONE kernel
+    call, and each distance is averaged over the un-padded points only.  Returns a list of floats."""
+    d = reference.ndim and reference.shape[-1]
+    if reference.ndim != 2 or d not in (2, 3):
+        raise ValueError("reference must be an (N, 2) or (N, 3) array")
+    module = chamfer_3DDist() if d == 3 else chamfer_2DDist()
+    len_r, len_s = reference.shape[0], [s.shape[0] for s in samples]
+    width = max([len_r] + len_s)
+
+    def padded(c):
+        out = np.full((width, d), 1e6, dtype=np.float32)
+        out[:c.shape[0]] = c
+        return out
+
+    ref = torch.from_numpy(padded(reference)).cuda()
+    smp = torch.from_numpy(np.stack([padded(c) for c in samples])).cuda()
+    dist_r, dist_s, _, _ = module(ref.expand_as(smp), smp)
+    return [((dist_r[i, :len_r].mean() + dist_s[i, :n].mean()) / 2.).item() for i, n in enumerate(len_s)]

@@ -46,3 +46,15 @@ def compute_pairwise_cd(x: np.ndarray, y: np.ndarray) -> float:
         x, y = x[None], y[None]
     d1, d2, _, _ = chamfer_forward(x, y)
     return float((np.float32(d1.mean(dtype=np.float32)) + np.float32(d2.mean(dtype=np.float32))) / 2)
+
+
+def compute_pairwise_cd_batch(reference: np.ndarray, samples):
+    """reference lidm/eval/metric_utils.py:426-444 (padding with 1e6 points, means over the un-padded prefix)."""
+    d = reference.shape[-1]
+    len_r, len_s = reference.shape[0], [s.shape[0] for s in samples]
+    width = max([len_r] + len_s)
+    pad = lambda c: np.vstack([c.astype(np.float32), np.full((width - c.shape[0], d), 1e6, np.float32)])
+    smp = np.stack([pad(c) for c in samples])
+    ref = np.broadcast_to(pad(reference), smp.shape)
+    d_r, d_s, _, _ = chamfer_forward(ref, smp)
+    return [float((d_r[i, :len_r].mean(dtype=np.float32) + d_s[i, :n].mean(dtype=np.float32)) / np.float32(2)) for i, n in enumerate(len_s)]

@@ -41,6 +41,17 @@ def test_padded_clouds_and_pairwise_cd(built_lib):
     assert compute_pairwise_cd(xp, y) == pytest.approx(E.compute_pairwise_cd(xp, y), rel=1e-6)
 
 
+def test_pairwise_cd_batch_ragged(built_lib):
+    from lidar_layout_b200.eval_ops import compute_pairwise_cd_batch
+    rng = np.random.default_rng(5)
+    for d in (3, 2):
+        ref = (rng.normal(size=(600, d)) * 10).astype(np.float32)
+        samples = [(rng.normal(size=(n, d)) * 10).astype(np.float32) for n in (1, 333, 600, 901)]
+        got = compute_pairwise_cd_batch(ref, samples)
+        want = E.compute_pairwise_cd_batch(ref, samples)
+        assert len(got) == 4 and got == pytest.approx(want, rel=1e-5)
+
+
 def test_properties_at_range_image_scale(built_lib):
     from lidar_layout_b200.eval_ops import chamfer_3DDist
     g = torch.Generator(device="cuda").manual_seed(0)

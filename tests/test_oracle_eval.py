@@ -38,3 +38,12 @@ def test_against_float64_brute_force():
             picked = np.take_along_axis(dd, idx[..., None].astype(np.int64), -1)[..., 0]
             np.testing.assert_allclose(picked, dd.min(-1), rtol=1e-6)   # the chosen neighbour is a (near-)minimiser
         assert i1.dtype == np.int32 and d1.dtype == np.float32
+
+
+def test_batch_padding_never_matches_real_points():
+    rng = np.random.default_rng(1)
+    ref = (rng.normal(size=(50, 3)) * 5).astype(np.float32)
+    samples = [(rng.normal(size=(n, 3)) * 5).astype(np.float32) for n in (10, 50, 80)]
+    batch = E.compute_pairwise_cd_batch(ref, samples)
+    single = [E.compute_pairwise_cd(ref, s) for s in samples]        # un-padded, one pair at a time
+    np.testing.assert_allclose(batch, single, rtol=1e-5)
