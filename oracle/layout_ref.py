@@ -1,0 +1,104 @@
+"""TEST INFRASTRUCTURE ONLY (imported by tests/ only).  CPU restatement of the condition encoder of the layout-conditioned
+LiDM ("next"): `LayoutTransformerEncoder.forward` (reference
+lidm/modules/encoders/layout_encoder.py:222-281) with its `Transformer` / `ResidualAttentionBlock` /
+`QKVMultiheadAttention` / `MLP` (layout_encoder.py:32-137), as plain functions over the module's state dict.
+Pinned bit-exactly against the unmodified reference module on CPU (tests/test_oracle_layout.py, fixture
+tests/golden/layout_encoder.npz written by oracle/make_golden_layout.py).  No CUDA path consumes it yet: it is the
+first gate for the layout U-Net row of the next round."""
+import math
+from typing import Dict, List, Sequence
+
+import torch
+import torch.nn.functional as F
+
+
+def _lin(sd, prefix, x):
+    return F.linear(x, sd[prefix + ".weight"], sd[prefix + ".bias"])
+
+
+def _ln(sd, prefix, x):
+    # LayerNorm subclass of the reference: computes in fp32, returns the input dtype (layout_encoder.py:23-29)
+    return F.layer_norm(x.float(), (x.shape[-1],), sd[prefix + ".weight"], sd[prefix + ".bias"], 1e-5).to(x.dtype)
+
+
+def qkv_multihead_attention(qkv: torch.Tensor, n_heads: int, key_padding_mask=None) -> torch.Tensor:
+    """QKVMultiheadAttention.forward (layout_encoder.py:65-84): qkv (B, L, heads*3*ch), per head [q | k | v]."""
+    bs, n_ctx, width = qkv.shape
+    ch = width // n_heads // 3
+    scale = 1 / math.sqrt(math.sqrt(ch))
+    q, k, v = torch.split(qkv.view(bs, n_ctx, n_heads, -1), ch, dim=-1)
+    w = torch.einsum("bthc,bshc->bhts", q * scale, k * scale)
+    if key_padding_mask is not None:
+        w = w.masked_fill(key_padding_mask.unsqueeze(1).unsqueeze(2), float("-inf"))
+    w = torch.softmax(w.float(), dim=-1).type(w.dtype)
+    return torch.einsum("bhts,bshc->bthc", w, v).reshape(bs, n_ctx, -1)
+
+
+def residual_attention_block(sd, prefix: str, x: torch.Tensor, n_heads: int, key_padding_mask=None) -> torch.Tensor:
+    """ResidualAttentionBlock.forward (layout_encoder.py:105-108)."""
+    h = _lin(sd, prefix + ".attn.c_qkv", _ln(sd, prefix + ".ln_1", x))
+    x = x + _lin(sd, prefix + ".attn.c_proj", qkv_multihead_attention(h, n_heads, key_padding_mask))
+    h = F.gelu(_lin(sd, prefix + ".mlp.c_fc", _ln(sd, prefix + ".ln_2", x)))
+    return x + _lin(sd, prefix + ".mlp.c_proj", h)
+
+
+def patch_boxes(feature_map_size: Sequence[int], rows: int) -> torch.Tensor:
+    """The (x0, y0, x1, y1) unit boxes of the image patches at one attention resolution (layout_encoder.py:198-204):
+    `rows` patch rows, columns scaled by the feature map's aspect ratio, row-major."""
+    cols = int(feature_map_size[1] / (feature_map_size[0] / rows))
+    di, dj = 1.0 / rows, 1.0 / cols
+    return torch.FloatTensor([(dj * j, di * i, dj * (j + 1), di * (i + 1)) for i in range(rows) for j in range(cols)])
+
+
+def layout_encoder_forward(sd: Dict[str, torch.Tensor], layout: torch.Tensor, *, num_layers: int, num_heads: int,
+                           used_condition_types: Sequence[str], feature_map_size: Sequence[int] = (8, 128),
+                           resolution_to_attention: Sequence[int] = (), use_positional_embedding: bool = False,
+                           use_final_ln: bool = True, use_key_padding_mask: bool = False,
+                           not_use_layout_fusion_module: bool = False, obj_mask=None) -> Dict[str, torch.Tensor]:
+    """LayoutTransformerEncoder.forward (layout_encoder.py:222-281).  layout (B, L, 13) = [bbox 8 | bbox_2d 4 | class 1]."""
+    out: Dict[str, torch.Tensor] = {}
+    obj_bbox, obj_bbox_2d, obj_class = torch.split(layout, [8, 4, 1], dim=-1)
+    is_valid_obj = obj_class > 0
+    obj_class = obj_class.squeeze(dim=-1)
+    xf_in = sd["positional_embedding"][None] if use_positional_embedding else None
+
+    def acc(term):
+        return term if xf_in is None else xf_in + term
+
+    if "obj_class" in used_condition_types:
+        e = F.embedding(obj_class.long(), sd["obj_class_embedding.weight"])
+        xf_in = acc(e)
+        out["obj_class_embedding"] = e.permute(0, 2, 1)
+    if "obj_bbox" in used_condition_types:
+        e = _lin(sd, "obj_bbox_embedding", obj_bbox_2d.float())
+        enc = _lin(sd, "obj_bbox_encoding", obj_bbox.float())
+        xf_in = (e + enc) if xf_in is None else (xf_in + e + enc)
+        out["obj_bbox_embedding"] = e.permute(0, 2, 1)
+        for r in resolution_to_attention:
+            pe = _lin(sd, "obj_bbox_embedding", patch_boxes(feature_map_size, r)).unsqueeze(0)
+            out[f"image_patch_bbox_embedding_for_resolution{r}"] = torch.repeat_interleave(pe, e.shape[0], dim=0).permute(0, 2, 1)
+    if "obj_mask" in used_condition_types:
+        xf_in = acc(_lin(sd, "obj_mask_embedding", obj_mask.view(*obj_mask.shape[:2], -1).float()))
+    if "is_valid_obj" in used_condition_types:
+        out["key_padding_mask"] = (1 - is_valid_obj.int()).bool()
+    kpm = out["key_padding_mask"] if use_key_padding_mask else None
+    x = xf_in.float()
+    if not not_use_layout_fusion_module:
+        for i in range(num_layers):
+            x = residual_attention_block(sd, f"transform.resblocks.{i}", x, num_heads, kpm)
+    if use_final_ln:
+        x = _ln(sd, "final_ln", x)
+    out["xf_proj"] = _lin(sd, "transformer_proj", x[:, 0])
+    out["xf_out"] = x.permute(0, 2, 1)
+    return out
+
+
+def synthetic_layout(B: int, L: int, n_classes: int, seed: int) -> torch.Tensor:
+    """A (B, L, 13) layout tensor with the reference's field order; trailing objects of each sample are padding (class 0)."""
+    g = torch.Generator().manual_seed(seed)
+    box = torch.rand(B, L, 8, generator=g) * 2 - 1
+    box2d = torch.rand(B, L, 4, generator=g)
+    cls = torch.randint(1, n_classes, (B, L, 1), generator=g).float()
+    for b in range(B):
+        cls[b, L - 1 - (b % 3):] = 0
+    return torch.cat([box, box2d, cls], dim=-1)
