@@ -102,3 +102,55 @@ def synthetic_layout(B: int, L: int, n_classes: int, seed: int) -> torch.Tensor:
     for b in range(B):
         cls[b, L - 1 - (b % 3):] = 0
     return torch.cat([box, box2d, cls], dim=-1)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# ObjectAwareCrossAttention (reference lidm/modules/unets/object_cross_unet.py:380-565): every image token attends to
+# the image tokens AND the layout tokens; queries / keys are [content | positional] halves (head width 2 x C / heads),
+# values are content only.
+
+def _gn32(sd, prefix, x):
+    # normalization() = GroupNorm32(32, C) computing in fp32 (lidm/modules/unets/nn.py:17-19,93-100)
+    return F.group_norm(x.float(), 32, sd[prefix + ".weight"], sd[prefix + ".bias"], 1e-5).type(x.dtype)
+
+
+def _conv1(sd, prefix, x):
+    return F.conv1d(x, sd[prefix + ".weight"], sd[prefix + ".bias"])
+
+
+def object_aware_cross_attention(sd: Dict[str, torch.Tensor], x: torch.Tensor, cond: Dict[str, torch.Tensor], *,
+                                 num_heads: int, resolution_rows: int, pos_scale: float = 1.0, norm_first: bool = False,
+                                 norm_for_obj_embedding: bool = False) -> torch.Tensor:
+    """ObjectAwareCrossAttention.forward (object_cross_unet.py:447-565, use_key_padding_mask False as shipped).
+    x (B, C, H, W); cond = outputs of the layout encoder.  Returns x + proj_out(attention)."""
+    b, c, *spatial = x.shape
+    x3 = x.reshape(b, c, -1)
+    qkv = _conv1(sd, "qkv_projector", _gn32(sd, "norm_for_qkv", x3))
+    C, L1 = c, qkv.shape[2]
+    L2 = cond["obj_bbox_embedding"].shape[-1]
+    cp = int(C * pos_scale)
+
+    def positional(src, norm_name):
+        if norm_first:
+            return _conv1(sd, "layout_position_embedding_projector", _gn32(sd, norm_name, src))
+        return _gn32(sd, norm_name, _conv1(sd, "layout_position_embedding_projector", src))
+
+    img_pos = positional(cond[f"image_patch_bbox_embedding_for_resolution{resolution_rows}"],
+                         "norm_for_image_patch_positional_embedding").reshape(b * num_heads, cp // num_heads, L1)
+    q_c, k_c, v_c = (t.reshape(b * num_heads, C // num_heads, L1) for t in qkv.split(C, dim=1))
+    q_img = torch.cat([q_c, img_pos], dim=1)
+    k_img = torch.cat([k_c, img_pos], dim=1)
+    lay_pos = positional(cond["obj_bbox_embedding"], "norm_for_layout_positional_embedding").reshape(
+        b * num_heads, cp // num_heads, L2)
+    xf = _gn32(sd, "norm_for_obj_embedding", cond["xf_out"]) if norm_for_obj_embedding else cond["xf_out"]
+    content = (xf + _gn32(sd, "norm_for_obj_class_embedding", cond["obj_class_embedding"])) / 2
+    k_l, v_l = _conv1(sd, "layout_content_embedding_projector", content).split(C, dim=1)
+    k_lay = torch.cat([k_l.reshape(b * num_heads, C // num_heads, L2), lay_pos], dim=1)
+    v_lay = v_l.reshape(b * num_heads, C // num_heads, L2)
+    k_mix = torch.cat([k_img, k_lay], dim=2)
+    v_mix = torch.cat([v_c, v_lay], dim=2)
+    scale = 1 / math.sqrt(math.sqrt(int((1 + pos_scale) * C) // num_heads))
+    w = torch.einsum("bct,bcs->bts", q_img * scale, k_mix * scale)
+    w = torch.softmax(w.float(), dim=-1).type(w.dtype)
+    a = torch.einsum("bts,bcs->bct", w, v_mix).reshape(b, C, L1)
+    return (x3 + _conv1(sd, "proj_out", a)).reshape(b, c, *spatial)

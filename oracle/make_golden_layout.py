@@ -11,6 +11,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = "/root/reference/lidm/modules/encoders/layout_encoder.py"
+REF_ROOT = "/root/reference"
 
 CASES = {
     # the structure of the nuScenes layout2lidar configuration (models/lidm/nuscenes/layout2lidar/config.yaml:64-82: 13
@@ -60,6 +61,25 @@ def main():
             out[f"{name}/layout"] = layout.numpy()
             for k, v in res.items():
                 out[f"{name}/out/{k}"] = v.numpy()
+        # ObjectAwareCrossAttention of the layout U-Net (lidm/modules/unets/object_cross_unet.py:380-565) on the "cfg"
+        # encoder outputs: 128 channels = 2 heads of 64 (+64 positional), 2x32 feature map (attention resolution 2),
+        # both norm orders; every parameter randomised (proj_out is zero-initialised in the reference)
+        sys.path.insert(0, REF_ROOT)
+        from lidm.modules.unets.object_cross_unet import ObjectAwareCrossAttention
+        cond = {k[len("cfg/out/"):]: torch.from_numpy(v) for k, v in out.items() if k.startswith("cfg/out/")}
+        for tag, norm_first, norm_obj in (("oaca", False, False), ("oaca_nf", True, True)):
+            torch.manual_seed(2)
+            blk = ObjectAwareCrossAttention(128, num_head_channels=64, encoder_channels=64, ds=4, resolution=[2, 32],
+                                            type="input", norm_first=norm_first, norm_for_obj_embedding=norm_obj).eval()
+            with torch.no_grad():
+                for prm in blk.parameters():
+                    prm.normal_(0, 0.08)
+                x = torch.randn(3, 128, 2, 32)
+                y, _ = blk(x, cond)
+            for k, v in blk.state_dict().items():
+                out[f"{tag}/sd/{k}"] = v.numpy()
+            out[f"{tag}/x"] = x.numpy()
+            out[f"{tag}/y"] = y.numpy()
     finally:
         torch.Tensor.cuda = orig_cuda
     path = os.path.join(ROOT, "tests", "golden", "layout_encoder.npz")

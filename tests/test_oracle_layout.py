@@ -39,3 +39,18 @@ def test_shapes_of_the_shipped_configuration():
         assert g[f"cfg/out/image_patch_bbox_embedding_for_resolution{r}"].shape == (3, 64, n)
         assert LR.patch_boxes([8, 128], r).shape == (n, 4)
     assert g["cfg/out/key_padding_mask"].dtype == np.bool_
+
+
+@pytest.mark.parametrize("tag,norm_first,norm_obj", [("oaca", False, False), ("oaca_nf", True, True)])
+def test_object_aware_cross_attention_bit_exact(tag, norm_first, norm_obj):
+    """ObjectAwareCrossAttention (object_cross_unet.py:380-565): image tokens attend to image + layout tokens with
+    [content | positional] query / key halves; pinned on the reference module's output for both norm orders."""
+    g = np.load(GOLD)
+    sd = {k[len(tag) + 4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith(tag + "/sd/")}
+    cond = {k[len("cfg/out/"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("cfg/out/")}
+    y = LR.object_aware_cross_attention(sd, torch.from_numpy(g[tag + "/x"]), cond, num_heads=2, resolution_rows=2,
+                                        norm_first=norm_first, norm_for_obj_embedding=norm_obj)
+    want = g[tag + "/y"]
+    assert y.shape == want.shape == (3, 128, 2, 32)
+    np.testing.assert_array_equal(y.numpy(), want)
+    assert float(np.abs(want - g[tag + "/x"]).max()) > 1e-2      # the block really did something (proj_out randomised)
