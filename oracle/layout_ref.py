@@ -154,3 +154,117 @@ def object_aware_cross_attention(sd: Dict[str, torch.Tensor], x: torch.Tensor, c
     w = torch.softmax(w.float(), dim=-1).type(w.dtype)
     a = torch.einsum("bts,bcs->bct", w, v_mix).reshape(b, C, L1)
     return (x3 + _conv1(sd, "proj_out", a)).reshape(b, c, *spatial)
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# LayoutDiffusionUNetModel (reference lidm/modules/unets/object_cross_unet.py:632-952): guided-diffusion style U-Net with
+# FiLM (scale-shift) ResBlocks, ResBlock up/down-sampling, ZERO-padded 3x3 convs and ObjectAwareCrossAttention blocks.
+
+def _silu(x):
+    return x * torch.sigmoid(x)        # SiLU of the reference (object_cross_unet.py:44-47)
+
+
+def _conv2(sd, prefix, x, padding):
+    return F.conv2d(x, sd[prefix + ".weight"], sd[prefix + ".bias"], padding=padding)
+
+
+def timestep_embedding(timesteps: torch.Tensor, dim: int, max_period: int = 10000) -> torch.Tensor:
+    """lidm/modules/unets/nn.py:103-121: [cos | sin] halves."""
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    args = timesteps[:, None].float() * freqs[None]
+    emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+    if dim % 2:
+        emb = torch.cat([emb, torch.zeros_like(emb[:, :1])], dim=-1)
+    return emb
+
+
+def layout_res_block(sd, prefix: str, x: torch.Tensor, emb: torch.Tensor, *, up: bool = False, down: bool = False,
+                     use_scale_shift_norm: bool = True) -> torch.Tensor:
+    """ResBlock.forward (object_cross_unet.py:253-283); Upsample / Downsample without conv (112-171)."""
+    h = _silu(_gn32(sd, prefix + ".in_layers.0", x))
+    if up:
+        h, x = (F.interpolate(t, scale_factor=2, mode="nearest") for t in (h, x))
+    elif down:
+        h, x = (F.avg_pool2d(t, kernel_size=2, stride=2) for t in (h, x))
+    h = _conv2(sd, prefix + ".in_layers.2", h, 1)
+    e = F.linear(_silu(emb), sd[prefix + ".emb_layers.1.weight"], sd[prefix + ".emb_layers.1.bias"]).type(h.dtype)
+    e = e[..., None, None]
+    if use_scale_shift_norm:
+        scale, shift = torch.chunk(e, 2, dim=1)
+        h = _gn32(sd, prefix + ".out_layers.0", h) * (1 + scale) + shift
+        h = _conv2(sd, prefix + ".out_layers.3", _silu(h), 1)
+    else:
+        h = _conv2(sd, prefix + ".out_layers.3", _silu(_gn32(sd, prefix + ".out_layers.0", h + e)), 1)
+    if prefix + ".skip_connection.weight" in sd:
+        w = sd[prefix + ".skip_connection.weight"]
+        x = F.conv2d(x, w, sd[prefix + ".skip_connection.bias"], padding=w.shape[-1] // 2)
+    return x + h
+
+
+def layout_unet_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, timesteps: torch.Tensor,
+                        layout_outputs: Dict[str, torch.Tensor], *, model_channels: int, channel_mult: Sequence[int],
+                        num_res_blocks: int, attention_ds: Sequence[int], image_size: Sequence[int], num_head_channels: int,
+                        num_attention_blocks: int = 1, use_scale_shift_norm: bool = True, pos_scale: float = 1.0,
+                        norm_first: bool = False, norm_for_obj_embedding: bool = False) -> torch.Tensor:
+    """LayoutDiffusionUNetModel.forward (object_cross_unet.py:923-951) for resblock_updown=True (the shipped setting);
+    the module list is walked exactly as the constructor builds it (object_cross_unet.py:742-912)."""
+    emb = F.linear(timestep_embedding(timesteps, model_channels), sd["time_embed.0.weight"], sd["time_embed.0.bias"])
+    emb = F.linear(_silu(emb), sd["time_embed.2.weight"], sd["time_embed.2.bias"])
+    emb = emb + layout_outputs["xf_proj"].to(emb)
+
+    def attn(prefix, h, ds):
+        ch = h.shape[1]
+        return object_aware_cross_attention(
+            {k[len(prefix) + 1:]: v for k, v in sd.items() if k.startswith(prefix + ".")}, h, layout_outputs,
+            num_heads=ch // num_head_channels, resolution_rows=int(image_size[0] // ds), pos_scale=pos_scale,
+            norm_first=norm_first, norm_for_obj_embedding=norm_for_obj_embedding)
+
+    res = lambda prefix, h, **kw: layout_res_block(sd, prefix, h, emb, use_scale_shift_norm=use_scale_shift_norm, **kw)
+    hs: List[torch.Tensor] = []
+    h = _conv2(sd, "input_blocks.0.0", x, 1)
+    hs.append(h)
+    idx, ds = 1, 1
+    for level, _ in enumerate(channel_mult):
+        for _ in range(num_res_blocks):
+            h = res(f"input_blocks.{idx}.0", h)
+            if ds in attention_ds:
+                for a in range(num_attention_blocks):
+                    h = attn(f"input_blocks.{idx}.{1 + a}", h, ds)
+            hs.append(h)
+            idx += 1
+        if level != len(channel_mult) - 1:
+            h = res(f"input_blocks.{idx}.0", h, down=True)
+            hs.append(h)
+            idx += 1
+            ds *= 2
+    h = res("middle_block.0", h)
+    h = attn("middle_block.1", h, ds)
+    h = res("middle_block.2", h)
+    idx = 0
+    for level in reversed(range(len(channel_mult))):
+        for i in range(num_res_blocks + 1):
+            h = res(f"output_blocks.{idx}.0", torch.cat([h, hs.pop()], dim=1))
+            j = 1
+            if ds in attention_ds:
+                for _ in range(num_attention_blocks):
+                    h = attn(f"output_blocks.{idx}.{j}", h, ds)
+                    j += 1
+            if level and i == num_res_blocks:
+                h = res(f"output_blocks.{idx}.{j}", h, up=True)
+                ds //= 2
+            idx += 1
+    return _conv2(sd, "out.2", _silu(_gn32(sd, "out.0", h)), 1)
+
+
+def seeded_state_dict(shapes: Dict[str, Sequence[int]], seed: int, std: float) -> Dict[str, torch.Tensor]:
+    """Deterministic fp32 weights for a {name: shape} table, independent of torch's RNG stream and of module
+    construction order: every tensor is N(0, std) from a numpy generator keyed by (seed, crc32(name)).  Fixtures store
+    the shape table only; the generator script loads these weights into the reference module, tests feed the oracle."""
+    import zlib
+    import numpy as np
+    out = {}
+    for name in sorted(shapes):
+        rng = np.random.default_rng([seed, zlib.crc32(name.encode())])
+        out[name] = torch.from_numpy((rng.standard_normal(tuple(shapes[name])) * std).astype(np.float32))
+    return out

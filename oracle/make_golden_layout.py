@@ -1,8 +1,12 @@
-"""TEST INFRASTRUCTURE ONLY.  Writes tests/golden/layout_encoder.npz by running the UNMODIFIED reference
-`LayoutTransformerEncoder` (lidm/modules/encoders/layout_encoder.py) from /root/reference on CPU with seeded random
-weights and a synthetic layout.  Runs in the build container only (the GPU box has no /root/reference).
+"""TEST INFRASTRUCTURE ONLY.  Writes tests/golden/layout_encoder.npz by running the UNMODIFIED reference modules of the
+layout-conditioned LiDM from /root/reference on CPU: `LayoutTransformerEncoder`
+(lidm/modules/encoders/layout_encoder.py), `ObjectAwareCrossAttention` and `LayoutDiffusionUNetModel`
+(lidm/modules/unets/object_cross_unet.py), with seeded weights (oracle.layout_ref.seeded_state_dict: the fixture stores
+only the {name: shape} tables) and synthetic inputs.  Runs in the build container only (the GPU box has no
+/root/reference).
     python -m oracle.make_golden_layout"""
 import importlib.util
+import json
 import os
 import sys
 
@@ -10,14 +14,14 @@ import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF = "/root/reference/lidm/modules/encoders/layout_encoder.py"
 REF_ROOT = "/root/reference"
+REF = REF_ROOT + "/lidm/modules/encoders/layout_encoder.py"
 
 CASES = {
     # the structure of the nuScenes layout2lidar configuration (models/lidm/nuscenes/layout2lidar/config.yaml:64-82: 13
     # layout tokens, 9 classes, attention resolutions 4/2/1 on the 8x128 feature map), narrowed from hidden 256 / output
-    # 1024 / 6 layers / 8 heads to keep the fixture small
-    "cfg": dict(layout_length=13, hidden_dim=64, output_dim=256, num_layers=2, num_heads=4, use_final_ln=True,
+    # 1024 / 6 layers / 8 heads to keep the run small
+    "cfg": dict(layout_length=13, hidden_dim=64, output_dim=128, num_layers=2, num_heads=4, use_final_ln=True,
                 num_classes_for_layout_object=9, mask_size_for_layout_object=32,
                 used_condition_types=["obj_class", "obj_bbox", "is_valid_obj"], feature_map_size=[8, 128],
                 use_positional_embedding=False, resolution_to_attention=[4, 2, 1], use_key_padding_mask=False,
@@ -31,6 +35,15 @@ CASES = {
                    use_positional_embedding=True, resolution_to_attention=[2], use_key_padding_mask=False,
                    not_use_layout_fusion_module=False),
 }
+# ObjectAwareCrossAttention alone: 128 channels = 2 heads of 64 (+64 positional), 2x32 feature map, both norm orders
+OACA = {"oaca": (False, False), "oaca_nf": (True, True)}
+# the whole denoiser at a small width (the shipped one: model_channels 256, mult [1,2,4], 2 res blocks, attention_ds [8,4,2])
+UNET = dict(image_size=[8, 128], use_fp16=False, use_scale_shift_norm=True, in_channels=8, out_channels=8, model_channels=32,
+            encoder_channels=64, num_head_channels=64, num_heads=-1, num_heads_upsample=-1, num_res_blocks=1,
+            num_attention_blocks=1, resblock_updown=True, attention_ds=[2], channel_mult=[1, 2], dropout=0.1,
+            use_checkpoint=False, use_positional_embedding_for_attention=True,
+            attention_block_type="ObjectAwareCrossAttention")
+STD = {"enc": 0.05, "oaca": 0.08, "unet": 0.05}
 
 
 def load_reference_module():
@@ -40,48 +53,57 @@ def load_reference_module():
     return mod
 
 
+def _seed_module(module, seed, std):
+    from oracle.layout_ref import seeded_state_dict
+    shapes = {k: tuple(v.shape) for k, v in module.state_dict().items()}
+    module.load_state_dict(seeded_state_dict(shapes, seed, std))
+    return shapes
+
+
 def main():
     from oracle.layout_ref import synthetic_layout
     mod = load_reference_module()
-    out = {}
+    out, shapes = {}, {}
     # the reference constructor moves its constant patch boxes to the GPU; on this CPU-only box .cuda() is made a no-op
     orig_cuda = torch.Tensor.cuda
     torch.Tensor.cuda = lambda self, *a, **k: self
     try:
+        cond = None
         for name, kw in CASES.items():
-            torch.manual_seed(0)
             enc = mod.LayoutTransformerEncoder(**kw).eval()
+            if kw["use_positional_embedding"]:
+                with torch.no_grad():
+                    enc.positional_embedding.zero_()          # torch.empty in the reference: give it defined contents
+            shapes[name] = _seed_module(enc, 11, STD["enc"])
             with torch.no_grad():
-                if kw["use_positional_embedding"]:
-                    enc.positional_embedding.normal_(0, 0.02)
                 layout = synthetic_layout(3, kw["layout_length"], kw["num_classes_for_layout_object"], seed=1)
                 res = enc(layout)
-            for k, v in enc.state_dict().items():
-                out[f"{name}/sd/{k}"] = v.numpy()
             out[f"{name}/layout"] = layout.numpy()
             for k, v in res.items():
                 out[f"{name}/out/{k}"] = v.numpy()
-        # ObjectAwareCrossAttention of the layout U-Net (lidm/modules/unets/object_cross_unet.py:380-565) on the "cfg"
-        # encoder outputs: 128 channels = 2 heads of 64 (+64 positional), 2x32 feature map (attention resolution 2),
-        # both norm orders; every parameter randomised (proj_out is zero-initialised in the reference)
+            if name == "cfg":
+                cond = res
         sys.path.insert(0, REF_ROOT)
-        from lidm.modules.unets.object_cross_unet import ObjectAwareCrossAttention
-        cond = {k[len("cfg/out/"):]: torch.from_numpy(v) for k, v in out.items() if k.startswith("cfg/out/")}
-        for tag, norm_first, norm_obj in (("oaca", False, False), ("oaca_nf", True, True)):
-            torch.manual_seed(2)
+        from lidm.modules.unets.object_cross_unet import LayoutDiffusionUNetModel, ObjectAwareCrossAttention
+        for tag, (norm_first, norm_obj) in OACA.items():
             blk = ObjectAwareCrossAttention(128, num_head_channels=64, encoder_channels=64, ds=4, resolution=[2, 32],
                                             type="input", norm_first=norm_first, norm_for_obj_embedding=norm_obj).eval()
+            shapes[tag] = _seed_module(blk, 12, STD["oaca"])
             with torch.no_grad():
-                for prm in blk.parameters():
-                    prm.normal_(0, 0.08)
-                x = torch.randn(3, 128, 2, 32)
+                x = torch.randn(3, 128, 2, 32, generator=torch.Generator().manual_seed(2))
                 y, _ = blk(x, cond)
-            for k, v in blk.state_dict().items():
-                out[f"{tag}/sd/{k}"] = v.numpy()
-            out[f"{tag}/x"] = x.numpy()
-            out[f"{tag}/y"] = y.numpy()
+            out[f"{tag}/x"], out[f"{tag}/y"] = x.numpy(), y.numpy()
+        net = LayoutDiffusionUNetModel(**UNET).eval()
+        shapes["unet"] = _seed_module(net, 13, STD["unet"])
+        with torch.no_grad():
+            x = torch.randn(3, 8, 8, 128, generator=torch.Generator().manual_seed(3))
+            t = torch.tensor([3, 500, 977])
+            y = net(x, t, cond)
+        out["unet/x"], out["unet/t"], out["unet/y"] = x.numpy(), t.numpy(), y.numpy()
     finally:
         torch.Tensor.cuda = orig_cuda
+    out["shapes_json"] = np.frombuffer(json.dumps({k: {n: list(s) for n, s in v.items()} for k, v in shapes.items()}).encode(),
+                                       dtype=np.uint8)
     path = os.path.join(ROOT, "tests", "golden", "layout_encoder.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, f"{os.path.getsize(path) / 1e6:.2f} MB", len(out), "arrays")
