@@ -27,6 +27,16 @@ extern "C" {
 
 #define LIDM_MAX_LEVELS 8
 
+/* Numeric modes of the tensor-core paths (lidm_config.precision / ae_precision).  All accumulate in fp32 in TMEM.
+ *   BF16   : bf16 operands and bf16 activations (north_star bf16 budget: eps within 2e-2)
+ *   BF16X3 : "precise", every GEMM as a 3-way bf16 operand split x*w = xh*wh + xl*wh + xh*wl with an fp32 residual
+ *            stream (fp32-class: eps within 1e-3, image within 1e-2), about 3x the GEMM work
+ *   FP16   : IEEE half operands and activations at the same tensor rate as bf16 (3 more mantissa bits: the first
+ *            stage's image error drops from 2.4e-2 to 3e-3); conversions saturate at +-65504 */
+#define LIDM_PREC_BF16 0
+#define LIDM_PREC_BF16X3 1
+#define LIDM_PREC_FP16 2
+
 typedef struct lidm_handle lidm_handle;
 
 /* Mirrors the YAML blocks the reference instantiates from (models/lidm/kitti/uncond/config.yaml):
@@ -47,9 +57,7 @@ typedef struct lidm_config {
   int32_t ae_ch_mult[LIDM_MAX_LEVELS];
   int32_t ae_strides[LIDM_MAX_LEVELS][2]; /* ae_n_ch_mult-1 entries (h, w) */
   float scale_factor;                     /* LatentDiffusion.scale_factor (ddpm.py:438,725) */
-  /* 0 = bf16 tensor-core path (north_star bf16 budget: eps within 2e-2);
-   * 1 = precise "fp32-class" path: every GEMM runs as a 3-way bf16 operand split x*w = xh*wh + xl*wh + xh*wl on the
-   *     same tcgen05 kernel with an fp32 residual stream (north_star fp32 bars: eps within 1e-3, image within 1e-2) */
+  /* numeric mode of the U-Net (LIDM_PREC_*), and of the first stage unless ae_precision says otherwise */
   int32_t precision;
   /* conditioning (DiffusionWrapper.forward, ddpm.py:2313-2339):
    * latent_channels: channels of x_t / eps; in_channels - latent_channels > 0 channels come from a 'concat' conditioning
@@ -60,6 +68,10 @@ typedef struct lidm_config {
   int32_t latent_channels;
   int32_t use_spatial_transformer, context_dim, transformer_depth;
   int32_t ae_in_channels;                  /* first-stage ddconfig.in_channels (encoder input), 0 => 1 */
+  /* numeric mode of the first stage (decoder, encoder): 0 = same as `precision`, otherwise LIDM_PREC_* + 1.  The
+   * benchmarked mix is precision = BF16, ae_precision = FP16 + 1: the decoder's bf16 rounding alone exceeds the 1e-2
+   * final-image budget, IEEE half meets it at the same speed. */
+  int32_t ae_precision;
 } lidm_config;
 
 /* Last error message for `h` (or, with h == NULL, for the calling thread's last failed lidm_create / stateless call). */

@@ -37,6 +37,7 @@ class CConfig(ctypes.Structure):
         ("latent_channels", c_int32),
         ("use_spatial_transformer", c_int32), ("context_dim", c_int32), ("transformer_depth", c_int32),
         ("ae_in_channels", c_int32),
+        ("ae_precision", c_int32),
     ]
 
 

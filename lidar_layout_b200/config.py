@@ -76,10 +76,21 @@ class LidmConfig:
     scale_factor: float = 1.0
     parameterization: str = "eps"
     conditioning_key: Optional[str] = None
-    # numeric mode of the CUDA path (not a reference option): "bf16" = plain bf16 tensor-core GEMMs (north_star bf16
-    # budget, eps within 2e-2); "fp32" = precise mode, every GEMM as a 3-way bf16 operand split with an fp32 residual
-    # stream (north_star fp32 bars: eps within 1e-3, final image within 1e-2), about 3x the GEMM work
+    # numeric mode of the CUDA path (not a reference option), U-Net: "bf16" = plain bf16 tensor-core GEMMs (north_star
+    # bf16 budget, eps within 2e-2); "fp32" = precise mode, every GEMM as a 3-way bf16 operand split with an fp32
+    # residual stream (north_star fp32 bars: eps within 1e-3, final image within 1e-2), about 3x the GEMM work;
+    # "fp16" = IEEE-half operands and activations at the bf16 tensor rate (saturating conversions)
     precision: str = "bf16"
+    # numeric mode of the first stage (decoder / encoder): "bf16" | "fp32" | "fp16"; None = "fp16" under a bf16 U-Net (the
+    # decoder's bf16 rounding alone is 2.4e-2 on the final image, above north_star's 1e-2; half precision gives 3e-3 at
+    # the same speed), otherwise the U-Net's mode
+    ae_precision: Optional[str] = None
+
+    @property
+    def ae_precision_resolved(self) -> str:
+        if self.ae_precision is not None:
+            return self.ae_precision
+        return "fp16" if self.precision == "bf16" else self.precision
     unet: UNetConfig = field(default_factory=UNetConfig)
     ae: AEConfig = field(default_factory=AEConfig)
     dataset: DatasetConfig = field(default_factory=DatasetConfig)

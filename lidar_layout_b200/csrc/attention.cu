@@ -66,7 +66,7 @@ __device__ __forceinline__ void ex2_poly2(float& y0, float& y1, float x0, float 
 
 // One 32-score chunk of a row: p = 2^(s*log2e - mb) as 16 bf16 pairs into pk, row sums into (s0..s3).  POLYP of every
 // 8 pairs (evenly spread) take the polynomial instead of MUFU.EX2.
-template <int POLYP, bool SUM>
+template <int POLYP, bool SUM, bool F16>
 __device__ __forceinline__ void exp_chunk(const uint32_t (&sv)[32], float mb, uint32_t* pk, float& s0, float& s1,
                                           float& s2, float& s3) {
   constexpr float LOG2E = 1.4426950408889634f;
@@ -84,7 +84,7 @@ __device__ __forceinline__ void exp_chunk(const uint32_t (&sv)[32], float mb, ui
       if (i & 1) add2(s2, s3, s2, s3, p0, p1);
       else add2(s0, s1, s0, s1, p0, p1);
     }
-    pk[i] = pack_bf16(p0, p1);
+    pk[i] = pack_h<F16>(p0, p1);
   }
 }
 
@@ -137,7 +137,7 @@ struct Cfg {
   static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
 };
 
-template <int NG, int BKV_, int POLYP, bool PP>
+template <int NG, int BKV_, int POLYP, bool PP, bool F16>
 __global__ void __launch_bounds__((Cfg<NG, BKV_>::THREADS), 1)
 attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                         bf16* __restrict__ out, int out_ld, int T, int q_col, int k_col, int v_col, int kv_len,
@@ -196,7 +196,7 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     for (int i = threadIdx.x; i < BKV_ * 4; i += blockDim.x) {
       const int r = i >> 2, cphys = i & 3;
       const int c = cphys ^ ((r >> 1) & 3);
-      ones[i] = make_uint4(c == 0 ? 0x00003f80u : 0u, 0u, 0u, 0u);   // bf16 1.0 in the low half = element 0
+      ones[i] = make_uint4(c == 0 ? (F16 ? 0x00003c00u : 0x00003f80u) : 0u, 0u, 0u, 0u);   // 1.0 in the low half = element 0
     }
     fence_proxy_async();
   }
@@ -242,8 +242,8 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       // barriers; a K/V stage goes back to the TMA warp when every group has committed its P*V on it
       if (lane == 0) {
         const int g = warp - 1;
-        constexpr uint32_t idesc_s = make_idesc_bf16(BQ, BKV_);
-        constexpr uint32_t idesc_o = make_idesc_bf16(BQ, MMA_ROWSUM ? 48 : D) | (1u << 16);   // V is an MN-major B operand
+        constexpr uint32_t idesc_s = make_idesc_h<F16>(BQ, BKV_);
+        constexpr uint32_t idesc_o = make_idesc_h<F16>(BQ, MMA_ROWSUM ? 48 : D) | (1u << 16);   // V is an MN-major B operand
         // tiles are counted cumulatively over all of this CTA's items (barrier phases never reset); the issue order is
         // fixed - S(n+1), then P(n) V(n) - and every wait parks the thread (mbar_wait), so the issuer takes no issue
         // slots from the softmax warps that share its scheduler
@@ -321,10 +321,10 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         uint4 u;
-        u.x = pack_bf16(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
-        u.y = pack_bf16(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
-        u.z = pack_bf16(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
-        u.w = pack_bf16(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
+        u.x = pack_h<F16>(__uint_as_float(o[8 * i + 0]) * inv, __uint_as_float(o[8 * i + 1]) * inv);
+        u.y = pack_h<F16>(__uint_as_float(o[8 * i + 2]) * inv, __uint_as_float(o[8 * i + 3]) * inv);
+        u.z = pack_h<F16>(__uint_as_float(o[8 * i + 4]) * inv, __uint_as_float(o[8 * i + 5]) * inv);
+        u.w = pack_h<F16>(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv);
         reinterpret_cast<uint4*>(op)[i] = u;
       }
     };
@@ -404,7 +404,7 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 #pragma unroll
       for (int c = 0; c < L::NCH; ++c) {
         uint32_t* pk = &pkk[(c & 1) * 16];
-        exp_chunk<POLYP, !MMA_ROWSUM>(sv[c], mb, pk, s0, s1, s2, s3);
+        exp_chunk<POLYP, !MMA_ROWSUM, F16>(sv[c], mb, pk, s0, s1, s2, s3);
         if (c & 1) {
           if (c == 1 && n > 0) {
             // the previous P*V of this group (the previous tile's, or the previous item's last) must have drained P
@@ -443,13 +443,13 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 }
 
 // q: (B, T, q_ld) rows with the heads at columns q_col + head*32; k / v: (B, kv_rows, kv_ld) rows at columns k_col / v_col.
-template <int NG, int BKV_, int POLYP, bool PP = (NG == 2)>
-void launch(const bf16* q, int q_ld, int q_col, const bf16* kv, int kv_ld, int k_col, int v_col, int kv_rows, const View& out,
+template <int NG, int BKV_, int POLYP, bool PP, bool F16>
+void launch_f(const bf16* q, int q_ld, int q_col, const bf16* kv, int kv_ld, int k_col, int v_col, int kv_rows, const View& out,
             int B, int T, int heads, cudaStream_t s) {
   using L = Cfg<NG, BKV_>;
   static bool configured = false;
   if (!configured) {
-    LIDM_CUDA_CHECK(cudaFuncSetAttribute(attention_d32_v5_kernel<NG, BKV_, POLYP, PP>,
+    LIDM_CUDA_CHECK(cudaFuncSetAttribute(attention_d32_v5_kernel<NG, BKV_, POLYP, PP, F16>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_TOTAL));
     configured = true;
   }
@@ -465,10 +465,17 @@ void launch(const bf16* q, int q_ld, int q_col, const bf16* kv, int kv_ld, int k
     LIDM_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = n_items < num_sms ? n_items : num_sms;     // one persistent CTA per SM
-  attention_d32_v5_kernel<NG, BKV_, POLYP, PP><<<grid, L::THREADS, L::SMEM_TOTAL, s>>>(tmQ, tmKV, out.p, out.ld, T, q_col, k_col,
+  attention_d32_v5_kernel<NG, BKV_, POLYP, PP, F16><<<grid, L::THREADS, L::SMEM_TOTAL, s>>>(tmQ, tmKV, out.p, out.ld, T, q_col, k_col,
                                                                                 v_col, kv_rows, n_qblk, heads, n_items);
   LIDM_CUDA_CHECK(cudaGetLastError());
   LIDM_COUNT_LAUNCH(1);
+}
+
+template <int NG, int BKV_, int POLYP, bool PP = (NG == 2)>
+void launch(const bf16* q, int q_ld, int q_col, const bf16* kv, int kv_ld, int k_col, int v_col, int kv_rows, const View& out,
+            int B, int T, int heads, cudaStream_t s) {
+  if (out.f16) launch_f<NG, BKV_, POLYP, PP, true>(q, q_ld, q_col, kv, kv_ld, k_col, v_col, kv_rows, out, B, T, heads, s);
+  else launch_f<NG, BKV_, POLYP, PP, false>(q, q_ld, q_col, kv, kv_ld, k_col, v_col, kv_rows, out, B, T, heads, s);
 }
 
 }  // namespace v5
@@ -627,7 +634,7 @@ void launch_cross_attention_d32(const bf16* q, int q_ld, const bf16* kv, int kv_
                                 const View& out, int B, int T, int heads, cudaStream_t s) {
   LIDM_REQUIRE(T % 128 == 0 && L >= 1, "cross attention: T must be a multiple of 128");
   static const bool no_small = getenv("LIDM_XATTN_TC") != nullptr;   // A/B switch: always take the tensor-core kernel
-  if (L <= xs::LMAX && !no_small && q_ld % 8 == 0 && out.ld % 8 == 0 && kv_ld % 8 == 0 && k_col % 8 == 0 && v_col % 8 == 0 &&
+  if (L <= xs::LMAX && !no_small && !out.f16 && q_ld % 8 == 0 && out.ld % 8 == 0 && kv_ld % 8 == 0 && k_col % 8 == 0 && v_col % 8 == 0 &&
       (size_t)2 * L * heads * xs::HP * sizeof(float) <= 48 * 1024) {
     LIDM_REQUIRE(out.hl == 0 && out.hr == 0 && out.H * out.W == T && out.B == B && out.C == heads * D, "attention out view");
     const int pairs = (T / 2) * heads;

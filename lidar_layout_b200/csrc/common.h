@@ -62,6 +62,9 @@ struct View {
   int gst_ld = 0;      // floats per (sample, slot) row = 2 * granules of the underlying buffer
   int gst_slots = 0;   // slots per sample (= H * W / 128 of the buffer)
   int gst_slot0 = 0;   // first slot this GEMM writes (output parity of a folded upsample conv)
+  // element format of this 2-byte tensor: false = bf16, true = IEEE half (same layouts, TMA maps and tensor rate; used by
+  // the first stage, whose bf16 rounding alone exceeds the 1e-2 final-image budget)
+  bool f16 = false;
   int Cphys() const { return cphys ? cphys : (lo_off ? lo_off + C : C); }
   int Wp() const { return W + hl + hr; }
   int pitch() const { return wpitch ? wpitch : Wp(); }
@@ -127,6 +130,7 @@ struct GemmB {
   //   2: [w_hi, w_lo]             A single plane (exact bf16 values, e.g. attention output)
   //   3: [w_hi, w_hi, w_lo]       A = hi/lo planes: segments read (hi, lo, hi)
   int nseg = 1;
+  bool f16 = false;         // element format (must match the A operand's View::f16)
 };
 
 // A: activation view (taps applied on the halo'd view).  N = logical output channels.
@@ -180,14 +184,14 @@ void launch_backproject(const float* img, int B, int H, int W, float fov_up_deg,
                         float dmax, float depth_scale, int log_scale, int input_is_unit, float* xyz, uint8_t* mask,
                         cudaStream_t s);
 void launch_im2col_nchw_f32(const float* x, int B, int C, int H, int W, int kh, int kw, int pl, int pt, bf16* out,
-                            int kpad, cudaStream_t s);
+                            int kpad, cudaStream_t s, bool f16 = false);
 // stride = vertical stride; stride_w = horizontal stride (0 => same as stride)
 void launch_im2col_nhwc(const View& x, int kh, int kw, int stride, int pl, int pt, int Ho, int Wo, bf16* out,
                         cudaStream_t s, int stride_w = 0);
 void launch_upsample_nearest2x(const View& x, const View& y, cudaStream_t s);
 void launch_upsample_bilinear(const View& x, const View& y, cudaStream_t s);
 void launch_copy_with_halo(const View& x, const View& y, cudaStream_t s);
-void launch_softmax_rows(const float* s, bf16* p, int64_t rows, int cols, cudaStream_t st);
+void launch_softmax_rows(const float* s, bf16* p, int64_t rows, int cols, cudaStream_t st, bool f16 = false);
 void launch_vq(const float* z, int B, int C, int HW, const float* codebook, const float* cb_norm, int n_embed,
                int quantize, const float* pq_w, const float* pq_b, float scale, float* out, int32_t* idx,
                cudaStream_t s);
@@ -199,7 +203,7 @@ void launch_linear_rows(const float* x, int nt, int K, const float* w, const flo
                         cudaStream_t s);
 void launch_pack_conv_weight(const float* w, int cout, int cin, int kh, int kw, int n_alloc, int k_alloc,
                              const int* row_perm, const float* row_scale_rows, float row_scale, int n_scaled_rows,
-                             bf16* out, cudaStream_t s);
+                             bf16* out, cudaStream_t s, bool f16 = false);
 void launch_mask_select(const float* dec, int B, int HW, float* out, cudaStream_t s);
 
 // ---- precise ("fp32-class") mode helpers (precise.cu): fp32 stream tensors <-> bf16 hi/lo planes -------------

@@ -121,7 +121,7 @@ __global__ void backproject_kernel(const float* __restrict__ img, int H, int W, 
 // ------------------------------------------------------------------------------------------ im2col (8-channel fp32 NCHW input)
 // out[(b*H*W + h*W + w) * kpad + (ky*kw + kx)*C + c] = x[b][c][h+ky-pt][(w+kx-pl) mod W]  (0 outside H)
 __global__ void im2col_nchw_f32_kernel(const float* __restrict__ x, int B, int C, int H, int W, int kh, int kw, int pl,
-                                       int pt, bf16* __restrict__ out, int kpad) {
+                                       int pt, bf16* __restrict__ out, int kpad, bool f16) {
   // one thread = 8 consecutive k of one pixel (a 16-byte store); kpad is a multiple of 8
   const int kv = kpad >> 3;
   const int64_t total = (int64_t)B * H * W * kv;
@@ -147,7 +147,8 @@ __global__ void im2col_nchw_f32_kernel(const float* __restrict__ x, int B, int C
       }
     }
     uint4 o;
-    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+    o.x = pack_hr(v[0], v[1], f16); o.y = pack_hr(v[2], v[3], f16); o.z = pack_hr(v[4], v[5], f16);
+    o.w = pack_hr(v[6], v[7], f16);
     reinterpret_cast<uint4*>(out)[i] = o;
   }
 }
@@ -206,7 +207,7 @@ __global__ void upsample_nearest_kernel(const bf16* __restrict__ x, int B, int H
 // bilinear, align_corners=True: src = dst * (in-1)/(out-1)   (ATen area_pixel_compute_scale)
 __global__ void upsample_bilinear_kernel(const bf16* __restrict__ x, int B, int H, int W, int xhl, int xWp, int xld,
                                          int C, bf16* __restrict__ y, int Ho, int Wo, int yhl, int yhr, int yWp,
-                                         int yld, float rh, float rw) {
+                                         int yld, float rh, float rw, bool f16) {
   const int vec = C >> 3;
   const int64_t total = (int64_t)B * Ho * Wo * vec;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -231,17 +232,17 @@ __global__ void upsample_bilinear_kernel(const bf16* __restrict__ x, int B, int 
     uint32_t o[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float2 fa = unpack_bf16(ua[k]), fb = unpack_bf16(ub[k]), fc = unpack_bf16(uc[k]), fd = unpack_bf16(ud[k]);
+      const float2 fa = unpack_hr(ua[k], f16), fb = unpack_hr(ub[k], f16), fc = unpack_hr(uc[k], f16), fd = unpack_hr(ud[k], f16);
       const float r0 = lh0 * (lw0 * fa.x + lw1 * fb.x) + lh1 * (lw0 * fc.x + lw1 * fd.x);
       const float r1 = lh0 * (lw0 * fa.y + lw1 * fb.y) + lh1 * (lw0 * fc.y + lw1 * fd.y);
-      o[k] = pack_bf16(r0, r1);
+      o[k] = pack_hr(r0, r1, f16);
     }
     store_with_halo(y, b, Ho, Wo, yhl, yhr, yWp, yld, ho, wo, cv, make_uint4(o[0], o[1], o[2], o[3]));
   }
 }
 
 // ------------------------------------------------------------------------------------------ softmax over rows (decoder attention)
-__global__ void softmax_rows_kernel(const float* __restrict__ s, bf16* __restrict__ p, int cols) {
+__global__ void softmax_rows_kernel(const float* __restrict__ s, bf16* __restrict__ p, int cols, bool f16) {
   const int64_t row = blockIdx.x;
   const float* sr = s + row * cols;
   bf16* pr = p + row * cols;
@@ -262,7 +263,7 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, bf16* __restric
   sum = 0.f;
   for (int i = 0; i < (int)(blockDim.x >> 5); ++i) sum += red[i];
   const float inv = 1.f / sum;
-  for (int i = threadIdx.x; i < cols; i += blockDim.x) pr[i] = __float2bfloat16(__expf(sr[i] - mx) * inv);
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) store_hr(pr + i, __expf(sr[i] - mx) * inv, f16);
 }
 
 // ------------------------------------------------------------------------------------------ vector quantiser
@@ -385,7 +386,7 @@ __global__ void linear_rows_kernel(const float* __restrict__ x, int nt, int K, c
 // rows < n_scaled_rows (after permutation) multiplied by row_scale.  Padding rows/cols are zero.
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int cout, int cin, int kh, int kw, int n_alloc,
                                         int k_alloc, const int* __restrict__ row_perm, float row_scale,
-                                        int n_scaled_rows, bf16* __restrict__ out) {
+                                        int n_scaled_rows, bf16* __restrict__ out, bool f16) {
   const int64_t total = (int64_t)n_alloc * k_alloc;
   const int taps = kh * kw;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -398,7 +399,7 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int cout, i
       v = w[((size_t)row * cin + c) * taps + tap];
       if (rowp < n_scaled_rows) v *= row_scale;
     }
-    out[i] = __float2bfloat16(v);
+    store_hr(out + i, v, f16);
   }
 }
 
@@ -502,10 +503,10 @@ void launch_backproject(const float* img, int B, int H, int W, float fov_up_deg,
 }
 
 void launch_im2col_nchw_f32(const float* x, int B, int C, int H, int W, int kh, int kw, int pl, int pt, bf16* out,
-                            int kpad, cudaStream_t s) {
+                            int kpad, cudaStream_t s, bool f16) {
   LIDM_REQUIRE(kh * kw * C <= kpad && kpad % 8 == 0 && pl < W && kw - 1 - pl < W, "im2col: kpad too small / not a multiple of 8");
   const int64_t total = (int64_t)B * H * W * (kpad / 8);
-  im2col_nchw_f32_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, B, C, H, W, kh, kw, pl, pt, out, kpad);
+  im2col_nchw_f32_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, B, C, H, W, kh, kw, pl, pt, out, kpad, f16);
   LIDM_CUDA_CHECK(cudaGetLastError());
   LIDM_COUNT_LAUNCH(1);
 }
@@ -530,12 +531,12 @@ void launch_upsample_nearest2x(const View& x, const View& y, cudaStream_t s) {
 }
 
 void launch_upsample_bilinear(const View& x, const View& y, cudaStream_t s) {
-  LIDM_REQUIRE(y.C == x.C && y.B == x.B && y.H >= x.H && y.W >= x.W, "bilinear upsample shapes");
+  LIDM_REQUIRE(y.C == x.C && y.B == x.B && y.H >= x.H && y.W >= x.W && x.f16 == y.f16, "bilinear upsample shapes");
   const float rh = y.H > 1 ? (float)(x.H - 1) / (float)(y.H - 1) : 0.f;
   const float rw = y.W > 1 ? (float)(x.W - 1) / (float)(y.W - 1) : 0.f;
   const int64_t total = (int64_t)y.B * y.H * y.W * (y.C / 8);
   upsample_bilinear_kernel<<<grid_for(total, 256), 256, 0, s>>>(x.p, x.B, x.H, x.W, x.hl, x.Wp(), x.ld, x.C, y.p, y.H,
-                                                                y.W, y.hl, y.hr, y.Wp(), y.ld, rh, rw);
+                                                                y.W, y.hl, y.hr, y.Wp(), y.ld, rh, rw, x.f16);
   LIDM_CUDA_CHECK(cudaGetLastError());
   LIDM_COUNT_LAUNCH(1);
 }
@@ -549,8 +550,8 @@ void launch_copy_with_halo(const View& x, const View& y, cudaStream_t s) {
   LIDM_COUNT_LAUNCH(1);
 }
 
-void launch_softmax_rows(const float* sc, bf16* p, int64_t rows, int cols, cudaStream_t st) {
-  softmax_rows_kernel<<<(unsigned)rows, 256, 0, st>>>(sc, p, cols);
+void launch_softmax_rows(const float* sc, bf16* p, int64_t rows, int cols, cudaStream_t st, bool f16) {
+  softmax_rows_kernel<<<(unsigned)rows, 256, 0, st>>>(sc, p, cols, f16);
   LIDM_CUDA_CHECK(cudaGetLastError());
   LIDM_COUNT_LAUNCH(1);
 }
@@ -592,10 +593,10 @@ void launch_linear_rows(const float* x, int nt, int K, const float* w, const flo
 
 void launch_pack_conv_weight(const float* w, int cout, int cin, int kh, int kw, int n_alloc, int k_alloc,
                              const int* row_perm, const float* /*unused*/, float row_scale, int n_scaled_rows,
-                             bf16* out, cudaStream_t s) {
+                             bf16* out, cudaStream_t s, bool f16) {
   const int64_t total = (int64_t)n_alloc * k_alloc;
   pack_conv_weight_kernel<<<grid_for(total, 256), 256, 0, s>>>(w, cout, cin, kh, kw, n_alloc, k_alloc, row_perm,
-                                                               row_scale, n_scaled_rows, out);
+                                                               row_scale, n_scaled_rows, out, f16);
   LIDM_CUDA_CHECK(cudaGetLastError());
   LIDM_COUNT_LAUNCH(1);
 }

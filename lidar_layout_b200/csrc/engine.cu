@@ -106,6 +106,7 @@ struct ConvW {
   int cout = 0, cin = 0, kh = 1, kw = 1;
   int n_alloc = 0, k_alloc = 0;
   int nseg = 1;   // operand-split segments per tap (precise mode: 3 for hi/lo inputs, 2 for exact-bf16 inputs)
+  bool f16 = false;   // packed as IEEE half instead of bf16
 };
 struct NormW { float* gamma = nullptr; float* beta = nullptr; int C = 0; };
 struct ResW { NormW n1, n2; ConvW c1, c2, skip; ConvW c2s; /* conv2 with the 1x1 skip appended along K */ bool has_skip = false; int emb_off = -1; int cin = 0, cout = 0; };
@@ -191,6 +192,7 @@ struct lidm_handle {
   lidm_config cfg{};
   std::string error;
   bool finalized = false;
+  int unet_prec = LIDM_PREC_BF16, ae_prec = LIDM_PREC_BF16;   // numeric mode of the U-Net / of the first stage
   std::unordered_map<std::string, DevTensor> raw;     // fp32 state-dict tensors on the device
   std::vector<void*> owned;                           // packed weight allocations
   // U-Net
@@ -280,6 +282,7 @@ struct Packer {
   bool ema;
   cudaStream_t s = 0;
   bool precise = false;
+  bool f16 = false;    // pack GEMM operands as IEEE half (never together with `precise`)
 
   float* f32(const std::string& name, int64_t expect_numel) {
     const DevTensor& t = find_raw(h, name, ema);
@@ -308,10 +311,11 @@ struct Packer {
     c.cout = cout; c.cin = cin; c.kh = kh; c.kw = kw;
     c.n_alloc = round_n_alloc(cout);
     c.nseg = precise ? nseg_p : 1;
+    c.f16 = f16;
     if (!precise) {
       c.k_alloc = k_alloc_override ? k_alloc_override : kh * kw * cin;
       c.w = dev_alloc<bf16>(h, (size_t)c.n_alloc * c.k_alloc);
-      launch_pack_conv_weight(t.p, cout, cin, kh, kw, c.n_alloc, c.k_alloc, nullptr, nullptr, 1.f, 0, c.w, s);
+      launch_pack_conv_weight(t.p, cout, cin, kh, kw, c.n_alloc, c.k_alloc, nullptr, nullptr, 1.f, 0, c.w, s, f16);
     } else if (k_alloc_override) {
       // K layout [seg][kpad]: reorder to fp32 [cout][kpad] (k = tap*cin + c) and split-pack it as a 1x1 conv
       float* tmp = nullptr;
@@ -336,7 +340,7 @@ struct Packer {
 struct LinPart { std::string name; float scale; };
 ConvW pack_stacked_linear(Packer& pk, const std::vector<LinPart>& parts, int cout_each, int cin, const std::string& bias_name) {
   lidm_handle* h = pk.h;
-  if (pk.precise) throw Error(LIDM_ERR_INVALID, "the precise (fp32-class) mode does not cover SpatialTransformer U-Nets");
+  if (pk.precise || pk.f16) throw Error(LIDM_ERR_INVALID, "SpatialTransformer U-Nets run in the bf16 mode only");
   ConvW c;
   c.cout = cout_each * (int)parts.size(); c.cin = cin; c.kh = c.kw = 1;
   c.n_alloc = round_n_alloc(c.cout);
@@ -390,6 +394,8 @@ struct Builder {
   Plan* P;
   ArenaPlanner ap;
   bool dry;
+  bool precise = false;   // this plan runs the operand-split (fp32-class) kernels
+  bool f16 = false;       // 2-byte activations of this plan are IEEE half instead of bf16
   // GroupNorm statistics written by GEMM epilogues (View::gst): which 8-channel granules of each statistics buffer have
   // been produced so far in plan order; a GroupNorm whose whole input is covered skips its statistics pass
   std::map<const float*, std::vector<char>> gst_cover;
@@ -397,10 +403,10 @@ struct Builder {
 
   View act(int B, int H, int W, int C, int hl, int hr, Buf* buf) {
     View v;
-    v.B = B; v.H = H; v.W = W; v.C = C; v.hl = hl; v.hr = hr; v.ld = C;
+    v.B = B; v.H = H; v.W = W; v.C = C; v.hl = hl; v.hr = hr; v.ld = C; v.f16 = f16;
     const size_t act_bytes = align_up((size_t)B * H * (W + hl + hr) * C * sizeof(bf16), 256);
     // halo-free tensors made of whole 128-pixel tiles get a statistics side buffer [B][H*W/128][C/8][2] floats
-    const bool want_gst = gst_enabled && h->cfg.precision == 0 && hl == 0 && hr == 0 && C % 8 == 0 && (H * W) % 128 == 0;
+    const bool want_gst = gst_enabled && !precise && hl == 0 && hr == 0 && C % 8 == 0 && (H * W) % 128 == 0;
     const size_t gst_bytes = want_gst ? (size_t)B * (H * W / 128) * (C / 8) * 2 * sizeof(float) : 0;
     buf->bytes = act_bytes + gst_bytes;
     buf->off = ap.alloc(buf->bytes);
@@ -449,6 +455,16 @@ struct Builder {
            std::to_string(a.H) + "x" + std::to_string(a.W);
   }
 
+  static GemmB gb(const ConvW& w) {
+    GemmB b; b.p = w.w; b.n_alloc = w.n_alloc; b.ld = w.k_alloc; b.nseg = w.nseg; b.f16 = w.f16;
+    return b;
+  }
+  // a plain channels-last matrix view over a raw buffer (im2col output, attention probabilities ...)
+  View mat(bf16* p, int B, int H, int W, int C, int ld) const {
+    View v; v.p = p; v.B = B; v.H = H; v.W = W; v.C = C; v.ld = ld; v.f16 = f16;
+    return v;
+  }
+
   static View chan_slice(const View& v, int c0, int C) {
     View s = v;
     s.p = v.p + c0;
@@ -465,7 +481,7 @@ struct Builder {
   }
 
   void gemm(const View& a, const ConvTaps& taps, const ConvW& w, const GemmEpilogue& ep_in) {
-    GemmB b; b.p = w.w; b.n_alloc = w.n_alloc; b.ld = w.k_alloc; b.nseg = w.nseg;
+    const GemmB b = gb(w);
     const int N = w.cout;
     GemmEpilogue ep = ep_in;
     prep_gst(ep, N, w.n_alloc);
@@ -627,17 +643,20 @@ struct Builder {
     release(ba);
   }
 
-  void down_p(const ConvW& c, const ViewF& x, const ViewF& dst) {
-    const int B = x.B, Ho = x.H / 2, Wo = x.W / 2, C = x.C;
+  // strided conv on the fp32 stream: U-Net Downsample (3x3 stride 2, pad 1/1) and the encoder's Downsample
+  // (model_lidm.py:68-83: 3x3, stride (sh, sw), pad left pl / top pt only)
+  void down_p(const ConvW& c, const ViewF& x, const ViewF& dst, int sh = 2, int sw = 2, int pl = 1, int pt = 1) {
+    const int B = x.B, Ho = dst.H, Wo = dst.W, C = x.C, nt = c.kh * c.kw;
     Buf bxs, bc;
     View xs = act_hl(B, x.H, x.W, C, 0, 0, &bxs);
     op([=](cudaStream_t s) { launch_split_f32(x, xs, s); });
-    bf16* col = raw<bf16>((size_t)B * Ho * Wo * 9 * 2 * C, &bc);
+    bf16* col = raw<bf16>((size_t)B * Ho * Wo * nt * 2 * C, &bc);
     View xs2 = xs; xs2.C = 2 * C; xs2.lo_off = 0;      // im2col moves both planes as one 2C-channel tensor
-    op([=](cudaStream_t s) { launch_im2col_nhwc(xs2, 3, 3, 2, 1, 1, Ho, Wo, col, s); });
+    const int kh = c.kh, kw = c.kw;
+    op([=](cudaStream_t s) { launch_im2col_nhwc(xs2, kh, kw, sh, pl, pt, Ho, Wo, col, s, sw); });
     release(bxs);
-    View a; a.p = col; a.B = B; a.H = Ho; a.W = Wo; a.C = C; a.ld = 18 * C; a.lo_off = C; a.cphys = 18 * C;
-    ConvTaps taps; taps.n = 9; taps.cstep = 2 * C;     // row = [tap][hi C | lo C]
+    View a; a.p = col; a.B = B; a.H = Ho; a.W = Wo; a.C = C; a.ld = 2 * nt * C; a.lo_off = C; a.cphys = 2 * nt * C;
+    ConvTaps taps; taps.n = nt; taps.cstep = 2 * C;    // row = [tap][hi C | lo C]
     GemmEpilogue ep;
     ep.bias = c.bias;
     set_out_f(ep, dst);
@@ -686,7 +705,7 @@ struct Builder {
       ep.bias = r.c1.bias;
       ep.out = hmid;
       prep_gst(ep, r.cout, r.c1.n_alloc);
-      GemmB b; b.p = r.c1.w; b.n_alloc = r.c1.n_alloc; b.ld = r.c1.k_alloc;
+      const GemmB b = gb(r.c1);
       const ConvTaps taps = taps_rect(kh, kw, pl, pt);
       const int N = r.cout, emb_off = r.emb_off;
       Plan* P_ = P;
@@ -708,7 +727,7 @@ struct Builder {
       ep.a2 = x;
       ep.out = dst;
       prep_gst(ep, r.cout, r.c2s.n_alloc);
-      GemmB b; b.p = r.c2s.w; b.n_alloc = r.c2s.n_alloc; b.ld = r.c2s.k_alloc;
+      const GemmB b = gb(r.c2s);
       const ConvTaps taps = taps_rect(kh, kw, pl, pt);
       const int N = r.cout;
       op([=](cudaStream_t s) { launch_conv_gemm(g2, taps, b, N, ep, s); }, PROF_GEMM,
@@ -786,18 +805,19 @@ struct Builder {
     float* S = raw<float>((size_t)B * T * T, &bs);
     {
       View q = chan_slice(qk, 0, C);
-      GemmB kb; kb.p = qk.p + C; kb.n_alloc = T; kb.ld = 2 * C; kb.batch_stride = (int64_t)T * 2 * C;
+      GemmB kb; kb.p = qk.p + C; kb.n_alloc = T; kb.ld = 2 * C; kb.batch_stride = (int64_t)T * 2 * C; kb.f16 = f16;
       GemmEpilogue ep;
       ep.out_f32_nhwc = S;
       op([=](cudaStream_t s) { launch_conv_gemm(q, taps_1x1(), kb, T, ep, s); }, PROF_GEMM, gemm_flops(q, 1, T));
     }
     bf16* Pm = raw<bf16>((size_t)B * T * T, &bp);
-    op([=](cudaStream_t s) { launch_softmax_rows(S, Pm, (int64_t)B * T, T, s); });
+    const bool f16_ = f16;
+    op([=](cudaStream_t s) { launch_softmax_rows(S, Pm, (int64_t)B * T, T, s, f16_); });
     release(bs);
     View ao = act(B, H, W, C, 0, 0, &ba);
     {
-      View pv; pv.p = Pm; pv.B = B; pv.H = T / 128; pv.W = 128; pv.C = T; pv.ld = T;
-      GemmB vb; vb.p = vt; vb.n_alloc = C; vb.ld = T; vb.batch_stride = (int64_t)C * T;
+      View pv = mat(Pm, B, T / 128, 128, T, T);
+      GemmB vb; vb.p = vt; vb.n_alloc = C; vb.ld = T; vb.batch_stride = (int64_t)C * T; vb.f16 = f16;
       GemmEpilogue ep;
       View o2 = ao; o2.H = T / 128; o2.W = 128; o2.gst = nullptr;
       ep.out = o2;
@@ -901,7 +921,7 @@ struct Builder {
     Buf bc;
     bf16* col = raw<bf16>((size_t)B * Ho * Wo * 9 * x.C, &bc);
     op([=](cudaStream_t s) { launch_im2col_nhwc(x, 3, 3, 2, 1, 1, Ho, Wo, col, s); });
-    View a; a.p = col; a.B = B; a.H = Ho; a.W = Wo; a.C = 9 * x.C; a.ld = 9 * x.C;
+    View a = mat(col, B, Ho, Wo, 9 * x.C, 9 * x.C);
     GemmEpilogue ep;
     ep.bias = c.bias;
     ep.out = dst;
@@ -917,7 +937,7 @@ struct Builder {
     bf16* col = raw<bf16>((size_t)B * Ho * Wo * taps * x.C, &bc);
     const int kh = c.kh, kw = c.kw;
     op([=](cudaStream_t s) { launch_im2col_nhwc(x, kh, kw, sh, pl, pt, Ho, Wo, col, s, sw); });
-    View a; a.p = col; a.B = B; a.H = Ho; a.W = Wo; a.C = taps * x.C; a.ld = taps * x.C;
+    View a = mat(col, B, Ho, Wo, taps * x.C, taps * x.C);
     GemmEpilogue ep;
     ep.bias = c.bias;
     ep.out = dst;
@@ -969,6 +989,7 @@ struct Builder {
 // ------------------------------------------------------------------------------------------- U-Net plan
 void build_unet_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
   Builder b{h, P, ArenaPlanner(), dry};
+  b.f16 = h->unet_prec == LIDM_PREC_FP16;
   const lidm_config& cfg = h->cfg;
   const int B = P->B;
   const int n_in = (int)h->in_blocks.size(), n_out = (int)h->out_blocks.size();
@@ -1052,8 +1073,9 @@ void build_unet_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
     Buf bc;
     bf16* col = b.raw<bf16>((size_t)B * H * W * kpad, &bc);
     const int Cin = cfg.in_channels;
-    b.op([=](cudaStream_t s) { launch_im2col_nchw_f32(P->xin, B, Cin, H, W, 3, 3, 1, 1, col, kpad, s); });
-    View a; a.p = col; a.B = B; a.H = H; a.W = W; a.C = kpad; a.ld = kpad;
+    const bool f16 = b.f16;
+    b.op([=](cudaStream_t s) { launch_im2col_nchw_f32(P->xin, B, Cin, H, W, 3, 3, 1, 1, col, kpad, s, f16); });
+    View a = b.mat(col, B, H, W, kpad, kpad);
     GemmEpilogue ep;
     ep.bias = h->in_blocks[0][0].c.bias;
     ep.out = Builder::chan_slice(cat[n_out - 1], Ca[n_out - 1], h->in_chans[0]);
@@ -1085,7 +1107,7 @@ void build_unet_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
     Buf bg;
     View g = b.act(B, hfinal.H, hfinal.W, hfinal.C, 1, 1, &bg);
     b.groupnorm(hfinal, g, h->out_norm, 1e-5f, true);
-    GemmB wb; wb.p = h->out_conv.w; wb.n_alloc = h->out_conv.n_alloc; wb.ld = h->out_conv.k_alloc;
+    const GemmB wb = Builder::gb(h->out_conv);
     const float* bias = h->out_conv.bias;
     const int N = h->out_conv.cout;
     const ConvTaps taps = taps_rect(3, 3, 1, 1);
@@ -1109,6 +1131,7 @@ void build_unet_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
 // ------------------------------------------------------------------------------------------- decoder plan
 void build_dec_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
   Builder b{h, P, ArenaPlanner(), dry};
+  b.f16 = h->ae_prec == LIDM_PREC_FP16;
   const lidm_config& cfg = h->cfg;
   const int B = P->B, lh = cfg.latent_h, lw = cfg.latent_w, zc = cfg.z_channels;
   Buf bzq, bcol;
@@ -1123,12 +1146,13 @@ void build_dec_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
   }
   const int kpad = h->dec_conv_in.k_alloc;
   bf16* col = b.raw<bf16>((size_t)B * lh * lw * kpad, &bcol);
-  b.op([=](cudaStream_t s) { launch_im2col_nchw_f32(zq, B, zc, lh, lw, 3, 3, 1, 1, col, kpad, s); });
+  const bool f16 = b.f16;
+  b.op([=](cudaStream_t s) { launch_im2col_nchw_f32(zq, B, zc, lh, lw, 3, 3, 1, 1, col, kpad, s, f16); });
   b.release(bzq);
   Buf bx;
   View x = b.act(B, lh, lw, h->dec_top, 0, 0, &bx);
   {
-    View a; a.p = col; a.B = B; a.H = lh; a.W = lw; a.C = kpad; a.ld = kpad;
+    View a = b.mat(col, B, lh, lw, kpad, kpad);
     GemmEpilogue ep;
     ep.bias = h->dec_conv_in.bias;
     ep.out = x;
@@ -1173,7 +1197,7 @@ void build_dec_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
     View g = b.act(B, H, W, h->dec_last, 1, 2, &bg);
     b.groupnorm(x, g, h->dec_norm_out, 1e-6f, true);
     b.release(bx);
-    GemmB wb; wb.p = h->dec_conv_out.w; wb.n_alloc = h->dec_conv_out.n_alloc; wb.ld = h->dec_conv_out.k_alloc;
+    const GemmB wb = Builder::gb(h->dec_conv_out);
     const float* bias = h->dec_conv_out.bias;
     const int N = h->dec_conv_out.cout;
     const ConvTaps taps = taps_rect(1, 4, 1, 0);
@@ -1202,6 +1226,7 @@ void build_dec_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
 // Encoder.forward + quant_conv (model_lidm.py:284-312, autoencoder.py:285-288); image (B,Cin,H,W) fp32 -> (B,embed,h,w)
 void build_enc_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
   Builder b{h, P, ArenaPlanner(), dry};
+  b.f16 = h->ae_prec == LIDM_PREC_FP16;
   const lidm_config& cfg = h->cfg;
   const int B = P->B;
   int H = h->img_h, W = h->img_w;
@@ -1209,10 +1234,11 @@ void build_enc_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
   Buf bcol, bx;
   bf16* col = b.raw<bf16>((size_t)B * H * W * kpad, &bcol);
   const int Cin = cfg.ae_in_channels;
-  b.op([=](cudaStream_t s) { launch_im2col_nchw_f32(P->x, B, Cin, H, W, 3, 3, 1, 1, col, kpad, s); });
+  const bool f16 = b.f16;
+  b.op([=](cudaStream_t s) { launch_im2col_nchw_f32(P->x, B, Cin, H, W, 3, 3, 1, 1, col, kpad, s, f16); });
   View x = b.act(B, H, W, cfg.ae_ch, 0, 0, &bx);
   {
-    View a; a.p = col; a.B = B; a.H = H; a.W = W; a.C = kpad; a.ld = kpad;
+    View a = b.mat(col, B, H, W, kpad, kpad);
     GemmEpilogue ep;
     ep.bias = h->enc_conv_in.bias;
     ep.out = x;
@@ -1243,7 +1269,7 @@ void build_enc_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
     View g = b.act(B, H, W, h->enc_top, 1, 1, &bg);
     b.groupnorm(x, g, h->enc_norm_out, 1e-6f, true);
     b.release(bx);
-    GemmB wb; wb.p = h->enc_conv_out.w; wb.n_alloc = h->enc_conv_out.n_alloc; wb.ld = h->enc_conv_out.k_alloc;
+    const GemmB wb = Builder::gb(h->enc_conv_out);
     const float* bias = h->enc_conv_out.bias;
     const int N = h->enc_conv_out.cout;
     const ConvTaps taps = taps_rect(3, 3, 1, 1);
@@ -1259,6 +1285,7 @@ void build_enc_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
 // ------------------------------------------------------------------------------------------- precise plans
 void build_unet_plan_pass_p(lidm_handle* h, Plan* P, bool dry, size_t* high) {
   Builder b{h, P, ArenaPlanner(), dry};
+  b.precise = true;
   const lidm_config& cfg = h->cfg;
   const int B = P->B;
   const int n_in = (int)h->in_blocks.size(), n_out = (int)h->out_blocks.size();
@@ -1363,6 +1390,7 @@ void build_unet_plan_pass_p(lidm_handle* h, Plan* P, bool dry, size_t* high) {
 
 void build_dec_plan_pass_p(lidm_handle* h, Plan* P, bool dry, size_t* high) {
   Builder b{h, P, ArenaPlanner(), dry};
+  b.precise = true;
   const lidm_config& cfg = h->cfg;
   const int B = P->B, lh = cfg.latent_h, lw = cfg.latent_w, zc = cfg.z_channels;
   Buf bzq, bcol;
@@ -1448,6 +1476,64 @@ void build_dec_plan_pass_p(lidm_handle* h, Plan* P, bool dry, size_t* high) {
         launch_conv_gemm(g, taps, wb, N, ep, s);
       }, PROF_GEMM, gemm_flops(g, taps.n, N) * wb.nseg);
     }
+    b.release(bg);
+  }
+  *high = b.ap.high();
+}
+
+// Encoder.forward + quant_conv in the operand-split (fp32-class) mode: fp32 residual stream, hi/lo bf16 GEMM operands
+void build_enc_plan_pass_p(lidm_handle* h, Plan* P, bool dry, size_t* high) {
+  Builder b{h, P, ArenaPlanner(), dry};
+  b.precise = true;
+  const lidm_config& cfg = h->cfg;
+  const int B = P->B;
+  int H = h->img_h, W = h->img_w;
+  const int kpad = h->enc_conv_in.k_alloc / h->enc_conv_in.nseg;
+  Buf bcol, bx;
+  bf16* col = b.raw<bf16>((size_t)B * H * W * 2 * kpad, &bcol);
+  const int Cin = cfg.ae_in_channels;
+  b.op([=](cudaStream_t s) { launch_im2col_nchw_f32_hl(P->x, B, Cin, H, W, 3, 3, 1, 1, col, kpad, s); });
+  ViewF x = b.actf(B, H, W, cfg.ae_ch, &bx);
+  {
+    View a; a.p = col; a.B = B; a.H = H; a.W = W; a.C = kpad; a.ld = 2 * kpad; a.lo_off = kpad;
+    GemmEpilogue ep;
+    ep.bias = h->enc_conv_in.bias;
+    Builder::set_out_f(ep, x);
+    b.gemm(a, taps_1x1(), h->enc_conv_in, ep);
+  }
+  b.release(bcol);
+  auto step = [&](std::function<void(const ViewF&, const ViewF&)> f, int Ho, int Wo, int C) {
+    Buf bo;
+    ViewF o = b.actf(B, Ho, Wo, C, &bo);
+    f(x, o);
+    b.release(bx);
+    bx = bo; x = o;
+  };
+  for (const EncLevel& L : h->enc_levels) {
+    for (const ResW& r : L.blocks)
+      step([&](const ViewF& i, const ViewF& o) { b.res_block_p(r, i, o, 3, 3, 1, 1, 1, 1e-6f); }, H, W, r.cout);
+    if (L.has_down) {
+      const int Ho = H / L.sh, Wo = W / L.sw;
+      step([&](const ViewF& i, const ViewF& o) { b.down_p(L.down, i, o, L.sh, L.sw, L.pl, L.pt); }, Ho, Wo, L.ch);
+      H = Ho; W = Wo;
+    }
+  }
+  step([&](const ViewF& i, const ViewF& o) { b.res_block_p(h->enc_mid1, i, o, 3, 3, 1, 1, 1, 1e-6f); }, H, W, h->enc_top);
+  step([&](const ViewF& i, const ViewF& o) { b.dec_attn_block_p(h->enc_attn, i, o); }, H, W, h->enc_top);
+  step([&](const ViewF& i, const ViewF& o) { b.res_block_p(h->enc_mid2, i, o, 3, 3, 1, 1, 1, 1e-6f); }, H, W, h->enc_top);
+  {
+    Buf bg;
+    View g = b.act_hl(B, H, W, h->enc_top, 1, 1, &bg);
+    b.groupnorm_f(x, g, h->enc_norm_out, 1e-6f, true);
+    b.release(bx);
+    const GemmB wb = Builder::gb(h->enc_conv_out);
+    const float* bias = h->enc_conv_out.bias;
+    const int N = h->enc_conv_out.cout;
+    const ConvTaps taps = taps_rect(3, 3, 1, 1);
+    b.op([=](cudaStream_t s) {
+      GemmEpilogue ep; ep.bias = bias; ep.out_f32_nchw = P->out;
+      launch_conv_gemm(g, taps, wb, N, ep, s);
+    }, PROF_GEMM, gemm_flops(g, taps.n, N) * wb.nseg);
     b.release(bg);
   }
   *high = b.ap.high();
@@ -1565,7 +1651,8 @@ ResW pack_res(Packer& pk, const std::string& p, int cin, int cout, int kh, int k
     f.n_alloc = r.c2.n_alloc; f.nseg = 1;
     f.k_alloc = kh * kw * cout + cin;
     f.w = dev_alloc<bf16>(h, (size_t)f.n_alloc * f.k_alloc);
-    launch_pack_conv_weight(t.p, cout, cout, kh, kw, f.n_alloc, f.k_alloc, nullptr, nullptr, 1.f, 0, f.w, pk.s);
+    f.f16 = pk.f16;
+    launch_pack_conv_weight(t.p, cout, cout, kh, kw, f.n_alloc, f.k_alloc, nullptr, nullptr, 1.f, 0, f.w, pk.s, pk.f16);
     LIDM_CUDA_CHECK(cudaMemcpy2DAsync(f.w + (size_t)kh * kw * cout, (size_t)f.k_alloc * sizeof(bf16), r.skip.w,
                                       (size_t)r.skip.k_alloc * sizeof(bf16), (size_t)cin * sizeof(bf16), r.skip.n_alloc,
                                       cudaMemcpyDeviceToDevice, pk.s));
@@ -1604,12 +1691,13 @@ AttnW pack_unet_attn(Packer& pk, const std::string& p, int ch, int heads) {
   c.cout = 3 * ch; c.cin = ch; c.kh = c.kw = 1;
   c.n_alloc = round_n_alloc(3 * ch);
   c.nseg = pk.precise ? 3 : 1;
+  c.f16 = pk.f16;
   c.k_alloc = c.nseg * ch;
   c.w = dev_alloc<bf16>(h, (size_t)c.n_alloc * c.k_alloc);
   if (pk.precise)
     launch_pack_conv_weight_split(w.p, 3 * ch, ch, 1, 1, c.n_alloc, 3, perm_dev, scale, 2 * ch, c.w, pk.s);
   else
-    launch_pack_conv_weight(w.p, 3 * ch, ch, 1, 1, c.n_alloc, c.k_alloc, perm_dev, nullptr, scale, 2 * ch, c.w, pk.s);
+    launch_pack_conv_weight(w.p, 3 * ch, ch, 1, 1, c.n_alloc, c.k_alloc, perm_dev, nullptr, scale, 2 * ch, c.w, pk.s, pk.f16);
   std::vector<float> bh(3 * ch), bp(3 * ch);
   LIDM_CUDA_CHECK(cudaMemcpyAsync(bh.data(), bsrc.p, bh.size() * sizeof(float), cudaMemcpyDeviceToHost, pk.s));
   LIDM_CUDA_CHECK(cudaStreamSynchronize(pk.s));
@@ -1631,6 +1719,7 @@ AttnW pack_dec_attn(Packer& pk, const std::string& p, int ch) {
   c.cout = 3 * ch; c.cin = ch; c.kh = c.kw = 1;
   c.n_alloc = round_n_alloc(3 * ch);
   c.nseg = pk.precise ? 3 : 1;
+  c.f16 = pk.f16;
   c.k_alloc = c.nseg * ch;
   if (c.n_alloc != 3 * ch) throw Error(LIDM_ERR_INVALID, "decoder attention channels must be a multiple of 128");
   c.w = dev_alloc<bf16>(h, (size_t)c.n_alloc * c.k_alloc);
@@ -1647,7 +1736,7 @@ AttnW pack_dec_attn(Packer& pk, const std::string& p, int ch) {
                                     c.w + (size_t)i * ch * c.k_alloc, pk.s);
     else
       launch_pack_conv_weight(w.p, ch, ch, 1, 1, ch, ch, nullptr, nullptr, i == 0 ? scale : 1.f, i == 0 ? ch : 0,
-                              c.w + (size_t)i * ch * ch, pk.s);
+                              c.w + (size_t)i * ch * ch, pk.s, pk.f16);
     LIDM_CUDA_CHECK(cudaMemcpy(bh.data(), bsrc.p, ch * sizeof(float), cudaMemcpyDeviceToHost));
     if (i == 0) for (float& v : bh) v *= scale;
     LIDM_CUDA_CHECK(cudaMemcpy(c.bias + (size_t)i * ch, bh.data(), ch * sizeof(float), cudaMemcpyHostToDevice));
@@ -1705,6 +1794,7 @@ void fold_upsample_conv(Packer& pk, const std::string& prefix, int ch, ConvW* ou
       if (itb != h->raw.end()) { cudaFree(itb->second.p); h->raw.erase(itb); }
       h->raw.emplace(name + ".bias", std::move(tb));
       Packer pk2{h, false, pk.s};
+      pk2.f16 = pk.f16;
       out4[py * 2 + px] = pk2.conv(name, ch, ch, 2, 2);
     }
 }
@@ -1717,7 +1807,8 @@ bool in_list(const int32_t* v, int n, int x) {
 void finalize(lidm_handle* h, bool use_ema) {
   const lidm_config& cfg = h->cfg;
   Packer pk{h, use_ema};
-  pk.precise = cfg.precision != 0;
+  pk.precise = h->unet_prec == LIDM_PREC_BF16X3;
+  pk.f16 = h->unet_prec == LIDM_PREC_FP16;
   const std::string U = "model.diffusion_model.";
   const int mc = cfg.model_channels, ted = mc * 4;
   h->latent_channels = cfg.latent_channels > 0 ? cfg.latent_channels : cfg.in_channels;
@@ -1787,7 +1878,7 @@ void finalize(lidm_handle* h, bool use_ema) {
   if (h->has_st) {
     LIDM_REQUIRE(cfg.context_dim > 0 && cfg.context_dim % 64 == 0, "context_dim must be a positive multiple of 64");
     LIDM_REQUIRE(cfg.transformer_depth >= 1, "transformer_depth");
-    LIDM_REQUIRE(!pk.precise, "precise mode does not cover SpatialTransformer U-Nets");
+    LIDM_REQUIRE(!pk.precise && !pk.f16, "SpatialTransformer U-Nets run in the bf16 mode only");
   }
   for (int level = 0; level < cfg.n_channel_mult; ++level) {
     const int mult = cfg.channel_mult[level];
@@ -1883,7 +1974,9 @@ void finalize(lidm_handle* h, bool use_ema) {
     }
   }
 
-  // ---- first stage (decode side)
+  // ---- first stage (decode side): its own numeric mode
+  pk.precise = h->ae_prec == LIDM_PREC_BF16X3;
+  pk.f16 = h->ae_prec == LIDM_PREC_FP16;
   const std::string A = "first_stage_model.";
   if (cfg.embed_dim != 8 || cfg.z_channels != 8) throw Error(LIDM_ERR_INVALID, "embed_dim and z_channels must be 8");
   h->codebook = pk.f32(A + "quantize.embedding.weight", (int64_t)cfg.n_embed * cfg.embed_dim);
@@ -1929,7 +2022,7 @@ void finalize(lidm_handle* h, bool use_ema) {
   if (cfg.ae_use_mask && cfg.ae_out_ch != 2) throw Error(LIDM_ERR_INVALID, "use_mask needs out_ch == 2");
   // ---- first stage (encode side), only when the state-dict carries it
   h->has_encoder = h->raw.count(A + "encoder.conv_in.weight") != 0;
-  if (h->has_encoder && !pk.precise) {
+  if (h->has_encoder) {
     const std::string E = A + "encoder.";
     h->enc_conv_in = pk.conv(E + "conv_in", cfg.ae_ch, cfg.ae_in_channels, 3, 3, (9 * cfg.ae_in_channels + 63) / 64 * 64);
     h->enc_levels.assign(nres, EncLevel());
@@ -1996,6 +2089,7 @@ void finalize(lidm_handle* h, bool use_ema) {
       put(E + "conv_out_q.weight", Wf, 4, wshape);
       put(E + "conv_out_q.bias", Bf, 1, bshape);
       Packer pk2{h, false};
+      pk2.precise = pk.precise; pk2.f16 = pk.f16;
       h->enc_conv_out = pk2.conv(E + "conv_out_q", ed, bin, 3, 3);
     }
   }
@@ -2170,8 +2264,12 @@ int lidm_create(const lidm_config* cfg, lidm_handle** out) {
     const int lw = cfg->latent_w / down, lh = cfg->latent_h / down;
     LIDM_REQUIRE((lw >= 128 ? lw % 128 == 0 : (128 % lw == 0 && lh % (128 / lw) == 0)),
                  "coarsest U-Net level must tile into 128-pixel patches");
+    LIDM_REQUIRE(cfg->precision >= LIDM_PREC_BF16 && cfg->precision <= LIDM_PREC_FP16, "precision");
+    LIDM_REQUIRE(cfg->ae_precision >= 0 && cfg->ae_precision <= LIDM_PREC_FP16 + 1, "ae_precision");
     lidm_handle* h = new lidm_handle();
     h->cfg = *cfg;
+    h->unet_prec = cfg->precision;
+    h->ae_prec = cfg->ae_precision == 0 ? cfg->precision : cfg->ae_precision - 1;
     if (h->cfg.ae_in_channels <= 0) h->cfg.ae_in_channels = 1;
     if (h->cfg.transformer_depth <= 0) h->cfg.transformer_depth = 1;
     *out = h;
@@ -2218,11 +2316,10 @@ int lidm_vq_encode(lidm_handle* h, const float* img, float* z_out, int32_t B, vo
   return guarded(h, [&] {
     require_ready(h, B);
     LIDM_REQUIRE(img != nullptr && z_out != nullptr, "null tensor");
-    if (h->cfg.precision) throw Error(LIDM_ERR_INVALID, "the precise mode does not cover the first-stage encoder");
     if (!h->has_encoder)
       throw Error(LIDM_ERR_STATE, "no encoder weights were loaded (first_stage_model.encoder.* / quant_conv.* missing from the state-dict)");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    Plan* P = get_plan(h, h->enc_plans, B, build_enc_plan_pass);
+    Plan* P = get_plan(h, h->enc_plans, B, h->ae_prec == LIDM_PREC_BF16X3 ? build_enc_plan_pass_p : build_enc_plan_pass);
     P->x = img; P->out = z_out;
     run_plan(P, s);
   });
@@ -2243,7 +2340,7 @@ int lidm_unet_forward_cond(lidm_handle* h, const float* x, const int64_t* t, con
     LIDM_REQUIRE(x != nullptr && t != nullptr && eps_out != nullptr, "null tensor");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     check_conditioning(h, c_concat, context, ctx_len);
-    Plan* P = get_plan(h, h->unet_plans, B, h->cfg.precision ? build_unet_plan_pass_p : build_unet_plan_pass,
+    Plan* P = get_plan(h, h->unet_plans, B, h->unet_prec == LIDM_PREC_BF16X3 ? build_unet_plan_pass_p : build_unet_plan_pass,
                        h->has_st ? ctx_len : 0);
     ensure_time_buffers(h, B);
     run_time_embed(h, t, B, s);
@@ -2297,7 +2394,7 @@ int lidm_ddim_sample_cond(lidm_handle* h, float* x_inout, const int64_t* timeste
     }
     const int Bp = guided ? 2 * B : B;       // batch the U-Net plan runs at
     const int L = h->has_st ? ctx_len : 0;
-    Plan* P = get_plan(h, h->unet_plans, Bp, h->cfg.precision ? build_unet_plan_pass_p : build_unet_plan_pass, L);
+    Plan* P = get_plan(h, h->unet_plans, Bp, h->unet_prec == LIDM_PREC_BF16X3 ? build_unet_plan_pass_p : build_unet_plan_pass, L);
     ensure_time_buffers(h, n_steps);
     const size_t HW = (size_t)cfg.latent_h * cfg.latent_w;
     const size_t elems = (size_t)B * h->latent_channels * HW;
@@ -2413,7 +2510,7 @@ int lidm_vq_decode(lidm_handle* h, const float* z, int32_t force_not_quantize, f
     require_ready(h, B);
     LIDM_REQUIRE(z != nullptr && img_out != nullptr, "null tensor");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    Plan* P = get_plan(h, h->dec_plans, B, h->cfg.precision ? build_dec_plan_pass_p : build_dec_plan_pass);
+    Plan* P = get_plan(h, h->dec_plans, B, h->ae_prec == LIDM_PREC_BF16X3 ? build_dec_plan_pass_p : build_dec_plan_pass);
     P->x = z; P->out = img_out; P->idx_out = idx_out; P->quantize = force_not_quantize ? 0 : 1;
     run_plan(P, s);
   });

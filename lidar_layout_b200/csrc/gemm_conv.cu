@@ -102,7 +102,7 @@ struct PersistLayout {
   static constexpr int COLS = BN / (EPI_WARPS / 4);                 // columns drained by one epilogue thread
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool F16>
 __global__ void __launch_bounds__((PersistLayout<BN, STAGES>::THREADS), 1)
 conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmA2,
@@ -174,7 +174,7 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc = make_idesc_h<F16>(BM, BN);
       int s = 0; uint32_t ph = 0;
       int lt = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
@@ -292,10 +292,10 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
                   for (int i = 0; i < 4; ++i) {
                     float2 f;
-                    f = unpack_bf16(rres[c][i].x); v[i * 8 + 0] += f.x; v[i * 8 + 1] += f.y;
-                    f = unpack_bf16(rres[c][i].y); v[i * 8 + 2] += f.x; v[i * 8 + 3] += f.y;
-                    f = unpack_bf16(rres[c][i].z); v[i * 8 + 4] += f.x; v[i * 8 + 5] += f.y;
-                    f = unpack_bf16(rres[c][i].w); v[i * 8 + 6] += f.x; v[i * 8 + 7] += f.y;
+                    f = unpack_h<F16>(rres[c][i].x); v[i * 8 + 0] += f.x; v[i * 8 + 1] += f.y;
+                    f = unpack_h<F16>(rres[c][i].y); v[i * 8 + 2] += f.x; v[i * 8 + 3] += f.y;
+                    f = unpack_h<F16>(rres[c][i].z); v[i * 8 + 4] += f.x; v[i * 8 + 5] += f.y;
+                    f = unpack_h<F16>(rres[c][i].w); v[i * 8 + 6] += f.x; v[i * 8 + 7] += f.y;
                   }
                 }
                 if (p.geglu) {
@@ -313,8 +313,8 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                       o[k] = v[i * 8 + k] * gelu_erf_fast(gt);
                     }
                     uint4 pk;
-                    pk.x = pack_bf16(o[0], o[1]); pk.y = pack_bf16(o[2], o[3]);
-                    pk.z = pack_bf16(o[4], o[5]); pk.w = pack_bf16(o[6], o[7]);
+                    pk.x = pack_h<F16>(o[0], o[1]); pk.y = pack_h<F16>(o[2], o[3]);
+                    pk.z = pack_h<F16>(o[4], o[5]); pk.w = pack_h<F16>(o[6], o[7]);
                     *reinterpret_cast<uint4*>(gb + (((gbase + i) ^ (row & 7)) << 4)) = pk;
                   }
                   continue;
@@ -324,10 +324,10 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   uint4 pk;
-                  pk.x = pack_bf16(v[i * 8 + 0], v[i * 8 + 1]);
-                  pk.y = pack_bf16(v[i * 8 + 2], v[i * 8 + 3]);
-                  pk.z = pack_bf16(v[i * 8 + 4], v[i * 8 + 5]);
-                  pk.w = pack_bf16(v[i * 8 + 6], v[i * 8 + 7]);
+                  pk.x = pack_h<F16>(v[i * 8 + 0], v[i * 8 + 1]);
+                  pk.y = pack_h<F16>(v[i * 8 + 2], v[i * 8 + 3]);
+                  pk.z = pack_h<F16>(v[i * 8 + 4], v[i * 8 + 5]);
+                  pk.w = pack_h<F16>(v[i * 8 + 6], v[i * 8 + 7]);
                   *reinterpret_cast<uint4*>(box + (((cbase + i) ^ (row & 7)) << 4)) = pk;
                 }
               }
@@ -366,7 +366,7 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  const float2 f = unpack_bf16(uu[i]);
+                  const float2 f = unpack_h<F16>(uu[i]);
                   gs += f.x + f.y;
                   gq += f.x * f.x + f.y * f.y;
                 }
@@ -427,16 +427,16 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             float2 f;
-            f = unpack_bf16(rres[i].x); v[i * 8 + 0] += f.x; v[i * 8 + 1] += f.y;
-            f = unpack_bf16(rres[i].y); v[i * 8 + 2] += f.x; v[i * 8 + 3] += f.y;
-            f = unpack_bf16(rres[i].z); v[i * 8 + 4] += f.x; v[i * 8 + 5] += f.y;
-            f = unpack_bf16(rres[i].w); v[i * 8 + 6] += f.x; v[i * 8 + 7] += f.y;
+            f = unpack_h<F16>(rres[i].x); v[i * 8 + 0] += f.x; v[i * 8 + 1] += f.y;
+            f = unpack_h<F16>(rres[i].y); v[i * 8 + 2] += f.x; v[i * 8 + 3] += f.y;
+            f = unpack_h<F16>(rres[i].z); v[i * 8 + 4] += f.x; v[i * 8 + 5] += f.y;
+            f = unpack_h<F16>(rres[i].w); v[i * 8 + 6] += f.x; v[i * 8 + 7] += f.y;
           }
         } else if (p.res != nullptr) {
           const bf16* rp = p.res + ((size_t)(b * p.H + h) * p.res_Wp + (w + p.res_hl)) * p.res_ld + n;
 #pragma unroll
           for (int j = 0; j < CH; ++j)
-            if (n + j < p.N) v[j] += __bfloat162float(rp[j]);
+            if (n + j < p.N) v[j] += load_h<F16>(rp + j);
         }
         if (p.res_f32 != nullptr) {
           const float* rp = p.res_f32 + ((size_t)b * HW + pix) * p.res_f32_ld + n;
@@ -457,16 +457,16 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (n >= p.split_n) {
           bf16* ot = p.out_t + ((size_t)b * (p.N - p.split_n) + (n - p.split_n)) * HW + pix;
 #pragma unroll
-          for (int j = 0; j < CH; ++j) ot[(size_t)j * HW] = __float2bfloat16(v[j]);
+          for (int j = 0; j < CH; ++j) store_h<F16>(ot + (size_t)j * HW, v[j]);
         } else if (p.out != nullptr) {
           if constexpr (CH == 32) {
             uint4 pk[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              pk[i].x = pack_bf16(v[i * 8 + 0], v[i * 8 + 1]);
-              pk[i].y = pack_bf16(v[i * 8 + 2], v[i * 8 + 3]);
-              pk[i].z = pack_bf16(v[i * 8 + 4], v[i * 8 + 5]);
-              pk[i].w = pack_bf16(v[i * 8 + 6], v[i * 8 + 7]);
+              pk[i].x = pack_h<F16>(v[i * 8 + 0], v[i * 8 + 1]);
+              pk[i].y = pack_h<F16>(v[i * 8 + 2], v[i * 8 + 3]);
+              pk[i].z = pack_h<F16>(v[i * 8 + 4], v[i * 8 + 5]);
+              pk[i].w = pack_h<F16>(v[i * 8 + 6], v[i * 8 + 7]);
             }
             if (use_tma_store) {
               // staging layout = TMA box [pixel row][64 ch] (128 B rows, 128B swizzle): chunk16 ^= (row & 7)
@@ -495,7 +495,7 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             bf16* o = p.out + ((size_t)(b * p.H + h) * p.out_Wp + (w + p.out_hl)) * p.out_ld + n;
 #pragma unroll
             for (int j = 0; j < CH; ++j)
-              if (n + j < p.N) o[j] = __float2bfloat16(v[j]);
+              if (n + j < p.N) store_h<F16>(o + j, v[j]);
           }
         }
         if (p.out_f32_nhwc != nullptr) {
@@ -536,21 +536,21 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, L::TMEM_COLS); }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool F16>
 void launch_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmA2,
                     const GemmKernelParams& p,
                     int num_m_tiles, int num_tiles, int use_tma_store, cudaStream_t stream) {
   using L = PersistLayout<BN, STAGES>;
   static int num_sms = 0;
   if (num_sms == 0) {
-    LIDM_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_persist_kernel<BN, STAGES>,
+    LIDM_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_persist_kernel<BN, STAGES, F16>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     int dev = 0;
     LIDM_CUDA_CHECK(cudaGetDevice(&dev));
     LIDM_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  conv_gemm_persist_kernel<BN, STAGES><<<grid, L::THREADS, L::TOTAL, stream>>>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles,
+  conv_gemm_persist_kernel<BN, STAGES, F16><<<grid, L::THREADS, L::TOTAL, stream>>>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles,
                                                                        use_tma_store);
   LIDM_CUDA_CHECK(cudaGetLastError());
   LIDM_COUNT_LAUNCH(1);
@@ -574,6 +574,10 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
   LIDM_REQUIRE(a.wpitch == 0 && ep.residual.wpitch == 0 && (ep.out.wpitch == 0 || ep.out.hl + ep.out.hr == 0),
                "a row pitch override is supported on halo-free outputs only");
   LIDM_REQUIRE(taps.n >= 1 && taps.n <= 9, "1..9 taps");
+  LIDM_REQUIRE(wtb.f16 == a.f16 && (ep.out.p == nullptr || ep.out.f16 == a.f16) &&
+                   (ep.residual.p == nullptr || ep.residual.f16 == a.f16) && (ep.a2.p == nullptr || ep.a2.f16 == a.f16) &&
+                   (!a.f16 || wtb.nseg == 1),
+               "GEMM operands and 2-byte outputs must share one element format (bf16 or fp16)");
   const int nseg = wtb.nseg;
   LIDM_REQUIRE(nseg >= 1 && nseg <= 3 && (nseg != 3 || a.lo_off > 0), "operand-split segments");
   const int W = a.W, H = a.H;
@@ -677,10 +681,16 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
                  "GroupNorm statistics need whole 128-pixel tiles inside one sample");
     p.gst = ep.out.gst; p.gst_ld = ep.out.gst_ld; p.gst_slots = ep.out.gst_slots; p.gst_slot0 = ep.out.gst_slot0;
   }
-  if (BN == 256) launch_persist<256, 3>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream);
-  else if (BN == 128) launch_persist<128, 4>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream);
-  else if (BN == 64) launch_persist<64, 6>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream);
-  else launch_persist<16, 6>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream);
+#define LIDM_LAUNCH_GEMM(F16)                                                                                         \
+  do {                                                                                                                  \
+    if (BN == 256) launch_persist<256, 3, F16>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream);   \
+    else if (BN == 128) launch_persist<128, 4, F16>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream); \
+    else if (BN == 64) launch_persist<64, 6, F16>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream); \
+    else launch_persist<16, 6, F16>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream);             \
+  } while (0)
+  if (a.f16) LIDM_LAUNCH_GEMM(true);
+  else LIDM_LAUNCH_GEMM(false);
+#undef LIDM_LAUNCH_GEMM
 }
 
 }  // namespace lidm

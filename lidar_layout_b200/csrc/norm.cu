@@ -17,7 +17,7 @@ namespace {
 // cpg = channels per group.  If cpg >= 8 the 8 channels fall in one group, otherwise in 8/cpg groups; NSUB == 8 is
 // the generic path (one accumulator per channel).  All reductions run in a fixed order: results are bit-reproducible
 // and, because the chunking depends only on (H*W, C), independent of the batch size.
-template <int NSUB>
+template <int NSUB, bool F16>
 __global__ void gn_stats_kernel(const bf16* __restrict__ x, int H, int W, int hl, int Wp, int ld, int C, int cpg,
                                 int groups, int pix_per_cta, float* __restrict__ partials, int nchunks) {
   extern __shared__ float sh[];  // [blockDim][NSUB][2]
@@ -37,7 +37,7 @@ __global__ void gn_stats_kernel(const bf16* __restrict__ x, int H, int W, int hl
     const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float2 f = unpack_bf16(uu[i]);
+      const float2 f = unpack_h<F16>(uu[i]);
       if constexpr (NSUB == 8) {
         s[2 * i] += f.x; q[2 * i] += f.x * f.x;
         s[2 * i + 1] += f.y; q[2 * i + 1] += f.y * f.y;
@@ -100,6 +100,7 @@ __device__ __forceinline__ float silu_f(float v) {
   return fmaf(h, t, h);
 }
 
+template <bool F16>
 __global__ void gn_apply_kernel(const bf16* __restrict__ x, int H, int W, int xhl, int xWp, int xld, bf16* __restrict__ y,
                                 int yhl, int yhr, int yWp, int yld, int C, int cpg, int groups,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
@@ -144,11 +145,11 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int H, int W, int xh
     uint32_t oo[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float2 f = unpack_bf16(uu[i]);
+      const float2 f = unpack_h<F16>(uu[i]);
       float a = f.x * sc[2 * i] + sf[2 * i];
       float c = f.y * sc[2 * i + 1] + sf[2 * i + 1];
       if (silu) { a = silu_f(a); c = silu_f(c); }
-      oo[i] = pack_bf16(a, c);
+      oo[i] = pack_h<F16>(a, c);
     }
     const uint4 o = make_uint4(oo[0], oo[1], oo[2], oo[3]);
     const size_t rowbase = (size_t)(b * H + h) * yWp;
@@ -171,6 +172,7 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int H, int W, int xh
 // element instead of 6) in a single launch.  Reductions run in a fixed order (per-thread partials -> fixed lane
 // assignment -> xor-shuffle tree): bit-reproducible and, one sample per CTA, independent of the batch size.
 // gn_apply with the statistics reduced from the producers' granule partials (View::gst) instead of a stats pass.
+template <bool F16>
 __global__ void gn_apply_gst_kernel(const bf16* __restrict__ x, int H, int W, int xhl, int xWp, int xld, bf16* __restrict__ y,
                                     int yhl, int yhr, int yWp, int yld, int C, int cpg, int groups,
                                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
@@ -235,11 +237,11 @@ __global__ void gn_apply_gst_kernel(const bf16* __restrict__ x, int H, int W, in
     uint32_t oo[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float2 f = unpack_bf16(uu[i]);
+      const float2 f = unpack_h<F16>(uu[i]);
       float a = f.x * sc[2 * i] + sf[2 * i];
       float c = f.y * sc[2 * i + 1] + sf[2 * i + 1];
       if (silu) { a = silu_f(a); c = silu_f(c); }
-      oo[i] = pack_bf16(a, c);
+      oo[i] = pack_h<F16>(a, c);
     }
     const uint4 o = make_uint4(oo[0], oo[1], oo[2], oo[3]);
     const size_t rowbase = (size_t)(b * H + h) * yWp;
@@ -259,7 +261,7 @@ __global__ void gn_apply_gst_kernel(const bf16* __restrict__ x, int H, int W, in
   for (; pix < p1; pix += pstride) emit(pix, __ldg(addr(pix)));
 }
 
-template <int NV>
+template <int NV, bool F16>
 __global__ void __launch_bounds__(512)
 gn_fused_kernel(const bf16* __restrict__ x, int H, int W, int xhl, int xWp, int xld, bf16* __restrict__ y, int yhl, int yhr,
                 int yWp, int yld, int cpg, int gpc, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -291,7 +293,7 @@ gn_fused_kernel(const bf16* __restrict__ x, int H, int W, int xhl, int xWp, int 
     const uint32_t uu[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float2 f = unpack_bf16(uu[i]);
+      const float2 f = unpack_h<F16>(uu[i]);
       sm += f.x + f.y;
       sq += f.x * f.x + f.y * f.y;
     }
@@ -341,11 +343,11 @@ gn_fused_kernel(const bf16* __restrict__ x, int H, int W, int xhl, int xWp, int 
     uint32_t oo[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float2 f = unpack_bf16(uu[i]);
+      const float2 f = unpack_h<F16>(uu[i]);
       float a = f.x * sc[2 * i] + sf[2 * i];
       float c = f.y * sc[2 * i + 1] + sf[2 * i + 1];
       if (silu) { a = silu_f(a); c = silu_f(c); }
-      oo[i] = pack_bf16(a, c);
+      oo[i] = pack_h<F16>(a, c);
     }
     const uint4 o = make_uint4(oo[0], oo[1], oo[2], oo[3]);
     const size_t rowbase = (size_t)(b * H + h) * yWp;
@@ -362,7 +364,7 @@ void launch_groupnorm(const View& x, const View& y, const float* gamma, const fl
                       bool silu, float* partials, cudaStream_t s) {
   const int C = x.C;
   LIDM_REQUIRE(C % 8 == 0 && C % groups == 0, "C must be a multiple of 8 and of the group count");
-  LIDM_REQUIRE(y.C == C && y.B == x.B && y.H == x.H && y.W == x.W, "GroupNorm in/out shape mismatch");
+  LIDM_REQUIRE(y.C == C && y.B == x.B && y.H == x.H && y.W == x.W && x.f16 == y.f16, "GroupNorm in/out shape mismatch");
   LIDM_REQUIRE(x.ld % 8 == 0 && y.ld % 8 == 0, "ld alignment");
   const int cpg = C / groups;
   const bool regular = cpg >= 8 ? (cpg % 8 == 0) : (8 % cpg == 0 && cpg >= 2);
@@ -391,8 +393,10 @@ void launch_groupnorm(const View& x, const View& y, const float* gamma, const fl
       const int v = best * vg, pr = 512 / v, nv = (HW + pr - 1) / pr;
       dim3 grid(groups / best, x.B);
 #define GN_FUSED(NV)                                                                                                  \
-  gn_fused_kernel<NV><<<grid, 512, 0, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, y.hl, y.hr, y.Wp(), y.ld, cpg, best, \
-                                           gamma, beta, eps, silu ? 1 : 0)
+  do {                                                                                                                \
+    if (x.f16) gn_fused_kernel<NV, true><<<grid, 512, 0, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, y.hl, y.hr, y.Wp(), y.ld, cpg, best, gamma, beta, eps, silu ? 1 : 0); \
+    else gn_fused_kernel<NV, false><<<grid, 512, 0, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, y.hl, y.hr, y.Wp(), y.ld, cpg, best, gamma, beta, eps, silu ? 1 : 0); \
+  } while (0)
       if (nv <= 4) GN_FUSED(4);
       else if (nv <= 8) GN_FUSED(8);
       else GN_FUSED(16);
@@ -413,22 +417,29 @@ void launch_groupnorm(const View& x, const View& y, const float* gamma, const fl
   const int nsub = !regular ? 8 : (cpg >= 8 ? 1 : 8 / cpg);
   const size_t shstats = (size_t)threads * nsub * 2 * sizeof(float);
   const size_t shbytes = groups * 2 * sizeof(float);
-  if (nsub == 8)
-    gn_stats_kernel<8><<<grid, threads, shstats, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, C, cpg, groups, pix_per_cta,
-                                                       partials, nchunks);
-  else if (nsub == 1)
-    gn_stats_kernel<1><<<grid, threads, shstats, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, C, cpg, groups, pix_per_cta,
-                                                       partials, nchunks);
-  else if (nsub == 2)
-    gn_stats_kernel<2><<<grid, threads, shstats, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, C, cpg, groups, pix_per_cta,
-                                                       partials, nchunks);
-  else
-    gn_stats_kernel<4><<<grid, threads, shstats, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, C, cpg, groups, pix_per_cta,
-                                                       partials, nchunks);
+#define GN_STATS(NS, F)                                                                                              \
+  gn_stats_kernel<NS, F><<<grid, threads, shstats, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, C, cpg, groups, pix_per_cta, \
+                                                        partials, nchunks)
+#define GN_STATS_F(F)                                                                                                 \
+  do {                                                                                                                \
+    if (nsub == 8) GN_STATS(8, F);                                                                                    \
+    else if (nsub == 1) GN_STATS(1, F);                                                                               \
+    else if (nsub == 2) GN_STATS(2, F);                                                                               \
+    else GN_STATS(4, F);                                                                                              \
+  } while (0)
+  if (x.f16) GN_STATS_F(true);
+  else GN_STATS_F(false);
+#undef GN_STATS_F
+#undef GN_STATS
   LIDM_CUDA_CHECK(cudaGetLastError());
-  gn_apply_kernel<<<grid, threads, shbytes, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, y.hl, y.hr, y.Wp(), y.ld, C,
-                                                 cpg, groups, gamma, beta, eps, silu ? 1 : 0, partials, nchunks,
-                                                 pix_per_cta);
+  if (x.f16)
+    gn_apply_kernel<true><<<grid, threads, shbytes, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, y.hl, y.hr, y.Wp(), y.ld, C,
+                                                         cpg, groups, gamma, beta, eps, silu ? 1 : 0, partials, nchunks,
+                                                         pix_per_cta);
+  else
+    gn_apply_kernel<false><<<grid, threads, shbytes, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, y.hl, y.hr, y.Wp(), y.ld, C,
+                                                          cpg, groups, gamma, beta, eps, silu ? 1 : 0, partials, nchunks,
+                                                          pix_per_cta);
   LIDM_CUDA_CHECK(cudaGetLastError());
   LIDM_COUNT_LAUNCH(2);
 }
@@ -450,7 +461,7 @@ void launch_groupnorm_from_gstats(const View& x, const View& y, const float* gam
   static int occ_cache[33] = {0};
   int& occ = occ_cache[threads / 32 <= 32 ? threads / 32 : 0];
   if (occ == 0) {
-    LIDM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_apply_gst_kernel, threads,
+    LIDM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_apply_gst_kernel<false>, threads,
                                                                   groups * 2 * sizeof(float)));
     if (occ < 1) occ = 1;
   }
@@ -462,10 +473,15 @@ void launch_groupnorm_from_gstats(const View& x, const View& y, const float* gam
   pix_per_cta = (pix_per_cta + pstride - 1) / pstride * pstride;
   nchunks = (HW + pix_per_cta - 1) / pix_per_cta;
   dim3 grid(nchunks, x.B);
-  gn_apply_gst_kernel<<<grid, threads, groups * 2 * sizeof(float), s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, y.hl, y.hr,
-                                                                       y.Wp(), y.ld, C, cpg, groups, gamma, beta, eps,
-                                                                       silu ? 1 : 0, x.gst, x.gst_ld, x.gst_slots,
-                                                                       pix_per_cta);
+  LIDM_REQUIRE(x.f16 == y.f16, "GroupNorm element formats");
+#define GN_GST(F)                                                                                                     \
+  gn_apply_gst_kernel<F><<<grid, threads, groups * 2 * sizeof(float), s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, y.hl, y.hr, \
+                                                                          y.Wp(), y.ld, C, cpg, groups, gamma, beta, eps, \
+                                                                          silu ? 1 : 0, x.gst, x.gst_ld, x.gst_slots,  \
+                                                                          pix_per_cta)
+  if (x.f16) GN_GST(true);
+  else GN_GST(false);
+#undef GN_GST
   LIDM_CUDA_CHECK(cudaGetLastError());
   LIDM_COUNT_LAUNCH(1);
 }

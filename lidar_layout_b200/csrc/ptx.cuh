@@ -2,6 +2,7 @@
 // Everything here is hand-written; no CUTLASS/CuTe dependency.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -245,6 +246,15 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// kind::f16 with IEEE half operands (A = B = F16, D = F32): same tensor rate as bf16, 3 more mantissa bits.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+template <bool F16>
+__host__ __device__ constexpr uint32_t make_idesc_h(int M, int N) {
+  return F16 ? make_idesc_f16(M, N) : make_idesc_bf16(M, N);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -252,6 +262,39 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
+}
+
+// IEEE half pairs; the conversion saturates to +-65504 instead of producing inf (an activation outside the half range is
+// clamped, never turned into NaNs further down)
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // first source -> upper half
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f16(uint32_t u) {
+  __half2 v = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(v);
+}
+// 2-byte activation / weight element of the tensor-core paths: bf16 (default) or IEEE half (View::f16)
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_h(float a, float b) { return F16 ? pack_f16(a, b) : pack_bf16(a, b); }
+template <bool F16>
+__device__ __forceinline__ float2 unpack_h(uint32_t u) { return F16 ? unpack_f16(u) : unpack_bf16(u); }
+template <bool F16>
+__device__ __forceinline__ void store_h(__nv_bfloat16* p, float v) {
+  if (F16) *reinterpret_cast<uint16_t*>(p) = static_cast<uint16_t>(pack_f16(v, 0.f) & 0xffffu);
+  else *p = __float2bfloat16(v);
+}
+template <bool F16>
+__device__ __forceinline__ float load_h(const __nv_bfloat16* p) {
+  if (F16) return __half2float(*reinterpret_cast<const __half*>(p));
+  return __bfloat162float(*p);
+}
+// runtime-flag forms for the memory-bound kernels
+__device__ __forceinline__ uint32_t pack_hr(float a, float b, bool f16) { return f16 ? pack_f16(a, b) : pack_bf16(a, b); }
+__device__ __forceinline__ float2 unpack_hr(uint32_t u, bool f16) { return f16 ? unpack_f16(u) : unpack_bf16(u); }
+__device__ __forceinline__ void store_hr(__nv_bfloat16* p, float v, bool f16) {
+  if (f16) store_h<true>(p, v); else store_h<false>(p, v);
 }
 
 }  // namespace lidm

@@ -55,10 +55,11 @@ class LatentDiffusion:
     """Drop-in for the sampling-side API of lidm.models.diffusion.ddpm.LatentDiffusion."""
 
     def __init__(self, cfg: LidmConfig, device: Optional[torch.device] = None, use_ema: bool = True,
-                 precision: Optional[str] = None):
-        if precision is not None:
+                 precision: Optional[str] = None, ae_precision: Optional[str] = None):
+        if precision is not None or ae_precision is not None:
             import dataclasses
-            cfg = dataclasses.replace(cfg, precision=precision)
+            cfg = dataclasses.replace(cfg, precision=precision or cfg.precision,
+                                      ae_precision=ae_precision or cfg.ae_precision)
         self.cfg = cfg
         self.engine = Engine(cfg, device)
         self.device = self.engine.device
@@ -82,11 +83,12 @@ class LatentDiffusion:
 
     # ---- construction ---------------------------------------------------------------------------------
     @classmethod
-    def from_config(cls, config, device=None, use_ema=True, precision=None) -> "LatentDiffusion":
+    def from_config(cls, config, device=None, use_ema=True, precision=None, ae_precision=None) -> "LatentDiffusion":
         """config: path to a reference YAML, or the parsed dict (what OmegaConf.load would give).
-        precision: None / "bf16" (fast path) or "fp32" (precise operand-split path)."""
+        precision (U-Net) / ae_precision (first stage): None, "bf16", "fp32" (precise operand-split path) or "fp16";
+        the default is a bf16 U-Net with an fp16 first stage (LidmConfig.ae_precision)."""
         cfg = from_yaml(config) if isinstance(config, str) else from_reference_dict(config)
-        return cls(cfg, device, use_ema, precision)
+        return cls(cfg, device, use_ema, precision, ae_precision)
 
     def register_schedule(self):
         """DDPM.register_schedule (ddpm.py:120-160)."""

@@ -58,9 +58,11 @@ def to_cconfig(cfg: LidmConfig) -> _lib.CConfig:
     for i, s in enumerate(a.strides):
         c.ae_strides[i][0], c.ae_strides[i][1] = s
     c.scale_factor = float(cfg.scale_factor)
-    if cfg.precision not in ("bf16", "fp32"):
-        raise ValueError("precision must be 'bf16' or 'fp32'")
-    c.precision = 1 if cfg.precision == "fp32" else 0
+    modes = {"bf16": 0, "fp32": 1, "fp16": 2}     # LIDM_PREC_BF16 / BF16X3 / FP16
+    if cfg.precision not in modes or cfg.ae_precision_resolved not in modes:
+        raise ValueError("precision / ae_precision must be one of 'bf16', 'fp32', 'fp16'")
+    c.precision = modes[cfg.precision]
+    c.ae_precision = modes[cfg.ae_precision_resolved] + 1
     c.latent_channels = cfg.channels
     c.use_spatial_transformer = int(bool(u.use_spatial_transformer))
     c.context_dim = int(u.context_dim or 0)

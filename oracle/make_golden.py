@@ -1,6 +1,7 @@
 """Generate tests/golden/*.npz by executing the UNMODIFIED reference modules (this container only).
 
     python -m oracle.make_golden            # writes tests/golden/{kitti_uncond,tiny}.npz
+    python -m oracle.make_golden --batch    # full-size fixture at B = 4 (kitti_uncond_b4.npz); also --cond / --ae / --ddpm
 
 The synthetic state-dict (lidar_layout_b200.weights.random_state_dict, numpy PCG64 => platform
 independent) is loaded with strict key/shape checking into the reference's LatentDiffusion built from
@@ -411,7 +412,35 @@ def main_cond():
     make_cond("kitti_cam2lidar_L77", full, tiny_yaml(full), B=1, S_short=0, L=77, full=False)
 
 
+@torch.no_grad()
+def make_batch(name, cfg, yaml_dict, B):
+    """Full-size parity at a batch > 1: apply_model with per-sample timesteps and
+    decode_first_stage (quantised and not) of the unmodified reference at batch B, on inputs of their own seed."""
+    model = build_reference(cfg, yaml_dict)
+    sd = load_synthetic(model, cfg)
+    x_T, _, z = inputs_for(cfg, B, 1, seed=INPUT_SEED + 21)
+    t = np.asarray([501, 21, 900, 333, 7, 650, 120, 999][:B], dtype=np.int64)
+    out = {"B": np.int64(B), "weight_seed": np.int64(WEIGHT_SEED), "input_seed": np.int64(INPUT_SEED + 21),
+           "weights_digest": np.frombuffer(sd_digest(sd).encode(), dtype=np.uint8), "t": t}
+    out["eps"] = model.apply_model(torch.from_numpy(x_T), torch.from_numpy(t), None).numpy()
+    out["decode_q"] = model.decode_first_stage(torch.from_numpy(z)).numpy()
+    out["decode_nq"] = model.decode_first_stage(torch.from_numpy(z), force_not_quantize=True).numpy()
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {os.path.getsize(path) / 1e6:.2f} MB; keys={sorted(out)}")
+
+
+def main_batch():
+    torch.set_num_threads(os.cpu_count())
+    import yaml
+    with open(os.path.join(ref_shim.REFERENCE_ROOT, "models/lidm/kitti/uncond/config.yaml")) as f:
+        y = yaml.safe_load(f)
+    make_batch("kitti_uncond_b4", cfgmod.from_reference_dict(y), y, B=4)
+
+
 def main():
+    if "--batch" in sys.argv:
+        return main_batch()
     if "--cond" in sys.argv:
         return main_cond()
     if "--ae" in sys.argv:

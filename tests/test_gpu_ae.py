@@ -1,6 +1,6 @@
 """GPU (-m gpu): first-stage encoder through the C ABI against fixtures of the UNMODIFIED
 reference (tests/golden/{tiny_ae,kitti_ae}.npz): VQModelInterface.encode and the encode -> decode round trip.
-bf16 tensor-core path: the encoder is a stack of ~25 convs + 20 GroupNorms, same error budget as the decoder."""
+Default numeric mix: the first stage runs in IEEE half (tests/test_gpu_modes.py covers the other modes)."""
 import os
 
 import numpy as np
@@ -39,7 +39,7 @@ def test_encode_first_stage(setup):
     assert z.shape == g["encode"].shape
     e = rel(z, g["encode"])
     print(f"[{name}] encode rel {e:.3e}")
-    assert e < 3e-2
+    assert e < 1e-2
     assert torch.equal(model.get_first_stage_encoding(z), cfg.scale_factor * z)
     # deterministic and batch-invariant
     z1 = model.encode_first_stage(x[:1])
@@ -53,10 +53,10 @@ def test_round_trip(setup):
     rec = model.decode_first_stage(z, force_not_quantize=True)
     e = rel(rec, g["recon_nq"])
     print(f"[{name}] encode->decode (not quantised) rel {e:.3e}")
-    assert e < 8e-2      # measured 6.0e-2 on the full-size AE: the 2e-2 encode error re-amplified by the bf16 decoder (2.4e-2 alone)
+    assert e < 2e-2      # two networks back to back (the decoder re-amplifies the encoder's error)
     # quantised decode of the reference's own latent: VQ indices are discrete, covered by test_gpu_model
     rec_q = model.decode_first_stage(torch.from_numpy(g["encode"]).cuda())
-    assert rel(rec_q, g["recon_q"]) < 4e-2
+    assert rel(rec_q, g["recon_q"]) < 1e-2
 
 
 def test_encoder_needs_its_weights(built_lib):

@@ -81,11 +81,13 @@ def test_decode_first_stage(setup):
     _, _, z = inputs_for(cfg, int(g["B"]), int(g["S_short"]) + 2)
     img, idx = eng.vq_decode(torch.from_numpy(z).cuda(), False, True)
     assert np.array_equal(idx.cpu().numpy(), g["vq_idx"])                 # integer work: exact
-    # bf16 decoder (39 convs + 30 GroupNorms in sequence): measured 2.4e-2 against north_star's bf16 budget of 2e-2
-    # per U-Net evaluation.  The 1e-2 final-image bar is met by the precise mode (tests/test_gpu_precise.py: 1e-3).
-    assert rel(img, g["decode_q"]) < 4e-2
+    # default mix: bf16 U-Net + IEEE-half first stage (a bf16 decoder's rounding alone is 2.4e-2; see
+    # tests/test_gpu_modes.py for every mode): north_star's 1e-2 final-image bar
+    e_q = rel(img, g["decode_q"])
     img = eng.vq_decode(torch.from_numpy(z).cuda(), True)
-    assert rel(img, g["decode_nq"]) < 4e-2
+    e_nq = rel(img, g["decode_nq"])
+    print(f"[{name}] decode rel: quantised {e_q:.3e}, not quantised {e_nq:.3e}")
+    assert e_q < IMG_TOL and e_nq < IMG_TOL
 
 
 def test_degenerate_codebook_and_determinism(setup):
@@ -98,18 +100,37 @@ def test_degenerate_codebook_and_determinism(setup):
 
 
 def test_headline_batch_properties(built_lib):
-    """BASELINE config 2 size (B=64 would take the whole decode workspace; B=16 keeps the test short): finite,
-    per-sample independent, and equal to the B=1 result for the same sample."""
+    """BASELINE config 2 at its benchmarked batch (B = 64, full size): U-Net and first-stage decode are finite and
+    bit-identical, sample for sample, to the same sample run at B = 4 and at B = 1 (nothing in the path reduces across
+    samples, and no tile-shape decision may change the bits)."""
+    import os
     from lidar_layout_b200.engine import Engine
     cfg = C.kitti_uncond()
     eng = Engine(cfg).load_state_dict(random_state_dict(cfg, 0))
-    x_T, _, _ = inputs_for(cfg, 16, 1, seed=3)
+    g4 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kitti_uncond_b4.npz"))
+    x4, _, z4 = inputs_for(cfg, 4, 1, seed=int(g4["input_seed"]))
+    x_T, _, z = inputs_for(cfg, 64, 1, seed=3)
+    x_T[10:14], z[10:14] = x4, z4                       # the fixture's samples ride inside the big batch
     x = torch.from_numpy(x_T).cuda()
-    t = torch.full((16,), 501, dtype=torch.long).cuda()
+    t = torch.full((64,), 501, dtype=torch.long)
+    t[10:14] = torch.from_numpy(g4["t"])
+    t = t.cuda()
     e = eng.unet_forward(x, t)
     assert bool(torch.isfinite(e).all())
-    e5 = eng.unet_forward(x[5:6], t[5:6])
-    assert torch.equal(e5[0], e[5])
+    e4 = eng.unet_forward(x[10:14], t[10:14])
+    e1 = eng.unet_forward(x[12:13], t[12:13])
+    assert torch.equal(e4, e[10:14]) and torch.equal(e1[0], e[12])
+    assert rel(e4, g4["eps"]) < EPS_TOL_BF16
+    zz = torch.from_numpy(z).cuda()
+    img = eng.vq_decode(zz)
+    assert bool(torch.isfinite(img).all())
+    img4 = eng.vq_decode(zz[10:14])
+    img1 = eng.vq_decode(zz[12:13])
+    assert torch.equal(img4, img[10:14]) and torch.equal(img1[0], img[12])
+    e_q = rel(img4, g4["decode_q"])
+    e_nq = rel(eng.vq_decode(zz[10:14], True), g4["decode_nq"])
+    print(f"full size B=4 fixture: eps {rel(e4, g4['eps']):.3e}, decode {e_q:.3e} / {e_nq:.3e}")
+    assert e_q < IMG_TOL and e_nq < IMG_TOL
 
 
 def test_plan_cache_eviction_keeps_results(built_lib):

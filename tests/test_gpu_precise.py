@@ -111,6 +111,7 @@ def test_ddim50_free_running_headline_config(built_lib):
     zb, _ = fast.ddim_sample(torch.from_numpy(x_T).cuda(), ts, tab)
     b_lat, b_img = rel(zb, z_ref), rel(fast.vq_decode(zb, True), img_ref)
     print(f"DDIM-50 full size: precise latent {e_lat:.2e} image {e_img:.2e}; bf16 latent {b_lat:.2e} image {b_img:.2e}")
-    # measured on B200: precise 6.8e-5 / 8.2e-5, bf16 1.2e-3 / 1.06e-2 (the bf16 decoder carries the image error)
+    # measured on B200: precise 6.8e-5 / 8.2e-5; bf16 U-Net latent 1.2e-3 (a bf16 decoder took the image to 1.06e-2; the
+    # default fp16 first stage keeps it within the bar)
     assert e_lat < 1e-3 and e_img < 1e-3
-    assert b_lat < IMG_TOL and b_img < 2e-2
+    assert b_lat < IMG_TOL and b_img < IMG_TOL
