@@ -33,6 +33,11 @@ DDIM_STEPS = 50
 METRIC = "samples/sec DDIM-50 64x1024 LiDM (sampling + VQ decode + back-projection)"
 
 
+_N = {"bf16": "bf16", "fp16": "fp16", "fp32": "bf16x3 (3-way bf16 operand split, fp32 residual stream)"}
+DTYPE_NAMES = {(u, a): (_N[u] if u == a else f"{_N[u]} U-Net + {_N[a]} first stage") + ", fp32 accumulate"
+               for u in _N for a in _N}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -160,13 +165,18 @@ def cpu_reference_run(cfg, sd, n_unet_steps, B, threads):
     return t_unet, t_dec, t_bp
 
 
-def cpu_samples_per_sec(cfg, sd, n_unet_steps, B, threads):
+REF_BATCH = 2      # samples per CPU step: one step = REF_BATCH samples through all 50 DDIM steps + decode + back-projection
+
+
+def cpu_step_seconds(cfg, sd, B, threads, n_unet_steps=DDIM_STEPS):
     t_unet, t_dec, t_bp = cpu_reference_run(cfg, sd, n_unet_steps, B, threads)
-    full = t_unet * (DDIM_STEPS / n_unet_steps) + t_dec + t_bp        # extrapolate the loop to 50 steps
-    return B / full, dict(t_unet_per_step=t_unet / n_unet_steps, t_decode=t_dec, t_backproject=t_bp)
+    return t_unet + t_dec + t_bp, dict(t_unet_per_step=t_unet / n_unet_steps, t_decode=t_dec, t_backproject=t_bp)
 
 
 def run_reference_arm(args):
+    """The reference algorithm on the host CPU (oracle port), every host thread.  One step = REF_BATCH samples through
+    the WHOLE path (all 50 DDIM steps, decode, back-projection): a bounded sample of the B = 64 workload (the metric is
+    per sample, and the CPU rate does not grow with the batch), timed as declared - no extrapolation."""
     rank, world, _ = dist_env()
     if rank != 0:
         return
@@ -175,28 +185,82 @@ def run_reference_arm(args):
     cfg = C.kitti_uncond()
     sd = random_state_dict(cfg, 0)
     threads = os.cpu_count() or 1
-    B, n_steps = 2, 10        # bounded sample: ~6 s of host work per repeat on 16 cores
-    vals = []
-    for i in range(args.warmup + args.steps):
-        if i >= min(args.warmup, 1) + args.steps and vals:      # bounded: the CPU arm is slow
-            break
-        v, detail = cpu_samples_per_sec(cfg, sd, n_steps, B, threads)
-        if i >= min(args.warmup, 1):
-            vals.append(v)
-        if len(vals) >= min(args.steps, 3):
-            break
-    v = float(np.mean(vals))
-    sample = (f"B={B}, {n_steps} of {DDIM_STEPS} DDIM steps timed and extrapolated x{DDIM_STEPS // n_steps}, "
-              f"full decode + back-projection; oracle port (torch fp32 CPU), {len(vals)} repeats")
+    B = REF_BATCH
+    warm = min(args.warmup, 1)
+    steps = max(1, min(args.steps, 3))        # ~20 s of host work per step on 16 cores
+    for _ in range(warm):
+        cpu_step_seconds(cfg, sd, B, threads, n_unet_steps=2)   # warm-up: page the weights in, size the thread pool
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _, detail = cpu_step_seconds(cfg, sd, B, threads)
+    sec = (time.perf_counter() - t0) / steps
+    v = B / sec
+    sample = (f"B={B} samples per step through all {DDIM_STEPS} DDIM steps + decode + back-projection (a bounded sample of the "
+              f"B={args.batch} workload: samples/s is per sample); oracle port (torch fp32 CPU), {steps} timed steps, "
+              f"per U-Net step {detail['t_unet_per_step']:.2f}s, decode {detail['t_decode']:.2f}s")
+    conf = workload_config(B, 1)
+    conf["sample_of"] = {"batch_per_gpu": args.batch, "n_gpus": args.gpus}
+    conf["parallelism"] = f"host CPU, {threads} threads (one process whatever --gpus says)"
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus,
-        "steps": len(vals), "warmup": min(args.warmup, 1), "ms_per_step": 1000.0 * B / v, "higher_is_better": True,
+        "steps": steps, "warmup": warm, "ms_per_step": 1000.0 * sec, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": workload_config(args.batch, 1),
+        "config": conf,
         "cpu_baseline": {"value": v, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ eager GPU baseline
+def gpu_eager_baseline(cfg, sd, B, dev, unet_steps=2):
+    """north_star target 1 ("reference-PyTorch-on-B200"): the reference algorithm as plain eager PyTorch on this GPU
+    (the oracle's torch restatement moved to cuda: cuDNN / cuBLAS kernels, the reference's own op sequence), outside the
+    timed region of the headline.  Bounded sample: `unet_steps` U-Net evaluations + DDIM updates and one decode at
+    batch B per numeric setting; samples/s = B / (50 * t_unet_step + t_decode)."""
+    from oracle import torch_ref as R
+    sdd = {k: v.to(dev) for k, v in sd.items()}
+    g = torch.Generator().manual_seed(1000)
+    x0 = torch.randn((B,) + tuple(cfg.latent_shape), generator=g).to(dev)
+    ts, table = R.ddim_schedule(cfg, DDIM_STEPS, 0.0)
+    n = len(ts)
+    out = {"batch": B, "sample": f"{unet_steps} U-Net evaluations + DDIM updates and one first-stage decode at B={B}, "
+                                 f"extrapolated to {DDIM_STEPS} steps; oracle/torch_ref.py on cuda (eager cuDNN/cuBLAS)", "unit": "samples/s"}
+
+    def one(name, tf32, autocast):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        ctx = torch.autocast("cuda", dtype=torch.bfloat16) if autocast else torch.autocast("cuda", enabled=False)
+        try:
+            with ctx, torch.no_grad():
+                def step(x, i):
+                    t = torch.full((B,), int(np.flip(ts)[i]), dtype=torch.long, device=dev)
+                    e = R.unet_forward(sdd, cfg.unet, x, t).float()
+                    return R.ddim_step(x, e, table[n - 1 - i])[0]
+                x = step(x0, 0)                     # warm-up (cuDNN autotune, allocator)
+                R.decode_first_stage(sdd, cfg, x0)
+                torch.cuda.synchronize()
+                a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                a.record()
+                x = x0
+                for i in range(unet_steps):
+                    x = step(x, i)
+                b.record()
+                R.decode_first_stage(sdd, cfg, x)
+                c.record()
+                torch.cuda.synchronize()
+            t_step, t_dec = a.elapsed_time(b) / unet_steps, b.elapsed_time(c)
+            out[name] = {"value": B / ((DDIM_STEPS * t_step + t_dec) / 1e3), "ms_per_unet_step": t_step, "decode_ms": t_dec}
+        except Exception as ex:                     # e.g. out of memory at a large batch: report, do not fail the bench
+            out[name] = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+        torch.cuda.empty_cache()
+
+    one("fp32", False, False)
+    one("tf32", True, False)
+    one("autocast_bf16", True, True)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = True
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -215,8 +279,9 @@ def run_gpu_arm(args):
     cfg = getattr(C, WORKLOADS[args.workload][0])()
     B = args.batch
     sd = random_state_dict(cfg, 0)
-    model = L.LatentDiffusion(cfg, device=dev, use_ema=False, precision=args.precision)
+    model = L.LatentDiffusion(cfg, device=dev, use_ema=False, precision=args.precision, ae_precision=args.ae_precision)
     model.load_state_dict(sd)
+    cfg = model.cfg
     sampler = L.DDIMSampler(model)
     sampler.make_schedule(DDIM_STEPS, ddim_eta=0.0)
     ts, table = sampler.ddim_timesteps, sampler.ddim_table
@@ -324,13 +389,63 @@ def run_gpu_arm(args):
             "whole_pipeline_frac_of_tensor_peak": value / world * WORKLOADS[args.workload][2] / 1e3 / peaks["bf16_tflops_sustained"],
         }
 
+    # strong scaling (BASELINE config 2 is a GLOBAL batch of 64 on 8 GPUs): the same global batch as one GPU's step, split
+    # over the ranks.  speedup_vs_n1 is against this run's own per-GPU rate (each rank's weak step IS the N = 1 workload).
+    strong = None
+    if world > 1 and B % world == 0:
+        Bs = B // world
+        xs_dev = parallel.local_slice(x_T_global[:B], rank, world).to(dev)
+        cs_kw = dict(context=parallel.local_slice(ctx_global[:B], rank, world).to(dev)) if cond is not None else {}
+
+        def strong_step():
+            z, _ = eng.ddim_sample(xs_dev, ts, table, **cs_kw)
+            img = eng.vq_decode(z)
+            xyz, mask = L.ops.backproject(img, ds.fov, ds.depth_range, ds.depth_scale, ds.log_scale)
+            return parallel.all_gather_batch(img, B), xyz, mask
+
+        for _ in range(2):
+            strong_step()
+        ms_s = timed(strong_step, args.steps)
+        sv = B * args.steps / (ms_s / 1000.0)
+        strong = {"global_batch": B, "batch_per_gpu": Bs, "value": sv, "unit": "samples/s", "ms_per_step": ms_s / args.steps,
+                  "speedup_vs_n1": sv / (value / world)}
+
+    # the other numeric modes, same step, fewer repeats (outside the headline's timed region)
+    modes = None
+    if rank == 0 and world == 1 and not args.no_modes and args.workload == "uncond":
+        modes = {}
+        for key, (pu, pa) in {"precise": ("fp32", "fp32"), "fp16": ("fp16", "fp16")}.items():
+            if (pu, pa) == (cfg.precision, cfg.ae_precision_resolved):
+                continue
+            m2 = L.LatentDiffusion(cfg, device=dev, use_ema=False, precision=pu, ae_precision=pa)
+            m2.load_state_dict(sd)
+            e2 = m2.engine
+
+            def mode_step():
+                z, _ = e2.ddim_sample(x_T_dev, ts, table, **cond_kw)
+                img = e2.vq_decode(z)
+                return L.ops.backproject(img, ds.fov, ds.depth_range, ds.depth_scale, ds.log_scale)
+
+            mode_step()
+            ms_m = timed(mode_step, 2)
+            modes[key] = {"value": B * 2 / (ms_m / 1000.0), "unit": "samples/s", "ms_per_step": ms_m / 2,
+                          "dtype": DTYPE_NAMES[(pu, pa)]}
+            del m2, e2
+            torch.cuda.empty_cache()
+
+    eager = None
+    if rank == 0 and world == 1 and not args.no_eager_baseline and args.workload == "uncond":
+        eager = gpu_eager_baseline(cfg, sd, B, dev)
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "uncond":
         threads = os.cpu_count() or 1
-        v, detail = cpu_samples_per_sec(cfg, sd, 10, 2, threads)
-        cpu = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
-               "sample": f"B=2, 10 of {DDIM_STEPS} DDIM steps timed and extrapolated x5, full decode + back-projection "
-                         f"(oracle port, torch fp32); per-step {detail['t_unet_per_step']:.2f}s decode {detail['t_decode']:.2f}s"}
+        sec, detail = cpu_step_seconds(cfg, sd, REF_BATCH, threads, n_unet_steps=10)
+        full = detail["t_unet_per_step"] * DDIM_STEPS + detail["t_decode"] + detail["t_backproject"]
+        cpu = {"value": REF_BATCH / full, "unit": "samples/s", "cores": threads, "kind": "port",
+               "sample": f"B={REF_BATCH}, 10 of {DDIM_STEPS} DDIM steps timed and extrapolated x5, full decode + back-projection "
+                         f"(oracle port, torch fp32); per-step {detail['t_unet_per_step']:.2f}s decode {detail['t_decode']:.2f}s "
+                         f"(`--impl reference` times all {DDIM_STEPS} steps)"}
 
     if rank == 0:
         h2d = x_T_host.numel() * 4
@@ -338,7 +453,7 @@ def run_gpu_arm(args):
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (3-way bf16 operand split, fp32 accumulate and residual stream)",
+            "vs_baseline": None, "dtype": DTYPE_NAMES[(cfg.precision, cfg.ae_precision_resolved)],
             "data": "synthetic",
             "config": workload_config(B, world, args.workload),
             "ms_per_unet_step": unet_ms,
@@ -348,6 +463,10 @@ def run_gpu_arm(args):
             "clocks": clk,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "gpu_eager_baseline": eager,
+            "precise": modes.get("precise") if modes else None,
+            "modes": modes,
+            "strong_scaling": strong,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -364,8 +483,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="uncond", choices=sorted(WORKLOADS),
                     help="uncond = the headline (BASELINE config 2); cam2lidar = BASELINE config 3(A), reported beside it")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
-                    help="bf16 = headline tensor-core path; fp32 = precise operand-split mode (parity mode)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "fp16"],
+                    help="U-Net numeric mode: bf16 = headline tensor-core path; fp32 = precise operand-split mode; fp16 = IEEE half")
+    ap.add_argument("--ae-precision", default=None, choices=["bf16", "fp32", "fp16"],
+                    help="first-stage numeric mode (default: fp16 under a bf16 U-Net, else the U-Net's)")
+    ap.add_argument("--no-modes", action="store_true", help="skip the precise / fp16 mode timings")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the eager-PyTorch-on-GPU baseline")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

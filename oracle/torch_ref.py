@@ -111,7 +111,7 @@ def circular_conv2d(x, w, b, pad=None, stride=1):
 def timestep_embedding(timesteps, dim, max_period=10000):
     """lidm/modules/basic.py:278-296 (cos first, then sin)."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32, device=timesteps.device) / half)
     args = timesteps[:, None].float() * freqs[None]
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 
@@ -391,10 +391,10 @@ def ddim_step(x, e_t, coef, noise=None, temperature=1.0, quantize=None):
     coef = (a_t, a_prev, sigma_t, sqrt_one_minus_at) float32 scalars.  quantize: optional callable applied to pred_x0
     (quantize_denoised, ddim.py:198-199)."""
     b = x.shape[0]
-    a_t = torch.full((b, 1, 1, 1), float(coef[0]))
-    a_prev = torch.full((b, 1, 1, 1), float(coef[1]))
-    sigma_t = torch.full((b, 1, 1, 1), float(coef[2]))
-    sqrt_one_minus_at = torch.full((b, 1, 1, 1), float(coef[3]))
+    a_t = torch.full((b, 1, 1, 1), float(coef[0]), device=x.device)
+    a_prev = torch.full((b, 1, 1, 1), float(coef[1]), device=x.device)
+    sigma_t = torch.full((b, 1, 1, 1), float(coef[2]), device=x.device)
+    sqrt_one_minus_at = torch.full((b, 1, 1, 1), float(coef[3]), device=x.device)
     pred_x0 = (x - sqrt_one_minus_at * e_t) / a_t.sqrt()
     if quantize is not None:
         pred_x0 = quantize(pred_x0)
