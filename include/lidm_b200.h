@@ -72,6 +72,14 @@ typedef struct lidm_config {
    * benchmarked mix is precision = BF16, ae_precision = FP16 + 1: the decoder's bf16 rounding alone exceeds the 1e-2
    * final-image budget, IEEE half meets it at the same speed. */
   int32_t ae_precision;
+  /* denoiser family: 0 = openaimodel.UNetModel (the fields above); 1 = LayoutDiffusionUNetModel
+   * (lidm/modules/unets/object_cross_unet.py:632-952, conditioning_key 'layout_crossattn'): FiLM scale-shift ResBlocks,
+   * ResBlock up/down-sampling, zero-padded 3x3 convs, ObjectAwareCrossAttention at the `attention_resolutions`
+   * (= attention_ds) downsampling rates with num_head_channels = 64.  encoder_channels = hidden width of the layout
+   * encoder (channels of xf_out / obj_*_embedding); conditioning arrives through lidm_layout_set_cond. */
+  int32_t unet_type;
+  int32_t encoder_channels;
+  int32_t num_attention_blocks;             /* 0 => 1 */
 } lidm_config;
 
 /* Last error message for `h` (or, with h == NULL, for the calling thread's last failed lidm_create / stateless call). */
@@ -102,6 +110,20 @@ int lidm_unet_forward(lidm_handle* h, const float* x, const int64_t* t, float* e
  * Pass NULL / 0 for the conditioning the model does not take; a mismatch is LIDM_ERR_INVALID. */
 int lidm_unet_forward_cond(lidm_handle* h, const float* x, const int64_t* t, const float* c_concat, const float* context,
                            int32_t ctx_len, float* eps_out, int32_t B, void* stream);
+
+/* Conditioning of the layout U-Net: the output dict of LayoutTransformerEncoder.forward
+ * (lidm/modules/encoders/layout_encoder.py:222-281) exactly as LatentDiffusion.apply_model hands it to
+ * DiffusionWrapper.forward (ddpm.py:2334-2335, `layout_outputs=kwargs`), all DEVICE fp32:
+ *   xf_proj (B, 4*model_channels); xf_out, obj_class_embedding, obj_bbox_embedding (B, encoder_channels, n_layout);
+ *   for each attention resolution r = res_rows[i]: image_patch_bbox_embedding_for_resolution{r} = patch_emb[i],
+ *   (patch_batch[i], encoder_channels, L1_r) with patch_batch[i] = B, or 1 when every sample holds the same rows (the
+ *   reference encoder repeat_interleaves one tensor, layout_encoder.py:251-257).
+ * Everything that depends on the conditioning only (positional projections + GroupNorm32 of image patches and layout
+ * boxes, the layout tokens' keys and values; object_cross_unet.py:462-520) is computed here once and reused by every
+ * lidm_unet_forward / lidm_ddim_sample call at this batch size until the next lidm_layout_set_cond. */
+int lidm_layout_set_cond(lidm_handle* h, int32_t B, int32_t n_layout, const float* xf_proj, const float* xf_out,
+                         const float* obj_class_embedding, const float* obj_bbox_embedding, int32_t n_res,
+                         const int32_t* res_rows, const float* const* patch_emb, const int32_t* patch_batch, void* stream);
 
 /* DDIMSampler.p_sample_ddim update arithmetic (lidm/models/diffusion/ddim.py:191-206), stateless:
  * pred_x0 = (x - sqrt(1-a_t) eps)/sqrt(a_t); x_prev = sqrt(a_prev) pred_x0 + sqrt(1-a_prev-sigma^2) eps + sigma noise T.

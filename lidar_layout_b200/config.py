@@ -31,6 +31,12 @@ class UNetConfig:
     resblock_updown: bool = False
     conv_resample: bool = True
     dropout: float = 0.0
+    # "openai" = lidm.modules.diffusion.openaimodel.UNetModel; "layout" = LayoutDiffusionUNetModel
+    # (lidm/modules/unets/object_cross_unet.py:632-952): attention_resolutions holds its attention_ds, encoder_channels the
+    # layout encoder's hidden width, use_scale_shift_norm / resblock_updown are True as shipped
+    unet_type: str = "openai"
+    encoder_channels: int = 0
+    num_attention_blocks: int = 1
 
     @property
     def time_embed_dim(self) -> int:
@@ -119,9 +125,22 @@ def from_reference_dict(cfg: dict) -> LidmConfig:
         raise ValueError(f"unsupported model target {target!r}: only LatentDiffusion is on the B200 path")
     p = model["params"]
     unet_p = p["unet_config"]["params"]
-    if not p["unet_config"]["target"].endswith("openaimodel.UNetModel"):
-        raise ValueError("unsupported unet target " + p["unet_config"]["target"])
-    unet = UNetConfig(**_pick(UNetConfig, unet_p))
+    utarget = p["unet_config"]["target"]
+    if utarget.endswith("object_cross_unet.LayoutDiffusionUNetModel"):
+        if unet_p.get("attention_block_type", "GLIDE") != "ObjectAwareCrossAttention":
+            raise ValueError("LayoutDiffusionUNetModel: only attention_block_type 'ObjectAwareCrossAttention' is supported")
+        for k, want in (("use_positional_embedding_for_attention", True), ("use_key_padding_mask", False),
+                        ("norm_first", False), ("norm_for_obj_embedding", False),
+                        ("channels_scale_for_positional_embedding", 1.0)):
+            if unet_p.get(k, want) != want:
+                raise ValueError(f"LayoutDiffusionUNetModel: {k}={unet_p[k]!r} is not supported (shipped value: {want!r})")
+        kw_u = _pick(UNetConfig, unet_p)
+        kw_u.update(unet_type="layout", attention_resolutions=_tup(unet_p["attention_ds"]), lib_name="ldm")
+        unet = UNetConfig(**kw_u)
+    elif utarget.endswith("openaimodel.UNetModel"):
+        unet = UNetConfig(**_pick(UNetConfig, unet_p))
+    else:
+        raise ValueError("unsupported unet target " + utarget)
     fs = p["first_stage_config"]
     if not fs["target"].endswith("VQModelInterface"):
         raise ValueError("unsupported first stage target " + fs["target"])
@@ -173,6 +192,27 @@ def kitti_sem2lidar() -> LidmConfig:
     """Concat-conditioned KITTI-360 LiDM (reference models/lidm/kitti/sem2lidar/config.yaml): the 8-channel
     rescaled semantic map is concatenated to the latent, U-Net in_channels 16."""
     return LidmConfig(conditioning_key="concat", unet=UNetConfig(in_channels=16))
+
+
+def nuscenes_layout2lidar() -> LidmConfig:
+    """Layout-conditioned nuScenes LiDM (reference models/lidm/nuscenes/layout2lidar/config.yaml): 32-beam range images
+    (32x1024 -> 8x128 latents), LayoutDiffusionUNetModel with ObjectAwareCrossAttention at ds 2 and 4, 13 layout tokens."""
+    return LidmConfig(conditioning_key="layout_crossattn", linear_end=0.0205, image_size=(8, 128),
+                      unet=UNetConfig(image_size=(8, 128), unet_type="layout", model_channels=256, encoder_channels=256,
+                                      num_head_channels=64, attention_resolutions=(8, 4, 2), channel_mult=(1, 2, 4),
+                                      num_res_blocks=2, use_scale_shift_norm=True, resblock_updown=True, lib_name="ldm"),
+                      dataset=DatasetConfig(size=(32, 1024), fov=(10.0, -30.0)))
+
+
+def tiny_layout() -> LidmConfig:
+    """The layout2lidar structure at a small width (same three resolutions 8x128 / 4x64 / 2x32, attention at ds 2 and 4,
+    13 layout tokens) with the small first stage of `tiny`: for fast tests."""
+    return LidmConfig(conditioning_key="layout_crossattn", linear_end=0.0205, image_size=(8, 128),
+                      unet=UNetConfig(image_size=(8, 128), unet_type="layout", model_channels=64, encoder_channels=64,
+                                      num_head_channels=64, attention_resolutions=(4, 2), channel_mult=(1, 2, 4),
+                                      num_res_blocks=1, use_scale_shift_norm=True, resblock_updown=True, lib_name="ldm"),
+                      ae=AEConfig(n_embed=512, ch=64, ch_mult=(1, 2, 2), strides=((1, 2), (2, 2)), num_res_blocks=1),
+                      dataset=DatasetConfig(size=(16, 512), fov=(10.0, -30.0)))
 
 
 def kitti_uncond() -> LidmConfig:

@@ -72,7 +72,7 @@ struct View {
 };
 
 // ---- TMA maps (cuTensorMapEncodeTiled through the runtime's driver entry point; no -lcuda link) -------
-CUtensorMap make_tma_act(const View& v, int box_c, int box_w, int box_h, int swizzle_bytes);
+CUtensorMap make_tma_act(const View& v, int box_c, int box_w, int box_h, int swizzle_bytes, int box_b = 1);
 CUtensorMap make_tma_3d(const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                         uint64_t stride2_bytes, uint32_t b0, uint32_t b1, int swizzle_bytes);
 
@@ -82,6 +82,9 @@ struct ConvTaps {
   int8_t dx[9] = {0};
   int8_t dy[9] = {0};
   int cstep = 0;   // channels between consecutive taps inside an im2col'd operand (0 => taps are spatial shifts)
+  // zero padding on W as well as H (plain nn.Conv2d(padding=1) of the layout U-Net, object_cross_unet.py): the operand is
+  // a halo-free tensor and every out-of-range column comes from TMA's out-of-bounds zero fill
+  bool zero_w = false;
 };
 
 // fp32 channels-last tensor (no halo): the residual stream of the precise mode
@@ -142,12 +145,14 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wt, int 
 bool conv_gemm_emits_gstats(const GemmEpilogue& ep, int n_alloc);
 
 // ---- normalisation (norm.cu) -----------------------------------------------------------------------------
+// film (optional): per-sample FiLM rows [B][film_ld] = [scale (C) | shift (C)]: y = norm(x) * (1 + scale) + shift, then SiLU
 void launch_groupnorm(const View& x, const View& y, const float* gamma, const float* beta, float eps, int groups,
-                      bool silu, float* partials /* workspace >= B*groups*2*GN_MAX_CHUNKS floats */, cudaStream_t s);
+                      bool silu, float* partials /* workspace >= B*groups*2*GN_MAX_CHUNKS floats */, cudaStream_t s,
+                      const float* film = nullptr, int film_ld = 0);
 constexpr int GN_MAX_CHUNKS = 64;
 // same, with the statistics taken from x.gst (written by the producing GEMMs' epilogues): one pass over x
 void launch_groupnorm_from_gstats(const View& x, const View& y, const float* gamma, const float* beta, float eps, int groups,
-                                  bool silu, cudaStream_t s);
+                                  bool silu, cudaStream_t s, const float* film = nullptr, int film_ld = 0);
 
 // ---- attention (attention.cu) ----------------------------------------------------------------------------
 // qkv: (B, T, 3C) bf16 = [q | k | v] (plain qkv GEMM output); V consumed as an MN-major tcgen05 operand
@@ -157,6 +162,22 @@ void launch_attention_d32_packed(const bf16* qkv, const View& out, int B, int T,
 // (B, L, kv_ld) at columns k_col / v_col; out (B,T,C) view.  Any L >= 1 (ragged last tile is masked).
 void launch_cross_attention_d32(const bf16* q, int q_ld, const bf16* kv, int kv_ld, int k_col, int v_col, int L,
                                 const View& out, int B, int T, int heads, cudaStream_t s);
+
+// ---- layout-conditioned denoiser (layout.cu) --------------------------------------------------------------------
+// ObjectAwareCrossAttention core (object_cross_unet.py:447-565): qkv (B,T,3C) = [q | k | v] with the 128^-1/4 scale folded
+// into q and k; pos (pos_batch,T,C) positional half of queries / image keys (pre-scaled); klay (B,16,2C) layout keys
+// [content | positional]; vlay (B,16,C); out (B,T,C).  Head width 64 (+64 positional).  T in {64, 128, 256}.
+void launch_oaca_attention(const bf16* qkv, const bf16* pos, int pos_batch, const bf16* klay, const bf16* vlay, int n_layout,
+                           const View& out, int B, int T, int C, cudaStream_t s);
+// dst[(b*rows + l)*dst_ld + dst_col + c] = scale * GroupNorm32(bias[c] + W[c,:] . src[b,:,l])   (src fp32 (Bsrc,E,Lt))
+void launch_oaca_pos(const float* src, int Bsrc, int E, int Lt, const float* W, const float* bias, const float* gamma,
+                     const float* beta, int C, float scale, bf16* dst, int rows, int dst_ld, int dst_col, bool f16,
+                     cudaStream_t s);
+// layout tokens' keys (scaled) and values from xf_out and the class embedding (both fp32 (B,E,Lt)), 16 slots per sample
+void launch_oaca_layout_kv(const float* xf_out, const float* cls, int B, int E, int Lt, const float* gamma, const float* beta,
+                           const float* Wc, const float* bc, int C, float scale, bf16* klay, bf16* vlay, bool f16,
+                           cudaStream_t s);
+void launch_avgpool2(const View& x, const View& y, cudaStream_t s);
 
 // ---- transformer pieces (transformer.cu) -------------------------------------------------------------------
 // nn.LayerNorm over the channel dimension of every pixel/token (eps 1e-5), bf16 in / bf16 out, fp32 statistics
@@ -184,7 +205,7 @@ void launch_backproject(const float* img, int B, int H, int W, float fov_up_deg,
                         float dmax, float depth_scale, int log_scale, int input_is_unit, float* xyz, uint8_t* mask,
                         cudaStream_t s);
 void launch_im2col_nchw_f32(const float* x, int B, int C, int H, int W, int kh, int kw, int pl, int pt, bf16* out,
-                            int kpad, cudaStream_t s, bool f16 = false);
+                            int kpad, cudaStream_t s, bool f16 = false, bool zero_w = false);
 // stride = vertical stride; stride_w = horizontal stride (0 => same as stride)
 void launch_im2col_nhwc(const View& x, int kh, int kw, int stride, int pl, int pt, int Ho, int Wo, bf16* out,
                         cudaStream_t s, int stride_w = 0);
@@ -198,7 +219,8 @@ void launch_vq(const float* z, int B, int C, int HW, const float* codebook, cons
 void launch_codebook_norm(const float* codebook, int n_embed, int dim, float* out, cudaStream_t s);
 void launch_time_embed(const int64_t* t_dev, int nt, int model_ch, const float* w0, const float* b0, const float* w2,
                        const float* b2, int ted, float* tmp /* nt*ted */, float* emb_silu /* nt*ted */,
-                       cudaStream_t s);
+                       cudaStream_t s, int t_stride = 1 /* 0: one timestep for every row */,
+                       const float* rowbias = nullptr /* [nt][ted] added to emb before the SiLU (layout encoder xf_proj) */);
 void launch_linear_rows(const float* x, int nt, int K, const float* w, const float* b, int N, float* out,
                         cudaStream_t s);
 void launch_pack_conv_weight(const float* w, int cout, int cin, int kh, int kw, int n_alloc, int k_alloc,

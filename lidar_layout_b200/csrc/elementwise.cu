@@ -121,7 +121,7 @@ __global__ void backproject_kernel(const float* __restrict__ img, int H, int W, 
 // ------------------------------------------------------------------------------------------ im2col (8-channel fp32 NCHW input)
 // out[(b*H*W + h*W + w) * kpad + (ky*kw + kx)*C + c] = x[b][c][h+ky-pt][(w+kx-pl) mod W]  (0 outside H)
 __global__ void im2col_nchw_f32_kernel(const float* __restrict__ x, int B, int C, int H, int W, int kh, int kw, int pl,
-                                       int pt, bf16* __restrict__ out, int kpad, bool f16) {
+                                       int pt, bf16* __restrict__ out, int kpad, bool f16, bool zero_w) {
   // one thread = 8 consecutive k of one pixel (a 16-byte store); kpad is a multiple of 8
   const int kv = kpad >> 3;
   const int64_t total = (int64_t)B * H * W * kv;
@@ -142,8 +142,9 @@ __global__ void im2col_nchw_f32_kernel(const float* __restrict__ x, int B, int C
         const int ky = tap / kw, kx = tap - ky * kw;
         const int hs = h + ky - pt;
         int ws = w + kx - pl;
+        const bool inside = ws >= 0 && ws < W;
         ws = ws < 0 ? ws + W : (ws >= W ? ws - W : ws);
-        if (hs >= 0 && hs < H) v[j] = __ldg(x + (((size_t)b * C + c) * H + hs) * W + ws);
+        if (hs >= 0 && hs < H && (inside || !zero_w)) v[j] = __ldg(x + (((size_t)b * C + c) * H + hs) * W + ws);
       }
     }
     uint4 o;
@@ -341,12 +342,12 @@ __global__ void vq_kernel(const float* __restrict__ z, int C, int HW, int64_t np
 
 // ------------------------------------------------------------------------------------------ timestep embedding MLP
 // tmp[r][j] = SiLU(b0[j] + sum_i w0[j][i] * temb(t_r)[i]),  temb = [cos(t f_i) | sin(t f_i)], f_i = exp(-ln(1e4) i / half)
-__global__ void time_embed_l0_kernel(const int64_t* __restrict__ t, int model_ch, const float* __restrict__ w0,
+__global__ void time_embed_l0_kernel(const int64_t* __restrict__ t, int t_stride, int model_ch, const float* __restrict__ w0,
                                      const float* __restrict__ b0, int ted, float* __restrict__ tmp) {
   extern __shared__ float te[];
   const int r = blockIdx.y;
   const int half = model_ch / 2;
-  const float tv = (float)t[r];
+  const float tv = (float)t[(size_t)r * t_stride];
   for (int i = threadIdx.x; i < half; i += blockDim.x) {
     const float f = expf(-logf(10000.f) * (float)i / (float)half);
     const float a = tv * f;
@@ -364,7 +365,8 @@ __global__ void time_embed_l0_kernel(const int64_t* __restrict__ t, int model_ch
 
 // out[r][n] = act(b[n] + sum_k w[n][k] x[r][k]); one warp per output n, loops over rows r.
 __global__ void linear_rows_kernel(const float* __restrict__ x, int nt, int K, const float* __restrict__ w,
-                                   const float* __restrict__ bvec, int N, float* __restrict__ out, int silu) {
+                                   const float* __restrict__ bvec, int N, float* __restrict__ out, int silu,
+                                   const float* __restrict__ rowbias) {
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (n >= N) return;
@@ -376,6 +378,7 @@ __global__ void linear_rows_kernel(const float* __restrict__ x, int nt, int K, c
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) {
       acc += bvec[n];
+      if (rowbias != nullptr) acc += rowbias[(size_t)r * N + n];
       out[(size_t)r * N + n] = silu ? acc / (1.f + expf(-acc)) : acc;
     }
   }
@@ -503,10 +506,10 @@ void launch_backproject(const float* img, int B, int H, int W, float fov_up_deg,
 }
 
 void launch_im2col_nchw_f32(const float* x, int B, int C, int H, int W, int kh, int kw, int pl, int pt, bf16* out,
-                            int kpad, cudaStream_t s, bool f16) {
+                            int kpad, cudaStream_t s, bool f16, bool zero_w) {
   LIDM_REQUIRE(kh * kw * C <= kpad && kpad % 8 == 0 && pl < W && kw - 1 - pl < W, "im2col: kpad too small / not a multiple of 8");
   const int64_t total = (int64_t)B * H * W * (kpad / 8);
-  im2col_nchw_f32_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, B, C, H, W, kh, kw, pl, pt, out, kpad, f16);
+  im2col_nchw_f32_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, B, C, H, W, kh, kw, pl, pt, out, kpad, f16, zero_w);
   LIDM_CUDA_CHECK(cudaGetLastError());
   LIDM_COUNT_LAUNCH(1);
 }
@@ -574,19 +577,21 @@ void launch_vq(const float* z, int B, int C, int HW, const float* codebook, cons
 }
 
 void launch_time_embed(const int64_t* t_dev, int nt, int model_ch, const float* w0, const float* b0, const float* w2,
-                       const float* b2, int ted, float* tmp, float* emb_silu, cudaStream_t s) {
+                       const float* b2, int ted, float* tmp, float* emb_silu, cudaStream_t s, int t_stride,
+                       const float* rowbias) {
   dim3 g0(cdiv(ted, 128), nt);
-  time_embed_l0_kernel<<<g0, 128, model_ch * sizeof(float), s>>>(t_dev, model_ch, w0, b0, ted, tmp);
+  time_embed_l0_kernel<<<g0, 128, model_ch * sizeof(float), s>>>(t_dev, t_stride, model_ch, w0, b0, ted, tmp);
   LIDM_CUDA_CHECK(cudaGetLastError());
-  // emb = Linear(tmp); every consumer applies SiLU first (openaimodel.py:222-223) so store SiLU(emb)
-  linear_rows_kernel<<<cdiv(ted, 8), 256, 0, s>>>(tmp, nt, ted, w2, b2, ted, emb_silu, 1);
+  // emb = Linear(tmp) (+ the layout encoder's xf_proj row); every consumer applies SiLU first (openaimodel.py:222-223)
+  // so store SiLU(emb)
+  linear_rows_kernel<<<cdiv(ted, 8), 256, 0, s>>>(tmp, nt, ted, w2, b2, ted, emb_silu, 1, rowbias);
   LIDM_CUDA_CHECK(cudaGetLastError());
   LIDM_COUNT_LAUNCH(1);
 }
 
 void launch_linear_rows(const float* x, int nt, int K, const float* w, const float* b, int N, float* out,
                         cudaStream_t s) {
-  linear_rows_kernel<<<cdiv(N, 8), 256, 0, s>>>(x, nt, K, w, b, N, out, 0);
+  linear_rows_kernel<<<cdiv(N, 8), 256, 0, s>>>(x, nt, K, w, b, N, out, 0, nullptr);
   LIDM_CUDA_CHECK(cudaGetLastError());
   LIDM_COUNT_LAUNCH(1);
 }

@@ -109,7 +109,12 @@ struct ConvW {
   bool f16 = false;   // packed as IEEE half instead of bf16
 };
 struct NormW { float* gamma = nullptr; float* beta = nullptr; int C = 0; };
-struct ResW { NormW n1, n2; ConvW c1, c2, skip; ConvW c2s; /* conv2 with the 1x1 skip appended along K */ bool has_skip = false; int emb_off = -1; int cin = 0, cout = 0; };
+struct ResW {
+  NormW n1, n2; ConvW c1, c2, skip; ConvW c2s; /* conv2 with the 1x1 skip appended along K */ bool has_skip = false; int emb_off = -1; int cin = 0, cout = 0;
+  // layout U-Net (object_cross_unet.py:253-283): FiLM scale-shift conditioning (emb_layers gives 2*cout values) and
+  // ResBlock up- (1) / down- (2) sampling of both h and x
+  bool film = false; int updown = 0;
+};
 struct AttnW { NormW n; ConvW qkv, proj; int ch = 0, heads = 0; };
 // BasicTransformerBlock / SpatialTransformer weights (reference lidm/modules/attention.py:196-261)
 struct STBlockW {
@@ -120,9 +125,19 @@ struct STBlockW {
   int kv_col = 0;             // column of this block's K rows inside the context K/V matrix (V at kv_col + C)
 };
 struct STW { NormW n; ConvW proj_in, proj_out; std::vector<STBlockW> blocks; int ch = 0, heads = 0; };
+// ObjectAwareCrossAttention (object_cross_unet.py:380-565): qkv rows with 128^-1/4 folded into q and k; the positional /
+// layout-content projectors stay fp32 (they run once per conditioning, lidm_layout_set_cond, into the buffers below)
+struct OacaW {
+  NormW n_qkv, n_img_pos, n_lay_pos, n_cls;
+  ConvW qkv, proj;
+  float *w_pos = nullptr, *b_pos = nullptr, *w_content = nullptr, *b_content = nullptr;
+  int ch = 0, heads = 0, rows = 0;    // rows: feature-map rows of this block = key of image_patch_bbox_embedding_for_resolution{rows}
+  bf16 *pos_img = nullptr, *klay = nullptr, *vlay = nullptr;    // conditioning buffers: (pos_batch,T,C), (B,16,2C), (B,16,C)
+  int pos_batch = 0;
+};
 struct Layer {
-  enum Kind { CONV, RES, ATTN, DOWN, UP, ST } kind;
-  ResW r; AttnW a; ConvW c; STW st;
+  enum Kind { CONV, RES, ATTN, DOWN, UP, ST, OACA } kind;
+  ResW r; AttnW a; ConvW c; STW st; OacaW oa;
   ConvW cpar[4];   // UP: the 3x3 conv after nearest x2, folded into one 2x2 conv per output parity (py * 2 + px)
   int cin = 0, cout = 0;
 };
@@ -158,6 +173,7 @@ struct Plan {
   float* out = nullptr;             // eps_out / img_out
   int32_t* idx_out = nullptr;
   int quantize = 1;
+  int64_t cond_gen = 0;             // generation of the layout conditioning buffers the ops read (lidm_layout_set_cond)
   const float* rowadd_base = nullptr;
   int rowadd_ld = 0;
   const float* ddim_noise = nullptr;
@@ -174,7 +190,8 @@ struct Plan {
   bool warmed = false;              // ran eagerly at least once (lazy one-time kernel attribute setup happens there)
   std::vector<const void*> io_key() const {
     return {x, xin, context, out, idx_out, rowadd_base, reinterpret_cast<const void*>((intptr_t)rowadd_ld), ddim_noise,
-            ddim_x_prev, ddim_pred_x0, ddim_coef, reinterpret_cast<const void*>((intptr_t)quantize)};
+            ddim_x_prev, ddim_pred_x0, ddim_coef, reinterpret_cast<const void*>((intptr_t)quantize),
+            reinterpret_cast<const void*>((intptr_t)cond_gen)};
   }
   ~Plan() {
     for (auto& g : gslot) if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -193,6 +210,12 @@ struct lidm_handle {
   std::string error;
   bool finalized = false;
   int unet_prec = LIDM_PREC_BF16, ae_prec = LIDM_PREC_BF16;   // numeric mode of the U-Net / of the first stage
+  // layout-conditioned U-Net: conditioning state written by lidm_layout_set_cond
+  bool is_layout = false;
+  int cond_B = 0, cond_n_layout = 0;
+  int64_t cond_gen = 0;                                   // bumps whenever the conditioning buffers move (CUDA-graph key)
+  float* cond_xf_proj = nullptr;                          // (cond_B, ted)
+  std::vector<void*> cond_owned;
   std::unordered_map<std::string, DevTensor> raw;     // fp32 state-dict tensors on the device
   std::vector<void*> owned;                           // packed weight allocations
   // U-Net
@@ -242,6 +265,8 @@ struct lidm_handle {
   ~lidm_handle() {
     for (auto& kv : raw) cudaFree(kv.second.p);
     for (void* p : owned) cudaFree(p);
+    for (void* p : cond_owned) cudaFree(p);
+    cudaFree(cond_xf_proj);
     cudaFree(te_tmp); cudaFree(te_emb); cudaFree(emb_out); cudaFree(t_dev); cudaFree(coef_dev);
     cudaFree(xa); cudaFree(xb); cudaFree(xcat); cudaFree(ctx2); cudaFree(eps2);
     cudaFree(emb_cur); cudaFree(coef_cur); cudaFree(noise_cur); cudaFree(pred_scratch);
@@ -680,17 +705,123 @@ struct Builder {
     gemm(u, taps_rect(3, 3, 1, 1), c, ep);
     release(bu);
   }
-  void groupnorm(const View& x, const View& y, const NormW& n, float eps, bool silu) {
+  // film_off >= 0: FiLM rows (scale | shift) of this block inside the per-sample emb_layers output (Plan::rowadd_base)
+  void groupnorm(const View& x, const View& y, const NormW& n, float eps, bool silu, int film_off = -1) {
     Plan* P_ = P;
     const std::string label = "gn C" + std::to_string(x.C) + " @" + std::to_string(x.H) + "x" + std::to_string(x.W);
     if (x.C % 32 == 0 && (x.C / 32) % 8 == 0 && x.hl == 0 && x.hr == 0 && gst_covered(x)) {
       // every producer of x left its granule statistics behind: one pass (read x, write y)
-      op([=](cudaStream_t s) { launch_groupnorm_from_gstats(x, y, n.gamma, n.beta, eps, 32, silu, s); }, PROF_NORM, 0,
-         4.0 * x.B * x.H * x.W * x.C, label);
+      op([=](cudaStream_t s) {
+        launch_groupnorm_from_gstats(x, y, n.gamma, n.beta, eps, 32, silu, s,
+                                     film_off >= 0 ? P_->rowadd_base + film_off : nullptr, P_->rowadd_ld);
+      }, PROF_NORM, 0, 4.0 * x.B * x.H * x.W * x.C, label);
       return;
     }
-    op([=](cudaStream_t s) { launch_groupnorm(x, y, n.gamma, n.beta, eps, 32, silu, P_->gn_partials, s); }, PROF_NORM, 0,
-       4.0 * x.B * x.H * x.W * x.C, label);
+    op([=](cudaStream_t s) {
+      launch_groupnorm(x, y, n.gamma, n.beta, eps, 32, silu, P_->gn_partials, s,
+                       film_off >= 0 ? P_->rowadd_base + film_off : nullptr, P_->rowadd_ld);
+    }, PROF_NORM, 0, 4.0 * x.B * x.H * x.W * x.C, label);
+  }
+
+  static ConvTaps taps_zero3x3() { ConvTaps t = taps_rect(3, 3, 1, 1); t.zero_w = true; return t; }
+
+  // ResBlock.forward of the layout U-Net (object_cross_unet.py:253-283): GN32 -> SiLU -> [nearest x2 | 2x2 average of h
+  // AND x] -> zero-padded conv3x3 -> GN32 * (1 + scale) + shift -> SiLU -> zero-padded conv3x3 -> + skip(x)
+  void res_block_film(const ResW& r, const View& x, const View& dst) {
+    const int B = x.B, H = x.H, W = x.W;
+    const int Ho = r.updown == 1 ? 2 * H : (r.updown == 2 ? H / 2 : H), Wo = r.updown == 1 ? 2 * W : (r.updown == 2 ? W / 2 : W);
+    Buf bg1, bg1r, bxr, bh, bg2;
+    View g1 = act(B, H, W, r.cin, 0, 0, &bg1);
+    groupnorm(x, g1, r.n1, 1e-5f, true);
+    View a1 = g1, xr = x;
+    if (r.updown) {
+      a1 = act(B, Ho, Wo, r.cin, 0, 0, &bg1r);
+      xr = act(B, Ho, Wo, r.cin, 0, 0, &bxr);
+      if (r.updown == 1) {
+        op([=](cudaStream_t s) { launch_upsample_nearest2x(g1, a1, s); });
+        op([=](cudaStream_t s) { launch_upsample_nearest2x(x, xr, s); });
+      } else {
+        op([=](cudaStream_t s) { launch_avgpool2(g1, a1, s); });
+        op([=](cudaStream_t s) { launch_avgpool2(x, xr, s); });
+      }
+      release(bg1);
+    }
+    View hmid = act(B, Ho, Wo, r.cout, 0, 0, &bh);
+    {
+      GemmEpilogue ep;
+      ep.bias = r.c1.bias;
+      ep.out = hmid;
+      gemm(a1, taps_zero3x3(), r.c1, ep);
+    }
+    release(r.updown ? bg1r : bg1);
+    View g2 = act(B, Ho, Wo, r.cout, 0, 0, &bg2);
+    groupnorm(hmid, g2, r.n2, 1e-5f, true, r.film ? r.emb_off : -1);
+    release(bh);
+    if (r.has_skip && r.c2s.w != nullptr && xr.wpitch == 0) {
+      GemmEpilogue ep;                   // conv2(h) + skip(x) as one GEMM (x rides along as one more K segment)
+      ep.bias = r.c2s.bias;
+      ep.a2 = xr;
+      ep.out = dst;
+      prep_gst(ep, r.cout, r.c2s.n_alloc);
+      const GemmB b = gb(r.c2s);
+      const ConvTaps taps = taps_zero3x3();
+      const int N = r.cout;
+      op([=](cudaStream_t s) { launch_conv_gemm(g2, taps, b, N, ep, s); }, PROF_GEMM,
+         gemm_flops(g2, taps.n, N) + gemm_flops(xr, 1, N), 0, gemm_label(g2, taps.n, N) + " +skip" + std::to_string(r.cin));
+    } else {
+      View resid = xr;
+      Buf bsk;
+      if (r.has_skip) {
+        View sk = act(B, Ho, Wo, r.cout, 0, 0, &bsk);
+        GemmEpilogue ep;
+        ep.bias = r.skip.bias;
+        ep.out = sk;
+        gemm(xr, taps_1x1(), r.skip, ep);
+        resid = sk;
+      }
+      GemmEpilogue ep;
+      ep.bias = r.c2.bias;
+      ep.residual = resid;
+      ep.out = dst;
+      gemm(g2, taps_zero3x3(), r.c2, ep);
+      if (r.has_skip) release(bsk);
+    }
+    release(bg2);
+    if (r.updown) release(bxr);
+  }
+
+  // ObjectAwareCrossAttention.forward (object_cross_unet.py:447-565): GN32 -> qkv 1x1 -> attention over image + layout
+  // keys (conditioning-only operands come from the buffers lidm_layout_set_cond filled) -> proj_out + x
+  void oaca_block(const OacaW* w, const View& x, const View& dst) {
+    const int B = x.B, H = x.H, W = x.W, C = w->ch, T = H * W;
+    Buf bg, bqkv, bao;
+    View g = act(B, H, W, C, 0, 0, &bg);
+    groupnorm(x, g, w->n_qkv, 1e-5f, false);
+    View qkv = act(B, H, W, 3 * C, 0, 0, &bqkv);
+    {
+      GemmEpilogue ep;
+      ep.bias = w->qkv.bias;
+      ep.out = qkv;
+      ep.out.gst = nullptr;
+      gemm(g, taps_1x1(), w->qkv, ep);
+    }
+    release(bg);
+    View ao = act(B, H, W, C, 0, 0, &bao);
+    lidm_handle* h_ = h;
+    op([=](cudaStream_t s) {
+      if (w->pos_img == nullptr || h_->cond_B != B)
+        throw Error(LIDM_ERR_STATE, "layout conditioning missing for this batch size: call lidm_layout_set_cond first");
+      launch_oaca_attention(qkv.p, w->pos_img, w->pos_batch, w->klay, w->vlay, h_->cond_n_layout, ao, B, T, C, s);
+    }, PROF_ATTN, 2.0 * B * (double)T * (T + 13) * (3 * C), 0, "oaca T" + std::to_string(T) + " C" + std::to_string(C));
+    release(bqkv);
+    {
+      GemmEpilogue ep;
+      ep.bias = w->proj.bias;
+      ep.residual = x;
+      ep.out = dst;
+      gemm(ao, taps_1x1(), w->proj, ep);
+    }
+    release(bao);
   }
 
   // ResBlock._forward (openaimodel.py:256-276) / ResnetBlock.forward (model_lidm.py:127-147, temb None)
@@ -998,10 +1129,12 @@ void build_unet_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
   {
     int H = cfg.latent_h, W = cfg.latent_w;
     for (int k = 0; k < n_in; ++k) {
-      if (h->in_blocks[k][0].kind == Layer::DOWN) { H /= 2; W /= 2; }
+      const Layer& L0 = h->in_blocks[k][0];
+      if (L0.kind == Layer::DOWN || (L0.kind == Layer::RES && L0.r.updown == 2)) { H /= 2; W /= 2; }
       rh[k] = H; rw[k] = W;
     }
   }
+  const bool zw = h->is_layout;        // plain zero-padded convolutions (no circular halo)
   // concat buffers: output block i consumes cat[h_prev (Ca) | hs[n_in-1-i] (Cb)]
   std::vector<View> cat(n_out);
   std::vector<Buf> catbuf(n_out);
@@ -1045,13 +1178,17 @@ void build_unet_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
       const Layer& L = layers[j];
       const bool last = (j + 1 == layers.size());
       int Ho = x.H, Wo = x.W;
-      if (L.kind == Layer::DOWN) { Ho /= 2; Wo /= 2; }
-      if (L.kind == Layer::UP) { Ho *= 2; Wo *= 2; }
+      if (L.kind == Layer::DOWN || (L.kind == Layer::RES && L.r.updown == 2)) { Ho /= 2; Wo /= 2; }
+      if (L.kind == Layer::UP || (L.kind == Layer::RES && L.r.updown == 1)) { Ho *= 2; Wo *= 2; }
       Buf ob; View o;
       if (last) o = dst;
       else o = b.act(B, Ho, Wo, L.cout, 0, 0, &ob);
       switch (L.kind) {
-        case Layer::RES: b.res_block(L.r, x, o, 3, 3, 1, 1, 1, 1e-5f); break;
+        case Layer::RES:
+          if (zw) b.res_block_film(L.r, x, o);
+          else b.res_block(L.r, x, o, 3, 3, 1, 1, 1, 1e-5f);
+          break;
+        case Layer::OACA: b.oaca_block(&L.oa, x, o); break;
         case Layer::ATTN: b.attn_block(L.a, x, o); break;
         case Layer::ST: b.st_block(L.st, x, o, ctx_kv, h->ctx_n, ctx_len); break;
         case Layer::DOWN: b.down(L.c, x, o); break;
@@ -1074,7 +1211,7 @@ void build_unet_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
     bf16* col = b.raw<bf16>((size_t)B * H * W * kpad, &bc);
     const int Cin = cfg.in_channels;
     const bool f16 = b.f16;
-    b.op([=](cudaStream_t s) { launch_im2col_nchw_f32(P->xin, B, Cin, H, W, 3, 3, 1, 1, col, kpad, s, f16); });
+    b.op([=](cudaStream_t s) { launch_im2col_nchw_f32(P->xin, B, Cin, H, W, 3, 3, 1, 1, col, kpad, s, f16, zw); });
     View a = b.mat(col, B, H, W, kpad, kpad);
     GemmEpilogue ep;
     ep.bias = h->in_blocks[0][0].c.bias;
@@ -1105,12 +1242,12 @@ void build_unet_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
   // out: GroupNorm32 + SiLU + conv3x3 (zero-init in the reference) -> eps (fp32 NCHW) [+ fused DDIM update]
   {
     Buf bg;
-    View g = b.act(B, hfinal.H, hfinal.W, hfinal.C, 1, 1, &bg);
+    View g = b.act(B, hfinal.H, hfinal.W, hfinal.C, zw ? 0 : 1, zw ? 0 : 1, &bg);
     b.groupnorm(hfinal, g, h->out_norm, 1e-5f, true);
     const GemmB wb = Builder::gb(h->out_conv);
     const float* bias = h->out_conv.bias;
     const int N = h->out_conv.cout;
-    const ConvTaps taps = taps_rect(3, 3, 1, 1);
+    const ConvTaps taps = zw ? Builder::taps_zero3x3() : taps_rect(3, 3, 1, 1);
     b.op([=](cudaStream_t s) {
       GemmEpilogue ep;
       ep.bias = bias;
@@ -1804,6 +1941,118 @@ bool in_list(const int32_t* v, int n, int x) {
   return false;
 }
 
+// ObjectAwareCrossAttention weights (object_cross_unet.py:430-446, shipped options: norm_first False, positional scale 1)
+OacaW pack_oaca(Packer& pk, const std::string& p, int ch, int rows) {
+  lidm_handle* h = pk.h;
+  const int E = h->cfg.encoder_channels;
+  OacaW a;
+  a.ch = ch; a.heads = ch / 64; a.rows = rows;
+  a.n_qkv = pk.norm(p + ".norm_for_qkv", ch);
+  a.n_img_pos = pk.norm(p + ".norm_for_image_patch_positional_embedding", ch);
+  a.n_lay_pos = pk.norm(p + ".norm_for_layout_positional_embedding", ch);
+  a.n_cls = pk.norm(p + ".norm_for_obj_class_embedding", E);
+  if (h->raw.count(p + ".norm_for_obj_embedding.weight"))
+    throw Error(LIDM_ERR_INVALID, "ObjectAwareCrossAttention: norm_for_obj_embedding / norm_first are not supported");
+  // q and k rows (and biases) carry the (2 * 64)^-1/4 scale of both score factors (object_cross_unet.py:533-536)
+  const float scale = 1.0f / std::sqrt(std::sqrt(128.0f));
+  const DevTensor& w = find_raw(h, p + ".qkv_projector.weight", pk.ema);
+  const DevTensor& bsrc = find_raw(h, p + ".qkv_projector.bias", pk.ema);
+  if (w.numel != (int64_t)3 * ch * ch || bsrc.numel != 3 * ch) throw Error(LIDM_ERR_STATE, "qkv_projector weight size: " + p);
+  ConvW c;
+  c.cout = 3 * ch; c.cin = ch; c.kh = c.kw = 1;
+  c.n_alloc = round_n_alloc(3 * ch);
+  c.f16 = pk.f16;
+  c.k_alloc = ch;
+  c.w = dev_alloc<bf16>(h, (size_t)c.n_alloc * c.k_alloc);
+  launch_pack_conv_weight(w.p, 3 * ch, ch, 1, 1, c.n_alloc, c.k_alloc, nullptr, nullptr, scale, 2 * ch, c.w, pk.s, pk.f16);
+  std::vector<float> bh(3 * ch);
+  LIDM_CUDA_CHECK(cudaMemcpyAsync(bh.data(), bsrc.p, bh.size() * sizeof(float), cudaMemcpyDeviceToHost, pk.s));
+  LIDM_CUDA_CHECK(cudaStreamSynchronize(pk.s));
+  for (int i = 0; i < 2 * ch; ++i) bh[i] *= scale;
+  c.bias = dev_alloc<float>(h, bh.size());
+  LIDM_CUDA_CHECK(cudaMemcpy(c.bias, bh.data(), bh.size() * sizeof(float), cudaMemcpyHostToDevice));
+  a.qkv = c;
+  a.proj = pk.conv(p + ".proj_out", ch, ch, 1, 1);
+  a.w_pos = pk.f32(p + ".layout_position_embedding_projector.weight", (int64_t)ch * E);
+  a.b_pos = pk.f32(p + ".layout_position_embedding_projector.bias", ch);
+  a.w_content = pk.f32(p + ".layout_content_embedding_projector.weight", (int64_t)2 * ch * E);
+  a.b_content = pk.f32(p + ".layout_content_embedding_projector.bias", 2 * ch);
+  return a;
+}
+
+// LayoutDiffusionUNetModel.__init__ (object_cross_unet.py:742-912, resblock_updown = True, use_scale_shift_norm = True)
+void finalize_unet_layout(lidm_handle* h, Packer& pk) {
+  const lidm_config& cfg = h->cfg;
+  const std::string U = "model.diffusion_model.";
+  const int mc = cfg.model_channels;
+  const int nab = cfg.num_attention_blocks > 0 ? cfg.num_attention_blocks : 1;
+  LIDM_REQUIRE(!pk.precise, "the layout U-Net runs in the bf16 / fp16 modes");
+  LIDM_REQUIRE(cfg.num_head_channels == 64 && cfg.encoder_channels > 0 && cfg.encoder_channels % 32 == 0,
+               "layout U-Net: num_head_channels must be 64 and encoder_channels a positive multiple of 32");
+  {
+    Layer L; L.kind = Layer::CONV; L.cin = cfg.in_channels; L.cout = mc;
+    L.c = pk.conv(U + "input_blocks.0.0", mc, cfg.in_channels, 3, 3, (9 * cfg.in_channels + 63) / 64 * 64);
+    h->in_blocks.push_back({L});
+    h->in_chans.push_back(mc);
+  }
+  auto make_res = [&](const std::string& p, int cin, int cout, int updown) {
+    Layer L; L.kind = Layer::RES; L.cin = cin; L.cout = cout;
+    L.r = pack_res(pk, p, cin, cout, 3, 3, true);
+    L.r.film = true; L.r.updown = updown;
+    return L;
+  };
+  auto make_attn = [&](const std::string& p, int c, int ds) {
+    Layer L; L.kind = Layer::OACA; L.cin = L.cout = c;
+    LIDM_REQUIRE(cfg.latent_h % ds == 0, "attention_ds must divide the latent height");
+    L.oa = pack_oaca(pk, p, c, cfg.latent_h / ds);
+    return L;
+  };
+  int ch = mc, ds = 1;
+  for (int level = 0; level < cfg.n_channel_mult; ++level) {
+    for (int r = 0; r < cfg.num_res_blocks; ++r) {
+      const std::string p = U + "input_blocks." + std::to_string(h->in_blocks.size());
+      std::vector<Layer> layers;
+      layers.push_back(make_res(p + ".0", ch, cfg.channel_mult[level] * mc, 0));
+      ch = cfg.channel_mult[level] * mc;
+      if (in_list(cfg.attention_resolutions, cfg.n_attention_resolutions, ds))
+        for (int a = 0; a < nab; ++a) layers.push_back(make_attn(p + "." + std::to_string(1 + a), ch, ds));
+      h->in_blocks.push_back(layers);
+      h->in_chans.push_back(ch);
+    }
+    if (level != cfg.n_channel_mult - 1) {
+      const std::string p = U + "input_blocks." + std::to_string(h->in_blocks.size());
+      h->in_blocks.push_back({make_res(p + ".0", ch, ch, 2)});
+      h->in_chans.push_back(ch);
+      ds *= 2;
+    }
+  }
+  h->mid_block.push_back(make_res(U + "middle_block.0", ch, ch, 0));
+  h->mid_block.push_back(make_attn(U + "middle_block.1", ch, ds));
+  h->mid_block.push_back(make_res(U + "middle_block.2", ch, ch, 0));
+  std::vector<int> chans = h->in_chans;
+  for (int level = cfg.n_channel_mult - 1; level >= 0; --level) {
+    for (int i = 0; i <= cfg.num_res_blocks; ++i) {
+      const int ich = chans.back();
+      chans.pop_back();
+      const std::string p = U + "output_blocks." + std::to_string(h->out_blocks.size());
+      std::vector<Layer> layers;
+      layers.push_back(make_res(p + ".0", ch + ich, mc * cfg.channel_mult[level], 0));
+      ch = mc * cfg.channel_mult[level];
+      int j = 1;
+      if (in_list(cfg.attention_resolutions, cfg.n_attention_resolutions, ds))
+        for (int a = 0; a < nab; ++a) layers.push_back(make_attn(p + "." + std::to_string(j++), ch, ds));
+      if (level && i == cfg.num_res_blocks) {
+        layers.push_back(make_res(p + "." + std::to_string(j++), ch, ch, 1));
+        ds /= 2;
+      }
+      h->out_blocks.push_back(layers);
+    }
+  }
+  h->out_norm = pk.norm(U + "out.0", ch);
+  h->out_conv = pk.conv(U + "out.2", cfg.out_channels, mc, 3, 3);
+  if (ch != mc) throw Error(LIDM_ERR_INVALID, "U-Net must end at model_channels");
+}
+
 void finalize(lidm_handle* h, bool use_ema) {
   const lidm_config& cfg = h->cfg;
   Packer pk{h, use_ema};
@@ -1820,9 +2069,14 @@ void finalize(lidm_handle* h, bool use_ema) {
   h->te_w2 = pk.f32(U + "time_embed.2.weight", (int64_t)ted * ted);
   h->te_b2 = pk.f32(U + "time_embed.2.bias", ted);
 
-  // ---- U-Net topology, exactly as UNetModel.__init__ walks it (openaimodel.py:516-687)
   std::vector<std::pair<std::string, ResW*>> emb_layers;
   h->in_blocks.clear(); h->out_blocks.clear(); h->mid_block.clear(); h->in_chans.clear();
+  h->is_layout = cfg.unet_type == 1;
+  h->has_st = false;
+  h->ctx_n = 0;
+  if (h->is_layout) finalize_unet_layout(h, pk);
+  else {
+  // ---- U-Net topology, exactly as UNetModel.__init__ walks it (openaimodel.py:516-687)
   {
     Layer L; L.kind = Layer::CONV; L.cin = cfg.in_channels; L.cout = mc;
     const int kpad = (9 * cfg.in_channels + 63) / 64 * 64;
@@ -1948,6 +2202,7 @@ void finalize(lidm_handle* h, bool use_ema) {
   h->out_norm = pk.norm(U + "out.0", ch);
   h->out_conv = pk.conv(U + "out.2", cfg.out_channels, mc, 3, 3);
   if (ch != mc) throw Error(LIDM_ERR_INVALID, "U-Net must end at model_channels");
+  }   // openaimodel.UNetModel
 
   // ---- emb_layers: one concatenated [emb_total][ted] fp32 matrix, evaluated once per step for all ResBlocks
   {
@@ -1960,14 +2215,15 @@ void finalize(lidm_handle* h, bool use_ema) {
     collect(h->mid_block, U + "middle_block");
     for (size_t i = 0; i < h->out_blocks.size(); ++i) collect(h->out_blocks[i], U + "output_blocks." + std::to_string(i));
     int total = 0;
-    for (auto& e : all) { e.second->emb_off = total; total += e.second->cout; }
+    for (auto& e : all) { e.second->emb_off = total; total += (e.second->film ? 2 : 1) * e.second->cout; }
     h->emb_total = total;
     h->emb_w = dev_alloc<float>(h, (size_t)total * ted);
     h->emb_b = dev_alloc<float>(h, total);
     for (auto& e : all) {
       const DevTensor& w = find_raw(h, e.first + ".emb_layers.1.weight", use_ema);
       const DevTensor& bb = find_raw(h, e.first + ".emb_layers.1.bias", use_ema);
-      if (w.numel != (int64_t)e.second->cout * ted || bb.numel != e.second->cout)
+      const int erows = (e.second->film ? 2 : 1) * e.second->cout;
+      if (w.numel != (int64_t)erows * ted || bb.numel != erows)
         throw Error(LIDM_ERR_STATE, "emb_layers size mismatch at " + e.first);
       LIDM_CUDA_CHECK(cudaMemcpy(h->emb_w + (size_t)e.second->emb_off * ted, w.p, w.numel * sizeof(float), cudaMemcpyDeviceToDevice));
       LIDM_CUDA_CHECK(cudaMemcpy(h->emb_b + e.second->emb_off, bb.p, bb.numel * sizeof(float), cudaMemcpyDeviceToDevice));
@@ -2112,10 +2368,16 @@ void ensure_time_buffers(lidm_handle* h, int rows) {
 }
 
 // timestep_embedding -> time_embed -> all emb_layers (basic.py:278-296, openaimodel.py:732-733, 262)
-void run_time_embed(lidm_handle* h, const int64_t* t_dev, int rows, cudaStream_t s) {
+void run_time_embed(lidm_handle* h, const int64_t* t_dev, int rows, cudaStream_t s, int t_stride = 1,
+                    const float* rowbias = nullptr) {
   launch_time_embed(t_dev, rows, h->cfg.model_channels, h->te_w0, h->te_b0, h->te_w2, h->te_b2, h->ted, h->te_tmp,
-                    h->te_emb, s);
+                    h->te_emb, s, t_stride, rowbias);
   launch_linear_rows(h->te_emb, rows, h->ted, h->emb_w, h->emb_b, h->emb_total, h->emb_out, s);
+}
+
+void require_layout_cond(lidm_handle* h, int B) {
+  if (h->cond_B != B || h->cond_xf_proj == nullptr)
+    throw Error(LIDM_ERR_STATE, "layout U-Net: lidm_layout_set_cond has not been called for batch size " + std::to_string(B));
 }
 
 void require_ready(lidm_handle* h, int B) {
@@ -2156,6 +2418,8 @@ __global__ void qkv_legacy_to_internal_kernel(const float* __restrict__ qkv, int
 
 // Which conditioning tensors this model takes (DiffusionWrapper.forward, ddpm.py:2313-2339).
 void check_conditioning(lidm_handle* h, const float* c_concat, const float* context, int ctx_len) {
+  if (h->is_layout && (c_concat != nullptr || context != nullptr))
+    throw Error(LIDM_ERR_INVALID, "the layout U-Net takes its conditioning through lidm_layout_set_cond");
   const bool wants_concat = h->cfg.in_channels > h->latent_channels;
   if (wants_concat != (c_concat != nullptr))
     throw Error(LIDM_ERR_INVALID, wants_concat ? "this model is concat-conditioned: c_concat is required"
@@ -2256,14 +2520,16 @@ int lidm_create(const lidm_config* cfg, lidm_handle** out) {
     LIDM_REQUIRE(cfg->n_channel_mult >= 1 && cfg->n_channel_mult <= LIDM_MAX_LEVELS, "n_channel_mult");
     LIDM_REQUIRE(cfg->ae_n_ch_mult >= 1 && cfg->ae_n_ch_mult <= LIDM_MAX_LEVELS, "ae_n_ch_mult");
     LIDM_REQUIRE(cfg->model_channels % 64 == 0, "model_channels must be a multiple of 64");
-    LIDM_REQUIRE(cfg->num_head_channels == 32, "num_head_channels must be 32");
+    LIDM_REQUIRE(cfg->unet_type == 0 || cfg->unet_type == 1, "unet_type");
+    LIDM_REQUIRE(cfg->num_head_channels == (cfg->unet_type == 1 ? 64 : 32),
+                 "num_head_channels must be 32 (openaimodel.UNetModel) / 64 (LayoutDiffusionUNetModel)");
     LIDM_REQUIRE(cfg->ae_ch % 64 == 0, "ae ch must be a multiple of 64");
     LIDM_REQUIRE(cfg->latent_h > 0 && cfg->latent_w > 0 && cfg->scale_factor != 0.f, "latent shape / scale_factor");
     const int down = 1 << (cfg->n_channel_mult - 1);
     LIDM_REQUIRE(cfg->latent_h % down == 0 && cfg->latent_w % down == 0, "latent not divisible by U-Net downsampling");
     const int lw = cfg->latent_w / down, lh = cfg->latent_h / down;
-    LIDM_REQUIRE((lw >= 128 ? lw % 128 == 0 : (128 % lw == 0 && lh % (128 / lw) == 0)),
-                 "coarsest U-Net level must tile into 128-pixel patches");
+    LIDM_REQUIRE((lw >= 128 ? lw % 128 == 0 : (128 % lw == 0 && (lh % (128 / lw) == 0 || lh * lw == 64 || lh * lw == 32))),
+                 "coarsest U-Net level must tile into 128-pixel patches (or hold 32 / 64 pixels)");
     LIDM_REQUIRE(cfg->precision >= LIDM_PREC_BF16 && cfg->precision <= LIDM_PREC_FP16, "precision");
     LIDM_REQUIRE(cfg->ae_precision >= 0 && cfg->ae_precision <= LIDM_PREC_FP16 + 1, "ae_precision");
     lidm_handle* h = new lidm_handle();
@@ -2343,13 +2609,87 @@ int lidm_unet_forward_cond(lidm_handle* h, const float* x, const int64_t* t, con
     Plan* P = get_plan(h, h->unet_plans, B, h->unet_prec == LIDM_PREC_BF16X3 ? build_unet_plan_pass_p : build_unet_plan_pass,
                        h->has_st ? ctx_len : 0);
     ensure_time_buffers(h, B);
-    run_time_embed(h, t, B, s);
+    if (h->is_layout) {
+      require_layout_cond(h, B);
+      run_time_embed(h, t, B, s, 1, h->cond_xf_proj);     // emb = time_embed(t) + xf_proj (object_cross_unet.py:934-936)
+    } else run_time_embed(h, t, B, s);
+    P->cond_gen = h->cond_gen;
     P->x = x; P->out = eps_out;
     P->xin = assemble_input(h, x, c_concat, B, 0, B, s);
     P->context = context;
     P->rowadd_base = h->emb_out; P->rowadd_ld = h->emb_total;
     P->ddim_x_prev = nullptr; P->ddim_noise = nullptr; P->ddim_pred_x0 = nullptr; P->ddim_coef = nullptr;
     run_plan(P, s);
+  });
+}
+
+int lidm_layout_set_cond(lidm_handle* h, int32_t B, int32_t n_layout, const float* xf_proj, const float* xf_out,
+                         const float* obj_class_embedding, const float* obj_bbox_embedding, int32_t n_res,
+                         const int32_t* res_rows, const float* const* patch_emb, const int32_t* patch_batch, void* stream) {
+  return guarded(h, [&] {
+    require_ready(h, B);
+    if (!h->is_layout) throw Error(LIDM_ERR_INVALID, "this model is not a layout U-Net");
+    LIDM_REQUIRE(xf_proj && xf_out && obj_class_embedding && obj_bbox_embedding && n_layout >= 1 && n_layout <= 16,
+                 "layout conditioning tensors (1..16 layout tokens)");
+    LIDM_REQUIRE(n_res >= 0 && (n_res == 0 || (res_rows && patch_emb && patch_batch)), "patch embedding tables");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const lidm_config& cfg = h->cfg;
+    const int E = cfg.encoder_channels;
+    const bool f16 = h->unet_prec == LIDM_PREC_FP16;
+    const float scale = 1.0f / std::sqrt(std::sqrt(128.0f));
+    // (re)allocate when the batch size or a broadcast flag changes; the buffers are read by plans / graphs of this B
+    std::vector<OacaW*> blocks;
+    auto collect = [&](std::vector<Layer>& ls) { for (Layer& L : ls) if (L.kind == Layer::OACA) blocks.push_back(&L.oa); };
+    for (auto& ls : h->in_blocks) collect(ls);
+    collect(h->mid_block);
+    for (auto& ls : h->out_blocks) collect(ls);
+    auto find_res = [&](int rows) {
+      for (int i = 0; i < n_res; ++i) if (res_rows[i] == rows) return i;
+      throw Error(LIDM_ERR_INVALID, "image_patch_bbox_embedding_for_resolution" + std::to_string(rows) + " missing");
+    };
+    bool realloc = h->cond_B != B;
+    for (OacaW* w : blocks) {
+      const int pb = patch_batch[find_res(w->rows)];
+      LIDM_REQUIRE(pb == 1 || pb == B, "patch embedding batch must be 1 or B");
+      if (w->pos_batch != pb) realloc = true;
+    }
+    if (realloc) {
+      LIDM_CUDA_CHECK(cudaDeviceSynchronize());
+      for (void* p : h->cond_owned) cudaFree(p);
+      h->cond_owned.clear();
+      cudaFree(h->cond_xf_proj); h->cond_xf_proj = nullptr;
+      LIDM_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&h->cond_xf_proj), (size_t)B * h->ted * sizeof(float)));
+      auto alloc = [&](size_t elems) {
+        void* p = nullptr;
+        LIDM_CUDA_CHECK(cudaMalloc(&p, elems * sizeof(bf16)));
+        LIDM_CUDA_CHECK(cudaMemset(p, 0, elems * sizeof(bf16)));
+        h->cond_owned.push_back(p);
+        return reinterpret_cast<bf16*>(p);
+      };
+      for (OacaW* w : blocks) {
+        const int T = w->rows * (cfg.latent_w * w->rows / cfg.latent_h);
+        w->pos_batch = patch_batch[find_res(w->rows)];
+        w->pos_img = alloc((size_t)w->pos_batch * T * w->ch);
+        w->klay = alloc((size_t)B * 16 * 2 * w->ch);
+        w->vlay = alloc((size_t)B * 16 * w->ch);
+      }
+      h->cond_B = B;
+      ++h->cond_gen;
+    }
+    h->cond_n_layout = n_layout;
+    LIDM_CUDA_CHECK(cudaMemcpyAsync(h->cond_xf_proj, xf_proj, (size_t)B * h->ted * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    for (OacaW* w : blocks) {
+      const int T = w->rows * (cfg.latent_w * w->rows / cfg.latent_h), C = w->ch;
+      // positional half of the queries / image keys: GN32(conv1(image_patch_bbox_embedding)) (object_cross_unet.py:468-476)
+      launch_oaca_pos(patch_emb[find_res(w->rows)], w->pos_batch, E, T, w->w_pos, w->b_pos, w->n_img_pos.gamma,
+                      w->n_img_pos.beta, C, scale, w->pos_img, T, C, 0, f16, s);
+      // positional half of the layout keys: GN32(conv1(obj_bbox_embedding)) (:493-503) -> columns [C, 2C) of klay
+      launch_oaca_pos(obj_bbox_embedding, B, E, n_layout, w->w_pos, w->b_pos, w->n_lay_pos.gamma, w->n_lay_pos.beta, C, scale,
+                      w->klay, 16, 2 * C, C, f16, s);
+      // content keys / values of the layout tokens (:505-520)
+      launch_oaca_layout_kv(xf_out, obj_class_embedding, B, E, n_layout, w->n_cls.gamma, w->n_cls.beta, w->w_content,
+                            w->b_content, C, scale, w->klay, w->vlay, f16, s);
+    }
   });
 }
 
@@ -2395,7 +2735,12 @@ int lidm_ddim_sample_cond(lidm_handle* h, float* x_inout, const int64_t* timeste
     const int Bp = guided ? 2 * B : B;       // batch the U-Net plan runs at
     const int L = h->has_st ? ctx_len : 0;
     Plan* P = get_plan(h, h->unet_plans, Bp, h->unet_prec == LIDM_PREC_BF16X3 ? build_unet_plan_pass_p : build_unet_plan_pass, L);
-    ensure_time_buffers(h, n_steps);
+    ensure_time_buffers(h, std::max(n_steps, B));
+    if (h->is_layout) {
+      require_layout_cond(h, B);
+      LIDM_REQUIRE(!guided, "classifier-free guidance is not wired for the layout U-Net");
+    }
+    P->cond_gen = h->cond_gen;
     const size_t HW = (size_t)cfg.latent_h * cfg.latent_w;
     const size_t elems = (size_t)B * h->latent_channels * HW;
     if (elems > h->xbuf_elems) {
@@ -2450,20 +2795,24 @@ int lidm_ddim_sample_cond(lidm_handle* h, float* x_inout, const int64_t* timeste
     // pageable -> device copies are staged by the runtime before returning, so the host vectors may go out of scope
     LIDM_CUDA_CHECK(cudaMemcpyAsync(h->t_dev, t_loop.data(), n_steps * sizeof(int64_t), cudaMemcpyHostToDevice, s));
     LIDM_CUDA_CHECK(cudaMemcpyAsync(h->coef_dev, coef.data(), coef.size() * sizeof(float), cudaMemcpyHostToDevice, s));
-    run_time_embed(h, h->t_dev, n_steps, s);   // all steps' embeddings at once (t is uniform over the batch)
+    if (!h->is_layout) run_time_embed(h, h->t_dev, n_steps, s);   // all steps' embeddings at once (t is uniform over the batch)
     LIDM_CUDA_CHECK(cudaMemcpyAsync(h->xa, x_inout, elems * sizeof(float), cudaMemcpyDeviceToDevice, s));
     float* cur = h->xa;
     float* nxt = h->xb;
     for (int i = 0; i < n_steps; ++i) {
       // this step's timestep-embedding row, coefficients and noise slice go to fixed staging addresses, so the same two
       // CUDA graphs (x ping-pong parity) replay the whole loop
-      LIDM_CUDA_CHECK(cudaMemcpyAsync(h->emb_cur, h->emb_out + (size_t)i * h->emb_total, (size_t)h->emb_total * sizeof(float),
-                                      cudaMemcpyDeviceToDevice, s));
+      if (h->is_layout)     // per-sample rows: emb = time_embed(t_i) + xf_proj[b] goes through a SiLU before emb_layers
+        run_time_embed(h, h->t_dev + i, B, s, 0, h->cond_xf_proj);
+      else
+        LIDM_CUDA_CHECK(cudaMemcpyAsync(h->emb_cur, h->emb_out + (size_t)i * h->emb_total, (size_t)h->emb_total * sizeof(float),
+                                        cudaMemcpyDeviceToDevice, s));
       LIDM_CUDA_CHECK(cudaMemcpyAsync(h->coef_cur, h->coef_dev + (size_t)i * 5, 5 * sizeof(float), cudaMemcpyDeviceToDevice, s));
       if (noise) LIDM_CUDA_CHECK(cudaMemcpyAsync(h->noise_cur, noise + (size_t)i * elems, elems * sizeof(float),
                                                  cudaMemcpyDeviceToDevice, s));
       P->context = ctx_run;
-      P->rowadd_base = h->emb_cur; P->rowadd_ld = 0;
+      if (h->is_layout) { P->rowadd_base = h->emb_out; P->rowadd_ld = h->emb_total; }
+      else { P->rowadd_base = h->emb_cur; P->rowadd_ld = 0; }
       const float* nz = noise ? h->noise_cur : nullptr;
       if (!guided) {
         P->x = cur;

@@ -27,6 +27,8 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
 
 struct GemmKernelParams {
   int tiles_w, tiles_per_img, Wbox, Hbox;
+  int bbox;                  // samples per 128-row tile (> 1 when one sample has fewer than 128 pixels), B = batch size
+  int B;
   int hl;
   int ntaps;                 // virtual taps = spatial taps x operand-split segments (<= 27)
   int8_t dx[27], dy[27];
@@ -145,8 +147,9 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_tile = p.n_fast ? tile / num_n_tiles : tile % num_m_tiles;
         const int n0 = (p.n_fast ? tile % num_n_tiles : tile / num_m_tiles) * BN;
-        const int b = m_tile / p.tiles_per_img;
-        const int r = m_tile - b * p.tiles_per_img;
+        const int bt = m_tile / p.tiles_per_img;
+        const int b = bt * p.bbox;
+        const int r = m_tile - bt * p.tiles_per_img;
         const int th = r / p.tiles_w;
         const int h0 = th * p.Hbox, w0 = (r - th * p.tiles_w) * p.Wbox;
         int it = 0;
@@ -202,8 +205,10 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int col_lo = wg * L::COLS;     // this thread drains tile columns [col_lo, col_lo + COLS)
     const int row = q * 32 + lane;
     const int e = threadIdx.x - 64;      // 0..EPI_THREADS-1
-    const int hh = row / p.Wbox;
-    const int ww = row - hh * p.Wbox;
+    const int rps = BM / p.bbox;         // tile rows per sample
+    const int rb = row / rps;            // sample of this row inside the tile (0 unless bbox > 1)
+    const int hh = (row - rb * rps) / p.Wbox;
+    const int ww = (row - rb * rps) - hh * p.Wbox;
     const int HW = p.H * p.W;
     float coef[5] = {0, 0, 0, 0, 0};
     if (p.ddim_x_prev != nullptr) {
@@ -217,8 +222,11 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int ab = lt & 1;
       const int m_tile = p.n_fast ? tile / num_n_tiles : tile % num_m_tiles;
         const int n0 = (p.n_fast ? tile % num_n_tiles : tile / num_m_tiles) * BN;
-      const int b = m_tile / p.tiles_per_img;
-      const int r = m_tile - b * p.tiles_per_img;
+      const int bt = m_tile / p.tiles_per_img;
+      const int b0 = bt * p.bbox;
+      const int b = b0 + rb;
+      const bool b_ok = b < p.B;          // a multi-sample tile may run past the batch
+      const int r = m_tile - bt * p.tiles_per_img;
       const int th = r / p.tiles_w;
       const int h0 = th * p.Hbox, w0 = (r - th * p.tiles_w) * p.Wbox;
       const int h = h0 + hh, w = w0 + ww;
@@ -229,7 +237,7 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         float v = 0.f;
         if (n < p.N) {
           if (p.bias != nullptr) v = __ldg(p.bias + n);
-          if (p.rowadd != nullptr) v += __ldg(p.rowadd + (size_t)b * p.rowadd_ld + n);
+          if (p.rowadd != nullptr) v += __ldg(p.rowadd + (size_t)b0 * p.rowadd_ld + n);
         }
         sbias[ab * SB + i] = v;
       }
@@ -245,7 +253,7 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           constexpr int HALF = L::COLS > 64 ? 64 : L::COLS;   // columns per register batch
           constexpr int NH = L::COLS / HALF;
           constexpr int NCH = HALF / 32;
-          const bool has_res = p.res != nullptr;
+          const bool has_res = p.res != nullptr && b_ok;
           const bf16* rp = has_res ? p.res + ((size_t)(b * p.H + h) * p.res_Wp + (w + p.res_hl)) * p.res_ld + n0 + col_lo
                                    : nullptr;
 #pragma unroll
@@ -340,12 +348,12 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
               for (int j = 0; j < L::OUT_BOXES / 2; ++j)
                 if ((n0 >> 1) + j * 64 < (p.N >> 1))
-                  tma_store_4d(&tmO, stage_out + j * (BM * 128), (n0 >> 1) + j * 64, w0, h0, b);
+                  tma_store_4d(&tmO, stage_out + j * (BM * 128), (n0 >> 1) + j * 64, w0, h0, b0);
             } else {
 #pragma unroll
               for (int j = 0; j < L::OUT_BOXES; ++j)
                 if (n0 + j * 64 < p.N)
-                  tma_store_4d(&tmO, stage_out + j * (BM * 128), n0 + j * 64, w0, h0, b);
+                  tma_store_4d(&tmO, stage_out + j * (BM * 128), n0 + j * 64, w0, h0, b0);
             }
             tma_store_commit();
           }
@@ -391,7 +399,7 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll 1
       for (int c0 = col_lo; c0 < col_lo + L::COLS; c0 += CH) {
         const int n = n0 + c0;
-        const bool live = n < p.N;   // warp-uniform
+        const bool live = n < p.N && b_ok;   // warp-uniform when bbox == 1
         uint4 rres[4];
         const bool has_res = live && p.res != nullptr && CH == 32;
         if (has_res) {
@@ -583,16 +591,26 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
   const int W = a.W, H = a.H;
   LIDM_REQUIRE((W <= BM && BM % W == 0) || (W % BM == 0), "W must divide or be a multiple of 128");
   const int Wbox = W < BM ? W : BM;
-  const int Hbox = BM / Wbox;
+  int Hbox = BM / Wbox;
+  // a sample smaller than one 128-row tile (the 2x32 level of the layout U-Net): the tile covers `bbox` whole samples
+  int bbox = 1;
+  if (H < Hbox) {
+    LIDM_REQUIRE(Hbox % H == 0 && Hbox / H <= 4, "a sample must hold 32, 64 or a multiple of 128 pixels");
+    bbox = Hbox / H;
+    Hbox = H;
+    LIDM_REQUIRE(ep.rowadd == nullptr || ep.rowadd_ld == 0, "per-sample epilogue rows need one sample per tile");
+    LIDM_REQUIRE(!wt_batched && ep.out_t == nullptr, "batched weights need one sample per tile");
+  }
   LIDM_REQUIRE(H % Hbox == 0, "H must be a multiple of 128/W");
-  for (int t = 0; t < taps.n && taps.cstep == 0; ++t) {
+  for (int t = 0; t < taps.n && taps.cstep == 0 && !taps.zero_w; ++t) {
     LIDM_REQUIRE(-taps.dx[t] <= a.hl && taps.dx[t] <= a.hr, "tap exceeds the materialised halo");
   }
+  if (taps.zero_w) LIDM_REQUIRE(a.hl == 0 && a.hr == 0, "zero-padded convolutions read halo-free tensors (TMA fills the border)");
   int BN;
   static const int force_bn = getenv("LIDM_GEMM_BN") ? atoi(getenv("LIDM_GEMM_BN")) : 0;
   if (n_alloc % 256 == 0 && force_bn != 128 && ep.out_t == nullptr) {
     // 128x256 tiles halve the B-operand traffic per MAC; take them unless wave quantisation on 148 SMs eats the gain
-    const long m_tiles = (long)a.B * (H / Hbox) * (W / Wbox);
+    const long m_tiles = bbox > 1 ? (a.B + bbox - 1) / bbox : (long)a.B * (H / Hbox) * (W / Wbox);
     auto eff = [&](long tiles) { const long rounds = (tiles + 147) / 148; return (double)tiles / (double)(rounds * 148); };
     const double e256 = eff(m_tiles * (n_alloc / 256)) * 1.30, e128 = eff(m_tiles * (n_alloc / 128));
     BN = (e256 >= e128 || force_bn == 256) ? 256 : 128;
@@ -606,6 +624,7 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
   p.tiles_w = W / Wbox;
   p.tiles_per_img = p.tiles_w * (H / Hbox);
   p.Wbox = Wbox; p.Hbox = Hbox; p.hl = a.hl;
+  p.bbox = bbox; p.B = a.B;
   p.ntaps = taps.n * nseg;
   for (int t = 0; t < taps.n; ++t) {
     for (int sg = 0; sg < nseg; ++sg) {
@@ -640,14 +659,14 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
   p.ddim_pred_x0 = ep.ddim_pred_x0; p.ddim_coef = ep.ddim_coef;
 
   uint64_t Ktot = (uint64_t)taps.n * nseg * a.C;
-  CUtensorMap tmA = make_tma_act(a, BK, Wbox, Hbox, 128);
+  CUtensorMap tmA = make_tma_act(a, BK, Wbox, Hbox, 128, bbox);
   CUtensorMap tmA2 = tmA;
   if (ep.a2.p != nullptr) {
     const View& a2 = ep.a2;
     LIDM_REQUIRE(nseg == 1 && a2.H == H && a2.W == W && a2.B == a.B && a2.C % BK == 0 && a2.ld % 8 == 0 && a2.wpitch == 0 &&
                      (reinterpret_cast<uintptr_t>(a2.p) & 15) == 0 && ep.residual.p == nullptr,
                  "second A operand: same pixels, channels a multiple of 64, bf16 mode, no residual");
-    tmA2 = make_tma_act(a2, BK, Wbox, Hbox, 128);
+    tmA2 = make_tma_act(a2, BK, Wbox, Hbox, 128, bbox);
     p.k2chunks = a2.C / BK; p.hl2 = a2.hl; p.b2_koff = (int)Ktot;
     Ktot += a2.C;
   }
@@ -656,7 +675,7 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
   CUtensorMap tmB = make_tma_3d(wt, Ktot, (uint64_t)n_alloc, wt_batched ? (uint64_t)a.B : 1, wld * 2,
                                 wt_batched ? (uint64_t)wtb.batch_stride * 2 : wld * 2 * (uint64_t)n_alloc, BK, BN,
                                 128);
-  const int num_m_tiles = a.B * p.tiles_per_img;
+  const int num_m_tiles = bbox > 1 ? (a.B + bbox - 1) / bbox : a.B * p.tiles_per_img;
   const int num_tiles = num_m_tiles * (n_alloc / BN);
   {
     // Tile order: the output-channel tiles of one pixel tile run back to back (and so concurrently on neighbouring
@@ -670,14 +689,14 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
                              ep.res_f32 == nullptr && ep.out_f32_nhwc == nullptr && ep.out_f32_nchw == nullptr)
                                 ? 1 : 0;
   CUtensorMap tmO = tmA;
-  if (use_tma_store) tmO = make_tma_act(ep.out, 64, Wbox, Hbox, 128);
+  if (use_tma_store) tmO = make_tma_act(ep.out, 64, Wbox, Hbox, 128, bbox);
   if (ep.geglu) {
     LIDM_REQUIRE(use_tma_store && BN >= 128 && N % 128 == 0 && ep.out.C == N / 2 && ep.residual.p == nullptr && ep.out.gst == nullptr,
                  "GEGLU epilogue needs a bf16 TMA-store output of N/2 channels and 128-column tiles");
     p.geglu = 1;
   }
   if (use_tma_store && ep.out.gst != nullptr) {
-    LIDM_REQUIRE(Wbox * Hbox == 128 && N % 8 == 0 && ep.out.gst_slots >= ep.out.gst_slot0 + p.tiles_per_img,
+    LIDM_REQUIRE(bbox == 1 && Wbox * Hbox == 128 && N % 8 == 0 && ep.out.gst_slots >= ep.out.gst_slot0 + p.tiles_per_img,
                  "GroupNorm statistics need whole 128-pixel tiles inside one sample");
     p.gst = ep.out.gst; p.gst_ld = ep.out.gst_ld; p.gst_slots = ep.out.gst_slots; p.gst_slot0 = ep.out.gst_slot0;
   }

@@ -1,0 +1,417 @@
+// Layout-conditioned denoiser pieces (sm_100a): the object-aware cross-attention of LayoutDiffusionUNetModel and the
+// small kernels around it.  Reference: lidm/modules/unets/object_cross_unet.py
+//   ObjectAwareCrossAttention.forward  :447-565   image tokens attend to image tokens AND the 13 layout tokens;
+//                                                 queries / keys = [content (64) | positional (64)] per head, values content
+//   ResBlock up / down sampling        :112-171, 253-283   nearest x2 / 2x2 average pooling of h and x
+//
+//   oaca_attention_kernel   one CTA per (128-query tile, head, sample): the whole key set (T <= 256 image keys + 16 layout
+//                           slots) fits one pass, so there is no online softmax: S = Qc Kc^T + Qp Kp^T accumulates in
+//                           TMEM (tcgen05.mma, K = 64 + 64, TMA-fed SWIZZLE_128B operands), every softmax thread owns one
+//                           row (two passes over its TMEM lane: max, then exp2 / sum / bf16 pack), P goes back to TMEM
+//                           (tcgen05.st) and is the A operand of the TS-form P*V product (V = MN-major B operand), O is
+//                           normalised and stored as 128-byte rows.  The 128^-1/4 scale is folded into q, k and the
+//                           positional tensors upstream.
+//   oaca_pos_kernel / oaca_layout_kv_kernel   once per conditioning: the positional projections + GroupNorm32 and the
+//                           layout tokens' keys / values (fp32 CUDA cores; 13 tokens, batch-broadcast aware)
+//   avgpool2_kernel         F.avg_pool2d(2, 2) on channels-last 2-byte tensors
+#include "common.h"
+#include "ptx.cuh"
+
+namespace lidm {
+
+namespace {
+
+constexpr int DH = 64;            // head channels (content); queries / keys carry DH positional channels on top
+constexpr int LAY = 16;           // layout key slots (13 objects in the shipped configuration, zero-padded)
+constexpr int QROWS = 128;
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+template <int T>
+struct OacaCfg {
+  static_assert(T == 64 || T == 128 || T == 192 || T == 256, "image key count");
+  static constexpr int OFF_QC = 0;                                   // [128][64] bf16, 128-byte rows, SWIZZLE_128B
+  static constexpr int OFF_QP = OFF_QC + QROWS * 128;
+  static constexpr int OFF_KC = OFF_QP + QROWS * 128;                // [T][64]
+  static constexpr int OFF_KP = OFF_KC + T * 128;
+  static constexpr int OFF_V = OFF_KP + T * 128;                     // [T][64] (MN-major B operand of P*V)
+  static constexpr int OFF_LC = OFF_V + T * 128;                     // layout keys, content half [16][64]
+  static constexpr int OFF_LP = OFF_LC + LAY * 128;                  // layout keys, positional half
+  static constexpr int OFF_LV = OFF_LP + LAY * 128;                  // layout values
+  static constexpr int OFF_BAR = OFF_LV + LAY * 128;
+  static constexpr int SMEM_TOTAL = OFF_BAR + 128 + 1024;
+  static constexpr uint32_t S_COLS = T + LAY;
+  static constexpr uint32_t P_COL = (S_COLS + 31) / 32 * 32;          // bf16 pairs: (T + 16) / 2 columns
+  static constexpr uint32_t O_COL = (P_COL + S_COLS / 2 + 31) / 32 * 32;
+  static constexpr uint32_t TMEM_COLS = (O_COL + DH) <= 256 ? 256 : 512;
+  static_assert(O_COL + DH <= 512, "TMEM budget");
+  static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
+};
+
+// qkv: (B, T, 3C) = [q | k | v] (q, k pre-scaled); pos: (Bp, T, C) positional half of queries and image keys (pre-scaled);
+// klay: (B, 16, 2C) = [layout key content | layout key positional]; vlay: (B, 16, C); out (B, T, C).
+template <int T, bool F16>
+__global__ void __launch_bounds__(160, 1)
+oaca_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmPos,
+                      const __grid_constant__ CUtensorMap tmKL, const __grid_constant__ CUtensorMap tmVL,
+                      bf16* __restrict__ out, int out_ld, int C, int pos_batched, int n_layout) {
+  using L = OacaCfg<T>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_qk = reinterpret_cast<uint64_t*>(smem + L::OFF_BAR);
+  uint64_t* full_v = full_qk + 1;
+  uint64_t* s_ready = full_qk + 2;
+  uint64_t* p_ready = full_qk + 3;
+  uint64_t* o_ready = full_qk + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full_qk + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * QROWS, head = blockIdx.y, b = blockIdx.z;
+  constexpr int QBOX = T < QROWS ? T : QROWS;          // query rows actually loaded (T = 64: half a tile)
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmQKV); prefetch_tensormap(&tmPos); prefetch_tensormap(&tmKL); prefetch_tensormap(&tmVL);
+    mbar_init(full_qk, 1); mbar_init(full_v, 1); mbar_init(s_ready, 1); mbar_init(p_ready, 4); mbar_init(o_ready, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) { tmem_alloc(tmem_slot, L::TMEM_COLS); tmem_relinquish(); }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      const int pb = pos_batched ? b : 0;
+      // ---- loads: 64-row boxes of 64 channels (8 KiB each)
+      mbar_arrive_expect_tx(full_qk, 2 * QBOX * 128 + 2 * T * 128 + 2 * LAY * 128);
+      for (int r = 0; r < QBOX; r += 64) {
+        tma_load_3d(smem + L::OFF_QC + r * 128, &tmQKV, full_qk, head * DH, q0 + r, b);
+        tma_load_3d(smem + L::OFF_QP + r * 128, &tmPos, full_qk, head * DH, q0 + r, pb);
+      }
+      for (int r = 0; r < T; r += 64) {
+        tma_load_3d(smem + L::OFF_KC + r * 128, &tmQKV, full_qk, C + head * DH, r, b);
+        tma_load_3d(smem + L::OFF_KP + r * 128, &tmPos, full_qk, head * DH, r, pb);
+      }
+      tma_load_3d(smem + L::OFF_LC, &tmKL, full_qk, head * DH, 0, b);
+      tma_load_3d(smem + L::OFF_LP, &tmKL, full_qk, C + head * DH, 0, b);
+      mbar_arrive_expect_tx(full_v, T * 128 + LAY * 128);
+      for (int r = 0; r < T; r += 64) tma_load_3d(smem + L::OFF_V + r * 128, &tmQKV, full_v, 2 * C + head * DH, r, b);
+      tma_load_3d(smem + L::OFF_LV, &tmVL, full_v, head * DH, 0, b);
+
+      // ---- S = Qc Kc^T + Qp Kp^T  (image keys: N = T, layout keys: N = 16)
+      constexpr uint32_t idesc_img = make_idesc_h<F16>(QROWS, T);
+      constexpr uint32_t idesc_lay = make_idesc_h<F16>(QROWS, LAY);
+      mbar_wait(full_qk, 0);
+      tcgen05_fence_after();
+      const uint64_t qc = make_kmajor_desc<128>(smem_u32(smem + L::OFF_QC)), qp = make_kmajor_desc<128>(smem_u32(smem + L::OFF_QP));
+      const uint64_t kc = make_kmajor_desc<128>(smem_u32(smem + L::OFF_KC)), kp = make_kmajor_desc<128>(smem_u32(smem + L::OFF_KP));
+      const uint64_t lc = make_kmajor_desc<128>(smem_u32(smem + L::OFF_LC)), lp = make_kmajor_desc<128>(smem_u32(smem + L::OFF_LP));
+#pragma unroll
+      for (int k = 0; k < DH / 16; ++k) umma_bf16_ss(tmem_base, qc + 2 * k, kc + 2 * k, idesc_img, k != 0);
+#pragma unroll
+      for (int k = 0; k < DH / 16; ++k) umma_bf16_ss(tmem_base, qp + 2 * k, kp + 2 * k, idesc_img, 1);
+#pragma unroll
+      for (int k = 0; k < DH / 16; ++k) umma_bf16_ss(tmem_base + T, qc + 2 * k, lc + 2 * k, idesc_lay, k != 0);
+#pragma unroll
+      for (int k = 0; k < DH / 16; ++k) umma_bf16_ss(tmem_base + T, qp + 2 * k, lp + 2 * k, idesc_lay, 1);
+      umma_commit(s_ready);
+
+      // ---- O = P V (P from tensor memory, V an MN-major shared-memory operand: 16 keys = two 8-row groups = 2 KiB)
+      constexpr uint32_t idesc_o = make_idesc_h<F16>(QROWS, DH) | (1u << 16);
+      mbar_wait(full_v, 0);
+      mbar_wait(p_ready, 0);
+      tcgen05_fence_after();
+      const uint64_t vd = make_kmajor_desc<128>(smem_u32(smem + L::OFF_V)), lv = make_kmajor_desc<128>(smem_u32(smem + L::OFF_LV));
+      const uint32_t tP = tmem_base + L::P_COL, dO = tmem_base + L::O_COL;
+#pragma unroll
+      for (int kk = 0; kk < T / 16; ++kk) umma_bf16_ts(dO, tP + kk * 8, vd + (uint64_t)((kk * 2048) >> 4), idesc_o, kk != 0);
+      umma_bf16_ts(dO, tP + (T / 16) * 8, lv, idesc_o, 1);
+      umma_commit(o_ready);
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax: one thread per query row
+    const int row = warp * 32 + lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    constexpr float LOG2E = 1.4426950408889634f;
+    mbar_wait(s_ready, 0);
+    tcgen05_fence_after();
+    float m = -INFINITY;
+    {
+#pragma unroll 1
+      for (int c = 0; c < T / 32; ++c) {
+        uint32_t sv[32];
+        tmem_ld_32x32b_x32(lane_base + c * 32, sv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(sv[i]));
+      }
+      uint32_t lv16[16];
+      tmem_ld_32x32b_x16(lane_base + T, lv16);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < LAY; ++i)
+        if (i < n_layout) m = fmaxf(m, __uint_as_float(lv16[i]));
+    }
+    const float mb = m * LOG2E;
+    float sum = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < T / 64; ++c) {
+      uint32_t sa[32], sb[32], pk[32];
+      tmem_ld_32x32b_x32(lane_base + c * 64, sa);
+      tmem_ld_32x32b_x32(lane_base + c * 64 + 32, sb);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float p0 = ex2f(fmaf(__uint_as_float(sa[2 * i]), LOG2E, -mb)), p1 = ex2f(fmaf(__uint_as_float(sa[2 * i + 1]), LOG2E, -mb));
+        const float p2 = ex2f(fmaf(__uint_as_float(sb[2 * i]), LOG2E, -mb)), p3 = ex2f(fmaf(__uint_as_float(sb[2 * i + 1]), LOG2E, -mb));
+        sum += (p0 + p1) + (p2 + p3);
+        pk[i] = pack_h<F16>(p0, p1);
+        pk[16 + i] = pack_h<F16>(p2, p3);
+      }
+      tmem_st_32x32b_x32(lane_base + L::P_COL + c * 32, pk);
+    }
+    {
+      uint32_t lv16[16], pk[8];
+      tmem_ld_32x32b_x16(lane_base + T, lv16);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float p0 = (2 * i < n_layout) ? ex2f(fmaf(__uint_as_float(lv16[2 * i]), LOG2E, -mb)) : 0.f;
+        const float p1 = (2 * i + 1 < n_layout) ? ex2f(fmaf(__uint_as_float(lv16[2 * i + 1]), LOG2E, -mb)) : 0.f;
+        sum += p0 + p1;
+        pk[i] = pack_h<F16>(p0, p1);
+      }
+      tmem_st_32x32b_x8(lane_base + L::P_COL + T / 2, pk);
+    }
+    tmem_st_wait();
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(p_ready);
+    // ---- epilogue
+    mbar_wait(o_ready, 0);
+    tcgen05_fence_after();
+    uint32_t o0[32], o1[32];
+    tmem_ld_32x32b_x32(lane_base + L::O_COL, o0);
+    tmem_ld_32x32b_x32(lane_base + L::O_COL + 32, o1);
+    tmem_ld_wait();
+    tcgen05_fence_before();
+    if (q0 + row < T) {
+      const float inv = 1.f / sum;
+      uint4* op = reinterpret_cast<uint4*>(out + ((size_t)b * T + q0 + row) * out_ld + head * DH);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = pack_h<F16>(__uint_as_float(o0[8 * i + 0]) * inv, __uint_as_float(o0[8 * i + 1]) * inv);
+        u.y = pack_h<F16>(__uint_as_float(o0[8 * i + 2]) * inv, __uint_as_float(o0[8 * i + 3]) * inv);
+        u.z = pack_h<F16>(__uint_as_float(o0[8 * i + 4]) * inv, __uint_as_float(o0[8 * i + 5]) * inv);
+        u.w = pack_h<F16>(__uint_as_float(o0[8 * i + 6]) * inv, __uint_as_float(o0[8 * i + 7]) * inv);
+        op[i] = u;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        u.x = pack_h<F16>(__uint_as_float(o1[8 * i + 0]) * inv, __uint_as_float(o1[8 * i + 1]) * inv);
+        u.y = pack_h<F16>(__uint_as_float(o1[8 * i + 2]) * inv, __uint_as_float(o1[8 * i + 3]) * inv);
+        u.z = pack_h<F16>(__uint_as_float(o1[8 * i + 4]) * inv, __uint_as_float(o1[8 * i + 5]) * inv);
+        u.w = pack_h<F16>(__uint_as_float(o1[8 * i + 6]) * inv, __uint_as_float(o1[8 * i + 7]) * inv);
+        op[4 + i] = u;
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 4) { tcgen05_fence_after(); tmem_dealloc(tmem_base, L::TMEM_COLS); }
+}
+
+template <int T, bool F16>
+void launch_oaca_t(const bf16* qkv, const bf16* pos, int pos_batch, const bf16* klay, const bf16* vlay, int n_layout,
+                   const View& out, int B, int C, cudaStream_t s) {
+  using L = OacaCfg<T>;
+  static bool configured = false;
+  if (!configured) {
+    LIDM_CUDA_CHECK(cudaFuncSetAttribute(oaca_attention_kernel<T, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_TOTAL));
+    configured = true;
+  }
+  const int heads = C / DH;
+  CUtensorMap tmQKV = make_tma_3d(qkv, 3 * C, T, B, (uint64_t)3 * C * 2, (uint64_t)T * 3 * C * 2, DH, 64, 128);
+  CUtensorMap tmPos = make_tma_3d(pos, C, T, pos_batch, (uint64_t)C * 2, (uint64_t)T * C * 2, DH, 64, 128);
+  CUtensorMap tmKL = make_tma_3d(klay, 2 * C, LAY, B, (uint64_t)2 * C * 2, (uint64_t)LAY * 2 * C * 2, DH, LAY, 128);
+  CUtensorMap tmVL = make_tma_3d(vlay, C, LAY, B, (uint64_t)C * 2, (uint64_t)LAY * C * 2, DH, LAY, 128);
+  dim3 grid((T + QROWS - 1) / QROWS, heads, B);
+  oaca_attention_kernel<T, F16><<<grid, 160, L::SMEM_TOTAL, s>>>(tmQKV, tmPos, tmKL, tmVL, out.p, out.ld, C, pos_batch > 1 ? 1 : 0,
+                                                                n_layout);
+  LIDM_CUDA_CHECK(cudaGetLastError());
+  LIDM_COUNT_LAUNCH(1);
+}
+
+// ------------------------------------------------------------------------------------------------- conditioning prep
+// y[b, c, l] = GroupNorm32( bias[c] + sum_e W[c, e] src[b, e, l] ) * scale  ->  dst[(b * rows + l) * dst_ld + dst_col + c]
+// One CTA per (sample, group): the group's (C / 32) x L projections live in shared memory between the two passes.
+__global__ void oaca_pos_kernel(const float* __restrict__ src, int E, int Lt, const float* __restrict__ W, const float* __restrict__ bias,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int C, float eps, float scale,
+                                bf16* __restrict__ dst, int rows, int dst_ld, int dst_col, bool f16) {
+  extern __shared__ float sh[];                  // [cpg][Lt] projections, then 64 floats of reduction scratch
+  const int b = blockIdx.y, g = blockIdx.x;
+  const int cpg = C / 32;
+  float* proj = sh;
+  float* red = sh + cpg * Lt;
+  const float* sb = src + (size_t)b * E * Lt;
+  float s = 0.f, q = 0.f;
+  for (int i = threadIdx.x; i < cpg * Lt; i += blockDim.x) {
+    const int cl = i / Lt, l = i - cl * Lt;
+    const int c = g * cpg + cl;
+    const float* wr = W + (size_t)c * E;
+    float acc = bias[c];
+    for (int e = 0; e < E; ++e) acc = fmaf(__ldg(wr + e), __ldg(sb + (size_t)e * Lt + l), acc);
+    proj[i] = acc;
+    s += acc; q += acc * acc;
+  }
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = s; red[32 + (threadIdx.x >> 5)] = q; }
+  __syncthreads();
+  s = 0.f; q = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { s += red[i]; q += red[32 + i]; }
+  const float n = (float)(cpg * Lt);
+  const float mean = s / n;
+  const float rstd = rsqrtf(fmaxf(q / n - mean * mean, 0.f) + eps);
+  for (int i = threadIdx.x; i < cpg * Lt; i += blockDim.x) {
+    const int cl = i % cpg, l = i / cpg;           // channel fastest: neighbouring threads write neighbouring channels
+    const int c = g * cpg + cl;
+    const float v = ((proj[cl * Lt + l] - mean) * rstd * gamma[c] + beta[c]) * scale;
+    store_hr(dst + ((size_t)b * rows + l) * dst_ld + dst_col + c, v, f16);
+  }
+}
+
+// layout tokens: content = (xf_out + GroupNorm32(obj_class_embedding)) / 2; [k | v] = Wc content + bc
+//   k * scale -> klay[(b * 16 + l) * 2C + c],  v -> vlay[(b * 16 + l) * C + c]     (one CTA per sample)
+__global__ void oaca_layout_kv_kernel(const float* __restrict__ xf_out, const float* __restrict__ cls, int E, int Lt,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                      const float* __restrict__ Wc, const float* __restrict__ bc, int C, float scale,
+                                      bf16* __restrict__ klay, bf16* __restrict__ vlay, bool f16) {
+  extern __shared__ float sh[];                  // content [E][Lt], then per-group (mean, rstd) [32][2]
+  const int b = blockIdx.x;
+  float* content = sh;
+  float* stat = sh + E * Lt;
+  const float* cb = cls + (size_t)b * E * Lt;
+  const float* xb = xf_out + (size_t)b * E * Lt;
+  const int cpg = E / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int g = warp; g < 32; g += blockDim.x >> 5) {
+    float s = 0.f, q = 0.f;
+    for (int i = lane; i < cpg * Lt; i += 32) { const float v = cb[(size_t)g * cpg * Lt + i]; s += v; q += v * v; }
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    if (lane == 0) {
+      const float n = (float)(cpg * Lt), mean = s / n;
+      stat[2 * g] = mean;
+      stat[2 * g + 1] = rsqrtf(fmaxf(q / n - mean * mean, 0.f) + eps);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < E * Lt; i += blockDim.x) {
+    const int e = i / Lt, g = e / cpg;
+    content[i] = (xb[i] + ((cb[i] - stat[2 * g]) * stat[2 * g + 1] * gamma[e] + beta[e])) * 0.5f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C * Lt; i += blockDim.x) {
+    const int n = i % (2 * C), l = i / (2 * C);
+    const float* wr = Wc + (size_t)n * E;
+    float acc = bc[n];
+    for (int e = 0; e < E; ++e) acc = fmaf(__ldg(wr + e), content[e * Lt + l], acc);
+    if (n < C) store_hr(klay + ((size_t)b * LAY + l) * 2 * C + n, acc * scale, f16);
+    else store_hr(vlay + ((size_t)b * LAY + l) * C + (n - C), acc, f16);
+  }
+}
+
+// F.avg_pool2d(kernel 2, stride 2) on a halo-free channels-last tensor; 16-byte vectors
+__global__ void avgpool2_kernel(const bf16* __restrict__ x, int B, int H, int W, int xld, int C, bf16* __restrict__ y, int yld,
+                                bool f16) {
+  const int vec = C >> 3, Ho = H / 2, Wo = W / 2;
+  const int64_t total = (int64_t)B * Ho * Wo * vec;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % vec);
+    int64_t r = i / vec;
+    const int wo = (int)(r % Wo);
+    r /= Wo;
+    const int ho = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    const bf16* base = x + ((size_t)(b * H + 2 * ho) * W + 2 * wo) * xld;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(base) + cv), bq = __ldg(reinterpret_cast<const uint4*>(base + xld) + cv);
+    const uint4 c = __ldg(reinterpret_cast<const uint4*>(base + (size_t)W * xld) + cv),
+                d = __ldg(reinterpret_cast<const uint4*>(base + (size_t)(W + 1) * xld) + cv);
+    const uint32_t ua[4] = {a.x, a.y, a.z, a.w}, ub[4] = {bq.x, bq.y, bq.z, bq.w}, uc[4] = {c.x, c.y, c.z, c.w},
+                   ud[4] = {d.x, d.y, d.z, d.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 fa = unpack_hr(ua[k], f16), fb = unpack_hr(ub[k], f16), fc = unpack_hr(uc[k], f16), fd = unpack_hr(ud[k], f16);
+      o[k] = pack_hr(((fa.x + fb.x) + (fc.x + fd.x)) * 0.25f, ((fa.y + fb.y) + (fc.y + fd.y)) * 0.25f, f16);
+    }
+    reinterpret_cast<uint4*>(y + ((size_t)(b * Ho + ho) * Wo + wo) * yld)[cv] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+}  // namespace
+
+void launch_oaca_attention(const bf16* qkv, const bf16* pos, int pos_batch, const bf16* klay, const bf16* vlay, int n_layout,
+                           const View& out, int B, int T, int C, cudaStream_t s) {
+  LIDM_REQUIRE(C % DH == 0 && out.C == C && out.B == B && out.H * out.W == T && out.hl == 0 && out.hr == 0 && out.ld % 8 == 0,
+               "object-aware attention: output view");
+  LIDM_REQUIRE(n_layout >= 1 && n_layout <= LAY, "object-aware attention: 1..16 layout tokens");
+  LIDM_REQUIRE(pos_batch == 1 || pos_batch == B, "object-aware attention: positional tensor batch");
+#define LIDM_OACA(TT)                                                                                   \
+  do {                                                                                                  \
+    if (out.f16) launch_oaca_t<TT, true>(qkv, pos, pos_batch, klay, vlay, n_layout, out, B, C, s);       \
+    else launch_oaca_t<TT, false>(qkv, pos, pos_batch, klay, vlay, n_layout, out, B, C, s);              \
+  } while (0)
+  if (T == 256) LIDM_OACA(256);
+  else if (T == 128) LIDM_OACA(128);
+  else if (T == 64) LIDM_OACA(64);
+  else throw Error(-1, "object-aware attention supports feature maps of 64, 128 or 256 positions (attention_ds of the "
+                       "shipped layout2lidar configuration); got " + std::to_string(T));
+#undef LIDM_OACA
+}
+
+void launch_oaca_pos(const float* src, int Bsrc, int E, int Lt, const float* W, const float* bias, const float* gamma,
+                     const float* beta, int C, float scale, bf16* dst, int rows, int dst_ld, int dst_col, bool f16,
+                     cudaStream_t s) {
+  LIDM_REQUIRE(C % 32 == 0 && Lt >= 1, "positional projection shape");
+  const size_t sh = ((size_t)(C / 32) * Lt + 64) * sizeof(float);
+  LIDM_REQUIRE(sh <= 48 * 1024, "positional projection: group slab too large");
+  oaca_pos_kernel<<<dim3(32, Bsrc), 256, sh, s>>>(src, E, Lt, W, bias, gamma, beta, C, 1e-5f, scale, dst, rows, dst_ld, dst_col, f16);
+  LIDM_CUDA_CHECK(cudaGetLastError());
+  LIDM_COUNT_LAUNCH(1);
+}
+
+void launch_oaca_layout_kv(const float* xf_out, const float* cls, int B, int E, int Lt, const float* gamma, const float* beta,
+                           const float* Wc, const float* bc, int C, float scale, bf16* klay, bf16* vlay, bool f16,
+                           cudaStream_t s) {
+  LIDM_REQUIRE(E % 32 == 0 && Lt >= 1 && Lt <= LAY, "layout token projection shape");
+  const size_t sh = ((size_t)E * Lt + 64) * sizeof(float);
+  LIDM_REQUIRE(sh <= 48 * 1024, "layout token projection: shared memory");
+  oaca_layout_kv_kernel<<<B, 256, sh, s>>>(xf_out, cls, E, Lt, gamma, beta, 1e-5f, Wc, bc, C, scale, klay, vlay, f16);
+  LIDM_CUDA_CHECK(cudaGetLastError());
+  LIDM_COUNT_LAUNCH(1);
+}
+
+void launch_avgpool2(const View& x, const View& y, cudaStream_t s) {
+  LIDM_REQUIRE(x.hl + x.hr + y.hl + y.hr == 0 && y.H * 2 == x.H && y.W * 2 == x.W && y.C == x.C && y.B == x.B && x.C % 8 == 0 &&
+                   x.f16 == y.f16 && x.wpitch == 0 && y.wpitch == 0,
+               "average pooling shapes");
+  const int64_t total = (int64_t)y.B * y.H * y.W * (y.C / 8);
+  int64_t g = (total + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  avgpool2_kernel<<<(int)g, 256, 0, s>>>(x.p, x.B, x.H, x.W, x.ld, x.C, y.p, y.ld, x.f16);
+  LIDM_CUDA_CHECK(cudaGetLastError());
+  LIDM_COUNT_LAUNCH(1);
+}
+
+}  // namespace lidm

@@ -104,7 +104,8 @@ template <bool F16>
 __global__ void gn_apply_kernel(const bf16* __restrict__ x, int H, int W, int xhl, int xWp, int xld, bf16* __restrict__ y,
                                 int yhl, int yhr, int yWp, int yld, int C, int cpg, int groups,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
-                                const float* __restrict__ partials, int nchunks, int pix_per_cta) {
+                                const float* __restrict__ partials, int nchunks, int pix_per_cta,
+                                const float* __restrict__ film, int film_ld) {
   extern __shared__ float sh[];  // mean[groups], rstd[groups]
   const int b = blockIdx.y;
   const int HW = H * W;
@@ -129,9 +130,15 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int H, int W, int xh
   for (int j = 0; j < 8; ++j) {
     const int c = cv * 8 + j;
     const int g = c / cpg;
-    const float ga = __ldg(gamma + c) * sh[groups + g];
+    float ga = __ldg(gamma + c) * sh[groups + g];
+    float of = __ldg(beta + c) - sh[g] * ga;
+    if (film != nullptr) {     // FiLM: norm(h) * (1 + scale) + shift (object_cross_unet.py:268-272)
+      const float s1 = 1.f + __ldg(film + (size_t)b * film_ld + c);
+      ga *= s1;
+      of = fmaf(of, s1, __ldg(film + (size_t)b * film_ld + C + c));
+    }
     sc[j] = ga;
-    sf[j] = __ldg(beta + c) - sh[g] * ga;
+    sf[j] = of;
   }
   const int p0 = blockIdx.x * pix_per_cta;
   const int p1 = min(HW, p0 + pix_per_cta);
@@ -176,7 +183,8 @@ template <bool F16>
 __global__ void gn_apply_gst_kernel(const bf16* __restrict__ x, int H, int W, int xhl, int xWp, int xld, bf16* __restrict__ y,
                                     int yhl, int yhr, int yWp, int yld, int C, int cpg, int groups,
                                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
-                                    const float* __restrict__ gst, int gst_ld, int gst_slots, int pix_per_cta) {
+                                    const float* __restrict__ gst, int gst_ld, int gst_slots, int pix_per_cta,
+                                    const float* __restrict__ film, int film_ld) {
   extern __shared__ float sh[];  // mean[groups], rstd[groups]
   const int b = blockIdx.y;
   const int HW = H * W;
@@ -227,9 +235,15 @@ __global__ void gn_apply_gst_kernel(const bf16* __restrict__ x, int H, int W, in
   for (int j = 0; j < 8; ++j) {
     const int c = cv * 8 + j;
     const int g = c / cpg;
-    const float ga = __ldg(gamma + c) * sh[groups + g];
+    float ga = __ldg(gamma + c) * sh[groups + g];
+    float of = __ldg(beta + c) - sh[g] * ga;
+    if (film != nullptr) {     // FiLM: norm(h) * (1 + scale) + shift (object_cross_unet.py:268-272)
+      const float s1 = 1.f + __ldg(film + (size_t)b * film_ld + c);
+      ga *= s1;
+      of = fmaf(of, s1, __ldg(film + (size_t)b * film_ld + C + c));
+    }
     sc[j] = ga;
-    sf[j] = __ldg(beta + c) - sh[g] * ga;
+    sf[j] = of;
   }
   auto emit = [&](int pix, const uint4& u) {
     const int h = pix / W, w = pix - h * W;
@@ -265,7 +279,7 @@ template <int NV, bool F16>
 __global__ void __launch_bounds__(512)
 gn_fused_kernel(const bf16* __restrict__ x, int H, int W, int xhl, int xWp, int xld, bf16* __restrict__ y, int yhl, int yhr,
                 int yWp, int yld, int cpg, int gpc, const float* __restrict__ gamma, const float* __restrict__ beta,
-                float eps, int silu) {
+                float eps, int silu, const float* __restrict__ film, int film_ld, int C) {
   __shared__ float2 red[512];
   __shared__ float2 stat[32];   // (mean, rstd) per local group
   const int b = blockIdx.y;
@@ -329,9 +343,15 @@ gn_fused_kernel(const bf16* __restrict__ x, int H, int W, int xhl, int xWp, int 
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = c0 + cv * 8 + j;
-      const float ga = __ldg(gamma + c) * st.y;
+      float ga = __ldg(gamma + c) * st.y;
+      float of = __ldg(beta + c) - st.x * ga;
+      if (film != nullptr) {
+        const float s1 = 1.f + __ldg(film + (size_t)b * film_ld + c);
+        ga *= s1;
+        of = fmaf(of, s1, __ldg(film + (size_t)b * film_ld + C + c));
+      }
       sc[j] = ga;
-      sf[j] = __ldg(beta + c) - st.x * ga;
+      sf[j] = of;
     }
   }
 #pragma unroll
@@ -361,7 +381,7 @@ gn_fused_kernel(const bf16* __restrict__ x, int H, int W, int xhl, int xWp, int 
 }  // namespace
 
 void launch_groupnorm(const View& x, const View& y, const float* gamma, const float* beta, float eps, int groups,
-                      bool silu, float* partials, cudaStream_t s) {
+                      bool silu, float* partials, cudaStream_t s, const float* film, int film_ld) {
   const int C = x.C;
   LIDM_REQUIRE(C % 8 == 0 && C % groups == 0, "C must be a multiple of 8 and of the group count");
   LIDM_REQUIRE(y.C == C && y.B == x.B && y.H == x.H && y.W == x.W && x.f16 == y.f16, "GroupNorm in/out shape mismatch");
@@ -394,8 +414,8 @@ void launch_groupnorm(const View& x, const View& y, const float* gamma, const fl
       dim3 grid(groups / best, x.B);
 #define GN_FUSED(NV)                                                                                                  \
   do {                                                                                                                \
-    if (x.f16) gn_fused_kernel<NV, true><<<grid, 512, 0, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, y.hl, y.hr, y.Wp(), y.ld, cpg, best, gamma, beta, eps, silu ? 1 : 0); \
-    else gn_fused_kernel<NV, false><<<grid, 512, 0, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, y.hl, y.hr, y.Wp(), y.ld, cpg, best, gamma, beta, eps, silu ? 1 : 0); \
+    if (x.f16) gn_fused_kernel<NV, true><<<grid, 512, 0, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, y.hl, y.hr, y.Wp(), y.ld, cpg, best, gamma, beta, eps, silu ? 1 : 0, film, film_ld, C); \
+    else gn_fused_kernel<NV, false><<<grid, 512, 0, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, y.hl, y.hr, y.Wp(), y.ld, cpg, best, gamma, beta, eps, silu ? 1 : 0, film, film_ld, C); \
   } while (0)
       if (nv <= 4) GN_FUSED(4);
       else if (nv <= 8) GN_FUSED(8);
@@ -435,17 +455,17 @@ void launch_groupnorm(const View& x, const View& y, const float* gamma, const fl
   if (x.f16)
     gn_apply_kernel<true><<<grid, threads, shbytes, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, y.hl, y.hr, y.Wp(), y.ld, C,
                                                          cpg, groups, gamma, beta, eps, silu ? 1 : 0, partials, nchunks,
-                                                         pix_per_cta);
+                                                         pix_per_cta, film, film_ld);
   else
     gn_apply_kernel<false><<<grid, threads, shbytes, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, y.hl, y.hr, y.Wp(), y.ld, C,
                                                           cpg, groups, gamma, beta, eps, silu ? 1 : 0, partials, nchunks,
-                                                          pix_per_cta);
+                                                          pix_per_cta, film, film_ld);
   LIDM_CUDA_CHECK(cudaGetLastError());
   LIDM_COUNT_LAUNCH(2);
 }
 
 void launch_groupnorm_from_gstats(const View& x, const View& y, const float* gamma, const float* beta, float eps, int groups,
-                                  bool silu, cudaStream_t s) {
+                                  bool silu, cudaStream_t s, const float* film, int film_ld) {
   const int C = x.C;
   LIDM_REQUIRE(x.gst != nullptr && C % groups == 0 && (C / groups) % 8 == 0, "granule statistics need 8 | channels per group");
   LIDM_REQUIRE(y.C == C && y.B == x.B && y.H == x.H && y.W == x.W && x.ld % 8 == 0 && y.ld % 8 == 0, "GroupNorm shapes");
@@ -478,7 +498,7 @@ void launch_groupnorm_from_gstats(const View& x, const View& y, const float* gam
   gn_apply_gst_kernel<F><<<grid, threads, groups * 2 * sizeof(float), s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, y.hl, y.hr, \
                                                                           y.Wp(), y.ld, C, cpg, groups, gamma, beta, eps, \
                                                                           silu ? 1 : 0, x.gst, x.gst_ld, x.gst_slots,  \
-                                                                          pix_per_cta)
+                                                                          pix_per_cta, film, film_ld)
   if (x.f16) GN_GST(true);
   else GN_GST(false);
 #undef GN_GST

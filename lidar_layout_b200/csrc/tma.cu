@@ -53,10 +53,10 @@ CUtensorMap encode(const void* base, int rank, const cuuint64_t* dims, const cuu
 }  // namespace
 
 // 4-D map over a channels-last activation view: dims (C, Wp, H, B), box (box_c, box_w, box_h, 1).
-CUtensorMap make_tma_act(const View& v, int box_c, int box_w, int box_h, int swizzle_bytes) {
+CUtensorMap make_tma_act(const View& v, int box_c, int box_w, int box_h, int swizzle_bytes, int box_b) {
   cuuint64_t dims[4] = {(cuuint64_t)v.Cphys(), (cuuint64_t)v.Wp(), (cuuint64_t)v.H, (cuuint64_t)v.B};
   cuuint64_t str[3] = {(cuuint64_t)v.ld * 2, (cuuint64_t)v.ld * 2 * v.pitch(), (cuuint64_t)v.ld * 2 * v.pitch() * v.H};
-  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_b};
   return encode(v.p, 4, dims, str, box, swizzle_bytes);
 }
 

@@ -102,7 +102,11 @@ class DDIMSampler(object):
         if fused:
             # conditioning tensors for the on-device loop (+ their unconditional twins for classifier-free guidance)
             cond_kw = {}
-            if cond is not None:
+            if self.model.model.conditioning_key == "layout_crossattn":
+                if unconditional_conditioning is not None and unconditional_guidance_scale != 1.:
+                    raise NotImplementedError("classifier-free guidance is not wired for the layout U-Net")
+                cond_kw = dict(layout_cond=cond)
+            elif cond is not None:
                 c_concat, context = self.model.split_conditioning(cond)
                 guided = unconditional_conditioning is not None and unconditional_guidance_scale != 1.
                 uc_concat, uc_context = (self.model.split_conditioning(unconditional_conditioning) if guided

@@ -154,6 +154,13 @@ class LatentDiffusion:
     def apply_model(self, x_noisy, t, cond, return_ids=False):
         """ddpm.py:900-1000 -> DiffusionWrapper.forward (:2313) -> UNetModel.forward."""
         assert not return_ids
+        if self.model.conditioning_key == "layout_crossattn":
+            # DiffusionWrapper.forward (ddpm.py:2334-2335): the whole dict of LayoutTransformerEncoder outputs goes to
+            # LayoutDiffusionUNetModel.forward as layout_outputs
+            if not isinstance(cond, dict) or "xf_proj" not in cond:
+                raise ValueError("layout_crossattn conditioning is the dict LayoutTransformerEncoder.forward returns "
+                                 "(model.get_learned_conditioning(layout) in the reference)")
+            return self.engine.unet_forward(x_noisy, t, layout_cond=cond)
         c_concat, context = self.split_conditioning(cond)
         return self.engine.unet_forward(x_noisy, t, c_concat=c_concat, context=context)
 

@@ -27,10 +27,18 @@ def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
 
 def to_cconfig(cfg: LidmConfig) -> _lib.CConfig:
     u, a = cfg.unet, cfg.ae
-    if cfg.conditioning_key not in (None, "concat", "crossattn", "hybrid"):
+    if cfg.conditioning_key not in (None, "concat", "crossattn", "hybrid", "layout_crossattn"):
         raise NotImplementedError(f"conditioning_key {cfg.conditioning_key!r} is not on the B200 path "
-                                  "(supported: None, 'concat', 'crossattn', 'hybrid')")
-    if u.use_scale_shift_norm or u.resblock_updown or not u.conv_resample:
+                                  "(supported: None, 'concat', 'crossattn', 'hybrid', 'layout_crossattn')")
+    layout = u.unet_type == "layout"
+    if layout != (cfg.conditioning_key == "layout_crossattn"):
+        raise ValueError("conditioning_key 'layout_crossattn' goes with LayoutDiffusionUNetModel (and vice versa)")
+    if layout:
+        if not (u.use_scale_shift_norm and u.resblock_updown):
+            raise NotImplementedError("LayoutDiffusionUNetModel: use_scale_shift_norm and resblock_updown must be True (as shipped)")
+        if u.encoder_channels <= 0:
+            raise ValueError("LayoutDiffusionUNetModel needs encoder_channels")
+    elif u.use_scale_shift_norm or u.resblock_updown or not u.conv_resample:
         raise NotImplementedError("unsupported UNetModel option for the B200 path")
     if tuple(u.image_size) != tuple(cfg.image_size) or u.in_channels < cfg.channels:
         raise ValueError("unet image_size/in_channels must match the latent shape")
@@ -68,6 +76,9 @@ def to_cconfig(cfg: LidmConfig) -> _lib.CConfig:
     c.context_dim = int(u.context_dim or 0)
     c.transformer_depth = int(u.transformer_depth)
     c.ae_in_channels = int(a.in_channels)
+    c.unet_type = 1 if layout else 0
+    c.encoder_channels = int(u.encoder_channels)
+    c.num_attention_blocks = int(u.num_attention_blocks)
     return c
 
 
@@ -132,8 +143,48 @@ class Engine:
             L = int(context.shape[1])
         return c_concat, context, L
 
+    # ---- layout conditioning (LayoutDiffusionUNetModel) -------------------------------------------------
+    def set_layout_cond(self, cond: Dict[str, "torch.Tensor"]):
+        """Hand the output dict of LayoutTransformerEncoder.forward (layout_encoder.py:222-281) to the engine: everything
+        that depends on the conditioning only is computed once here (lidm_layout_set_cond).  Cached on the identity and
+        version of the dict's tensors, so a sampler that passes the same dict every step pays once."""
+        need = ("xf_proj", "xf_out", "obj_class_embedding", "obj_bbox_embedding")
+        for k in need:
+            if k not in cond:
+                raise KeyError(f"layout conditioning is missing {k!r}")
+        key = tuple((k, v.data_ptr(), v._version, tuple(v.shape)) for k, v in sorted(cond.items())
+                    if isinstance(v, torch.Tensor))
+        if getattr(self, "_layout_key", None) == key:
+            return
+        t = {k: _f32c(cond[k], k) for k in need}
+        B, E, Lt = t["xf_out"].shape
+        if E != self.cfg.unet.encoder_channels or t["xf_proj"].shape != (B, self.cfg.unet.time_embed_dim):
+            raise ValueError("layout conditioning: xf_out must be (B, encoder_channels, L), xf_proj (B, 4*model_channels)")
+        rows, embs, batches, keep = [], [], [], []
+        pre = "image_patch_bbox_embedding_for_resolution"
+        for k, v in cond.items():
+            if not k.startswith(pre):
+                continue
+            v = _f32c(v, k)
+            # the reference encoder repeat_interleaves one (1, E, L1) tensor over the batch (layout_encoder.py:251-257):
+            # detect that once and let the engine compute the positional projection a single time
+            same = bool(v.shape[0] > 1 and torch.equal(v[:1].expand_as(v), v))
+            vv = v[:1].contiguous() if same or v.shape[0] == 1 else v
+            if vv.shape[0] not in (1, B):
+                raise ValueError(f"{k}: batch {vv.shape[0]} does not match the conditioning batch {B}")
+            rows.append(int(k[len(pre):])); embs.append(vv.data_ptr()); batches.append(int(vv.shape[0])); keep.append(vv)
+        n = len(rows)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.lidm_layout_set_cond(
+                self._h, B, Lt, t["xf_proj"].data_ptr(), t["xf_out"].data_ptr(), t["obj_class_embedding"].data_ptr(),
+                t["obj_bbox_embedding"].data_ptr(), n, (c_int32 * max(n, 1))(*rows), (c_void_p * max(n, 1))(*embs),
+                (c_int32 * max(n, 1))(*batches), _stream_ptr(self.device)), self._h)
+        self._layout_key = key
+
     def unet_forward(self, x: torch.Tensor, t: torch.Tensor, c_concat: Optional[torch.Tensor] = None,
-                     context: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     context: Optional[torch.Tensor] = None, layout_cond: Optional[Dict] = None) -> torch.Tensor:
+        if layout_cond is not None:
+            self.set_layout_cond(layout_cond)
         x = _f32c(x, "x")
         t = t.to(device=x.device, dtype=torch.int64).contiguous()
         out = torch.empty_like(x)
@@ -158,9 +209,11 @@ class Engine:
                     noise: Optional[torch.Tensor] = None, temperature: float = 1.0, want_pred_x0: bool = False,
                     c_concat: Optional[torch.Tensor] = None, context: Optional[torch.Tensor] = None,
                     uncond_concat: Optional[torch.Tensor] = None, uncond_context: Optional[torch.Tensor] = None,
-                    guidance_scale: float = 1.0):
+                    guidance_scale: float = 1.0, layout_cond: Optional[Dict] = None):
         """Whole DDIM loop on the device.  timesteps ascending int64 [n]; table float32 [n,4].  Optional conditioning
         (concat tensor and / or cross-attention context) and classifier-free guidance against its unconditional twin."""
+        if layout_cond is not None:
+            self.set_layout_cond(layout_cond)
         x = _f32c(x_T, "x_T").clone()
         n = int(len(timesteps))
         ts = np.ascontiguousarray(timesteps, dtype=np.int64)

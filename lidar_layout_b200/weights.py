@@ -140,7 +140,88 @@ def _block_spec(spec, prefix, layers, ted):
             raise ValueError(kind)
 
 
+def layout_unet_blocks(cfg: UNetConfig):
+    """Walk LayoutDiffusionUNetModel.__init__ (reference lidm/modules/unets/object_cross_unet.py:742-912,
+    resblock_updown = True).  Layer tuples: ("conv", cin, cout), ("fres", cin, cout, updown) with updown in
+    {None, "up", "down"}, ("oaca", ch, ds)."""
+    mc = cfg.model_channels
+    inputs = [[("conv", cfg.in_channels, mc)]]
+    chans = [mc]
+    ch, ds = mc, 1
+    attn = lambda c, d: [("oaca", c, d)] * cfg.num_attention_blocks if d in cfg.attention_resolutions else []
+    for level, mult in enumerate(cfg.channel_mult):
+        for _ in range(cfg.num_res_blocks):
+            layers = [("fres", ch, mult * mc, None)]
+            ch = mult * mc
+            layers += attn(ch, ds)
+            inputs.append(layers)
+            chans.append(ch)
+        if level != len(cfg.channel_mult) - 1:
+            inputs.append([("fres", ch, ch, "down")])
+            chans.append(ch)
+            ds *= 2
+    middle = [("fres", ch, ch, None), ("oaca", ch, ds), ("fres", ch, ch, None)]
+    outputs = []
+    for level, mult in list(enumerate(cfg.channel_mult))[::-1]:
+        for i in range(cfg.num_res_blocks + 1):
+            ich = chans.pop()
+            layers = [("fres", ch + ich, mc * mult, None)]
+            ch = mc * mult
+            layers += attn(ch, ds)
+            if level and i == cfg.num_res_blocks:
+                layers.append(("fres", ch, ch, "up"))
+                ds //= 2
+            outputs.append(layers)
+    return inputs, middle, outputs, ch
+
+
+def _layout_block_spec(spec, prefix, layers, ted, enc_ch):
+    for j, layer in enumerate(layers):
+        p = f"{prefix}.{j}"
+        if layer[0] == "conv":
+            _conv(spec, p, layer[2], layer[1], 3, 3)
+        elif layer[0] == "fres":       # ResBlock with use_scale_shift_norm (object_cross_unet.py:176-251)
+            _, cin, cout, _ = layer
+            _norm(spec, p + ".in_layers.0", cin)
+            _conv(spec, p + ".in_layers.2", cout, cin, 3, 3)
+            _linear(spec, p + ".emb_layers.1", 2 * cout, ted)
+            _norm(spec, p + ".out_layers.0", cout)
+            _conv(spec, p + ".out_layers.3", cout, cout, 3, 3, zero_init=True)
+            if cin != cout:
+                _conv(spec, p + ".skip_connection", cout, cin, 1, 1)
+        elif layer[0] == "oaca":       # ObjectAwareCrossAttention (object_cross_unet.py:430-446, norm_first False)
+            ch = layer[1]
+            _conv1d(spec, p + ".qkv_projector", 3 * ch, ch)
+            _norm(spec, p + ".norm_for_qkv", ch)
+            _conv1d(spec, p + ".layout_content_embedding_projector", 2 * ch, enc_ch)
+            _conv1d(spec, p + ".layout_position_embedding_projector", ch, enc_ch)
+            _norm(spec, p + ".norm_for_obj_class_embedding", enc_ch)
+            _norm(spec, p + ".norm_for_layout_positional_embedding", ch)
+            _norm(spec, p + ".norm_for_image_patch_positional_embedding", ch)
+            _conv1d(spec, p + ".proj_out", ch, ch, zero_init=True)
+        else:  # pragma: no cover
+            raise ValueError(layer[0])
+
+
+def layout_unet_param_spec(cfg: UNetConfig, prefix: str = UNET_PREFIX) -> "OrderedDict[str, Tuple[tuple, str]]":
+    spec: OrderedDict = OrderedDict()
+    mc, ted = cfg.model_channels, cfg.time_embed_dim
+    _linear(spec, prefix + "time_embed.0", ted, mc)
+    _linear(spec, prefix + "time_embed.2", ted, ted)
+    inputs, middle, outputs, ch = layout_unet_blocks(cfg)
+    for i, layers in enumerate(inputs):
+        _layout_block_spec(spec, f"{prefix}input_blocks.{i}", layers, ted, cfg.encoder_channels)
+    _layout_block_spec(spec, f"{prefix}middle_block", middle, ted, cfg.encoder_channels)
+    for i, layers in enumerate(outputs):
+        _layout_block_spec(spec, f"{prefix}output_blocks.{i}", layers, ted, cfg.encoder_channels)
+    _norm(spec, prefix + "out.0", ch)
+    _conv(spec, prefix + "out.2", cfg.out_channels, mc, 3, 3, zero_init=True)
+    return spec
+
+
 def unet_param_spec(cfg: UNetConfig, prefix: str = UNET_PREFIX) -> "OrderedDict[str, Tuple[tuple, str]]":
+    if cfg.unet_type == "layout":
+        return layout_unet_param_spec(cfg, prefix)
     spec: OrderedDict = OrderedDict()
     mc, ted = cfg.model_channels, cfg.time_embed_dim
     _linear(spec, prefix + "time_embed.0", ted, mc)

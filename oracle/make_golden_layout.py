@@ -109,6 +109,69 @@ def main():
     print("wrote", path, f"{os.path.getsize(path) / 1e6:.2f} MB", len(out), "arrays")
 
 
+# --------------------------------------------------------------------------------------------------------------------
+# Runnable-width fixtures for the CUDA path (python -m oracle.make_golden_layout --unet): the reference
+# LayoutDiffusionUNetModel built from the product's config objects (tiny_layout: the shipped structure at 64 channels;
+# nuscenes_layout2lidar: the shipped models/lidm/nuscenes/layout2lidar/config.yaml), loaded STRICTLY with the product's
+# seeded state-dict (lidar_layout_b200.weights.random_state_dict: pins every key and shape), conditioned on the outputs of
+# the reference LayoutTransformerEncoder (seeded weights) for a synthetic layout.  Stored: x, t, the conditioning dict, eps.
+ENC_FULL = dict(layout_length=13, hidden_dim=256, output_dim=1024, num_layers=6, num_heads=8, use_final_ln=True,
+                num_classes_for_layout_object=9, mask_size_for_layout_object=32,
+                used_condition_types=["obj_class", "obj_bbox", "is_valid_obj"], feature_map_size=[8, 128],
+                use_positional_embedding=False, resolution_to_attention=[4, 2, 1], use_key_padding_mask=False,
+                not_use_layout_fusion_module=False)
+ENC_SMALL = dict(ENC_FULL, hidden_dim=64, output_dim=256, num_layers=2, num_heads=4)
+
+
+def main_unet():
+    from lidar_layout_b200 import config as C
+    from lidar_layout_b200.weights import UNET_PREFIX, random_state_dict
+    from oracle.layout_ref import synthetic_layout
+    mod = load_reference_module()
+    sys.path.insert(0, REF_ROOT)
+    from lidm.modules.unets.object_cross_unet import LayoutDiffusionUNetModel
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.set_num_threads(os.cpu_count())
+    try:
+        for name, cfg, enc_kw, B in (("layout_unet_small", C.tiny_layout(), ENC_SMALL, 3),
+                                     ("layout_unet_full", C.nuscenes_layout2lidar(), ENC_FULL, 2)):
+            u = cfg.unet
+            enc = mod.LayoutTransformerEncoder(**enc_kw).eval()
+            _seed_module(enc, 21, STD["enc"])
+            net = LayoutDiffusionUNetModel(
+                image_size=list(u.image_size), use_fp16=False, use_scale_shift_norm=True, in_channels=u.in_channels,
+                out_channels=u.out_channels, model_channels=u.model_channels, encoder_channels=u.encoder_channels,
+                num_head_channels=u.num_head_channels, num_heads=-1, num_heads_upsample=-1, num_res_blocks=u.num_res_blocks,
+                num_attention_blocks=u.num_attention_blocks, resblock_updown=True, attention_ds=list(u.attention_resolutions),
+                channel_mult=list(u.channel_mult), dropout=0.1, use_checkpoint=False,
+                use_positional_embedding_for_attention=True, attention_block_type="ObjectAwareCrossAttention").eval()
+            sd = random_state_dict(cfg, 0)
+            usd = {k[len(UNET_PREFIX):]: v for k, v in sd.items() if k.startswith(UNET_PREFIX)}
+            net.load_state_dict(usd, strict=True)            # every key and shape of the product's spec is the reference's
+            with torch.no_grad():
+                layout = synthetic_layout(B, 13, 9, seed=5)
+                cond = enc(layout)
+                g = torch.Generator().manual_seed(6)
+                x = torch.randn(B, u.in_channels, *u.image_size, generator=g)
+                t = torch.tensor([3, 500, 977][:B])
+                y = net(x, t, cond)
+            out = {"x": x.numpy(), "t": t.numpy(), "eps": y.numpy(), "layout": layout.numpy()}
+            for k, v in cond.items():
+                if k.startswith("image_patch_bbox_embedding"):
+                    assert torch.equal(v[:1].expand_as(v), v)
+                    v = v[:1]                                   # batch-broadcast by construction: store one row
+                out["cond/" + k] = v.numpy()
+            path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+            np.savez_compressed(path, **out)
+            print("wrote", path, f"{os.path.getsize(path) / 1e6:.2f} MB", "eps rms", float(y.pow(2).mean().sqrt()))
+    finally:
+        torch.Tensor.cuda = orig_cuda
+
+
 if __name__ == "__main__":
     sys.path.insert(0, ROOT)
-    main()
+    if "--unet" in sys.argv:
+        main_unet()
+    else:
+        main()

@@ -82,3 +82,24 @@ def test_layout_unet_bit_exact(gold):
     want = g["unet/y"]
     assert y.shape == want.shape == (3, 8, 8, 128) and np.isfinite(want).all() and float(np.abs(want).max()) > 1e-3
     np.testing.assert_array_equal(y.numpy(), want)
+
+
+@pytest.mark.parametrize("name", ["layout_unet_small", "layout_unet_full"])
+def test_runnable_layout_unet_fixtures(name):
+    """The fixtures the CUDA path is tested against (tiny_layout / the shipped layout2lidar structure, product-seeded
+    weights loaded strictly into the reference module) are reproduced by the oracle."""
+    from lidar_layout_b200 import config as C
+    from lidar_layout_b200.weights import UNET_PREFIX, random_state_dict
+    g = np.load(os.path.join(os.path.dirname(GOLD), name + ".npz"))
+    cfg = C.tiny_layout() if name.endswith("small") else C.nuscenes_layout2lidar()
+    u = cfg.unet
+    sd = {k[len(UNET_PREFIX):]: v for k, v in random_state_dict(cfg, 0).items() if k.startswith(UNET_PREFIX)}
+    B = g["x"].shape[0]
+    cond = {k[5:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("cond/")}
+    cond = {k: (v.expand(B, *v.shape[1:]) if k.startswith("image_patch") else v) for k, v in cond.items()}
+    y = LR.layout_unet_forward(sd, torch.from_numpy(g["x"]), torch.from_numpy(g["t"]), cond, model_channels=u.model_channels,
+                               channel_mult=u.channel_mult, num_res_blocks=u.num_res_blocks,
+                               attention_ds=u.attention_resolutions, image_size=u.image_size,
+                               num_head_channels=u.num_head_channels, num_attention_blocks=u.num_attention_blocks)
+    err = float((y - torch.from_numpy(g["eps"])).norm() / torch.from_numpy(g["eps"]).norm())
+    assert err < 1e-5, err
