@@ -102,7 +102,7 @@ class DDIMSampler(object):
         if fused:
             # conditioning tensors for the on-device loop (+ their unconditional twins for classifier-free guidance)
             cond_kw = {}
-            if self.model.model.conditioning_key == "layout_crossattn":
+            if getattr(getattr(self.model, "model", None), "conditioning_key", None) == "layout_crossattn":
                 if unconditional_conditioning is not None and unconditional_guidance_scale != 1.:
                     raise NotImplementedError("classifier-free guidance is not wired for the layout U-Net")
                 cond_kw = dict(layout_cond=cond)
