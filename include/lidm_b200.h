@@ -80,6 +80,9 @@ typedef struct lidm_config {
   int32_t unet_type;
   int32_t encoder_channels;
   int32_t num_attention_blocks;             /* 0 => 1 */
+  /* LayoutTransformerEncoder (cond_stage_config of layout2lidar; lidm/modules/encoders/layout_encoder.py:140-220):
+   * hidden_dim = encoder_channels, enc_out_dim = output_dim (= 4 * model_channels), transformer depth / heads, classes */
+  int32_t enc_layers, enc_heads, enc_out_dim, enc_num_classes;
 } lidm_config;
 
 /* Last error message for `h` (or, with h == NULL, for the calling thread's last failed lidm_create / stateless call). */
@@ -124,6 +127,16 @@ int lidm_unet_forward_cond(lidm_handle* h, const float* x, const int64_t* t, con
 int lidm_layout_set_cond(lidm_handle* h, int32_t B, int32_t n_layout, const float* xf_proj, const float* xf_out,
                          const float* obj_class_embedding, const float* obj_bbox_embedding, int32_t n_res,
                          const int32_t* res_rows, const float* const* patch_emb, const int32_t* patch_batch, void* stream);
+
+/* LatentDiffusion.get_learned_conditioning(layout) -> LayoutTransformerEncoder.forward
+ * (ddpm.py:558-569, lidm/modules/encoders/layout_encoder.py:222-281) for the shipped condition types (obj_class, obj_bbox,
+ * is_valid_obj), fp32.  layout: DEVICE (B, n_layout, 13) = [bbox 8 | bbox_2d 4 | class 1].  Outputs, DEVICE fp32:
+ * xf_proj (B, 4*model_channels); xf_out / obj_class_embedding / obj_bbox_embedding (B, encoder_channels, n_layout);
+ * patch_emb[i] (1, encoder_channels, L1) = image_patch_bbox_embedding_for_resolution{res_rows[i]} (one row: the reference
+ * repeats it over the batch).  Needs cond_stage_model.* in the loaded state-dict. */
+int lidm_layout_encode(lidm_handle* h, const float* layout, int32_t B, int32_t n_layout, float* xf_proj, float* xf_out,
+                       float* obj_class_embedding, float* obj_bbox_embedding, int32_t n_res, const int32_t* res_rows,
+                       float* const* patch_emb, void* stream);
 
 /* DDIMSampler.p_sample_ddim update arithmetic (lidm/models/diffusion/ddim.py:191-206), stateless:
  * pred_x0 = (x - sqrt(1-a_t) eps)/sqrt(a_t); x_prev = sqrt(a_prev) pred_x0 + sqrt(1-a_prev-sigma^2) eps + sigma noise T.

@@ -39,13 +39,14 @@ class CConfig(ctypes.Structure):
         ("ae_in_channels", c_int32),
         ("ae_precision", c_int32),
         ("unet_type", c_int32), ("encoder_channels", c_int32), ("num_attention_blocks", c_int32),
+        ("enc_layers", c_int32), ("enc_heads", c_int32), ("enc_out_dim", c_int32), ("enc_num_classes", c_int32),
     ]
 
 
 EXPORTS = [
     "lidm_last_error", "lidm_create", "lidm_destroy", "lidm_load_weight", "lidm_finalize_weights",
     "lidm_unet_forward", "lidm_unet_forward_cond", "lidm_ddim_step", "lidm_ddim_sample", "lidm_ddim_sample_cond",
-    "lidm_cfg_combine", "lidm_layout_set_cond", "lidm_vq_decode", "lidm_vq_encode", "lidm_vq_quantize", "lidm_image_shape",
+    "lidm_cfg_combine", "lidm_layout_set_cond", "lidm_layout_encode", "lidm_vq_decode", "lidm_vq_encode", "lidm_vq_quantize", "lidm_image_shape",
     "lidm_backproject", "lidm_to_uint8_image", "lidm_compact_points", "lidm_chamfer_nn", "lidm_op_circular_conv2d", "lidm_op_groupnorm", "lidm_op_qkv_attention_legacy",
     "lidm_launch_count", "lidm_profile_begin", "lidm_profile_end",
 ]
@@ -76,6 +77,8 @@ def load() -> ctypes.CDLL:
                                           c_float, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p, c_void_p,
                                           c_float, c_void_p]
     lib.lidm_cfg_combine.argtypes = [c_void_p, c_float, c_void_p, c_int64, c_void_p]
+    lib.lidm_layout_encode.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
+                                       POINTER(c_int32), POINTER(c_void_p), c_void_p]
     lib.lidm_layout_set_cond.argtypes = [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                          POINTER(c_int32), POINTER(c_void_p), POINTER(c_int32), c_void_p]
     lib.lidm_ddim_step.argtypes = [c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_float,

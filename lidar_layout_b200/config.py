@@ -62,6 +62,25 @@ class AEConfig:
 
 
 @dataclass
+class LayoutEncoderConfig:
+    """cond_stage_config of the layout-conditioned LiDM: LayoutTransformerEncoder.__init__
+    (reference lidm/modules/encoders/layout_encoder.py:140-220), shipped condition types only."""
+    layout_length: int = 13
+    hidden_dim: int = 256
+    output_dim: int = 1024
+    num_layers: int = 6
+    num_heads: int = 8
+    use_final_ln: bool = True
+    num_classes_for_layout_object: int = 9
+    feature_map_size: Tuple[int, int] = (8, 128)
+    resolution_to_attention: Tuple[int, ...] = (4, 2, 1)
+    used_condition_types: Tuple[str, ...] = ("obj_class", "obj_bbox", "is_valid_obj")
+    use_positional_embedding: bool = False
+    use_key_padding_mask: bool = False
+    not_use_layout_fusion_module: bool = False
+
+
+@dataclass
 class DatasetConfig:
     """`data.params.dataset` block (what range2pcd / range2xyz are called with, scripts/sample.py:29-35)."""
     size: Tuple[int, int] = (64, 1024)
@@ -100,6 +119,7 @@ class LidmConfig:
     unet: UNetConfig = field(default_factory=UNetConfig)
     ae: AEConfig = field(default_factory=AEConfig)
     dataset: DatasetConfig = field(default_factory=DatasetConfig)
+    layout_encoder: Optional[LayoutEncoderConfig] = None     # cond stage of layout_crossattn models
 
     @property
     def latent_shape(self) -> Tuple[int, int, int]:
@@ -166,6 +186,13 @@ def from_reference_dict(cfg: dict) -> LidmConfig:
         conditioning_key=conditioning_key,
         unet=unet, ae=ae,
     )
+    if isinstance(cond, dict) and str(cond.get("target", "")).endswith("layout_encoder.LayoutTransformerEncoder"):
+        le = LayoutEncoderConfig(**_pick(LayoutEncoderConfig, cond["params"]))
+        if set(le.used_condition_types) != {"obj_class", "obj_bbox", "is_valid_obj"} or le.use_positional_embedding \
+                or le.use_key_padding_mask or le.not_use_layout_fusion_module:
+            raise ValueError("LayoutTransformerEncoder: only the shipped options are supported (obj_class / obj_bbox / "
+                             "is_valid_obj, no positional embedding, no key padding mask)")
+        kw["layout_encoder"] = le
     ds = DatasetConfig()
     try:
         ds = DatasetConfig(**_pick(DatasetConfig, cfg["data"]["params"]["dataset"]))
@@ -201,6 +228,7 @@ def nuscenes_layout2lidar() -> LidmConfig:
                       unet=UNetConfig(image_size=(8, 128), unet_type="layout", model_channels=256, encoder_channels=256,
                                       num_head_channels=64, attention_resolutions=(8, 4, 2), channel_mult=(1, 2, 4),
                                       num_res_blocks=2, use_scale_shift_norm=True, resblock_updown=True, lib_name="ldm"),
+                      layout_encoder=LayoutEncoderConfig(),
                       dataset=DatasetConfig(size=(32, 1024), fov=(10.0, -30.0)))
 
 
@@ -212,6 +240,7 @@ def tiny_layout() -> LidmConfig:
                                       num_head_channels=64, attention_resolutions=(4, 2), channel_mult=(1, 2, 4),
                                       num_res_blocks=1, use_scale_shift_norm=True, resblock_updown=True, lib_name="ldm"),
                       ae=AEConfig(n_embed=512, ch=64, ch_mult=(1, 2, 2), strides=((1, 2), (2, 2)), num_res_blocks=1),
+                      layout_encoder=LayoutEncoderConfig(hidden_dim=64, output_dim=256, num_layers=2, num_heads=4),
                       dataset=DatasetConfig(size=(16, 512), fov=(10.0, -30.0)))
 
 

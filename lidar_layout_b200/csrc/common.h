@@ -178,6 +178,14 @@ void launch_oaca_layout_kv(const float* xf_out, const float* cls, int B, int E, 
                            const float* Wc, const float* bc, int C, float scale, bf16* klay, bf16* vlay, bool f16,
                            cudaStream_t s);
 void launch_avgpool2(const View& x, const View& y, cudaStream_t s);
+// LayoutTransformerEncoder.forward (layout_encoder.py:222-281), fp32, one CTA per sample.  layers_dev: device array of
+// n_layers x 12 float pointers {ln_1 g/b, c_qkv w/b, c_proj w/b, ln_2 g/b, c_fc w/b, mlp.c_proj w/b}.  Outputs (NCL fp32):
+// xf_proj (B,out_dim), xf_out / obj_class_embedding / obj_bbox_embedding (B,H,L).
+void launch_layout_encoder(const float* layout, int B, int L, int H, int heads, int n_layers, const void* layers_dev,
+                           const float* cls_emb, int n_classes, const float* be_w, const float* be_b, const float* bx_w,
+                           const float* bx_b, const float* fln_g, const float* fln_b, const float* tp_w, const float* tp_b,
+                           int out_dim, float* xf_proj, float* xf_out, float* cls_out, float* bbox_out, cudaStream_t s);
+void launch_patch_table(const float* be_w, const float* be_b, int H, int rows, int cols, float* out, cudaStream_t s);
 
 // ---- transformer pieces (transformer.cu) -------------------------------------------------------------------
 // nn.LayerNorm over the channel dimension of every pixel/token (eps 1e-5), bf16 in / bf16 out, fp32 statistics

@@ -216,6 +216,11 @@ struct lidm_handle {
   int64_t cond_gen = 0;                                   // bumps whenever the conditioning buffers move (CUDA-graph key)
   float* cond_xf_proj = nullptr;                          // (cond_B, ted)
   std::vector<void*> cond_owned;
+  // LayoutTransformerEncoder (cond_stage_model.*), fp32; packed when the state-dict carries it
+  bool has_layout_encoder = false;
+  void* lenc_layers = nullptr;                            // device array of n_layers x 12 float pointers
+  float *lenc_cls = nullptr, *lenc_be_w = nullptr, *lenc_be_b = nullptr, *lenc_bx_w = nullptr, *lenc_bx_b = nullptr,
+        *lenc_fln_g = nullptr, *lenc_fln_b = nullptr, *lenc_tp_w = nullptr, *lenc_tp_b = nullptr;
   std::unordered_map<std::string, DevTensor> raw;     // fp32 state-dict tensors on the device
   std::vector<void*> owned;                           // packed weight allocations
   // U-Net
@@ -2230,6 +2235,38 @@ void finalize(lidm_handle* h, bool use_ema) {
     }
   }
 
+  // ---- layout encoder (the cond stage of layout_crossattn models), fp32
+  h->has_layout_encoder = h->is_layout && h->raw.count("cond_stage_model.transformer_proj.weight") != 0;
+  if (h->has_layout_encoder) {
+    const std::string Cn = "cond_stage_model.";
+    const int Hd = cfg.encoder_channels;
+    LIDM_REQUIRE(cfg.enc_layers >= 0 && cfg.enc_heads >= 1 && cfg.enc_out_dim == ted && cfg.enc_num_classes >= 1,
+                 "layout encoder: enc_layers / enc_heads / enc_num_classes, and enc_out_dim must equal 4 * model_channels");
+    std::vector<const float*> ptrs;
+    for (int i = 0; i < cfg.enc_layers; ++i) {
+      const std::string p = Cn + "transform.resblocks." + std::to_string(i);
+      ptrs.push_back(pk.f32(p + ".ln_1.weight", Hd)); ptrs.push_back(pk.f32(p + ".ln_1.bias", Hd));
+      ptrs.push_back(pk.f32(p + ".attn.c_qkv.weight", (int64_t)3 * Hd * Hd)); ptrs.push_back(pk.f32(p + ".attn.c_qkv.bias", 3 * Hd));
+      ptrs.push_back(pk.f32(p + ".attn.c_proj.weight", (int64_t)Hd * Hd)); ptrs.push_back(pk.f32(p + ".attn.c_proj.bias", Hd));
+      ptrs.push_back(pk.f32(p + ".ln_2.weight", Hd)); ptrs.push_back(pk.f32(p + ".ln_2.bias", Hd));
+      ptrs.push_back(pk.f32(p + ".mlp.c_fc.weight", (int64_t)4 * Hd * Hd)); ptrs.push_back(pk.f32(p + ".mlp.c_fc.bias", 4 * Hd));
+      ptrs.push_back(pk.f32(p + ".mlp.c_proj.weight", (int64_t)4 * Hd * Hd)); ptrs.push_back(pk.f32(p + ".mlp.c_proj.bias", Hd));
+    }
+    h->lenc_layers = dev_alloc<const float*>(h, ptrs.size());
+    LIDM_CUDA_CHECK(cudaMemcpy(h->lenc_layers, ptrs.data(), ptrs.size() * sizeof(const float*), cudaMemcpyHostToDevice));
+    h->lenc_cls = pk.f32(Cn + "obj_class_embedding.weight", (int64_t)cfg.enc_num_classes * Hd);
+    h->lenc_be_w = pk.f32(Cn + "obj_bbox_embedding.weight", (int64_t)Hd * 4);
+    h->lenc_be_b = pk.f32(Cn + "obj_bbox_embedding.bias", Hd);
+    h->lenc_bx_w = pk.f32(Cn + "obj_bbox_encoding.weight", (int64_t)Hd * 8);
+    h->lenc_bx_b = pk.f32(Cn + "obj_bbox_encoding.bias", Hd);
+    if (h->raw.count(Cn + "final_ln.weight")) {
+      h->lenc_fln_g = pk.f32(Cn + "final_ln.weight", Hd);
+      h->lenc_fln_b = pk.f32(Cn + "final_ln.bias", Hd);
+    }
+    h->lenc_tp_w = pk.f32(Cn + "transformer_proj.weight", (int64_t)ted * Hd);
+    h->lenc_tp_b = pk.f32(Cn + "transformer_proj.bias", ted);
+  }
+
   // ---- first stage (decode side): its own numeric mode
   pk.precise = h->ae_prec == LIDM_PREC_BF16X3;
   pk.f16 = h->ae_prec == LIDM_PREC_FP16;
@@ -2689,6 +2726,28 @@ int lidm_layout_set_cond(lidm_handle* h, int32_t B, int32_t n_layout, const floa
       // content keys / values of the layout tokens (:505-520)
       launch_oaca_layout_kv(xf_out, obj_class_embedding, B, E, n_layout, w->n_cls.gamma, w->n_cls.beta, w->w_content,
                             w->b_content, C, scale, w->klay, w->vlay, f16, s);
+    }
+  });
+}
+
+int lidm_layout_encode(lidm_handle* h, const float* layout, int32_t B, int32_t n_layout, float* xf_proj, float* xf_out,
+                       float* obj_class_embedding, float* obj_bbox_embedding, int32_t n_res, const int32_t* res_rows,
+                       float* const* patch_emb, void* stream) {
+  return guarded(h, [&] {
+    require_ready(h, B);
+    if (!h->has_layout_encoder)
+      throw Error(LIDM_ERR_STATE, "no layout encoder weights were loaded (cond_stage_model.* missing from the state-dict)");
+    LIDM_REQUIRE(layout && xf_proj && xf_out && obj_class_embedding && obj_bbox_embedding && n_layout >= 1 && n_layout <= 16,
+                 "layout encoder tensors (1..16 layout tokens)");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const lidm_config& cfg = h->cfg;
+    launch_layout_encoder(layout, B, n_layout, cfg.encoder_channels, cfg.enc_heads, cfg.enc_layers, h->lenc_layers, h->lenc_cls,
+                          cfg.enc_num_classes, h->lenc_be_w, h->lenc_be_b, h->lenc_bx_w, h->lenc_bx_b, h->lenc_fln_g, h->lenc_fln_b,
+                          h->lenc_tp_w, h->lenc_tp_b, h->ted, xf_proj, xf_out, obj_class_embedding, obj_bbox_embedding, s);
+    for (int i = 0; i < n_res; ++i) {
+      LIDM_REQUIRE(res_rows[i] >= 1 && cfg.latent_h % res_rows[i] == 0 && patch_emb[i] != nullptr, "patch table resolution");
+      launch_patch_table(h->lenc_be_w, h->lenc_be_b, cfg.encoder_channels, res_rows[i], cfg.latent_w * res_rows[i] / cfg.latent_h,
+                         patch_emb[i], s);
     }
   });
 }

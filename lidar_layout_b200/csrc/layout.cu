@@ -359,7 +359,187 @@ __global__ void avgpool2_kernel(const bf16* __restrict__ x, int B, int H, int W,
   }
 }
 
+// ------------------------------------------------------------------------------------------------- layout encoder
+// LayoutTransformerEncoder.forward (lidm/modules/encoders/layout_encoder.py:222-281) with its Transformer /
+// ResidualAttentionBlock / QKVMultiheadAttention / MLP (:32-137) for the shipped condition types (obj_class, obj_bbox,
+// is_valid_obj; no positional embedding, no key padding mask): 13 tokens of width H per sample - one CTA per sample keeps
+// the token matrix in shared memory for the whole stack, fp32 throughout (runs once per conditioning).
+// out[l][n] (+)= act(bias[n] + sum_k W[n][k] in[l][k]): one warp per output feature, lanes over k (coalesced weight rows)
+template <int MODE>   // 0 store, 1 accumulate into out (residual), 2 store GELU (exact erf form)
+__device__ __forceinline__ void enc_linear(const float* __restrict__ in, int ldi, int K, const float* __restrict__ W,
+                                           const float* __restrict__ bias, int N, float* __restrict__ out, int ldo, int L) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int n = warp; n < N; n += nw) {
+    float acc[LAY];
+#pragma unroll
+    for (int l = 0; l < LAY; ++l) acc[l] = 0.f;
+    const float* wr = W + (size_t)n * K;
+    for (int k = lane; k < K; k += 32) {
+      const float wv = __ldg(wr + k);
+#pragma unroll
+      for (int l = 0; l < LAY; ++l)
+        if (l < L) acc[l] = fmaf(wv, in[l * ldi + k], acc[l]);
+    }
+#pragma unroll
+    for (int l = 0; l < LAY; ++l) {
+      float v = acc[l];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == l && l < L) {
+        v += bias[n];
+        if (MODE == 2) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+        if (MODE == 1) out[l * ldo + n] += v;
+        else out[l * ldo + n] = v;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void enc_layernorm(const float* __restrict__ x, float* __restrict__ y, int H, int L,
+                                              const float* __restrict__ g, const float* __restrict__ b) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int l = warp; l < L; l += nw) {
+    float s = 0.f;
+    for (int k = lane; k < H; k += 32) s += x[l * H + k];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)H;
+    float q = 0.f;
+    for (int k = lane; k < H; k += 32) { const float d = x[l * H + k] - mean; q += d * d; }
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / (float)H + 1e-5f);
+    for (int k = lane; k < H; k += 32) y[l * H + k] = (x[l * H + k] - mean) * rstd * g[k] + b[k];
+  }
+}
+
+struct EncLayerP { const float *ln1_g, *ln1_b, *qkv_w, *qkv_b, *proj_w, *proj_b, *ln2_g, *ln2_b, *fc_w, *fc_b, *fc2_w, *fc2_b; };
+
+__global__ void __launch_bounds__(512)
+layout_encoder_kernel(const float* __restrict__ layout, int L, int H, int heads, int n_layers, const EncLayerP* __restrict__ layers,
+                      const float* __restrict__ cls_emb, int n_classes, const float* __restrict__ be_w, const float* __restrict__ be_b,
+                      const float* __restrict__ bx_w, const float* __restrict__ bx_b, const float* __restrict__ fln_g,
+                      const float* __restrict__ fln_b, const float* __restrict__ tp_w, const float* __restrict__ tp_b, int out_dim,
+                      float* __restrict__ xf_proj, float* __restrict__ xf_out, float* __restrict__ cls_out, float* __restrict__ bbox_out) {
+  extern __shared__ float sh[];
+  float* x = sh;                    // [L][H] token stream
+  float* y = x + LAY * H;           // [L][H] LayerNorm output / attention output
+  float* big = y + LAY * H;         // [L][4H] qkv (3H) or MLP hidden (4H)
+  const int b = blockIdx.x;
+  const float* lay = layout + (size_t)b * L * 13;
+  // token embedding: class embedding + Linear(bbox_2d) + Linear(bbox) (layout_encoder.py:233-249)
+  for (int i = threadIdx.x; i < L * H; i += blockDim.x) {
+    const int l = i / H, k = i - l * H;
+    const float* t = lay + l * 13;
+    int c = (int)t[12];
+    c = c < 0 ? 0 : (c >= n_classes ? n_classes - 1 : c);
+    const float ce = cls_emb[(size_t)c * H + k];
+    float e2 = be_b[k];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) e2 = fmaf(be_w[k * 4 + j], t[8 + j], e2);
+    float e8 = bx_b[k];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) e8 = fmaf(bx_w[k * 8 + j], t[j], e8);
+    x[i] = ce + e2 + e8;
+    cls_out[((size_t)b * H + k) * L + l] = ce;
+    bbox_out[((size_t)b * H + k) * L + l] = e2;
+  }
+  __syncthreads();
+  const int ch = H / heads;
+  const float scale2 = rsqrtf((float)ch);            // (ch^-1/4)^2
+  for (int li = 0; li < n_layers; ++li) {
+    const EncLayerP P = layers[li];
+    enc_layernorm(x, y, H, L, P.ln1_g, P.ln1_b);
+    __syncthreads();
+    enc_linear<0>(y, H, H, P.qkv_w, P.qkv_b, 3 * H, big, 3 * H, L);
+    __syncthreads();
+    // QKVMultiheadAttention (layout_encoder.py:65-84): per head [q | k | v], softmax in fp32
+    for (int i = threadIdx.x; i < heads * L; i += blockDim.x) {
+      const int hd = i / L, t = i - hd * L;
+      const float* q = big + t * 3 * H + hd * 3 * ch;
+      float sc[LAY];
+      float mx = -INFINITY;
+      for (int s2 = 0; s2 < L; ++s2) {
+        const float* k = big + s2 * 3 * H + hd * 3 * ch + ch;
+        float a = 0.f;
+        for (int c = 0; c < ch; ++c) a = fmaf(q[c], k[c], a);
+        a *= scale2;
+        sc[s2] = a;
+        mx = fmaxf(mx, a);
+      }
+      float sum = 0.f;
+      for (int s2 = 0; s2 < L; ++s2) { sc[s2] = expf(sc[s2] - mx); sum += sc[s2]; }
+      const float inv = 1.f / sum;
+      for (int c = 0; c < ch; ++c) {
+        float a = 0.f;
+        for (int s2 = 0; s2 < L; ++s2) a = fmaf(sc[s2] * inv, big[s2 * 3 * H + hd * 3 * ch + 2 * ch + c], a);
+        y[t * H + hd * ch + c] = a;
+      }
+    }
+    __syncthreads();
+    enc_linear<1>(y, H, H, P.proj_w, P.proj_b, H, x, H, L);
+    __syncthreads();
+    enc_layernorm(x, y, H, L, P.ln2_g, P.ln2_b);
+    __syncthreads();
+    enc_linear<2>(y, H, H, P.fc_w, P.fc_b, 4 * H, big, 4 * H, L);
+    __syncthreads();
+    enc_linear<1>(big, 4 * H, 4 * H, P.fc2_w, P.fc2_b, H, x, H, L);
+    __syncthreads();
+  }
+  if (fln_g != nullptr) {
+    enc_layernorm(x, y, H, L, fln_g, fln_b);
+    __syncthreads();
+  } else {
+    for (int i = threadIdx.x; i < L * H; i += blockDim.x) y[i] = x[i];
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < L * H; i += blockDim.x) {
+    const int l = i / H, k = i - l * H;
+    xf_out[((size_t)b * H + k) * L + l] = y[i];
+  }
+  enc_linear<0>(y, H, H, tp_w, tp_b, out_dim, xf_proj + (size_t)b * out_dim, out_dim, 1);   // transformer_proj(x[:, 0])
+}
+
+// image_patch_bbox_embedding_for_resolution{rows} = Linear_bbox_emb(patch boxes) (layout_encoder.py:198-204, 251-257):
+// out (1, H, rows * cols), boxes (x0, y0, x1, y1) of the rows x cols patch grid in unit coordinates (float64 -> float32)
+__global__ void patch_table_kernel(const float* __restrict__ be_w, const float* __restrict__ be_b, int H, int rows, int cols,
+                                   float* __restrict__ out) {
+  const int n = rows * cols;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * n; i += gridDim.x * blockDim.x) {
+    const int k = i / n, pch = i - k * n;
+    const int pi = pch / cols, pj = pch - pi * cols;
+    const double di = 1.0 / rows, dj = 1.0 / cols;
+    const float box[4] = {(float)(dj * pj), (float)(di * pi), (float)(dj * (pj + 1)), (float)(di * (pi + 1))};
+    float e = be_b[k];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) e = fmaf(be_w[k * 4 + j], box[j], e);
+    out[i] = e;
+  }
+}
+
 }  // namespace
+
+void launch_layout_encoder(const float* layout, int B, int L, int H, int heads, int n_layers, const void* layers_dev,
+                           const float* cls_emb, int n_classes, const float* be_w, const float* be_b, const float* bx_w,
+                           const float* bx_b, const float* fln_g, const float* fln_b, const float* tp_w, const float* tp_b,
+                           int out_dim, float* xf_proj, float* xf_out, float* cls_out, float* bbox_out, cudaStream_t s) {
+  LIDM_REQUIRE(L >= 1 && L <= LAY && H % 32 == 0 && H % heads == 0, "layout encoder: 1..16 tokens, width a multiple of 32");
+  const size_t sh = (size_t)LAY * H * 6 * sizeof(float);
+  static size_t configured = 0;
+  if (sh > configured) {
+    LIDM_CUDA_CHECK(cudaFuncSetAttribute(layout_encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    configured = sh;
+  }
+  layout_encoder_kernel<<<B, 512, sh, s>>>(layout, L, H, heads, n_layers, reinterpret_cast<const EncLayerP*>(layers_dev), cls_emb,
+                                          n_classes, be_w, be_b, bx_w, bx_b, fln_g, fln_b, tp_w, tp_b, out_dim, xf_proj, xf_out,
+                                          cls_out, bbox_out);
+  LIDM_CUDA_CHECK(cudaGetLastError());
+  LIDM_COUNT_LAUNCH(1);
+}
+
+void launch_patch_table(const float* be_w, const float* be_b, int H, int rows, int cols, float* out, cudaStream_t s) {
+  const int total = H * rows * cols;
+  patch_table_kernel<<<(total + 255) / 256, 256, 0, s>>>(be_w, be_b, H, rows, cols, out);
+  LIDM_CUDA_CHECK(cudaGetLastError());
+  LIDM_COUNT_LAUNCH(1);
+}
 
 void launch_oaca_attention(const bf16* qkv, const bf16* pos, int pos_batch, const bf16* klay, const bf16* vlay, int n_layout,
                            const View& out, int B, int T, int C, cudaStream_t s) {

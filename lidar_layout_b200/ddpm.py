@@ -122,6 +122,14 @@ class LatentDiffusion:
         yield None
 
     # ---- per-step hook --------------------------------------------------------------------------------
+    @torch.no_grad()
+    def get_learned_conditioning(self, c):
+        """ddpm.py:558-569 for the layout-conditioned model: cond_stage_model(c) = LayoutTransformerEncoder.forward.
+        (The CLIP / rescaler encoders of the other conditioned models stay outside the path: hand apply_model their output.)"""
+        if self.model.conditioning_key != "layout_crossattn":
+            raise NotImplementedError("get_learned_conditioning is on the B200 path for layout_crossattn models only")
+        return self.engine.layout_encode(c.to(self.device))
+
     def split_conditioning(self, cond):
         """The dispatch of apply_model + DiffusionWrapper.forward (ddpm.py:900-909, 2313-2339) for the conditioning
         keys None / 'concat' / 'crossattn' / 'hybrid': cond (tensor, list or {'c_concat': [...], 'c_crossattn': [...]})

@@ -79,6 +79,12 @@ def to_cconfig(cfg: LidmConfig) -> _lib.CConfig:
     c.unet_type = 1 if layout else 0
     c.encoder_channels = int(u.encoder_channels)
     c.num_attention_blocks = int(u.num_attention_blocks)
+    le = cfg.layout_encoder
+    if layout and le is not None:
+        if le.hidden_dim != u.encoder_channels or le.output_dim != u.time_embed_dim:
+            raise ValueError("layout encoder: hidden_dim must equal the U-Net's encoder_channels, output_dim 4*model_channels")
+        c.enc_layers, c.enc_heads, c.enc_out_dim = int(le.num_layers), int(le.num_heads), int(le.output_dim)
+        c.enc_num_classes = int(le.num_classes_for_layout_object)
     return c
 
 
@@ -109,7 +115,7 @@ class Engine:
         with torch.cuda.device(self.device):
             for name, t in sd.items():
                 if not (name.startswith("model.diffusion_model.") or name.startswith("model_ema.")
-                        or name.startswith("first_stage_model.")):
+                        or name.startswith("first_stage_model.") or name.startswith("cond_stage_model.")):
                     continue
                 if name.startswith("first_stage_model.loss."):
                     continue
@@ -144,6 +150,34 @@ class Engine:
         return c_concat, context, L
 
     # ---- layout conditioning (LayoutDiffusionUNetModel) -------------------------------------------------
+    def layout_encode(self, layout: torch.Tensor) -> Dict[str, "torch.Tensor"]:
+        """LayoutTransformerEncoder.forward (layout_encoder.py:222-281): layout (B, L, 13) -> the conditioning dict."""
+        le = self.cfg.layout_encoder
+        if le is None:
+            raise ValueError("this model has no layout encoder configuration")
+        layout = _f32c(layout, "layout")
+        if layout.dim() != 3 or layout.shape[2] != 13:
+            raise ValueError(f"layout must be (B, L, 13) = [bbox 8 | bbox_2d 4 | class 1], got {tuple(layout.shape)}")
+        B, Lt, _ = layout.shape
+        E, dev = le.hidden_dim, layout.device
+        f = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+        out = {"xf_proj": f(B, le.output_dim), "xf_out": f(B, E, Lt), "obj_class_embedding": f(B, E, Lt),
+               "obj_bbox_embedding": f(B, E, Lt)}
+        rows = [int(r) for r in le.resolution_to_attention]
+        fh, fw = le.feature_map_size
+        tables = [f(1, E, r * int(fw / (fh / r))) for r in rows]
+        n = len(rows)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.lidm_layout_encode(
+                self._h, layout.data_ptr(), B, Lt, out["xf_proj"].data_ptr(), out["xf_out"].data_ptr(),
+                out["obj_class_embedding"].data_ptr(), out["obj_bbox_embedding"].data_ptr(), n, (c_int32 * max(n, 1))(*rows),
+                (c_void_p * max(n, 1))(*[t.data_ptr() for t in tables]), _stream_ptr(self.device)), self._h)
+        for r, t in zip(rows, tables):       # the reference repeat_interleaves the table over the batch: an expanded view
+            out[f"image_patch_bbox_embedding_for_resolution{r}"] = t.expand(B, -1, -1)
+        # is_valid_obj (layout_encoder.py:224,268): the reference keeps the class column's trailing dimension
+        out["key_padding_mask"] = (1 - (layout[..., 12:13] > 0).int()).bool()
+        return out
+
     def set_layout_cond(self, cond: Dict[str, "torch.Tensor"]):
         """Hand the output dict of LayoutTransformerEncoder.forward (layout_encoder.py:222-281) to the engine: everything
         that depends on the conditioning only is computed once here (lidm_layout_set_cond).  Cached on the identity and
@@ -165,6 +199,8 @@ class Engine:
         for k, v in cond.items():
             if not k.startswith(pre):
                 continue
+            if v.dim() == 3 and v.stride(0) == 0:          # an expanded (batch-broadcast) table: take its single row
+                v = v[:1]
             v = _f32c(v, k)
             # the reference encoder repeat_interleaves one (1, E, L1) tensor over the batch (layout_encoder.py:251-257):
             # detect that once and let the engine compute the positional projection a single time
@@ -180,6 +216,7 @@ class Engine:
                 t["obj_bbox_embedding"].data_ptr(), n, (c_int32 * max(n, 1))(*rows), (c_void_p * max(n, 1))(*embs),
                 (c_int32 * max(n, 1))(*batches), _stream_ptr(self.device)), self._h)
         self._layout_key = key
+        self._layout_refs = list(cond.values())     # keep the keyed tensors alive: their addresses cannot be recycled
 
     def unet_forward(self, x: torch.Tensor, t: torch.Tensor, c_concat: Optional[torch.Tensor] = None,
                      context: Optional[torch.Tensor] = None, layout_cond: Optional[Dict] = None) -> torch.Tensor:

@@ -344,6 +344,43 @@ def ae_encoder_param_spec(cfg: AEConfig, prefix: str = AE_PREFIX) -> "OrderedDic
     return spec
 
 
+COND_PREFIX = "cond_stage_model."
+
+
+def layout_encoder_param_spec(le, prefix: str = COND_PREFIX) -> "OrderedDict[str, Tuple[tuple, str]]":
+    """LayoutTransformerEncoder tensors (reference lidm/modules/encoders/layout_encoder.py:140-220 with its Transformer,
+    :32-137) for the shipped condition types; `le` is a config.LayoutEncoderConfig."""
+    spec: OrderedDict = OrderedDict()
+    H = le.hidden_dim
+    for i in range(le.num_layers):
+        p = f"{prefix}transform.resblocks.{i}"
+        _linear(spec, p + ".attn.c_qkv", 3 * H, H)
+        _linear(spec, p + ".attn.c_proj", H, H)
+        _norm(spec, p + ".ln_1", H)
+        _linear(spec, p + ".mlp.c_fc", 4 * H, H)
+        _linear(spec, p + ".mlp.c_proj", H, 4 * H)
+        _norm(spec, p + ".ln_2", H)
+    _linear(spec, prefix + "transformer_proj", le.output_dim, H)
+    spec[prefix + "obj_class_embedding.weight"] = ((le.num_classes_for_layout_object, H), "codebook")
+    _linear(spec, prefix + "obj_bbox_embedding", H, 4)
+    _linear(spec, prefix + "obj_bbox_encoding", H, 8)
+    if le.use_final_ln:
+        _norm(spec, prefix + "final_ln", H)
+    return spec
+
+
+def random_layout_encoder_state_dict(cfg: LidmConfig, seed: int = 0, as_torch: bool = True):
+    """Synthetic cond-stage tensors (LayoutTransformerEncoder), drawn from their own generator (the sampling-side
+    state-dict of `random_state_dict` does not depend on them)."""
+    rng = np.random.Generator(np.random.PCG64(seed + 104729))
+    out = OrderedDict((name, _draw(rng, shape, kind, 1.0, 1.0))
+                      for name, (shape, kind) in layout_encoder_param_spec(cfg.layout_encoder).items())
+    if as_torch:
+        import torch
+        return OrderedDict((k, torch.from_numpy(v)) for k, v in out.items())
+    return out
+
+
 def param_spec(cfg: LidmConfig):
     spec = unet_param_spec(cfg.unet)
     spec.update(ae_param_spec(cfg.ae))

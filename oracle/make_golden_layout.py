@@ -123,6 +123,17 @@ ENC_FULL = dict(layout_length=13, hidden_dim=256, output_dim=1024, num_layers=6,
 ENC_SMALL = dict(ENC_FULL, hidden_dim=64, output_dim=256, num_layers=2, num_heads=4)
 
 
+def enc_small_weights():
+    """The seeded encoder weights of the layout_unet_small fixture (seed 21, as main_unet draws them), rebuilt from the
+    product's own parameter spec: (LayoutEncoderConfig, {name without the cond_stage_model. prefix: tensor})."""
+    from lidar_layout_b200 import config as C
+    from lidar_layout_b200.weights import COND_PREFIX, layout_encoder_param_spec
+    from oracle.layout_ref import seeded_state_dict
+    le = C.tiny_layout().layout_encoder
+    shapes = {k[len(COND_PREFIX):]: shp for k, (shp, _) in layout_encoder_param_spec(le).items()}
+    return le, seeded_state_dict(shapes, 21, STD["enc"])
+
+
 def main_unet():
     from lidar_layout_b200 import config as C
     from lidar_layout_b200.weights import UNET_PREFIX, random_state_dict

@@ -115,3 +115,34 @@ def test_layout_needs_its_conditioning(built_lib):
         model.apply_model(x, torch.zeros(1, dtype=torch.long).cuda(), None)
     with pytest.raises(LidmError):
         model.engine.unet_forward(x, torch.zeros(1, dtype=torch.long).cuda())
+
+
+def test_layout_encoder_against_reference(built_lib):
+    """LatentDiffusion.get_learned_conditioning(layout) -> LayoutTransformerEncoder.forward on the device (fp32) against the
+    reference encoder's outputs stored in layout_unet_small.npz (weights rebuilt from the product's parameter spec)."""
+    import lidar_layout_b200 as L
+    from lidar_layout_b200.weights import COND_PREFIX
+    from oracle.make_golden_layout import enc_small_weights
+    cfg = C.tiny_layout()
+    g, cond = _load("layout_unet_small")
+    le, esd = enc_small_weights()
+    model = L.LatentDiffusion(cfg, use_ema=False)
+    model.load_state_dict({**random_state_dict(cfg, 0), **{COND_PREFIX + k: v for k, v in esd.items()}})
+    out = model.get_learned_conditioning(torch.from_numpy(g["layout"]))
+    for k in ("xf_proj", "xf_out", "obj_class_embedding", "obj_bbox_embedding"):
+        err = rel(out[k], g["cond/" + k])
+        print(f"layout encoder {k}: rel {err:.2e}")
+        assert err < 1e-5
+    for r in le.resolution_to_attention:
+        k = f"image_patch_bbox_embedding_for_resolution{r}"
+        assert out[k].shape[0] == g["layout"].shape[0] and rel(out[k][:1], g["cond/" + k]) < 1e-6
+    assert out["key_padding_mask"].shape == (3, 13, 1)
+    # the encoder's dict drives the U-Net exactly like the reference's: eps within the bf16 budget of the fixture
+    e = model.apply_model(torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda(), out)
+    assert rel(e, g["eps"]) < EPS_TOL_BF16
+    # a model without cond_stage_model.* weights says so
+    from lidar_layout_b200._lib import LidmError
+    bare = L.LatentDiffusion(cfg, use_ema=False)
+    bare.load_state_dict(random_state_dict(cfg, 0))
+    with pytest.raises(LidmError):
+        bare.get_learned_conditioning(torch.from_numpy(g["layout"]))

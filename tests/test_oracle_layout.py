@@ -103,3 +103,19 @@ def test_runnable_layout_unet_fixtures(name):
                                num_head_channels=u.num_head_channels, num_attention_blocks=u.num_attention_blocks)
     err = float((y - torch.from_numpy(g["eps"])).norm() / torch.from_numpy(g["eps"]).norm())
     assert err < 1e-5, err
+
+
+def test_encoder_spec_and_oracle_reproduce_the_unet_fixture_conditioning():
+    """layout_unet_small.npz stores the layout and the reference encoder's outputs: the product's parameter spec
+    (names, shapes) + the oracle reproduce them bit for bit."""
+    g = np.load(os.path.join(os.path.dirname(GOLD), "layout_unet_small.npz"))
+    from oracle.make_golden_layout import enc_small_weights
+    le, sd = enc_small_weights()
+    out = LR.layout_encoder_forward(sd, torch.from_numpy(g["layout"]), num_layers=le.num_layers, num_heads=le.num_heads,
+                                    used_condition_types=le.used_condition_types, feature_map_size=le.feature_map_size,
+                                    resolution_to_attention=le.resolution_to_attention)
+    for k in ("xf_proj", "xf_out", "obj_class_embedding", "obj_bbox_embedding"):
+        np.testing.assert_array_equal(out[k].numpy(), g["cond/" + k], err_msg=k)
+    for r in le.resolution_to_attention:
+        k = f"image_patch_bbox_embedding_for_resolution{r}"
+        np.testing.assert_array_equal(out[k][:1].numpy(), g["cond/" + k], err_msg=k)
