@@ -204,6 +204,8 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp < 4) {
     if (NG == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
@@ -465,9 +467,8 @@ void launch_f(const bf16* q, int q_ld, int q_col, const bf16* kv, int kv_ld, int
     LIDM_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = n_items < num_sms ? n_items : num_sms;     // one persistent CTA per SM
-  attention_d32_v5_kernel<NG, BKV_, POLYP, PP, F16><<<grid, L::THREADS, L::SMEM_TOTAL, s>>>(tmQ, tmKV, out.p, out.ld, T, q_col, k_col,
-                                                                                v_col, kv_rows, n_qblk, heads, n_items);
-  LIDM_CUDA_CHECK(cudaGetLastError());
+  launch_pdl(attention_d32_v5_kernel<NG, BKV_, POLYP, PP, F16>, dim3(grid), dim3(L::THREADS), L::SMEM_TOTAL, s, tmQ, tmKV, out.p,
+             out.ld, T, q_col, k_col, v_col, kv_rows, n_qblk, heads, n_items);
   LIDM_COUNT_LAUNCH(1);
 }
 

@@ -71,6 +71,22 @@ struct View {
   size_t pix_index(int b, int h, int w) const { return ((size_t)(b * H + h) * Wp() + (w + hl)); }
 };
 
+// Kernel launch with the programmatic-dependent-launch attribute (the kernel must call pdl_wait() before touching anything
+// an earlier kernel wrote).  LIDM_NO_PDL turns the attribute off (A/B runs): the same kernels then serialise normally.
+bool pdl_enabled();
+template <class... KArgs, class... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  if (pdl_enabled()) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
+  LIDM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+}
+
 // ---- TMA maps (cuTensorMapEncodeTiled through the runtime's driver entry point; no -lcuda link) -------
 CUtensorMap make_tma_act(const View& v, int box_c, int box_w, int box_h, int swizzle_bytes, int box_b = 1);
 CUtensorMap make_tma_3d(const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,

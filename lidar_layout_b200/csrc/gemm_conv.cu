@@ -139,6 +139,8 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                  // everything below reads / writes tensors of earlier kernels
+  pdl_launch_dependents();     // the next kernel may run its prologue while this one drains
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -558,9 +560,8 @@ void launch_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtens
     LIDM_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  conv_gemm_persist_kernel<BN, STAGES, F16><<<grid, L::THREADS, L::TOTAL, stream>>>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles,
-                                                                       use_tma_store);
-  LIDM_CUDA_CHECK(cudaGetLastError());
+  launch_pdl(conv_gemm_persist_kernel<BN, STAGES, F16>, dim3(grid), dim3(L::THREADS), L::TOTAL, stream, tmA, tmB, tmO, tmA2, p,
+             num_m_tiles, num_tiles, use_tma_store);
   LIDM_COUNT_LAUNCH(1);
 }
 

@@ -21,6 +21,8 @@ template <int NSUB, bool F16>
 __global__ void gn_stats_kernel(const bf16* __restrict__ x, int H, int W, int hl, int Wp, int ld, int C, int cpg,
                                 int groups, int pix_per_cta, float* __restrict__ partials, int nchunks) {
   extern __shared__ float sh[];  // [blockDim][NSUB][2]
+  pdl_wait();
+  pdl_launch_dependents();
   const int b = blockIdx.y;
   const int chunk = blockIdx.x;
   const int vec_per_pix = C >> 3;
@@ -107,6 +109,8 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int H, int W, int xh
                                 const float* __restrict__ partials, int nchunks, int pix_per_cta,
                                 const float* __restrict__ film, int film_ld) {
   extern __shared__ float sh[];  // mean[groups], rstd[groups]
+  pdl_wait();
+  pdl_launch_dependents();
   const int b = blockIdx.y;
   const int HW = H * W;
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
@@ -186,6 +190,8 @@ __global__ void gn_apply_gst_kernel(const bf16* __restrict__ x, int H, int W, in
                                     const float* __restrict__ gst, int gst_ld, int gst_slots, int pix_per_cta,
                                     const float* __restrict__ film, int film_ld) {
   extern __shared__ float sh[];  // mean[groups], rstd[groups]
+  pdl_wait();
+  pdl_launch_dependents();
   const int b = blockIdx.y;
   const int HW = H * W;
   const int gpg = cpg >> 3;      // granules per group
@@ -281,6 +287,8 @@ gn_fused_kernel(const bf16* __restrict__ x, int H, int W, int xhl, int xWp, int 
                 int yWp, int yld, int cpg, int gpc, const float* __restrict__ gamma, const float* __restrict__ beta,
                 float eps, int silu, const float* __restrict__ film, int film_ld, int C) {
   __shared__ float2 red[512];
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float2 stat[32];   // (mean, rstd) per local group
   const int b = blockIdx.y;
   const int c0 = blockIdx.x * gpc * cpg;
@@ -414,8 +422,8 @@ void launch_groupnorm(const View& x, const View& y, const float* gamma, const fl
       dim3 grid(groups / best, x.B);
 #define GN_FUSED(NV)                                                                                                  \
   do {                                                                                                                \
-    if (x.f16) gn_fused_kernel<NV, true><<<grid, 512, 0, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, y.hl, y.hr, y.Wp(), y.ld, cpg, best, gamma, beta, eps, silu ? 1 : 0, film, film_ld, C); \
-    else gn_fused_kernel<NV, false><<<grid, 512, 0, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, y.hl, y.hr, y.Wp(), y.ld, cpg, best, gamma, beta, eps, silu ? 1 : 0, film, film_ld, C); \
+    if (x.f16) launch_pdl(gn_fused_kernel<NV, true>, grid, dim3(512), 0, s, x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, y.hl, y.hr, y.Wp(), y.ld, cpg, best, gamma, beta, eps, silu ? 1 : 0, film, film_ld, C); \
+    else launch_pdl(gn_fused_kernel<NV, false>, grid, dim3(512), 0, s, x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, y.hl, y.hr, y.Wp(), y.ld, cpg, best, gamma, beta, eps, silu ? 1 : 0, film, film_ld, C); \
   } while (0)
       if (nv <= 4) GN_FUSED(4);
       else if (nv <= 8) GN_FUSED(8);
@@ -438,8 +446,8 @@ void launch_groupnorm(const View& x, const View& y, const float* gamma, const fl
   const size_t shstats = (size_t)threads * nsub * 2 * sizeof(float);
   const size_t shbytes = groups * 2 * sizeof(float);
 #define GN_STATS(NS, F)                                                                                              \
-  gn_stats_kernel<NS, F><<<grid, threads, shstats, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, C, cpg, groups, pix_per_cta, \
-                                                        partials, nchunks)
+  launch_pdl(gn_stats_kernel<NS, F>, grid, dim3(threads), shstats, s, x.p, x.H, x.W, x.hl, x.Wp(), x.ld, C, cpg, groups, \
+             pix_per_cta, partials, nchunks)
 #define GN_STATS_F(F)                                                                                                 \
   do {                                                                                                                \
     if (nsub == 8) GN_STATS(8, F);                                                                                    \
@@ -453,13 +461,13 @@ void launch_groupnorm(const View& x, const View& y, const float* gamma, const fl
 #undef GN_STATS
   LIDM_CUDA_CHECK(cudaGetLastError());
   if (x.f16)
-    gn_apply_kernel<true><<<grid, threads, shbytes, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, y.hl, y.hr, y.Wp(), y.ld, C,
-                                                         cpg, groups, gamma, beta, eps, silu ? 1 : 0, partials, nchunks,
-                                                         pix_per_cta, film, film_ld);
+    launch_pdl(gn_apply_kernel<true>, grid, dim3(threads), shbytes, s, x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, y.hl, y.hr,
+               y.Wp(), y.ld, C, cpg, groups, gamma, beta, eps, silu ? 1 : 0, (const float*)partials, nchunks, pix_per_cta, film,
+               film_ld);
   else
-    gn_apply_kernel<false><<<grid, threads, shbytes, s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, y.hl, y.hr, y.Wp(), y.ld, C,
-                                                          cpg, groups, gamma, beta, eps, silu ? 1 : 0, partials, nchunks,
-                                                          pix_per_cta, film, film_ld);
+    launch_pdl(gn_apply_kernel<false>, grid, dim3(threads), shbytes, s, x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, y.hl, y.hr,
+               y.Wp(), y.ld, C, cpg, groups, gamma, beta, eps, silu ? 1 : 0, (const float*)partials, nchunks, pix_per_cta, film,
+               film_ld);
   LIDM_CUDA_CHECK(cudaGetLastError());
   LIDM_COUNT_LAUNCH(2);
 }
@@ -495,10 +503,9 @@ void launch_groupnorm_from_gstats(const View& x, const View& y, const float* gam
   dim3 grid(nchunks, x.B);
   LIDM_REQUIRE(x.f16 == y.f16, "GroupNorm element formats");
 #define GN_GST(F)                                                                                                     \
-  gn_apply_gst_kernel<F><<<grid, threads, groups * 2 * sizeof(float), s>>>(x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, y.hl, y.hr, \
-                                                                          y.Wp(), y.ld, C, cpg, groups, gamma, beta, eps, \
-                                                                          silu ? 1 : 0, x.gst, x.gst_ld, x.gst_slots,  \
-                                                                          pix_per_cta, film, film_ld)
+  launch_pdl(gn_apply_gst_kernel<F>, grid, dim3(threads), groups * 2 * sizeof(float), s, x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, \
+             y.hl, y.hr, y.Wp(), y.ld, C, cpg, groups, gamma, beta, eps, silu ? 1 : 0, (const float*)x.gst, x.gst_ld,       \
+             x.gst_slots, pix_per_cta, film, film_ld)
   if (x.f16) GN_GST(true);
   else GN_GST(false);
 #undef GN_GST

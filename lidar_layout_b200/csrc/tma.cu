@@ -4,6 +4,11 @@
 
 namespace lidm {
 
+bool pdl_enabled() {
+  static const bool on = getenv("LIDM_NO_PDL") == nullptr;
+  return on;
+}
+
 namespace {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
