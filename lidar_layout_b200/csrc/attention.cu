@@ -118,31 +118,37 @@ namespace v5 {
 constexpr int KV_ST = 4;
 constexpr float RESCALE_LOG2 = 8.f;
 
-template <int NG, int BKV_>
+// HS (half split): every 128-row query tile is served by TWO softmax warpgroups, each owning 64 of the tile's 128 key
+// columns (the row max is exchanged through shared memory), i.e. four softmax warps per scheduler instead of two - the
+// exponential phase is bound by dependency stalls that two warps per scheduler cannot cover (ncu: top stall "wait").
+template <int NG, int BKV_, bool HS = false>
 struct Cfg {
   static constexpr int KB = BKV_ * 64;                        // bytes of one K (or V) tile
   static constexpr int OFF_Q = 0;                             // two buffers: the next work item's queries load early
   static constexpr int OFF_K = OFF_Q + 2 * NG * Q_BYTES;
   static constexpr int OFF_V = OFF_K + KV_ST * KB;
   static constexpr int OFF_ONES = OFF_V + KV_ST * KB;          // constant second N-atom of the P*V B operand (row sums)
-  static constexpr int OFF_BAR = OFF_ONES + KB;
+  static constexpr int OFF_XMAX = OFF_ONES + KB;                // HS: [parity][group][half][128 rows] half-row maxima
+  static constexpr int OFF_BAR = OFF_XMAX + (HS ? 2 * NG * 2 * 128 * 4 : 0);
   static constexpr int SMEM_TOTAL = OFF_BAR + 512 + 1024;
+  static constexpr int SPLIT = HS ? 2 : 1;                      // softmax warpgroups per query tile
   static constexpr uint32_t P_COL = NG * BKV_;
   static constexpr uint32_t O_COL = P_COL + NG * (BKV_ / 2);
   static constexpr uint32_t O_STRIDE = 64;                    // 32 columns of O, column 32 = row sum (N = 48 P*V), padding
   static constexpr uint32_t TMEM_COLS = (O_COL + NG * O_STRIDE) <= 256 ? 256 : 512;
-  static constexpr int THREADS = 128 + NG * 128;
-  static constexpr int NCH = BKV_ / 32;                       // 32-column chunks per S row
+  static constexpr int THREADS = 128 + NG * 128 * SPLIT;
+  static constexpr int NCH = BKV_ / 32 / SPLIT;               // 32-column chunks of an S row per softmax thread
   static_assert(O_COL + NG * O_STRIDE <= 512, "TMEM budget");
   static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
 };
 
-template <int NG, int BKV_, int POLYP, bool PP, bool F16>
-__global__ void __launch_bounds__((Cfg<NG, BKV_>::THREADS), 1)
+template <int NG, int BKV_, int POLYP, bool PP, bool F16, bool HS>
+__global__ void __launch_bounds__((Cfg<NG, BKV_, HS>::THREADS), 1)
 attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                         bf16* __restrict__ out, int out_ld, int T, int q_col, int k_col, int v_col, int kv_len,
                         int n_qblk, int heads, int n_items) {
-  using L = Cfg<NG, BKV_>;
+  using L = Cfg<NG, BKV_, HS>;
+  static_assert(!HS || (!PP && BKV_ == 128), "half split: free-running groups, 128-key tiles");
   // Row sums on the tensor pipe: the P*V product runs with N = 48, the B operand's second 32-column atom being a constant
   // tile whose first column is all ones, so column 32 of O accumulates sum_k P[row][k] (of the bf16-rounded P the
   // numerator uses) for free - an N = 48 instruction costs what N = 32 does - and the softmax warps drop one FADD2
@@ -183,8 +189,8 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     prefetch_tensormap(&tmKV);
     for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], NG); }
     for (int s = 0; s < KV_ST; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], NG); }
-    for (int g = 0; g < NG; ++g) { mbar_init(&s_ready[g], 1); mbar_init(&s_free[g], 4); mbar_init(&stagger[g], 4); }
-    for (int i = 0; i < NG; ++i) { mbar_init(&p_ready[i], 4); mbar_init(&pv_done[i], 1); }
+    for (int g = 0; g < NG; ++g) { mbar_init(&s_ready[g], 1); mbar_init(&s_free[g], 4 * L::SPLIT); mbar_init(&stagger[g], 4 * L::SPLIT); }
+    for (int i = 0; i < NG; ++i) { mbar_init(&p_ready[i], 4 * L::SPLIT); mbar_init(&pv_done[i], 1); }
     for (int i = 0; i < 8; ++i) mbar_init(&xu_go[i], 1);
     fence_barrier_init();
   }
@@ -208,7 +214,8 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   pdl_launch_dependents();
 
   if (warp < 4) {
-    if (NG == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (HS) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    else if (NG == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
       if (lane == 0) {
         auto load_q = [&](int it) {
@@ -294,13 +301,17 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
     }
   } else {
-    if (NG == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-    const int g = (warp - 4) >> 2;                 // softmax group = query tile
+    if (HS) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    else if (NG == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    const int g = (warp - 4) / (4 * L::SPLIT);     // softmax group = query tile
+    const int half = HS ? ((warp - 4) >> 2) & 1 : 0;   // which 64 of the tile's 128 key columns this warpgroup owns
     const int qd = warp & 3;                       // TMEM lane quadrant
     const int row = qd * 32 + lane;                // row inside the 128-row tile
-    const uint32_t tS = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + g * BKV_;
+    const int col0 = half * (BKV_ / 2);            // first key column of this thread inside a K/V tile
+    const uint32_t tS = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + g * BKV_ + col0;
     const uint32_t tO = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + L::O_COL + g * L::O_STRIDE;
-    const uint32_t tP = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + L::P_COL + g * (BKV_ / 2);
+    const uint32_t tP = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + L::P_COL + g * (BKV_ / 2) + col0 / 2;
+    float* xmax = reinterpret_cast<float*>(smem + L::OFF_XMAX);
     constexpr float LOG2E = 1.4426950408889634f;
     int n = 0;                                     // cumulative tile index over this CTA's items (barrier phases)
     const bool restagger = nkv >= 8;
@@ -313,6 +324,7 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     bool pending = false;
     float l = 0.f;
     auto item_epilogue = [&]() {
+      if (HS && half != 0) return;                   // the partner warpgroup stores the tile
       uint32_t o[32];
       tmem_ld_32x32b_x32(tO, o);
       if (MMA_ROWSUM) l = __uint_as_float(tmem_ld_32x32b_x1(tO + 32));
@@ -346,7 +358,7 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[g]);      // S_g(j+1) may overwrite the TMEM buffer now
       if (kv_len - j * BKV_ < BKV_) {               // ragged last tile (cross-attention context): mask the padding keys
-        const int valid = kv_len - j * BKV_;
+        const int valid = kv_len - j * BKV_ - col0;
 #pragma unroll
         for (int c = 0; c < L::NCH; ++c) {
 #pragma unroll
@@ -365,7 +377,15 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           m3 = max3(m3, __uint_as_float(sv[c][8 * i + 6]), __uint_as_float(sv[c][8 * i + 7]));
         }
       }
-      const float r = max3(fmaxf(m0, m1), m2, m3);
+      float r = max3(fmaxf(m0, m1), m2, m3);
+      if (HS) {
+        // the row max over all 128 keys: swap half-row maxima with the partner warp (same lane quadrant, other half);
+        // parity double-buffered, one 64-thread named barrier per (group, quadrant)
+        float* xm = xmax + (((n & 1) * NG + g) * 2) * 128;
+        xm[half * 128 + row] = r;
+        named_bar_sync(1 + g * 4 + qd, 64);
+        r = fmaxf(r, xm[(half ^ 1) * 128 + row]);
+      }
       if (j == 0) {
         m = r;
       } else if (__any_sync(0xffffffffu, (r - m) * LOG2E > RESCALE_LOG2)) {
@@ -374,18 +394,20 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         tcgen05_fence_after();
         const float mn = fmaxf(m, r);
         const float alpha = ex2((m - mn) * LOG2E);
-        uint32_t o[32];
-        tmem_ld_32x32b_x32(tO, o);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-        tmem_st_32x32b_x32(tO, o);
-        if (MMA_ROWSUM) {
-          const uint32_t lr = tmem_ld_32x32b_x1(tO + 32);
+        if (!HS || half == 0) {       // both halves take the same decision (same rows, same maxima); one rescales O
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(tO, o);
           tmem_ld_wait();
-          tmem_st_32x32b_x1(tO + 32, __float_as_uint(__uint_as_float(lr) * alpha));
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_32x32b_x32(tO, o);
+          if (MMA_ROWSUM) {
+            const uint32_t lr = tmem_ld_32x32b_x1(tO + 32);
+            tmem_ld_wait();
+            tmem_st_32x32b_x1(tO + 32, __float_as_uint(__uint_as_float(lr) * alpha));
+          }
+          tmem_st_wait();
         }
-        tmem_st_wait();
         lcur *= alpha;
         m = mn;
       }
@@ -405,9 +427,16 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       uint32_t pkk[32];
 #pragma unroll
       for (int c = 0; c < L::NCH; ++c) {
-        uint32_t* pk = &pkk[(c & 1) * 16];
+        uint32_t* pk = &pkk[HS ? 0 : (c & 1) * 16];
         exp_chunk<POLYP, !MMA_ROWSUM, F16>(sv[c], mb, pk, s0, s1, s2, s3);
-        if (c & 1) {
+        if (HS) {
+          // half split: 16 columns (32 keys) per store keeps the packed pairs out of the register budget of 96
+          if (c == 0 && n > 0) {
+            mbar_wait(&pv_done[g], (n - 1) & 1);
+            tcgen05_fence_after();
+          }
+          tmem_st_32x32b_x16(tP + c * 16, pk);
+        } else if (c & 1) {
           if (c == 1 && n > 0) {
             // the previous P*V of this group (the previous tile's, or the previous item's last) must have drained P
             // before it is overwritten; by now half of this tile's exponentials are done, so the wait is normally free
@@ -416,7 +445,7 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           }
           tmem_st_32x32b_x32(tP + (c >> 1) * 32, pkk);   // 64 keys = 32 columns of bf16 pairs
         }
-        if (!PINGPONG && c == L::NCH / NG - 1 + (L::NCH / NG == 0) && j == 0 && (it == 0 || restagger) && g + 1 < NG && lane == 0)
+        if (!PINGPONG && c == (HS ? 0 : L::NCH / NG - 1 + (L::NCH / NG == 0)) && j == 0 && (it == 0 || restagger) && g + 1 < NG && lane == 0)
           mbar_arrive(&stagger[g + 1]);
       }
       if (PINGPONG && lane == 0) mbar_arrive(&xu_go[(g == 0 ? 4 : 0) + qd]);   // hand the MUFU unit to the partner warp
@@ -445,13 +474,13 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 }
 
 // q: (B, T, q_ld) rows with the heads at columns q_col + head*32; k / v: (B, kv_rows, kv_ld) rows at columns k_col / v_col.
-template <int NG, int BKV_, int POLYP, bool PP, bool F16>
+template <int NG, int BKV_, int POLYP, bool PP, bool F16, bool HS = false>
 void launch_f(const bf16* q, int q_ld, int q_col, const bf16* kv, int kv_ld, int k_col, int v_col, int kv_rows, const View& out,
             int B, int T, int heads, cudaStream_t s) {
-  using L = Cfg<NG, BKV_>;
+  using L = Cfg<NG, BKV_, HS>;
   static bool configured = false;
   if (!configured) {
-    LIDM_CUDA_CHECK(cudaFuncSetAttribute(attention_d32_v5_kernel<NG, BKV_, POLYP, PP, F16>,
+    LIDM_CUDA_CHECK(cudaFuncSetAttribute(attention_d32_v5_kernel<NG, BKV_, POLYP, PP, F16, HS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM_TOTAL));
     configured = true;
   }
@@ -467,16 +496,16 @@ void launch_f(const bf16* q, int q_ld, int q_col, const bf16* kv, int kv_ld, int
     LIDM_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = n_items < num_sms ? n_items : num_sms;     // one persistent CTA per SM
-  launch_pdl(attention_d32_v5_kernel<NG, BKV_, POLYP, PP, F16>, dim3(grid), dim3(L::THREADS), L::SMEM_TOTAL, s, tmQ, tmKV, out.p,
+  launch_pdl(attention_d32_v5_kernel<NG, BKV_, POLYP, PP, F16, HS>, dim3(grid), dim3(L::THREADS), L::SMEM_TOTAL, s, tmQ, tmKV, out.p,
              out.ld, T, q_col, k_col, v_col, kv_rows, n_qblk, heads, n_items);
   LIDM_COUNT_LAUNCH(1);
 }
 
-template <int NG, int BKV_, int POLYP, bool PP = (NG == 2)>
+template <int NG, int BKV_, int POLYP, bool PP = (NG == 2), bool HS = false>
 void launch(const bf16* q, int q_ld, int q_col, const bf16* kv, int kv_ld, int k_col, int v_col, int kv_rows, const View& out,
             int B, int T, int heads, cudaStream_t s) {
-  if (out.f16) launch_f<NG, BKV_, POLYP, PP, true>(q, q_ld, q_col, kv, kv_ld, k_col, v_col, kv_rows, out, B, T, heads, s);
-  else launch_f<NG, BKV_, POLYP, PP, false>(q, q_ld, q_col, kv, kv_ld, k_col, v_col, kv_rows, out, B, T, heads, s);
+  if (out.f16) launch_f<NG, BKV_, POLYP, PP, true, HS>(q, q_ld, q_col, kv, kv_ld, k_col, v_col, kv_rows, out, B, T, heads, s);
+  else launch_f<NG, BKV_, POLYP, PP, false, HS>(q, q_ld, q_col, kv, kv_ld, k_col, v_col, kv_rows, out, B, T, heads, s);
 }
 
 }  // namespace v5
@@ -619,8 +648,10 @@ void launch_attention_d32_packed(const bf16* qkv, const View& out, int B, int T,
   // stays available as the PP template flag and serves the single-tile cross-attention items.  Odd multiples of 128
   // (T = 128: the 4x32 level) take one query tile per item; the persistent kernel beats a one-tile-per-CTA kernel with
   // two CTAs per SM there too (35.4 against 39.5 us at B = 64).
+  static const int hs = getenv("LIDM_ATTN_HS") ? atoi(getenv("LIDM_ATTN_HS")) : 0;
   if (T % 256 == 0) {
-    if (poly) v5::launch<2, 128, 2, false>(LIDM_ATTN_ARGS);
+    if (hs) v5::launch<2, 128, 2, false, true>(LIDM_ATTN_ARGS);
+    else if (poly) v5::launch<2, 128, 2, false>(LIDM_ATTN_ARGS);
     else v5::launch<2, 128, 0, false>(LIDM_ATTN_ARGS);
   } else {
     if (poly) v5::launch<1, 128, 2, false>(LIDM_ATTN_ARGS);

@@ -904,6 +904,7 @@ struct Builder {
       GemmEpilogue ep;
       ep.bias = a.qkv.bias;
       ep.out = qkv;
+      ep.out.gst = nullptr;        // q | k | v feed the attention kernel, never a GroupNorm: no statistics pass
       gemm(g, taps_1x1(), a.qkv, ep);
     }
     release(bg);

@@ -21,6 +21,9 @@ namespace lidm {
 
 namespace {
 
+#ifndef LIDM_EPI16
+#define LIDM_EPI16 0
+#endif
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
@@ -98,7 +101,9 @@ struct PersistLayout {
   static constexpr uint32_t ACC_COLS = BN;                          // TMEM columns per accumulator buffer
   static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   // epilogue warps: 4 cover the 128 TMEM lanes; wide tiles use two such groups, each draining half of the columns
-  static constexpr int EPI_WARPS = BN >= 64 ? 8 : 4;
+  // (BN = 256: sixteen - four per scheduler, 64 columns per thread: the short-K 1x1 GEMMs are bound by the epilogue's
+  // dependent chain TMEM load -> bias/residual -> pack -> staging store, which two warps per scheduler do not cover)
+  static constexpr int EPI_WARPS = BN >= 256 ? LIDM_EPI16 * 8 + 8 : (BN >= 64 ? 8 : 4);
   static constexpr int EPI_THREADS = EPI_WARPS * 32;
   static constexpr int THREADS = 64 + EPI_THREADS;
   static constexpr int COLS = BN / (EPI_WARPS / 4);                 // columns drained by one epilogue thread
@@ -252,7 +257,7 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           // Fast path (bf16 output through TMA stores): the residual row is requested before the accumulator is
           // even ready, the whole accumulator row is pulled out of TMEM with back-to-back loads and one wait, and
           // the TMEM buffer is handed back to the MMA warp before any arithmetic or store happens.
-          constexpr int HALF = L::COLS > 64 ? 64 : L::COLS;   // columns per register batch
+          constexpr int HALF = L::EPI_WARPS == 16 ? 32 : (L::COLS > 64 ? 64 : L::COLS);   // columns per register batch
           constexpr int NH = L::COLS / HALF;
           constexpr int NCH = HALF / 32;
           const bool has_res = p.res != nullptr && b_ok;

@@ -14,15 +14,24 @@ if os.path.exists(path):
     os.unlink(path)
 which = sys.argv[2] if len(sys.argv) > 2 else "uncond"
 L = int(sys.argv[3]) if len(sys.argv) > 3 else 4
-cfg = {"uncond": C.kitti_uncond, "cam2lidar": C.kitti_cam2lidar, "sem2lidar": C.kitti_sem2lidar}[which]()
+cfg = {"uncond": C.kitti_uncond, "cam2lidar": C.kitti_cam2lidar, "sem2lidar": C.kitti_sem2lidar,
+       "layout2lidar": C.nuscenes_layout2lidar}[which]()
 eng = Engine(cfg).load_state_dict(random_state_dict(cfg, 0))
-x = torch.randn(B, 8, 16, 128, device="cuda")
+x = torch.randn((B,) + tuple(cfg.latent_shape), device="cuda")
 t = torch.full((B,), 501, dtype=torch.long, device="cuda")
 kw = {}
 if which == "cam2lidar":
     kw["context"] = torch.randn(B, L, cfg.unet.context_dim, device="cuda")
 if which == "sem2lidar":
     kw["c_concat"] = torch.randn(B, cfg.unet.in_channels - 8, 16, 128, device="cuda")
+if which == "layout2lidar":
+    E = cfg.unet.encoder_channels
+    cond = {"xf_proj": 0.1 * torch.randn(B, cfg.unet.time_embed_dim, device="cuda")}
+    for k in ("xf_out", "obj_class_embedding", "obj_bbox_embedding"):
+        cond[k] = torch.randn(B, E, 13, device="cuda")
+    for r in (4, 2, 1):
+        cond[f"image_patch_bbox_embedding_for_resolution{r}"] = torch.randn(1, E, 16 * r * r, device="cuda")
+    kw["layout_cond"] = cond
 for _ in range(3):
     eng.unet_forward(x, t, **kw)
 torch.cuda.synchronize()
