@@ -83,6 +83,14 @@ typedef struct lidm_config {
   /* LayoutTransformerEncoder (cond_stage_config of layout2lidar; lidm/modules/encoders/layout_encoder.py:140-220):
    * hidden_dim = encoder_channels, enc_out_dim = output_dim (= 4 * model_channels), transformer depth / heads, classes */
   int32_t enc_layers, enc_heads, enc_out_dim, enc_num_classes;
+  /* unet_type 2 = EfficientUNet, the pixel-space R2DM denoiser (lidm/modules/unets/efficient_unet.py:188-295; no first
+   * stage: the ae_* fields are ignored): in_channels (2) image channels on a latent_h x latent_w = resolution grid,
+   * model_channels = base_channels, channel_mult[4] = channel_multiplier, eff_res_blocks[4] = num_residual_blocks,
+   * GroupNorm with eff_gn_groups groups and eps eff_gn_eps, eff_attn_heads attention heads, Fourier-feature coordinate
+   * encoding, ring (circular) padding. */
+  int32_t eff_res_blocks[LIDM_MAX_LEVELS];
+  int32_t eff_gn_groups, eff_attn_heads;
+  float eff_gn_eps;
 } lidm_config;
 
 /* Last error message for `h` (or, with h == NULL, for the calling thread's last failed lidm_create / stateless call). */

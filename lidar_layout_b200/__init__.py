@@ -19,6 +19,9 @@ def __getattr__(name):
     if name in ("LatentDiffusion",):
         from .ddpm import LatentDiffusion
         return LatentDiffusion
+    if name in ("R2DMDiffusion",):
+        from .ddpm import R2DMDiffusion
+        return R2DMDiffusion
     if name in ("DDIMSampler",):
         from .ddim import DDIMSampler
         return DDIMSampler

@@ -40,6 +40,8 @@ class CConfig(ctypes.Structure):
         ("ae_precision", c_int32),
         ("unet_type", c_int32), ("encoder_channels", c_int32), ("num_attention_blocks", c_int32),
         ("enc_layers", c_int32), ("enc_heads", c_int32), ("enc_out_dim", c_int32), ("enc_num_classes", c_int32),
+        ("eff_res_blocks", c_int32 * MAX_LEVELS), ("eff_gn_groups", c_int32), ("eff_attn_heads", c_int32),
+        ("eff_gn_eps", c_float),
     ]
 
 

@@ -37,6 +37,11 @@ class UNetConfig:
     unet_type: str = "openai"
     encoder_channels: int = 0
     num_attention_blocks: int = 1
+    # "efficient" = lidm.modules.unets.efficient_unet.EfficientUNet (the R2DM pixel-space denoiser): image_size = resolution,
+    # model_channels = base_channels, channel_mult = channel_multiplier, num_heads = attn_num_heads, plus:
+    num_residual_blocks: Tuple[int, ...] = (3, 3, 3, 3)
+    gn_num_groups: int = 8
+    gn_eps: float = 1e-6
 
     @property
     def time_embed_dim(self) -> int:
@@ -141,11 +146,13 @@ def from_reference_dict(cfg: dict) -> LidmConfig:
     """Build a LidmConfig from a parsed reference YAML (dict with `model:` and optional `data:`)."""
     model = cfg["model"]
     target = model.get("target", "")
-    if not target.endswith("LatentDiffusion"):
-        raise ValueError(f"unsupported model target {target!r}: only LatentDiffusion is on the B200 path")
+    if not (target.endswith("LatentDiffusion") or target.endswith("R2DMDiffusion")):
+        raise ValueError(f"unsupported model target {target!r}: only LatentDiffusion / R2DMDiffusion are on the B200 path")
     p = model["params"]
     unet_p = p["unet_config"]["params"]
     utarget = p["unet_config"]["target"]
+    if target.endswith("R2DMDiffusion"):
+        return _r2dm_from_reference_dict(cfg)
     if utarget.endswith("object_cross_unet.LayoutDiffusionUNetModel"):
         if unet_p.get("attention_block_type", "GLIDE") != "ObjectAwareCrossAttention":
             raise ValueError("LayoutDiffusionUNetModel: only attention_block_type 'ObjectAwareCrossAttention' is supported")
@@ -199,6 +206,59 @@ def from_reference_dict(cfg: dict) -> LidmConfig:
     except (KeyError, TypeError):
         pass
     return LidmConfig(dataset=ds, **kw)
+
+
+def _r2dm_from_reference_dict(cfg: dict) -> LidmConfig:
+    """R2DMDiffusion (lidm/models/diffusion/ddpm_r2dm.py) + EfficientUNet (efficient_unet.py:188-260): pixel space, no
+    first stage."""
+    p = cfg["model"]["params"]
+    up = p["unet_config"]["params"]
+    if not p["unet_config"]["target"].endswith("efficient_unet.EfficientUNet"):
+        raise ValueError("unsupported unet target " + p["unet_config"]["target"])
+    if up.get("coords_encoding", "spherical_harmonics") != "fourier_features" or not up.get("ring", True):
+        raise ValueError("EfficientUNet: only coords_encoding 'fourier_features' with ring padding is supported (as shipped)")
+    if up.get("temb_channels") not in (None, 4 * up.get("base_channels", 128)) or up.get("out_channels") not in (None, up["in_channels"]):
+        raise ValueError("EfficientUNet: temb_channels / out_channels must keep their defaults")
+    mult = up.get("channel_multiplier", (1, 2, 4, 8))
+    nres = up.get("num_residual_blocks", (3, 3, 3, 3))
+    mult = tuple(mult) if isinstance(mult, (list, tuple)) else (mult,) * 4
+    nres = tuple(nres) if isinstance(nres, (list, tuple)) else (nres,) * 4
+    res = up["resolution"]
+    res = tuple(res) if isinstance(res, (list, tuple)) else (res, res)
+    unet = UNetConfig(image_size=res, in_channels=up["in_channels"], out_channels=up["in_channels"],
+                      model_channels=up.get("base_channels", 128), channel_mult=mult, num_residual_blocks=nres,
+                      gn_num_groups=up.get("gn_num_groups", 8), gn_eps=float(up.get("gn_eps", 1e-6)),
+                      num_heads=up.get("attn_num_heads", 8), unet_type="efficient", attention_resolutions=(), lib_name="r2dm")
+    if p.get("cond_stage_config", "__is_unconditional__") != "__is_unconditional__":
+        raise ValueError("R2DMDiffusion: only the unconditional model is supported")
+    kw = dict(timesteps=p.get("timesteps", 1000), linear_start=p.get("linear_start", 1e-4), linear_end=p.get("linear_end", 2e-2),
+              beta_schedule=p.get("beta_schedule", "linear"), channels=p.get("channels", up["in_channels"]),
+              image_size=_tup(p.get("image_size", res)), scale_factor=1.0, parameterization=p.get("parameterization", "eps"),
+              conditioning_key=None, unet=unet, ae=AEConfig(ch=0, ch_mult=(), strides=()))
+    ds = DatasetConfig()
+    try:
+        ds = DatasetConfig(**_pick(DatasetConfig, cfg["data"]["params"]["dataset"]))
+    except (KeyError, TypeError):
+        pass
+    return LidmConfig(dataset=ds, **kw)
+
+
+def nuscenes_r2dm(resolution=(32, 1024)) -> LidmConfig:
+    """The R2DM pixel-space model (reference models/lidm/nuscenes/r2dm/config.yaml): EfficientUNet on 2-channel (depth,
+    reflectance) range images, 1024 diffusion steps; BASELINE config 5 also runs it at 64x1024."""
+    H, W = resolution
+    return LidmConfig(timesteps=1024, linear_start=0.0015, linear_end=0.0195, channels=2, image_size=(H, W),
+                      unet=UNetConfig(image_size=(H, W), in_channels=2, out_channels=2, model_channels=64,
+                                      channel_mult=(1, 2, 4, 8), num_residual_blocks=(3, 3, 3, 3), gn_num_groups=8, gn_eps=1e-6,
+                                      num_heads=8, unet_type="efficient", attention_resolutions=(), lib_name="r2dm"),
+                      ae=AEConfig(ch=0, ch_mult=(), strides=()),
+                      dataset=DatasetConfig(size=(H, W), fov=(10.0, -30.0)))
+
+
+def tiny_r2dm() -> LidmConfig:
+    """R2DM at 16x512 with one residual block per level (same four levels, both attention head widths): for fast tests."""
+    c = nuscenes_r2dm((16, 512))
+    return dataclasses.replace(c, unet=dataclasses.replace(c.unet, num_residual_blocks=(1, 1, 1, 1)))
 
 
 def from_yaml(path: str) -> LidmConfig:

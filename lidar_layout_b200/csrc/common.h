@@ -115,6 +115,7 @@ struct GemmEpilogue {
   const float* rowadd = nullptr;   // per-sample additive term (timestep embedding): [B][rowadd_ld] or null
   int rowadd_ld = 0;               // 0 => same row for every sample
   View residual;                   // optional bf16 residual (p == null => none), same logical shape as out
+  float res_scale = 1.f;           // the residual enters as res_scale * residual
   // optional second A operand appended along K as one more (unshifted) tap: out += a2 * B[:, Kmain : Kmain + a2.C]
   // (a ResBlock's 1x1 skip convolution folded into its second conv: one GEMM, no skip tensor written or re-read)
   View a2;
@@ -194,6 +195,10 @@ void launch_oaca_layout_kv(const float* xf_out, const float* cls, int B, int E, 
                            const float* Wc, const float* bc, int C, float scale, bf16* klay, bf16* vlay, bool f16,
                            cudaStream_t s);
 void launch_avgpool2(const View& x, const View& y, cudaStream_t s);
+// ops.Resample (lidm/modules/unets/ops.py:52-143) with the [1,3,3,1] window, ring = True: x2 up / down sampling of a
+// halo-free channels-last tensor (circular on W, zeros on H)
+void launch_fir_down2(const View& x, const View& y, cudaStream_t s);
+void launch_fir_up2(const View& x, const View& y, cudaStream_t s);
 // LayoutTransformerEncoder.forward (layout_encoder.py:222-281), fp32, one CTA per sample.  layers_dev: device array of
 // n_layers x 12 float pointers {ln_1 g/b, c_qkv w/b, c_proj w/b, ln_2 g/b, c_fc w/b, mlp.c_proj w/b}.  Outputs (NCL fp32):
 // xf_proj (B,out_dim), xf_out / obj_class_embedding / obj_bbox_embedding (B,H,L).
@@ -244,7 +249,9 @@ void launch_codebook_norm(const float* codebook, int n_embed, int dim, float* ou
 void launch_time_embed(const int64_t* t_dev, int nt, int model_ch, const float* w0, const float* b0, const float* w2,
                        const float* b2, int ted, float* tmp /* nt*ted */, float* emb_silu /* nt*ted */,
                        cudaStream_t s, int t_stride = 1 /* 0: one timestep for every row */,
-                       const float* rowbias = nullptr /* [nt][ted] added to emb before the SiLU (layout encoder xf_proj) */);
+                       const float* rowbias = nullptr /* [nt][ted] added to emb before the SiLU (layout encoder xf_proj) */,
+                       int style = 0 /* 0: [cos | sin], f_i = P^(-i/half) (basic.py:278-296); 1: [sin | cos], f_i = P^(-i/(half-1))
+                                        (R2DM, unets/ops.py:14-27) */);
 void launch_linear_rows(const float* x, int nt, int K, const float* w, const float* b, int N, float* out,
                         cudaStream_t s);
 void launch_pack_conv_weight(const float* w, int cout, int cin, int kh, int kw, int n_alloc, int k_alloc,

@@ -343,16 +343,23 @@ __global__ void vq_kernel(const float* __restrict__ z, int C, int HW, int64_t np
 // ------------------------------------------------------------------------------------------ timestep embedding MLP
 // tmp[r][j] = SiLU(b0[j] + sum_i w0[j][i] * temb(t_r)[i]),  temb = [cos(t f_i) | sin(t f_i)], f_i = exp(-ln(1e4) i / half)
 __global__ void time_embed_l0_kernel(const int64_t* __restrict__ t, int t_stride, int model_ch, const float* __restrict__ w0,
-                                     const float* __restrict__ b0, int ted, float* __restrict__ tmp) {
+                                     const float* __restrict__ b0, int ted, float* __restrict__ tmp, int style) {
   extern __shared__ float te[];
   const int r = blockIdx.y;
   const int half = model_ch / 2;
   const float tv = (float)t[(size_t)r * t_stride];
   for (int i = threadIdx.x; i < half; i += blockDim.x) {
-    const float f = expf(-logf(10000.f) * (float)i / (float)half);
-    const float a = tv * f;
-    te[i] = cosf(a);
-    te[half + i] = sinf(a);
+    if (style == 0) {
+      const float f = expf(-logf(10000.f) * (float)i / (float)half);
+      const float a = tv * f;
+      te[i] = cosf(a);
+      te[half + i] = sinf(a);
+    } else {      // SinusoidalPositionalEmbedding (unets/ops.py:14-27): exp(h * i), h = -ln(P) / (half - 1), float64 h as numpy
+      const float f = expf((float)(-9.210340371976184 / (double)(half - 1)) * (float)i);
+      const float a = tv * f;
+      te[i] = sinf(a);
+      te[half + i] = cosf(a);
+    }
   }
   __syncthreads();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -578,9 +585,9 @@ void launch_vq(const float* z, int B, int C, int HW, const float* codebook, cons
 
 void launch_time_embed(const int64_t* t_dev, int nt, int model_ch, const float* w0, const float* b0, const float* w2,
                        const float* b2, int ted, float* tmp, float* emb_silu, cudaStream_t s, int t_stride,
-                       const float* rowbias) {
+                       const float* rowbias, int style) {
   dim3 g0(cdiv(ted, 128), nt);
-  time_embed_l0_kernel<<<g0, 128, model_ch * sizeof(float), s>>>(t_dev, t_stride, model_ch, w0, b0, ted, tmp);
+  time_embed_l0_kernel<<<g0, 128, model_ch * sizeof(float), s>>>(t_dev, t_stride, model_ch, w0, b0, ted, tmp, style);
   LIDM_CUDA_CHECK(cudaGetLastError());
   // emb = Linear(tmp) (+ the layout encoder's xf_proj row); every consumer applies SiLU first (openaimodel.py:222-223)
   // so store SiLU(emb)

@@ -174,6 +174,7 @@ struct Plan {
   int32_t* idx_out = nullptr;
   int quantize = 1;
   int64_t cond_gen = 0;             // generation of the layout conditioning buffers the ops read (lidm_layout_set_cond)
+  bool eff_input_ready = false;     // EfficientUNet: the constant coordinate-encoding channels of the input buffer are filled
   const float* rowadd_base = nullptr;
   int rowadd_ld = 0;
   const float* ddim_noise = nullptr;
@@ -216,6 +217,18 @@ struct lidm_handle {
   int64_t cond_gen = 0;                                   // bumps whenever the conditioning buffers move (CUDA-graph key)
   float* cond_xf_proj = nullptr;                          // (cond_B, ted)
   std::vector<void*> cond_owned;
+  // EfficientUNet (R2DM, unet_type 2)
+  bool is_eff = false;
+  struct EffBlock {
+    bool has_down = false, has_up = false, has_attn = false;
+    ConvW down, up;                                       // conv before the FIR down-sampler / after the FIR up-sampler
+    std::vector<ResW> res;
+    NormW attn_norm; ConvW attn_qkv, attn_proj; int attn_heads = 0, ch = 0, cin = 0;
+  };
+  EffBlock eff_d[4], eff_u[4];
+  ConvW eff_in_conv;
+  float* eff_cenc = nullptr; int eff_cenc_ch = 0;          // Fourier features of the polar coordinates (extra_ch, H, W) fp32
+  float *ones_c = nullptr, *zeros_c = nullptr;            // AdaGN = GroupNorm without affine parameters
   // LayoutTransformerEncoder (cond_stage_model.*), fp32; packed when the state-dict carries it
   bool has_layout_encoder = false;
   void* lenc_layers = nullptr;                            // device array of n_layers x 12 float pointers
@@ -333,7 +346,8 @@ struct Packer {
   // k_alloc_override: K of the packed matrix (for im2col'd operands padded to a multiple of 64)
   // k_alloc_override: per-plane K of an im2col'd small-channel operand (padded to a multiple of 64)
   // nseg_p: operand-split segments used in precise mode (3: hi/lo activations, 2: exact bf16 activations)
-  ConvW conv(const std::string& prefix, int cout, int cin, int kh, int kw, int k_alloc_override = 0, int nseg_p = 3) {
+  ConvW conv(const std::string& prefix, int cout, int cin, int kh, int kw, int k_alloc_override = 0, int nseg_p = 3,
+             float scale = 1.f /* multiplies weights and bias (bf16 / fp16 modes only) */) {
     const DevTensor& t = find_raw(h, prefix + ".weight", ema);
     if (t.numel != (int64_t)cout * cin * kh * kw)
       throw Error(LIDM_ERR_STATE, "weight '" + prefix + ".weight' has unexpected size");
@@ -345,7 +359,8 @@ struct Packer {
     if (!precise) {
       c.k_alloc = k_alloc_override ? k_alloc_override : kh * kw * cin;
       c.w = dev_alloc<bf16>(h, (size_t)c.n_alloc * c.k_alloc);
-      launch_pack_conv_weight(t.p, cout, cin, kh, kw, c.n_alloc, c.k_alloc, nullptr, nullptr, 1.f, 0, c.w, s, f16);
+      launch_pack_conv_weight(t.p, cout, cin, kh, kw, c.n_alloc, c.k_alloc, nullptr, nullptr, scale, scale != 1.f ? cout : 0,
+                              c.w, s, f16);
     } else if (k_alloc_override) {
       // K layout [seg][kpad]: reorder to fp32 [cout][kpad] (k = tap*cin + c) and split-pack it as a 1x1 conv
       float* tmp = nullptr;
@@ -362,6 +377,14 @@ struct Packer {
       launch_pack_conv_weight_split(t.p, cout, cin, kh, kw, c.n_alloc, c.nseg, nullptr, 1.f, 0, c.w, s);
     }
     c.bias = f32(prefix + ".bias", cout);
+    if (scale != 1.f) {
+      if (precise) throw Error(LIDM_ERR_INVALID, "internal: scaled convolutions are not packed in the operand-split mode");
+      std::vector<float> bh(cout);
+      LIDM_CUDA_CHECK(cudaMemcpyAsync(bh.data(), c.bias, cout * sizeof(float), cudaMemcpyDeviceToHost, s));
+      LIDM_CUDA_CHECK(cudaStreamSynchronize(s));
+      for (float& v : bh) v *= scale;
+      LIDM_CUDA_CHECK(cudaMemcpy(c.bias, bh.data(), cout * sizeof(float), cudaMemcpyHostToDevice));
+    }
     return c;
   }
 };
@@ -426,6 +449,7 @@ struct Builder {
   bool dry;
   bool precise = false;   // this plan runs the operand-split (fp32-class) kernels
   bool f16 = false;       // 2-byte activations of this plan are IEEE half instead of bf16
+  int gn_groups = 32;     // GroupNorm group count (32 everywhere but the R2DM U-Net: 8)
   // GroupNorm statistics written by GEMM epilogues (View::gst): which 8-channel granules of each statistics buffer have
   // been produced so far in plan order; a GroupNorm whose whole input is covered skips its statistics pass
   std::map<const float*, std::vector<char>> gst_cover;
@@ -714,16 +738,17 @@ struct Builder {
   void groupnorm(const View& x, const View& y, const NormW& n, float eps, bool silu, int film_off = -1) {
     Plan* P_ = P;
     const std::string label = "gn C" + std::to_string(x.C) + " @" + std::to_string(x.H) + "x" + std::to_string(x.W);
-    if (x.C % 32 == 0 && (x.C / 32) % 8 == 0 && x.hl == 0 && x.hr == 0 && gst_covered(x)) {
+    const int G = gn_groups;
+    if (x.C % G == 0 && (x.C / G) % 8 == 0 && x.hl == 0 && x.hr == 0 && gst_covered(x)) {
       // every producer of x left its granule statistics behind: one pass (read x, write y)
       op([=](cudaStream_t s) {
-        launch_groupnorm_from_gstats(x, y, n.gamma, n.beta, eps, 32, silu, s,
+        launch_groupnorm_from_gstats(x, y, n.gamma, n.beta, eps, G, silu, s,
                                      film_off >= 0 ? P_->rowadd_base + film_off : nullptr, P_->rowadd_ld);
       }, PROF_NORM, 0, 4.0 * x.B * x.H * x.W * x.C, label);
       return;
     }
     op([=](cudaStream_t s) {
-      launch_groupnorm(x, y, n.gamma, n.beta, eps, 32, silu, P_->gn_partials, s,
+      launch_groupnorm(x, y, n.gamma, n.beta, eps, G, silu, P_->gn_partials, s,
                        film_off >= 0 ? P_->rowadd_base + film_off : nullptr, P_->rowadd_ld);
     }, PROF_NORM, 0, 4.0 * x.B * x.H * x.W * x.C, label);
   }
@@ -793,6 +818,114 @@ struct Builder {
     }
     release(bg2);
     if (r.updown) release(bxr);
+  }
+
+  // ResidualBlock.forward of the R2DM U-Net (efficient_unet.py:55-110): GN -> SiLU -> ring conv -> AdaGN(temb) -> SiLU ->
+  // ring conv; (skip(x) + h) / sqrt 2 with the scale folded into conv2 / skip (an identity skip enters as res_scale * x)
+  void res_block_eff(const ResW& r, const View& x, const View& dst, float eps) {
+    const int B = x.B, H = x.H, W = x.W;
+    Buf bg1, bh, bg2;
+    View g1 = act(B, H, W, r.cin, 1, 1, &bg1);
+    groupnorm(x, g1, r.n1, eps, true);
+    View hmid = act(B, H, W, r.cout, 0, 0, &bh);
+    {
+      GemmEpilogue ep;
+      ep.bias = r.c1.bias;
+      ep.out = hmid;
+      gemm(g1, taps_rect(3, 3, 1, 1), r.c1, ep);
+    }
+    release(bg1);
+    View g2 = act(B, H, W, r.cout, 1, 1, &bg2);
+    groupnorm(hmid, g2, r.n2, eps, true, r.emb_off);
+    release(bh);
+    if (r.has_skip && r.c2s.w != nullptr && x.wpitch == 0) {
+      GemmEpilogue ep;
+      ep.bias = r.c2s.bias;
+      ep.a2 = x;
+      ep.out = dst;
+      prep_gst(ep, r.cout, r.c2s.n_alloc);
+      const GemmB b = gb(r.c2s);
+      const ConvTaps taps = taps_rect(3, 3, 1, 1);
+      const int N = r.cout;
+      op([=](cudaStream_t s) { launch_conv_gemm(g2, taps, b, N, ep, s); }, PROF_GEMM,
+         gemm_flops(g2, taps.n, N) + gemm_flops(x, 1, N), 0, gemm_label(g2, taps.n, N) + " +skip" + std::to_string(r.cin));
+    } else {
+      if (r.has_skip) throw Error(LIDM_ERR_INVALID, "internal: EfficientUNet skip convolutions are always folded");
+      GemmEpilogue ep;
+      ep.bias = r.c2.bias;
+      ep.residual = x;
+      ep.res_scale = 0.70710678118654752f;
+      ep.out = dst;
+      gemm(g2, taps_rect(3, 3, 1, 1), r.c2, ep);
+    }
+    release(bg2);
+  }
+
+  // SelfAttentionBlock.forward (efficient_unet.py:23-52): GN -> nn.MultiheadAttention -> (x + h) / sqrt 2.  Head width 32
+  // runs the flash kernel; head width 64 runs per-head GEMMs (S = Q K^T, row softmax, P V) on the conv-GEMM kernel.
+  void attn_block_eff(const lidm_handle::EffBlock& blk, const View& x, const View& dst, float eps) {
+    const int B = x.B, H = x.H, W = x.W, C = blk.ch, T = H * W, heads = blk.attn_heads, d = C / heads;
+    Buf bg, bqk, bvt, bs, bp, ba;
+    View g = act(B, H, W, C, 0, 0, &bg);
+    groupnorm(x, g, blk.attn_norm, eps, false);
+    View ao;
+    if (d == 32) {
+      View qkv = act(B, H, W, 3 * C, 0, 0, &bqk);
+      GemmEpilogue ep;
+      ep.bias = blk.attn_qkv.bias;
+      ep.out = qkv;
+      ep.out.gst = nullptr;
+      gemm(g, taps_1x1(), blk.attn_qkv, ep);
+      release(bg);
+      ao = act(B, H, W, C, 0, 0, &ba);
+      op([=](cudaStream_t s) { launch_attention_d32_packed(qkv.p, ao, B, T, heads, s); }, PROF_ATTN,
+         4.0 * B * heads * (double)T * T * 32, 0, "attn T" + std::to_string(T) + " heads" + std::to_string(heads));
+      release(bqk);
+    } else {
+      if (T % 128 != 0 || T > 4096) throw Error(LIDM_ERR_INVALID, "EfficientUNet attention (head width 64): T must be a multiple of 128");
+      View qk = act(B, H, W, 2 * C, 0, 0, &bqk);
+      bf16* vt = raw<bf16>((size_t)B * C * T, &bvt);
+      {
+        GemmEpilogue ep;
+        ep.bias = blk.attn_qkv.bias;
+        ep.out = qk;
+        ep.out.gst = nullptr;
+        ep.split_n = 2 * C;
+        ep.out_t = vt;
+        gemm(g, taps_1x1(), blk.attn_qkv, ep);
+      }
+      release(bg);
+      ao = act(B, H, W, C, 0, 0, &ba);
+      float* S = raw<float>((size_t)B * T * T, &bs);
+      bf16* Pm = raw<bf16>((size_t)B * T * T, &bp);
+      const bool f16_ = f16;
+      for (int hd = 0; hd < heads; ++hd) {
+        View q = chan_slice(qk, hd * d, d);
+        q.gst = nullptr;
+        GemmB kb; kb.p = qk.p + C + hd * d; kb.n_alloc = T; kb.ld = 2 * C; kb.batch_stride = (int64_t)T * 2 * C; kb.f16 = f16;
+        GemmEpilogue es;
+        es.out_f32_nhwc = S;
+        op([=](cudaStream_t s) { launch_conv_gemm(q, taps_1x1(), kb, T, es, s); }, PROF_ATTN, gemm_flops(q, 1, T));
+        op([=](cudaStream_t s) { launch_softmax_rows(S, Pm, (int64_t)B * T, T, s, f16_); }, PROF_ATTN);
+        View pv = mat(Pm, B, T / 128, 128, T, T);
+        GemmB vb; vb.p = vt + (size_t)hd * d * T; vb.n_alloc = d; vb.ld = T; vb.batch_stride = (int64_t)C * T; vb.f16 = f16;
+        GemmEpilogue eo;
+        View o2 = chan_slice(ao, hd * d, d);
+        o2.H = T / 128; o2.W = 128; o2.gst = nullptr;
+        eo.out = o2;
+        op([=](cudaStream_t s) { launch_conv_gemm(pv, taps_1x1(), vb, d, eo, s); }, PROF_ATTN, gemm_flops(pv, 1, d));
+      }
+      release(bs); release(bp); release(bqk); release(bvt);
+    }
+    {
+      GemmEpilogue ep;
+      ep.bias = blk.attn_proj.bias;
+      ep.residual = x;
+      ep.res_scale = 0.70710678118654752f;
+      ep.out = dst;
+      gemm(ao, taps_1x1(), blk.attn_proj, ep);
+    }
+    release(ba);
   }
 
   // ObjectAwareCrossAttention.forward (object_cross_unet.py:447-565): GN32 -> qkv 1x1 -> attention over image + layout
@@ -1268,6 +1401,144 @@ void build_unet_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
     b.release(bfinal);
   }
   if (h->has_st) b.release(bctx_kv);
+  *high = b.ap.high();
+}
+
+// ------------------------------------------------------------------------------------------- EfficientUNet plan
+// EfficientUNet.forward (efficient_unet.py:262-295): [x | Fourier features] -> in_conv -> 4 down blocks -> 4 up blocks (skip
+// concatenations written in place) -> out_conv -> eps (fp32 NCHW) [+ fused DDIM update]
+void build_eff_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
+  Builder b{h, P, ArenaPlanner(), dry};
+  b.f16 = h->unet_prec == LIDM_PREC_FP16;
+  b.gn_groups = h->cfg.eff_gn_groups;
+  const lidm_config& cfg = h->cfg;
+  const float eps = cfg.eff_gn_eps;
+  const int B = P->B, H = cfg.latent_h, W = cfg.latent_w, Cx = cfg.in_channels, Ce = h->eff_cenc_ch, Cin = Cx + Ce;
+  const int C0 = cfg.model_channels;
+  int C[5] = {C0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; ++i) C[i + 1] = C0 * cfg.channel_mult[i];
+  // the assembled input lives for the whole plan: the coordinate channels are written once, the image channels per call
+  Buf bxin;
+  float* xin = b.raw<float>((size_t)B * Cin * H * W, &bxin);
+  const size_t HW = (size_t)H * W;
+  b.op([=](cudaStream_t s) {
+    if (!P->eff_input_ready) {
+      for (int bb = 0; bb < B; ++bb)
+        LIDM_CUDA_CHECK(cudaMemcpyAsync(xin + ((size_t)bb * Cin + Cx) * HW, h->eff_cenc, (size_t)Ce * HW * sizeof(float),
+                                        cudaMemcpyDeviceToDevice, s));
+      P->eff_input_ready = true;
+    }
+    LIDM_CUDA_CHECK(cudaMemcpy2DAsync(xin, (size_t)Cin * HW * sizeof(float), P->x, (size_t)Cx * HW * sizeof(float),
+                                      (size_t)Cx * HW * sizeof(float), B, cudaMemcpyDeviceToDevice, s));
+  });
+  // skip-concatenation buffers [up-path tensor | down-path tensor] at levels 1..3
+  Buf bcat[4];
+  View cat[4];
+  for (int l = 1; l <= 3; ++l) cat[l] = b.act(B, H >> (l - 1), W >> (l - 1), 2 * C[l], 0, 0, &bcat[l]);
+  Buf bh0;
+  View h0 = b.act(B, H, W, C[0], 0, 0, &bh0);
+  {
+    const int kpad = h->eff_in_conv.k_alloc;
+    Buf bc;
+    bf16* col = b.raw<bf16>((size_t)B * HW * kpad, &bc);
+    const bool f16 = b.f16;
+    b.op([=](cudaStream_t s) { launch_im2col_nchw_f32(xin, B, Cin, H, W, 3, 3, 1, 1, col, kpad, s, f16); });
+    View a = b.mat(col, B, H, W, kpad, kpad);
+    GemmEpilogue ep;
+    ep.bias = h->eff_in_conv.bias;
+    ep.out = h0;
+    b.gemm(a, taps_1x1(), h->eff_in_conv, ep);
+    b.release(bc);
+  }
+  // one Block (efficient_unet.py:113-186)
+  auto run_block = [&](const lidm_handle::EffBlock& blk, View x, Buf xbuf, bool own_x, const View& dst) {
+    // [ring conv 3x3 + FIR x1/2]
+    if (blk.has_down) {
+      Buf bxh, by, bz;
+      View xh = b.act(B, x.H, x.W, x.C, 1, 1, &bxh);
+      b.op([=](cudaStream_t s) { launch_copy_with_halo(x, xh, s); });
+      if (own_x) b.release(xbuf);
+      View y = b.act(B, x.H, x.W, blk.ch, 0, 0, &by);
+      GemmEpilogue ep;
+      ep.bias = blk.down.bias;
+      ep.out = y;
+      ep.out.gst = nullptr;
+      b.gemm(xh, taps_rect(3, 3, 1, 1), blk.down, ep);
+      b.release(bxh);
+      View z = b.act(B, x.H / 2, x.W / 2, blk.ch, 0, 0, &bz);
+      z.gst = nullptr;                      // produced by the FIR kernel: the first GroupNorm takes its own statistics
+      b.op([=](cudaStream_t s) { launch_fir_down2(y, z, s); });
+      b.release(by);
+      x = z; xbuf = bz; own_x = true;
+    }
+    const int n = (int)blk.res.size();
+    const bool tail = blk.has_attn || blk.has_up;
+    for (int i = 0; i < n; ++i) {
+      const bool last = (i + 1 == n) && !tail;
+      Buf bo; View o;
+      if (last) o = dst;
+      else o = b.act(B, x.H, x.W, blk.ch, 0, 0, &bo);
+      b.res_block_eff(blk.res[i], x, o, eps);
+      if (own_x) b.release(xbuf);
+      x = o; xbuf = bo; own_x = !last;
+    }
+    if (blk.has_attn) {
+      const bool last = !blk.has_up;
+      Buf bo; View o;
+      if (last) o = dst;
+      else o = b.act(B, x.H, x.W, blk.ch, 0, 0, &bo);
+      b.attn_block_eff(blk, x, o, eps);
+      if (own_x) b.release(xbuf);
+      x = o; xbuf = bo; own_x = !last;
+    }
+    if (blk.has_up) {
+      Buf bu;
+      View u = b.act(B, 2 * x.H, 2 * x.W, blk.ch, 1, 1, &bu);
+      b.op([=](cudaStream_t s) { launch_fir_up2(x, u, s); });
+      if (own_x) b.release(xbuf);
+      GemmEpilogue ep;
+      ep.bias = blk.up.bias;
+      ep.out = dst;
+      b.gemm(u, taps_rect(3, 3, 1, 1), blk.up, ep);
+      b.release(bu);
+    }
+  };
+  // down path: h1, h2, h3 land in the second halves of the concatenation buffers
+  run_block(h->eff_d[0], h0, bh0, true, Builder::chan_slice(cat[1], C[1], C[1]));
+  run_block(h->eff_d[1], Builder::chan_slice(cat[1], C[1], C[1]), Buf(), false, Builder::chan_slice(cat[2], C[2], C[2]));
+  run_block(h->eff_d[2], Builder::chan_slice(cat[2], C[2], C[2]), Buf(), false, Builder::chan_slice(cat[3], C[3], C[3]));
+  Buf bh4;
+  View h4 = b.act(B, H >> 3, W >> 3, C[4], 0, 0, &bh4);
+  run_block(h->eff_d[3], Builder::chan_slice(cat[3], C[3], C[3]), Buf(), false, h4);
+  // up path
+  run_block(h->eff_u[3], h4, bh4, true, Builder::chan_slice(cat[3], 0, C[3]));
+  run_block(h->eff_u[2], cat[3], bcat[3], true, Builder::chan_slice(cat[2], 0, C[2]));
+  run_block(h->eff_u[1], cat[2], bcat[2], true, Builder::chan_slice(cat[1], 0, C[1]));
+  Buf bhf;
+  View hf = b.act(B, H, W, C[0], 0, 0, &bhf);
+  run_block(h->eff_u[0], cat[1], bcat[1], true, hf);
+  // out_conv: ring conv 3x3 straight on h (no norm) -> eps [+ DDIM update]
+  {
+    Buf bg;
+    View g = b.act(B, H, W, C[0], 1, 1, &bg);
+    b.op([=](cudaStream_t s) { launch_copy_with_halo(hf, g, s); });
+    b.release(bhf);
+    const GemmB wb = Builder::gb(h->out_conv);
+    const float* bias = h->out_conv.bias;
+    const int N = h->out_conv.cout;
+    const ConvTaps taps = taps_rect(3, 3, 1, 1);
+    b.op([=](cudaStream_t s) {
+      GemmEpilogue ep;
+      ep.bias = bias;
+      ep.out_f32_nchw = P->out;
+      if (P->ddim_x_prev != nullptr) {
+        ep.ddim_x = P->x; ep.ddim_noise = P->ddim_noise; ep.ddim_x_prev = P->ddim_x_prev;
+        ep.ddim_pred_x0 = P->ddim_pred_x0; ep.ddim_coef = P->ddim_coef;
+      }
+      launch_conv_gemm(g, taps, wb, N, ep, s);
+    }, PROF_GEMM, gemm_flops(g, taps.n, N));
+    b.release(bg);
+  }
   *high = b.ap.high();
 }
 
@@ -2059,6 +2330,132 @@ void finalize_unet_layout(lidm_handle* h, Packer& pk) {
   if (ch != mc) throw Error(LIDM_ERR_INVALID, "U-Net must end at model_channels");
 }
 
+// EfficientUNet.__init__ (lidm/modules/unets/efficient_unet.py:188-260).  Every residual path ends in "* 1/sqrt 2": the
+// scale is folded into the last conv's (and the skip conv's) weights and bias; an identity skip enters the GEMM epilogue as
+// res_scale * x.
+void finalize_unet_efficient(lidm_handle* h, Packer& pk, std::vector<std::pair<std::string, ResW*>>& emb) {
+  const lidm_config& cfg = h->cfg;
+  const std::string U = "model.diffusion_model.";
+  LIDM_REQUIRE(!pk.precise, "the R2DM U-Net runs in the bf16 / fp16 modes");
+  LIDM_REQUIRE(cfg.n_channel_mult == 4, "EfficientUNet has four resolution levels");
+  LIDM_REQUIRE(cfg.eff_gn_groups >= 1 && cfg.eff_attn_heads >= 1 && cfg.eff_gn_eps > 0.f, "EfficientUNet: GroupNorm / attention options");
+  const int mc = cfg.model_channels, H = cfg.latent_h, W = cfg.latent_w;
+  const float S = 0.70710678118654752f;
+  int C[5] = {mc, 0, 0, 0, 0};
+  for (int i = 0; i < 4; ++i) {
+    C[i + 1] = mc * cfg.channel_mult[i];
+    LIDM_REQUIRE(C[i + 1] % 64 == 0 && (C[i + 1] / cfg.eff_gn_groups) % 8 == 0 && cfg.eff_res_blocks[i] >= 1,
+                 "EfficientUNet: channels must be multiples of 64 with >= 8 channels per GroupNorm group");
+  }
+  h->ones_c = dev_alloc<float>(h, 4096);
+  h->zeros_c = dev_alloc<float>(h, 4096);
+  {
+    std::vector<float> o(4096, 1.f);
+    LIDM_CUDA_CHECK(cudaMemcpy(h->ones_c, o.data(), o.size() * sizeof(float), cudaMemcpyHostToDevice));
+    LIDM_CUDA_CHECK(cudaMemset(h->zeros_c, 0, 4096 * sizeof(float)));
+  }
+  // Fourier features of the polar coordinates (encoding.py:93-105, 133-163), float32 like the reference's buffers
+  {
+    const int Lh = (int)std::ceil(std::log2((double)H)), Lw = (int)std::ceil(std::log2((double)W)), nf = Lh + Lw;
+    h->eff_cenc_ch = 2 * nf;
+    std::vector<float> ce((size_t)2 * nf * H * W);
+    const float d2r = (float)(M_PI / 180.0);
+    for (int y = 0; y < H; ++y) {
+      const float el = ((1.f - (float)y / (float)H) * 40.f + (-30.f)) * d2r;
+      for (int x = 0; x < W; ++x) {
+        const float az = ((1.f - (float)x / (float)W) * 360.f + (-180.f)) * d2r;
+        for (int k = 0; k < nf; ++k) {
+          const float a = k < Lh ? el * std::exp2((float)k) : az * std::exp2((float)(k - Lh));
+          ce[((size_t)k * H + y) * W + x] = std::sin(a);
+          ce[((size_t)(nf + k) * H + y) * W + x] = std::cos(a);
+        }
+      }
+    }
+    h->eff_cenc = dev_alloc<float>(h, ce.size());
+    LIDM_CUDA_CHECK(cudaMemcpy(h->eff_cenc, ce.data(), ce.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  const int cin0 = cfg.in_channels + h->eff_cenc_ch;
+  h->eff_in_conv = pk.conv(U + "in_conv", C[0], cin0, 3, 3, (9 * cin0 + 63) / 64 * 64);
+  auto pack_res_eff = [&](const std::string& p, int cin, int cout, ResW& r) {
+    r.cin = cin; r.cout = cout; r.film = true;
+    r.n1 = pk.norm(p + ".norm1", cin);
+    r.c1 = pk.conv(p + ".conv1", cout, cin, 3, 3);
+    r.n2.C = cout; r.n2.gamma = h->ones_c; r.n2.beta = h->zeros_c;
+    r.c2 = pk.conv(p + ".conv2", cout, cout, 3, 3, 0, 3, S);
+    r.has_skip = cin != cout;
+    if (r.has_skip) {
+      r.skip = pk.conv(p + ".skip", cout, cin, 1, 1, 0, 3, S);
+      // conv2(h) + skip(x) as one GEMM (both already carry the 1/sqrt 2)
+      const DevTensor& t = find_raw(h, p + ".conv2.weight", pk.ema);
+      ConvW f;
+      f.cout = cout; f.cin = cout; f.kh = f.kw = 3; f.f16 = pk.f16;
+      f.n_alloc = r.c2.n_alloc; f.k_alloc = 9 * cout + cin;
+      f.w = dev_alloc<bf16>(h, (size_t)f.n_alloc * f.k_alloc);
+      launch_pack_conv_weight(t.p, cout, cout, 3, 3, f.n_alloc, f.k_alloc, nullptr, nullptr, S, cout, f.w, pk.s, pk.f16);
+      LIDM_CUDA_CHECK(cudaMemcpy2DAsync(f.w + (size_t)9 * cout, (size_t)f.k_alloc * sizeof(bf16), r.skip.w,
+                                        (size_t)r.skip.k_alloc * sizeof(bf16), (size_t)cin * sizeof(bf16), r.skip.n_alloc,
+                                        cudaMemcpyDeviceToDevice, pk.s));
+      std::vector<float> b2(cout), bs(cout);
+      LIDM_CUDA_CHECK(cudaMemcpyAsync(b2.data(), r.c2.bias, cout * sizeof(float), cudaMemcpyDeviceToHost, pk.s));
+      LIDM_CUDA_CHECK(cudaMemcpyAsync(bs.data(), r.skip.bias, cout * sizeof(float), cudaMemcpyDeviceToHost, pk.s));
+      LIDM_CUDA_CHECK(cudaStreamSynchronize(pk.s));
+      for (int i = 0; i < cout; ++i) b2[i] += bs[i];
+      f.bias = dev_alloc<float>(h, cout);
+      LIDM_CUDA_CHECK(cudaMemcpy(f.bias, b2.data(), cout * sizeof(float), cudaMemcpyHostToDevice));
+      r.c2s = f;
+    }
+  };
+  auto pack_block = [&](lidm_handle::EffBlock& blk, const std::string& p, int cin, int cout, int nres, bool down, bool up, bool attn) {
+    blk.cin = cin; blk.ch = cout; blk.has_down = down; blk.has_up = up; blk.has_attn = attn;
+    if (down) blk.down = pk.conv(p + ".downsample.0", cout, cin, 3, 3);
+    blk.res.resize(nres);
+    for (int i = 0; i < nres; ++i) {
+      const std::string rp = p + ".residual_blocks." + std::to_string(i);
+      pack_res_eff(rp, (i != 0 || down) ? cout : cin, cout, blk.res[i]);
+      emb.emplace_back(rp + ".norm2.proj.1", &blk.res[i]);
+    }
+    if (attn) {
+      const std::string ap = p + ".self_attn_block";
+      const int heads = cfg.eff_attn_heads, d = cout / heads;
+      LIDM_REQUIRE(cout % heads == 0 && (d == 32 || d == 64), "EfficientUNet attention: head width 32 or 64");
+      blk.attn_heads = heads;
+      blk.attn_norm = pk.norm(ap + ".norm", cout);
+      // nn.MultiheadAttention: in_proj rows [q | k | v], softmax(q k^T / sqrt d): d^-1/4 on q and k rows (head width 32, flash
+      // kernel) or d^-1/2 on the q rows (head width 64, GEMM path)
+      const DevTensor& w = find_raw(h, ap + ".attn.in_proj_weight", pk.ema);
+      const DevTensor& bsrc = find_raw(h, ap + ".attn.in_proj_bias", pk.ema);
+      if (w.numel != (int64_t)3 * cout * cout || bsrc.numel != 3 * cout) throw Error(LIDM_ERR_STATE, "in_proj weight size: " + ap);
+      const float sc = d == 32 ? 1.0f / std::sqrt(std::sqrt((float)d)) : 1.0f / std::sqrt((float)d);
+      const int nsc = d == 32 ? 2 * cout : cout;
+      ConvW c;
+      c.cout = 3 * cout; c.cin = cout; c.kh = c.kw = 1; c.f16 = pk.f16;
+      c.n_alloc = round_n_alloc(3 * cout); c.k_alloc = cout;
+      c.w = dev_alloc<bf16>(h, (size_t)c.n_alloc * c.k_alloc);
+      launch_pack_conv_weight(w.p, 3 * cout, cout, 1, 1, c.n_alloc, c.k_alloc, nullptr, nullptr, sc, nsc, c.w, pk.s, pk.f16);
+      std::vector<float> bh(3 * cout);
+      LIDM_CUDA_CHECK(cudaMemcpyAsync(bh.data(), bsrc.p, bh.size() * sizeof(float), cudaMemcpyDeviceToHost, pk.s));
+      LIDM_CUDA_CHECK(cudaStreamSynchronize(pk.s));
+      for (int i = 0; i < nsc; ++i) bh[i] *= sc;
+      c.bias = dev_alloc<float>(h, bh.size());
+      LIDM_CUDA_CHECK(cudaMemcpy(c.bias, bh.data(), bh.size() * sizeof(float), cudaMemcpyHostToDevice));
+      blk.attn_qkv = c;
+      // out_proj is an nn.Linear (2-D weight): same memory layout as a 1x1 conv
+      blk.attn_proj = pk.conv(ap + ".attn.out_proj", cout, cout, 1, 1, 0, 3, S);
+    }
+    if (up) blk.up = pk.conv(p + ".upsample.1", cout, cout, 3, 3);
+  };
+  const int32_t* N = cfg.eff_res_blocks;
+  pack_block(h->eff_d[0], U + "d_block1", C[0], C[1], N[0], false, false, false);
+  pack_block(h->eff_d[1], U + "d_block2", C[1], C[2], N[1], true, false, false);
+  pack_block(h->eff_d[2], U + "d_block3", C[2], C[3], N[2], true, false, false);
+  pack_block(h->eff_d[3], U + "d_block4", C[3], C[4], N[3], true, false, true);
+  pack_block(h->eff_u[3], U + "u_block4", C[4], C[3], N[3], false, true, true);
+  pack_block(h->eff_u[2], U + "u_block3", 2 * C[3], C[2], N[2], false, true, false);
+  pack_block(h->eff_u[1], U + "u_block2", 2 * C[2], C[1], N[1], false, true, false);
+  pack_block(h->eff_u[0], U + "u_block1", 2 * C[1], C[0], N[0], false, false, false);
+  h->out_conv = pk.conv(U + "out_conv", cfg.out_channels, C[0], 3, 3);
+}
+
 void finalize(lidm_handle* h, bool use_ema) {
   const lidm_config& cfg = h->cfg;
   Packer pk{h, use_ema};
@@ -2070,17 +2467,21 @@ void finalize(lidm_handle* h, bool use_ema) {
   LIDM_REQUIRE(h->latent_channels <= cfg.in_channels && h->latent_channels == cfg.out_channels,
                "latent channels must equal out_channels and not exceed in_channels");
   h->ted = ted;
-  h->te_w0 = pk.f32(U + "time_embed.0.weight", (int64_t)ted * mc);
-  h->te_b0 = pk.f32(U + "time_embed.0.bias", ted);
-  h->te_w2 = pk.f32(U + "time_embed.2.weight", (int64_t)ted * ted);
-  h->te_b2 = pk.f32(U + "time_embed.2.bias", ted);
+  const bool eff_names = cfg.unet_type == 2;      // EfficientUNet: time_embedding = [sinusoidal, Linear, SiLU, Linear]
+  h->te_w0 = pk.f32(U + (eff_names ? "time_embedding.1.weight" : "time_embed.0.weight"), (int64_t)ted * mc);
+  h->te_b0 = pk.f32(U + (eff_names ? "time_embedding.1.bias" : "time_embed.0.bias"), ted);
+  h->te_w2 = pk.f32(U + (eff_names ? "time_embedding.3.weight" : "time_embed.2.weight"), (int64_t)ted * ted);
+  h->te_b2 = pk.f32(U + (eff_names ? "time_embedding.3.bias" : "time_embed.2.bias"), ted);
 
   std::vector<std::pair<std::string, ResW*>> emb_layers;
   h->in_blocks.clear(); h->out_blocks.clear(); h->mid_block.clear(); h->in_chans.clear();
   h->is_layout = cfg.unet_type == 1;
+  h->is_eff = cfg.unet_type == 2;
   h->has_st = false;
   h->ctx_n = 0;
+  std::vector<std::pair<std::string, ResW*>> eff_emb;
   if (h->is_layout) finalize_unet_layout(h, pk);
+  else if (h->is_eff) finalize_unet_efficient(h, pk, eff_emb);
   else {
   // ---- U-Net topology, exactly as UNetModel.__init__ walks it (openaimodel.py:516-687)
   {
@@ -2215,19 +2616,20 @@ void finalize(lidm_handle* h, bool use_ema) {
     std::vector<std::pair<std::string, ResW*>> all;
     auto collect = [&](std::vector<Layer>& layers, const std::string& p) {
       for (size_t j = 0; j < layers.size(); ++j)
-        if (layers[j].kind == Layer::RES) all.emplace_back(p + "." + std::to_string(j), &layers[j].r);
+        if (layers[j].kind == Layer::RES) all.emplace_back(p + "." + std::to_string(j) + ".emb_layers.1", &layers[j].r);
     };
     for (size_t i = 0; i < h->in_blocks.size(); ++i) collect(h->in_blocks[i], U + "input_blocks." + std::to_string(i));
     collect(h->mid_block, U + "middle_block");
     for (size_t i = 0; i < h->out_blocks.size(); ++i) collect(h->out_blocks[i], U + "output_blocks." + std::to_string(i));
+    for (auto& e : eff_emb) all.push_back(e);
     int total = 0;
     for (auto& e : all) { e.second->emb_off = total; total += (e.second->film ? 2 : 1) * e.second->cout; }
     h->emb_total = total;
     h->emb_w = dev_alloc<float>(h, (size_t)total * ted);
     h->emb_b = dev_alloc<float>(h, total);
     for (auto& e : all) {
-      const DevTensor& w = find_raw(h, e.first + ".emb_layers.1.weight", use_ema);
-      const DevTensor& bb = find_raw(h, e.first + ".emb_layers.1.bias", use_ema);
+      const DevTensor& w = find_raw(h, e.first + ".weight", use_ema);
+      const DevTensor& bb = find_raw(h, e.first + ".bias", use_ema);
       const int erows = (e.second->film ? 2 : 1) * e.second->cout;
       if (w.numel != (int64_t)erows * ted || bb.numel != erows)
         throw Error(LIDM_ERR_STATE, "emb_layers size mismatch at " + e.first);
@@ -2268,6 +2670,13 @@ void finalize(lidm_handle* h, bool use_ema) {
     h->lenc_tp_b = pk.f32(Cn + "transformer_proj.bias", ted);
   }
 
+  if (h->is_eff) {                 // pixel-space model: no first stage
+    LIDM_CUDA_CHECK(cudaDeviceSynchronize());
+    for (auto& kv : h->raw) cudaFree(kv.second.p);
+    h->raw.clear();
+    h->finalized = true;
+    return;
+  }
   // ---- first stage (decode side): its own numeric mode
   pk.precise = h->ae_prec == LIDM_PREC_BF16X3;
   pk.f16 = h->ae_prec == LIDM_PREC_FP16;
@@ -2409,8 +2818,14 @@ void ensure_time_buffers(lidm_handle* h, int rows) {
 void run_time_embed(lidm_handle* h, const int64_t* t_dev, int rows, cudaStream_t s, int t_stride = 1,
                     const float* rowbias = nullptr) {
   launch_time_embed(t_dev, rows, h->cfg.model_channels, h->te_w0, h->te_b0, h->te_w2, h->te_b2, h->ted, h->te_tmp,
-                    h->te_emb, s, t_stride, rowbias);
+                    h->te_emb, s, t_stride, rowbias, h->is_eff ? 1 : 0);
   launch_linear_rows(h->te_emb, rows, h->ted, h->emb_w, h->emb_b, h->emb_total, h->emb_out, s);
+}
+
+typedef void (*PlanPass)(lidm_handle*, Plan*, bool, size_t*);
+PlanPass unet_pass(lidm_handle* h) {
+  if (h->is_eff) return build_eff_plan_pass;
+  return h->unet_prec == LIDM_PREC_BF16X3 ? build_unet_plan_pass_p : build_unet_plan_pass;
 }
 
 void require_layout_cond(lidm_handle* h, int B) {
@@ -2556,10 +2971,10 @@ int lidm_create(const lidm_config* cfg, lidm_handle** out) {
     LIDM_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
     if (prop.major != 10) throw Error(LIDM_ERR_CUDA, std::string("sm_100a (B200) required, found ") + prop.name);
     LIDM_REQUIRE(cfg->n_channel_mult >= 1 && cfg->n_channel_mult <= LIDM_MAX_LEVELS, "n_channel_mult");
-    LIDM_REQUIRE(cfg->ae_n_ch_mult >= 1 && cfg->ae_n_ch_mult <= LIDM_MAX_LEVELS, "ae_n_ch_mult");
+    LIDM_REQUIRE(cfg->unet_type == 2 || (cfg->ae_n_ch_mult >= 1 && cfg->ae_n_ch_mult <= LIDM_MAX_LEVELS), "ae_n_ch_mult");
     LIDM_REQUIRE(cfg->model_channels % 64 == 0, "model_channels must be a multiple of 64");
-    LIDM_REQUIRE(cfg->unet_type == 0 || cfg->unet_type == 1, "unet_type");
-    LIDM_REQUIRE(cfg->num_head_channels == (cfg->unet_type == 1 ? 64 : 32),
+    LIDM_REQUIRE(cfg->unet_type >= 0 && cfg->unet_type <= 2, "unet_type");
+    LIDM_REQUIRE(cfg->unet_type == 2 || cfg->num_head_channels == (cfg->unet_type == 1 ? 64 : 32),
                  "num_head_channels must be 32 (openaimodel.UNetModel) / 64 (LayoutDiffusionUNetModel)");
     LIDM_REQUIRE(cfg->ae_ch % 64 == 0, "ae ch must be a multiple of 64");
     LIDM_REQUIRE(cfg->latent_h > 0 && cfg->latent_w > 0 && cfg->scale_factor != 0.f, "latent shape / scale_factor");
@@ -2620,6 +3035,7 @@ int lidm_vq_encode(lidm_handle* h, const float* img, float* z_out, int32_t B, vo
   return guarded(h, [&] {
     require_ready(h, B);
     LIDM_REQUIRE(img != nullptr && z_out != nullptr, "null tensor");
+    if (h->is_eff) throw Error(LIDM_ERR_INVALID, "the R2DM pixel-space model has no first stage");
     if (!h->has_encoder)
       throw Error(LIDM_ERR_STATE, "no encoder weights were loaded (first_stage_model.encoder.* / quant_conv.* missing from the state-dict)");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -2644,7 +3060,7 @@ int lidm_unet_forward_cond(lidm_handle* h, const float* x, const int64_t* t, con
     LIDM_REQUIRE(x != nullptr && t != nullptr && eps_out != nullptr, "null tensor");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     check_conditioning(h, c_concat, context, ctx_len);
-    Plan* P = get_plan(h, h->unet_plans, B, h->unet_prec == LIDM_PREC_BF16X3 ? build_unet_plan_pass_p : build_unet_plan_pass,
+    Plan* P = get_plan(h, h->unet_plans, B, unet_pass(h),
                        h->has_st ? ctx_len : 0);
     ensure_time_buffers(h, B);
     if (h->is_layout) {
@@ -2794,7 +3210,7 @@ int lidm_ddim_sample_cond(lidm_handle* h, float* x_inout, const int64_t* timeste
     }
     const int Bp = guided ? 2 * B : B;       // batch the U-Net plan runs at
     const int L = h->has_st ? ctx_len : 0;
-    Plan* P = get_plan(h, h->unet_plans, Bp, h->unet_prec == LIDM_PREC_BF16X3 ? build_unet_plan_pass_p : build_unet_plan_pass, L);
+    Plan* P = get_plan(h, h->unet_plans, Bp, unet_pass(h), L);
     ensure_time_buffers(h, std::max(n_steps, B));
     if (h->is_layout) {
       require_layout_cond(h, B);
@@ -2919,6 +3335,7 @@ int lidm_vq_decode(lidm_handle* h, const float* z, int32_t force_not_quantize, f
     require_ready(h, B);
     LIDM_REQUIRE(z != nullptr && img_out != nullptr, "null tensor");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (h->is_eff) throw Error(LIDM_ERR_INVALID, "the R2DM pixel-space model has no first stage");
     Plan* P = get_plan(h, h->dec_plans, B, h->ae_prec == LIDM_PREC_BF16X3 ? build_dec_plan_pass_p : build_dec_plan_pass);
     P->x = z; P->out = img_out; P->idx_out = idx_out; P->quantize = force_not_quantize ? 0 : 1;
     run_plan(P, s);

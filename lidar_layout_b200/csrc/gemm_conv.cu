@@ -45,6 +45,7 @@ struct GemmKernelParams {
   const float* rowadd;
   int rowadd_ld;
   const bf16* res;
+  float res_scale;           // out = acc + bias + res_scale * residual (R2DM: (x + f(x)) / sqrt 2 with f's scale folded into W)
   int n_fast;                // tile order: output-channel tiles of one pixel tile back to back (A read from HBM once)
   int res_ld, res_hl, res_Wp;
   const float* res_f32;      // fp32 channels-last residual (precise mode), no halo
@@ -307,10 +308,11 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
                   for (int i = 0; i < 4; ++i) {
                     float2 f;
-                    f = unpack_h<F16>(rres[c][i].x); v[i * 8 + 0] += f.x; v[i * 8 + 1] += f.y;
-                    f = unpack_h<F16>(rres[c][i].y); v[i * 8 + 2] += f.x; v[i * 8 + 3] += f.y;
-                    f = unpack_h<F16>(rres[c][i].z); v[i * 8 + 4] += f.x; v[i * 8 + 5] += f.y;
-                    f = unpack_h<F16>(rres[c][i].w); v[i * 8 + 6] += f.x; v[i * 8 + 7] += f.y;
+                    const float rs = p.res_scale;
+                    f = unpack_h<F16>(rres[c][i].x); v[i * 8 + 0] = fmaf(f.x, rs, v[i * 8 + 0]); v[i * 8 + 1] = fmaf(f.y, rs, v[i * 8 + 1]);
+                    f = unpack_h<F16>(rres[c][i].y); v[i * 8 + 2] = fmaf(f.x, rs, v[i * 8 + 2]); v[i * 8 + 3] = fmaf(f.y, rs, v[i * 8 + 3]);
+                    f = unpack_h<F16>(rres[c][i].z); v[i * 8 + 4] = fmaf(f.x, rs, v[i * 8 + 4]); v[i * 8 + 5] = fmaf(f.y, rs, v[i * 8 + 5]);
+                    f = unpack_h<F16>(rres[c][i].w); v[i * 8 + 6] = fmaf(f.x, rs, v[i * 8 + 6]); v[i * 8 + 7] = fmaf(f.y, rs, v[i * 8 + 7]);
                   }
                 }
                 if (p.geglu) {
@@ -442,16 +444,17 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             float2 f;
-            f = unpack_h<F16>(rres[i].x); v[i * 8 + 0] += f.x; v[i * 8 + 1] += f.y;
-            f = unpack_h<F16>(rres[i].y); v[i * 8 + 2] += f.x; v[i * 8 + 3] += f.y;
-            f = unpack_h<F16>(rres[i].z); v[i * 8 + 4] += f.x; v[i * 8 + 5] += f.y;
-            f = unpack_h<F16>(rres[i].w); v[i * 8 + 6] += f.x; v[i * 8 + 7] += f.y;
+            const float rs = p.res_scale;
+            f = unpack_h<F16>(rres[i].x); v[i * 8 + 0] = fmaf(f.x, rs, v[i * 8 + 0]); v[i * 8 + 1] = fmaf(f.y, rs, v[i * 8 + 1]);
+            f = unpack_h<F16>(rres[i].y); v[i * 8 + 2] = fmaf(f.x, rs, v[i * 8 + 2]); v[i * 8 + 3] = fmaf(f.y, rs, v[i * 8 + 3]);
+            f = unpack_h<F16>(rres[i].z); v[i * 8 + 4] = fmaf(f.x, rs, v[i * 8 + 4]); v[i * 8 + 5] = fmaf(f.y, rs, v[i * 8 + 5]);
+            f = unpack_h<F16>(rres[i].w); v[i * 8 + 6] = fmaf(f.x, rs, v[i * 8 + 6]); v[i * 8 + 7] = fmaf(f.y, rs, v[i * 8 + 7]);
           }
         } else if (p.res != nullptr) {
           const bf16* rp = p.res + ((size_t)(b * p.H + h) * p.res_Wp + (w + p.res_hl)) * p.res_ld + n;
 #pragma unroll
           for (int j = 0; j < CH; ++j)
-            if (n + j < p.N) v[j] += load_h<F16>(rp + j);
+            if (n + j < p.N) v[j] = fmaf(load_h<F16>(rp + j), p.res_scale, v[j]);
         }
         if (p.res_f32 != nullptr) {
           const float* rp = p.res_f32 + ((size_t)b * HW + pix) * p.res_f32_ld + n;
@@ -649,6 +652,7 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
     LIDM_REQUIRE(ep.residual.H == H && ep.residual.W == W && ep.residual.B == a.B, "residual shape mismatch");
     LIDM_REQUIRE(ep.residual.ld % 8 == 0, "residual ld");
     p.res = ep.residual.p; p.res_ld = ep.residual.ld; p.res_hl = ep.residual.hl; p.res_Wp = ep.residual.Wp();
+    p.res_scale = ep.res_scale;
   }
   if (ep.out.p != nullptr) {
     LIDM_REQUIRE(ep.out.H == H && ep.out.W == W && ep.out.B == a.B, "output shape mismatch");

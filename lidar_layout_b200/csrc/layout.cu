@@ -359,6 +359,99 @@ __global__ void avgpool2_kernel(const bf16* __restrict__ x, int B, int H, int W,
   }
 }
 
+// ------------------------------------------------------------------------------------------------- R2DM FIR resampling
+// Resample(down=2) (unets/ops.py:52-143, window [1,3,3,1]/8 per axis): y[ho][wo] = sum_ij k_i k_j x[2ho+i-1][(2wo+j-1) mod W]
+__global__ void fir_down2_kernel(const bf16* __restrict__ x, int B, int H, int W, int xld, int C, bf16* __restrict__ y, int yld,
+                                 bool f16) {
+  const int vec = C >> 3, Ho = H / 2, Wo = W / 2;
+  const int64_t total = (int64_t)B * Ho * Wo * vec;
+  const float k[4] = {0.125f, 0.375f, 0.375f, 0.125f};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % vec);
+    int64_t r = i / vec;
+    const int wo = (int)(r % Wo);
+    r /= Wo;
+    const int ho = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int hs = 2 * ho + a - 1;
+      if (hs < 0 || hs >= H) continue;
+      float row[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        int ws = 2 * wo + c - 1;
+        ws = ws < 0 ? ws + W : (ws >= W ? ws - W : ws);
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + ((size_t)(b * H + hs) * W + ws) * xld) + cv);
+        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = unpack_hr(uu[q], f16);
+          row[2 * q] = fmaf(k[c], f.x, row[2 * q]);
+          row[2 * q + 1] = fmaf(k[c], f.y, row[2 * q + 1]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = fmaf(k[a], row[q], acc[q]);
+    }
+    uint4 o;
+    o.x = pack_hr(acc[0], acc[1], f16); o.y = pack_hr(acc[2], acc[3], f16);
+    o.z = pack_hr(acc[4], acc[5], f16); o.w = pack_hr(acc[6], acc[7], f16);
+    reinterpret_cast<uint4*>(y + ((size_t)(b * Ho + ho) * Wo + wo) * yld)[cv] = o;
+  }
+}
+
+// Resample(up=2): zero insertion + [1,3,3,1]/4 per axis = y[2m] = x[m-1]/4 + 3 x[m]/4, y[2m+1] = 3 x[m]/4 + x[m+1]/4 on both axes
+__global__ void fir_up2_kernel(const bf16* __restrict__ x, int B, int H, int W, int xld, int C, bf16* __restrict__ y, int yld,
+                               int yhl, int yhr, bool f16) {
+  const int vec = C >> 3, Ho = H * 2, Wo = W * 2;
+  const int64_t total = (int64_t)B * Ho * Wo * vec;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % vec);
+    int64_t r = i / vec;
+    const int wo = (int)(r % Wo);
+    r /= Wo;
+    const int ho = (int)(r % Ho);
+    const int b = (int)(r / Ho);
+    // the two source rows / columns and their weights (the first listed is the far one, weight 1/4)
+    const int h_far = (ho & 1) ? ho / 2 + 1 : ho / 2 - 1, h_near = ho / 2;
+    int w_far = (wo & 1) ? wo / 2 + 1 : wo / 2 - 1;
+    const int w_near = wo / 2;
+    w_far = w_far < 0 ? w_far + W : (w_far >= W ? w_far - W : w_far);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const int hs = a ? h_near : h_far;
+      const float kh = a ? 0.75f : 0.25f;
+      if (hs < 0 || hs >= H) continue;
+      float row[8];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int ws = c ? w_near : w_far;
+        const float kw = c ? 0.75f : 0.25f;
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + ((size_t)(b * H + hs) * W + ws) * xld) + cv);
+        const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = unpack_hr(uu[q], f16);
+          row[2 * q] = c ? fmaf(kw, f.x, row[2 * q]) : kw * f.x;
+          row[2 * q + 1] = c ? fmaf(kw, f.y, row[2 * q + 1]) : kw * f.y;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = fmaf(kh, row[q], acc[q]);
+    }
+    uint4 o;
+    o.x = pack_hr(acc[0], acc[1], f16); o.y = pack_hr(acc[2], acc[3], f16);
+    o.z = pack_hr(acc[4], acc[5], f16); o.w = pack_hr(acc[6], acc[7], f16);
+    const size_t rowbase = (size_t)(b * Ho + ho) * (Wo + yhl + yhr);      // circular halo columns for the conv that follows
+    reinterpret_cast<uint4*>(y + (rowbase + wo + yhl) * yld)[cv] = o;
+    if (wo < yhr) reinterpret_cast<uint4*>(y + (rowbase + Wo + yhl + wo) * yld)[cv] = o;
+    if (wo >= Wo - yhl) reinterpret_cast<uint4*>(y + (rowbase + (wo - (Wo - yhl))) * yld)[cv] = o;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------- layout encoder
 // LayoutTransformerEncoder.forward (lidm/modules/encoders/layout_encoder.py:222-281) with its Transformer /
 // ResidualAttentionBlock / QKVMultiheadAttention / MLP (:32-137) for the shipped condition types (obj_class, obj_bbox,
@@ -578,6 +671,27 @@ void launch_oaca_layout_kv(const float* xf_out, const float* cls, int B, int E, 
   const size_t sh = ((size_t)E * Lt + 64) * sizeof(float);
   LIDM_REQUIRE(sh <= 48 * 1024, "layout token projection: shared memory");
   oaca_layout_kv_kernel<<<B, 256, sh, s>>>(xf_out, cls, E, Lt, gamma, beta, 1e-5f, Wc, bc, C, scale, klay, vlay, f16);
+  LIDM_CUDA_CHECK(cudaGetLastError());
+  LIDM_COUNT_LAUNCH(1);
+}
+
+static int fir_grid(int64_t total) {
+  int64_t g = (total + 255) / 256;
+  return (int)(g > 148 * 16 ? 148 * 16 : g);
+}
+void launch_fir_down2(const View& x, const View& y, cudaStream_t s) {
+  LIDM_REQUIRE(x.hl + x.hr + y.hl + y.hr == 0 && y.H * 2 == x.H && y.W * 2 == x.W && y.C == x.C && y.B == x.B && x.C % 8 == 0 &&
+                   x.f16 == y.f16 && x.wpitch == 0 && y.wpitch == 0, "FIR downsampling shapes");
+  const int64_t total = (int64_t)y.B * y.H * y.W * (y.C / 8);
+  fir_down2_kernel<<<fir_grid(total), 256, 0, s>>>(x.p, x.B, x.H, x.W, x.ld, x.C, y.p, y.ld, x.f16);
+  LIDM_CUDA_CHECK(cudaGetLastError());
+  LIDM_COUNT_LAUNCH(1);
+}
+void launch_fir_up2(const View& x, const View& y, cudaStream_t s) {
+  LIDM_REQUIRE(x.hl + x.hr == 0 && y.H == 2 * x.H && y.W == 2 * x.W && y.C == x.C && y.B == x.B && x.C % 8 == 0 && x.f16 == y.f16 &&
+                   x.wpitch == 0 && y.wpitch == 0, "FIR upsampling shapes");
+  const int64_t total = (int64_t)y.B * y.H * y.W * (y.C / 8);
+  fir_up2_kernel<<<fir_grid(total), 256, 0, s>>>(x.p, x.B, x.H, x.W, x.ld, x.C, y.p, y.ld, y.hl, y.hr, x.f16);
   LIDM_CUDA_CHECK(cudaGetLastError());
   LIDM_COUNT_LAUNCH(1);
 }

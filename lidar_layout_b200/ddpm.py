@@ -281,6 +281,38 @@ class LatentDiffusion:
         return self.sample(cond=cond, batch_size=batch_size, return_intermediates=True, **kwargs)
 
 
+class R2DMDiffusion(LatentDiffusion):
+    """Drop-in for the sampling-side API of lidm.models.diffusion.ddpm_r2dm.R2DMDiffusion (ddpm_r2dm.py:11-380): the
+    pixel-space range-image diffusion.  Same DDPM schedule / ancestral sampler / DDIM sampler as LatentDiffusion; the
+    denoiser is the EfficientUNet (efficient_unet.py:188-295) and there is no first stage."""
+
+    def __init__(self, cfg: LidmConfig, device: Optional[torch.device] = None, use_ema: bool = True,
+                 precision: Optional[str] = None):
+        if cfg.unet.unet_type != "efficient":
+            raise ValueError("R2DMDiffusion needs an EfficientUNet configuration")
+        super().__init__(cfg, device, use_ema, precision)
+        self.first_stage_model = None
+        self.lidar_utils_config = dict(log_scale=cfg.dataset.log_scale, depth_range=list(cfg.dataset.depth_range))
+
+    @classmethod
+    def from_config(cls, config, device=None, use_ema=True, precision=None):
+        cfg = from_yaml(config) if isinstance(config, str) else from_reference_dict(config)
+        return cls(cfg, device, use_ema, precision)
+
+    @torch.no_grad()
+    def apply_model(self, x_noisy, t, cond=None, return_ids=False):
+        """ddpm_r2dm.py:274-286 -> DiffusionWrapper.forward (conditioning_key None) -> EfficientUNet.forward."""
+        assert not return_ids
+        if cond not in (None, {}) and not (isinstance(cond, (list, tuple)) and all(c is None for c in cond)):
+            raise ValueError("the R2DM model on the B200 path is unconditional")
+        return self.engine.unet_forward(x_noisy, t)
+
+    def decode_first_stage(self, z, *a, **k):
+        raise NotImplementedError("R2DMDiffusion is a pixel-space model: there is no first stage")
+
+    encode_first_stage = decode_first_stage
+
+
 def range_images_to_points(x, dataset_cfg):
     """custom_to_pcd for a whole batch on the device (scripts/sample.py:29-35): x (B,1,H,W) in [-1,1] ->
     xyz (B,3,H,W) fp32 with -1 where masked, mask (B,H,W) uint8."""

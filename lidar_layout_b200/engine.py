@@ -30,6 +30,8 @@ def to_cconfig(cfg: LidmConfig) -> _lib.CConfig:
     if cfg.conditioning_key not in (None, "concat", "crossattn", "hybrid", "layout_crossattn"):
         raise NotImplementedError(f"conditioning_key {cfg.conditioning_key!r} is not on the B200 path "
                                   "(supported: None, 'concat', 'crossattn', 'hybrid', 'layout_crossattn')")
+    if u.unet_type == "efficient":
+        return _eff_cconfig(cfg)
     layout = u.unet_type == "layout"
     if layout != (cfg.conditioning_key == "layout_crossattn"):
         raise ValueError("conditioning_key 'layout_crossattn' goes with LayoutDiffusionUNetModel (and vice versa)")
@@ -85,6 +87,33 @@ def to_cconfig(cfg: LidmConfig) -> _lib.CConfig:
             raise ValueError("layout encoder: hidden_dim must equal the U-Net's encoder_channels, output_dim 4*model_channels")
         c.enc_layers, c.enc_heads, c.enc_out_dim = int(le.num_layers), int(le.num_heads), int(le.output_dim)
         c.enc_num_classes = int(le.num_classes_for_layout_object)
+    return c
+
+
+def _eff_cconfig(cfg: LidmConfig) -> _lib.CConfig:
+    """struct lidm_config for the pixel-space R2DM model (unet_type 2): no first stage."""
+    u = cfg.unet
+    if cfg.conditioning_key is not None:
+        raise NotImplementedError("R2DM: only the unconditional model is on the B200 path")
+    if tuple(u.image_size) != tuple(cfg.image_size) or u.in_channels != cfg.channels or len(u.channel_mult) != 4:
+        raise ValueError("R2DM: unet resolution / channels must match the image, four levels")
+    modes = {"bf16": 0, "fp16": 2}
+    if cfg.precision not in modes:
+        raise ValueError("R2DM: precision must be 'bf16' or 'fp16'")
+    c = _lib.CConfig()
+    c.unet_type = 2
+    c.in_channels = c.out_channels = c.latent_channels = u.in_channels
+    c.model_channels = u.model_channels
+    c.n_channel_mult = 4
+    for i, m in enumerate(u.channel_mult):
+        c.channel_mult[i] = m
+    for i, n in enumerate(u.num_residual_blocks):
+        c.eff_res_blocks[i] = n
+    c.eff_gn_groups, c.eff_attn_heads, c.eff_gn_eps = int(u.gn_num_groups), int(u.num_heads), float(u.gn_eps)
+    c.latent_h, c.latent_w = cfg.image_size
+    c.scale_factor = 1.0
+    c.precision = modes[cfg.precision]
+    c.ae_precision = 0
     return c
 
 

@@ -219,9 +219,58 @@ def layout_unet_param_spec(cfg: UNetConfig, prefix: str = UNET_PREFIX) -> "Order
     return spec
 
 
+def efficient_unet_param_spec(cfg: UNetConfig, prefix: str = UNET_PREFIX) -> "OrderedDict[str, Tuple[tuple, str]]":
+    """EfficientUNet tensors (reference lidm/modules/unets/efficient_unet.py:188-260, coords_encoding 'fourier_features':
+    the `coords` / `coords_encoding.*` / `*.scale` buffers are constants and not part of the spec)."""
+    spec: OrderedDict = OrderedDict()
+    mc, ted = cfg.model_channels, cfg.model_channels * 4
+    H, W = cfg.image_size
+    extra = 2 * (int(np.ceil(np.log2(H))) + int(np.ceil(np.log2(W))))
+    _linear(spec, prefix + "time_embedding.1", ted, mc)
+    _linear(spec, prefix + "time_embedding.3", ted, ted)
+    C = [mc] + [mc * m for m in cfg.channel_mult]
+    N = list(cfg.num_residual_blocks)
+    _conv(spec, prefix + "in_conv", C[0], cfg.in_channels + extra, 3, 3)
+
+    def block(p, cin, cout, n, down=False, up=False, attn=False):
+        if down:
+            _conv(spec, p + ".downsample.0", cout, cin, 3, 3)
+        for i in range(n):
+            rp = f"{p}.residual_blocks.{i}"
+            ci = cout if (i != 0 or down) else cin
+            _norm(spec, rp + ".norm1", ci)
+            _conv(spec, rp + ".conv1", cout, ci, 3, 3)
+            _linear(spec, rp + ".norm2.proj.1", 2 * cout, ted)
+            _conv(spec, rp + ".conv2", cout, cout, 3, 3, zero_init=True)
+            if ci != cout:
+                _conv(spec, rp + ".skip", cout, ci, 1, 1)
+        if attn:
+            ap = p + ".self_attn_block"
+            _norm(spec, ap + ".norm", cout)
+            spec[ap + ".attn.in_proj_weight"] = ((3 * cout, cout), "conv")
+            spec[ap + ".attn.in_proj_bias"] = ((3 * cout,), "bias")
+            spec[ap + ".attn.out_proj.weight"] = ((cout, cout), "conv_zero")
+            spec[ap + ".attn.out_proj.bias"] = ((cout,), "bias")
+        if up:
+            _conv(spec, p + ".upsample.1", cout, cout, 3, 3)
+
+    block(prefix + "d_block1", C[0], C[1], N[0])
+    block(prefix + "d_block2", C[1], C[2], N[1], down=True)
+    block(prefix + "d_block3", C[2], C[3], N[2], down=True)
+    block(prefix + "d_block4", C[3], C[4], N[3], down=True, attn=True)
+    block(prefix + "u_block4", C[4], C[3], N[3], up=True, attn=True)
+    block(prefix + "u_block3", 2 * C[3], C[2], N[2], up=True)
+    block(prefix + "u_block2", 2 * C[2], C[1], N[1], up=True)
+    block(prefix + "u_block1", 2 * C[1], C[0], N[0])
+    _conv(spec, prefix + "out_conv", cfg.out_channels, C[0], 3, 3, zero_init=True)
+    return spec
+
+
 def unet_param_spec(cfg: UNetConfig, prefix: str = UNET_PREFIX) -> "OrderedDict[str, Tuple[tuple, str]]":
     if cfg.unet_type == "layout":
         return layout_unet_param_spec(cfg, prefix)
+    if cfg.unet_type == "efficient":
+        return efficient_unet_param_spec(cfg, prefix)
     spec: OrderedDict = OrderedDict()
     mc, ted = cfg.model_channels, cfg.time_embed_dim
     _linear(spec, prefix + "time_embed.0", ted, mc)
@@ -383,7 +432,8 @@ def random_layout_encoder_state_dict(cfg: LidmConfig, seed: int = 0, as_torch: b
 
 def param_spec(cfg: LidmConfig):
     spec = unet_param_spec(cfg.unet)
-    spec.update(ae_param_spec(cfg.ae))
+    if cfg.unet.unet_type != "efficient":       # the pixel-space R2DM model has no first stage
+        spec.update(ae_param_spec(cfg.ae))
     return spec
 
 

@@ -1,0 +1,99 @@
+"""GPU (-m gpu): the R2DM pixel-space denoiser (EfficientUNet; SURVEY.md section 8 f4, BASELINE config 5) through the C ABI
+against fixtures of the UNMODIFIED reference module (tests/golden/r2dm_{small,full}.npz): ring-padded convs, AdaGN (FiLM on a
+GroupNorm without affine), FIR x2 resampling, nn.MultiheadAttention at head widths 64 and 32, 1/sqrt 2 residual scaling.
+north_star: eps within 2e-2 relative L2 in bf16."""
+import dataclasses
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from lidar_layout_b200 import config as C
+from lidar_layout_b200.weights import UNET_PREFIX, random_state_dict
+from oracle import r2dm_ref as RR
+from oracle import torch_ref as R
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel(a, b):
+    return R.rel_l2(a.detach().cpu(), b)
+
+
+@pytest.fixture(scope="module", params=["r2dm_small", "r2dm_full"])
+def setup(request, built_lib):
+    import lidar_layout_b200 as L
+    name = request.param
+    cfg = C.tiny_r2dm() if name.endswith("small") else C.nuscenes_r2dm()
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    model = L.R2DMDiffusion(cfg, use_ema=False)
+    model.load_state_dict(random_state_dict(cfg, 0))
+    return name, cfg, g, model
+
+
+def test_efficient_unet_eps(setup):
+    name, cfg, g, model = setup
+    x, t = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda()
+    e = model.apply_model(x, t, None)
+    err = rel(e, g["eps"])
+    print(f"[{name}] EfficientUNet eps rel {err:.3e}")
+    assert err < 2e-2
+    e1 = model.apply_model(x[:1], t[:1], None)
+    assert torch.equal(e1[0], e[0])                       # batch-invariant, deterministic
+
+
+def test_fp16_mode(setup):
+    import lidar_layout_b200 as L
+    name, cfg, g, _ = setup
+    m16 = L.R2DMDiffusion(cfg, use_ema=False, precision="fp16")
+    m16.load_state_dict(random_state_dict(cfg, 0))
+    e = m16.apply_model(torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda(), None)
+    err = rel(e, g["eps"])
+    print(f"[{name}] EfficientUNet eps rel (fp16 mode) {err:.3e}")
+    assert err < 5e-3
+
+
+def test_r2dm_ddim_loop(setup):
+    """DDIMSampler over the pixel-space model: fused on-device loop == step-by-step path bit for bit; the small config also
+    against the oracle's loop on the host."""
+    import lidar_layout_b200 as L
+    from lidar_layout_b200 import ops
+    name, cfg, g, model = setup
+    x = torch.from_numpy(g["x"]).cuda()
+    B, S = x.shape[0], 4
+    sampler = L.DDIMSampler(model)
+    z, _ = sampler.sample(S, batch_size=B, shape=cfg.latent_shape, eta=0.0, x_T=x.clone(), verbose=False)
+    ts, tab = sampler.ddim_timesteps, sampler.ddim_table
+    xs = x.clone()
+    for i, step in enumerate(np.flip(ts)):
+        e = model.apply_model(xs, torch.full((B,), int(step), dtype=torch.long).cuda(), None)
+        xs, _ = ops.ddim_step(xs, e, tab[S - 1 - i])
+    assert torch.equal(xs, z)
+    if name.endswith("small"):
+        u = cfg.unet
+        sd = {k[len(UNET_PREFIX):]: v for k, v in random_state_dict(cfg, 0).items()}
+        xr = torch.from_numpy(g["x"])
+        for i, step in enumerate(np.flip(ts)):
+            e = RR.efficient_unet_forward(sd, xr, torch.full((B,), int(step), dtype=torch.long), resolution=u.image_size,
+                                          base_channels=u.model_channels, channel_multiplier=u.channel_mult,
+                                          num_residual_blocks=u.num_residual_blocks, gn_num_groups=u.gn_num_groups,
+                                          gn_eps=u.gn_eps, attn_num_heads=u.num_heads)
+            xr, _ = R.ddim_step(xr, e, tab[S - 1 - i])
+        err = rel(z, xr)
+        print(f"[{name}] 4-step DDIM image rel {err:.3e}")
+        assert err < 1e-2
+
+
+def test_no_first_stage(built_lib):
+    import lidar_layout_b200 as L
+    from lidar_layout_b200._lib import LidmError
+    cfg = C.tiny_r2dm()
+    model = L.R2DMDiffusion(cfg, use_ema=False)
+    model.load_state_dict(random_state_dict(cfg, 0))
+    with pytest.raises(NotImplementedError):
+        model.decode_first_stage(torch.zeros(1, 2, 16, 512).cuda())
+    with pytest.raises(LidmError):
+        model.engine.vq_decode(torch.zeros(1, 2, 16, 512).cuda())
