@@ -132,12 +132,16 @@ WORKLOADS = {
     "layout2lidar": ("nuscenes_layout2lidar", "layout-conditioned LiDM nuScenes 32x1024 (models/lidm/nuscenes/layout2lidar, "
                                               "LayoutDiffusionUNetModel, synthetic layout_outputs for 13 objects, random-init), "
                                               "DDIM-50 eta=0 + VQ decode + back-projection", 50 * 83.2 + 0.27 + 59.5),
+    # BASELINE config 5: the R2DM pixel-space model (EfficientUNet, 2-channel 64x1024 range images), DDIM-256, no first stage
+    "r2dm": ("nuscenes_r2dm", "R2DM pixel-space range-image diffusion (configs/r2dm, EfficientUNet, 64x1024, random-init), "
+                              "DDIM-256 eta=0 + back-projection", 256 * 228.975),
 }
+WORKLOAD_STEPS = {"r2dm": 256}
 
 
 def workload_config(B, world, name="uncond"):
     return {"workload": WORKLOADS[name][1],
-            "batch_per_gpu": B, "global_batch": B * world, "ddim_steps": DDIM_STEPS,
+            "batch_per_gpu": B, "global_batch": B * world, "ddim_steps": WORKLOAD_STEPS.get(name, DDIM_STEPS),
             "l2": "working set per step (GBs of activations + 0.5 GB weights) >> 126 MB L2",
             "parallelism": f"batch-sharded x{world}, one all-gather of range images"}
 
@@ -281,16 +285,21 @@ def run_gpu_arm(args):
     from lidar_layout_b200 import _lib, config as C, parallel
     from lidar_layout_b200.weights import random_state_dict
 
-    cfg = getattr(C, WORKLOADS[args.workload][0])()
+    r2dm = args.workload == "r2dm"
+    cfg = C.nuscenes_r2dm((64, 1024)) if r2dm else getattr(C, WORKLOADS[args.workload][0])()
     B = args.batch
+    n_ddim = WORKLOAD_STEPS.get(args.workload, DDIM_STEPS)
     sd = random_state_dict(cfg, 0)
-    model = L.LatentDiffusion(cfg, device=dev, use_ema=False, precision=args.precision, ae_precision=args.ae_precision)
+    if r2dm:
+        model = L.R2DMDiffusion(cfg, device=dev, use_ema=False, precision=None if args.precision == "bf16" else args.precision)
+    else:
+        model = L.LatentDiffusion(cfg, device=dev, use_ema=False, precision=args.precision, ae_precision=args.ae_precision)
     model.load_state_dict(sd)
     cfg = model.cfg
     sampler = L.DDIMSampler(model)
-    sampler.make_schedule(DDIM_STEPS, ddim_eta=0.0)
+    sampler.make_schedule(n_ddim, ddim_eta=0.0)
     ts, table = sampler.ddim_timesteps, sampler.ddim_table
-    assert len(ts) == DDIM_STEPS
+    assert len(ts) == n_ddim
     ds = cfg.dataset
     global_B = B * world
     x_T_global, _ = parallel.global_noise((global_B,) + tuple(cfg.latent_shape), seed=1000)
@@ -314,9 +323,12 @@ def run_gpu_arm(args):
             cond[f"image_patch_bbox_embedding_for_resolution{r}"] = torch.randn((1, E, r * 16 * r), generator=gctx).to(dev)
         cond_kw = dict(layout_cond=cond)
 
+    def decode(z):      # first-stage decode; the pixel-space model's sample is the image: channel 0 = depth
+        return z[:, :1].contiguous() if r2dm else eng.vq_decode(z)
+
     def device_step():
         z, _ = eng.ddim_sample(x_T_dev, ts, table, **cond_kw)
-        img = eng.vq_decode(z)
+        img = decode(z)
         xyz, mask = L.ops.backproject(img, ds.fov, ds.depth_range, ds.depth_scale, ds.log_scale)
         if world > 1:
             img = parallel.all_gather_batch(img, global_B)
@@ -329,8 +341,8 @@ def run_gpu_arm(args):
         # the call sequence a reference user makes (scripts/sample.py:89-110,129), host buffers in and out
         x = x_T_host.to(dev, non_blocking=True)
         with model.ema_scope("Plotting"):
-            z, _ = sampler.sample(DDIM_STEPS, batch_size=B, shape=cfg.latent_shape, eta=0.0, x_T=x, conditioning=cond)
-        img = model.decode_first_stage(z)
+            z, _ = sampler.sample(n_ddim, batch_size=B, shape=cfg.latent_shape, eta=0.0, x_T=x, conditioning=cond)
+        img = z[:, :1].contiguous() if r2dm else model.decode_first_stage(z)
         xyz, mask = L.ops.backproject(img, ds.fov, ds.depth_range, ds.depth_scale, ds.log_scale)
         if world > 1:
             img = parallel.all_gather_batch(img, global_B)
@@ -382,12 +394,12 @@ def run_gpu_arm(args):
         z, _ = eng.ddim_sample(x_T_dev, ts, table, **cond_kw)
         prof_unet = _lib.profile_end()
         _lib.profile_begin()
-        img = eng.vq_decode(z)
+        img = decode(z)
         prof_dec = _lib.profile_end()
         peaks = measured_peaks()
         g = prof_unet["conv_gemm"]
         ach = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
-        unet_ms = sum(v["ms"] for v in prof_unet.values()) / DDIM_STEPS
+        unet_ms = sum(v["ms"] for v in prof_unet.values()) / n_ddim
         roof = {
             "bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit-GEMM conv, all U-Net launches of one DDIM-50 loop)",
             "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
@@ -417,7 +429,7 @@ def run_gpu_arm(args):
 
         def strong_step():
             z, _ = eng.ddim_sample(xs_dev, ts, table, **cs_kw)
-            img = eng.vq_decode(z)
+            img = decode(z)
             xyz, mask = L.ops.backproject(img, ds.fov, ds.depth_range, ds.depth_scale, ds.log_scale)
             return parallel.all_gather_batch(img, B), xyz, mask
 
@@ -472,7 +484,7 @@ def run_gpu_arm(args):
         line = {
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": DTYPE_NAMES[(cfg.precision, cfg.ae_precision_resolved)],
+            "vs_baseline": None, "dtype": (cfg.precision + ", fp32 accumulate") if r2dm else DTYPE_NAMES[(cfg.precision, cfg.ae_precision_resolved)],
             "data": "synthetic",
             "config": workload_config(B, world, args.workload),
             "ms_per_unet_step": unet_ms,

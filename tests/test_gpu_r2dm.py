@@ -39,21 +39,21 @@ def test_efficient_unet_eps(setup):
     x, t = torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda()
     e = model.apply_model(x, t, None)
     err = rel(e, g["eps"])
-    print(f"[{name}] EfficientUNet eps rel {err:.3e}")
-    assert err < 2e-2
+    print(f"[{name}] EfficientUNet eps rel {err:.3e} (default mode: {cfg.precision})")
+    assert err < 5e-3
     e1 = model.apply_model(x[:1], t[:1], None)
     assert torch.equal(e1[0], e[0])                       # batch-invariant, deterministic
 
 
-def test_fp16_mode(setup):
+def test_bf16_mode(setup):
     import lidar_layout_b200 as L
     name, cfg, g, _ = setup
-    m16 = L.R2DMDiffusion(cfg, use_ema=False, precision="fp16")
+    m16 = L.R2DMDiffusion(cfg, use_ema=False, precision="bf16")
     m16.load_state_dict(random_state_dict(cfg, 0))
     e = m16.apply_model(torch.from_numpy(g["x"]).cuda(), torch.from_numpy(g["t"]).cuda(), None)
     err = rel(e, g["eps"])
-    print(f"[{name}] EfficientUNet eps rel (fp16 mode) {err:.3e}")
-    assert err < 5e-3
+    print(f"[{name}] EfficientUNet eps rel (bf16 mode) {err:.3e}")
+    assert err < 2e-2        # north_star's bf16 budget (measured 8.4e-3 small / 1.95e-2 shipped size: why fp16 is the default)
 
 
 def test_r2dm_ddim_loop(setup):
