@@ -218,6 +218,28 @@ int lidm_compact_points(const float* xyz, const uint8_t* mask, int32_t B, int32_
 int lidm_chamfer_nn(const float* xyz1, const float* xyz2, int32_t B, int32_t N, int32_t M, int32_t dim, float* dist1,
                     int32_t* idx1, float* dist2, int32_t* idx2, void* stream);
 
+/* The same with the rounding of the distance chosen: contract_fma != 0 evaluates fma(dz, dz, fma(dx, dx, dy*dy)), which is
+ * how nvcc compiles the reference's `dx*dx + dy*dy + dz*dz` (bit-identical to the reference extension built for sm_100,
+ * tests/test_gpu_eval_ref.py) and what lidm_chamfer_nn uses; 0 rounds every operation separately (the numpy form). */
+int lidm_chamfer_nn_ex(const float* xyz1, const float* xyz2, int32_t B, int32_t N, int32_t M, int32_t dim, float* dist1,
+                       int32_t* idx1, float* dist2, int32_t* idx2, int32_t contract_fma, void* stream);
+
+/* Backward of the Chamfer extension (chamfer_cuda.cpp:22-26 -> chamfer3D.cu:155-185, NmDistanceGradKernel): gradxyz1 (B,N,dim)
+ * and gradxyz2 (B,M,dim) are zeroed and receive 2 g (p - nn(p)) from both directions (atomics, like the reference). */
+int lidm_chamfer_backward(const float* xyz1, const float* xyz2, int32_t B, int32_t N, int32_t M, int32_t dim, const float* graddist1,
+                          const float* graddist2, const int32_t* idx1, const int32_t* idx2, float* gradxyz1, float* gradxyz2,
+                          void* stream);
+
+/* The reference's EMD extension (lidm/eval/modules/emd/emd.cpp:17-25 -> emd_cuda.cu:226-284, auction algorithm; called from
+ * lidm/eval/metric_utils.py:447-458 with eps 0.005, 50 iterations): xyz1 / xyz2 (B,n,3) fp32 in [0,1], n a multiple of 1024,
+ * B <= 512 (the reference's own limits).  dist (B,n) squared distance of every xyz1 point to its assigned xyz2 point;
+ * assignment (B,n) int32.  Workspaces are allocated from the stream's memory pool. */
+int lidm_emd_forward(const float* xyz1, const float* xyz2, int32_t B, int32_t n, float eps, int32_t iters, float* dist,
+                     int32_t* assignment, void* stream);
+/* emd_cuda.cu:286-316: gradxyz1 (B,n,3) = 2 g (p - assigned(p)); only xyz1 receives a gradient, as in the reference. */
+int lidm_emd_backward(const float* xyz1, const float* xyz2, const float* graddist, const int32_t* assignment, int32_t B, int32_t n,
+                      float* gradxyz1, void* stream);
+
 /* ---- operator-level entry points (the same kernels the model uses; exposed for parity tests and reuse) ---------
  * All tensors fp32 NCHW device pointers; conversions to the internal channels-last bf16 layout happen inside. */
 

@@ -223,7 +223,16 @@ void launch_to_uint8_image(const float* x, uint8_t* y, int64_t n, cudaStream_t s
 // xyz (B,3,HW) + mask (B,HW) -> points (B, HW, 3) with the valid points of sample b packed, in pixel order, at the
 // front of block b; counts (B) = number of valid points per sample
 // eval_kernels.cu: nearest point of set b (B,m,dim) for every point of set a (B,n,dim): squared distance + index
-void launch_nn_dist(const float* a, int n, const float* b, int m, int B, int dim, float* dist, int32_t* idx, cudaStream_t s);
+void launch_nn_dist(const float* a, int n, const float* b, int m, int B, int dim, float* dist, int32_t* idx, cudaStream_t s,
+                    bool fma = true);
+// Chamfer backward (chamfer3D.cu:155-185): grad_a / grad_b accumulate (callers zero them), one call per direction
+void launch_chamfer_grad(const float* a, int n, const float* b, int m, int B, int dim, const float* grad_dist, const int32_t* idx,
+                         float* grad_a, float* grad_b, cudaStream_t s);
+// EMD auction (emd_cuda.cu:226-284): workspace >= (7 * B * n + B) * 4 bytes
+void launch_emd_forward(const float* xyz1, const float* xyz2, int B, int n, float eps, int iters, float* dist, int32_t* assignment,
+                        void* workspace, cudaStream_t s, bool fma = true);
+void launch_emd_backward(const float* xyz1, const float* xyz2, const float* grad_dist, const int32_t* assignment, int B, int n,
+                         float* grad_xyz1, cudaStream_t s);
 void launch_compact_points(const float* xyz, const uint8_t* mask, int B, int HW, float* points, int32_t* counts,
                            cudaStream_t s);
 

@@ -3367,14 +3367,64 @@ int lidm_compact_points(const float* xyz, const uint8_t* mask, int32_t B, int32_
   });
 }
 
-int lidm_chamfer_nn(const float* xyz1, const float* xyz2, int32_t B, int32_t N, int32_t M, int32_t dim, float* dist1,
-                    int32_t* idx1, float* dist2, int32_t* idx2, void* stream) {
+int lidm_chamfer_nn_ex(const float* xyz1, const float* xyz2, int32_t B, int32_t N, int32_t M, int32_t dim, float* dist1,
+                       int32_t* idx1, float* dist2, int32_t* idx2, int32_t contract_fma, void* stream) {
   return guarded(nullptr, [&] {
     LIDM_REQUIRE(xyz1 && xyz2 && dist1 && idx1 && dist2 && idx2, "null tensor");
     LIDM_REQUIRE(B > 0 && N > 0 && M > 0 && (dim == 2 || dim == 3), "chamfer: B, N, M > 0 and dim 2 or 3");
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    launch_nn_dist(xyz1, N, xyz2, M, B, dim, dist1, idx1, s);
-    launch_nn_dist(xyz2, M, xyz1, N, B, dim, dist2, idx2, s);
+    launch_nn_dist(xyz1, N, xyz2, M, B, dim, dist1, idx1, s, contract_fma != 0);
+    launch_nn_dist(xyz2, M, xyz1, N, B, dim, dist2, idx2, s, contract_fma != 0);
+  });
+}
+
+int lidm_chamfer_nn(const float* xyz1, const float* xyz2, int32_t B, int32_t N, int32_t M, int32_t dim, float* dist1,
+                    int32_t* idx1, float* dist2, int32_t* idx2, void* stream) {
+  return lidm_chamfer_nn_ex(xyz1, xyz2, B, N, M, dim, dist1, idx1, dist2, idx2, 1, stream);
+}
+
+int lidm_chamfer_backward(const float* xyz1, const float* xyz2, int32_t B, int32_t N, int32_t M, int32_t dim, const float* graddist1,
+                          const float* graddist2, const int32_t* idx1, const int32_t* idx2, float* gradxyz1, float* gradxyz2,
+                          void* stream) {
+  return guarded(nullptr, [&] {
+    LIDM_REQUIRE(xyz1 && xyz2 && graddist1 && graddist2 && idx1 && idx2 && gradxyz1 && gradxyz2, "null tensor");
+    LIDM_REQUIRE(B > 0 && N > 0 && M > 0 && (dim == 2 || dim == 3), "chamfer: B, N, M > 0 and dim 2 or 3");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    LIDM_CUDA_CHECK(cudaMemsetAsync(gradxyz1, 0, (size_t)B * N * dim * sizeof(float), s));
+    LIDM_CUDA_CHECK(cudaMemsetAsync(gradxyz2, 0, (size_t)B * M * dim * sizeof(float), s));
+    launch_chamfer_grad(xyz1, N, xyz2, M, B, dim, graddist1, idx1, gradxyz1, gradxyz2, s);
+    launch_chamfer_grad(xyz2, M, xyz1, N, B, dim, graddist2, idx2, gradxyz2, gradxyz1, s);
+  });
+}
+
+int lidm_emd_forward(const float* xyz1, const float* xyz2, int32_t B, int32_t n, float eps, int32_t iters, float* dist,
+                     int32_t* assignment, void* stream) {
+  return guarded(nullptr, [&] {
+    LIDM_REQUIRE(xyz1 && xyz2 && dist && assignment, "null tensor");
+    // the limits of the reference extension (emd_cuda.cu:232-245)
+    LIDM_REQUIRE(B > 0 && B <= 512, "emd: the batch size should be no greater than 512");
+    LIDM_REQUIRE(n > 0 && n % 1024 == 0, "emd: the size of the point clouds should be a multiple of 1024");
+    LIDM_REQUIRE(iters >= 1, "emd: iters");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    void* ws = nullptr;
+    LIDM_CUDA_CHECK(cudaMallocAsync(&ws, ((size_t)7 * B * n + B) * 4, s));
+    try {
+      launch_emd_forward(xyz1, xyz2, B, n, eps, iters, dist, assignment, ws, s);
+    } catch (...) {
+      cudaFreeAsync(ws, s);
+      throw;
+    }
+    LIDM_CUDA_CHECK(cudaFreeAsync(ws, s));
+  });
+}
+
+int lidm_emd_backward(const float* xyz1, const float* xyz2, const float* graddist, const int32_t* assignment, int32_t B, int32_t n,
+                      float* gradxyz1, void* stream) {
+  return guarded(nullptr, [&] {
+    LIDM_REQUIRE(xyz1 && xyz2 && graddist && assignment && gradxyz1 && B > 0 && n > 0, "emd backward arguments");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    LIDM_CUDA_CHECK(cudaMemsetAsync(gradxyz1, 0, (size_t)B * n * 3 * sizeof(float), s));
+    launch_emd_backward(xyz1, xyz2, graddist, assignment, B, n, gradxyz1, s);
   });
 }
 

@@ -1,7 +1,8 @@
-"""GPU (-m gpu): the Chamfer nearest-neighbour kernel through the C ABI (`lidm_chamfer_nn`, mirrored by
-`eval_ops.chamfer_3DDist` / `chamfer_2DDist`) against the oracle: distances and indices bit-exact (same fp32 operation
-order, ties to the lowest index), ragged sizes, padded clouds as `compute_pairwise_cd_batch` builds them, and
-size-independent properties at range-image scale."""
+"""GPU (-m gpu): the evaluation-toolbox kernels through the C ABI (`lidm_chamfer_nn[_ex]`, `lidm_chamfer_backward`,
+`lidm_emd_forward`, `lidm_emd_backward`, mirrored by `eval_ops.chamfer_3DDist` / `chamfer_2DDist` / `emdModule`) against the
+oracle: distances, indices and auction assignments bit-exact (same fp32 operation order, ties to the lowest index), ragged
+sizes, padded clouds as `compute_pairwise_cd_batch` builds them, and size-independent properties at range-image scale.
+tests/test_gpu_eval_ref.py pins the same against the reference's own extensions."""
 import numpy as np
 import pytest
 import torch
@@ -11,9 +12,10 @@ pytestmark = pytest.mark.gpu
 from oracle import eval_ref as E
 
 
+@pytest.mark.parametrize("fma", [True, False])
 @pytest.mark.parametrize("dim", [3, 2])
 @pytest.mark.parametrize("shape", [(1, 1, 1), (2, 257, 1031), (3, 1024, 1024), (1, 2500, 513)])
-def test_matches_oracle_bit_exact(built_lib, dim, shape):
+def test_matches_oracle_bit_exact(built_lib, dim, shape, fma):
     from lidar_layout_b200.eval_ops import chamfer_2DDist, chamfer_3DDist
     B, N, M = shape
     rng = np.random.default_rng(B * 1000 + N + dim)
@@ -21,8 +23,10 @@ def test_matches_oracle_bit_exact(built_lib, dim, shape):
     b = (rng.normal(size=(B, M, dim)) * 20).astype(np.float32)
     b[:, M // 2] = b[:, 0]                                     # duplicated target point: the lower index must win
     mod = chamfer_3DDist() if dim == 3 else chamfer_2DDist()
+    mod.CONTRACT_FMA = fma
     d1, d2, i1, i2 = mod(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda())
-    r1, r2, j1, j2 = E.chamfer_forward(a, b)
+    # fma: the reference extension's rounding (the C oracle spells the fmaf() out); else the numpy form
+    r1, r2, j1, j2 = E.c_chamfer_forward(a, b, fma=True) if fma else E.chamfer_forward(a, b)
     assert d1.dtype == torch.float32 and i1.dtype == torch.int32 and d1.shape == (B, N) and i2.shape == (B, M)
     np.testing.assert_array_equal(i1.cpu().numpy(), j1)
     np.testing.assert_array_equal(i2.cpu().numpy(), j2)
@@ -77,3 +81,50 @@ def test_error_behaviour(built_lib):
         chamfer_3DDist()(torch.zeros(1, 4, 2, device="cuda"), torch.zeros(1, 4, 3, device="cuda"))
     with pytest.raises(ValueError):
         chamfer_3DDist()(torch.zeros(1, 4, 3), torch.zeros(1, 4, 3))
+
+
+@pytest.mark.parametrize("dim", [3, 2])
+def test_chamfer_backward_against_oracle(built_lib, dim):
+    from lidar_layout_b200.eval_ops import chamfer_2DDist, chamfer_3DDist
+    rng = np.random.default_rng(11 + dim)
+    a = (rng.normal(size=(3, 700, dim)) * 10).astype(np.float32)
+    b = (rng.normal(size=(3, 1300, dim)) * 10).astype(np.float32)
+    g1, g2 = rng.normal(size=(3, 700)).astype(np.float32), rng.normal(size=(3, 1300)).astype(np.float32)
+    ta, tb = torch.from_numpy(a).cuda().requires_grad_(), torch.from_numpy(b).cuda().requires_grad_()
+    d1, d2, i1, i2 = (chamfer_3DDist() if dim == 3 else chamfer_2DDist())(ta, tb)
+    ((d1 * torch.from_numpy(g1).cuda()).sum() + (d2 * torch.from_numpy(g2).cuda()).sum()).backward()
+    ra, rb = E.c_chamfer_backward(a, b, g1, g2, i1.cpu().numpy(), i2.cpu().numpy())
+    # the scatter into the other set is a sum of atomics (order free, as in the reference): equal up to reassociation
+    np.testing.assert_allclose(ta.grad.cpu().numpy(), ra, rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(tb.grad.cpu().numpy(), rb, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("shape,eps,iters", [((2, 1024), 0.005, 50), ((3, 2048), 0.005, 50), ((1, 4096), 0.002, 20), ((1, 1024), 0.005, 1)])
+def test_emd_matches_oracle_bit_exact(built_lib, shape, eps, iters):
+    """The auction through the C ABI (lidm_emd_forward) against the sequential C restatement: assignment and distances
+    identical (same arithmetic, same tie rules), gradient identical."""
+    from lidar_layout_b200.eval_ops import emdModule
+    B, n = shape
+    rng = np.random.default_rng(B * 7 + n)
+    a, b = rng.random((B, n, 3), dtype=np.float32), rng.random((B, n, 3), dtype=np.float32)
+    b[:, 5] = b[:, 900]                                      # duplicated object: equal values go to the lower index
+    ta = torch.from_numpy(a).cuda().requires_grad_()
+    dist, ass = emdModule()(ta, torch.from_numpy(b).cuda(), eps, iters)
+    rd, ra = E.c_emd_forward(a, b, eps, iters)
+    assert dist.dtype == torch.float32 and ass.dtype == torch.int32 and dist.shape == (B, n)
+    np.testing.assert_array_equal(ass.cpu().numpy(), ra)
+    np.testing.assert_array_equal(dist.detach().cpu().numpy(), rd)
+    g = rng.normal(size=(B, n)).astype(np.float32)
+    (dist * torch.from_numpy(g).cuda()).sum().backward()
+    np.testing.assert_array_equal(ta.grad.cpu().numpy(), E.c_emd_backward(a, b, g, ra))
+
+
+def test_emd_pairwise_and_limits(built_lib):
+    from lidar_layout_b200.eval_ops import compute_pairwise_emd, emdModule
+    rng = np.random.default_rng(9)
+    x, y = rng.random((2500, 3), dtype=np.float32), rng.random((2100, 3), dtype=np.float32)   # truncated to 2048 points
+    assert compute_pairwise_emd(x, y) == pytest.approx(E.compute_pairwise_emd(x, y), rel=1e-6)
+    with pytest.raises(RuntimeError, match="multiple of 1024"):                              # emd_cuda.cu:242-245
+        emdModule()(torch.zeros(1, 1000, 3).cuda(), torch.zeros(1, 1000, 3).cuda(), 0.005, 5)
+    with pytest.raises(AssertionError):                                                      # emd_module.py:53
+        emdModule()(torch.zeros(1, 1024, 3).cuda(), torch.zeros(1, 2048, 3).cuda(), 0.005, 5)
