@@ -156,3 +156,34 @@ def test_ddim_inpainting_against_reference(model, monkeypatch):
     z, _ = L.DDIMSampler(model).sample(S, batch_size=B, shape=cfg.latent_shape, eta=0.0, x_T=torch.from_numpy(x_T).cuda(),
                                        mask=torch.from_numpy(g["mask"]).cuda(), x0=torch.from_numpy(x0).cuda())
     assert R.rel_l2(z.cpu(), g["final"]) < 1e-2
+
+
+def test_use_ema_selects_the_shadow_weights(built_lib):
+    """DDPM.ema_scope / LitEma.copy_to (ddpm.py:174-187, ema.py:46-57): with use_ema the `model_ema.*` shadow buffers (the
+    parameter names with the dots removed, ema.py:19-21) replace `model.*` for the denoiser; here they come from another seed."""
+    import lidar_layout_b200 as L
+    cfg = C.tiny()
+    sd_a, sd_b = random_state_dict(cfg, 0), random_state_dict(cfg, 7)
+    sd = dict(sd_a)
+    n_shadow = 0
+    for k, v in sd_b.items():
+        if k.startswith("model.diffusion_model."):
+            sd["model_ema." + k[len("model."):].replace(".", "")] = v
+            n_shadow += 1
+    sd["model_ema.decay"] = torch.tensor(0.9999)
+    sd["model_ema.num_updates"] = torch.tensor(12, dtype=torch.int)
+    assert n_shadow > 50
+
+    def eps_of(state, use_ema):
+        m = L.LatentDiffusion.from_config(tiny_yaml(cfg), use_ema=use_ema)
+        m.load_state_dict(state, strict=False)
+        g = torch.Generator().manual_seed(5)
+        x = torch.randn((2,) + tuple(cfg.latent_shape), generator=g).cuda()
+        t = torch.tensor([3, 700], device="cuda")
+        with m.ema_scope():
+            return m.apply_model(x, t, None)
+
+    e_shadow, e_plain = eps_of(sd, True), eps_of(sd, False)
+    assert torch.equal(e_shadow, eps_of(sd_b, False))            # the shadow weights, bit for bit
+    assert torch.equal(e_plain, eps_of(sd_a, False))             # use_ema=False ignores them
+    assert R.rel_l2(e_shadow.cpu(), e_plain.cpu()) > 0.1         # and the two really differ
