@@ -119,6 +119,11 @@ struct GemmEpilogue {
   // optional second A operand appended along K as one more (unshifted) tap: out += a2 * B[:, Kmain : Kmain + a2.C]
   // (a ResBlock's 1x1 skip convolution folded into its second conv: one GEMM, no skip tensor written or re-read)
   View a2;
+  // a2 as a RESIDUAL (out += a2, a2.C == N): the appended B block is the identity, so an output-channel tile only needs the
+  // a2 channels it covers - the kernel walks those K chunks alone.  The residual then arrives through the TMA ring as full
+  // 128-byte rows instead of per-thread 16-byte loads strided by the row pitch (ncu / A-B: 28 of the 65 us of the
+  // 256 -> 256 attention output projection at 16x128, B = 64), at the price of BN more K columns on an idle tensor pipe.
+  bool a2_diag = false;
   View out;                        // bf16 NHWC output (p == null => none); halos are written when hl/hr > 0
   // columns >= split_n go, transposed, to out_t[(b * (N - split_n) + (n - split_n)) * HW + pixel]  (V^T for attention)
   int split_n = 1 << 30;

@@ -115,7 +115,7 @@ struct ResW {
   // ResBlock up- (1) / down- (2) sampling of both h and x
   bool film = false; int updown = 0;
 };
-struct AttnW { NormW n; ConvW qkv, proj; int ch = 0, heads = 0; };
+struct AttnW { NormW n; ConvW qkv, proj; ConvW proj_id; /* proj with an identity block appended along K: the residual rides in as a second A operand */ int ch = 0, heads = 0; };
 // BasicTransformerBlock / SpatialTransformer weights (reference lidm/modules/attention.py:196-261)
 struct STBlockW {
   NormW n1, n2, n3;           // LayerNorms
@@ -1046,11 +1046,18 @@ struct Builder {
        4.0 * B * heads * (double)T * T * 32, 0, "attn T" + std::to_string(T) + " heads" + std::to_string(heads));
     release(bqk);
     {
+      static const bool no_idres = getenv("LIDM_NO_IDRES") != nullptr;   // A/B switch
       GemmEpilogue ep;
       ep.bias = a.proj.bias;
-      ep.residual = x;
       ep.out = dst;
-      gemm(ao, taps_1x1(), a.proj, ep);
+      if (a.proj_id.w != nullptr && !no_idres && x.wpitch == 0 && x.C == C && x.f16 == ao.f16) {
+        ep.a2 = x;               // out = proj(a) + x with x as a second A operand against an identity block
+        ep.a2_diag = true;
+        gemm(ao, taps_1x1(), a.proj_id, ep);
+      } else {
+        ep.residual = x;
+        gemm(ao, taps_1x1(), a.proj, ep);
+      }
     }
     release(ba);
   }
@@ -2038,6 +2045,27 @@ void run_plan_graphed(lidm_handle* h, Plan* P, int slot, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------- finalize
+// [W | I]: a 1x1 projection whose residual is added by the GEMM itself (GemmEpilogue::a2 + a2_diag): the residual tensor
+// streams through the TMA ring as a second A operand against the identity block.
+ConvW with_identity(Packer& pk, const ConvW& c) {
+  ConvW f = c;
+  if (c.w == nullptr || c.nseg != 1 || c.kh != 1 || c.kw != 1 || c.k_alloc != c.cin || c.cout % 256 != 0 || c.cout > 1024) {
+    f.w = nullptr;
+    return f;
+  }
+  lidm_handle* h = pk.h;
+  f.k_alloc = c.cin + c.cout;
+  f.w = dev_alloc<bf16>(h, (size_t)f.n_alloc * f.k_alloc);
+  LIDM_CUDA_CHECK(cudaMemcpy2DAsync(f.w, (size_t)f.k_alloc * sizeof(bf16), c.w, (size_t)c.k_alloc * sizeof(bf16),
+                                    (size_t)c.cin * sizeof(bf16), c.n_alloc, cudaMemcpyDeviceToDevice, pk.s));
+  std::vector<uint16_t> eye((size_t)f.n_alloc * c.cout, 0);
+  for (int i = 0; i < c.cout; ++i) eye[(size_t)i * c.cout + i] = pk.f16 ? 0x3c00 : 0x3f80;   // 1.0 as IEEE half / bf16
+  LIDM_CUDA_CHECK(cudaMemcpy2DAsync(f.w + c.cin, (size_t)f.k_alloc * sizeof(bf16), eye.data(), (size_t)c.cout * sizeof(bf16),
+                                    (size_t)c.cout * sizeof(bf16), f.n_alloc, cudaMemcpyHostToDevice, pk.s));
+  LIDM_CUDA_CHECK(cudaStreamSynchronize(pk.s));
+  return f;
+}
+
 ResW pack_res(Packer& pk, const std::string& p, int cin, int cout, int kh, int kw, bool unet) {
   ResW r;
   r.cin = cin; r.cout = cout;
@@ -2120,6 +2148,7 @@ AttnW pack_unet_attn(Packer& pk, const std::string& p, int ch, int heads) {
   LIDM_CUDA_CHECK(cudaMemcpy(c.bias, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice));
   a.qkv = c;
   a.proj = pk.conv(p + ".proj_out", ch, ch, 1, 1, 0, 2);   // its input (attention output) is exact bf16
+  if (!pk.precise) a.proj_id = with_identity(pk, a.proj);
   return a;
 }
 

@@ -39,6 +39,7 @@ struct GemmKernelParams {
   int b_koff[27];            // first K column of this virtual tap in the B matrix
   int kchunks;
   int k2chunks, hl2, b2_koff;  // second A operand (GemmEpilogue::a2): K chunks, its left halo, its first B column
+  int a2_diag;               // the a2 block of B is the identity: a channel tile reads only its own BN / 64 chunks of a2
   int N, H, W;
   int wt_batched;
   const float* bias;
@@ -57,6 +58,7 @@ struct GemmKernelParams {
   float* gst;                // GroupNorm granule statistics of the output (View::gst), or null
   int gst_ld, gst_slots, gst_slot0;
   int split_n;
+  int dbg;                   // developer experiments (LIDM_GEMM_DBG)
   bf16* out_t;
   float* out_f32_nchw;
   float* out_f32_nhwc;
@@ -86,19 +88,26 @@ __device__ __forceinline__ float gelu_erf_fast(float g) {
 // running CTAs share the A tile in L2; the weights are L2-resident anyway); two TMEM accumulator buffers let the MMA warp start tile i+1 while the epilogue warps drain tile i; the
 // tile's bias + timestep-embedding row is staged once in shared memory; bf16 outputs leave through a swizzled
 // shared-memory staging buffer and TMA stores (full 128-byte lines), double-buffered across tiles.
-template <int BN, int STAGES>
+// RESK > 0 (resident weights): a 1x1 GEMM whose whole K = RESK weight slice of one output-channel tile fits in shared
+// memory keeps it there for the life of the CTA - every CTA owns ONE output-channel tile and walks pixel tiles, the
+// ring of STAGES buffers then carries A chunks only.  With streamed weights a short-K tile re-reads its 2 * BN * K bytes of
+// B for every 128 pixels (128 KB of B against 64 KB of A at K = 256, BN = 256) and the 3-stage ring bounds the tile time
+// by the load latency (ncu: the epilogue warps spend 59 % of their samples waiting for the accumulator).
+template <int BN, int STAGES, int RESK = 0>
 struct PersistLayout {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int B_STRIDE = (B_STAGE_BYTES + 1023) / 1024 * 1024;
+  static constexpr int B_BUFS = RESK > 0 ? RESK / BK : STAGES;       // resident: one buffer per K chunk
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
   static constexpr int OUT_BOXES = BN >= 64 ? BN / 64 : 0;          // 64-channel TMA store boxes per tile
   static constexpr int OUT_BUF_BYTES = OUT_BOXES * BM * 128;        // bf16 staging for one tile
-  static constexpr int OUT_BUFS = BN > 128 ? 1 : 2;                 // staging buffers (double-buffered when they fit)
-  static constexpr int OUT_OFF = B_OFF + STAGES * B_STRIDE;
+  static constexpr int OUT_BUFS = (BN > 128 || RESK > 256) ? 1 : 2; // staging buffers (double-buffered when they fit)
+  static constexpr int OUT_OFF = B_OFF + B_BUFS * B_STRIDE;
   static constexpr int BIAS_OFF = OUT_OFF + OUT_BUFS * OUT_BUF_BYTES;
   static constexpr int BAR_OFF = BIAS_OFF + 2 * (BN < 32 ? 32 : BN) * 4;
   static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+  static_assert(TOTAL <= 227 * 1024, "shared memory budget");
   static constexpr uint32_t ACC_COLS = BN;                          // TMEM columns per accumulator buffer
   static constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   // epilogue warps: 4 cover the 128 TMEM lanes; wide tiles use two such groups, each draining half of the columns
@@ -110,26 +119,33 @@ struct PersistLayout {
   static constexpr int COLS = BN / (EPI_WARPS / 4);                 // columns drained by one epilogue thread
 };
 
-template <int BN, int STAGES, bool F16>
-__global__ void __launch_bounds__((PersistLayout<BN, STAGES>::THREADS), 1)
+template <int BN, int STAGES, bool F16, int RESK = 0>
+__global__ void __launch_bounds__((PersistLayout<BN, STAGES, RESK>::THREADS), 1)
 conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmA2,
                          const GemmKernelParams p, int num_m_tiles,
                          int num_tiles, int use_tma_store) {
-  using L = PersistLayout<BN, STAGES>;
+  using L = PersistLayout<BN, STAGES, RESK>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;       // [2] accumulator drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* bres_bar = tempty_bar + 2;        // resident weights have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
   float* sbias = reinterpret_cast<float*>(smem + L::BIAS_OFF);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform as far as the compiler can tell
   const int lane = threadIdx.x & 31;
-  const int num_it = p.ntaps * p.kchunks + p.k2chunks;
+  const int num_it = p.ntaps * p.kchunks + (p.a2_diag ? BN / BK : p.k2chunks);
   const int num_n_tiles = num_tiles / num_m_tiles;
+  // tile walk: streamed weights - tiles blockIdx.x, + gridDim.x, ... of the (pixel tile, channel tile) grid; resident weights -
+  // the CTA owns channel tile blockIdx.x % num_n_tiles and walks pixel tiles (the launcher makes gridDim.x a multiple of it)
+  const int tile_first = RESK > 0 ? (int)blockIdx.x / num_n_tiles : (int)blockIdx.x;
+  const int tile_step = RESK > 0 ? (int)gridDim.x / num_n_tiles : (int)gridDim.x;
+  const int tile_end = RESK > 0 ? num_m_tiles : num_tiles;
+  const int res_n0 = ((int)blockIdx.x % num_n_tiles) * BN;
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tmA);
@@ -138,6 +154,7 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (p.k2chunks) prefetch_tensormap(&tmA2);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], L::EPI_WARPS); }
+    mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, L::TMEM_COLS); tmem_relinquish(); }
@@ -150,45 +167,73 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // The whole warp walks the loop (warp-uniform control flow and operands: the compiler keeps tile coordinates, stage
+    // indices and descriptors in uniform registers); one elected lane issues the asynchronous instructions.  With the loop
+    // under `if (lane == 0)` every UTMALDG / UTCHMMA / UTCBAR was wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY
+    // retry loop over the "divergent" operands, several hundred clocks of single-thread overhead per K chunk.
+    {
+      const bool leader = elect_one() != 0;
       int s = 0; uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = p.n_fast ? tile / num_n_tiles : tile % num_m_tiles;
-        const int n0 = (p.n_fast ? tile % num_n_tiles : tile / num_m_tiles) * BN;
+      if (RESK > 0 && tile_first < tile_end) {
+        if (leader) {
+          mbar_arrive_expect_tx(bres_bar, L::B_BUFS * L::B_STAGE_BYTES);
+#pragma unroll
+          for (int kc = 0; kc < L::B_BUFS; ++kc)
+            tma_load_3d(smem + L::B_OFF + kc * L::B_STRIDE, &tmB, bres_bar, kc * BK, res_n0, 0);
+        }
+        __syncwarp();
+      }
+      for (int tile = tile_first; tile < tile_end; tile += tile_step) {
+        const int m_tile = RESK > 0 ? tile : (p.n_fast ? tile / num_n_tiles : tile % num_m_tiles);
+        const int n0 = RESK > 0 ? res_n0 : (p.n_fast ? tile % num_n_tiles : tile / num_m_tiles) * BN;
         const int bt = m_tile / p.tiles_per_img;
         const int b = bt * p.bbox;
         const int r = m_tile - bt * p.tiles_per_img;
         const int th = r / p.tiles_w;
         const int h0 = th * p.Hbox, w0 = (r - th * p.tiles_w) * p.Wbox;
-        int it = 0;
         for (int tap = 0; tap < p.ntaps; ++tap) {
           const int x = w0 + p.hl + p.dx[tap], y = h0 + p.dy[tap];
-          for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+          const int acoff = p.a_coff[tap], bkoff = p.b_koff[tap];
+          for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(&empty_bar[s], ph ^ 1);
-            mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + L::B_STAGE_BYTES);
-            tma_load_4d(smem + L::A_OFF + s * A_STAGE_BYTES, &tmA, &full_bar[s], p.a_coff[tap] + kc * BK, x, y, b);
-            tma_load_3d(smem + L::B_OFF + s * L::B_STRIDE, &tmB, &full_bar[s], p.b_koff[tap] + kc * BK, n0,
-                        p.wt_batched ? b : 0);
+            if (leader) {
+              if (RESK > 0) {
+                mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES);
+                tma_load_4d(smem + L::A_OFF + s * A_STAGE_BYTES, &tmA, &full_bar[s], acoff + kc * BK, x, y, b);
+              } else {
+                mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + L::B_STAGE_BYTES);
+                tma_load_4d(smem + L::A_OFF + s * A_STAGE_BYTES, &tmA, &full_bar[s], acoff + kc * BK, x, y, b);
+                tma_load_3d(smem + L::B_OFF + s * L::B_STRIDE, &tmB, &full_bar[s], bkoff + kc * BK, n0,
+                            p.wt_batched ? b : 0);
+              }
+            }
+            __syncwarp();
             if (++s == STAGES) { s = 0; ph ^= 1; }
           }
         }
-        for (int kc = 0; kc < p.k2chunks; ++kc) {     // second A operand: one unshifted tap after the main K range
+        const int k2lo = p.a2_diag ? n0 / BK : 0, k2hi = p.a2_diag ? (n0 + BN) / BK : p.k2chunks;
+        for (int kc = k2lo; kc < k2hi; ++kc) {        // second A operand: one unshifted tap after the main K range
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + L::B_STAGE_BYTES);
-          tma_load_4d(smem + L::A_OFF + s * A_STAGE_BYTES, &tmA2, &full_bar[s], kc * BK, w0 + p.hl2, h0, b);
-          tma_load_3d(smem + L::B_OFF + s * L::B_STRIDE, &tmB, &full_bar[s], p.b2_koff + kc * BK, n0,
-                      p.wt_batched ? b : 0);
+          if (leader) {
+            mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + L::B_STAGE_BYTES);
+            tma_load_4d(smem + L::A_OFF + s * A_STAGE_BYTES, &tmA2, &full_bar[s], kc * BK, w0 + p.hl2, h0, b);
+            tma_load_3d(smem + L::B_OFF + s * L::B_STRIDE, &tmB, &full_bar[s], p.b2_koff + kc * BK, n0,
+                        p.wt_batched ? b : 0);
+          }
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (whole warp in the loop, one elected lane issues)
+    {
+      const bool leader = elect_one() != 0;
       constexpr uint32_t idesc = make_idesc_h<F16>(BM, BN);
       int s = 0; uint32_t ph = 0;
       int lt = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      if (RESK > 0 && tile_first < tile_end) mbar_wait(bres_bar, 0);
+      for (int tile = tile_first; tile < tile_end; tile += tile_step, ++lt) {
         const int ab = lt & 1;
         mbar_wait(&tempty_bar[ab], ((lt >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
         tcgen05_fence_after();
@@ -197,13 +242,17 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           mbar_wait(&full_bar[s], ph);
           tcgen05_fence_after();
           const uint64_t adesc = make_kmajor_desc<128>(smem_u32(smem + L::A_OFF + s * A_STAGE_BYTES));
-          const uint64_t bdesc = make_kmajor_desc<128>(smem_u32(smem + L::B_OFF + s * L::B_STRIDE));
+          const uint64_t bdesc = make_kmajor_desc<128>(smem_u32(smem + L::B_OFF + (RESK > 0 ? it : s) * L::B_STRIDE));
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) umma_bf16_ss(d, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
-          umma_commit(&empty_bar[s]);
+            for (int k = 0; k < BK / 16; ++k) umma_bf16_ss(d, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+            umma_commit(&empty_bar[s]);
+          }
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tfull_bar[ab]);
+        if (leader) umma_commit(&tfull_bar[ab]);
+        __syncwarp();
       }
     }
   } else {
@@ -226,10 +275,174 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     constexpr int CH = BN < 32 ? BN : 32;
     constexpr int SB = BN < 32 ? 32 : BN;
     int lt = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+    if constexpr (RESK > 0) {
+      // ---- resident-weight tiles (BN = 128, bf16 output through TMA stores): the CTA's channel tile never changes, so the
+      // bias is staged once, and the per-tile chain is  residual of the NEXT tile requested -> accumulator -> registers ->
+      // staging -> ONE named barrier -> TMA store.  The staging buffer of tile t was last read by the store of tile t - 2,
+      // which thread 0 waits for before it arrives at the barrier of tile t - 1 (one whole tile after issuing it).
+      static_assert(BN == 128 && L::COLS == 64, "resident-weight epilogue: 128-column tiles, 64 columns per thread");
+      constexpr int NCH = 2;
+      for (int i = e; i < BN; i += L::EPI_THREADS) sbias[i] = (res_n0 + i < p.N && p.bias != nullptr) ? __ldg(p.bias + res_n0 + i) : 0.f;
+      named_bar_sync(1, L::EPI_THREADS);
+      const int n0 = res_n0;
+      const bool has_res = p.res != nullptr && !(p.dbg & 2);
+      auto tile_pixel = [&](int m_tile, int& b0, int& r, int& h0, int& w0) {
+        b0 = m_tile / p.tiles_per_img;
+        r = m_tile - b0 * p.tiles_per_img;
+        const int th = r / p.tiles_w;
+        h0 = th * p.Hbox; w0 = (r - th * p.tiles_w) * p.Wbox;
+      };
+      uint4 rnext[NCH][4];
+      auto load_res = [&](int m_tile) {
+        int b0, r, h0, w0;
+        tile_pixel(m_tile, b0, r, h0, w0);
+        const bf16* rp = p.res + ((size_t)(b0 * p.H + h0 + hh) * p.res_Wp + (w0 + ww + p.res_hl)) * p.res_ld + n0 + col_lo;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          if (n0 + col_lo + c * 32 < p.N) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rnext[c][i] = __ldg(reinterpret_cast<const uint4*>(rp + c * 32) + i);
+          }
+        }
+      };
+      if (has_res && tile_first < tile_end) load_res(tile_first);
+      for (int tile = tile_first; tile < tile_end; tile += tile_step, ++lt) {
+        const int ab = lt & 1;
+        int b0, r, h0, w0;
+        tile_pixel(tile, b0, r, h0, w0);
+        const int b = b0;
+        uint4 rres[NCH][4];
+        if (has_res) {
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rres[c][i] = rnext[c][i];
+          }
+          if (tile + tile_step < tile_end) load_res(tile + tile_step);
+        }
+        if constexpr (L::OUT_BUFS == 1) {
+          if (e == 0) tma_store_wait_read<0>();
+          named_bar_sync(1, L::EPI_THREADS);
+        }
+        const uint32_t taddr_row = tmem_base + ab * L::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+        uint8_t* stage_out = smem + L::OUT_OFF + (L::OUT_BUFS == 2 ? ab : 0) * L::OUT_BUF_BYTES;
+        mbar_wait(&tfull_bar[ab], (lt >> 1) & 1);
+        tcgen05_fence_after();
+        uint32_t raw[NCH][32];
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) tmem_ld_32x32b_x32(taddr_row + col_lo + c * 32, raw[c]);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[ab]);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int cc = col_lo + c * 32;
+          if (n0 + cc < p.N) {
+            float v[32];
+            const float4* sb4 = reinterpret_cast<const float4*>(sbias + cc);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 t = sb4[j];
+              v[4 * j] = __uint_as_float(raw[c][4 * j]) + t.x;
+              v[4 * j + 1] = __uint_as_float(raw[c][4 * j + 1]) + t.y;
+              v[4 * j + 2] = __uint_as_float(raw[c][4 * j + 2]) + t.z;
+              v[4 * j + 3] = __uint_as_float(raw[c][4 * j + 3]) + t.w;
+            }
+            if (has_res) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float2 f;
+                const float rs = p.res_scale;
+                f = unpack_h<F16>(rres[c][i].x); v[i * 8 + 0] = fmaf(f.x, rs, v[i * 8 + 0]); v[i * 8 + 1] = fmaf(f.y, rs, v[i * 8 + 1]);
+                f = unpack_h<F16>(rres[c][i].y); v[i * 8 + 2] = fmaf(f.x, rs, v[i * 8 + 2]); v[i * 8 + 3] = fmaf(f.y, rs, v[i * 8 + 3]);
+                f = unpack_h<F16>(rres[c][i].z); v[i * 8 + 4] = fmaf(f.x, rs, v[i * 8 + 4]); v[i * 8 + 5] = fmaf(f.y, rs, v[i * 8 + 5]);
+                f = unpack_h<F16>(rres[c][i].w); v[i * 8 + 6] = fmaf(f.x, rs, v[i * 8 + 6]); v[i * 8 + 7] = fmaf(f.y, rs, v[i * 8 + 7]);
+              }
+            }
+            if (p.geglu) {
+              const int oc = cc >> 1;
+              uint8_t* gb = stage_out + (oc >> 6) * (BM * 128) + row * 128;
+              const int gbase = (oc & 63) >> 3;
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                float o[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] = v[i * 8 + k] * gelu_erf_fast(v[16 + i * 8 + k]);
+                uint4 pk;
+                pk.x = pack_h<F16>(o[0], o[1]); pk.y = pack_h<F16>(o[2], o[3]);
+                pk.z = pack_h<F16>(o[4], o[5]); pk.w = pack_h<F16>(o[6], o[7]);
+                *reinterpret_cast<uint4*>(gb + (((gbase + i) ^ (row & 7)) << 4)) = pk;
+              }
+              continue;
+            }
+            uint8_t* box = stage_out + (cc >> 6) * (BM * 128) + row * 128;
+            const int cbase = (cc & 63) >> 3;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 pk;
+              pk.x = pack_h<F16>(v[i * 8 + 0], v[i * 8 + 1]);
+              pk.y = pack_h<F16>(v[i * 8 + 2], v[i * 8 + 3]);
+              pk.z = pack_h<F16>(v[i * 8 + 4], v[i * 8 + 5]);
+              pk.w = pack_h<F16>(v[i * 8 + 6], v[i * 8 + 7]);
+              *reinterpret_cast<uint4*>(box + (((cbase + i) ^ (row & 7)) << 4)) = pk;
+            }
+          }
+        }
+        fence_proxy_async();          // staging writes -> visible to the TMA engine
+        if constexpr (L::OUT_BUFS == 2) {
+          if (e == 0) tma_store_wait_read<0>();   // the other buffer's store (a tile ago) has been read: the next tile may refill it
+        }
+        named_bar_sync(2, L::EPI_THREADS);
+        if (e == 0 && !(p.dbg & 1)) {
+          if (p.geglu) {
+            if ((n0 >> 1) < (p.N >> 1)) tma_store_4d(&tmO, stage_out, n0 >> 1, w0, h0, b0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < L::OUT_BOXES; ++j)
+              if (n0 + j * 64 < p.N) tma_store_4d(&tmO, stage_out + j * (BM * 128), n0 + j * 64, w0, h0, b0);
+          }
+          tma_store_commit();
+        }
+        if (p.gst != nullptr && !(p.dbg & 4)) {
+          // GroupNorm statistics of the tile from the staged values: identical granule / lane / row order to the streamed
+          // path below (8 lanes per 8-channel granule, rows sub, sub + 8, ...), so the sums are the same bits
+          constexpr int GRAN = BN / 8;
+          constexpr int TPG = 8;
+          const int gi = e / TPG, sub = e % TPG;
+          float gs = 0.f, gq = 0.f;
+          if (gi < GRAN) {
+            const uint8_t* gbox = stage_out + (gi >> 3) * (BM * 128);
+#pragma unroll 4
+            for (int rr = sub; rr < BM; rr += TPG) {
+              const uint4 u = *reinterpret_cast<const uint4*>(gbox + rr * 128 + (((gi & 7) ^ (rr & 7)) << 4));
+              const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = unpack_h<F16>(uu[i]);
+                gs += f.x + f.y;
+                gq += f.x * f.x + f.y * f.y;
+              }
+            }
+          }
+#pragma unroll
+          for (int o = TPG / 2; o > 0; o >>= 1) {
+            gs += __shfl_xor_sync(0xffffffffu, gs, o);
+            gq += __shfl_xor_sync(0xffffffffu, gq, o);
+          }
+          if (sub == 0 && gi < GRAN && n0 + gi * 8 < p.N) {
+            float* dst = p.gst + ((size_t)b * p.gst_slots + p.gst_slot0 + r) * p.gst_ld + (size_t)(n0 / 8 + gi) * 2;
+            dst[0] = gs;
+            dst[1] = gq;
+          }
+          // (this pass reads the staging buffer that the tile after next refills: the next tile's barrier lies in between)
+        }
+      }
+    } else
+    for (int tile = tile_first; tile < tile_end; tile += tile_step, ++lt) {
       const int ab = lt & 1;
-      const int m_tile = p.n_fast ? tile / num_n_tiles : tile % num_m_tiles;
-        const int n0 = (p.n_fast ? tile % num_n_tiles : tile / num_m_tiles) * BN;
+      const int m_tile = RESK > 0 ? tile : (p.n_fast ? tile / num_n_tiles : tile % num_m_tiles);
+      const int n0 = RESK > 0 ? res_n0 : (p.n_fast ? tile % num_n_tiles : tile / num_m_tiles) * BN;
       const int bt = m_tile / p.tiles_per_img;
       const int b0 = bt * p.bbox;
       const int b = b0 + rb;
@@ -554,21 +767,28 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, L::TMEM_COLS); }
 }
 
-template <int BN, int STAGES, bool F16>
+template <int BN, int STAGES, bool F16, int RESK = 0>
 void launch_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmA2,
                     const GemmKernelParams& p,
                     int num_m_tiles, int num_tiles, int use_tma_store, cudaStream_t stream) {
-  using L = PersistLayout<BN, STAGES>;
+  using L = PersistLayout<BN, STAGES, RESK>;
   static int num_sms = 0;
   if (num_sms == 0) {
-    LIDM_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_persist_kernel<BN, STAGES, F16>,
+    LIDM_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_persist_kernel<BN, STAGES, F16, RESK>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     int dev = 0;
     LIDM_CUDA_CHECK(cudaGetDevice(&dev));
     LIDM_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int grid = num_tiles < num_sms ? num_tiles : num_sms;
-  launch_pdl(conv_gemm_persist_kernel<BN, STAGES, F16>, dim3(grid), dim3(L::THREADS), L::TOTAL, stream, tmA, tmB, tmO, tmA2, p,
+  int grid = num_tiles < num_sms ? num_tiles : num_sms;
+  if (RESK > 0) {
+    // every CTA owns one output-channel tile: a whole number of CTAs per channel tile, no more than there are pixel tiles
+    const int num_n_tiles = num_tiles / num_m_tiles;
+    int per_n = num_sms / num_n_tiles;
+    if (per_n > num_m_tiles) per_n = num_m_tiles;
+    grid = per_n * num_n_tiles;
+  }
+  launch_pdl(conv_gemm_persist_kernel<BN, STAGES, F16, RESK>, dim3(grid), dim3(L::THREADS), L::TOTAL, stream, tmA, tmB, tmO, tmA2, p,
              num_m_tiles, num_tiles, use_tma_store);
   LIDM_COUNT_LAUNCH(1);
 }
@@ -617,7 +837,18 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
   if (taps.zero_w) LIDM_REQUIRE(a.hl == 0 && a.hr == 0, "zero-padded convolutions read halo-free tensors (TMA fills the border)");
   int BN;
   static const int force_bn = getenv("LIDM_GEMM_BN") ? atoi(getenv("LIDM_GEMM_BN")) : 0;
-  if (n_alloc % 256 == 0 && force_bn != 128 && ep.out_t == nullptr) {
+  // resident weights (PersistLayout RESK): 1x1 GEMMs over 256 or 512 input channels whose output leaves through TMA stores
+  // (LIDM_GEMM_RESB = 0: off, 1: both, 256 / 512: that K only - A/B switch).  Measured at B = 64: 256 -> 768 @16x128 71.7 ->
+  // 67.1 us resident; 512 -> 1536 @8x64 55.7 -> 67.5 us (twice the tiles at BN = 128, single staging buffer): K = 256 only.
+  static const int resb_on = getenv("LIDM_GEMM_RESB") ? atoi(getenv("LIDM_GEMM_RESB")) : 256;
+  int resk = 0;
+  if (resb_on && taps.n == 1 && nseg == 1 && ep.a2.p == nullptr && !wt_batched && bbox == 1 && (a.C == 256 || a.C == 512) &&
+      n_alloc % 128 == 0 && n_alloc / 128 <= 148 && ep.out.p != nullptr && ep.out.hl == 0 && ep.out.hr == 0 && ep.out_t == nullptr &&
+      ep.res_f32 == nullptr && ep.out_f32_nhwc == nullptr && ep.out_f32_nchw == nullptr && ep.rowadd == nullptr &&
+      (resb_on == 1 || a.C == resb_on))
+    resk = a.C;
+  if (resk) BN = 128;
+  else if (n_alloc % 256 == 0 && force_bn != 128 && ep.out_t == nullptr) {
     // 128x256 tiles halve the B-operand traffic per MAC; take them unless wave quantisation on 148 SMs eats the gain
     const long m_tiles = bbox > 1 ? (a.B + bbox - 1) / bbox : (long)a.B * (H / Hbox) * (W / Wbox);
     auto eff = [&](long tiles) { const long rounds = (tiles + 147) / 148; return (double)tiles / (double)(rounds * 148); };
@@ -660,6 +891,7 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
     p.out = ep.out.p; p.out_ld = ep.out.ld; p.out_hl = ep.out.hl; p.out_hr = ep.out.hr; p.out_Wp = ep.out.pitch();
   }
   p.split_n = ep.split_n; p.out_t = ep.out_t;
+  { static const int dbg = getenv("LIDM_GEMM_DBG") ? atoi(getenv("LIDM_GEMM_DBG")) : 0; p.dbg = dbg; }
   if (ep.out_t != nullptr) LIDM_REQUIRE(ep.split_n % BN == 0, "split_n must be tile aligned");
   p.out_f32_nchw = ep.out_f32_nchw; p.out_f32_nhwc = ep.out_f32_nhwc;
   p.out_f32_ld = ep.out_f32_ld ? ep.out_f32_ld : N;
@@ -679,6 +911,10 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
     tmA2 = make_tma_act(a2, BK, Wbox, Hbox, 128, bbox);
     p.k2chunks = a2.C / BK; p.hl2 = a2.hl; p.b2_koff = (int)Ktot;
     Ktot += a2.C;
+    if (ep.a2_diag) {
+      LIDM_REQUIRE(a2.C == N && N % BN == 0 && BN >= BK, "identity-folded residual: a2 must have the output's channels, whole tiles");
+      p.a2_diag = 1;
+    }
   }
   const uint64_t wld = wtb.ld != 0 ? (uint64_t)wtb.ld : Ktot;
   LIDM_REQUIRE(wld >= Ktot && wld % 8 == 0 && (reinterpret_cast<uintptr_t>(wt) & 15) == 0, "weight operand alignment");
@@ -712,7 +948,9 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
   }
 #define LIDM_LAUNCH_GEMM(F16)                                                                                         \
   do {                                                                                                                  \
-    if (BN == 256) launch_persist<256, 3, F16>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream);   \
+    if (resk == 256) launch_persist<128, 6, F16, 256>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream); \
+    else if (resk == 512) launch_persist<128, 4, F16, 512>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream); \
+    else if (BN == 256) launch_persist<256, 3, F16>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream);   \
     else if (BN == 128) launch_persist<128, 4, F16>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream); \
     else if (BN == 64) launch_persist<64, 6, F16>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream); \
     else launch_persist<16, 6, F16>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream);             \
