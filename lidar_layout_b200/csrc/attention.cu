@@ -168,7 +168,7 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
   uint64_t* xu_go = stagger + NG;          // [2 groups][4 schedulers]: exp-phase ping-pong between the two warps of a scheduler
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xu_go + 8);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform as far as the compiler can tell
   const int lane = threadIdx.x & 31;
   const int nkv = (kv_len + BKV_ - 1) / BKV_;   // rows past kv_len are zero-filled by TMA and masked to -inf below
   // persistent CTA: work item = (query block, head, sample); this CTA takes items blockIdx.x, blockIdx.x + gridDim.x, ...
@@ -217,15 +217,20 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     if (HS) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     else if (NG == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0) {
-      if (lane == 0) {
+      // the whole warp walks the loop (warp-uniform operands stay in uniform registers); one elected lane issues
+      {
+        const bool leader = elect_one() != 0;
         auto load_q = [&](int it) {
           int q0, head, b;
           item_coords(it, q0, head, b);
           uint64_t* bar = &q_full[it & 1];
-          mbar_arrive_expect_tx(bar, NG * Q_BYTES);
+          if (leader) {
+            mbar_arrive_expect_tx(bar, NG * Q_BYTES);
 #pragma unroll
-          for (int i = 0; i < NG; i += 2)                                     // 256 query rows per box
-            tma_load_3d(smem + L::OFF_Q + ((it & 1) * NG + i) * Q_BYTES, &tmQ, bar, q_col + head * D, q0 + i * BQ, b);
+            for (int i = 0; i < NG; i += 2)                                     // 256 query rows per box
+              tma_load_3d(smem + L::OFF_Q + ((it & 1) * NG + i) * Q_BYTES, &tmQ, bar, q_col + head * D, q0 + i * BQ, b);
+          }
+          __syncwarp();
         };
         if (n_my > 0) load_q(0);
         int s = 0; uint32_t ph = 0;
@@ -238,9 +243,12 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           item_coords(it, q0, head, b);
           for (int j = 0; j < nkv; ++j) {
             mbar_wait(&kv_empty[s], ph ^ 1);
-            mbar_arrive_expect_tx(&kv_full[s], 2 * L::KB);
-            tma_load_3d(smem + L::OFF_K + s * L::KB, &tmKV, &kv_full[s], k_col + head * D, j * BKV_, b);
-            tma_load_3d(smem + L::OFF_V + s * L::KB, &tmKV, &kv_full[s], v_col + head * D, j * BKV_, b);
+            if (leader) {
+              mbar_arrive_expect_tx(&kv_full[s], 2 * L::KB);
+              tma_load_3d(smem + L::OFF_K + s * L::KB, &tmKV, &kv_full[s], k_col + head * D, j * BKV_, b);
+              tma_load_3d(smem + L::OFF_V + s * L::KB, &tmKV, &kv_full[s], v_col + head * D, j * BKV_, b);
+            }
+            __syncwarp();
             if (++s == KV_ST) { s = 0; ph ^= 1; }
           }
         }
@@ -249,7 +257,8 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       // one MMA-issuing thread per group (tcgen05.mma issue blocks until the tensor pipe accepts the instruction, so a
       // single thread serving both groups delays one group's S / P*V behind the other's): each polls only its own
       // barriers; a K/V stage goes back to the TMA warp when every group has committed its P*V on it
-      if (lane == 0) {
+      {
+        const bool leader = elect_one() != 0;
         const int g = warp - 1;
         constexpr uint32_t idesc_s = make_idesc_h<F16>(BQ, BKV_);
         constexpr uint32_t idesc_o = make_idesc_h<F16>(BQ, MMA_ROWSUM ? 48 : D) | (1u << 16);   // V is an MN-major B operand
@@ -269,10 +278,13 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
           tcgen05_fence_after();
           const uint64_t qdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_Q + ((it_s & 1) * NG + g) * Q_BYTES));
           const uint64_t kdesc = make_kmajor_desc<64>(smem_u32(smem + L::OFF_K + st * L::KB));
-          umma_bf16_ss(dS, qdesc, kdesc, idesc_s, 0);
-          umma_bf16_ss(dS, qdesc + 2, kdesc + 2, idesc_s, 1);
-          umma_commit(&s_ready[g]);
-          if (j_s == nkv - 1) umma_commit(&q_empty[it_s & 1]);   // this group no longer reads the item's queries
+          if (leader) {
+            umma_bf16_ss(dS, qdesc, kdesc, idesc_s, 0);
+            umma_bf16_ss(dS, qdesc + 2, kdesc + 2, idesc_s, 1);
+            umma_commit(&s_ready[g]);
+            if (j_s == nkv - 1) umma_commit(&q_empty[it_s & 1]);   // this group no longer reads the item's queries
+          }
+          __syncwarp();
           if (++j_s == nkv) { j_s = 0; ++it_s; }
         };
         if (total > 0) issue_s(0);
@@ -289,13 +301,16 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             const uint64_t lbo = (uint64_t)(L::OFF_ONES - (L::OFF_V + st * L::KB)) >> 4;
             vdesc = (vdesc & ~(0x3FFFull << 16)) | (lbo << 16);
           }
+          if (leader) {
 #pragma unroll
-          for (int kk = 0; kk < BKV_ / 16; ++kk) {
-            const uint64_t vb = vdesc + (uint64_t)((kk * 1024) >> 4);
-            umma_bf16_ts(dO, tP + kk * 8, vb, idesc_o, (j_p > 0 || kk != 0) ? 1u : 0u);   // 16 bf16 = 8 columns
+            for (int kk = 0; kk < BKV_ / 16; ++kk) {
+              const uint64_t vb = vdesc + (uint64_t)((kk * 1024) >> 4);
+              umma_bf16_ts(dO, tP + kk * 8, vb, idesc_o, (j_p > 0 || kk != 0) ? 1u : 0u);   // 16 bf16 = 8 columns
+            }
+            umma_commit(&pv_done[g]);
+            umma_commit(&kv_empty[st]);      // this group is done with the K/V tile
           }
-          umma_commit(&pv_done[g]);
-          umma_commit(&kv_empty[st]);      // this group is done with the K/V tile
+          __syncwarp();
           if (++j_p == nkv) j_p = 0;
         }
       }
