@@ -11,7 +11,9 @@
 // Warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue.
 // Epilogue fusions: bias, per-sample timestep-embedding add, residual add, halo write, transposed V^T store for
 // attention, fp32 NCHW/NHWC stores, and the DDIM update (ddim.py:191-206) for the U-Net's final conv.
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "common.h"
 #include "ddim_math.cuh"
@@ -27,6 +29,20 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
+
+// developer timeline (compile with -DLIDM_GEMM_TRACE_ON=1, run with LIDM_GEMM_TRACE=path): CTA 0 of the resident-weight
+// kernel writes clock64 stamps [row][tile][8] - how the per-tile latency chains documented below were measured
+#ifndef LIDM_GEMM_TRACE_ON
+#define LIDM_GEMM_TRACE_ON 0
+#endif
+#if LIDM_GEMM_TRACE_ON
+#define LIDM_TRACE(rowi, t, k)                                                                                        \
+  do {                                                                                                                  \
+    if (RESK > 0 && p.trace != nullptr && blockIdx.x == 0 && (t) < 64) p.trace[((size_t)(rowi) * 64 + (t)) * 8 + (k)] = clock64(); \
+  } while (0)
+#else
+#define LIDM_TRACE(rowi, t, k) do { } while (0)
+#endif
 
 struct GemmKernelParams {
   int tiles_w, tiles_per_img, Wbox, Hbox;
@@ -58,7 +74,7 @@ struct GemmKernelParams {
   float* gst;                // GroupNorm granule statistics of the output (View::gst), or null
   int gst_ld, gst_slots, gst_slot0;
   int split_n;
-  int dbg;                   // developer experiments (LIDM_GEMM_DBG)
+  long long* trace;          // developer timeline (LIDM_GEMM_TRACE): [cta][tile][8] clock64 stamps, resident-weight kernel only
   bf16* out_t;
   float* out_f32_nchw;
   float* out_f32_nhwc;
@@ -101,7 +117,7 @@ struct PersistLayout {
   static constexpr int A_OFF = 0;
   static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
   static constexpr int OUT_BOXES = BN >= 64 ? BN / 64 : 0;          // 64-channel TMA store boxes per tile
-  static constexpr int OUT_BUF_BYTES = OUT_BOXES * BM * 128;        // bf16 staging for one tile
+  static constexpr int OUT_BUF_BYTES = (RESK > 0 ? 1 : OUT_BOXES) * BM * 128;   // 2-byte staging: one tile (resident: one 64-column box per group)
   static constexpr int OUT_BUFS = (BN > 128 || RESK > 256) ? 1 : 2; // staging buffers (double-buffered when they fit)
   static constexpr int OUT_OFF = B_OFF + B_BUFS * B_STRIDE;
   static constexpr int BIAS_OFF = OUT_OFF + OUT_BUFS * OUT_BUF_BYTES;
@@ -153,7 +169,7 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (use_tma_store) prefetch_tensormap(&tmO);
     if (p.k2chunks) prefetch_tensormap(&tmA2);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], L::EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], RESK > 0 ? 4 : L::EPI_WARPS); }
     mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
@@ -183,6 +199,32 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         __syncwarp();
       }
+      if constexpr (RESK > 0) {
+        // resident weights: the ring is two whole-tile buffers of RESK / 64 chunks with ONE barrier pair per tile - the
+        // issuing threads' per-chunk scalar work (~300 clocks of dependent uniform-datapath instructions per chunk, measured)
+        // would otherwise outlast the 256 clocks the tensor pipe needs for a 128-wide chunk
+        constexpr int KCH = RESK / BK;
+        static_assert(STAGES == 2 * KCH, "resident weights: two tile buffers");
+        int lt = 0;
+        for (int tile = tile_first; tile < tile_end; tile += tile_step, ++lt) {
+          const int tb = lt & 1;
+          const int bt = tile / p.tiles_per_img;
+          const int r = tile - bt * p.tiles_per_img;
+          const int th = r / p.tiles_w;
+          const int h0 = th * p.Hbox, w0 = (r - th * p.tiles_w) * p.Wbox;
+          mbar_wait(&empty_bar[tb], ((lt >> 1) & 1) ^ 1);
+          if (leader) {
+            LIDM_TRACE(0, lt, 0);
+            mbar_arrive_expect_tx(&full_bar[tb], KCH * A_STAGE_BYTES);
+#pragma unroll
+            for (int kc = 0; kc < KCH; ++kc)
+              tma_load_4d(smem + L::A_OFF + (tb * KCH + kc) * A_STAGE_BYTES, &tmA, &full_bar[tb], p.a_coff[0] + kc * BK, w0 + p.hl,
+                          h0, bt);
+            LIDM_TRACE(0, lt, 1);
+          }
+          __syncwarp();
+        }
+      } else
       for (int tile = tile_first; tile < tile_end; tile += tile_step) {
         const int m_tile = RESK > 0 ? tile : (p.n_fast ? tile / num_n_tiles : tile % num_m_tiles);
         const int n0 = RESK > 0 ? res_n0 : (p.n_fast ? tile % num_n_tiles : tile / num_m_tiles) * BN;
@@ -233,6 +275,34 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       int s = 0; uint32_t ph = 0;
       int lt = 0;
       if (RESK > 0 && tile_first < tile_end) mbar_wait(bres_bar, 0);
+      if constexpr (RESK > 0) {
+        constexpr int KCH = RESK / BK;
+        for (int tile = tile_first; tile < tile_end; tile += tile_step, ++lt) {
+          const int ab = lt & 1;                             // accumulator and tile buffer
+          if (leader) LIDM_TRACE(0, lt, 2);
+          mbar_wait(&tempty_bar[ab], ((lt >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+          if (leader) LIDM_TRACE(0, lt, 3);
+          mbar_wait(&full_bar[ab], (lt >> 1) & 1);           // the whole A tile has landed
+          tcgen05_fence_after();
+          if (leader) LIDM_TRACE(0, lt, 4);
+          const uint32_t d = tmem_base + ab * L::ACC_COLS;
+          const uint64_t adesc0 = make_kmajor_desc<128>(smem_u32(smem + L::A_OFF + ab * KCH * A_STAGE_BYTES));
+          const uint64_t bdesc0 = make_kmajor_desc<128>(smem_u32(smem + L::B_OFF));
+          if (leader) {
+#pragma unroll
+            for (int kc = 0; kc < KCH; ++kc) {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k)
+                umma_bf16_ss(d, adesc0 + (uint64_t)((kc * A_STAGE_BYTES) >> 4) + 2 * k, bdesc0 + (uint64_t)((kc * L::B_STRIDE) >> 4) + 2 * k,
+                             idesc, (kc | k) != 0);
+            }
+            umma_commit(&empty_bar[ab]);
+            umma_commit(&tfull_bar[ab]);
+            LIDM_TRACE(0, lt, 6);
+          }
+          __syncwarp();
+        }
+      } else
       for (int tile = tile_first; tile < tile_end; tile += tile_step, ++lt) {
         const int ab = lt & 1;
         mbar_wait(&tempty_bar[ab], ((lt >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
@@ -242,7 +312,7 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           mbar_wait(&full_bar[s], ph);
           tcgen05_fence_after();
           const uint64_t adesc = make_kmajor_desc<128>(smem_u32(smem + L::A_OFF + s * A_STAGE_BYTES));
-          const uint64_t bdesc = make_kmajor_desc<128>(smem_u32(smem + L::B_OFF + (RESK > 0 ? it : s) * L::B_STRIDE));
+          const uint64_t bdesc = make_kmajor_desc<128>(smem_u32(smem + L::B_OFF + s * L::B_STRIDE));
           if (leader) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) umma_bf16_ss(d, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
@@ -276,146 +346,111 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     constexpr int SB = BN < 32 ? 32 : BN;
     int lt = 0;
     if constexpr (RESK > 0) {
-      // ---- resident-weight tiles (BN = 128, bf16 output through TMA stores): the CTA's channel tile never changes, so the
-      // bias is staged once, and the per-tile chain is  residual of the NEXT tile requested -> accumulator -> registers ->
-      // staging -> ONE named barrier -> TMA store.  The staging buffer of tile t was last read by the store of tile t - 2,
-      // which thread 0 waits for before it arrives at the barrier of tile t - 1 (one whole tile after issuing it).
-      static_assert(BN == 128 && L::COLS == 64, "resident-weight epilogue: 128-column tiles, 64 columns per thread");
-      constexpr int NCH = 2;
+      // ---- resident-weight tiles (BN = 128, 2-byte output through TMA stores, no residual).  The per-tile epilogue is a
+      // serial chain of synchronisations (accumulator barrier, TMEM load, proxy fence, staging-buffer reuse, named barrier,
+      // store issue: ~1500 clocks of latency measured with clock64 stamps against ~800 of data work for 64 columns per
+      // thread), so TWO groups of four warps take alternate tiles and run two such chains at once: group g owns
+      // accumulator g and ONE 64-column staging box (16 KB - the shared memory goes to the A ring, whose depth bounds the
+      // tile rate: STAGES chunks per ~2000-clock load latency), drains its tile in two 64-column passes, each staged and
+      // stored on its own; the group's first thread issues the stores.  The channel tile never changes, so the bias is
+      // staged once; pixel coordinates advance incrementally; staging and bias traffic uses shared-space accesses.
+      static_assert(BN == 128 && L::EPI_WARPS == 8 && L::OUT_BUFS == 2, "resident-weight epilogue: 128-column tiles, two groups of four warps");
+      const int grp = wg;                    // tile parity this warp serves
+      const int eg = e & 127;                // thread index inside the group
       for (int i = e; i < BN; i += L::EPI_THREADS) sbias[i] = (res_n0 + i < p.N && p.bias != nullptr) ? __ldg(p.bias + res_n0 + i) : 0.f;
       named_bar_sync(1, L::EPI_THREADS);
       const int n0 = res_n0;
-      const bool has_res = p.res != nullptr && !(p.dbg & 2);
-      auto tile_pixel = [&](int m_tile, int& b0, int& r, int& h0, int& w0) {
-        b0 = m_tile / p.tiles_per_img;
-        r = m_tile - b0 * p.tiles_per_img;
-        const int th = r / p.tiles_w;
-        h0 = th * p.Hbox; w0 = (r - th * p.tiles_w) * p.Wbox;
-      };
-      uint4 rnext[NCH][4];
-      auto load_res = [&](int m_tile) {
-        int b0, r, h0, w0;
-        tile_pixel(m_tile, b0, r, h0, w0);
-        const bf16* rp = p.res + ((size_t)(b0 * p.H + h0 + hh) * p.res_Wp + (w0 + ww + p.res_hl)) * p.res_ld + n0 + col_lo;
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          if (n0 + col_lo + c * 32 < p.N) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) rnext[c][i] = __ldg(reinterpret_cast<const uint4*>(rp + c * 32) + i);
-          }
-        }
-      };
-      if (has_res && tile_first < tile_end) load_res(tile_first);
-      for (int tile = tile_first; tile < tile_end; tile += tile_step, ++lt) {
-        const int ab = lt & 1;
-        int b0, r, h0, w0;
-        tile_pixel(tile, b0, r, h0, w0);
+      const uint32_t sbias_s = smem_u32(sbias);
+      uint8_t* stage_out = smem + L::OUT_OFF + grp * L::OUT_BUF_BYTES;
+      const uint32_t stage_s = smem_u32(stage_out);
+      const uint32_t taddr_row = tmem_base + grp * L::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t row_s = stage_s + row * 128;
+      // this group's tiles: tile_first + grp * tile_step, then every 2 * tile_step; (sample, tile-in-sample) kept incrementally
+      const int gstep = 2 * tile_step;
+      const int step_b = gstep / p.tiles_per_img, step_r = gstep - step_b * p.tiles_per_img;
+      int tile = tile_first + grp * tile_step;
+      int b0 = tile / p.tiles_per_img, r = tile - b0 * p.tiles_per_img;
+      const bool geglu = p.geglu != 0;       // GEGLU: a pass yields 32 output channels, the box leaves after the second pass
+      bool buf_busy = false;                 // a store from this group's box may still be reading it
+      for (int gl = 0; tile < tile_end; tile += gstep, ++gl) {
+        const int th = p.tiles_w == 1 ? r : r / p.tiles_w;
+        const int h0 = th * p.Hbox, w0 = (r - th * p.tiles_w) * p.Wbox;
         const int b = b0;
-        uint4 rres[NCH][4];
-        if (has_res) {
-#pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) rres[c][i] = rnext[c][i];
-          }
-          if (tile + tile_step < tile_end) load_res(tile + tile_step);
-        }
-        if constexpr (L::OUT_BUFS == 1) {
-          if (e == 0) tma_store_wait_read<0>();
-          named_bar_sync(1, L::EPI_THREADS);
-        }
-        const uint32_t taddr_row = tmem_base + ab * L::ACC_COLS + (static_cast<uint32_t>(q * 32) << 16);
-        uint8_t* stage_out = smem + L::OUT_OFF + (L::OUT_BUFS == 2 ? ab : 0) * L::OUT_BUF_BYTES;
-        mbar_wait(&tfull_bar[ab], (lt >> 1) & 1);
+        if (eg == 0) LIDM_TRACE(1 + grp, gl, 0);
+        mbar_wait(&tfull_bar[grp], gl & 1);
         tcgen05_fence_after();
-        uint32_t raw[NCH][32];
+        if (eg == 0) LIDM_TRACE(1 + grp, gl, 1);
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) tmem_ld_32x32b_x32(taddr_row + col_lo + c * 32, raw[c]);
-        tmem_ld_wait();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[ab]);
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t raw[2][32];
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          const int cc = col_lo + c * 32;
-          if (n0 + cc < p.N) {
-            float v[32];
-            const float4* sb4 = reinterpret_cast<const float4*>(sbias + cc);
+          for (int c = 0; c < 2; ++c) tmem_ld_32x32b_x32(taddr_row + hf * 64 + c * 32, raw[c]);
+          tmem_ld_wait();
+          if (hf == 1) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[grp]);
+            if (eg == 0) LIDM_TRACE(1 + grp, gl, 3);
+          }
+          if (buf_busy && (!geglu || hf == 0)) {
+            if (eg == 0) tma_store_wait_read<0>();     // the previous store of this group has left the box
+            named_bar_sync(4 + grp, 128);
+          }
+          if (n0 + hf * 64 < p.N) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 t = sb4[j];
-              v[4 * j] = __uint_as_float(raw[c][4 * j]) + t.x;
-              v[4 * j + 1] = __uint_as_float(raw[c][4 * j + 1]) + t.y;
-              v[4 * j + 2] = __uint_as_float(raw[c][4 * j + 2]) + t.z;
-              v[4 * j + 3] = __uint_as_float(raw[c][4 * j + 3]) + t.w;
-            }
-            if (has_res) {
+            for (int c = 0; c < 2; ++c) {
+              const int cc = hf * 64 + c * 32;
+              float v[32];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float2 f;
-                const float rs = p.res_scale;
-                f = unpack_h<F16>(rres[c][i].x); v[i * 8 + 0] = fmaf(f.x, rs, v[i * 8 + 0]); v[i * 8 + 1] = fmaf(f.y, rs, v[i * 8 + 1]);
-                f = unpack_h<F16>(rres[c][i].y); v[i * 8 + 2] = fmaf(f.x, rs, v[i * 8 + 2]); v[i * 8 + 3] = fmaf(f.y, rs, v[i * 8 + 3]);
-                f = unpack_h<F16>(rres[c][i].z); v[i * 8 + 4] = fmaf(f.x, rs, v[i * 8 + 4]); v[i * 8 + 5] = fmaf(f.y, rs, v[i * 8 + 5]);
-                f = unpack_h<F16>(rres[c][i].w); v[i * 8 + 6] = fmaf(f.x, rs, v[i * 8 + 6]); v[i * 8 + 7] = fmaf(f.y, rs, v[i * 8 + 7]);
+              for (int j = 0; j < 8; ++j) {
+                const float4 t = ld_shared_f4(sbias_s + (cc + 4 * j) * 4);
+                v[4 * j] = __uint_as_float(raw[c][4 * j]) + t.x;
+                v[4 * j + 1] = __uint_as_float(raw[c][4 * j + 1]) + t.y;
+                v[4 * j + 2] = __uint_as_float(raw[c][4 * j + 2]) + t.z;
+                v[4 * j + 3] = __uint_as_float(raw[c][4 * j + 3]) + t.w;
+              }
+              if (geglu) {
+                const int gbase = (cc >> 1) >> 3;      // output channel cc / 2 of the tile's 64: 16-byte chunk index
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                  float o[8];
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) o[k] = v[i * 8 + k] * gelu_erf_fast(v[16 + i * 8 + k]);
+                  st_shared_v4(row_s + (((gbase + i) ^ (row & 7)) << 4), pack_h<F16>(o[0], o[1]), pack_h<F16>(o[2], o[3]),
+                               pack_h<F16>(o[4], o[5]), pack_h<F16>(o[6], o[7]));
+                }
+              } else {
+                const int cbase = c * 4;               // 32 channels = four 16-byte chunks of the 64-channel box row
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  st_shared_v4(row_s + (((cbase + i) ^ (row & 7)) << 4), pack_h<F16>(v[i * 8 + 0], v[i * 8 + 1]),
+                               pack_h<F16>(v[i * 8 + 2], v[i * 8 + 3]), pack_h<F16>(v[i * 8 + 4], v[i * 8 + 5]),
+                               pack_h<F16>(v[i * 8 + 6], v[i * 8 + 7]));
               }
             }
-            if (p.geglu) {
-              const int oc = cc >> 1;
-              uint8_t* gb = stage_out + (oc >> 6) * (BM * 128) + row * 128;
-              const int gbase = (oc & 63) >> 3;
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                float o[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) o[k] = v[i * 8 + k] * gelu_erf_fast(v[16 + i * 8 + k]);
-                uint4 pk;
-                pk.x = pack_h<F16>(o[0], o[1]); pk.y = pack_h<F16>(o[2], o[3]);
-                pk.z = pack_h<F16>(o[4], o[5]); pk.w = pack_h<F16>(o[6], o[7]);
-                *reinterpret_cast<uint4*>(gb + (((gbase + i) ^ (row & 7)) << 4)) = pk;
-              }
-              continue;
-            }
-            uint8_t* box = stage_out + (cc >> 6) * (BM * 128) + row * 128;
-            const int cbase = (cc & 63) >> 3;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 pk;
-              pk.x = pack_h<F16>(v[i * 8 + 0], v[i * 8 + 1]);
-              pk.y = pack_h<F16>(v[i * 8 + 2], v[i * 8 + 3]);
-              pk.z = pack_h<F16>(v[i * 8 + 4], v[i * 8 + 5]);
-              pk.w = pack_h<F16>(v[i * 8 + 6], v[i * 8 + 7]);
-              *reinterpret_cast<uint4*>(box + (((cbase + i) ^ (row & 7)) << 4)) = pk;
-            }
           }
-        }
-        fence_proxy_async();          // staging writes -> visible to the TMA engine
-        if constexpr (L::OUT_BUFS == 2) {
-          if (e == 0) tma_store_wait_read<0>();   // the other buffer's store (a tile ago) has been read: the next tile may refill it
-        }
-        named_bar_sync(2, L::EPI_THREADS);
-        if (e == 0 && !(p.dbg & 1)) {
-          if (p.geglu) {
-            if ((n0 >> 1) < (p.N >> 1)) tma_store_4d(&tmO, stage_out, n0 >> 1, w0, h0, b0);
-          } else {
-#pragma unroll
-            for (int j = 0; j < L::OUT_BOXES; ++j)
-              if (n0 + j * 64 < p.N) tma_store_4d(&tmO, stage_out + j * (BM * 128), n0 + j * 64, w0, h0, b0);
+          if (geglu && hf == 0) continue;
+          fence_proxy_async();          // staging writes -> visible to the TMA engine
+          named_bar_sync(2 + grp, 128);
+          if (eg == 0) {
+            if (geglu) {
+              if ((n0 >> 1) < (p.N >> 1)) tma_store_4d(&tmO, stage_out, n0 >> 1, w0, h0, b0);
+            } else if (n0 + hf * 64 < p.N) {
+              tma_store_4d(&tmO, stage_out, n0 + hf * 64, w0, h0, b0);
+            }
+            tma_store_commit();
           }
-          tma_store_commit();
-        }
-        if (p.gst != nullptr && !(p.dbg & 4)) {
-          // GroupNorm statistics of the tile from the staged values: identical granule / lane / row order to the streamed
-          // path below (8 lanes per 8-channel granule, rows sub, sub + 8, ...), so the sums are the same bits
-          constexpr int GRAN = BN / 8;
-          constexpr int TPG = 8;
-          const int gi = e / TPG, sub = e % TPG;
-          float gs = 0.f, gq = 0.f;
-          if (gi < GRAN) {
-            const uint8_t* gbox = stage_out + (gi >> 3) * (BM * 128);
+          buf_busy = true;
+          if (p.gst != nullptr && eg < 64) {
+            // GroupNorm statistics of the staged box: identical granule / lane / row order to the streamed path below
+            // (8 lanes per 8-channel granule, rows sub, sub + 8, ...), so the sums are the same bits.  (The box is refilled
+            // only after this group's next barrier 4 + grp.)
+            constexpr int TPG = 8;
+            const int gi = eg / TPG, sub = eg % TPG;     // 8 granules x 8 lanes
+            float gs = 0.f, gq = 0.f;
 #pragma unroll 4
             for (int rr = sub; rr < BM; rr += TPG) {
-              const uint4 u = *reinterpret_cast<const uint4*>(gbox + rr * 128 + (((gi & 7) ^ (rr & 7)) << 4));
+              const uint4 u = ld_shared_v4(stage_s + rr * 128 + ((gi ^ (rr & 7)) << 4));
               const uint32_t uu[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -424,19 +459,21 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 gq += f.x * f.x + f.y * f.y;
               }
             }
-          }
 #pragma unroll
-          for (int o = TPG / 2; o > 0; o >>= 1) {
-            gs += __shfl_xor_sync(0xffffffffu, gs, o);
-            gq += __shfl_xor_sync(0xffffffffu, gq, o);
+            for (int o = TPG / 2; o > 0; o >>= 1) {
+              gs += __shfl_xor_sync(0xffffffffu, gs, o);
+              gq += __shfl_xor_sync(0xffffffffu, gq, o);
+            }
+            if (sub == 0 && n0 + hf * 64 + gi * 8 < p.N) {
+              float* dst = p.gst + ((size_t)b * p.gst_slots + p.gst_slot0 + r) * p.gst_ld + (size_t)((n0 + hf * 64) / 8 + gi) * 2;
+              dst[0] = gs;
+              dst[1] = gq;
+            }
           }
-          if (sub == 0 && gi < GRAN && n0 + gi * 8 < p.N) {
-            float* dst = p.gst + ((size_t)b * p.gst_slots + p.gst_slot0 + r) * p.gst_ld + (size_t)(n0 / 8 + gi) * 2;
-            dst[0] = gs;
-            dst[1] = gq;
-          }
-          // (this pass reads the staging buffer that the tile after next refills: the next tile's barrier lies in between)
         }
+        if (eg == 0) LIDM_TRACE(1 + grp, gl, 6);
+        b0 += step_b; r += step_r;
+        if (r >= p.tiles_per_img) { r -= p.tiles_per_img; ++b0; }
       }
     } else
     for (int tile = tile_first; tile < tile_end; tile += tile_step, ++lt) {
@@ -842,10 +879,10 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
   // 67.1 us resident; 512 -> 1536 @8x64 55.7 -> 67.5 us (twice the tiles at BN = 128, single staging buffer): K = 256 only.
   static const int resb_on = getenv("LIDM_GEMM_RESB") ? atoi(getenv("LIDM_GEMM_RESB")) : 256;
   int resk = 0;
-  if (resb_on && taps.n == 1 && nseg == 1 && ep.a2.p == nullptr && !wt_batched && bbox == 1 && (a.C == 256 || a.C == 512) &&
+  if (resb_on && taps.n == 1 && nseg == 1 && ep.a2.p == nullptr && !wt_batched && bbox == 1 && a.C == 256 && ep.residual.p == nullptr &&
       n_alloc % 128 == 0 && n_alloc / 128 <= 148 && ep.out.p != nullptr && ep.out.hl == 0 && ep.out.hr == 0 && ep.out_t == nullptr &&
       ep.res_f32 == nullptr && ep.out_f32_nhwc == nullptr && ep.out_f32_nchw == nullptr && ep.rowadd == nullptr &&
-      (resb_on == 1 || a.C == resb_on))
+      (resb_on == 1 || a.C == resb_on))   // (a 512-channel variant, B resident in 128 KB with one staging buffer, measured slower)
     resk = a.C;
   if (resk) BN = 128;
   else if (n_alloc % 256 == 0 && force_bn != 128 && ep.out_t == nullptr) {
@@ -891,7 +928,6 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
     p.out = ep.out.p; p.out_ld = ep.out.ld; p.out_hl = ep.out.hl; p.out_hr = ep.out.hr; p.out_Wp = ep.out.pitch();
   }
   p.split_n = ep.split_n; p.out_t = ep.out_t;
-  { static const int dbg = getenv("LIDM_GEMM_DBG") ? atoi(getenv("LIDM_GEMM_DBG")) : 0; p.dbg = dbg; }
   if (ep.out_t != nullptr) LIDM_REQUIRE(ep.split_n % BN == 0, "split_n must be tile aligned");
   p.out_f32_nchw = ep.out_f32_nchw; p.out_f32_nhwc = ep.out_f32_nhwc;
   p.out_f32_ld = ep.out_f32_ld ? ep.out_f32_ld : N;
@@ -946,10 +982,18 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
                  "GroupNorm statistics need whole 128-pixel tiles inside one sample");
     p.gst = ep.out.gst; p.gst_ld = ep.out.gst_ld; p.gst_slots = ep.out.gst_slots; p.gst_slot0 = ep.out.gst_slot0;
   }
+  static const char* trace_path = getenv("LIDM_GEMM_TRACE");
+  static long long* trace_dev = nullptr;
+  static int trace_left = getenv("LIDM_GEMM_TRACE_N") ? atoi(getenv("LIDM_GEMM_TRACE_N")) : 4;   // dump the first few qualifying launches
+  const bool tracing = LIDM_GEMM_TRACE_ON && trace_path != nullptr && resk != 0 && trace_left > 0;
+  if (tracing) {
+    if (trace_dev == nullptr) LIDM_CUDA_CHECK(cudaMalloc(&trace_dev, 8 * 64 * 8 * sizeof(long long)));
+    LIDM_CUDA_CHECK(cudaMemsetAsync(trace_dev, 0, 8 * 64 * 8 * sizeof(long long), stream));
+    p.trace = trace_dev;
+  }
 #define LIDM_LAUNCH_GEMM(F16)                                                                                         \
   do {                                                                                                                  \
-    if (resk == 256) launch_persist<128, 6, F16, 256>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream); \
-    else if (resk == 512) launch_persist<128, 4, F16, 512>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream); \
+    if (resk == 256) launch_persist<128, 8, F16, 256>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream); \
     else if (BN == 256) launch_persist<256, 3, F16>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream);   \
     else if (BN == 128) launch_persist<128, 4, F16>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream); \
     else if (BN == 64) launch_persist<64, 6, F16>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream); \
@@ -958,6 +1002,27 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
   if (a.f16) LIDM_LAUNCH_GEMM(true);
   else LIDM_LAUNCH_GEMM(false);
 #undef LIDM_LAUNCH_GEMM
+  if (tracing) {
+    std::vector<long long> hbuf(8 * 64 * 8);
+    LIDM_CUDA_CHECK(cudaStreamSynchronize(stream));
+    LIDM_CUDA_CHECK(cudaMemcpy(hbuf.data(), trace_dev, hbuf.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    FILE* f = fopen(trace_path, "a");
+    if (f != nullptr) {
+      fprintf(f, "# launch K=%d N=%d m_tiles=%d res=%d gst=%d  CTA 0; row 0 = producer / MMA: A_issue A_issued mma_tile_start acc_free tile_landed - committed; rows 1, 2 = epilogue groups: start tfull - acc_released - - tile_done\n",
+              a.C, N, num_m_tiles, ep.residual.p != nullptr, p.gst != nullptr);
+      for (int c = 0; c < 4; ++c)
+        for (int t = 0; t < 64; ++t) {
+          const long long* r = &hbuf[((size_t)c * 64 + t) * 8];
+          if (r[0] == 0) break;
+          const long long t0 = hbuf[0];
+          fprintf(f, "%d %d", c, t);
+          for (int k = 0; k < 8; ++k) fprintf(f, " %lld", r[k] - t0);
+          fprintf(f, "\n");
+        }
+      fclose(f);
+    }
+    --trace_left;
+  }
 }
 
 }  // namespace lidm

@@ -74,7 +74,7 @@ oaca_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
   uint64_t* o_ready = full_qk + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full_qk + 5);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // warp index: warp-uniform for the compiler
   const int q0 = blockIdx.x * QROWS, head = blockIdx.y, b = blockIdx.z;
   constexpr int QBOX = T < QROWS ? T : QROWS;          // query rows actually loaded (T = 64: half a tile)
 
@@ -90,9 +90,12 @@ oaca_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 4) {
-    if (lane == 0) {
+    // the whole warp runs this role (warp-uniform operands stay in uniform registers); one elected lane issues
+    const bool leader = elect_one() != 0;
+    {
       const int pb = pos_batched ? b : 0;
       // ---- loads: 64-row boxes of 64 channels (8 KiB each)
+      if (leader) {
       mbar_arrive_expect_tx(full_qk, 2 * QBOX * 128 + 2 * T * 128 + 2 * LAY * 128);
       for (int r = 0; r < QBOX; r += 64) {
         tma_load_3d(smem + L::OFF_QC + r * 128, &tmQKV, full_qk, head * DH, q0 + r, b);
@@ -107,6 +110,8 @@ oaca_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       mbar_arrive_expect_tx(full_v, T * 128 + LAY * 128);
       for (int r = 0; r < T; r += 64) tma_load_3d(smem + L::OFF_V + r * 128, &tmQKV, full_v, 2 * C + head * DH, r, b);
       tma_load_3d(smem + L::OFF_LV, &tmVL, full_v, head * DH, 0, b);
+      }
+      __syncwarp();
 
       // ---- S = Qc Kc^T + Qp Kp^T  (image keys: N = T, layout keys: N = 16)
       constexpr uint32_t idesc_img = make_idesc_h<F16>(QROWS, T);
@@ -116,6 +121,7 @@ oaca_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       const uint64_t qc = make_kmajor_desc<128>(smem_u32(smem + L::OFF_QC)), qp = make_kmajor_desc<128>(smem_u32(smem + L::OFF_QP));
       const uint64_t kc = make_kmajor_desc<128>(smem_u32(smem + L::OFF_KC)), kp = make_kmajor_desc<128>(smem_u32(smem + L::OFF_KP));
       const uint64_t lc = make_kmajor_desc<128>(smem_u32(smem + L::OFF_LC)), lp = make_kmajor_desc<128>(smem_u32(smem + L::OFF_LP));
+      if (leader) {
 #pragma unroll
       for (int k = 0; k < DH / 16; ++k) umma_bf16_ss(tmem_base, qc + 2 * k, kc + 2 * k, idesc_img, k != 0);
 #pragma unroll
@@ -125,6 +131,8 @@ oaca_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
 #pragma unroll
       for (int k = 0; k < DH / 16; ++k) umma_bf16_ss(tmem_base + T, qp + 2 * k, lp + 2 * k, idesc_lay, 1);
       umma_commit(s_ready);
+      }
+      __syncwarp();
 
       // ---- O = P V (P from tensor memory, V an MN-major shared-memory operand: 16 keys = two 8-row groups = 2 KiB)
       constexpr uint32_t idesc_o = make_idesc_h<F16>(QROWS, DH) | (1u << 16);
@@ -133,10 +141,13 @@ oaca_attention_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       tcgen05_fence_after();
       const uint64_t vd = make_kmajor_desc<128>(smem_u32(smem + L::OFF_V)), lv = make_kmajor_desc<128>(smem_u32(smem + L::OFF_LV));
       const uint32_t tP = tmem_base + L::P_COL, dO = tmem_base + L::O_COL;
+      if (leader) {
 #pragma unroll
       for (int kk = 0; kk < T / 16; ++kk) umma_bf16_ts(dO, tP + kk * 8, vd + (uint64_t)((kk * 2048) >> 4), idesc_o, kk != 0);
       umma_bf16_ts(dO, tP + (T / 16) * 8, lv, idesc_o, 1);
       umma_commit(o_ready);
+      }
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------------ softmax: one thread per query row
