@@ -894,6 +894,15 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
   } else if (n_alloc % 128 == 0) BN = 128;
   else if (n_alloc % 64 == 0) BN = 64;
   else { LIDM_REQUIRE(n_alloc % 16 == 0, "n_alloc must be a multiple of 16"); BN = 16; }
+  {
+    // small batches: a GEMM that fills less than half of the chip with 128-wide tiles takes 64-wide ones (twice the CTAs,
+    // each streaming half of the weight slice: the coarse 3x3 convs at B <= 8 are bound by per-SM weight streaming)
+    static const int small_bn = getenv("LIDM_GEMM_SMALL_BN") ? atoi(getenv("LIDM_GEMM_SMALL_BN")) : 1;
+    const long m_tiles = bbox > 1 ? (a.B + bbox - 1) / bbox : (long)a.B * (H / Hbox) * (W / Wbox);
+    if (small_bn && !resk && BN == 128 && force_bn == 0 && n_alloc % 64 == 0 && m_tiles * (n_alloc / 128) <= 74 && !ep.geglu &&
+        taps.n * nseg * (a.C / BK) >= 32)
+      BN = 64;
+  }
   LIDM_REQUIRE(N <= n_alloc, "N > n_alloc");
   LIDM_REQUIRE(BN == 16 || N % 32 == 0, "N must be a multiple of 32 (or <= 16)");
 

@@ -90,6 +90,8 @@ __device__ __forceinline__ bool mbar_try_wait_parked(uint64_t* bar, uint32_t par
 }
 // Bounded wait: a protocol bug turns into a trap (error code) instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // a phase that is already complete costs 15 clocks to test, 48 through the parked form (tests/microbench/mbar_latency.cu)
+  if (mbar_test_wait(bar, parity)) return;
   if (mbar_try_wait_parked(bar, parity)) return;
   long long t0 = 0;
   uint32_t spins = 0;
