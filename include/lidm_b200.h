@@ -152,6 +152,14 @@ int lidm_layout_encode(lidm_handle* h, const float* layout, int32_t B, int32_t n
 int lidm_ddim_step(const float* x, const float* eps, const float* noise, float a_t, float a_prev, float sigma_t,
                    float sqrt_one_minus_at, float temperature, float* x_prev, float* pred_x0, int64_t n, void* stream);
 
+/* The ancestral DDPM update (LatentDiffusion.p_sample after the U-Net: predict_start_from_noise + q_posterior + noise,
+ * reference lidm/models/diffusion/ddpm.py:219-232, 1090-1119), fused.  coef: device [B][5] fp32 per-sample coefficients
+ * (sqrt_recip_alphas_cumprod[t], sqrt_recipm1_alphas_cumprod[t], posterior_mean_coef1[t], posterior_mean_coef2[t],
+ * (t != 0) * exp(0.5 * posterior_log_variance_clipped[t])); noise already holds temperature (and dropout).  x_recon may be
+ * NULL.  Bit-identical to the reference's eager expression (every product and sum rounded on its own, same order). */
+int lidm_ddpm_step(const float* x, const float* eps, const float* noise, const float* coef, int32_t B, int64_t n_per_sample,
+                   int32_t clip_denoised, float* x_prev, float* x_recon, void* stream);
+
 /* DDIMSampler.ddim_sampling loop (ddim.py:115-165), unconditional, whole loop on the device with the DDIM update
  * fused into the U-Net's last conv epilogue.  x_inout: x_T in, x_0 estimate out, (B,C,H,W).
  * timesteps: HOST int64[n_steps] ascending (ddim_timesteps); sched: HOST float[n_steps*4] rows

@@ -47,7 +47,7 @@ class CConfig(ctypes.Structure):
 
 EXPORTS = [
     "lidm_last_error", "lidm_create", "lidm_destroy", "lidm_load_weight", "lidm_finalize_weights",
-    "lidm_unet_forward", "lidm_unet_forward_cond", "lidm_ddim_step", "lidm_ddim_sample", "lidm_ddim_sample_cond",
+    "lidm_unet_forward", "lidm_unet_forward_cond", "lidm_ddim_step", "lidm_ddpm_step", "lidm_ddim_sample", "lidm_ddim_sample_cond",
     "lidm_cfg_combine", "lidm_layout_set_cond", "lidm_layout_encode", "lidm_vq_decode", "lidm_vq_encode", "lidm_vq_quantize", "lidm_image_shape",
     "lidm_backproject", "lidm_to_uint8_image", "lidm_compact_points", "lidm_chamfer_nn", "lidm_chamfer_nn_ex",
     "lidm_chamfer_backward", "lidm_emd_forward", "lidm_emd_backward", "lidm_op_circular_conv2d", "lidm_op_groupnorm", "lidm_op_qkv_attention_legacy",
@@ -96,6 +96,7 @@ def load() -> ctypes.CDLL:
                                      c_int32, c_int32, c_void_p, c_void_p, c_void_p]
     lib.lidm_to_uint8_image.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
     lib.lidm_compact_points.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]
+    lib.lidm_ddpm_step.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, ctypes.c_int64, c_int32, c_void_p, c_void_p, c_void_p]
     lib.lidm_chamfer_nn.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p]
     lib.lidm_chamfer_nn_ex.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,

@@ -242,6 +242,9 @@ void launch_compact_points(const float* xyz, const uint8_t* mask, int B, int HW,
                            cudaStream_t s);
 
 // ---- elementwise (elementwise.cu) ------------------------------------------------------------------------
+// ancestral DDPM update (ddpm.py:1090-1119) with per-sample coefficients coef[B][5] on the device
+void launch_ddpm_step(const float* x, const float* eps, const float* noise, const float* coef, int B, int64_t n_per_sample, int clip,
+                      float* x_prev, float* x_recon, cudaStream_t s);
 void launch_ddim_step(const float* x, const float* eps, const float* noise, const float* coef_dev, float* x_prev,
                       float* pred_x0, int64_t n, cudaStream_t s);
 void launch_backproject(const float* img, int B, int H, int W, float fov_up_deg, float fov_down_deg, float dmin,

@@ -7,6 +7,8 @@
 //   vq               taming VectorQuantizer2 argmin + post_quant_conv (lidm/models/ae/vq.py:71-79, autoencoder.py:293-296)
 //   time_embed       timestep_embedding + time_embed MLP + emb_layers (basic.py:278-296, openaimodel.py:509-514,262)
 //   softmax_rows, weight packing, layout conversions.
+#include <algorithm>
+
 #include "common.h"
 #include "ddim_math.cuh"
 #include "ptx.cuh"
@@ -46,6 +48,29 @@ __global__ void ddim_step_kernel(const float* __restrict__ x, const float* __res
         if (pred_x0 != nullptr) pred_x0[k] = x0;
       }
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ ancestral DDPM step
+// p_sample (reference lidm/models/diffusion/ddpm.py:1090-1119) after the U-Net: per sample b with coefficients
+// coef[b] = (sqrt_recip_ac, sqrt_recipm1_ac, posterior_mean_coef1, posterior_mean_coef2, mask * exp(0.5 logvar))
+//   x0  = a x - b eps                 (predict_start_from_noise, ddpm.py:219-223; optional clamp to [-1, 1])
+//   out = (c1 x0 + c2 x) + m noise    (q_posterior mean, ddpm.py:225-232, plus the masked noise term)
+// every product and sum rounded on its own, in the reference's order: bit-identical to the eager tensor expression.
+__global__ void ddpm_step_kernel(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ noise,
+                                 const float* __restrict__ coef, int64_t n_per_sample, int clip, float* __restrict__ x_prev,
+                                 float* __restrict__ x_recon) {
+  const int b = blockIdx.y;
+  const float a = __ldg(coef + b * 5), bb = __ldg(coef + b * 5 + 1), c1 = __ldg(coef + b * 5 + 2), c2 = __ldg(coef + b * 5 + 3),
+              m = __ldg(coef + b * 5 + 4);
+  const size_t base = (size_t)b * n_per_sample;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_per_sample; i += (int64_t)gridDim.x * blockDim.x) {
+    const float xv = x[base + i];
+    float x0 = __fsub_rn(__fmul_rn(a, xv), __fmul_rn(bb, eps[base + i]));
+    if (clip) x0 = fminf(fmaxf(x0, -1.f), 1.f);
+    const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, xv));
+    x_prev[base + i] = __fadd_rn(mean, __fmul_rn(m, noise[base + i]));
+    if (x_recon != nullptr) x_recon[base + i] = x0;
   }
 }
 
@@ -492,6 +517,14 @@ void launch_ddim_step(const float* x, const float* eps, const float* noise, cons
                    ((uintptr_t)pred_x0 & 15) == 0 && ((uintptr_t)noise & 15) == 0,
                "ddim_step: pointers must be 16-byte aligned");
   ddim_step_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, s>>>(x, eps, noise, coef_dev, x_prev, pred_x0, n);
+  LIDM_CUDA_CHECK(cudaGetLastError());
+  LIDM_COUNT_LAUNCH(1);
+}
+
+void launch_ddpm_step(const float* x, const float* eps, const float* noise, const float* coef, int B, int64_t n_per_sample, int clip,
+                      float* x_prev, float* x_recon, cudaStream_t s) {
+  dim3 grid((unsigned)std::min<int64_t>((n_per_sample + 255) / 256, 1024), B);
+  ddpm_step_kernel<<<grid, 256, 0, s>>>(x, eps, noise, coef, n_per_sample, clip, x_prev, x_recon);
   LIDM_CUDA_CHECK(cudaGetLastError());
   LIDM_COUNT_LAUNCH(1);
 }

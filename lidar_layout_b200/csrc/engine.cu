@@ -3218,6 +3218,15 @@ int lidm_ddim_step(const float* x, const float* eps, const float* noise, float a
   });
 }
 
+int lidm_ddpm_step(const float* x, const float* eps, const float* noise, const float* coef, int32_t B, int64_t n_per_sample,
+                   int32_t clip_denoised, float* x_prev, float* x_recon, void* stream) {
+  return guarded(nullptr, [&] {
+    LIDM_REQUIRE(x != nullptr && eps != nullptr && noise != nullptr && coef != nullptr && x_prev != nullptr, "null tensor");
+    LIDM_REQUIRE(B > 0 && n_per_sample > 0, "ddpm_step: empty batch");
+    launch_ddpm_step(x, eps, noise, coef, B, n_per_sample, clip_denoised, x_prev, x_recon, reinterpret_cast<cudaStream_t>(stream));
+  });
+}
+
 int lidm_ddim_sample_cond(lidm_handle* h, float* x_inout, const int64_t* timesteps, const float* sched, int32_t n_steps,
                           const float* noise, float temperature, float* pred_x0_out, int32_t B, const float* c_concat,
                           const float* context, int32_t ctx_len, const float* uncond_concat, const float* uncond_context,

@@ -223,17 +223,30 @@ class LatentDiffusion:
     @torch.no_grad()
     def p_sample(self, x, c, t, clip_denoised=False, repeat_noise=False, return_x0=False, temperature=1.,
                  noise_dropout=0., quantize_denoised=False):
-        """ddpm.py:1090-1119."""
+        """ddpm.py:1090-1119.  Without quantize_denoised the whole update after the U-Net (predict_start_from_noise,
+        q_posterior, the masked noise term) is one kernel (`lidm_ddpm_step`), bit-identical to the tensor expression; the
+        per-sample coefficients are gathered from the same (T,) buffers with the same torch ops as the reference."""
         b = x.shape[0]
-        outputs = self.p_mean_variance(x=x, c=c, t=t, clip_denoised=clip_denoised, return_x0=return_x0,
-                                       quantize_denoised=quantize_denoised)
-        mean, _, logvar = outputs[:3]
+        if quantize_denoised:
+            outputs = self.p_mean_variance(x=x, c=c, t=t, clip_denoised=clip_denoised, return_x0=return_x0,
+                                           quantize_denoised=quantize_denoised)
+            mean, _, logvar = outputs[:3]
+            noise = noise_like(x.shape, x.device, repeat_noise) * temperature
+            if noise_dropout > 0.:
+                noise = torch.nn.functional.dropout(noise, p=noise_dropout)
+            nonzero_mask = (1 - (t == 0).float()).reshape(b, *((1,) * (len(x.shape) - 1)))
+            out = mean + nonzero_mask * (0.5 * logvar).exp() * noise
+            return (out, outputs[3]) if return_x0 else out
+        from . import ops
+        model_out = self.apply_model(x, t, c)
         noise = noise_like(x.shape, x.device, repeat_noise) * temperature
         if noise_dropout > 0.:
             noise = torch.nn.functional.dropout(noise, p=noise_dropout)
-        nonzero_mask = (1 - (t == 0).float()).reshape(b, *((1,) * (len(x.shape) - 1)))
-        out = mean + nonzero_mask * (0.5 * logvar).exp() * noise
-        return (out, outputs[3]) if return_x0 else out
+        nonzero_mask = 1 - (t == 0).float()
+        coef = torch.stack([self.sqrt_recip_alphas_cumprod[t], self.sqrt_recipm1_alphas_cumprod[t],
+                            self.posterior_mean_coef1[t], self.posterior_mean_coef2[t],
+                            nonzero_mask * (0.5 * self.posterior_log_variance_clipped[t]).exp()], dim=1).float()
+        return ops.ddpm_step(x, model_out, noise, coef, clip_denoised=clip_denoised, return_x0=return_x0)
 
     @torch.no_grad()
     def p_sample_loop(self, cond, shape, return_intermediates=False, x_T=None, verbose=True, callback=None,

@@ -71,6 +71,25 @@ def ddim_step(x, e_t, coef, noise=None, temperature=1.0):
     return x_prev, pred_x0
 
 
+def ddpm_step(x, eps, noise, coef, clip_denoised=False, return_x0=False):
+    """Ancestral DDPM update (reference ddpm.py:1090-1119 after the U-Net) in one kernel.  coef: (B, 5) fp32 CUDA tensor of
+    per-sample (sqrt_recip_ac, sqrt_recipm1_ac, posterior_mean_coef1, posterior_mean_coef2, (t != 0) * exp(0.5 logvar)).
+    Returns x_prev (and x_recon).  Bit-identical to the eager tensor expression."""
+    x, eps, noise = _f32c(x, "x"), _f32c(eps, "eps"), _f32c(noise, "noise")
+    coef = _f32c(coef, "coef")
+    B = x.shape[0]
+    if coef.shape != (B, 5) or eps.shape != x.shape or noise.shape != x.shape:
+        raise ValueError("ddpm_step: eps / noise must match x and coef must be (B, 5)")
+    x_prev = torch.empty_like(x)
+    x0 = torch.empty_like(x) if return_x0 else None
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.lidm_ddpm_step(x.data_ptr(), eps.data_ptr(), noise.data_ptr(), coef.data_ptr(), B, x.numel() // B,
+                                      int(bool(clip_denoised)), x_prev.data_ptr(), x0.data_ptr() if x0 is not None else None,
+                                      _stream_ptr(x.device)))
+    return (x_prev, x0) if return_x0 else x_prev
+
+
 def backproject(img, fov, depth_range, depth_scale, log_scale=True, return_mask=True, input_is_unit=False):
     """range2xyz on the device: img (B,H,W) or (B,1,H,W) fp32 in [-1,1] -> xyz (B,3,H,W) fp32 (-1 where masked),
     mask (B,H,W) uint8 (reference lidm/utils/lidar_utils.py:175-204 + scripts/sample.py:29-35)."""

@@ -104,6 +104,19 @@ def test_ancestral_ddpm_against_reference(model, monkeypatch):
         mask = (1 - (t == 0).float()).reshape(B, 1, 1, 1)
         xp = mean + mask * (0.5 * logvar).exp() * nz
         assert R.rel_l2(xp.cpu(), g["xt"][i + 1]) < 1e-6
+        # the fused kernel behind p_sample (lidm_ddpm_step) is that expression, bit for bit (incl. clamp and the t == 0 mask)
+        from lidar_layout_b200 import ops
+        for tt, clip in ((t, False), (t, True), (torch.zeros_like(t), False)):
+            xr = model.predict_start_from_noise(xt, t=tt, noise=e)
+            if clip:
+                xr = xr.clamp(-1., 1.)
+            mean, _, logvar = model.q_posterior(x_start=xr, x_t=xt, t=tt)
+            want = mean + (1 - (tt == 0).float()).reshape(B, 1, 1, 1) * (0.5 * logvar).exp() * nz
+            coef = torch.stack([model.sqrt_recip_alphas_cumprod[tt], model.sqrt_recipm1_alphas_cumprod[tt],
+                                model.posterior_mean_coef1[tt], model.posterior_mean_coef2[tt],
+                                (1 - (tt == 0).float()) * (0.5 * model.posterior_log_variance_clipped[tt]).exp()], dim=1).float()
+            got, got0 = ops.ddpm_step(xt, e, nz, coef, clip_denoised=clip, return_x0=True)
+            assert torch.equal(got, want) and torch.equal(got0, xr)
     # and without injected noise it runs on the global RNG like the reference
     monkeypatch.undo()
     torch.manual_seed(0)
