@@ -107,6 +107,10 @@ struct ConvW {
   int n_alloc = 0, k_alloc = 0;
   int nseg = 1;   // operand-split segments per tap (precise mode: 3 for hi/lo inputs, 2 for exact-bf16 inputs)
   bool f16 = false;   // packed as IEEE half instead of bf16
+  // optional copy with an identity block appended along K ([W | I], row stride k_alloc_id): a 1x1 projection whose residual
+  // is added by the GEMM itself, the residual tensor riding in as a second A operand (GemmEpilogue::a2 + a2_diag)
+  bf16* w_id = nullptr;
+  int k_alloc_id = 0;
 };
 struct NormW { float* gamma = nullptr; float* beta = nullptr; int C = 0; };
 struct ResW {
@@ -115,7 +119,7 @@ struct ResW {
   // ResBlock up- (1) / down- (2) sampling of both h and x
   bool film = false; int updown = 0;
 };
-struct AttnW { NormW n; ConvW qkv, proj; ConvW proj_id; /* proj with an identity block appended along K: the residual rides in as a second A operand */ int ch = 0, heads = 0; };
+struct AttnW { NormW n; ConvW qkv, proj; int ch = 0, heads = 0; };
 // BasicTransformerBlock / SpatialTransformer weights (reference lidm/modules/attention.py:196-261)
 struct STBlockW {
   NormW n1, n2, n3;           // LayerNorms
@@ -541,6 +545,25 @@ struct Builder {
     prep_gst(ep, N, w.n_alloc);
     op([=](cudaStream_t s) { launch_conv_gemm(a, taps, b, N, ep, s); }, PROF_GEMM, gemm_flops(a, taps.n, N) * w.nseg, 0,
        gemm_label(a, taps.n * w.nseg, N));
+  }
+
+  // 1x1 GEMM + residual: through the identity-extended weights when they exist (the residual is a second A operand,
+  // full 128-byte rows through the TMA ring), else as a per-thread residual read in the epilogue
+  void gemm_res(const View& a, const ConvW& w, const GemmEpilogue& ep_in, const View& residual, float res_scale = 1.f) {
+    static const bool no_idres = getenv("LIDM_NO_IDRES") != nullptr;   // A/B switch
+    GemmEpilogue ep = ep_in;
+    if (w.w_id != nullptr && !no_idres && res_scale == 1.f && residual.wpitch == 0 && residual.C == w.cout && residual.f16 == a.f16 &&
+        residual.B == a.B && residual.H == a.H && residual.W == a.W && !ep.geglu) {
+      ConvW wi = w;
+      wi.w = w.w_id; wi.k_alloc = w.k_alloc_id;
+      ep.a2 = residual;
+      ep.a2_diag = true;
+      gemm(a, taps_1x1(), wi, ep);
+    } else {
+      ep.residual = residual;
+      ep.res_scale = res_scale;
+      gemm(a, taps_1x1(), w, ep);
+    }
   }
 
   // =============================================================================================== precise mode
@@ -1046,18 +1069,10 @@ struct Builder {
        4.0 * B * heads * (double)T * T * 32, 0, "attn T" + std::to_string(T) + " heads" + std::to_string(heads));
     release(bqk);
     {
-      static const bool no_idres = getenv("LIDM_NO_IDRES") != nullptr;   // A/B switch
       GemmEpilogue ep;
       ep.bias = a.proj.bias;
       ep.out = dst;
-      if (a.proj_id.w != nullptr && !no_idres && x.wpitch == 0 && x.C == C && x.f16 == ao.f16) {
-        ep.a2 = x;               // out = proj(a) + x with x as a second A operand against an identity block
-        ep.a2_diag = true;
-        gemm(ao, taps_1x1(), a.proj_id, ep);
-      } else {
-        ep.residual = x;
-        gemm(ao, taps_1x1(), a.proj, ep);
-      }
+      gemm_res(ao, a.proj, ep, x);
     }
     release(ba);
   }
@@ -1115,12 +1130,15 @@ struct Builder {
     op([=](cudaStream_t s) { launch_layernorm(x, y, n.gamma, n.beta, 1e-5f, s); }, PROF_NORM, 0,
        4.0 * x.B * x.H * x.W * x.C, "ln C" + std::to_string(x.C) + " @" + std::to_string(x.H) + "x" + std::to_string(x.W));
   }
-  void lin(const View& a, const ConvW& w, const View& out, const View* residual = nullptr) {
+  // `stats`: the output feeds a GroupNorm (the producing GEMM emits its granule statistics); LayerNorm / attention consumers
+  // take none, and the statistics pass is a fifth of a short-K epilogue
+  void lin(const View& a, const ConvW& w, const View& out, const View* residual = nullptr, bool stats = false) {
     GemmEpilogue ep;
     ep.bias = w.bias;
-    if (residual) ep.residual = *residual;
     ep.out = out;
-    gemm(a, taps_1x1(), w, ep);
+    if (!stats) ep.out.gst = nullptr;
+    if (residual) gemm_res(a, w, ep, *residual);
+    else gemm(a, taps_1x1(), w, ep);
   }
 
   // SpatialTransformer.forward / BasicTransformerBlock._forward / CrossAttention.forward / GEGLU
@@ -1188,7 +1206,7 @@ struct Builder {
       release(bh2);
       hcur = h3; bh = bh3;
     }
-    lin(hcur, t.proj_out, dst, &x);
+    lin(hcur, t.proj_out, dst, &x, true);
     release(bh);
   }
 
@@ -2047,23 +2065,20 @@ void run_plan_graphed(lidm_handle* h, Plan* P, int slot, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------- finalize
 // [W | I]: a 1x1 projection whose residual is added by the GEMM itself (GemmEpilogue::a2 + a2_diag): the residual tensor
 // streams through the TMA ring as a second A operand against the identity block.
-ConvW with_identity(Packer& pk, const ConvW& c) {
-  ConvW f = c;
-  if (c.w == nullptr || c.nseg != 1 || c.kh != 1 || c.kw != 1 || c.k_alloc != c.cin || c.cout % 256 != 0 || c.cout > 1024) {
-    f.w = nullptr;
-    return f;
-  }
+void add_identity(Packer& pk, ConvW& c) {
+  if (pk.precise || c.w == nullptr || c.nseg != 1 || c.kh != 1 || c.kw != 1 || c.k_alloc != c.cin || c.cin % 64 != 0 ||
+      c.cout % 256 != 0 || c.cout > 1024)
+    return;
   lidm_handle* h = pk.h;
-  f.k_alloc = c.cin + c.cout;
-  f.w = dev_alloc<bf16>(h, (size_t)f.n_alloc * f.k_alloc);
-  LIDM_CUDA_CHECK(cudaMemcpy2DAsync(f.w, (size_t)f.k_alloc * sizeof(bf16), c.w, (size_t)c.k_alloc * sizeof(bf16),
+  c.k_alloc_id = c.cin + c.cout;
+  c.w_id = dev_alloc<bf16>(h, (size_t)c.n_alloc * c.k_alloc_id);
+  LIDM_CUDA_CHECK(cudaMemcpy2DAsync(c.w_id, (size_t)c.k_alloc_id * sizeof(bf16), c.w, (size_t)c.k_alloc * sizeof(bf16),
                                     (size_t)c.cin * sizeof(bf16), c.n_alloc, cudaMemcpyDeviceToDevice, pk.s));
-  std::vector<uint16_t> eye((size_t)f.n_alloc * c.cout, 0);
+  std::vector<uint16_t> eye((size_t)c.n_alloc * c.cout, 0);
   for (int i = 0; i < c.cout; ++i) eye[(size_t)i * c.cout + i] = pk.f16 ? 0x3c00 : 0x3f80;   // 1.0 as IEEE half / bf16
-  LIDM_CUDA_CHECK(cudaMemcpy2DAsync(f.w + c.cin, (size_t)f.k_alloc * sizeof(bf16), eye.data(), (size_t)c.cout * sizeof(bf16),
-                                    (size_t)c.cout * sizeof(bf16), f.n_alloc, cudaMemcpyHostToDevice, pk.s));
+  LIDM_CUDA_CHECK(cudaMemcpy2DAsync(c.w_id + c.cin, (size_t)c.k_alloc_id * sizeof(bf16), eye.data(), (size_t)c.cout * sizeof(bf16),
+                                    (size_t)c.cout * sizeof(bf16), c.n_alloc, cudaMemcpyHostToDevice, pk.s));
   LIDM_CUDA_CHECK(cudaStreamSynchronize(pk.s));
-  return f;
 }
 
 ResW pack_res(Packer& pk, const std::string& p, int cin, int cout, int kh, int kw, bool unet) {
@@ -2148,7 +2163,7 @@ AttnW pack_unet_attn(Packer& pk, const std::string& p, int ch, int heads) {
   LIDM_CUDA_CHECK(cudaMemcpy(c.bias, bp.data(), bp.size() * sizeof(float), cudaMemcpyHostToDevice));
   a.qkv = c;
   a.proj = pk.conv(p + ".proj_out", ch, ch, 1, 1, 0, 2);   // its input (attention output) is exact bf16
-  if (!pk.precise) a.proj_id = with_identity(pk, a.proj);
+  add_identity(pk, a.proj);
   return a;
 }
 
@@ -2543,6 +2558,7 @@ void finalize(lidm_handle* h, bool use_ema) {
     t.n = pk.norm(p + ".norm", c);
     t.proj_in = pk.conv(p + ".proj_in", c, c, 1, 1);
     t.proj_out = pk.conv(p + ".proj_out", c, c, 1, 1);
+    add_identity(pk, t.proj_out);
     for (int k = 0; k < cfg.transformer_depth; ++k) {
       const std::string bp = p + ".transformer_blocks." + std::to_string(k);
       STBlockW w;
@@ -2556,6 +2572,7 @@ void finalize(lidm_handle* h, bool use_ema) {
       w.out2 = pack_stacked_linear(pk, {{bp + ".attn2.to_out.0.weight", 1.f}}, c, c, bp + ".attn2.to_out.0.bias");
       w.ff0 = pack_geglu_linear(pk, bp + ".ff.net.0.proj", 8 * c, c);
       w.ff2 = pack_stacked_linear(pk, {{bp + ".ff.net.2.weight", 1.f}}, c, 4 * c, bp + ".ff.net.2.bias");
+      add_identity(pk, w.out1); add_identity(pk, w.out2);   // (ff2: K = 4C is long enough to hide the residual read)
       w.kv_col = h->ctx_n;
       h->ctx_n += 2 * c;
       st_blocks.emplace_back(bp, c);
