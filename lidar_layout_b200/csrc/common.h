@@ -202,6 +202,10 @@ void launch_oaca_layout_kv(const float* xf_out, const float* cls, int B, int E, 
 void launch_avgpool2(const View& x, const View& y, cudaStream_t s);
 // ops.Resample (lidm/modules/unets/ops.py:52-143) with the [1,3,3,1] window, ring = True: x2 up / down sampling of a
 // halo-free channels-last tensor (circular on W, zeros on H)
+// R2DM input convolution: constant coordinate-channel map (once) + per-step convolution of the image channels (layout.cu)
+void launch_eff_in_map(const float* w, const float* bias, const float* cenc, int Cx, int Ce, int H, int W, int C0, float* map,
+                        cudaStream_t s);
+void launch_eff_in_conv(const float* x, const float* w, const float* map, int Cx, const View& out, cudaStream_t s);
 void launch_fir_down2(const View& x, const View& y, cudaStream_t s);
 void launch_fir_up2(const View& x, const View& y, cudaStream_t s);
 // LayoutTransformerEncoder.forward (layout_encoder.py:222-281), fp32, one CTA per sample.  layers_dev: device array of

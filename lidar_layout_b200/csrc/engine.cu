@@ -232,6 +232,8 @@ struct lidm_handle {
   EffBlock eff_d[4], eff_u[4];
   ConvW eff_in_conv;
   float* eff_cenc = nullptr; int eff_cenc_ch = 0;          // Fourier features of the polar coordinates (extra_ch, H, W) fp32
+  float* eff_in_map = nullptr;                             // in_conv of the coordinate channels + bias: constant (H, W, C0) fp32 map
+  float* eff_in_w = nullptr;                               // in_conv weights of the image channels [C0][Cx][9] fp32
   float *ones_c = nullptr, *zeros_c = nullptr;            // AdaGN = GroupNorm without affine parameters
   // LayoutTransformerEncoder (cond_stage_model.*), fp32; packed when the state-dict carries it
   bool has_layout_encoder = false;
@@ -1442,38 +1444,17 @@ void build_eff_plan_pass(lidm_handle* h, Plan* P, bool dry, size_t* high) {
   const int C0 = cfg.model_channels;
   int C[5] = {C0, 0, 0, 0, 0};
   for (int i = 0; i < 4; ++i) C[i + 1] = C0 * cfg.channel_mult[i];
-  // the assembled input lives for the whole plan: the coordinate channels are written once, the image channels per call
-  Buf bxin;
-  float* xin = b.raw<float>((size_t)B * Cin * H * W, &bxin);
-  const size_t HW = (size_t)H * W;
-  b.op([=](cudaStream_t s) {
-    if (!P->eff_input_ready) {
-      for (int bb = 0; bb < B; ++bb)
-        LIDM_CUDA_CHECK(cudaMemcpyAsync(xin + ((size_t)bb * Cin + Cx) * HW, h->eff_cenc, (size_t)Ce * HW * sizeof(float),
-                                        cudaMemcpyDeviceToDevice, s));
-      P->eff_input_ready = true;
-    }
-    LIDM_CUDA_CHECK(cudaMemcpy2DAsync(xin, (size_t)Cin * HW * sizeof(float), P->x, (size_t)Cx * HW * sizeof(float),
-                                      (size_t)Cx * HW * sizeof(float), B, cudaMemcpyDeviceToDevice, s));
-  });
   // skip-concatenation buffers [up-path tensor | down-path tensor] at levels 1..3
   Buf bcat[4];
   View cat[4];
   for (int l = 1; l <= 3; ++l) cat[l] = b.act(B, H >> (l - 1), W >> (l - 1), 2 * C[l], 0, 0, &bcat[l]);
   Buf bh0;
   View h0 = b.act(B, H, W, C[0], 0, 0, &bh0);
-  {
-    const int kpad = h->eff_in_conv.k_alloc;
-    Buf bc;
-    bf16* col = b.raw<bf16>((size_t)B * HW * kpad, &bc);
-    const bool f16 = b.f16;
-    b.op([=](cudaStream_t s) { launch_im2col_nchw_f32(xin, B, Cin, H, W, 3, 3, 1, 1, col, kpad, s, f16); });
-    View a = b.mat(col, B, H, W, kpad, kpad);
-    GemmEpilogue ep;
-    ep.bias = h->eff_in_conv.bias;
-    ep.out = h0;
-    b.gemm(a, taps_1x1(), h->eff_in_conv, ep);
-    b.release(bc);
+  h0.gst = nullptr;     // written by the CUDA-core input convolution: the first GroupNorm takes its own statistics
+  if (Cx <= 2 && C[0] % 8 == 0) {
+    b.op([=](cudaStream_t s) { launch_eff_in_conv(P->x, h->eff_in_w, h->eff_in_map, Cx, h0, s); });
+  } else {
+    throw Error(LIDM_ERR_INVALID, "EfficientUNet input convolution: one or two image channels");
   }
   // one Block (efficient_unet.py:113-186)
   auto run_block = [&](const lidm_handle::EffBlock& blk, View x, Buf xbuf, bool own_x, const View& dst) {
@@ -2420,6 +2401,20 @@ void finalize_unet_efficient(lidm_handle* h, Packer& pk, std::vector<std::pair<s
   }
   const int cin0 = cfg.in_channels + h->eff_cenc_ch;
   h->eff_in_conv = pk.conv(U + "in_conv", C[0], cin0, 3, 3, (9 * cin0 + 63) / 64 * 64);
+  {
+    // the coordinate channels are constants: their share of in_conv (+ bias) becomes a per-pixel map, the image channels keep
+    // their fp32 weights for the per-step CUDA-core convolution (launch_eff_in_conv)
+    const DevTensor& wraw = find_raw(h, U + "in_conv.weight", pk.ema);
+    const DevTensor& braw = find_raw(h, U + "in_conv.bias", pk.ema);
+    LIDM_REQUIRE(wraw.numel == (int64_t)C[0] * cin0 * 9 && braw.numel == C[0], "in_conv weight size");
+    const int Cx = cfg.in_channels;
+    h->eff_in_map = dev_alloc<float>(h, (size_t)H * W * C[0]);
+    h->eff_in_w = dev_alloc<float>(h, (size_t)C[0] * Cx * 9);
+    launch_eff_in_map(wraw.p, braw.p, h->eff_cenc, Cx, h->eff_cenc_ch, H, W, C[0], h->eff_in_map, pk.s);
+    LIDM_CUDA_CHECK(cudaMemcpy2DAsync(h->eff_in_w, (size_t)Cx * 9 * sizeof(float), wraw.p, (size_t)cin0 * 9 * sizeof(float),
+                                      (size_t)Cx * 9 * sizeof(float), C[0], cudaMemcpyDeviceToDevice, pk.s));
+    LIDM_CUDA_CHECK(cudaStreamSynchronize(pk.s));
+  }
   auto pack_res_eff = [&](const std::string& p, int cin, int cout, ResW& r) {
     r.cin = cin; r.cout = cout; r.film = true;
     r.n1 = pk.norm(p + ".norm1", cin);

@@ -1,5 +1,5 @@
 """Developer tool: per-op CUDA-event breakdown of one U-Net evaluation (and optionally the decoder) at batch B.
-    LIDM_PROFILE_DUMP=gpurun_out/ops.csv python tests/op_profile.py [B] [uncond|cam2lidar|sem2lidar] [ctx_len]"""
+    LIDM_PROFILE_DUMP=gpurun_out/ops.csv python tests/op_profile.py [B] [uncond|cam2lidar|sem2lidar|layout2lidar|r2dm] [ctx_len]"""
 import collections, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -15,7 +15,7 @@ if os.path.exists(path):
 which = sys.argv[2] if len(sys.argv) > 2 else "uncond"
 L = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 cfg = {"uncond": C.kitti_uncond, "cam2lidar": C.kitti_cam2lidar, "sem2lidar": C.kitti_sem2lidar,
-       "layout2lidar": C.nuscenes_layout2lidar}[which]()
+       "layout2lidar": C.nuscenes_layout2lidar, "r2dm": lambda: C.nuscenes_r2dm((64, 1024))}[which]()
 eng = Engine(cfg).load_state_dict(random_state_dict(cfg, 0))
 x = torch.randn((B,) + tuple(cfg.latent_shape), device="cuda")
 t = torch.full((B,), 501, dtype=torch.long, device="cuda")
