@@ -109,9 +109,13 @@ __device__ __forceinline__ float gelu_erf_fast(float g) {
 // ring of STAGES buffers then carries A chunks only.  With streamed weights a short-K tile re-reads its 2 * BN * K bytes of
 // B for every 128 pixels (128 KB of B against 64 KB of A at K = 256, BN = 256) and the 3-stage ring bounds the tile time
 // by the load latency (ncu: the epilogue warps spend 59 % of their samples waiting for the accumulator).
-template <int BN, int STAGES, int RESK = 0>
+// PAIR: two CTAs of a cluster work as one tcgen05 cta_group::2 unit on two pixel tiles of the SAME channel tile: each CTA
+// loads its own A rows and HALF of the B rows, the leader's MMAs (M = 256) read both halves, each CTA's tensor memory gets
+// its own 128 rows.  A 128x256 tile re-reads 32 KB of weights per 16 KB of activations per K chunk and the 3x3 convs are
+// bound by exactly that L2 -> shared-memory traffic (profiles/r02f_summary.md); the pair halves the weight share.
+template <int BN, int STAGES, int RESK = 0, bool PAIR = false>
 struct PersistLayout {
-  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int B_STAGE_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;
   static constexpr int B_STRIDE = (B_STAGE_BYTES + 1023) / 1024 * 1024;
   static constexpr int B_BUFS = RESK > 0 ? RESK / BK : STAGES;       // resident: one buffer per K chunk
   static constexpr int A_OFF = 0;
@@ -135,13 +139,14 @@ struct PersistLayout {
   static constexpr int COLS = BN / (EPI_WARPS / 4);                 // columns drained by one epilogue thread
 };
 
-template <int BN, int STAGES, bool F16, int RESK = 0>
-__global__ void __launch_bounds__((PersistLayout<BN, STAGES, RESK>::THREADS), 1)
+template <int BN, int STAGES, bool F16, int RESK = 0, bool PAIR = false>
+__global__ void __launch_bounds__((PersistLayout<BN, STAGES, RESK, PAIR>::THREADS), 1)
 conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmA2,
                          const GemmKernelParams p, int num_m_tiles,
                          int num_tiles, int use_tma_store) {
-  using L = PersistLayout<BN, STAGES, RESK>;
+  using L = PersistLayout<BN, STAGES, RESK, PAIR>;
+  static_assert(!(PAIR && RESK > 0), "CTA pairs: streamed weights only");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
@@ -158,10 +163,19 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int num_n_tiles = num_tiles / num_m_tiles;
   // tile walk: streamed weights - tiles blockIdx.x, + gridDim.x, ... of the (pixel tile, channel tile) grid; resident weights -
   // the CTA owns channel tile blockIdx.x % num_n_tiles and walks pixel tiles (the launcher makes gridDim.x a multiple of it)
-  const int tile_first = RESK > 0 ? (int)blockIdx.x / num_n_tiles : (int)blockIdx.x;
-  const int tile_step = RESK > 0 ? (int)gridDim.x / num_n_tiles : (int)gridDim.x;
-  const int tile_end = RESK > 0 ? num_m_tiles : num_tiles;
+  // CTA pairs: the walk is over PAIRS of pixel tiles (2 mp + rank), blockIdx.x / 2 = the cluster
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const int num_m_units = PAIR ? num_m_tiles / 2 : num_m_tiles;
+  const int tile_first = RESK > 0 ? (int)blockIdx.x / num_n_tiles : (PAIR ? (int)blockIdx.x / 2 : (int)blockIdx.x);
+  const int tile_step = RESK > 0 ? (int)gridDim.x / num_n_tiles : (PAIR ? (int)gridDim.x / 2 : (int)gridDim.x);
+  const int tile_end = RESK > 0 ? num_m_tiles : num_m_units * num_n_tiles;
   const int res_n0 = ((int)blockIdx.x % num_n_tiles) * BN;
+  auto tile_coords = [&](int tile, int& m_tile, int& n0) {
+    if (RESK > 0) { m_tile = tile; n0 = res_n0; return; }
+    const int mu = p.n_fast ? tile / num_n_tiles : tile % num_m_units;
+    n0 = (p.n_fast ? tile % num_n_tiles : tile / num_m_units) * BN;
+    m_tile = PAIR ? 2 * mu + (int)cta_rank : mu;
+  };
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tmA);
@@ -169,13 +183,20 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (use_tma_store) prefetch_tensormap(&tmO);
     if (p.k2chunks) prefetch_tensormap(&tmA2);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], RESK > 0 ? 4 : L::EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], RESK > 0 ? 4 : (PAIR ? 2 * L::EPI_WARPS : L::EPI_WARPS));   // pair: both CTAs' epilogues release the leader
+    }
     mbar_init(bres_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, L::TMEM_COLS); tmem_relinquish(); }
+  if (warp == 1) {
+    if (PAIR) { tmem_alloc_2sm(tmem_slot, L::TMEM_COLS); tmem_relinquish_2sm(); }
+    else { tmem_alloc(tmem_slot, L::TMEM_COLS); tmem_relinquish(); }
+  }
   tcgen05_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();      // barrier inits and the allocation are visible to the peer before any remote arrive / MMA
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                  // everything below reads / writes tensors of earlier kernels
@@ -226,8 +247,9 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
       } else
       for (int tile = tile_first; tile < tile_end; tile += tile_step) {
-        const int m_tile = RESK > 0 ? tile : (p.n_fast ? tile / num_n_tiles : tile % num_m_tiles);
-        const int n0 = RESK > 0 ? res_n0 : (p.n_fast ? tile % num_n_tiles : tile / num_m_tiles) * BN;
+        int m_tile, n0;
+        tile_coords(tile, m_tile, n0);
+        const int bn0 = n0 + (PAIR ? (int)cta_rank * (BN / 2) : 0);       // this CTA's rows of the B tile
         const int bt = m_tile / p.tiles_per_img;
         const int b = bt * p.bbox;
         const int r = m_tile - bt * p.tiles_per_img;
@@ -242,6 +264,12 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               if (RESK > 0) {
                 mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES);
                 tma_load_4d(smem + L::A_OFF + s * A_STAGE_BYTES, &tmA, &full_bar[s], acoff + kc * BK, x, y, b);
+              } else if (PAIR) {
+                // both CTAs' bytes are counted on the LEADER's barrier (its MMA thread waits for the whole pair)
+                const uint32_t fb = mapa_shared(smem_u32(&full_bar[s]), 0);
+                if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * (A_STAGE_BYTES + L::B_STAGE_BYTES));
+                tma_load_4d_2sm(smem + L::A_OFF + s * A_STAGE_BYTES, &tmA, fb, acoff + kc * BK, x, y, b);
+                tma_load_3d_2sm(smem + L::B_OFF + s * L::B_STRIDE, &tmB, fb, bkoff + kc * BK, bn0, p.wt_batched ? b : 0);
               } else {
                 mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + L::B_STAGE_BYTES);
                 tma_load_4d(smem + L::A_OFF + s * A_STAGE_BYTES, &tmA, &full_bar[s], acoff + kc * BK, x, y, b);
@@ -256,7 +284,12 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int k2lo = p.a2_diag ? n0 / BK : 0, k2hi = p.a2_diag ? (n0 + BN) / BK : p.k2chunks;
         for (int kc = k2lo; kc < k2hi; ++kc) {        // second A operand: one unshifted tap after the main K range
           mbar_wait(&empty_bar[s], ph ^ 1);
-          if (leader) {
+          if (leader && PAIR) {
+            const uint32_t fb = mapa_shared(smem_u32(&full_bar[s]), 0);
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * (A_STAGE_BYTES + L::B_STAGE_BYTES));
+            tma_load_4d_2sm(smem + L::A_OFF + s * A_STAGE_BYTES, &tmA2, fb, kc * BK, w0 + p.hl2, h0, b);
+            tma_load_3d_2sm(smem + L::B_OFF + s * L::B_STRIDE, &tmB, fb, p.b2_koff + kc * BK, bn0, p.wt_batched ? b : 0);
+          } else if (leader) {
             mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + L::B_STAGE_BYTES);
             tma_load_4d(smem + L::A_OFF + s * A_STAGE_BYTES, &tmA2, &full_bar[s], kc * BK, w0 + p.hl2, h0, b);
             tma_load_3d(smem + L::B_OFF + s * L::B_STRIDE, &tmB, &full_bar[s], p.b2_koff + kc * BK, n0,
@@ -272,6 +305,7 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     {
       const bool leader = elect_one() != 0;
       constexpr uint32_t idesc = make_idesc_h<F16>(BM, BN);
+      constexpr uint32_t idesc_pair = make_idesc_h<F16>(2 * BM, BN);
       int s = 0; uint32_t ph = 0;
       int lt = 0;
       if (RESK > 0 && tile_first < tile_end) mbar_wait(bres_bar, 0);
@@ -302,10 +336,10 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
           __syncwarp();
         }
-      } else
+      } else if (!PAIR || cta_rank == 0)       // pair: the leader issues for both CTAs
       for (int tile = tile_first; tile < tile_end; tile += tile_step, ++lt) {
         const int ab = lt & 1;
-        mbar_wait(&tempty_bar[ab], ((lt >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+        mbar_wait(&tempty_bar[ab], ((lt >> 1) & 1) ^ 1);   // epilogue(s) have drained this accumulator
         tcgen05_fence_after();
         const uint32_t d = tmem_base + ab * L::ACC_COLS;
         for (int it = 0; it < num_it; ++it) {
@@ -314,14 +348,23 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           const uint64_t adesc = make_kmajor_desc<128>(smem_u32(smem + L::A_OFF + s * A_STAGE_BYTES));
           const uint64_t bdesc = make_kmajor_desc<128>(smem_u32(smem + L::B_OFF + s * L::B_STRIDE));
           if (leader) {
+            if (PAIR) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) umma_bf16_ss(d, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
-            umma_commit(&empty_bar[s]);
+              for (int k = 0; k < BK / 16; ++k) umma_bf16_ss_2sm(d, adesc + 2 * k, bdesc + 2 * k, idesc_pair, (it | k) != 0);
+              umma_commit_2sm(&empty_bar[s], 3);           // frees the stage in both CTAs
+            } else {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) umma_bf16_ss(d, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0);
+              umma_commit(&empty_bar[s]);
+            }
           }
           __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        if (leader) umma_commit(&tfull_bar[ab]);
+        if (leader) {
+          if (PAIR) umma_commit_2sm(&tfull_bar[ab], 3);
+          else umma_commit(&tfull_bar[ab]);
+        }
         __syncwarp();
       }
     }
@@ -478,8 +521,8 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     } else
     for (int tile = tile_first; tile < tile_end; tile += tile_step, ++lt) {
       const int ab = lt & 1;
-      const int m_tile = RESK > 0 ? tile : (p.n_fast ? tile / num_n_tiles : tile % num_m_tiles);
-      const int n0 = RESK > 0 ? res_n0 : (p.n_fast ? tile % num_n_tiles : tile / num_m_tiles) * BN;
+      int m_tile, n0;
+      tile_coords(tile, m_tile, n0);
       const int bt = m_tile / p.tiles_per_img;
       const int b0 = bt * p.bbox;
       const int b = b0 + rb;
@@ -538,7 +581,7 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             if (hf == NH - 1) {
               tcgen05_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(&tempty_bar[ab]);
+              if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[ab]), 0)); else mbar_arrive(&tempty_bar[ab]); }
             }
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
@@ -679,7 +722,7 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (c0 + CH >= col_lo + L::COLS) {   // last TMEM read of this thread: hand the accumulator back to the MMA warp
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[ab]);
+          if (lane == 0) { if (PAIR) mbar_arrive_cluster(mapa_shared(smem_u32(&tempty_bar[ab]), 0)); else mbar_arrive(&tempty_bar[ab]); }
         }
         if (!live) continue;
         {
@@ -800,18 +843,23 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     tcgen05_fence_before();
   }
 
-  __syncthreads();
-  if (warp == 1) { tcgen05_fence_after(); tmem_dealloc(tmem_base, L::TMEM_COLS); }
+  if (PAIR) cluster_sync_all();      // the peer's tensor memory and barriers stay valid until both CTAs are done
+  else __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    if (PAIR) tmem_dealloc_2sm(tmem_base, L::TMEM_COLS);
+    else tmem_dealloc(tmem_base, L::TMEM_COLS);
+  }
 }
 
-template <int BN, int STAGES, bool F16, int RESK = 0>
+template <int BN, int STAGES, bool F16, int RESK = 0, bool PAIR = false>
 void launch_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const CUtensorMap& tmA2,
                     const GemmKernelParams& p,
                     int num_m_tiles, int num_tiles, int use_tma_store, cudaStream_t stream) {
-  using L = PersistLayout<BN, STAGES, RESK>;
+  using L = PersistLayout<BN, STAGES, RESK, PAIR>;
   static int num_sms = 0;
   if (num_sms == 0) {
-    LIDM_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_persist_kernel<BN, STAGES, F16, RESK>,
+    LIDM_CUDA_CHECK(cudaFuncSetAttribute(conv_gemm_persist_kernel<BN, STAGES, F16, RESK, PAIR>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     int dev = 0;
     LIDM_CUDA_CHECK(cudaGetDevice(&dev));
@@ -825,8 +873,26 @@ void launch_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtens
     if (per_n > num_m_tiles) per_n = num_m_tiles;
     grid = per_n * num_n_tiles;
   }
-  launch_pdl(conv_gemm_persist_kernel<BN, STAGES, F16, RESK>, dim3(grid), dim3(L::THREADS), L::TOTAL, stream, tmA, tmB, tmO, tmA2, p,
-             num_m_tiles, num_tiles, use_tma_store);
+  if (PAIR) {
+    grid &= ~1;                        // whole clusters of two
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(L::THREADS); cfg.dynamicSmemBytes = L::TOTAL; cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    int na = 1;
+    if (pdl_enabled()) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    LIDM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, conv_gemm_persist_kernel<BN, STAGES, F16, RESK, PAIR>, tmA, tmB, tmO, tmA2, p, num_m_tiles,
+                                       num_tiles, use_tma_store));
+  } else {
+    launch_pdl(conv_gemm_persist_kernel<BN, STAGES, F16, RESK, PAIR>, dim3(grid), dim3(L::THREADS), L::TOTAL, stream, tmA, tmB, tmO, tmA2,
+               p, num_m_tiles, num_tiles, use_tma_store);
+  }
   LIDM_COUNT_LAUNCH(1);
 }
 
@@ -963,11 +1029,16 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
   }
   const uint64_t wld = wtb.ld != 0 ? (uint64_t)wtb.ld : Ktot;
   LIDM_REQUIRE(wld >= Ktot && wld % 8 == 0 && (reinterpret_cast<uintptr_t>(wt) & 15) == 0, "weight operand alignment");
-  CUtensorMap tmB = make_tma_3d(wt, Ktot, (uint64_t)n_alloc, wt_batched ? (uint64_t)a.B : 1, wld * 2,
-                                wt_batched ? (uint64_t)wtb.batch_stride * 2 : wld * 2 * (uint64_t)n_alloc, BK, BN,
-                                128);
   const int num_m_tiles = bbox > 1 ? (a.B + bbox - 1) / bbox : a.B * p.tiles_per_img;
   const int num_tiles = num_m_tiles * (n_alloc / BN);
+  // CTA pairs (cta_group::2) for the wide streamed-weight tiles: two pixel tiles of one channel tile per cluster, each CTA loads
+  // half of the B rows (LIDM_GEMM_PAIR=0 switches them off)
+  static const int pair_on = getenv("LIDM_GEMM_PAIR") ? atoi(getenv("LIDM_GEMM_PAIR")) : 1;
+  const bool pair = pair_on && BN == 256 && !resk && bbox == 1 && num_m_tiles % 2 == 0 && num_m_tiles >= 2 &&
+                    (!wt_batched || p.tiles_per_img % 2 == 0);
+  CUtensorMap tmB = make_tma_3d(wt, Ktot, (uint64_t)n_alloc, wt_batched ? (uint64_t)a.B : 1, wld * 2,
+                                wt_batched ? (uint64_t)wtb.batch_stride * 2 : wld * 2 * (uint64_t)n_alloc, BK, pair ? BN / 2 : BN,
+                                128);
   {
     // Tile order: the output-channel tiles of one pixel tile run back to back (and so concurrently on neighbouring
     // CTAs), so an A tile comes from HBM once and from L2 afterwards.  Measured in the U-Net at B = 64: the wide 3x3
@@ -1003,6 +1074,7 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
 #define LIDM_LAUNCH_GEMM(F16)                                                                                         \
   do {                                                                                                                  \
     if (resk == 256) launch_persist<128, 8, F16, 256>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream); \
+    else if (BN == 256 && pair) launch_persist<256, 4, F16, 0, true>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream); \
     else if (BN == 256) launch_persist<256, 3, F16>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream);   \
     else if (BN == 128) launch_persist<128, 4, F16>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream); \
     else if (BN == 64) launch_persist<64, 6, F16>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream); \
