@@ -146,7 +146,7 @@ template <int NG, int BKV_, int POLYP, bool PP, bool F16, bool HS>
 __global__ void __launch_bounds__((Cfg<NG, BKV_, HS>::THREADS), 1)
 attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                         bf16* __restrict__ out, int out_ld, int T, int q_col, int k_col, int v_col, int kv_len,
-                        int n_qblk, int heads, int n_items) {
+                        int n_qblk, int heads, int n_items, int submax) {
   using L = Cfg<NG, BKV_, HS>;
   static_assert(!HS || (!PP && BKV_ == 128), "half split: free-running groups, 128-key tiles");
   // Row sums on the tensor pipe: the P*V product runs with N = 48, the B operand's second 32-column atom being a constant
@@ -382,14 +382,27 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         }
       }
       float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+      if (submax && !F16 && !HS) {
+        // Sub-sampled reference: the running value m only has to stay within the exponent range of the true row maximum
+        // (P = 2^(s - m) and the row sum l are formed against the SAME m, so any m gives the same quotient; in bf16 / fp32 a
+        // score 2^100 above m still neither overflows nor loses precision), so the maximum over every fourth column pair
+        // (16 of the 64 FMNMX3 of a tile, a tenth of the softmax warps' issue slots) is as good a reference as the exact one.
+        // IEEE-half P (F16) keeps the exact maximum: its exponent range is too short for values far below the reference.
 #pragma unroll
-      for (int c = 0; c < L::NCH; ++c) {
+        for (int c = 0; c < L::NCH; ++c) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          m0 = max3(m0, __uint_as_float(sv[c][8 * i + 0]), __uint_as_float(sv[c][8 * i + 1]));
-          m1 = max3(m1, __uint_as_float(sv[c][8 * i + 2]), __uint_as_float(sv[c][8 * i + 3]));
-          m2 = max3(m2, __uint_as_float(sv[c][8 * i + 4]), __uint_as_float(sv[c][8 * i + 5]));
-          m3 = max3(m3, __uint_as_float(sv[c][8 * i + 6]), __uint_as_float(sv[c][8 * i + 7]));
+          for (int i = 0; i < 4; ++i) m0 = max3(m0, __uint_as_float(sv[c][8 * i + 0]), __uint_as_float(sv[c][8 * i + 1]));
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < L::NCH; ++c) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            m0 = max3(m0, __uint_as_float(sv[c][8 * i + 0]), __uint_as_float(sv[c][8 * i + 1]));
+            m1 = max3(m1, __uint_as_float(sv[c][8 * i + 2]), __uint_as_float(sv[c][8 * i + 3]));
+            m2 = max3(m2, __uint_as_float(sv[c][8 * i + 4]), __uint_as_float(sv[c][8 * i + 5]));
+            m3 = max3(m3, __uint_as_float(sv[c][8 * i + 6]), __uint_as_float(sv[c][8 * i + 7]));
+          }
         }
       }
       float r = max3(fmaxf(m0, m1), m2, m3);
@@ -511,8 +524,9 @@ void launch_f(const bf16* q, int q_ld, int q_col, const bf16* kv, int kv_ld, int
     LIDM_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = n_items < num_sms ? n_items : num_sms;     // one persistent CTA per SM
+  static const int submax = getenv("LIDM_ATTN_SUBMAX") ? atoi(getenv("LIDM_ATTN_SUBMAX")) : 1;   // A/B switch (T = 2048: 698 -> 640 us)
   launch_pdl(attention_d32_v5_kernel<NG, BKV_, POLYP, PP, F16, HS>, dim3(grid), dim3(L::THREADS), L::SMEM_TOTAL, s, tmQ, tmKV, out.p,
-             out.ld, T, q_col, k_col, v_col, kv_rows, n_qblk, heads, n_items);
+             out.ld, T, q_col, k_col, v_col, kv_rows, n_qblk, heads, n_items, submax);
   LIDM_COUNT_LAUNCH(1);
 }
 

@@ -1032,9 +1032,10 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
   const int num_m_tiles = bbox > 1 ? (a.B + bbox - 1) / bbox : a.B * p.tiles_per_img;
   const int num_tiles = num_m_tiles * (n_alloc / BN);
   // CTA pairs (cta_group::2) for the wide streamed-weight tiles: two pixel tiles of one channel tile per cluster, each CTA loads
-  // half of the B rows (LIDM_GEMM_PAIR=0 switches them off)
+  // half of the B rows (LIDM_GEMM_PAIR=0 switches them off; 128 extends them to the 128-wide tiles, which was measured
+  // slower on the decoder's HBM-bound 128-channel levels: (1,4) conv 128 -> 128 @64x512 410 -> 499 us)
   static const int pair_on = getenv("LIDM_GEMM_PAIR") ? atoi(getenv("LIDM_GEMM_PAIR")) : 1;
-  const bool pair = pair_on && BN == 256 && !resk && bbox == 1 && num_m_tiles % 2 == 0 && num_m_tiles >= 2 &&
+  const bool pair = pair_on && (BN == 256 || (BN == 128 && pair_on == 128)) && !resk && bbox == 1 && num_m_tiles % 2 == 0 && num_m_tiles >= 2 &&
                     (!wt_batched || p.tiles_per_img % 2 == 0);
   CUtensorMap tmB = make_tma_3d(wt, Ktot, (uint64_t)n_alloc, wt_batched ? (uint64_t)a.B : 1, wld * 2,
                                 wt_batched ? (uint64_t)wtb.batch_stride * 2 : wld * 2 * (uint64_t)n_alloc, BK, pair ? BN / 2 : BN,
@@ -1076,6 +1077,7 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
     if (resk == 256) launch_persist<128, 8, F16, 256>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream); \
     else if (BN == 256 && pair) launch_persist<256, 4, F16, 0, true>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream); \
     else if (BN == 256) launch_persist<256, 3, F16>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream);   \
+    else if (BN == 128 && pair) launch_persist<128, 6, F16, 0, true>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream); \
     else if (BN == 128) launch_persist<128, 4, F16>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream); \
     else if (BN == 64) launch_persist<64, 6, F16>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream); \
     else launch_persist<16, 6, F16>(tmA, tmB, tmO, tmA2, p, num_m_tiles, num_tiles, use_tma_store, stream);             \
