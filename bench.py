@@ -405,7 +405,7 @@ def run_gpu_arm(args):
             "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
             "frac": ach / peaks["bf16_tflops_sustained"], "peak_source": peaks["source"] + " (sustained: kernel timed inside a long step)",
             "traffic": captured_traffic(),
-            "traffic_unit": "bytes per launch (mean of the 12 launches in profiles/roofline_traffic.json)",
+            "traffic_unit": "bytes per launch (mean of the launches captured in profiles/roofline_traffic.json)",
             "launches": g["launches"], "avg_launch_ms": g["ms"] / max(g["launches"], 1),
             "share_of_step": {k: v["ms"] / max(sum(x["ms"] for x in prof_unet.values()), 1e-9) for k, v in prof_unet.items()},
             "groupnorm_GBps": (prof_unet["groupnorm"]["bytes"] / (prof_unet["groupnorm"]["ms"] * 1e-3) / 1e9
