@@ -66,7 +66,13 @@ __device__ __forceinline__ void ex2_poly2(float& y0, float& y1, float x0, float 
 
 // One 32-score chunk of a row: p = 2^(s*log2e - mb) as 16 bf16 pairs into pk, row sums into (s0..s3).  POLYP of every
 // 8 pairs (evenly spread) take the polynomial instead of MUFU.EX2.
-template <int POLYP, bool SUM, bool F16>
+// TRUNC (bf16 only): P is cut to bf16 by taking the upper halves of the two fp32 values (one PRMT, one issue slot) instead of
+// round-to-nearest packing (F2FP: two).  The numerator P*V and the row sum (ones column of the same MMA) are formed from the
+// SAME truncated P, so the downward bias of truncation cancels in O / l; the rounding noise keeps its variance.
+#ifndef LIDM_ATTN_TRUNC
+#define LIDM_ATTN_TRUNC 1
+#endif
+template <int POLYP, bool SUM, bool F16, bool TRUNC = false>
 __device__ __forceinline__ void exp_chunk(const uint32_t (&sv)[32], float mb, uint32_t* pk, float& s0, float& s1,
                                           float& s2, float& s3) {
   constexpr float LOG2E = 1.4426950408889634f;
@@ -84,7 +90,8 @@ __device__ __forceinline__ void exp_chunk(const uint32_t (&sv)[32], float mb, ui
       if (i & 1) add2(s2, s3, s2, s3, p0, p1);
       else add2(s0, s1, s0, s1, p0, p1);
     }
-    pk[i] = pack_h<F16>(p0, p1);
+    if (TRUNC && !F16) pk[i] = __byte_perm(__float_as_uint(p0), __float_as_uint(p1), 0x7632);
+    else pk[i] = pack_h<F16>(p0, p1);
   }
 }
 
@@ -456,7 +463,7 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 #pragma unroll
       for (int c = 0; c < L::NCH; ++c) {
         uint32_t* pk = &pkk[HS ? 0 : (c & 1) * 16];
-        exp_chunk<POLYP, !MMA_ROWSUM, F16>(sv[c], mb, pk, s0, s1, s2, s3);
+        exp_chunk<POLYP, !MMA_ROWSUM, F16, LIDM_ATTN_TRUNC != 0>(sv[c], mb, pk, s0, s1, s2, s3);
         if (HS) {
           // half split: 16 columns (32 keys) per store keeps the packed pairs out of the register budget of 96
           if (c == 0 && n > 0) {
