@@ -141,3 +141,23 @@ def test_backproject_edges_and_full_size(ops):
     m = mask.bool().cpu()
     assert torch.equal(m, (depth > 1.0) & (depth < 56.0))
     assert float(((norm - depth)[m]).abs().max()) < 1e-4
+
+
+def test_attention_reference_value_margin(ops):
+    """The bf16 softmax takes its running reference over every fourth column pair (attention.cu: sub-sampled maximum).  Any
+    reference is exact as long as 2^(s - m) stays inside the fp32 / bf16 exponent range, i.e. while no score lies more than
+    ~85 nats above the sampled maximum.  Plant outliers in UNSAMPLED key columns (2..7 of every 8) far above everything else -
+    up to 60 nats, far outside anything a softmax over real logits produces - and compare with the fp32 reference."""
+    B, heads, T, d = 1, 2, 512, 32
+    g = torch.Generator().manual_seed(5)
+    qkv = torch.randn(B, heads * 3 * d, T, generator=g) * 0.5
+    v = qkv.view(B, heads, 3, d, T)
+    for head, (key, gap) in enumerate(((133, 30.0), (390, 60.0))):          # 133 % 8 = 5, 390 % 8 = 6: never sampled
+        q_dir = torch.randn(d, generator=g)
+        q_dir /= q_dir.norm()
+        v[0, head, 0] = q_dir[:, None] * 4.0 + 0.05 * torch.randn(d, T, generator=g)      # every query points along q_dir
+        v[0, head, 1, :, key] = q_dir * gap * d ** 0.5 / 4.0                                  # q . k / sqrt(d) ~ gap for that key
+    y = ops.qkv_attention_legacy(qkv.cuda(), heads)
+    ref = R.qkv_attention_legacy(qkv, heads)
+    assert bool(torch.isfinite(y).all())
+    assert rel(y, ref) < 1e-2
