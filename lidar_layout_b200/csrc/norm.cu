@@ -187,6 +187,8 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, int H, int W, int xh
 // element instead of 6) in a single launch.  Reductions run in a fixed order (per-thread partials -> fixed lane
 // assignment -> xor-shuffle tree): bit-reproducible and, one sample per CTA, independent of the batch size.
 // gn_apply with the statistics reduced from the producers' granule partials (View::gst) instead of a stats pass.
+constexpr int GN_GST_STAGE_MAX = 2048;   // float2 partials staged in shared memory (16 KB)
+
 template <bool F16>
 __global__ void gn_apply_gst_kernel(const bf16* __restrict__ x, int H, int W, int xhl, int xWp, int xld, bf16* __restrict__ y,
                                     int yhl, int yhr, int yWp, int yld, int C, int cpg, int groups,
@@ -218,20 +220,36 @@ __global__ void gn_apply_gst_kernel(const bf16* __restrict__ x, int H, int W, in
     u0 = __ldg(addr(pix)); u1 = __ldg(addr(pix + pstride)); u2 = __ldg(addr(pix + 2 * pstride));
     u3 = __ldg(addr(pix + 3 * pstride));
   }
+  // statistics prologue: the granule partials of this sample (gst_slots x groups x gpg pairs) are staged in shared memory by
+  // ALL threads in one round of loads (32 threads walking 16 slots four loads at a time cost 3-4 dependent L2 round trips per
+  // launch, a quarter of a small launch); one thread per group then sums them in the same slot-major order as before, so the
+  // statistics keep their bits
+  const int row2 = gst_ld >> 1;
+  const int per_slot = groups * gpg;                 // float2 partials per slot
+  const int n_part = gst_slots * per_slot;
+  float2* stage = reinterpret_cast<float2*>(sh + 2 * groups);
+  const bool staged = n_part <= GN_GST_STAGE_MAX;
+  const float2* pb = reinterpret_cast<const float2*>(gst + (size_t)b * gst_slots * gst_ld);
+  if (staged) {
+    for (int i = threadIdx.x; i < n_part; i += blockDim.x) {
+      const int sl = i / per_slot, k = i - sl * per_slot;
+      stage[i] = __ldg(pb + (size_t)sl * row2 + k);
+    }
+    __syncthreads();
+  }
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     float s = 0.f, q = 0.f;
-    const float2* pp = reinterpret_cast<const float2*>(gst + (size_t)b * gst_slots * gst_ld) + (size_t)g * gpg;
-    const int row2 = gst_ld >> 1;
+    // order of the sums (unchanged since the first version, the statistics are part of the bit-reproducibility contract):
+    // blocks of four slots, inside a block granule-major, then the slots of the block; leftover slots one by one
+    auto part = [&](int sl, int k) {
+      return staged ? stage[sl * per_slot + g * gpg + k] : __ldg(pb + (size_t)sl * row2 + (size_t)g * gpg + k);
+    };
     int sl = 0;
-    for (; sl + 4 <= gst_slots; sl += 4) {          // 4 slots' loads in flight; summed in slot order
-      for (int k = 0; k < gpg; ++k) {
-        const float2 a0 = __ldg(pp + (size_t)sl * row2 + k), a1 = __ldg(pp + (size_t)(sl + 1) * row2 + k),
-                     a2 = __ldg(pp + (size_t)(sl + 2) * row2 + k), a3 = __ldg(pp + (size_t)(sl + 3) * row2 + k);
-        s += a0.x; q += a0.y; s += a1.x; q += a1.y; s += a2.x; q += a2.y; s += a3.x; q += a3.y;
-      }
-    }
+    for (; sl + 4 <= gst_slots; sl += 4)
+      for (int k = 0; k < gpg; ++k)
+        for (int j = 0; j < 4; ++j) { const float2 a = part(sl + j, k); s += a.x; q += a.y; }
     for (; sl < gst_slots; ++sl)
-      for (int k = 0; k < gpg; ++k) { const float2 a = __ldg(pp + (size_t)sl * row2 + k); s += a.x; q += a.y; }
+      for (int k = 0; k < gpg; ++k) { const float2 a = part(sl, k); s += a.x; q += a.y; }
     const float n = (float)HW * (float)cpg;
     const float mean = s / n;
     const float var = fmaxf(q / n - mean * mean, 0.f);
@@ -496,7 +514,7 @@ void launch_groupnorm_from_gstats(const View& x, const View& y, const float* gam
   int& occ = occ_cache[threads / 32 <= 32 ? threads / 32 : 0];
   if (occ == 0) {
     LIDM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_apply_gst_kernel<false>, threads,
-                                                                  groups * 2 * sizeof(float)));
+                                                                  groups * 2 * sizeof(float) + GN_GST_STAGE_MAX * sizeof(float2)));
     if (occ < 1) occ = 1;
   }
   const int resident = 148 * occ;
@@ -509,7 +527,7 @@ void launch_groupnorm_from_gstats(const View& x, const View& y, const float* gam
   dim3 grid(nchunks, x.B);
   LIDM_REQUIRE(x.f16 == y.f16, "GroupNorm element formats");
 #define GN_GST(F)                                                                                                     \
-  launch_pdl(gn_apply_gst_kernel<F>, grid, dim3(threads), groups * 2 * sizeof(float), s, x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, \
+  launch_pdl(gn_apply_gst_kernel<F>, grid, dim3(threads), groups * 2 * sizeof(float) + GN_GST_STAGE_MAX * sizeof(float2), s, x.p, x.H, x.W, x.hl, x.Wp(), x.ld, y.p, \
              y.hl, y.hr, y.Wp(), y.ld, C, cpg, groups, gamma, beta, eps, silu ? 1 : 0, (const float*)x.gst, x.gst_ld,       \
              x.gst_slots, pix_per_cta, film, film_ld)
   if (x.f16) GN_GST(true);
