@@ -504,6 +504,128 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
+def run_ae_arm(args):
+    """BASELINE config 4: first-stage autoencoder throughput - VQModel encode (Encoder -> quant_conv) + decode
+    (quantise -> post_quant_conv -> Decoder) of 64x1024 range images, `--batch` images per GPU and step (default 64), inputs
+    clip(N(0, 0.5), -1, 1).  Same line format as the headline: `value` with the images resident in HBM, `e2e` through the
+    reference-facing calls (encode_first_stage / decode_first_stage) with pinned host buffers in and out."""
+    import torch
+    rank, world, local = dist_env()
+    assert torch.cuda.is_available(), "bench.py --workload ae needs a B200"
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import lidar_layout_b200 as L
+    from lidar_layout_b200 import _lib, config as C
+    from lidar_layout_b200.weights import random_encoder_state_dict, random_state_dict
+    cfg = C.kitti_uncond()
+    B = args.batch
+    model = L.LatentDiffusion(cfg, device=dev, use_ema=False, precision=args.precision, ae_precision=args.ae_precision)
+    sd = {**random_state_dict(cfg, 0), **random_encoder_state_dict(cfg, 0)}
+    model.load_state_dict(sd)
+    cfg = model.cfg
+    eng = model.engine
+    H, W = cfg.dataset.size
+    g = torch.Generator().manual_seed(1000 + rank)
+    x_host = (torch.randn((B, 1, H, W), generator=g) * 0.5).clamp_(-1, 1).pin_memory()
+    x_dev = x_host.to(dev)
+    out_host = torch.empty((B, 1, H, W), dtype=torch.float32).pin_memory()
+
+    def device_step():
+        return eng.vq_decode(eng.vq_encode(x_dev))
+
+    def e2e_step():
+        x = x_host.to(dev, non_blocking=True)
+        rec = model.decode_first_stage(model.encode_first_stage(x))
+        out_host.copy_(rec, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    steps = max(args.steps, 1) * 10          # one step is ~40 ms: time ten per requested step
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = _lib.launch_count()
+    ms = timed(device_step, steps)
+    launches = _lib.launch_count() - l0
+    clk = clocks.stop() if rank == 0 else {}
+    value = B * world * steps / (ms / 1000.0)
+    e2e_step()
+    ms_e2e = timed(e2e_step, steps)
+    roof = cpu = None
+    if rank == 0:
+        torch.cuda.synchronize()
+        _lib.profile_begin()
+        z = eng.vq_encode(x_dev)
+        prof_enc = _lib.profile_end()
+        _lib.profile_begin()
+        eng.vq_decode(z)
+        prof_dec = _lib.profile_end()
+        peaks = measured_peaks()
+        gm = {k: prof_enc["conv_gemm"][k] + prof_dec["conv_gemm"][k] for k in ("flops", "ms", "launches")}
+        gn = {k: prof_enc["groupnorm"][k] + prof_dec["groupnorm"][k] for k in ("bytes", "ms")}
+        ach = gm["flops"] / (gm["ms"] * 1e-3) / 1e12 if gm["ms"] > 0 else 0.0
+        tot = sum(v["ms"] for v in prof_enc.values()) + sum(v["ms"] for v in prof_dec.values())
+        roof = {"bound": "tensor", "kernel": "conv_gemm_kernel (all encoder + decoder launches of one step)", "achieved": ach,
+                "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"],
+                "peak_source": peaks["source"] + " (sustained)", "traffic": None, "launches": gm["launches"],
+                "avg_launch_ms": gm["ms"] / max(gm["launches"], 1),
+                "share_of_step": {"conv_gemm": gm["ms"] / tot, "groupnorm": gn["ms"] / tot},
+                "groupnorm_GBps": gn["bytes"] / (gn["ms"] * 1e-3) / 1e9 if gn["ms"] > 0 else None,
+                "encode_ms": sum(v["ms"] for v in prof_enc.values()), "decode_ms": sum(v["ms"] for v in prof_dec.values()),
+                "note": "92.6 + 119.1 GFLOP per image (SURVEY section 8d); the 64 / 128-channel full-resolution levels are HBM-bound"}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import torch_ref as R
+            threads = os.cpu_count() or 1
+            torch.set_num_threads(threads)
+            xs = x_host[:1].clone()
+            with torch.no_grad():
+                t0 = time.perf_counter()
+                zz = R.encode_first_stage(sd, cfg, xs)
+                R.decode_first_stage(sd, cfg, zz)
+                dt = time.perf_counter() - t0
+            cpu = {"value": 1.0 / dt, "unit": "images/s", "cores": threads, "kind": "port",
+                   "sample": "B=1: one encode + quantised decode (oracle port, torch fp32)"}
+        line = {
+            "metric": "images/sec first-stage VQ autoencoder 64x1024 (encode + quantised decode)", "value": value, "unit": "images/s",
+            "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_NAMES[(cfg.precision, cfg.ae_precision_resolved)].split(" U-Net + ")[-1],
+            "data": "synthetic",
+            "config": {"workload": "first-stage autoencoder f_c2_p4 (models/first_stage_models/kitti/f_c2_p4, random-init), "
+                                   "VQModel encode + decode of 64x1024 range images (BASELINE config 4)",
+                       "batch_per_gpu": B, "global_batch": B * world,
+                       "l2": "activations of one step (GBs) >> 126 MB L2", "parallelism": f"batch-sharded x{world}, no collective"},
+            "e2e": {"value": B * world * steps / (ms_e2e / 1000.0), "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4,
+                    "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": ms_e2e / steps},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -512,7 +634,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="samples per GPU per step (BASELINE config 2: 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="uncond", choices=sorted(WORKLOADS),
+    ap.add_argument("--workload", default="uncond", choices=sorted(WORKLOADS) + ["ae"],
                     help="uncond = the headline (BASELINE config 2); cam2lidar = BASELINE config 3(A), reported beside it")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "fp16"],
                     help="U-Net numeric mode: bf16 = headline tensor-core path; fp32 = precise operand-split mode; fp16 = IEEE half")
@@ -523,6 +645,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "ae":
+        run_ae_arm(args)
     else:
         run_gpu_arm(args)
 
