@@ -258,6 +258,15 @@ int lidm_op_circular_conv2d(const float* x, int32_t B, int32_t Cin, int32_t H, i
                             int32_t pad_t, int32_t pad_b, int32_t stride, const float* residual, float* out,
                             void* stream);
 
+/* The same convolution as the MODEL runs it (stride 1, Cin and Cout multiples of 64, H*W a multiple of 128): the output is
+ * stored channels-last bf16 and the epilogue also writes the GroupNorm granule statistics of the stored values, both of which
+ * this entry point hands back (out: the stored values widened to fp32 NCHW; gst_out: (B, H*W/128, Cout/8, 2) partial sums and
+ * sums of squares, or NULL).  residual enters as res_scale * residual.  halo_kernel = 1 forces the halo-tile kernel
+ * (gemm_halo.cu; error if the shape is not one it takes), 0 the streamed implicit-GEMM kernel: the two must agree bit for bit. */
+int lidm_op_conv2d_stored(const float* x, int32_t B, int32_t Cin, int32_t H, int32_t W, const float* weight, const float* bias,
+                          int32_t Cout, int32_t kh, int32_t kw, int32_t pad_l, int32_t pad_r, int32_t pad_t, const float* residual,
+                          float res_scale, int32_t halo_kernel, float* out, float* gst_out, void* stream);
+
 /* GroupNorm32 (+SiLU) (lidm/modules/basic.py:339-341, openaimodel.py:205-207). */
 int lidm_op_groupnorm(const float* x, int32_t B, int32_t C, int32_t H, int32_t W, const float* gamma,
                       const float* beta, float eps, int32_t groups, int32_t silu, float* out, void* stream);

@@ -50,7 +50,7 @@ EXPORTS = [
     "lidm_unet_forward", "lidm_unet_forward_cond", "lidm_ddim_step", "lidm_ddpm_step", "lidm_ddim_sample", "lidm_ddim_sample_cond",
     "lidm_cfg_combine", "lidm_layout_set_cond", "lidm_layout_encode", "lidm_vq_decode", "lidm_vq_encode", "lidm_vq_quantize", "lidm_image_shape",
     "lidm_backproject", "lidm_to_uint8_image", "lidm_compact_points", "lidm_chamfer_nn", "lidm_chamfer_nn_ex",
-    "lidm_chamfer_backward", "lidm_emd_forward", "lidm_emd_backward", "lidm_op_circular_conv2d", "lidm_op_groupnorm", "lidm_op_qkv_attention_legacy",
+    "lidm_chamfer_backward", "lidm_emd_forward", "lidm_emd_backward", "lidm_op_circular_conv2d", "lidm_op_conv2d_stored", "lidm_op_groupnorm", "lidm_op_qkv_attention_legacy",
     "lidm_launch_count", "lidm_profile_begin", "lidm_profile_end",
 ]
 
@@ -108,6 +108,9 @@ def load() -> ctypes.CDLL:
     lib.lidm_op_circular_conv2d.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32,
                                             c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                             c_void_p, c_void_p]
+    lib.lidm_op_conv2d_stored.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32,
+                                          c_int32, c_int32, c_int32, c_int32, c_void_p, c_float, c_int32, c_void_p, c_void_p,
+                                          c_void_p]
     lib.lidm_op_groupnorm.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_float,
                                       c_int32, c_int32, c_void_p, c_void_p]
     lib.lidm_op_qkv_attention_legacy.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]

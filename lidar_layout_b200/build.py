@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "liblidm_b200.so")
-SOURCES = ["tma.cu", "gemm_conv.cu", "norm.cu", "attention.cu", "elementwise.cu", "transformer.cu", "postprocess.cu", "eval_kernels.cu", "precise.cu", "layout.cu",
+SOURCES = ["tma.cu", "gemm_conv.cu", "gemm_halo.cu", "norm.cu", "attention.cu", "elementwise.cu", "transformer.cu", "postprocess.cu", "eval_kernels.cu", "precise.cu", "layout.cu",
            "engine.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]

@@ -164,6 +164,10 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wt, int 
 
 // True when launch_conv_gemm will take the TMA-store epilogue for this output, the one that can also emit the
 // GroupNorm granule statistics of View::gst.
+// halo-tile variant for 64 -> 64 channel convolutions (gemm_halo.cu); launch_conv_gemm dispatches to it
+bool conv_halo64_applicable(const View& a, const ConvTaps& taps, const GemmB& wtb, int N, const GemmEpilogue& ep);
+void launch_conv_halo64(const View& a, const ConvTaps& taps, const GemmB& wtb, int N, const GemmEpilogue& ep, cudaStream_t stream);
+void conv_halo64_override(int on);   // -1: LIDM_GEMM_HALO decides (default); 0 / 1: off / on (parity tests of the two paths)
 bool conv_gemm_emits_gstats(const GemmEpilogue& ep, int n_alloc);
 
 // ---- normalisation (norm.cu) -----------------------------------------------------------------------------

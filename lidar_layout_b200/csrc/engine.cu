@@ -3527,6 +3527,46 @@ int lidm_op_circular_conv2d(const float* x, int32_t B, int32_t Cin, int32_t H, i
   });
 }
 
+int lidm_op_conv2d_stored(const float* x, int32_t B, int32_t Cin, int32_t H, int32_t W, const float* weight, const float* bias,
+                          int32_t Cout, int32_t kh, int32_t kw, int32_t pad_l, int32_t pad_r, int32_t pad_t, const float* residual,
+                          float res_scale, int32_t halo_kernel, float* out, float* gst_out, void* stream) {
+  return guarded(nullptr, [&] {
+    LIDM_REQUIRE(x && weight && out && B > 0 && Cin % 64 == 0 && Cout % 64 == 0 && (H * W) % 128 == 0, "bad argument");
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    TmpBufs tmp;
+    const int n_alloc = round_n_alloc(Cout), K = kh * kw * Cin;
+    bf16* wp = tmp.get<bf16>((size_t)n_alloc * K);
+    launch_pack_conv_weight(weight, Cout, Cin, kh, kw, n_alloc, K, nullptr, nullptr, 1.f, 0, wp, s);
+    GemmB wb; wb.p = wp; wb.n_alloc = n_alloc; wb.ld = K;
+    GemmEpilogue ep;
+    ep.bias = bias;
+    View o; o.B = B; o.H = H; o.W = W; o.C = Cout; o.ld = Cout;
+    o.p = tmp.get<bf16>((size_t)B * H * W * Cout);
+    o.gst_ld = (Cout / 8) * 2; o.gst_slots = H * W / 128;
+    o.gst = o.gst_base = tmp.get<float>((size_t)B * o.gst_slots * o.gst_ld);
+    ep.out = o;
+    if (residual != nullptr) {
+      View rv = o; rv.gst = rv.gst_base = nullptr;
+      rv.p = tmp.get<bf16>((size_t)B * H * W * Cout);
+      launch_f32_to_nhwc_bf16(residual, B, Cout, H * W, rv, s);
+      ep.residual = rv; ep.res_scale = res_scale;
+    }
+    View a; a.B = B; a.H = H; a.W = W; a.C = Cin; a.ld = Cin; a.hl = pad_l; a.hr = pad_r;
+    a.p = tmp.get<bf16>((size_t)B * H * a.Wp() * Cin);
+    launch_f32_to_nhwc_bf16(x, B, Cin, H * W, a, s);
+    const ConvTaps taps = taps_rect(kh, kw, pad_l, pad_t);
+    conv_halo64_override(halo_kernel ? 1 : 0);
+    const bool ok = !halo_kernel || conv_halo64_applicable(a, taps, wb, Cout, ep);
+    if (ok) launch_conv_gemm(a, taps, wb, Cout, ep, s);
+    conv_halo64_override(-1);
+    LIDM_REQUIRE(ok, "halo-tile kernel requested for a shape it does not take");
+    launch_nhwc_bf16_to_f32_nchw(o, out, s);
+    if (gst_out != nullptr)
+      LIDM_CUDA_CHECK(cudaMemcpyAsync(gst_out, o.gst, (size_t)B * o.gst_slots * o.gst_ld * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    LIDM_CUDA_CHECK(cudaStreamSynchronize(s));
+  });
+}
+
 int lidm_op_groupnorm(const float* x, int32_t B, int32_t C, int32_t H, int32_t W, const float* gamma,
                       const float* beta, float eps, int32_t groups, int32_t silu, float* out, void* stream) {
   return guarded(nullptr, [&] {

@@ -920,6 +920,10 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
                "GEMM operands and 2-byte outputs must share one element format (bf16 or fp16)");
   const int nseg = wtb.nseg;
   LIDM_REQUIRE(nseg >= 1 && nseg <= 3 && (nseg != 3 || a.lo_off > 0), "operand-split segments");
+  if (conv_halo64_applicable(a, taps, wtb, N, ep)) {      // 64 -> 64 channels: one halo box per tile, resident weights
+    launch_conv_halo64(a, taps, wtb, N, ep, stream);
+    return;
+  }
   const int W = a.W, H = a.H;
   LIDM_REQUIRE((W <= BM && BM % W == 0) || (W % BM == 0), "W must divide or be a multiple of 128");
   const int Wbox = W < BM ? W : BM;

@@ -31,6 +31,26 @@ def circular_conv2d(x, weight, bias=None, padding: Optional[Sequence[int]] = Non
     return out
 
 
+def conv2d_stored(x, weight, bias=None, padding=(1, 1, 1), residual=None, res_scale=1.0, halo_kernel=False):
+    """The convolution as the model runs it: bf16 channels-last stored output plus the GroupNorm granule statistics the epilogue
+    writes.  padding = (left, right, top); returns (out fp32 NCHW, gst (B, H*W/128, Cout/8, 2)).  halo_kernel picks the halo-tile
+    kernel (csrc/gemm_halo.cu) instead of the streamed implicit GEMM; both must produce the same bits."""
+    x, weight = _f32c(x, "x"), _f32c(weight, "weight")
+    B, Cin, H, W = x.shape
+    Cout, _, kh, kw = weight.shape
+    pl, pr, pt = padding
+    out = torch.empty((B, Cout, H, W), dtype=torch.float32, device=x.device)
+    gst = torch.empty((B, H * W // 128, Cout // 8, 2), dtype=torch.float32, device=x.device)
+    b = _f32c(bias, "bias") if bias is not None else None
+    r = _f32c(residual, "residual") if residual is not None else None
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.lidm_op_conv2d_stored(x.data_ptr(), B, Cin, H, W, weight.data_ptr(), b.data_ptr() if b is not None else None,
+                                             Cout, kh, kw, pl, pr, pt, r.data_ptr() if r is not None else None, float(res_scale),
+                                             int(halo_kernel), out.data_ptr(), gst.data_ptr(), _stream_ptr(x.device)))
+    return out, gst
+
+
 def group_norm(x, gamma, beta, eps=1e-5, groups=32, silu=False):
     """GroupNorm32 (+ SiLU) (reference lidm/modules/basic.py:339-341)."""
     x, gamma, beta = _f32c(x, "x"), _f32c(gamma, "gamma"), _f32c(beta, "beta")

@@ -37,6 +37,9 @@ CONV_CASES = [
     (1, 128, 8, 256, 128, 1, 5, (2, 2, 0, 0), 1),               # decoder Upsample conv (1,5)
     (1, 64, 8, 256, 1, 1, 4, (1, 2, 0, 0), 1),                  # decoder conv_out
     (1, 128, 8, 256, 64, 1, 4, (1, 2, 0, 0), 1),                # Cout = 64 tile
+    (2, 64, 8, 256, 64, 3, 3, (1, 1, 1, 1), 1),                 # 64 -> 64 ring conv (R2DM level 0): halo-tile kernel
+    (1, 64, 4, 512, 64, 1, 4, (1, 2, 0, 0), 1),                 # 64 -> 64 (1,4) (decoder full resolution): halo-tile kernel
+    (1, 64, 4, 128, 64, 1, 5, (2, 2, 0, 0), 1),                 # 64 -> 64 (1,5), one tile per row
 ]
 
 
@@ -161,3 +164,38 @@ def test_attention_reference_value_margin(ops):
     ref = R.qkv_attention_legacy(qkv, heads)
     assert bool(torch.isfinite(y).all())
     assert rel(y, ref) < 1e-2
+
+
+HALO_CASES = [
+    # B, H, W, kh, kw, pad(l, r, t), residual scale (None: no residual)
+    (2, 8, 256, 3, 3, (1, 1, 1), None),          # R2DM level-0 ring conv, small
+    (2, 64, 1024, 3, 3, (1, 1, 1), 0.70710678),  # the same at 64 x 1024: ~7 tiles per CTA, every barrier phase several times
+    (1, 4, 512, 1, 4, (1, 2, 0), 1.0),           # decoder curve-wise (1,4), asymmetric circular pad
+    (1, 4, 128, 1, 5, (2, 2, 0), None),          # decoder Upsample conv (1,5): one tile per row
+    (3, 16, 512, 3, 3, (1, 1, 1), 1.0),
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES)
+def test_halo_tile_conv_matches_streamed_kernel(ops, case):
+    """64 -> 64 channel convolutions take the halo-tile kernel (gemm_halo.cu) in the models.  Run the conv as the models do
+    (stored bf16 output + GroupNorm granule statistics) on both kernels: same K order per output element and same statistics
+    order, so stored values and statistics must be the same bits; and the stored values sit within bf16 rounding of the oracle."""
+    B, H, W, kh, kw, pad, rs = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    x = torch.randn(B, 64, H, W, generator=g)
+    w = torch.randn(64, 64, kh, kw, generator=g) / (64 * kh * kw) ** 0.5
+    b = torch.randn(64, generator=g)
+    res = torch.randn(B, 64, H, W, generator=g) if rs is not None else None
+    kw_ = dict(padding=pad, residual=res.cuda() if res is not None else None, res_scale=rs if rs is not None else 1.0)
+    y1, g1 = ops.conv2d_stored(x.cuda(), w.cuda(), b.cuda(), halo_kernel=True, **kw_)
+    y0, g0 = ops.conv2d_stored(x.cuda(), w.cuda(), b.cuda(), halo_kernel=False, **kw_)
+    ref = R.circular_conv2d(x.bfloat16().float(), w.bfloat16().float(), b, (pad[0], pad[1], pad[2], kh - 1 - pad[2]))
+    if res is not None:
+        ref = ref + rs * res.bfloat16().float()
+    assert rel(y0, ref) < 3e-3 and rel(y1, ref) < 3e-3
+    assert torch.equal(y1, y0)
+    assert torch.equal(g1, g0)
+    # the statistics are those of the stored values: summed over the tiles they give the per-granule sums
+    s = y1.reshape(B, 8, 8, H * W).sum(dim=(2, 3))
+    assert torch.allclose(g1[..., 0].sum(dim=1), s, rtol=1e-3, atol=1e-1)
