@@ -88,7 +88,7 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
 }
 
 // ---- TMA maps (cuTensorMapEncodeTiled through the runtime's driver entry point; no -lcuda link) -------
-CUtensorMap make_tma_act(const View& v, int box_c, int box_w, int box_h, int swizzle_bytes, int box_b = 1);
+CUtensorMap make_tma_act(const View& v, int box_c, int box_w, int box_h, int swizzle_bytes, int box_b = 1, int sx = 1, int sy = 1);
 CUtensorMap make_tma_3d(const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                         uint64_t stride2_bytes, uint32_t b0, uint32_t b1, int swizzle_bytes);
 
@@ -101,6 +101,9 @@ struct ConvTaps {
   // zero padding on W as well as H (plain nn.Conv2d(padding=1) of the layout U-Net, object_cross_unet.py): the operand is
   // a halo-free tensor and every out-of-range column comes from TMA's out-of-bounds zero fill
   bool zero_w = false;
+  // strided convolution: output pixel (h, w) reads input (h * sy + dy, w * sx + dx); the operand view is the INPUT tensor
+  // (a.H = H_out * sy, a.W = W_out * sx) and arrives through TMA traversal strides - no im2col
+  int sx = 1, sy = 1;
 };
 
 // fp32 channels-last tensor (no halo): the residual stream of the precise mode

@@ -545,8 +545,9 @@ struct Builder {
     const int N = w.cout;
     GemmEpilogue ep = ep_in;
     prep_gst(ep, N, w.n_alloc);
-    op([=](cudaStream_t s) { launch_conv_gemm(a, taps, b, N, ep, s); }, PROF_GEMM, gemm_flops(a, taps.n, N) * w.nseg, 0,
-       gemm_label(a, taps.n * w.nseg, N));
+    op([=](cudaStream_t s) { launch_conv_gemm(a, taps, b, N, ep, s); }, PROF_GEMM,
+       gemm_flops(a, taps.n, N) * w.nseg / (taps.sx * taps.sy), 0,
+       gemm_label(a, taps.n * w.nseg, N) + (taps.sx * taps.sy > 1 ? " /" + std::to_string(taps.sy) + "x" + std::to_string(taps.sx) : ""));
   }
 
   // 1x1 GEMM + residual: through the identity-extended weights when they exist (the residual is a second A operand,
@@ -1212,34 +1213,52 @@ struct Builder {
     release(bh);
   }
 
-  // Downsample.forward (openaimodel.py:159-161): circular 3x3 stride 2 via channels-last im2col + GEMM
-  void down(const ConvW& c, const View& x, const View& dst) {
-    const int B = x.B, Ho = x.H / 2, Wo = x.W / 2;
-    Buf bc;
-    bf16* col = raw<bf16>((size_t)B * Ho * Wo * 9 * x.C, &bc);
-    op([=](cudaStream_t s) { launch_im2col_nhwc(x, 3, 3, 2, 1, 1, Ho, Wo, col, s); });
-    View a = mat(col, B, Ho, Wo, 9 * x.C, 9 * x.C);
+  // Strided circular convolution (kernel (kh,kw), stride (sh,sw), circular pad pl on the left of W, zero pad pt on top of H;
+  // whatever the kernel reaches beyond the right / bottom edge is the circular wrap / zero as well).  Implicit GEMM: the
+  // operand is the input tensor itself, read through TMA traversal strides (tap (ky,kx) of output pixel (h,w) = input
+  // (h*sh + ky - pt, w*sw + kx - pl)); the circular wrap columns come from a halo, added by one copy when the producer wrote
+  // none.  Shapes whose output does not tile into 128-pixel boxes fall back to channels-last im2col + GEMM.
+  void conv_strided(const ConvW& c, const View& x, const View& dst, int sh, int sw, int pl, int pt) {
+    static const bool no_implicit = getenv("LIDM_NO_STRIDED_TMA") != nullptr;     // A/B switch
+    const int B = x.B, Ho = dst.H, Wo = dst.W, kh = c.kh, kw = c.kw;
+    const int need_hr = std::max(0, (Wo - 1) * sw + kw - 1 - pl - (x.W - 1));
+    const bool tiles = (Wo <= 128 && 128 % Wo == 0 && Ho % (128 / Wo) == 0) || Wo % 128 == 0;
+    const bool implicit = !no_implicit && !precise && c.nseg == 1 && x.C % 64 == 0 && x.W == Wo * sw && x.H == Ho * sh && tiles && x.wpitch == 0 &&
+                          x.ld == x.C && std::min(Wo, 128) * sw <= 256 && (128 / std::min(Wo, 128)) * sh <= 256;
     GemmEpilogue ep;
     ep.bias = c.bias;
     ep.out = dst;
+    if (implicit) {
+      View xin = x;
+      Buf bh;
+      const bool need_copy = x.hl < pl || x.hr < need_hr;
+      if (need_copy) {
+        xin = act(B, x.H, x.W, x.C, pl, need_hr, &bh);
+        const View xh = xin;
+        op([=](cudaStream_t s) { launch_copy_with_halo(x, xh, s); });
+      }
+      ConvTaps taps = taps_rect(kh, kw, pl, pt);
+      taps.sx = sw; taps.sy = sh;
+      gemm(xin, taps, c, ep);
+      if (need_copy) release(bh);
+      return;
+    }
+    const int ntap = kh * kw;
+    Buf bc;
+    bf16* col = raw<bf16>((size_t)B * Ho * Wo * ntap * x.C, &bc);
+    op([=](cudaStream_t s) { launch_im2col_nhwc(x, kh, kw, sh, pl, pt, Ho, Wo, col, s, sw); });
+    View a = mat(col, B, Ho, Wo, ntap * x.C, ntap * x.C);
     gemm(a, taps_1x1(), c, ep);
     release(bc);
   }
 
+  // Downsample.forward (openaimodel.py:159-161): circular 3x3 stride 2, pad 1
+  void down(const ConvW& c, const View& x, const View& dst) { conv_strided(c, x, dst, 2, 2, 1, 1); }
+
   // Downsample.forward of the first-stage encoder (model_lidm.py:68-83): CircularConv2d kernel (kh,kw), stride (sh,sw),
-  // circular pad (pl, .) on W / zero pad (pt, .) on H — channels-last im2col + GEMM
+  // circular pad (pl, .) on W / zero pad (pt, .) on H
   void down_strided(const ConvW& c, const View& x, const View& dst, int sh, int sw, int pl, int pt) {
-    const int B = x.B, Ho = dst.H, Wo = dst.W, taps = c.kh * c.kw;
-    Buf bc;
-    bf16* col = raw<bf16>((size_t)B * Ho * Wo * taps * x.C, &bc);
-    const int kh = c.kh, kw = c.kw;
-    op([=](cudaStream_t s) { launch_im2col_nhwc(x, kh, kw, sh, pl, pt, Ho, Wo, col, s, sw); });
-    View a = mat(col, B, Ho, Wo, taps * x.C, taps * x.C);
-    GemmEpilogue ep;
-    ep.bias = c.bias;
-    ep.out = dst;
-    gemm(a, taps_1x1(), c, ep);
-    release(bc);
+    conv_strided(c, x, dst, sh, sw, pl, pt);
   }
 
   // Upsample.forward (openaimodel.py:108-118), nearest x2 followed by the circular 3x3 conv, without materialising
@@ -3488,7 +3507,9 @@ int lidm_op_circular_conv2d(const float* x, int32_t B, int32_t Cin, int32_t H, i
     const int Ho = (H + pad_t + pad_b - kh) / stride + 1, Wo = (W + pad_l + pad_r - kw) / stride + 1;
     TmpBufs tmp;
     const int n_alloc = round_n_alloc(Cout);
-    const bool implicit = stride == 1 && Cin % 64 == 0 && Ho == H && Wo == W;
+    const bool strided_ok = stride > 1 && H % stride == 0 && W % stride == 0 && Ho == H / stride && Wo == W / stride &&
+                            ((Wo <= 128 && 128 % Wo == 0 && Ho % (128 / Wo) == 0) || Wo % 128 == 0) && std::min(Wo, 128) * stride <= 256;
+    const bool implicit = Cin % 64 == 0 && ((stride == 1 && Ho == H && Wo == W) || strided_ok);
     const int K = kh * kw * Cin;
     const int k_alloc = implicit ? K : (K + 63) / 64 * 64;
     bf16* wp = tmp.get<bf16>((size_t)n_alloc * k_alloc);
@@ -3508,7 +3529,9 @@ int lidm_op_circular_conv2d(const float* x, int32_t B, int32_t Cin, int32_t H, i
       View a; a.B = B; a.H = H; a.W = W; a.C = Cin; a.ld = Cin; a.hl = pad_l; a.hr = pad_r;
       a.p = tmp.get<bf16>((size_t)B * H * a.Wp() * Cin);
       launch_f32_to_nhwc_bf16(x, B, Cin, H * W, a, s);
-      launch_conv_gemm(a, taps_rect(kh, kw, pad_l, pad_t), wb, Cout, ep, s);
+      ConvTaps taps = taps_rect(kh, kw, pad_l, pad_t);
+      taps.sx = taps.sy = stride;
+      launch_conv_gemm(a, taps, wb, Cout, ep, s);
     } else {
       bf16* col = tmp.get<bf16>((size_t)B * Ho * Wo * k_alloc);
       if (Cin % 8 == 0 && k_alloc == K) {

@@ -49,6 +49,7 @@ struct GemmKernelParams {
   int bbox;                  // samples per 128-row tile (> 1 when one sample has fewer than 128 pixels), B = batch size
   int B;
   int hl;
+  int sx, sy;                // convolution stride (input pixel = output pixel * stride + tap offset)
   int ntaps;                 // virtual taps = spatial taps x operand-split segments (<= 27)
   int8_t dx[27], dy[27];
   int a_coff[27];            // channel offset of the A plane read by this virtual tap (hi / lo plane)
@@ -256,7 +257,7 @@ conv_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int th = r / p.tiles_w;
         const int h0 = th * p.Hbox, w0 = (r - th * p.tiles_w) * p.Wbox;
         for (int tap = 0; tap < p.ntaps; ++tap) {
-          const int x = w0 + p.hl + p.dx[tap], y = h0 + p.dy[tap];
+          const int x = w0 * p.sx + p.hl + p.dx[tap], y = h0 * p.sy + p.dy[tap];
           const int acoff = p.a_coff[tap], bkoff = p.b_koff[tap];
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(&empty_bar[s], ph ^ 1);
@@ -924,7 +925,12 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
     launch_conv_halo64(a, taps, wtb, N, ep, stream);
     return;
   }
-  const int W = a.W, H = a.H;
+  const int sx = taps.sx, sy = taps.sy;
+  const bool strided = sx != 1 || sy != 1;
+  LIDM_REQUIRE(sx >= 1 && sy >= 1 && a.W % sx == 0 && a.H % sy == 0, "stride must divide the input");
+  const int W = a.W / sx, H = a.H / sy;      // output pixels (= input pixels unless strided)
+  LIDM_REQUIRE(!strided || (taps.cstep == 0 && !taps.zero_w && nseg == 1 && ep.a2.p == nullptr && !wt_batched && H * W >= BM),
+               "strided convolution: plain circular conv, one sample per tile");
   LIDM_REQUIRE((W <= BM && BM % W == 0) || (W % BM == 0), "W must divide or be a multiple of 128");
   const int Wbox = W < BM ? W : BM;
   int Hbox = BM / Wbox;
@@ -939,7 +945,7 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
   }
   LIDM_REQUIRE(H % Hbox == 0, "H must be a multiple of 128/W");
   for (int t = 0; t < taps.n && taps.cstep == 0 && !taps.zero_w; ++t) {
-    LIDM_REQUIRE(-taps.dx[t] <= a.hl && taps.dx[t] <= a.hr, "tap exceeds the materialised halo");
+    LIDM_REQUIRE(-taps.dx[t] <= a.hl && (W - 1) * sx + taps.dx[t] <= a.W - 1 + a.hr, "tap exceeds the materialised halo");
   }
   if (taps.zero_w) LIDM_REQUIRE(a.hl == 0 && a.hr == 0, "zero-padded convolutions read halo-free tensors (TMA fills the border)");
   int BN;
@@ -949,7 +955,7 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
   // 67.1 us resident; 512 -> 1536 @8x64 55.7 -> 67.5 us (twice the tiles at BN = 128, single staging buffer): K = 256 only.
   static const int resb_on = getenv("LIDM_GEMM_RESB") ? atoi(getenv("LIDM_GEMM_RESB")) : 256;
   int resk = 0;
-  if (resb_on && taps.n == 1 && nseg == 1 && ep.a2.p == nullptr && !wt_batched && bbox == 1 && a.C == 256 && ep.residual.p == nullptr &&
+  if (resb_on && !strided && taps.n == 1 && nseg == 1 && ep.a2.p == nullptr && !wt_batched && bbox == 1 && a.C == 256 && ep.residual.p == nullptr &&
       n_alloc % 128 == 0 && n_alloc / 128 <= 148 && ep.out.p != nullptr && ep.out.hl == 0 && ep.out.hr == 0 && ep.out_t == nullptr &&
       ep.res_f32 == nullptr && ep.out_f32_nhwc == nullptr && ep.out_f32_nchw == nullptr && ep.rowadd == nullptr &&
       (resb_on == 1 || a.C == resb_on))   // (a 512-channel variant, B resident in 128 KB with one staging buffer, measured slower)
@@ -980,6 +986,7 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
   p.tiles_w = W / Wbox;
   p.tiles_per_img = p.tiles_w * (H / Hbox);
   p.Wbox = Wbox; p.Hbox = Hbox; p.hl = a.hl;
+  p.sx = sx; p.sy = sy;
   p.bbox = bbox; p.B = a.B;
   p.ntaps = taps.n * nseg;
   for (int t = 0; t < taps.n; ++t) {
@@ -1016,7 +1023,7 @@ void launch_conv_gemm(const View& a, const ConvTaps& taps, const GemmB& wtb, int
   p.ddim_pred_x0 = ep.ddim_pred_x0; p.ddim_coef = ep.ddim_coef;
 
   uint64_t Ktot = (uint64_t)taps.n * nseg * a.C;
-  CUtensorMap tmA = make_tma_act(a, BK, Wbox, Hbox, 128, bbox);
+  CUtensorMap tmA = make_tma_act(a, BK, Wbox, Hbox, 128, bbox, sx, sy);
   CUtensorMap tmA2 = tmA;
   if (ep.a2.p != nullptr) {
     const View& a2 = ep.a2;

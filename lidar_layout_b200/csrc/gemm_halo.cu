@@ -258,7 +258,7 @@ void conv_halo64_override(int on) { g_halo_override = on; }
 bool conv_halo64_applicable(const View& a, const ConvTaps& taps, const GemmB& wtb, int N, const GemmEpilogue& ep) {
   static const int env_on = getenv("LIDM_GEMM_HALO") ? atoi(getenv("LIDM_GEMM_HALO")) : 1;
   const int on = g_halo_override >= 0 ? g_halo_override : env_on;
-  if (!on || a.C != 64 || N != 64 || wtb.n_alloc != 64 || wtb.nseg != 1 || wtb.batch_stride != 0 || taps.cstep != 0 || taps.n < 2 ||
+  if (!on || a.C != 64 || N != 64 || wtb.n_alloc != 64 || wtb.nseg != 1 || wtb.batch_stride != 0 || taps.cstep != 0 || taps.sx != 1 || taps.sy != 1 || taps.n < 2 ||
       taps.n > HT_MAX_TAPS || a.W % HT_BM != 0 || a.wpitch != 0 || a.lo_off != 0 || a.ld != 64)
     return false;
   if (ep.a2.p != nullptr || ep.rowadd != nullptr || ep.out_t != nullptr || ep.geglu || ep.res_f32 != nullptr ||

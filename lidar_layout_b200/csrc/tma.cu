@@ -37,9 +37,10 @@ CUtensorMapSwizzle swz(int bytes) {
 }
 
 CUtensorMap encode(const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                   const cuuint32_t* box, int swizzle_bytes) {
+                   const cuuint32_t* box, int swizzle_bytes, const cuuint32_t* elem_strides = nullptr) {
   CUtensorMap m;
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < rank && elem_strides != nullptr; ++i) estr[i] = elem_strides[i];
   CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
                            strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz(swizzle_bytes),
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -58,11 +59,15 @@ CUtensorMap encode(const void* base, int rank, const cuuint64_t* dims, const cuu
 }  // namespace
 
 // 4-D map over a channels-last activation view: dims (C, Wp, H, B), box (box_c, box_w, box_h, 1).
-CUtensorMap make_tma_act(const View& v, int box_c, int box_w, int box_h, int swizzle_bytes, int box_b) {
+// sx, sy > 1: traversal strides (a strided convolution's operand): the box still delivers box_w x box_h pixels, taken
+// every sx-th column / sy-th row from the start coordinate (the driver wants boxDim = pixels * stride there).
+CUtensorMap make_tma_act(const View& v, int box_c, int box_w, int box_h, int swizzle_bytes, int box_b, int sx, int sy) {
   cuuint64_t dims[4] = {(cuuint64_t)v.Cphys(), (cuuint64_t)v.Wp(), (cuuint64_t)v.H, (cuuint64_t)v.B};
   cuuint64_t str[3] = {(cuuint64_t)v.ld * 2, (cuuint64_t)v.ld * 2 * v.pitch(), (cuuint64_t)v.ld * 2 * v.pitch() * v.H};
-  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_b};
-  return encode(v.p, 4, dims, str, box, swizzle_bytes);
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)(box_w * sx), (cuuint32_t)(box_h * sy), (cuuint32_t)box_b};
+  cuuint32_t est[4] = {1, (cuuint32_t)sx, (cuuint32_t)sy, 1};
+  LIDM_REQUIRE(sx >= 1 && sy >= 1 && sx <= 8 && sy <= 8 && box_w * sx <= 256 && box_h * sy <= 256, "TMA traversal stride / box");
+  return encode(v.p, 4, dims, str, box, swizzle_bytes, (sx > 1 || sy > 1) ? est : nullptr);
 }
 
 CUtensorMap make_tma_3d(const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,

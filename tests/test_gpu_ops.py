@@ -32,7 +32,9 @@ CONV_CASES = [
     (2, 768, 16, 128, 256, 3, 3, (1, 1, 1, 1), 1),              # concat input
     (2, 8, 16, 128, 256, 3, 3, (1, 1, 1, 1), 1),                # input conv (im2col, K padded)
     (2, 256, 16, 128, 8, 3, 3, (1, 1, 1, 1), 1),                # out conv (N = 8)
-    (2, 256, 16, 128, 256, 3, 3, (1, 1, 1, 1), 2),              # Downsample
+    (2, 256, 16, 128, 256, 3, 3, (1, 1, 1, 1), 2),              # Downsample: strided TMA boxes, 64-pixel rows
+    (2, 512, 8, 64, 512, 3, 3, (1, 1, 1, 1), 2),                # Downsample to 4x32 (4-row tiles)
+    (1, 64, 8, 512, 128, 3, 3, (1, 1, 1, 1), 2),                # stride 2 at 256-pixel output rows (two tiles per row)
     (1, 128, 8, 256, 128, 1, 4, (1, 2, 0, 0), 1),               # decoder curve-wise (1,4), asymmetric pad
     (1, 128, 8, 256, 128, 1, 5, (2, 2, 0, 0), 1),               # decoder Upsample conv (1,5)
     (1, 64, 8, 256, 1, 1, 4, (1, 2, 0, 0), 1),                  # decoder conv_out
