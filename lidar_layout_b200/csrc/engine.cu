@@ -1224,7 +1224,7 @@ struct Builder {
     const int need_hr = std::max(0, (Wo - 1) * sw + kw - 1 - pl - (x.W - 1));
     const bool tiles = (Wo <= 128 && 128 % Wo == 0 && Ho % (128 / Wo) == 0) || Wo % 128 == 0;
     const bool implicit = !no_implicit && !precise && c.nseg == 1 && x.C % 64 == 0 && x.W == Wo * sw && x.H == Ho * sh && tiles && x.wpitch == 0 &&
-                          x.ld == x.C && std::min(Wo, 128) * sw <= 256 && (128 / std::min(Wo, 128)) * sh <= 256;
+                          std::min(Wo, 128) * sw <= 256 && (128 / std::min(Wo, 128)) * sh <= 256;
     GemmEpilogue ep;
     ep.bias = c.bias;
     ep.out = dst;
