@@ -367,12 +367,47 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     for (int it = 0; it < n_my; ++it) {
     int q0, head, b;
     item_coords(it, q0, head, b);
-    float m = 0.f;
+    float m = 0.f, rprev = 0.f;
     float lcur = 0.f;                               // running row sum of this item when it is not taken from the MMA
     for (int j = 0; j < nkv; ++j, ++n) {
       mbar_wait(&s_ready[g], n & 1);
       tcgen05_fence_after();
       uint32_t sv[L::NCH][32];
+      // Streamed tiles (bf16 P, every tile after an item's first, no ragged tail): the exponentials are taken against the
+      // reference m carried over from the earlier tiles, so nothing in the tile waits for its own maximum - the first
+      // 32-column chunk is loaded alone, the other loads fly while its exponentials run, and this tile's (sub-sampled)
+      // maximum is gathered on the side for the NEXT tile's rescale decision.  A reference that lags one tile is as good as
+      // any other (P and the row sum share it; bf16 / fp32 keep their precision ~85 nats above it) - the per-tile chain
+      // "all loads -> maximum -> exponentials" was a third of a softmax warp's time with the MUFU pipe idle.
+      bool streamed = false;
+      if constexpr (!HS && !F16) streamed = (submax & 2) != 0 && j > 0 && kv_len - j * BKV_ >= BKV_;
+      if (streamed) {
+        if (__any_sync(0xffffffffu, (rprev - m) * LOG2E > RESCALE_LOG2)) {
+          // rare: the previous tile raised the row maximum past the threshold - refresh m and rescale O in TMEM
+          mbar_wait(&pv_done[g], (n - 1) & 1);   // every P*V issued so far (the previous tile's included) has completed
+          tcgen05_fence_after();
+          const float mn = fmaxf(m, rprev);
+          const float alpha = ex2((m - mn) * LOG2E);
+          uint32_t o[32];
+          tmem_ld_32x32b_x32(tO, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_32x32b_x32(tO, o);
+          if (MMA_ROWSUM) {
+            const uint32_t lr = tmem_ld_32x32b_x1(tO + 32);
+            tmem_ld_wait();
+            tmem_st_32x32b_x1(tO + 32, __float_as_uint(__uint_as_float(lr) * alpha));
+          }
+          tmem_st_wait();
+          lcur *= alpha;
+          m = mn;
+        }
+        tmem_ld_32x32b_x32(tS, sv[0]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 1; c < L::NCH; ++c) tmem_ld_32x32b_x32(tS + c * 32, sv[c]);
+      } else {
 #pragma unroll
       for (int c = 0; c < L::NCH; ++c) tmem_ld_32x32b_x32(tS + c * 32, sv[c]);
       tmem_ld_wait();
@@ -389,7 +424,7 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         }
       }
       float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-      if (submax && !F16 && !HS) {
+      if ((submax & 1) && !F16 && !HS) {
         // Sub-sampled reference: the running value m only has to stay within the exponent range of the true row maximum
         // (P = 2^(s - m) and the row sum l are formed against the SAME m, so any m gives the same quotient; in bf16 / fp32 a
         // score 2^100 above m still neither overflows nor loses precision), so the maximum over every fourth column pair
@@ -421,6 +456,7 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         named_bar_sync(1 + g * 4 + qd, 64);
         r = fmaxf(r, xm[(half ^ 1) * 128 + row]);
       }
+      rprev = r;
       if (j == 0) {
         m = r;
       } else if (__any_sync(0xffffffffu, (r - m) * LOG2E > RESCALE_LOG2)) {
@@ -457,13 +493,25 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       } else if (j == 0 && g > 0 && nkv > 1 && (it == 0 || restagger)) {
         mbar_wait(&stagger[g], restagger ? (it & 1) : 0);
       }
+      }   // !streamed
       const float mb = m * LOG2E;
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
       uint32_t pkk[32];
+      float rs = -INFINITY;                          // streamed tile: its sub-sampled maximum, for the next tile
 #pragma unroll
       for (int c = 0; c < L::NCH; ++c) {
         uint32_t* pk = &pkk[HS ? 0 : (c & 1) * 16];
+        if (streamed) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rs = max3(rs, __uint_as_float(sv[c][8 * i + 0]), __uint_as_float(sv[c][8 * i + 1]));
+        }
         exp_chunk<POLYP, !MMA_ROWSUM, F16, LIDM_ATTN_TRUNC != 0>(sv[c], mb, pk, s0, s1, s2, s3);
+        if (streamed && c == 0) {                    // the other chunks have landed behind these exponentials
+          tmem_ld_wait();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free[g]);
+        }
         if (HS) {
           // half split: 16 columns (32 keys) per store keeps the packed pairs out of the register budget of 96
           if (c == 0 && n > 0) {
@@ -483,6 +531,7 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         if (!PINGPONG && c == (HS ? 0 : L::NCH / NG - 1 + (L::NCH / NG == 0)) && j == 0 && (it == 0 || restagger) && g + 1 < NG && lane == 0)
           mbar_arrive(&stagger[g + 1]);
       }
+      if (streamed) rprev = rs;
       if (PINGPONG && lane == 0) mbar_arrive(&xu_go[(g == 0 ? 4 : 0) + qd]);   // hand the MUFU unit to the partner warp
       if (!MMA_ROWSUM) lcur += (s0 + s1) + (s2 + s3);
       tmem_st_wait();
@@ -531,7 +580,10 @@ void launch_f(const bf16* q, int q_ld, int q_col, const bf16* kv, int kv_ld, int
     LIDM_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const int grid = n_items < num_sms ? n_items : num_sms;     // one persistent CTA per SM
-  static const int submax = getenv("LIDM_ATTN_SUBMAX") ? atoi(getenv("LIDM_ATTN_SUBMAX")) : 1;   // A/B switch (T = 2048: 698 -> 640 us)
+  // bit 0: sub-sampled maximum (T = 2048: 698 -> 640 us); bit 1: streamed tiles against the lagging reference (same box:
+  // 689 -> 628 us; requesting the next tile's first chunk during the last chunk's exponentials on top of it: 656-668 us,
+  // not kept).  A/B switch; 0 = exact maximum of every tile before its exponentials.
+  static const int submax = getenv("LIDM_ATTN_SUBMAX") ? atoi(getenv("LIDM_ATTN_SUBMAX")) : 3;
   launch_pdl(attention_d32_v5_kernel<NG, BKV_, POLYP, PP, F16, HS>, dim3(grid), dim3(L::THREADS), L::SMEM_TOTAL, s, tmQ, tmKV, out.p,
              out.ld, T, q_col, k_col, v_col, kv_rows, n_qblk, heads, n_items, submax);
   LIDM_COUNT_LAUNCH(1);
@@ -677,7 +729,7 @@ void launch_attention_d32_packed(const bf16* qkv, const View& out, int B, int T,
   // 1820 clk per tile pair in isolation; T = 2048 784 -> 738 us, T = 512 121 -> 119 us in the U-Net at B = 64);
   // 3 of 8 is already slower (also with the row sums on the tensor pipe: T = 2048 703 us at 2 of 8, 711 us at 3 of 8).
   // LIDM_ATTN_POLY=0 turns it off (A/B runs).
-  static const int poly = getenv("LIDM_ATTN_POLY") ? atoi(getenv("LIDM_ATTN_POLY")) : 2;
+  static const int poly = getenv("LIDM_ATTN_POLY") ? atoi(getenv("LIDM_ATTN_POLY")) : 3;
 #define LIDM_ATTN_ARGS qkv, 3 * C, 0, qkv, 3 * C, C, 2 * C, T, out, B, T, heads, s
   // Free-running (staggered) softmax groups at every length: with the packed softmax and parked waits the strict
   // ping-pong no longer pays even for short items (T = 512, same box: 125.0 us free-running, 128.5 us ping-pong); it
@@ -687,6 +739,9 @@ void launch_attention_d32_packed(const bf16* qkv, const View& out, int B, int T,
   static const int hs = getenv("LIDM_ATTN_HS") ? atoi(getenv("LIDM_ATTN_HS")) : 0;
   if (T % 256 == 0) {
     if (hs) v5::launch<2, 128, 2, false, true>(LIDM_ATTN_ARGS);
+    else if (poly == 3) v5::launch<2, 128, 3, false>(LIDM_ATTN_ARGS);
+    else if (poly == 4) v5::launch<2, 128, 4, false>(LIDM_ATTN_ARGS);
+    else if (poly == 1) v5::launch<2, 128, 1, false>(LIDM_ATTN_ARGS);
     else if (poly) v5::launch<2, 128, 2, false>(LIDM_ATTN_ARGS);
     else v5::launch<2, 128, 0, false>(LIDM_ATTN_ARGS);
   } else {
