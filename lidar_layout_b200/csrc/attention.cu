@@ -11,6 +11,8 @@
 //   xs: CUDA-core kernel for cross-attention against a handful of context tokens.
 #include <cstdlib>
 
+#include <type_traits>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -72,14 +74,16 @@ __device__ __forceinline__ void ex2_poly2(float& y0, float& y1, float x0, float 
 #ifndef LIDM_ATTN_TRUNC
 #define LIDM_ATTN_TRUNC 1
 #endif
-template <int POLYP, bool SUM, bool F16, bool TRUNC = false>
-__device__ __forceinline__ void exp_chunk(const uint32_t (&sv)[32], float mb, uint32_t* pk, float& s0, float& s1,
+// sc: what turns a score into a base-2 exponent (log2 e, or 1 when the q / k weights carry it); FAST: sc == 1 and the row's
+// reference is 0, so the score IS the exponent - no scale-and-subtract at all.
+template <int POLYP, bool SUM, bool F16, bool TRUNC = false, bool FAST = false>
+__device__ __forceinline__ void exp_chunk(const uint32_t (&sv)[32], float sc, float mb, uint32_t* pk, float& s0, float& s1,
                                           float& s2, float& s3) {
-  constexpr float LOG2E = 1.4426950408889634f;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     float x0, x1, p0, p1;
-    fma2(x0, x1, __uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1]), LOG2E, LOG2E, -mb, -mb);
+    if (FAST) { x0 = __uint_as_float(sv[2 * i]); x1 = __uint_as_float(sv[2 * i + 1]); }
+    else fma2(x0, x1, __uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1]), sc, sc, -mb, -mb);
     if (((i & 7) * POLYP) % 8 < POLYP) {
       ex2_poly2(p0, p1, x0, x1);
     } else {
@@ -153,7 +157,7 @@ template <int NG, int BKV_, int POLYP, bool PP, bool F16, bool HS>
 __global__ void __launch_bounds__((Cfg<NG, BKV_, HS>::THREADS), 1)
 attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                         bf16* __restrict__ out, int out_ld, int T, int q_col, int k_col, int v_col, int kv_len,
-                        int n_qblk, int heads, int n_items, int submax) {
+                        int n_qblk, int heads, int n_items, int submax, float sscale) {
   using L = Cfg<NG, BKV_, HS>;
   static_assert(!HS || (!PP && BKV_ == 128), "half split: free-running groups, 128-key tiles");
   // Row sums on the tensor pipe: the P*V product runs with N = 48, the B operand's second 32-column atom being a constant
@@ -334,7 +338,14 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const uint32_t tO = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + L::O_COL + g * L::O_STRIDE;
     const uint32_t tP = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + L::P_COL + g * (BKV_ / 2) + col0 / 2;
     float* xmax = reinterpret_cast<float*>(smem + L::OFF_XMAX);
-    constexpr float LOG2E = 1.4426950408889634f;
+    // sscale turns scores into base-2 exponents: log2 e, or 1 when the packed q / k weights already carry it (the engine's
+    // own weights do).  Then, in the streamed bf16 mode, a row whose first-tile maximum lies within 2^+-64 takes reference 0
+    // and its scores go to the exponential as they are (fast tiles: one FFMA2 per pair less in the dispatch-bound phase);
+    // the reference is only moved when a later tile's maximum leaves that range (threshold 64: bf16 P and the fp32 row sums
+    // and accumulators hold 2^+-126).
+    const float LOG2E = sscale;
+    const bool fast_ok = !HS && !F16 && (submax & 2) != 0 && (submax & 8) == 0 && sscale == 1.f;
+    const float rescale_th = (!HS && !F16 && (submax & 2) != 0) ? 64.f : RESCALE_LOG2;
     int n = 0;                                     // cumulative tile index over this CTA's items (barrier phases)
     const bool restagger = nkv >= 8;
     constexpr bool PINGPONG = PP;
@@ -382,7 +393,7 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       bool streamed = false;
       if constexpr (!HS && !F16) streamed = (submax & 2) != 0 && j > 0 && kv_len - j * BKV_ >= BKV_;
       if (streamed) {
-        if (__any_sync(0xffffffffu, (rprev - m) * LOG2E > RESCALE_LOG2)) {
+        if (__any_sync(0xffffffffu, (rprev - m) * LOG2E > rescale_th)) {
           // rare: the previous tile raised the row maximum past the threshold - refresh m and rescale O in TMEM
           mbar_wait(&pv_done[g], (n - 1) & 1);   // every P*V issued so far (the previous tile's included) has completed
           tcgen05_fence_after();
@@ -458,8 +469,8 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
       rprev = r;
       if (j == 0) {
-        m = r;
-      } else if (__any_sync(0xffffffffu, (r - m) * LOG2E > RESCALE_LOG2)) {
+        m = (fast_ok && fabsf(r) <= 64.f) ? 0.f : r;
+      } else if (__any_sync(0xffffffffu, (r - m) * LOG2E > rescale_th)) {
         // rare: refresh the running max of every row of this warp and rescale O in TMEM
         mbar_wait(&pv_done[g], (n - 1) & 1);   // every P*V issued so far has completed
         tcgen05_fence_after();
@@ -498,6 +509,9 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
       uint32_t pkk[32];
       float rs = -INFINITY;                          // streamed tile: its sub-sampled maximum, for the next tile
+      const bool fast = fast_ok && __all_sync(0xffffffffu, m == 0.f);
+      auto chunks = [&](auto fast_tag) {
+        constexpr bool FAST = decltype(fast_tag)::value;
 #pragma unroll
       for (int c = 0; c < L::NCH; ++c) {
         uint32_t* pk = &pkk[HS ? 0 : (c & 1) * 16];
@@ -505,7 +519,7 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 #pragma unroll
           for (int i = 0; i < 4; ++i) rs = max3(rs, __uint_as_float(sv[c][8 * i + 0]), __uint_as_float(sv[c][8 * i + 1]));
         }
-        exp_chunk<POLYP, !MMA_ROWSUM, F16, LIDM_ATTN_TRUNC != 0>(sv[c], mb, pk, s0, s1, s2, s3);
+        exp_chunk<POLYP, !MMA_ROWSUM, F16, LIDM_ATTN_TRUNC != 0, FAST>(sv[c], LOG2E, mb, pk, s0, s1, s2, s3);
         if (streamed && c == 0) {                    // the other chunks have landed behind these exponentials
           tmem_ld_wait();
           tcgen05_fence_before();
@@ -531,6 +545,9 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         if (!PINGPONG && c == (HS ? 0 : L::NCH / NG - 1 + (L::NCH / NG == 0)) && j == 0 && (it == 0 || restagger) && g + 1 < NG && lane == 0)
           mbar_arrive(&stagger[g + 1]);
       }
+      };
+      if (fast) chunks(std::true_type{});
+      else chunks(std::false_type{});
       if (streamed) rprev = rs;
       if (PINGPONG && lane == 0) mbar_arrive(&xu_go[(g == 0 ? 4 : 0) + qd]);   // hand the MUFU unit to the partner warp
       if (!MMA_ROWSUM) lcur += (s0 + s1) + (s2 + s3);
@@ -560,7 +577,7 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
 // q: (B, T, q_ld) rows with the heads at columns q_col + head*32; k / v: (B, kv_rows, kv_ld) rows at columns k_col / v_col.
 template <int NG, int BKV_, int POLYP, bool PP, bool F16, bool HS = false>
 void launch_f(const bf16* q, int q_ld, int q_col, const bf16* kv, int kv_ld, int k_col, int v_col, int kv_rows, const View& out,
-            int B, int T, int heads, cudaStream_t s) {
+            int B, int T, int heads, cudaStream_t s, float sscale) {
   using L = Cfg<NG, BKV_, HS>;
   static bool configured = false;
   if (!configured) {
@@ -585,15 +602,15 @@ void launch_f(const bf16* q, int q_ld, int q_col, const bf16* kv, int kv_ld, int
   // not kept).  A/B switch; 0 = exact maximum of every tile before its exponentials.
   static const int submax = getenv("LIDM_ATTN_SUBMAX") ? atoi(getenv("LIDM_ATTN_SUBMAX")) : 3;
   launch_pdl(attention_d32_v5_kernel<NG, BKV_, POLYP, PP, F16, HS>, dim3(grid), dim3(L::THREADS), L::SMEM_TOTAL, s, tmQ, tmKV, out.p,
-             out.ld, T, q_col, k_col, v_col, kv_rows, n_qblk, heads, n_items, submax);
+             out.ld, T, q_col, k_col, v_col, kv_rows, n_qblk, heads, n_items, submax, sscale);
   LIDM_COUNT_LAUNCH(1);
 }
 
 template <int NG, int BKV_, int POLYP, bool PP = (NG == 2), bool HS = false>
 void launch(const bf16* q, int q_ld, int q_col, const bf16* kv, int kv_ld, int k_col, int v_col, int kv_rows, const View& out,
-            int B, int T, int heads, cudaStream_t s) {
-  if (out.f16) launch_f<NG, BKV_, POLYP, PP, true, HS>(q, q_ld, q_col, kv, kv_ld, k_col, v_col, kv_rows, out, B, T, heads, s);
-  else launch_f<NG, BKV_, POLYP, PP, false, HS>(q, q_ld, q_col, kv, kv_ld, k_col, v_col, kv_rows, out, B, T, heads, s);
+            int B, int T, int heads, cudaStream_t s, float sscale) {
+  if (out.f16) launch_f<NG, BKV_, POLYP, PP, true, HS>(q, q_ld, q_col, kv, kv_ld, k_col, v_col, kv_rows, out, B, T, heads, s, sscale);
+  else launch_f<NG, BKV_, POLYP, PP, false, HS>(q, q_ld, q_col, kv, kv_ld, k_col, v_col, kv_rows, out, B, T, heads, s, sscale);
 }
 
 }  // namespace v5
@@ -611,7 +628,7 @@ constexpr int HP = 33;   // padded floats per (token, head) row
 
 __global__ void __launch_bounds__(256)
 xattn_small_kernel(const bf16* __restrict__ q, int q_ld, const bf16* __restrict__ kv, int kv_ld, int k_col, int v_col, int L,
-                   bf16* __restrict__ out, int out_ld, int T, int heads) {
+                   bf16* __restrict__ out, int out_ld, int T, int heads, float sscale) {
   extern __shared__ float skv[];                     // K: [L][heads][HP], then V: same
   const int b = blockIdx.y;
   const int C = heads * D;
@@ -633,7 +650,7 @@ xattn_small_kernel(const bf16* __restrict__ q, int q_ld, const bf16* __restrict_
     }
   }
   __syncthreads();
-  constexpr float LOG2E = 1.4426950408889634f;
+  const float LOG2E = sscale;                        // log2 e, or 1 when the q weights carry it
   const int pairs = (T / 2) * heads;                 // work item = (pixel pair, head); heads fastest -> coalesced rows
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < pairs; idx += gridDim.x * blockDim.x) {
     const int hd = idx % heads, t0 = (idx / heads) * 2;
@@ -717,8 +734,9 @@ xattn_small_kernel(const bf16* __restrict__ q, int q_ld, const bf16* __restrict_
 
 }  // namespace
 
-void launch_attention_d32_packed(const bf16* qkv, const View& out, int B, int T, int heads, cudaStream_t s) {
+void launch_attention_d32_packed(const bf16* qkv, const View& out, int B, int T, int heads, cudaStream_t s, bool log2_scores) {
   const int C = heads * D;
+  const float sscale = log2_scores ? 1.f : 1.4426950408889634f;   // q . k is already a base-2 exponent when the weights carry log2 e
   LIDM_REQUIRE(T % 128 == 0, "attention: T must be a multiple of 128");
   LIDM_REQUIRE(out.hl == 0 && out.hr == 0 && out.H * out.W == T && out.B == B && out.C == C, "attention out view");
   LIDM_REQUIRE(out.ld % 8 == 0, "attention out ld");
@@ -730,7 +748,7 @@ void launch_attention_d32_packed(const bf16* qkv, const View& out, int B, int T,
   // 3 of 8 is already slower (also with the row sums on the tensor pipe: T = 2048 703 us at 2 of 8, 711 us at 3 of 8).
   // LIDM_ATTN_POLY=0 turns it off (A/B runs).
   static const int poly = getenv("LIDM_ATTN_POLY") ? atoi(getenv("LIDM_ATTN_POLY")) : 3;
-#define LIDM_ATTN_ARGS qkv, 3 * C, 0, qkv, 3 * C, C, 2 * C, T, out, B, T, heads, s
+#define LIDM_ATTN_ARGS qkv, 3 * C, 0, qkv, 3 * C, C, 2 * C, T, out, B, T, heads, s, sscale
   // Free-running (staggered) softmax groups at every length: with the packed softmax and parked waits the strict
   // ping-pong no longer pays even for short items (T = 512, same box: 125.0 us free-running, 128.5 us ping-pong); it
   // stays available as the PP template flag and serves the single-tile cross-attention items.  Odd multiples of 128
@@ -754,8 +772,9 @@ void launch_attention_d32_packed(const bf16* qkv, const View& out, int B, int T,
 // CrossAttention.forward core (reference lidm/modules/attention.py:170-193) for head dim 32: q (B,T,q_ld) against a
 // short context k/v (B, L, kv_ld), L not necessarily a multiple of 128 (TMA zero-fills, the kernel masks).
 void launch_cross_attention_d32(const bf16* q, int q_ld, const bf16* kv, int kv_ld, int k_col, int v_col, int L,
-                                const View& out, int B, int T, int heads, cudaStream_t s) {
+                                const View& out, int B, int T, int heads, cudaStream_t s, bool log2_scores) {
   LIDM_REQUIRE(T % 128 == 0 && L >= 1, "cross attention: T must be a multiple of 128");
+  const float sscale = log2_scores ? 1.f : 1.4426950408889634f;
   static const bool no_small = getenv("LIDM_XATTN_TC") != nullptr;   // A/B switch: always take the tensor-core kernel
   if (L <= xs::LMAX && !no_small && !out.f16 && q_ld % 8 == 0 && out.ld % 8 == 0 && kv_ld % 8 == 0 && k_col % 8 == 0 && v_col % 8 == 0 &&
       (size_t)2 * L * heads * xs::HP * sizeof(float) <= 48 * 1024) {
@@ -765,13 +784,13 @@ void launch_cross_attention_d32(const bf16* q, int q_ld, const bf16* kv, int kv_
     const int cap = (148 * 8 + B - 1) / B;           // ~4 waves at 2 CTAs per SM: measured faster than one long-running wave
     if (gx > cap) gx = cap;
     const size_t smem = (size_t)2 * L * heads * xs::HP * sizeof(float);
-    xs::xattn_small_kernel<<<dim3(gx, B), 256, smem, s>>>(q, q_ld, kv, kv_ld, k_col, v_col, L, out.p, out.ld, T, heads);
+    xs::xattn_small_kernel<<<dim3(gx, B), 256, smem, s>>>(q, q_ld, kv, kv_ld, k_col, v_col, L, out.p, out.ld, T, heads, sscale);
     LIDM_CUDA_CHECK(cudaGetLastError());
     LIDM_COUNT_LAUNCH(1);
     return;
   }
-  if (T % 256 == 0) v5::launch<2, 128, 0>(q, q_ld, 0, kv, kv_ld, k_col, v_col, L, out, B, T, heads, s);
-  else v5::launch<1, 128, 0>(q, q_ld, 0, kv, kv_ld, k_col, v_col, L, out, B, T, heads, s);
+  if (T % 256 == 0) v5::launch<2, 128, 0>(q, q_ld, 0, kv, kv_ld, k_col, v_col, L, out, B, T, heads, s, sscale);
+  else v5::launch<1, 128, 0>(q, q_ld, 0, kv, kv_ld, k_col, v_col, L, out, B, T, heads, s, sscale);
 }
 
 }  // namespace lidm

@@ -185,12 +185,14 @@ void launch_groupnorm_from_gstats(const View& x, const View& y, const float* gam
 
 // ---- attention (attention.cu) ----------------------------------------------------------------------------
 // qkv: (B, T, 3C) bf16 = [q | k | v] (plain qkv GEMM output); V consumed as an MN-major tcgen05 operand
-void launch_attention_d32_packed(const bf16* qkv, const View& out, int B, int T, int heads, cudaStream_t s);
+// log2_scores: the q / k weights carry log2 e on top of the softmax scale (q . k is a base-2 exponent): the kernel then runs
+// its exponentials on the raw scores wherever the row maximum allows reference 0
+void launch_attention_d32_packed(const bf16* qkv, const View& out, int B, int T, int heads, cudaStream_t s, bool log2_scores = false);
 
 // q (B,T,q_ld) bf16 (heads at columns head*32, softmax scale already folded in); k / v rows of the context
 // (B, L, kv_ld) at columns k_col / v_col; out (B,T,C) view.  Any L >= 1 (ragged last tile is masked).
 void launch_cross_attention_d32(const bf16* q, int q_ld, const bf16* kv, int kv_ld, int k_col, int v_col, int L,
-                                const View& out, int B, int T, int heads, cudaStream_t s);
+                                const View& out, int B, int T, int heads, cudaStream_t s, bool log2_scores = false);
 
 // ---- layout-conditioned denoiser (layout.cu) --------------------------------------------------------------------
 // ObjectAwareCrossAttention core (object_cross_unet.py:447-565): qkv (B,T,3C) = [q | k | v] with the 128^-1/4 scale folded

@@ -157,6 +157,11 @@ ConvTaps taps_rect(int kh, int kw, int pl, int pt) {
 }
 ConvTaps taps_1x1() { ConvTaps t; t.n = 1; return t; }
 
+// log2 e rides on the softmax scale that is folded into the packed q / k weights (its square root on each of q and k, all of
+// it on q where k comes from the shared context matrix): q . k is then the base-2 exponent the attention kernels feed to ex2
+const float kLog2e = 1.4426950408889634f;
+const float kSqrtLog2e = 1.2011224087864498f;
+
 int round_n_alloc(int cout) {
   if (cout >= 128) return (cout + 127) / 128 * 128;
   if (cout > 16) return (cout + 63) / 64 * 64;
@@ -663,7 +668,7 @@ struct Builder {
     release(bg);
     View ao = act(B, H, W, C, 0, 0, &ba);
     const int heads = a.heads;
-    op([=](cudaStream_t s) { launch_attention_d32_packed(qkv.p, ao, B, T, heads, s); }, PROF_ATTN,
+    op([=](cudaStream_t s) { launch_attention_d32_packed(qkv.p, ao, B, T, heads, s, true); }, PROF_ATTN,
        4.0 * B * heads * (double)T * T * 32, 0, "attn T" + std::to_string(T) + " heads" + std::to_string(heads));
     release(bqk);
     {
@@ -904,7 +909,7 @@ struct Builder {
       gemm(g, taps_1x1(), blk.attn_qkv, ep);
       release(bg);
       ao = act(B, H, W, C, 0, 0, &ba);
-      op([=](cudaStream_t s) { launch_attention_d32_packed(qkv.p, ao, B, T, heads, s); }, PROF_ATTN,
+      op([=](cudaStream_t s) { launch_attention_d32_packed(qkv.p, ao, B, T, heads, s, true); }, PROF_ATTN,
          4.0 * B * heads * (double)T * T * 32, 0, "attn T" + std::to_string(T) + " heads" + std::to_string(heads));
       release(bqk);
     } else {
@@ -1068,7 +1073,7 @@ struct Builder {
     }
     release(bg);
     View ao = act(B, H, W, C, 0, 0, &ba);
-    op([=](cudaStream_t s) { launch_attention_d32_packed(qkv.p, ao, B, T, heads, s); }, PROF_ATTN,
+    op([=](cudaStream_t s) { launch_attention_d32_packed(qkv.p, ao, B, T, heads, s, true); }, PROF_ATTN,
        4.0 * B * heads * (double)T * T * 32, 0, "attn T" + std::to_string(T) + " heads" + std::to_string(heads));
     release(bqk);
     {
@@ -1164,7 +1169,7 @@ struct Builder {
       lin(n1, k.qkv1, qkv);
       release(bn);
       View ao = act(B, H, W, C, 0, 0, &bao);
-      op([=](cudaStream_t s) { launch_attention_d32_packed(qkv.p, ao, B, T, heads, s); }, PROF_ATTN,
+      op([=](cudaStream_t s) { launch_attention_d32_packed(qkv.p, ao, B, T, heads, s, true); }, PROF_ATTN,
          4.0 * B * heads * (double)T * T * 32, 0, "attn T" + std::to_string(T) + " heads" + std::to_string(heads));
       release(bqkv);
       View h1 = act(B, H, W, C, 0, 0, &bh1);
@@ -1181,7 +1186,7 @@ struct Builder {
       View ao2 = act(B, H, W, C, 0, 0, &bao2);
       const int kv_col = k.kv_col;
       op([=](cudaStream_t s) {
-        launch_cross_attention_d32(q2.p, q2.ld, ctx_kv, ctx_n, kv_col, kv_col + C, ctx_len, ao2, B, T, heads, s);
+        launch_cross_attention_d32(q2.p, q2.ld, ctx_kv, ctx_n, kv_col, kv_col + C, ctx_len, ao2, B, T, heads, s, true);
       }, PROF_ATTN, 4.0 * B * heads * (double)T * ctx_len * 32, 0,
          "xattn T" + std::to_string(T) + " L" + std::to_string(ctx_len) + " heads" + std::to_string(heads));
       release(bq2);
@@ -2143,7 +2148,7 @@ AttnW pack_unet_attn(Packer& pk, const std::string& p, int ch, int heads) {
       for (int c = 0; c < d; ++c) perm[part * ch + hd * d + c] = hd * 3 * d + part * d + c;
   int* perm_dev = dev_alloc<int>(h, perm.size());
   LIDM_CUDA_CHECK(cudaMemcpyAsync(perm_dev, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice, pk.s));
-  const float scale = 1.0f / std::sqrt(std::sqrt((float)d));
+  const float scale = kSqrtLog2e / std::sqrt(std::sqrt((float)d));
   ConvW c;
   c.cout = 3 * ch; c.cin = ch; c.kh = c.kw = 1;
   c.n_alloc = round_n_alloc(3 * ch);
@@ -2483,7 +2488,7 @@ void finalize_unet_efficient(lidm_handle* h, Packer& pk, std::vector<std::pair<s
       const DevTensor& w = find_raw(h, ap + ".attn.in_proj_weight", pk.ema);
       const DevTensor& bsrc = find_raw(h, ap + ".attn.in_proj_bias", pk.ema);
       if (w.numel != (int64_t)3 * cout * cout || bsrc.numel != 3 * cout) throw Error(LIDM_ERR_STATE, "in_proj weight size: " + ap);
-      const float sc = d == 32 ? 1.0f / std::sqrt(std::sqrt((float)d)) : 1.0f / std::sqrt((float)d);
+      const float sc = d == 32 ? kSqrtLog2e / std::sqrt(std::sqrt((float)d)) : 1.0f / std::sqrt((float)d);
       const int nsc = d == 32 ? 2 * cout : cout;
       ConvW c;
       c.cout = 3 * cout; c.cin = cout; c.kh = c.kw = 1; c.f16 = pk.f16;
@@ -2568,7 +2573,7 @@ void finalize(lidm_handle* h, bool use_ema) {
     STW& t = L.st;
     t.ch = c; t.heads = c / cfg.num_head_channels;
     const float d = (float)cfg.num_head_channels;
-    const float s4 = 1.0f / std::sqrt(std::sqrt(d)), s2 = 1.0f / std::sqrt(d);
+    const float s4 = kSqrtLog2e / std::sqrt(std::sqrt(d)), s2 = kLog2e / std::sqrt(d);
     t.n = pk.norm(p + ".norm", c);
     t.proj_in = pk.conv(p + ".proj_in", c, c, 1, 1);
     t.proj_out = pk.conv(p + ".proj_out", c, c, 1, 1);
@@ -3615,12 +3620,12 @@ int lidm_op_qkv_attention_legacy(const float* qkv, int32_t B, int32_t heads, int
     const int C = heads * 32;
     TmpBufs tmp;
     bf16* qk = tmp.get<bf16>((size_t)B * T * 3 * C);
-    const float scale = 1.0f / std::sqrt(std::sqrt(32.0f));
+    const float scale = kSqrtLog2e / std::sqrt(std::sqrt(32.0f));
     qkv_legacy_to_internal_kernel<<<148 * 8, 256, 0, s>>>(qkv, B, heads, T, scale, qk);
     LIDM_CUDA_CHECK(cudaGetLastError());
     View o; o.B = B; o.H = T / 128; o.W = 128; o.C = C; o.ld = C;
     o.p = tmp.get<bf16>((size_t)B * T * C);
-    launch_attention_d32_packed(qk, o, B, T, heads, s);
+    launch_attention_d32_packed(qk, o, B, T, heads, s, true);
     launch_nhwc_bf16_to_f32_nchw(o, out, s);
     LIDM_CUDA_CHECK(cudaStreamSynchronize(s));
   });
