@@ -339,13 +339,18 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const uint32_t tP = tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + L::P_COL + g * (BKV_ / 2) + col0 / 2;
     float* xmax = reinterpret_cast<float*>(smem + L::OFF_XMAX);
     // sscale turns scores into base-2 exponents: log2 e, or 1 when the packed q / k weights already carry it (the engine's
-    // own weights do).  Then, in the streamed bf16 mode, a row whose first-tile maximum lies within 2^+-64 takes reference 0
-    // and its scores go to the exponential as they are (fast tiles: one FFMA2 per pair less in the dispatch-bound phase);
-    // the reference is only moved when a later tile's maximum leaves that range (threshold 64: bf16 P and the fp32 row sums
-    // and accumulators hold 2^+-126).
+    // own weights do).  Then, in the streamed bf16 mode, a row whose first-tile maximum lies within 2^+-24 takes reference 0
+    // and its scores go to the exponential as they are (fast tiles: one FFMA2 per pair less in the dispatch-bound phase).
+    // Streamed tiles move the reference one tile late, when a tile's maximum has left the one the reference was set from by
+    // more than 2^24.  A reference that is not 0 sits 2^40 ABOVE that maximum (P = 2^(s - m) <= 2^-40 while nothing has grown):
+    // bf16 P and the fp32 row sums / accumulators reach 2^127, so a row maximum may grow by 2^130 (90 nats) from one 128-key
+    // tile to the next before anything overflows, while scores more than 2^86 (60 nats) below the maximum flush to zero -
+    // they carry less than 2^-86 of the row sum (tests/test_gpu_ops.py::test_attention_reference_regimes walks the regimes).
     const float LOG2E = sscale;
+    constexpr float REF_RANGE = 24.f;
     const bool fast_ok = !HS && !F16 && (submax & 2) != 0 && (submax & 8) == 0 && sscale == 1.f;
-    const float rescale_th = (!HS && !F16 && (submax & 2) != 0) ? 64.f : RESCALE_LOG2;
+    const float rescale_th = (!HS && !F16 && (submax & 2) != 0) ? REF_RANGE : RESCALE_LOG2;
+    const float ref_bias = (!HS && !F16 && (submax & 2) != 0) ? 40.f / sscale : 0.f;   // in score units
     int n = 0;                                     // cumulative tile index over this CTA's items (barrier phases)
     const bool restagger = nkv >= 8;
     constexpr bool PINGPONG = PP;
@@ -378,7 +383,7 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     for (int it = 0; it < n_my; ++it) {
     int q0, head, b;
     item_coords(it, q0, head, b);
-    float m = 0.f, rprev = 0.f;
+    float m = 0.f, mx = 0.f, rprev = 0.f;         // reference subtracted from the scores; the maximum it was set from; last tile's maximum
     float lcur = 0.f;                               // running row sum of this item when it is not taken from the MMA
     for (int j = 0; j < nkv; ++j, ++n) {
       mbar_wait(&s_ready[g], n & 1);
@@ -393,11 +398,12 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       bool streamed = false;
       if constexpr (!HS && !F16) streamed = (submax & 2) != 0 && j > 0 && kv_len - j * BKV_ >= BKV_;
       if (streamed) {
-        if (__any_sync(0xffffffffu, (rprev - m) * LOG2E > rescale_th)) {
+        if (__any_sync(0xffffffffu, (rprev - mx) * LOG2E > rescale_th)) {
           // rare: the previous tile raised the row maximum past the threshold - refresh m and rescale O in TMEM
           mbar_wait(&pv_done[g], (n - 1) & 1);   // every P*V issued so far (the previous tile's included) has completed
           tcgen05_fence_after();
-          const float mn = fmaxf(m, rprev);
+          mx = fmaxf(mx, rprev);
+          const float mn = mx + ref_bias;
           const float alpha = ex2((m - mn) * LOG2E);
           uint32_t o[32];
           tmem_ld_32x32b_x32(tO, o);
@@ -469,12 +475,15 @@ attention_d32_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
       }
       rprev = r;
       if (j == 0) {
-        m = (fast_ok && fabsf(r) <= 64.f) ? 0.f : r;
-      } else if (__any_sync(0xffffffffu, (r - m) * LOG2E > rescale_th)) {
+        const bool zero_ref = fast_ok && fabsf(r) <= REF_RANGE;      // (fast_ok: scores are base-2 exponents)
+        mx = zero_ref ? 0.f : r;
+        m = zero_ref ? 0.f : r + ref_bias;
+      } else if (__any_sync(0xffffffffu, (r - mx) * LOG2E > rescale_th)) {
         // rare: refresh the running max of every row of this warp and rescale O in TMEM
         mbar_wait(&pv_done[g], (n - 1) & 1);   // every P*V issued so far has completed
         tcgen05_fence_after();
-        const float mn = fmaxf(m, r);
+        mx = fmaxf(mx, r);
+        const float mn = mx + ref_bias;
         const float alpha = ex2((m - mn) * LOG2E);
         if (!HS || half == 0) {       // both halves take the same decision (same rows, same maxima); one rescales O
           uint32_t o[32];

@@ -201,3 +201,22 @@ def test_halo_tile_conv_matches_streamed_kernel(ops, case):
     # the statistics are those of the stored values: summed over the tiles they give the per-granule sums
     s = y1.reshape(B, 8, 8, H * W).sum(dim=(2, 3))
     assert torch.allclose(g1[..., 0].sum(dim=1), s, rtol=1e-3, atol=1e-1)
+
+
+@pytest.mark.parametrize("sigma,tol", [(1.0, 1e-2), (3.0, 1e-2), (5.0, 5e-2)])
+def test_attention_reference_regimes(ops, sigma, tol):
+    """The bf16 softmax keeps reference 0 for rows whose first-tile maximum lies within 2^+-24 (raw scores go to ex2), otherwise
+    a reference 2^40 above the tile maximum, and moves it, one tile late, when a later tile's maximum has left the range
+    (attention.cu: streamed tiles, fast tiles).  sigma = 1: every row stays on reference 0; 3: logits of +-40 nats, rows start on
+    either side and cross over; 5: +-100 nats, near one-hot rows whose maxima jump by tens of nats between tiles (there the bf16
+    rounding of q and k alone moves a logit by +-0.3 nats, hence the wider bound).  All against the fp32 reference, all finite."""
+    B, heads, T, d = 1, 4, 1024, 32
+    g = torch.Generator().manual_seed(int(sigma * 10))
+    qkv = torch.randn(B, heads * 3 * d, T, generator=g)
+    v = qkv.view(B, heads, 3, d, T)
+    v[:, :, 0] *= sigma
+    v[:, :, 1] *= sigma
+    y = ops.qkv_attention_legacy(qkv.cuda(), heads)
+    ref = R.qkv_attention_legacy(qkv, heads)
+    assert bool(torch.isfinite(y).all())
+    assert rel(y, ref) < tol
