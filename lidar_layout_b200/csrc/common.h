@@ -74,6 +74,7 @@ struct View {
 // Kernel launch with the programmatic-dependent-launch attribute (the kernel must call pdl_wait() before touching anything
 // an earlier kernel wrote).  LIDM_NO_PDL turns the attribute off (A/B runs): the same kernels then serialise normally.
 bool pdl_enabled();
+void pdl_set_batch(int batch);   // the engine tells the launchers which batch size the plan it is about to run has
 template <class... KArgs, class... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
   cudaLaunchConfig_t cfg = {};

@@ -2011,6 +2011,7 @@ Plan* get_plan(lidm_handle* h, std::map<int64_t, std::unique_ptr<Plan>>& cache, 
 }
 
 void run_plan(Plan* P, cudaStream_t s) {
+  pdl_set_batch(P->B);
   if (!g_prof.on) {
     for (auto& o : P->ops) o.fn(s);
     return;

@@ -1,12 +1,21 @@
 // TMA descriptor (CUtensorMap) construction.  cuTensorMapEncodeTiled is fetched through
 // cudaGetDriverEntryPoint so the library has no link-time dependency on libcuda.
+#include <atomic>
+
 #include "common.h"
 
 namespace lidm {
 
+// Programmatic dependent launch: on for small batches (the per-kernel launch latency is what bounds them; B <= 16 measured
+// neutral to +1 %), off for large ones - at B = 64 the dependents' early CTAs compete with the last wave of the multi-wave
+// kernels: the power-capped bench loop runs 98.7-99.1 samples/s with it and 100.0-100.1 without, same box
+// (profiles/r02j_sustained_ab_pdl.txt).  LIDM_NO_PDL: never; LIDM_PDL_ALWAYS: at every batch size.
+static std::atomic<int> g_pdl_large_batch{0};
+void pdl_set_batch(int batch) { g_pdl_large_batch.store(batch > 16 ? 1 : 0, std::memory_order_relaxed); }
 bool pdl_enabled() {
   static const bool on = getenv("LIDM_NO_PDL") == nullptr;
-  return on;
+  static const bool always = getenv("LIDM_PDL_ALWAYS") != nullptr;
+  return on && (always || g_pdl_large_batch.load(std::memory_order_relaxed) == 0);
 }
 
 namespace {
